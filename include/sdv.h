@@ -1,0 +1,306 @@
+/*
+ * sdv.h — C ABI of the B200-native sliding-window BA/VIO backend.
+ *
+ * This is the drop-in boundary for the one hot path this repository replaces:
+ * SaDVIO's windowed optimisation `isae::AOptimizer::localMapVIOptimization`
+ * (reference cpp/src/optimizers/AOptimizer.cpp:352-446) and
+ * `isae::AOptimizer::localMapBA` (AOptimizer.cpp:299-350), i.e. the Ceres
+ * problem build + `ceres::Solve` + the cost functors it calls back into.
+ *
+ * The reference has no FFI: the boundary upstream is the C++ abstract class
+ * `isae::AOptimizer` (cpp/include/isaeslam/optimizers/AOptimizer.h:13-91).
+ * Every entry point below names the reference code it replaces.  Signatures
+ * are plain C: pointers, sizes, POD structs — no torch / Eigen / STL types.
+ * All floating point data is FP64 (the reference is `double` throughout),
+ * indices are int32, matrices are row-major, rigid transforms are 3x4
+ * row-major [R | t] (the top three rows of Eigen::Affine3d::matrix()).
+ *
+ * Ownership: the caller owns every buffer reachable from `sdv_window`,
+ * `sdv_delta` and `sdv_stats`; the library copies host->device inside the
+ * call and keeps nothing but device scratch tied to the handle.  A handle is
+ * bound to one CUDA device, is not re-entrant, and mirrors one
+ * `isae::AOptimizer` instance (the back-end one, slamParameters.cpp:273-274).
+ *
+ * Errors: every function returns an `sdv_status` (0 = ok).  No exception
+ * crosses the ABI.  The reference returns `bool` and practically always
+ * `true`; the C++ adapter (sadvio_b200/host/b200_optimizer.hpp) maps a
+ * non-zero status to `false` and leaves the state untouched.
+ */
+#ifndef SDV_H
+#define SDV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDV_ABI_VERSION 1
+#define SDV_MAX_TRACE 64
+
+typedef enum sdv_status {
+    SDV_OK = 0,
+    SDV_ERR_INVALID_ARGUMENT = 1, /* null pointer, negative size, index out of range */
+    SDV_ERR_CUDA = 2,             /* a CUDA runtime call failed (see sdv_last_error) */
+    SDV_ERR_NO_DEVICE = 3,        /* no usable sm_100 device: there is NO CPU fallback */
+    SDV_ERR_UNSUPPORTED = 4,      /* structurally valid input this build cannot solve */
+    SDV_ERR_NUMERICAL_FAILURE = 5,/* Ceres would report FAILURE (5 invalid steps in a row) */
+    SDV_ERR_COMM = 6              /* NCCL communicator problem */
+} sdv_status;
+
+/* Which visual cost functor the window uses (one optimizer class = one kind). */
+typedef enum sdv_factor_kind {
+    /* AngularAdjustmentCERESAnalytic::AngularErrCeres_pointxd_dx
+       (AngularAdjustmentCERESAnalytic.h:45-120) — the default optimizer. */
+    SDV_FACTOR_ANGULAR = 0,
+    /* BundleAdjustmentCERESAnalytic::ReprojectionErrCeres_pointxd_dx
+       (BundleAdjustmentCERESAnalytic.h:41-98) + Camera::project (Camera.cpp:84-139). */
+    SDV_FACTOR_PIXEL = 1
+} sdv_factor_kind;
+
+/* Termination, named after ceres::TerminationType + the message it carries. */
+typedef enum sdv_termination {
+    SDV_TERM_NO_CONVERGENCE = 0,      /* max_num_iterations reached */
+    SDV_TERM_FUNCTION_TOLERANCE = 1,  /* |dcost| <= function_tolerance * cost (candidate NOT applied) */
+    SDV_TERM_GRADIENT_TOLERANCE = 2,  /* max|g| <= gradient_tolerance */
+    SDV_TERM_PARAMETER_TOLERANCE = 3, /* |step| <= parameter_tolerance * (|x| + parameter_tolerance) */
+    SDV_TERM_MIN_RADIUS = 4,          /* trust region radius fell below min_trust_region_radius */
+    SDV_TERM_FAILURE = 5              /* max_num_consecutive_invalid_steps reached */
+} sdv_termination;
+
+/*
+ * Solver options.  Defaults (sdv_default_config) are the options the reference
+ * sets at AOptimizer.cpp:376-388 plus the Ceres 2.2.0 defaults it leaves
+ * untouched (docker/Dockerfile:50 pins 2.2.0; Ceres itself is not part of
+ * /root/reference — see oracle/README.md "parity pin").
+ */
+typedef struct sdv_config {
+    int32_t abi_version;             /* SDV_ABI_VERSION */
+    int32_t device;                  /* CUDA device ordinal */
+    int32_t max_num_iterations;      /* 20     AOptimizer.cpp:380 */
+    int32_t max_consecutive_invalid_steps; /* 5   Ceres default */
+    int32_t jacobi_scaling;          /* 1      Ceres default */
+    int32_t reserved0;
+    double function_tolerance;       /* 1e-3   AOptimizer.cpp:384 */
+    double gradient_tolerance;       /* 1e-10  Ceres default */
+    double parameter_tolerance;      /* 1e-8   Ceres default */
+    double initial_trust_region_radius; /* 1e4 */
+    double max_trust_region_radius;  /* 1e16 */
+    double min_trust_region_radius;  /* 1e-32 */
+    double min_lm_diagonal;          /* 1e-6 */
+    double max_lm_diagonal;          /* 1e32 */
+    double min_relative_decrease;    /* 1e-3 */
+} sdv_config;
+
+/*
+ * Dense marginalisation prior = isae::MarginalizationFactor
+ * (marginalization.hpp:88-218): r = r0 + J * dx, J is n_full x n, dx gathers
+ * the kept frame's (pose6, v3, ba3, bg3) at column `frame_col` and each kept
+ * landmark's dp3 at `keep_col[k]` (keep_col < 0 = landmark skipped, as
+ * `_map_lmk_idx == -1` at marginalization.hpp:139).  Kept landmarks couple
+ * to each other through J, so they live in the reduced (dense) system,
+ * mirroring elimination group 2 (AngularAdjustmentCERESAnalytic.cpp:352-379).
+ */
+typedef struct sdv_dense_prior {
+    int32_t n_full;          /* rows of J  (_n_full) */
+    int32_t n;               /* cols of J  (_n) */
+    const double *J;         /* [n_full][n] row-major  (_marginalization_jacobian) */
+    const double *r0;        /* [n_full]               (_marginalization_residual) */
+    int32_t frame;           /* index into frames[] of _frame_to_keep, or -1 */
+    int32_t frame_col;       /* _map_frame_idx.at(_frame_to_keep) */
+    int32_t n_keep;          /* number of kept landmarks */
+    int32_t reserved0;
+    const int32_t *keep_lmk; /* [n_keep] landmark indices, _lmk_to_keep iteration order */
+    const int32_t *keep_col; /* [n_keep] _map_lmk_idx.at(lmk) */
+} sdv_dense_prior;
+
+/*
+ * Sparsified prior (AngularAdjustmentCERESAnalytic.cpp:387-483):
+ *  VIO case: one IMUPriordx (residuals.hpp:634-700) on the kept frame and one
+ *            PoseToLandmarkFactor (residuals.hpp:561-599) per kept landmark;
+ *  VO case : one Landmark3DPrior (residuals.hpp:506-526) and a chain of
+ *            LandmarkToLandmarkFactor (residuals.hpp:528-559).
+ */
+typedef struct sdv_sparse_prior {
+    /* --- VIO --- */
+    int32_t has_imu_prior;      /* 1 => IMUPriordx on `frame` */
+    int32_t frame;              /* index into frames[] of frame_to_keep */
+    double T_prior[12];         /* _T_prior */
+    double v_prior[3], ba_prior[3], bg_prior[3];
+    double imu_sqrt_inf[225];   /* 15x15 row-major, _map_frame_inf.at(frame_to_keep) */
+    int32_t n_p2l;              /* PoseToLandmarkFactor count */
+    int32_t reserved0;
+    const int32_t *p2l_lmk;     /* [n_p2l] */
+    const double *p2l_delta;    /* [n_p2l][3]  _map_lmk_prior.at(lmk) */
+    const double *p2l_sqrt_inf; /* [n_p2l][9]  _map_lmk_inf.at(lmk) */
+    /* --- VO --- */
+    int32_t has_lmk_prior;      /* 1 => Landmark3DPrior on lmk0 */
+    int32_t lmk0;               /* _lmk_with_prior */
+    double lmk_prior[3];        /* _prior_lmk */
+    double lmk_sqrt_inf[9];     /* _info_lmk */
+    int32_t n_l2l;              /* LandmarkToLandmarkFactor count */
+    int32_t reserved1;
+    const int32_t *l2l_a;       /* [n_l2l] lmk_k   */
+    const int32_t *l2l_b;       /* [n_l2l] lmk_kp1 */
+    const double *l2l_delta;    /* [n_l2l][3] */
+    const double *l2l_sqrt_inf; /* [n_l2l][9] */
+} sdv_sparse_prior;
+
+/*
+ * One sliding window, flattened to structure-of-arrays in the order the
+ * reference walks its pointer graph:
+ *   frames    NEWEST -> OLDEST, as LocalMap::getLastNFramesIn fills
+ *             frame_vector (amap.h:28-32); the LAST `n_fixed` are constant
+ *             (AngularAdjustmentCERESAnalytic.cpp:234-236, AOptimizer.cpp:46-51);
+ *   landmarks local_map->getLandmarks()["pointxd"] order, filtered by
+ *             isInitialized && !isOutlier (…Analytic.cpp:254);
+ *   obs       landmark-major, lmk->getFeatures() order within a landmark,
+ *             filtered as at …Analytic.cpp:272-275  => obs_lmk is non-decreasing;
+ *   imu       one entry per (framei = lastKF(framej), framej) pair that passes
+ *             the tests at AOptimizer.cpp:55-71, in frame_vector order of j.
+ */
+typedef struct sdv_window {
+    int32_t abi_version;     /* SDV_ABI_VERSION */
+    int32_t vio;             /* 1: localMapVIOptimization (pose6+v3+ba3+bg3 per frame); 0: localMapBA (pose6) */
+    int32_t factor_kind;     /* sdv_factor_kind */
+    int32_t n_frames;
+    int32_t n_fixed;         /* fixed_frame_number argument */
+    int32_t n_cams;
+    int32_t n_lmks;
+    int32_t n_obs;
+    int32_t n_imu;
+    int32_t reserved0;
+
+    /* frames */
+    const double *T_f_w;     /* [F][12] Frame::getWorld2FrameTransform() */
+    const double *v;         /* [F][3]  IMU::getVelocity()   (vio) */
+    const double *ba;        /* [F][3]  IMU::getBa()         (vio) */
+    const double *bg;        /* [F][3]  IMU::getBg()         (vio) */
+    const uint8_t *has_imu;  /* [F]     frame->getIMU() != nullptr (vio); NULL => all 1 */
+    const uint8_t *has_prior;/* [F]     Frame::hasPrior(); NULL => none */
+    const double *T_prior;   /* [F][12] Frame::getPrior()      (used where has_prior) */
+    const double *inf_prior; /* [F][6]  Frame::getInfPrior(), used AS sqrt-information
+                                        (…Analytic.cpp:241 passes it .asDiagonal() to PosePriordx) */
+
+    /* cameras: one entry per distinct (extrinsics, intrinsics) sensor model */
+    const double *T_s_f;     /* [C][12] ASensor::getFrame2SensorTransform() */
+    const double *K;         /* [C][4]  fx, fy, cx, cy  (Camera::getCalibration()); focal = (fx+fy)/2 (Camera.h:46) */
+
+    /* landmarks */
+    const double *lmk_t;     /* [L][3]  ALandmark::getPose().translation() */
+
+    /* observations (visual residual blocks) */
+    const int32_t *obs_lmk;  /* [O] */
+    const int32_t *obs_frame;/* [O] */
+    const int32_t *obs_cam;  /* [O] */
+    const double *obs_bearing; /* [O][3] AFeature::getBearingVectors().at(0)  (SDV_FACTOR_ANGULAR) */
+    const double *obs_uv;      /* [O][2] AFeature::getPoints().at(0)          (SDV_FACTOR_PIXEL)   */
+    const double *obs_sigma;   /* [O] or NULL => reference default: 1.5/focal (angular, …Analytic.cpp:283), 1.0 (pixel) */
+
+    /* IMU pre-integration factors: IMUFactor + IMUBiasFactor per entry (AOptimizer.cpp:72-93) */
+    const int32_t *imu_i;    /* [P] frame index of framei */
+    const int32_t *imu_j;    /* [P] frame index of framej */
+    const double *imu_dt;    /* [P] (ts_j - ts_i) * 1e-9 */
+    const double *imu_dR;    /* [P][9]  imu_j->getDeltaR() */
+    const double *imu_dv;    /* [P][3]  getDeltaV() */
+    const double *imu_dp;    /* [P][3]  getDeltaP() */
+    const double *imu_cov;   /* [P][81] getCov() */
+    const double *imu_J_dR_bg; /* [P][9] */
+    const double *imu_J_dv_ba; /* [P][9] */
+    const double *imu_J_dv_bg; /* [P][9] */
+    const double *imu_J_dp_ba; /* [P][9] */
+    const double *imu_J_dp_bg; /* [P][9] */
+    const double *imu_sigma_ba; /* [P] imu_i->getbAccNoise() (residuals.hpp:259) */
+    const double *imu_sigma_bg; /* [P] imu_i->getbGyrNoise() (residuals.hpp:261) */
+
+    /* priors injected by addMarginalizationResiduals (…Analytic.cpp:341-486); either may be NULL */
+    const sdv_dense_prior *dense_prior;
+    const sdv_sparse_prior *sparse_prior;
+} sdv_window;
+
+/*
+ * Solution = the values of the Ceres parameter blocks after the solve
+ * (all start at zero, parametersBlock.hpp:44,84).  The caller applies them as
+ * AOptimizer.cpp:391-434 does: T_f_w <- T_f_w * [exp(dw)|dt], lmk += dp,
+ * v += dv, ba += dba, bg += dbg, then IMU::biasDeltaCorrection.
+ */
+typedef struct sdv_delta {
+    double *dpose; /* [F][6]  (rotvec3, trans3) */
+    double *dv;    /* [F][3]  may be NULL when !vio */
+    double *dba;   /* [F][3] */
+    double *dbg;   /* [F][3] */
+    double *dlmk;  /* [L][3] */
+} sdv_delta;
+
+typedef struct sdv_stats {
+    int32_t iterations;         /* ceres Summary::iterations.size()-1 : trust-region steps attempted */
+    int32_t termination;        /* sdv_termination */
+    int32_t num_successful_steps;
+    int32_t num_unsuccessful_steps;
+    int32_t n_reduced;          /* dimension of the dense reduced system */
+    int32_t n_residual_blocks;  /* blocks kept in the reduced program */
+    double initial_cost;        /* without fixed_cost, as Ceres' x_cost_ */
+    double final_cost;
+    double fixed_cost;          /* cost of residual blocks whose parameter blocks are all constant */
+    double final_radius;
+    /* per-iteration trace, entry 0 = iteration 0 */
+    double trace_cost[SDV_MAX_TRACE];
+    double trace_radius[SDV_MAX_TRACE];
+    double trace_model_change[SDV_MAX_TRACE];
+    int32_t trace_accepted[SDV_MAX_TRACE]; /* 1 accepted, 0 rejected, -1 invalid step */
+    /* timing (ms): device = CUDA events around the solve (inputs resident); */
+    double ms_h2d, ms_solve_device, ms_d2h, ms_total_host;
+    int64_t kernel_launches;    /* kernels this call launched */
+    int64_t h2d_bytes, d2h_bytes;
+} sdv_stats;
+
+typedef struct sdv_handle sdv_handle;
+
+/* Fill `cfg` with the reference's options (AOptimizer.cpp:376-388 + Ceres 2.2 defaults). */
+void sdv_default_config(sdv_config *cfg);
+
+/* Replaces: constructing the optimizer object (slamParameters.cpp:263-282). Fails with
+   SDV_ERR_NO_DEVICE when no sm_100 GPU is visible — the product has no CPU path. */
+int sdv_create(sdv_handle **out, const sdv_config *cfg);
+int sdv_destroy(sdv_handle *h);
+
+/* Replaces: AOptimizer::localMapVIOptimization / localMapBA up to (not including) the
+   state write-back — problem build (addResidualsLocalMap, addIMUResiduals,
+   addMarginalizationResiduals) + ceres::Solve.  Host buffers in, host buffers out. */
+int sdv_solve_window(sdv_handle *h, const sdv_window *win, sdv_delta *out, sdv_stats *stats);
+
+/* The same solve split so that benchmarks can keep inputs resident in HBM:
+   upload once, solve many times (each solve restarts from dx = 0), download. */
+int sdv_upload_window(sdv_handle *h, const sdv_window *win);
+int sdv_solve_resident(sdv_handle *h, sdv_stats *stats);
+int sdv_download_delta(sdv_handle *h, sdv_delta *out);
+
+/* Replaces: one Evaluate() sweep over every visual residual block as Ceres performs it
+   (AngularAdjustmentCERESAnalytic.h:55-111 / BundleAdjustmentCERESAnalytic.h:52-90) at the
+   parameter values `x` (NULL = zeros).  Outputs are per observation, Ceres row-major block
+   layout: r[O][2], J_pose[O][12] (2x6), J_lmk[O][6] (2x3).  Test / profiling entry point. */
+int sdv_eval_visual(sdv_handle *h, const sdv_delta *x, double *r, double *J_pose, double *J_lmk, double *cost);
+
+/* Replaces: IMUFactor::Evaluate + IMUBiasFactor::Evaluate (residuals.hpp:133-300) for every
+   pair of the uploaded window.  r_imu[P][9], J_imu[P][9*24] (row-major 9 x (6,6,3,3,3,3)
+   concatenated column-wise), r_bias[P][6]. */
+int sdv_eval_imu(sdv_handle *h, const sdv_delta *x, double *r_imu, double *J_imu, double *r_bias);
+
+/* Multi-GPU (landmark-sharded Schur reduction, one NCCL all-reduce of [S|g|…] per LM iteration).
+   `nccl_unique_id` is the 128-byte ncclUniqueId every rank received from rank 0. */
+int sdv_comm_unique_id(void *out_128_bytes);
+int sdv_comm_init(sdv_handle *h, const void *nccl_unique_id, int32_t rank, int32_t world);
+
+/* Benchmark helper: time `repeats` launches of the visual residual+Jacobian kernel on the
+   resident window with CUDA events on the handle's stream; returns mean ms per launch. */
+int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_per_launch);
+
+const char *sdv_strerror(int status);
+const char *sdv_last_error(const sdv_handle *h); /* detail of the last failure on this handle */
+int sdv_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDV_H */

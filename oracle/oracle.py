@@ -1,0 +1,212 @@
+"""ctypes loader for the CPU oracle.  TEST INFRASTRUCTURE.
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import
+this module; nothing under ``sadvio_b200/`` does (tests/test_layout.py greps for it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from sadvio_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+_SRCS = ["sdv_oracle.cpp", "factors.hpp", "smallmat.hpp", os.path.join("..", "include", "sdv.h")]
+
+
+def build(force: bool = False) -> str:
+    stale = force or not os.path.exists(_SO)
+    if not stale:
+        t = os.path.getmtime(_SO)
+        stale = any(os.path.getmtime(os.path.join(_HERE, s)) > t for s in _SRCS)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        dp, ip = abi.c_double_p, abi.c_int32_p
+        _lib.orc_default_config.argtypes = [C.POINTER(abi.SdvConfig)]
+        _lib.orc_solve_window.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvConfig), C.POINTER(abi.SdvDelta),
+                                          C.POINTER(abi.SdvStats), C.c_int, C.c_int]
+        _lib.orc_eval_visual.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp, dp, dp]
+        _lib.orc_eval_imu.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp, dp]
+        _lib.orc_cost.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp]
+        for name in ("orc_exp_so3", "orc_log_so3", "orc_right_jacobian"):
+            getattr(_lib, name).argtypes = [dp, dp]
+        _lib.orc_angular_eval.argtypes = [dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp]
+        _lib.orc_reproj_eval.argtypes = [dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp]
+        _lib.orc_pose_prior_eval.argtypes = [dp, dp, dp, dp, dp, dp]
+        _lib.orc_p2l_eval.argtypes = [dp, dp, dp, dp, dp, dp, dp, dp, dp]
+        _lib.orc_imu_factor_eval.argtypes = [dp, dp, dp, dp, C.c_double, dp, dp, dp, dp]
+        _lib.orc_process_imu.argtypes = [dp, dp, dp, C.c_double, dp, C.c_double, dp]
+        _lib.orc_bias_delta_correction.argtypes = [dp, dp, dp]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(abi.c_double_p)
+
+
+def _a(x, n=None):
+    a = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    if n is not None:
+        assert a.size == n, (a.size, n)
+    return a
+
+
+def default_config() -> abi.SdvConfig:
+    cfg = abi.SdvConfig()
+    lib().orc_default_config(C.byref(cfg))
+    return cfg
+
+
+def solve_window(win: abi.Window, cfg: abi.SdvConfig | None = None, mode: int = 0, nthreads: int = 1):
+    """Run the restated Ceres LM loop. mode 0 = landmark Schur elimination, 1 = dense full normal equations."""
+    cfg = cfg or default_config()
+    ws = win.as_struct()
+    out = abi.Delta.zeros(win.n_frames, win.n_lmks)
+    ds = out.as_struct()
+    st = abi.SdvStats()
+    rc = lib().orc_solve_window(C.byref(ws), C.byref(cfg), C.byref(ds), C.byref(st), mode, nthreads)
+    return rc, out, abi.stats_to_dict(st)
+
+
+def eval_visual(win: abi.Window, x: abi.Delta | None = None):
+    ws = win.as_struct()
+    O = win.n_obs
+    r, Jp, Jl = np.zeros((O, 2)), np.zeros((O, 12)), np.zeros((O, 6))
+    cost = np.zeros(1)
+    xs = x.as_struct() if x is not None else None
+    lib().orc_eval_visual(C.byref(ws), C.byref(xs) if xs is not None else None, _p(r), _p(Jp), _p(Jl), _p(cost))
+    return r, Jp, Jl, float(cost[0])
+
+
+def eval_imu(win: abi.Window, x: abi.Delta | None = None):
+    ws = win.as_struct()
+    P = win.n_imu
+    r, J, rb = np.zeros((P, 9)), np.zeros((P, 9 * 24)), np.zeros((P, 6))
+    xs = x.as_struct() if x is not None else None
+    lib().orc_eval_imu(C.byref(ws), C.byref(xs) if xs is not None else None, _p(r), _p(J), _p(rb))
+    return r, J.reshape(P, 9, 24), rb
+
+
+def cost(win: abi.Window, x: abi.Delta | None = None):
+    ws = win.as_struct()
+    c, fc = np.zeros(1), np.zeros(1)
+    xs = x.as_struct() if x is not None else None
+    lib().orc_cost(C.byref(ws), C.byref(xs) if xs is not None else None, _p(c), _p(fc))
+    return float(c[0]), float(fc[0])
+
+
+def exp_so3(v):
+    R = np.zeros(9)
+    lib().orc_exp_so3(_p(_a(v, 3)), _p(R))
+    return R.reshape(3, 3)
+
+
+def log_so3(R):
+    v = np.zeros(3)
+    lib().orc_log_so3(_p(_a(R, 9)), _p(v))
+    return v
+
+
+def right_jacobian(v):
+    J = np.zeros(9)
+    lib().orc_right_jacobian(_p(_a(v, 3)), _p(J))
+    return J.reshape(3, 3)
+
+
+def angular_eval(bearing, T_s_f, T_f_w, t_w_lmk, sigma, dx=None, dp=None, jac=True):
+    dx = _a(np.zeros(6) if dx is None else dx, 6)
+    dp = _a(np.zeros(3) if dp is None else dp, 3)
+    r, J6, J3 = np.zeros(2), np.zeros(12), np.zeros(6)
+    lib().orc_angular_eval(_p(_a(bearing, 3)), _p(_a(T_s_f, 12)), _p(_a(T_f_w, 12)), _p(_a(t_w_lmk, 3)), float(sigma),
+                           _p(dx), _p(dp), _p(r), _p(J6) if jac else None, _p(J3) if jac else None)
+    return r, J6.reshape(2, 6), J3.reshape(2, 3)
+
+
+def reproj_eval(uv, K, T_s_f, T_f_w, t_w_lmk, sigma=1.0, dx=None, dp=None, jac=True):
+    dx = _a(np.zeros(6) if dx is None else dx, 6)
+    dp = _a(np.zeros(3) if dp is None else dp, 3)
+    r, J6, J3 = np.zeros(2), np.zeros(12), np.zeros(6)
+    lib().orc_reproj_eval(_p(_a(uv, 2)), _p(_a(K, 4)), _p(_a(T_s_f, 12)), _p(_a(T_f_w, 12)), _p(_a(t_w_lmk, 3)),
+                          float(sigma), _p(dx), _p(dp), _p(r), _p(J6) if jac else None, _p(J3) if jac else None)
+    return r, J6.reshape(2, 6), J3.reshape(2, 3)
+
+
+def pose_prior_eval(T, T_prior, sqrt_inf_diag, dx=None, jac=True):
+    dx = _a(np.zeros(6) if dx is None else dx, 6)
+    r, J = np.zeros(6), np.zeros(36)
+    lib().orc_pose_prior_eval(_p(_a(T, 12)), _p(_a(T_prior, 12)), _p(_a(sqrt_inf_diag, 6)), _p(dx), _p(r),
+                              _p(J) if jac else None)
+    return r, J.reshape(6, 6)
+
+
+def p2l_eval(delta, T_f_w, t_w_lmk, sqrt_inf, dx=None, dp=None, jac=True):
+    dx = _a(np.zeros(6) if dx is None else dx, 6)
+    dp = _a(np.zeros(3) if dp is None else dp, 3)
+    r, J6, J3 = np.zeros(3), np.zeros(18), np.zeros(9)
+    lib().orc_p2l_eval(_p(_a(delta, 3)), _p(_a(T_f_w, 12)), _p(_a(t_w_lmk, 3)), _p(_a(sqrt_inf, 9)), _p(dx), _p(dp),
+                       _p(r), _p(J6) if jac else None, _p(J3) if jac else None)
+    return r, J6.reshape(3, 6), J3.reshape(3, 3)
+
+
+def pack_preint(dR, dv, dp, cov, J_dR_bg, J_dv_ba, J_dv_bg, J_dp_ba, J_dp_bg):
+    return np.concatenate([_a(dR, 9), _a(dv, 3), _a(dp, 3), _a(cov, 81), _a(J_dR_bg, 9), _a(J_dv_ba, 9), _a(J_dv_bg, 9),
+                           _a(J_dp_ba, 9), _a(J_dp_bg, 9)])
+
+
+def imu_factor_eval(T_i, T_j, v_i, v_j, dt, pre, params=None, jac=True):
+    params = _a(np.zeros(24) if params is None else params, 24)
+    r, J = np.zeros(9), np.zeros(9 * 24)
+    rc = lib().orc_imu_factor_eval(_p(_a(T_i, 12)), _p(_a(T_j, 12)), _p(_a(v_i, 3)), _p(_a(v_j, 3)), float(dt),
+                                   _p(_a(pre, 147)), _p(params), _p(r), _p(J) if jac else None)
+    assert rc == 0
+    return r, J.reshape(9, 24)
+
+
+IMU_STATE = dict(acc=(0, 3), gyr=(3, 6), ba=(6, 9), bg=(9, 12), v=(12, 15), T_f_w=(15, 27), is_kf=(27, 28),
+                 dR=(28, 37), dv=(37, 40), dp=(40, 43), Sigma=(43, 124), J_dR_bg=(124, 133), J_dv_ba=(133, 142),
+                 J_dv_bg=(142, 151), J_dp_ba=(151, 160), J_dp_bg=(160, 169))
+
+
+def imu_state(acc, gyr, T_f_w=None, v=None, ba=None, bg=None, is_kf=False):
+    """An isae::IMU object as the config constructor leaves it (IMU.h:26-42): zero biases/velocity, delta_R = I."""
+    s = np.zeros(169)
+    s[0:3], s[3:6] = acc, gyr
+    s[6:9] = 0 if ba is None else ba
+    s[9:12] = 0 if bg is None else bg
+    s[12:15] = 0 if v is None else v
+    s[15:27] = np.eye(3, 4).reshape(12) if T_f_w is None else _a(T_f_w, 12)
+    s[27] = 1.0 if is_kf else 0.0
+    s[28:37] = np.eye(3).reshape(9)
+    return s
+
+
+def imu_get(s, name):
+    a, b = IMU_STATE[name]
+    return s[a:b].copy()
+
+
+def process_imu(last, kf_ba, kf_bg, dt, eta, rate_hz, acc, gyr, is_kf=False):
+    cur = imu_state(acc, gyr, is_kf=is_kf)
+    lib().orc_process_imu(_p(_a(last, 169)), _p(_a(kf_ba, 3)), _p(_a(kf_bg, 3)), float(dt), _p(_a(eta, 6)), float(rate_hz),
+                          _p(cur))
+    return cur
+
+
+def bias_delta_correction(state, d_ba, d_bg):
+    s = _a(state, 169).copy()
+    lib().orc_bias_delta_correction(_p(s), _p(_a(d_ba, 3)), _p(_a(d_bg, 3)))
+    return s
