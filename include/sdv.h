@@ -296,6 +296,11 @@ int sdv_comm_init(sdv_handle *h, const void *nccl_unique_id, int32_t rank, int32
    resident window with CUDA events on the handle's stream; returns mean ms per launch. */
 int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_per_launch);
 
+/* Test / debugging aids: copy an internal device buffer to the host (what: 0 reduced system [S|g|diag|grad],
+   1 Cholesky factor, 2 reduced step, 3 jacobi scale, 4 LM damping) and report the reduced dimensions. */
+int sdv_debug_read(sdv_handle *h, int32_t what, double *out, int64_t count);
+int sdv_debug_dims(sdv_handle *h, int32_t *n, int32_t *n_pad);
+
 const char *sdv_strerror(int status);
 const char *sdv_last_error(const sdv_handle *h); /* detail of the last failure on this handle */
 int sdv_abi_version(void);

@@ -171,7 +171,7 @@ def imu_factor_eval(T_i, T_j, v_i, v_j, dt, pre, params=None, jac=True):
     params = _a(np.zeros(24) if params is None else params, 24)
     r, J = np.zeros(9), np.zeros(9 * 24)
     rc = lib().orc_imu_factor_eval(_p(_a(T_i, 12)), _p(_a(T_j, 12)), _p(_a(v_i, 3)), _p(_a(v_j, 3)), float(dt),
-                                   _p(_a(pre, 147)), _p(params), _p(r), _p(J) if jac else None)
+                                   _p(_a(pre, 141)), _p(params), _p(r), _p(J) if jac else None)
     assert rc == 0
     return r, J.reshape(9, 24)
 

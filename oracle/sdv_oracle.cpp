@@ -1169,7 +1169,7 @@ int orc_p2l_eval(const double *delta, const double *T_f_w, const double *t_w_lmk
     double *J[2] = {J36, J33};
     return e.Evaluate(par, r3, (J36 || J33) ? J : nullptr) ? 0 : 1;
 }
-// IMU factor with explicit inputs: pre = [dR9 dv3 dp3 cov81 J_dR_bg9 J_dv_ba9 J_dv_bg9 J_dp_ba9 J_dp_bg9] (147 doubles);
+// IMU factor with explicit inputs: pre = [dR9 dv3 dp3 cov81 J_dR_bg9 J_dv_ba9 J_dv_bg9 J_dp_ba9 J_dp_bg9] (141 doubles);
 // params = [dTi6 dTj6 dvi3 dvj3 dba3 dbg3] (24); outputs r9 and J (9x24 row-major, may be NULL).
 int orc_imu_factor_eval(const double *T_i, const double *T_j, const double *v_i, const double *v_j, double dt, const double *pre,
                         const double *params24, double *r9, double *J924) {

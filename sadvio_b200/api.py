@@ -1,0 +1,212 @@
+"""Python binding of the C ABI (include/sdv.h) and a host-side mirror of the reference optimizer interface.
+
+The product path is the CUDA library only: if ``libsadvio_b200.so`` is missing or no sm_100 GPU is visible, calls fail
+loudly (``BackendUnavailable``); there is no CPU fallback and this module never imports ``oracle``.
+
+``B200Optimizer`` mirrors ``isae::AOptimizer`` for the two entry points this repository replaces
+(reference cpp/include/isaeslam/optimizers/AOptimizer.h:28-30):
+    bool localMapBA(local_map, fixed_frame_number = 0)
+    bool localMapVIOptimization(local_map, fixed_frame_number = 0)
+operating on a flattened ``abi.Window`` (the C++ adapter sadvio_b200/host/b200_optimizer.hpp does the flattening of the
+pointer graph).  Both return ``True``/``False`` like the reference and update the window state in place exactly as
+AOptimizer.cpp:391-434 does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, build as _build
+from .synth import exp_so3
+
+
+class BackendUnavailable(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        raise BackendUnavailable(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(path)
+    dp = abi.c_double_p
+    L.sdv_abi_version.restype = C.c_int
+    L.sdv_strerror.restype = C.c_char_p
+    L.sdv_strerror.argtypes = [C.c_int]
+    L.sdv_last_error.restype = C.c_char_p
+    L.sdv_last_error.argtypes = [C.c_void_p]
+    L.sdv_default_config.argtypes = [C.POINTER(abi.SdvConfig)]
+    L.sdv_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(abi.SdvConfig)]
+    L.sdv_destroy.argtypes = [C.c_void_p]
+    L.sdv_solve_window.argtypes = [C.c_void_p, C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), C.POINTER(abi.SdvStats)]
+    L.sdv_upload_window.argtypes = [C.c_void_p, C.POINTER(abi.SdvWindow)]
+    L.sdv_solve_resident.argtypes = [C.c_void_p, C.POINTER(abi.SdvStats)]
+    L.sdv_download_delta.argtypes = [C.c_void_p, C.POINTER(abi.SdvDelta)]
+    L.sdv_eval_visual.argtypes = [C.c_void_p, C.POINTER(abi.SdvDelta), dp, dp, dp, dp]
+    L.sdv_eval_imu.argtypes = [C.c_void_p, C.POINTER(abi.SdvDelta), dp, dp, dp]
+    L.sdv_comm_unique_id.argtypes = [C.c_void_p]
+    L.sdv_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    L.sdv_time_kernel.argtypes = [C.c_void_p, C.c_int32, C.c_int32, dp]
+    L.sdv_debug_read.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int64]
+    L.sdv_debug_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    _lib = L
+    return L
+
+
+def default_config() -> abi.SdvConfig:
+    cfg = abi.SdvConfig()
+    lib().sdv_default_config(C.byref(cfg))
+    return cfg
+
+
+class Solver:
+    """Thin RAII wrapper around ``sdv_handle``."""
+
+    def __init__(self, cfg: abi.SdvConfig | None = None, device: int = 0):
+        L = lib()
+        self.cfg = cfg or default_config()
+        self.cfg.device = device
+        self._h = C.c_void_p()
+        rc = L.sdv_create(C.byref(self._h), C.byref(self.cfg))
+        if rc != 0:
+            self._h = None
+            raise BackendUnavailable(f"sdv_create failed: {L.sdv_strerror(rc).decode()}")
+        self._win = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sdv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, allow=(0,)):
+        if rc not in allow:
+            L = lib()
+            raise RuntimeError(f"sdv error {rc} ({L.sdv_strerror(rc).decode()}): {L.sdv_last_error(self._h).decode()}")
+        return rc
+
+    # -- the reference-facing call: host buffers in, host buffers out
+    def solve_window(self, win: abi.Window):
+        ws = win.as_struct()
+        out = abi.Delta.zeros(win.n_frames, win.n_lmks)
+        ds = out.as_struct()
+        st = abi.SdvStats()
+        rc = self._check(lib().sdv_solve_window(self._h, C.byref(ws), C.byref(ds), C.byref(st)), allow=(0, 5))
+        self._win = win
+        return rc, out, abi.stats_to_dict(st)
+
+    # -- resident variant (bench: inputs already in HBM)
+    def upload(self, win: abi.Window):
+        ws = win.as_struct()
+        self._check(lib().sdv_upload_window(self._h, C.byref(ws)))
+        self._win = win
+
+    def solve_resident(self):
+        st = abi.SdvStats()
+        rc = self._check(lib().sdv_solve_resident(self._h, C.byref(st)), allow=(0, 5))
+        return rc, abi.stats_to_dict(st)
+
+    def download(self) -> abi.Delta:
+        out = abi.Delta.zeros(self._win.n_frames, self._win.n_lmks)
+        ds = out.as_struct()
+        self._check(lib().sdv_download_delta(self._h, C.byref(ds)))
+        return out
+
+    def eval_visual(self, x: abi.Delta | None = None):
+        O = self._win.n_obs
+        r, Jp, Jl, cost = np.zeros((O, 2)), np.zeros((O, 12)), np.zeros((O, 6)), np.zeros(1)
+        xs = x.as_struct() if x is not None else None
+        p = lambda a: a.ctypes.data_as(abi.c_double_p)
+        self._check(lib().sdv_eval_visual(self._h, C.byref(xs) if xs is not None else None, p(r), p(Jp), p(Jl), p(cost)))
+        return r, Jp, Jl, float(cost[0])
+
+    def eval_imu(self, x: abi.Delta | None = None):
+        P = self._win.n_imu
+        r, J, rb = np.zeros((P, 9)), np.zeros((P, 216)), np.zeros((P, 6))
+        xs = x.as_struct() if x is not None else None
+        p = lambda a: a.ctypes.data_as(abi.c_double_p)
+        self._check(lib().sdv_eval_imu(self._h, C.byref(xs) if xs is not None else None, p(r), p(J), p(rb)))
+        return r, J.reshape(P, 9, 24), rb
+
+    def time_kernel(self, which: int, repeats: int = 20) -> float:
+        ms = np.zeros(1)
+        self._check(lib().sdv_time_kernel(self._h, which, repeats, ms.ctypes.data_as(abi.c_double_p)))
+        return float(ms[0])
+
+    def debug_dims(self):
+        n, npad = C.c_int32(), C.c_int32()
+        self._check(lib().sdv_debug_dims(self._h, C.byref(n), C.byref(npad)))
+        return n.value, npad.value
+
+    def debug_read(self, what: int, count: int) -> np.ndarray:
+        out = np.zeros(count)
+        self._check(lib().sdv_debug_read(self._h, what, out.ctypes.data_as(abi.c_double_p), count))
+        return out
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(uid, 128)
+        self._check(lib().sdv_comm_init(self._h, buf, rank, world))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().sdv_comm_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError("sdv_comm_unique_id failed")
+    return buf.raw
+
+
+class B200Optimizer:
+    """Host-side mirror of ``isae::AOptimizer`` for the window solves (see module docstring)."""
+
+    def __init__(self, device: int = 0, cfg: abi.SdvConfig | None = None):
+        self.solver = Solver(cfg, device)
+        self.last_stats: dict | None = None
+
+    def _run(self, win: abi.Window, fixed_frame_number: int, vio: bool) -> bool:
+        win.n_fixed = int(fixed_frame_number)
+        win.vio = vio
+        try:
+            rc, d, st = self.solver.solve_window(win)
+        except RuntimeError:
+            return False  # the adapter maps a non-zero status to `false` and leaves the state untouched
+        self.last_stats = st
+        # state write-back, AOptimizer.cpp:391-418
+        for f in range(win.n_frames):
+            T = np.vstack([win.T_f_w[f].reshape(3, 4), [0, 0, 0, 1]])
+            dT = np.eye(4)
+            dT[:3, :3] = exp_so3(d.dpose[f, :3])
+            dT[:3, 3] = d.dpose[f, 3:]
+            win.T_f_w[f] = (T @ dT)[:3, :4].reshape(12)
+        win.lmk_t += d.dlmk
+        if vio:
+            win.v += d.dv
+            win.ba += d.dba
+            win.bg += d.dbg
+            # IMU::biasDeltaCorrection with the PREVIOUS keyframe's dba, dbg (AOptimizer.cpp:421-434, IMU.cpp:104-108)
+            for p in range(win.n_imu):
+                i = int(win.imu_i[p])
+                dba, dbg = d.dba[i], d.dbg[i]
+                win.imu_dp[p] += win.imu_J_dp_ba[p].reshape(3, 3) @ dba + win.imu_J_dp_bg[p].reshape(3, 3) @ dbg
+                win.imu_dv[p] += win.imu_J_dv_ba[p].reshape(3, 3) @ dba + win.imu_J_dv_bg[p].reshape(3, 3) @ dbg
+                win.imu_dR[p] = (win.imu_dR[p].reshape(3, 3) @ exp_so3(win.imu_J_dR_bg[p].reshape(3, 3) @ dbg)).reshape(9)
+        return True
+
+    def localMapVIOptimization(self, local_map: abi.Window, fixed_frame_number: int = 0) -> bool:  # noqa: N802
+        return self._run(local_map, fixed_frame_number, True)
+
+    def localMapBA(self, local_map: abi.Window, fixed_frame_number: int = 0) -> bool:  # noqa: N802
+        return self._run(local_map, fixed_frame_number, False)

@@ -1,0 +1,1033 @@
+// C-ABI implementation (include/sdv.h) — host side of the B200 sliding-window BA/VIO backend.
+//
+// Replaces, behind the C ABI, the reference's Ceres problem build + solve:
+//   AOptimizer::localMapVIOptimization / localMapBA   (cpp/src/optimizers/AOptimizer.cpp:299-446)
+//   addResidualsLocalMap / addIMUResiduals / addMarginalizationResiduals
+//   (AngularAdjustmentCERESAnalytic.cpp:212-339, AOptimizer.cpp:22-96, …Analytic.cpp:341-486)
+// There is NO CPU fallback: without a CUDA device sdv_create fails with SDV_ERR_NO_DEVICE.
+#include "../../include/sdv.h"
+#include "sdv_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace sdv;
+
+namespace {
+
+struct Arena { // host-pinned mirror of one contiguous device allocation
+    size_t size = 0;
+    std::vector<std::pair<size_t, size_t>> parts;
+    size_t add(size_t bytes) {
+        size_t off = (size + 255) & ~size_t(255);
+        size = off + bytes;
+        return off;
+    }
+};
+
+// NCCL through dlopen so that single-GPU use has no NCCL dependency
+struct NcclUid { char internal[128]; };
+typedef int (*nccl_get_uid_t)(NcclUid *);
+typedef int (*nccl_init_rank_t)(void **, int, NcclUid, int);
+typedef int (*nccl_allreduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_destroy_t)(void *);
+struct NcclApi {
+    void *lib = nullptr;
+    nccl_get_uid_t get_uid = nullptr;
+    nccl_init_rank_t init_rank = nullptr;
+    nccl_allreduce_t allreduce = nullptr;
+    nccl_destroy_t destroy = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        get_uid = (nccl_get_uid_t)dlsym(lib, "ncclGetUniqueId");
+        init_rank = (nccl_init_rank_t)dlsym(lib, "ncclCommInitRank");
+        allreduce = (nccl_allreduce_t)dlsym(lib, "ncclAllReduce");
+        destroy = (nccl_destroy_t)dlsym(lib, "ncclCommDestroy");
+        return get_uid && init_rank && allreduce && destroy;
+    }
+};
+NcclApi g_nccl;
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+
+} // namespace
+
+struct sdv_handle {
+    sdv_config cfg;
+    SolverOpts opt;
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    // input arena
+    unsigned char *d_in = nullptr, *h_in = nullptr;
+    size_t in_cap = 0, in_bytes = 0, h2d_last = 0;
+    // scratch
+    unsigned char *d_scr = nullptr;
+    size_t scr_cap = 0;
+    // small pinned readback
+    unsigned char *h_rb = nullptr;
+    size_t rb_cap = 0;
+    unsigned char *d_out = nullptr; // solution blocks
+    size_t out_cap = 0;
+    DevProblem P;
+    LinBuf B[2];
+    LMState *d_st = nullptr;
+    Accum *d_acc = nullptr;
+    double *d_Sb = nullptr, *d_Lo = nullptr, *d_scale_p = nullptr, *d_damp_p = nullptr, *d_graw_p = nullptr, *d_dxp = nullptr,
+           *d_scale_l = nullptr, *d_red = nullptr;
+    size_t sb_elems = 0;
+    bool resident = false;
+    int lin_grid = 0, lin_smem = 0, sch_grid = 0, fac_grid = 0;
+    int64_t launches = 0;
+    // comm
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    LMState h_state;
+    Accum h_acc;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return SDV_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int fail(sdv_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+template <class T> T *at(unsigned char *base, size_t off) { return reinterpret_cast<T *>(base + off); }
+
+int ensure(sdv_handle *h, unsigned char **d, size_t *cap, size_t need, bool pinned_host = false) {
+    if (need <= *cap) return SDV_OK;
+    size_t ncap = std::max(need, *cap * 2);
+    if (pinned_host) {
+        if (*d) cudaFreeHost(*d);
+        CK(cudaMallocHost((void **)d, ncap));
+    } else {
+        if (*d) cudaFree(*d);
+        CK(cudaMalloc((void **)d, ncap));
+    }
+    *cap = ncap;
+    return SDV_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sdv_abi_version(void) { return SDV_ABI_VERSION; }
+
+const char *sdv_strerror(int s) {
+    switch (s) {
+    case SDV_OK: return "ok";
+    case SDV_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case SDV_ERR_CUDA: return "CUDA error";
+    case SDV_ERR_NO_DEVICE: return "no CUDA device (this backend has no CPU path)";
+    case SDV_ERR_UNSUPPORTED: return "unsupported input";
+    case SDV_ERR_NUMERICAL_FAILURE: return "numerical failure";
+    case SDV_ERR_COMM: return "communicator error";
+    }
+    return "unknown status";
+}
+
+const char *sdv_last_error(const sdv_handle *h) { return h ? h->err.c_str() : ""; }
+
+void sdv_default_config(sdv_config *c) {
+    std::memset(c, 0, sizeof(*c));
+    c->abi_version = SDV_ABI_VERSION;
+    c->device = 0;
+    c->max_num_iterations = 20;           // AOptimizer.cpp:380
+    c->max_consecutive_invalid_steps = 5; // Ceres 2.2 default
+    c->jacobi_scaling = 1;                // Ceres 2.2 default
+    c->function_tolerance = 1e-3;         // AOptimizer.cpp:384
+    c->gradient_tolerance = 1e-10;
+    c->parameter_tolerance = 1e-8;
+    c->initial_trust_region_radius = 1e4;
+    c->max_trust_region_radius = 1e16;
+    c->min_trust_region_radius = 1e-32;
+    c->min_lm_diagonal = 1e-6;
+    c->max_lm_diagonal = 1e32;
+    c->min_relative_decrease = 1e-3;
+}
+
+int sdv_create(sdv_handle **out, const sdv_config *cfg) {
+    if (!out || !cfg || cfg->abi_version != SDV_ABI_VERSION) return SDV_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return SDV_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return SDV_ERR_NO_DEVICE;
+    if (prop.major < 10) return SDV_ERR_NO_DEVICE; // kernels are built for sm_100a only
+    sdv_handle *h = new sdv_handle();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    h->num_sms = prop.multiProcessorCount;
+    SolverOpts &o = h->opt;
+    o.max_num_iterations = cfg->max_num_iterations;
+    o.max_consecutive_invalid_steps = cfg->max_consecutive_invalid_steps;
+    o.jacobi_scaling = cfg->jacobi_scaling;
+    o.function_tolerance = cfg->function_tolerance;
+    o.gradient_tolerance = cfg->gradient_tolerance;
+    o.parameter_tolerance = cfg->parameter_tolerance;
+    o.initial_radius = cfg->initial_trust_region_radius;
+    o.max_radius = cfg->max_trust_region_radius;
+    o.min_radius = cfg->min_trust_region_radius;
+    o.min_diag = cfg->min_lm_diagonal;
+    o.max_diag = cfg->max_lm_diagonal;
+    o.min_relative_decrease = cfg->min_relative_decrease;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return SDV_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    std::memset(&h->P, 0, sizeof(h->P));
+    *out = h;
+    return SDV_OK;
+}
+
+int sdv_destroy(sdv_handle *h) {
+    if (!h) return SDV_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->d_scr) cudaFree(h->d_scr);
+    if (h->h_rb) cudaFreeHost(h->h_rb);
+    if (h->d_out) cudaFree(h->d_out);
+    for (int i = 0; i < 4; i++)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return SDV_OK;
+}
+
+int sdv_comm_unique_id(void *out) {
+    if (!out) return SDV_ERR_INVALID_ARGUMENT;
+    if (!g_nccl.load()) return SDV_ERR_COMM;
+    NcclUid id;
+    if (g_nccl.get_uid(&id) != 0) return SDV_ERR_COMM;
+    std::memcpy(out, &id, sizeof(id));
+    return SDV_OK;
+}
+
+int sdv_comm_init(sdv_handle *h, const void *uid, int32_t rank, int32_t world) {
+    if (!h || !uid || world < 1 || rank < 0 || rank >= world) return SDV_ERR_INVALID_ARGUMENT;
+    if (world == 1) {
+        h->rank = 0;
+        h->world = 1;
+        return SDV_OK;
+    }
+    if (!g_nccl.load()) return fail(h, SDV_ERR_COMM, "libnccl.so.2 not loadable");
+    cudaSetDevice(h->device);
+    NcclUid id;
+    std::memcpy(&id, uid, sizeof(id));
+    if (g_nccl.init_rank(&h->comm, world, id, rank) != 0) return fail(h, SDV_ERR_COMM, "ncclCommInitRank failed");
+    h->rank = rank;
+    h->world = world;
+    h->resident = false;
+    return SDV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// upload: validate, derive the reduced-program structure, pack one pinned arena, one H2D copy
+// ---------------------------------------------------------------------------------------------------------------------
+int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
+    if (!h || !w) return SDV_ERR_INVALID_ARGUMENT;
+    if (w->abi_version != SDV_ABI_VERSION) return fail(h, SDV_ERR_INVALID_ARGUMENT, "abi_version mismatch");
+    const int F = w->n_frames, C = w->n_cams, L = w->n_lmks, O = w->n_obs, Pn = w->vio ? w->n_imu : 0;
+    if (F <= 0 || C <= 0 || L < 0 || O < 0 || Pn < 0 || w->n_fixed < 0) return fail(h, SDV_ERR_INVALID_ARGUMENT, "negative or empty sizes");
+    if (!w->T_f_w || !w->T_s_f || !w->K || (L > 0 && !w->lmk_t)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "null frame/camera/landmark arrays");
+    if (O > 0 && (!w->obs_lmk || !w->obs_frame || !w->obs_cam)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "null observation index arrays");
+    const int kind = w->factor_kind;
+    if (kind != SDV_FACTOR_ANGULAR && kind != SDV_FACTOR_PIXEL) return fail(h, SDV_ERR_INVALID_ARGUMENT, "bad factor_kind");
+    if (O > 0 && kind == SDV_FACTOR_ANGULAR && !w->obs_bearing) return fail(h, SDV_ERR_INVALID_ARGUMENT, "obs_bearing is null");
+    if (O > 0 && kind == SDV_FACTOR_PIXEL && !w->obs_uv) return fail(h, SDV_ERR_INVALID_ARGUMENT, "obs_uv is null");
+    if (w->vio && (!w->v || !w->ba || !w->bg)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "vio window without v/ba/bg");
+    if (Pn > 0 && (!w->imu_i || !w->imu_j || !w->imu_dt || !w->imu_dR || !w->imu_dv || !w->imu_dp || !w->imu_cov || !w->imu_J_dR_bg ||
+                   !w->imu_J_dv_ba || !w->imu_J_dv_bg || !w->imu_J_dp_ba || !w->imu_J_dp_bg || !w->imu_sigma_ba || !w->imu_sigma_bg))
+        return fail(h, SDV_ERR_INVALID_ARGUMENT, "null IMU arrays");
+    if (w->has_prior && (!w->T_prior || !w->inf_prior)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "has_prior without T_prior/inf_prior");
+    if (w->sparse_prior) return fail(h, SDV_ERR_UNSUPPORTED, "sparsified prior factors are not implemented in this build");
+    for (int o = 0; o < O; o++) {
+        if (w->obs_lmk[o] < 0 || w->obs_lmk[o] >= L || w->obs_frame[o] < 0 || w->obs_frame[o] >= F || w->obs_cam[o] < 0 || w->obs_cam[o] >= C)
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "observation index out of range");
+        if (o > 0 && w->obs_lmk[o] < w->obs_lmk[o - 1])
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "observations must be landmark-major (reference walk order)");
+    }
+    for (int p = 0; p < Pn; p++)
+        if (w->imu_i[p] < 0 || w->imu_i[p] >= F || w->imu_j[p] < 0 || w->imu_j[p] >= F || w->imu_i[p] == w->imu_j[p])
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "imu pair index out of range");
+    const sdv_dense_prior *dp = w->dense_prior;
+    if (dp) {
+        if (dp->n_full <= 0 || dp->n <= 0 || !dp->J || !dp->r0 || dp->frame >= F || (dp->n_keep > 0 && (!dp->keep_lmk || !dp->keep_col)))
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "malformed dense prior");
+        if (dp->frame >= 0 && (dp->frame_col < 0 || dp->frame_col + 15 > dp->n)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "dense prior frame_col");
+        for (int k = 0; k < dp->n_keep; k++)
+            if (dp->keep_lmk[k] < 0 || dp->keep_lmk[k] >= L || dp->keep_col[k] + 3 > dp->n)
+                return fail(h, SDV_ERR_INVALID_ARGUMENT, "dense prior landmark index/column out of range");
+    }
+    cudaSetDevice(h->device);
+
+    // ---- reduced-program structure (what Ceres' preprocessor derives: constant blocks dropped, unused blocks dropped)
+    std::vector<char> pose_used(F, 0), vb_used(F, 0);
+    for (int o = 0; o < O; o++) pose_used[w->obs_frame[o]] = 1;
+    for (int p = 0; p < Pn; p++) {
+        pose_used[w->imu_i[p]] = pose_used[w->imu_j[p]] = 1;
+        vb_used[w->imu_i[p]] = vb_used[w->imu_j[p]] = 1;
+    }
+    if (w->has_prior)
+        for (int f = 0; f < F; f++)
+            if (w->has_prior[f]) pose_used[f] = 1;
+    if (dp && dp->frame >= 0) {
+        pose_used[dp->frame] = 1;
+        if (w->vio) vb_used[dp->frame] = 1;
+    }
+    std::vector<int> pose_col(F, -1), vb_col(F, -1), lmk_col(L, -1);
+    int n = 0;
+    for (int f = 0; f < F; f++) {
+        bool fixed = f > (F - w->n_fixed - 1); // AngularAdjustmentCERESAnalytic.cpp:234, AOptimizer.cpp:47
+        if (!fixed && pose_used[f]) {
+            pose_col[f] = n;
+            n += 6;
+        }
+        if (!fixed && w->vio && vb_used[f]) {
+            vb_col[f] = n;
+            n += 9;
+        }
+    }
+    if (dp)
+        for (int k = 0; k < dp->n_keep; k++) {
+            if (dp->keep_col[k] < 0) continue;
+            int l = dp->keep_lmk[k];
+            if (lmk_col[l] < 0) {
+                lmk_col[l] = n;
+                n += 3;
+            }
+        }
+    if (n == 0) return fail(h, SDV_ERR_UNSUPPORTED, "window has no free frame parameter (pure landmark refinement is landmarkOptimization, not this entry point)");
+    const int n_pad = (n + 31) / 32 * 32, ld = n_pad;
+
+    // ---- slots: (landmark, distinct keyframe) groups
+    std::vector<int> slot_ptr(L + 1, 0), slot_frame, slot_obs_ptr, slot_obs(O);
+    slot_frame.reserve(O);
+    slot_obs_ptr.reserve(O + 1);
+    {
+        int o = 0;
+        std::vector<int> tmp_frames, tmp_count;
+        for (int l = 0; l < L; l++) {
+            slot_ptr[l] = (int)slot_frame.size();
+            int o_begin = o;
+            tmp_frames.clear();
+            while (o < O && w->obs_lmk[o] == l) {
+                int f = w->obs_frame[o];
+                if (std::find(tmp_frames.begin(), tmp_frames.end(), f) == tmp_frames.end()) tmp_frames.push_back(f);
+                o++;
+            }
+            if ((int)tmp_frames.size() > MAX_SLOTS)
+                return fail(h, SDV_ERR_UNSUPPORTED, "a landmark is observed from more than 32 keyframes (kernel limit of this build)");
+            for (int f : tmp_frames) {
+                slot_frame.push_back(f);
+                slot_obs_ptr.push_back(0);
+            }
+            // fill slot_obs grouped by slot, keeping observation order inside a slot
+            int base = slot_ptr[l];
+            std::vector<int> cnt(tmp_frames.size(), 0);
+            for (int q = o_begin; q < o; q++) {
+                int s = (int)(std::find(tmp_frames.begin(), tmp_frames.end(), w->obs_frame[q]) - tmp_frames.begin());
+                cnt[s]++;
+            }
+            int run = o_begin;
+            for (size_t s = 0; s < tmp_frames.size(); s++) {
+                slot_obs_ptr[base + s] = run;
+                run += cnt[s];
+                cnt[s] = 0;
+            }
+            for (int q = o_begin; q < o; q++) {
+                int s = (int)(std::find(tmp_frames.begin(), tmp_frames.end(), w->obs_frame[q]) - tmp_frames.begin());
+                slot_obs[slot_obs_ptr[base + s] + cnt[s]++] = q;
+            }
+        }
+        slot_ptr[L] = (int)slot_frame.size();
+        slot_obs_ptr.push_back(O);
+    }
+    const int nslots = (int)slot_frame.size();
+
+    // ---- landmark shard of this rank (contiguous, balanced by observation count)
+    std::vector<int> lmk_obs_ptr(L + 1, 0);
+    {
+        int o = 0;
+        for (int l = 0; l < L; l++) {
+            lmk_obs_ptr[l] = o;
+            while (o < O && w->obs_lmk[o] == l) o++;
+        }
+        lmk_obs_ptr[L] = O;
+    }
+    int l0 = 0, l1 = L;
+    if (h->world > 1) {
+        auto cut = [&](int r) {
+            long long target = (long long)O * r / h->world;
+            int l = (int)(std::lower_bound(lmk_obs_ptr.begin(), lmk_obs_ptr.end(), (int)target) - lmk_obs_ptr.begin());
+            return std::min(l, L);
+        };
+        l0 = cut(h->rank);
+        l1 = h->rank == h->world - 1 ? L : cut(h->rank + 1);
+    }
+    const int o0 = lmk_obs_ptr[l0], o1 = lmk_obs_ptr[l1], Oloc = o1 - o0;
+
+    // ---- dense prior column maps
+    std::vector<int> mp_src, mp_dst;
+    if (dp) {
+        if (dp->frame >= 0) {
+            for (int q = 0; q < 15; q++) {
+                mp_src.push_back(dp->frame_col + q);
+                int dst = -1;
+                if (q < 6) dst = pose_col[dp->frame] >= 0 ? pose_col[dp->frame] + q : -1;
+                else dst = vb_col[dp->frame] >= 0 ? vb_col[dp->frame] + (q - 6) : -1;
+                mp_dst.push_back(dst);
+            }
+        }
+        for (int k = 0; k < dp->n_keep; k++) {
+            if (dp->keep_col[k] < 0) continue;
+            for (int q = 0; q < 3; q++) {
+                mp_src.push_back(dp->keep_col[k] + q);
+                mp_dst.push_back(lmk_col[dp->keep_lmk[k]] + q);
+            }
+        }
+    }
+    const int nm = (int)mp_src.size();
+
+    // ---- input arena
+    Arena A;
+    auto D = sizeof(double);
+    size_t o_T = A.add(D * 12 * F), o_v = A.add(D * 3 * F), o_ba = A.add(D * 3 * F), o_bg = A.add(D * 3 * F);
+    size_t o_hp = A.add(F), o_Tp = A.add(D * 12 * F), o_ip = A.add(D * 6 * F);
+    size_t o_pc = A.add(4 * F), o_vc = A.add(4 * F);
+    size_t o_Ts = A.add(D * 12 * C), o_K = A.add(D * 4 * C), o_cw = A.add(D * C);
+    size_t o_lt = A.add(D * 3 * std::max(L, 1)), o_lc = A.add(4 * std::max(L, 1));
+    size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(O, 1));
+    size_t o_ol = A.add(4 * std::max(O, 1)), o_ofc = A.add(4 * std::max(O, 1));
+    const int mplanes = kind == SDV_FACTOR_ANGULAR ? 3 : 2;
+    size_t o_om = A.add(D * mplanes * std::max(O, 1));
+    size_t o_ow = w->obs_sigma ? A.add(D * std::max(O, 1)) : 0;
+    size_t o_ii = A.add(4 * std::max(Pn, 1)), o_ij = A.add(4 * std::max(Pn, 1));
+    size_t o_idt = A.add(D * std::max(Pn, 1)), o_idR = A.add(D * 9 * std::max(Pn, 1)), o_idv = A.add(D * 3 * std::max(Pn, 1)),
+           o_idp = A.add(D * 3 * std::max(Pn, 1)), o_icov = A.add(D * 81 * std::max(Pn, 1));
+    size_t o_j1 = A.add(D * 9 * std::max(Pn, 1)), o_j2 = A.add(D * 9 * std::max(Pn, 1)), o_j3 = A.add(D * 9 * std::max(Pn, 1)),
+           o_j4 = A.add(D * 9 * std::max(Pn, 1)), o_j5 = A.add(D * 9 * std::max(Pn, 1));
+    size_t o_sba = A.add(D * std::max(Pn, 1)), o_sbg = A.add(D * std::max(Pn, 1));
+    size_t o_mJ = 0, o_mr = 0, o_ms = 0, o_md = 0;
+    if (dp) {
+        o_mJ = A.add(D * (size_t)dp->n_full * dp->n);
+        o_mr = A.add(D * dp->n_full);
+        o_ms = A.add(4 * std::max(nm, 1));
+        o_md = A.add(4 * std::max(nm, 1));
+    }
+    int rc;
+    if ((rc = ensure(h, &h->h_in, &h->in_cap, A.size, true)) != SDV_OK) return rc;
+    {
+        size_t dcap = h->in_bytes;
+        unsigned char *dptr = h->d_in;
+        if (A.size > dcap) {
+            if (dptr) cudaFree(dptr);
+            CK(cudaMalloc((void **)&dptr, A.size * 2));
+            h->d_in = dptr;
+            h->in_bytes = A.size * 2;
+        }
+    }
+    unsigned char *hb = h->h_in;
+    auto t_pack0 = std::chrono::steady_clock::now();
+    std::memcpy(hb + o_T, w->T_f_w, D * 12 * F);
+    if (w->vio) {
+        std::memcpy(hb + o_v, w->v, D * 3 * F);
+        std::memcpy(hb + o_ba, w->ba, D * 3 * F);
+        std::memcpy(hb + o_bg, w->bg, D * 3 * F);
+    } else {
+        std::memset(hb + o_v, 0, D * 3 * F);
+        std::memset(hb + o_ba, 0, D * 3 * F);
+        std::memset(hb + o_bg, 0, D * 3 * F);
+    }
+    if (w->has_prior) {
+        std::memcpy(hb + o_hp, w->has_prior, F);
+        std::memcpy(hb + o_Tp, w->T_prior, D * 12 * F);
+        std::memcpy(hb + o_ip, w->inf_prior, D * 6 * F);
+    } else {
+        std::memset(hb + o_hp, 0, F);
+    }
+    std::memcpy(hb + o_pc, pose_col.data(), 4 * F);
+    std::memcpy(hb + o_vc, vb_col.data(), 4 * F);
+    std::memcpy(hb + o_Ts, w->T_s_f, D * 12 * C);
+    std::memcpy(hb + o_K, w->K, D * 4 * C);
+    for (int c = 0; c < C; c++) {
+        double focal = (w->K[4 * c] + w->K[4 * c + 1]) / 2; // Camera.h:46
+        double sigma = kind == SDV_FACTOR_ANGULAR ? 1.5 / focal : 1.0; // …Analytic.cpp:283 ; BA…Analytic.h:47
+        at<double>(hb, o_cw)[c] = 1.0 / sigma;
+    }
+    if (L > 0) {
+        std::memcpy(hb + o_lt, w->lmk_t, D * 3 * L);
+        std::memcpy(hb + o_lc, lmk_col.data(), 4 * L);
+    }
+    std::memcpy(hb + o_sp, slot_ptr.data(), 4 * (L + 1));
+    if (nslots) std::memcpy(hb + o_sf, slot_frame.data(), 4 * nslots);
+    std::memcpy(hb + o_sop, slot_obs_ptr.data(), 4 * (nslots + 1));
+    if (O) {
+        std::memcpy(hb + o_so, slot_obs.data(), 4 * O);
+        std::memcpy(hb + o_ol, w->obs_lmk, 4 * O);
+        int *fc = at<int>(hb, o_ofc);
+        for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o];
+        double *om = at<double>(hb, o_om);
+        const double *src = kind == SDV_FACTOR_ANGULAR ? w->obs_bearing : w->obs_uv;
+        for (int o = 0; o < O; o++)
+            for (int k = 0; k < mplanes; k++) om[(size_t)k * O + o] = src[(size_t)o * mplanes + k];
+        if (w->obs_sigma) {
+            double *ow = at<double>(hb, o_ow);
+            for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
+        }
+    }
+    if (Pn) {
+        std::memcpy(hb + o_ii, w->imu_i, 4 * Pn);
+        std::memcpy(hb + o_ij, w->imu_j, 4 * Pn);
+        std::memcpy(hb + o_idt, w->imu_dt, D * Pn);
+        std::memcpy(hb + o_idR, w->imu_dR, D * 9 * Pn);
+        std::memcpy(hb + o_idv, w->imu_dv, D * 3 * Pn);
+        std::memcpy(hb + o_idp, w->imu_dp, D * 3 * Pn);
+        std::memcpy(hb + o_icov, w->imu_cov, D * 81 * Pn);
+        std::memcpy(hb + o_j1, w->imu_J_dR_bg, D * 9 * Pn);
+        std::memcpy(hb + o_j2, w->imu_J_dv_ba, D * 9 * Pn);
+        std::memcpy(hb + o_j3, w->imu_J_dv_bg, D * 9 * Pn);
+        std::memcpy(hb + o_j4, w->imu_J_dp_ba, D * 9 * Pn);
+        std::memcpy(hb + o_j5, w->imu_J_dp_bg, D * 9 * Pn);
+        std::memcpy(hb + o_sba, w->imu_sigma_ba, D * Pn);
+        std::memcpy(hb + o_sbg, w->imu_sigma_bg, D * Pn);
+    }
+    if (dp) {
+        std::memcpy(hb + o_mJ, dp->J, D * (size_t)dp->n_full * dp->n);
+        std::memcpy(hb + o_mr, dp->r0, D * dp->n_full);
+        if (nm) {
+            std::memcpy(hb + o_ms, mp_src.data(), 4 * nm);
+            std::memcpy(hb + o_md, mp_dst.data(), 4 * nm);
+        }
+    }
+    (void)t_pack0;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    h->h2d_last = A.size;
+    unsigned char *db = h->d_in;
+
+    // ---- scratch arena (device only)
+    Arena S;
+    size_t s_st = S.add(sizeof(LMState)), s_acc = S.add(sizeof(Accum));
+    size_t s_lin[2][12];
+    for (int b = 0; b < 2; b++) {
+        s_lin[b][0] = S.add(D * FCT_ROW * F * C);
+        s_lin[b][1] = S.add(D * 2 * std::max(Oloc, 1));
+        s_lin[b][2] = S.add(D * 12 * std::max(Oloc, 1));
+        s_lin[b][3] = S.add(D * 6 * std::max(Oloc, 1));
+        s_lin[b][4] = S.add(D * 9 * std::max(Pn, 1));
+        s_lin[b][5] = S.add(D * 216 * std::max(Pn, 1));
+        s_lin[b][6] = S.add(D * 6 * std::max(Pn, 1));
+        s_lin[b][7] = S.add(D * 6 * F);
+        s_lin[b][8] = S.add(D * 36 * F);
+        s_lin[b][9] = S.add(D * std::max(dp ? dp->n_full : 1, 1));
+        s_lin[b][10] = S.add(D * n_pad);
+        s_lin[b][11] = S.add(D * 3 * std::max(L, 1));
+    }
+    const size_t sb_elems = (size_t)(n_pad + 32) * ld;
+    size_t s_Sb = S.add(D * sb_elems), s_Lo = S.add(D * sb_elems);
+    size_t s_sp = S.add(D * n_pad), s_dp = S.add(D * n_pad), s_gp = S.add(D * n_pad), s_dx = S.add(D * n_pad);
+    size_t s_sl = S.add(D * 3 * std::max(L, 1));
+    size_t s_inf = S.add(D * 81 * std::max(Pn, 1));
+    size_t s_mH = S.add(D * std::max((size_t)nm * nm, (size_t)1)), s_mg = S.add(D * std::max(nm, 1));
+    size_t s_red = S.add(D * 16);
+    if ((rc = ensure(h, &h->d_scr, &h->scr_cap, S.size)) != SDV_OK) return rc;
+    unsigned char *sb = h->d_scr;
+    size_t out_bytes = D * ((size_t)15 * F + 3 * (size_t)std::max(L, 1));
+    if ((rc = ensure(h, &h->d_out, &h->out_cap, out_bytes)) != SDV_OK) return rc;
+    if ((rc = ensure(h, &h->h_rb, &h->rb_cap, std::max(out_bytes, sizeof(LMState) + sizeof(Accum) + 256), true)) != SDV_OK) return rc;
+
+    DevProblem &P = h->P;
+    std::memset(&P, 0, sizeof(P));
+    P.F = F; P.C = C; P.L = L; P.O = O; P.P = Pn;
+    P.vio = w->vio; P.kind = kind;
+    P.n = n; P.n_pad = n_pad; P.ld = ld; P.nslots = nslots;
+    P.l0 = l0; P.l1 = l1; P.o0 = o0; P.o1 = o1;
+    P.rank = h->rank; P.world = h->world;
+    P.T_f_w = at<double>(db, o_T); P.v = at<double>(db, o_v); P.ba = at<double>(db, o_ba); P.bg = at<double>(db, o_bg);
+    P.has_prior = w->has_prior ? at<unsigned char>(db, o_hp) : nullptr;
+    P.T_prior = at<double>(db, o_Tp); P.inf_prior = at<double>(db, o_ip);
+    P.pose_col = at<int>(db, o_pc); P.vb_col = at<int>(db, o_vc);
+    P.T_s_f = at<double>(db, o_Ts); P.K = at<double>(db, o_K); P.cam_w = at<double>(db, o_cw);
+    P.lmk_t = at<double>(db, o_lt); P.lmk_col = at<int>(db, o_lc);
+    P.slot_ptr = at<int>(db, o_sp); P.slot_frame = at<int>(db, o_sf); P.slot_obs_ptr = at<int>(db, o_sop); P.slot_obs = at<int>(db, o_so);
+    P.obs_lmk = at<int>(db, o_ol); P.obs_fc = at<int>(db, o_ofc); P.obs_meas = at<double>(db, o_om);
+    P.obs_w = w->obs_sigma ? at<double>(db, o_ow) : nullptr;
+    P.imu_i = at<int>(db, o_ii); P.imu_j = at<int>(db, o_ij); P.imu_dt = at<double>(db, o_idt); P.imu_dR = at<double>(db, o_idR);
+    P.imu_dv = at<double>(db, o_idv); P.imu_dp = at<double>(db, o_idp); P.imu_cov = at<double>(db, o_icov);
+    P.imu_J_dR_bg = at<double>(db, o_j1); P.imu_J_dv_ba = at<double>(db, o_j2); P.imu_J_dv_bg = at<double>(db, o_j3);
+    P.imu_J_dp_ba = at<double>(db, o_j4); P.imu_J_dp_bg = at<double>(db, o_j5);
+    P.imu_sigma_ba = at<double>(db, o_sba); P.imu_sigma_bg = at<double>(db, o_sbg);
+    P.imu_inf_sqrt = at<double>(sb, s_inf);
+    if (dp) {
+        P.mp_nfull = dp->n_full; P.mp_n = dp->n; P.mp_nmap = nm;
+        P.mp_J = at<double>(db, o_mJ); P.mp_r0 = at<double>(db, o_mr);
+        P.mp_src_col = at<int>(db, o_ms); P.mp_dst_col = at<int>(db, o_md);
+        P.mp_H = at<double>(sb, s_mH); P.mp_g0 = at<double>(sb, s_mg);
+    }
+    for (int b = 0; b < 2; b++) {
+        LinBuf &B = h->B[b];
+        B.fct = at<double>(sb, s_lin[b][0]); B.r = at<double>(sb, s_lin[b][1]); B.Jp = at<double>(sb, s_lin[b][2]);
+        B.Jl = at<double>(sb, s_lin[b][3]); B.imu_r = at<double>(sb, s_lin[b][4]); B.imu_J = at<double>(sb, s_lin[b][5]);
+        B.bias_r = at<double>(sb, s_lin[b][6]); B.prior_r = at<double>(sb, s_lin[b][7]); B.prior_J = at<double>(sb, s_lin[b][8]);
+        B.mp_r = at<double>(sb, s_lin[b][9]); B.xp = at<double>(sb, s_lin[b][10]); B.xl = at<double>(sb, s_lin[b][11]);
+    }
+    h->d_st = at<LMState>(sb, s_st);
+    h->d_acc = at<Accum>(sb, s_acc);
+    h->d_Sb = at<double>(sb, s_Sb); h->d_Lo = at<double>(sb, s_Lo);
+    h->d_scale_p = at<double>(sb, s_sp); h->d_damp_p = at<double>(sb, s_dp); h->d_graw_p = at<double>(sb, s_gp); h->d_dxp = at<double>(sb, s_dx);
+    h->d_scale_l = at<double>(sb, s_sl);
+    h->d_red = at<double>(sb, s_red);
+    h->sb_elems = sb_elems;
+
+    // ---- launch geometry
+    size_t fct_bytes = (size_t)F * C * FCT_ROW * D;
+    P.fct_in_smem = fct_bytes <= 160 * 1024 ? 1 : 0;
+    h->lin_smem = P.fct_in_smem ? (int)fct_bytes : 0;
+    if (kind == SDV_FACTOR_ANGULAR) CK(cudaFuncSetAttribute(k_lin_visual<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    else CK(cudaFuncSetAttribute(k_lin_visual<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_trisolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = 1;
+    if (kind == SDV_FACTOR_ANGULAR) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lin_visual<0>, LIN_THREADS, h->lin_smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lin_visual<1>, LIN_THREADS, h->lin_smem));
+    per_sm = std::max(per_sm, 1);
+    h->lin_grid = std::max(1, std::min((Oloc + LIN_THREADS - 1) / LIN_THREADS, h->num_sms * per_sm));
+    h->sch_grid = std::max(1, std::min(((l1 - l0) + SCH_WARPS - 1) / SCH_WARPS, h->num_sms * 8));
+    h->fac_grid = std::max(1, (std::max(Pn, 1) + FAC_WARPS - 1) / FAC_WARPS);
+
+    // ---- one-time device setup for this window
+    if (Pn > 0) {
+        k_imu_inf_sqrt<<<(Pn + 31) / 32, 32, 0, h->stream>>>(P);
+        h->launches++;
+    }
+    if (dp && nm > 0) {
+        k_prior_setup<<<std::min(64, (nm * nm + 255) / 256 + 1), 256, 0, h->stream>>>(P);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->resident = true;
+    return SDV_OK;
+}
+
+} // extern "C"
+
+namespace {
+
+int launch_linearize(sdv_handle *h, int which) {
+    const DevProblem &P = h->P;
+    if (P.o1 > P.o0) {
+        if (P.kind == SDV_FACTOR_ANGULAR)
+            k_lin_visual<0><<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        else
+            k_lin_visual<1><<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        h->launches++;
+    }
+    if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0)) {
+        k_lin_factors<<<h->fac_grid, FAC_WARPS * 32, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        h->launches++;
+    }
+    return SDV_OK;
+}
+
+int allreduce(sdv_handle *h, double *buf, size_t count) {
+    if (h->world <= 1) return SDV_OK;
+    if (g_nccl.allreduce(buf, buf, count, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream) != 0) return fail(h, SDV_ERR_COMM, "ncclAllReduce failed");
+    return SDV_OK;
+}
+
+__global__ void k_pack_scalars(const LMState *st, Accum *acc, double *red, int dir, int which /* buffer: -2 candidate, 0 initial */) {
+    int b = which >= 0 ? which : 1 - st->cur;
+    if (dir == 0) {
+        red[0] = acc->cost[b];
+        red[1] = acc->model_gd;
+        red[2] = acc->model_dd;
+        red[3] = acc->step_norm2;
+        red[4] = acc->cand_norm2;
+        red[5] = acc->fixed_cost;
+    } else {
+        acc->cost[b] = red[0];
+        acc->model_gd = red[1];
+        acc->model_dd = red[2];
+        acc->step_norm2 = red[3];
+        acc->cand_norm2 = red[4];
+        acc->fixed_cost = red[5];
+    }
+}
+
+int reduce_scalars(sdv_handle *h, int which) {
+    if (h->world <= 1) return SDV_OK;
+    k_pack_scalars<<<1, 1, 0, h->stream>>>(h->d_st, h->d_acc, h->d_red, 0, which);
+    int rc = allreduce(h, h->d_red, 6);
+    if (rc != SDV_OK) return rc;
+    k_pack_scalars<<<1, 1, 0, h->stream>>>(h->d_st, h->d_acc, h->d_red, 1, which);
+    h->launches += 2;
+    return SDV_OK;
+}
+
+// grad_max over landmark columns must be a MAX across ranks: reduce it as a count of violations instead
+__global__ void k_gradmax_to_flag(Accum *acc, double tol, double *red, int dir) {
+    if (dir == 0) red[8] = (__longlong_as_double((long long)acc->grad_max_bits) > tol) ? 1.0 : 0.0;
+    else acc->grad_max_bits = red[8] > 0.0 ? (unsigned long long)__double_as_longlong(1e300) : 0ull;
+}
+
+int trisolve_smem(const DevProblem &P) { return (int)((P.n_pad + 1024 + 32 * 33) * sizeof(double)); }
+
+int launch_iteration(sdv_handle *h) {
+    const DevProblem &P = h->P;
+    const int T = P.n_pad / CH_T;
+    cudaStream_t s = h->stream;
+    k_iter_begin<<<1, 1, 0, s>>>(h->d_st);
+    if (cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s) != cudaSuccess) return fail(h, SDV_ERR_CUDA, "memset S");
+    k_schur<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+    h->launches += 3;
+    if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0)) {
+        k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
+        h->launches++;
+    }
+    if (h->world > 1) {
+        // one all-reduce of [S | g | diag | grad] per LM iteration, plus the gradient-violation flag
+        k_gradmax_to_flag<<<1, 1, 0, s>>>(h->d_acc, h->opt.gradient_tolerance, h->d_red, 0);
+        int rc = allreduce(h, h->d_Sb, (size_t)(P.n_pad + 3) * P.ld);
+        if (rc != SDV_OK) return rc;
+        rc = allreduce(h, h->d_red + 8, 1);
+        if (rc != SDV_OK) return rc;
+        k_gradmax_to_flag<<<1, 1, 0, s>>>(h->d_acc, h->opt.gradient_tolerance, h->d_red, 1);
+        h->launches += 2;
+    }
+    k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
+    h->launches++;
+    for (int k = 0; k < T; k++) {
+        int npanel = T - k + 1, ntrail = 0;
+        for (int i = k + 1; i <= T; i++) ntrail += std::min(i, T - 1) - k;
+        k_chol_panel<<<npanel + ntrail, CH_THREADS, 0, s>>>(h->d_Sb, h->d_Lo, P.ld, T, k, h->d_st, h->d_acc);
+        h->launches++;
+    }
+    k_trisolve<<<1, TS_THREADS, trisolve_smem(P), s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Lo, h->d_damp_p, h->d_graw_p, h->d_dxp);
+    k_backsub<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
+    h->launches += 2;
+    launch_linearize(h, -2);
+    int rc = reduce_scalars(h, -2);
+    if (rc != SDV_OK) return rc;
+    k_ctrl<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
+    h->launches++;
+    return SDV_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
+    if (!h) return SDV_ERR_INVALID_ARGUMENT;
+    if (!h->resident) return fail(h, SDV_ERR_INVALID_ARGUMENT, "no window uploaded");
+    cudaSetDevice(h->device);
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    int64_t launches0 = h->launches;
+    auto t0 = std::chrono::steady_clock::now();
+    CK(cudaEventRecord(h->ev[2], s));
+    // x = 0
+    CK(cudaMemsetAsync(h->B[0].xp, 0, sizeof(double) * P.n_pad, s));
+    CK(cudaMemsetAsync(h->B[1].xp, 0, sizeof(double) * P.n_pad, s));
+    CK(cudaMemsetAsync(h->B[0].xl, 0, sizeof(double) * 3 * std::max(P.L, 1), s));
+    CK(cudaMemsetAsync(h->B[1].xl, 0, sizeof(double) * 3 * std::max(P.L, 1), s));
+    CK(cudaMemsetAsync(h->d_st, 0, sizeof(LMState), s));
+    CK(cudaMemsetAsync(h->d_acc, 0, sizeof(Accum), s));
+    k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, 0);
+    h->launches++;
+    launch_linearize(h, 0);
+    int rc = reduce_scalars(h, 0);
+    if (rc != SDV_OK) return rc;
+    k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
+    h->launches++;
+    int *h_status = reinterpret_cast<int *>(h->h_rb);
+    for (int it = 0; it < h->opt.max_num_iterations + 1; it++) {
+        rc = launch_iteration(h);
+        if (rc != SDV_OK) return rc;
+        CK(cudaMemcpyAsync(h_status, &h->d_st->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (*h_status != 0) break;
+    }
+    CK(cudaEventRecord(h->ev[3], s));
+    CK(cudaMemcpyAsync(h->h_rb, h->d_st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_rb + sizeof(LMState), h->d_acc, sizeof(Accum), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    std::memcpy(&h->h_state, h->h_rb, sizeof(LMState));
+    std::memcpy(&h->h_acc, h->h_rb + sizeof(LMState), sizeof(Accum));
+    auto t1 = std::chrono::steady_clock::now();
+    if (stats) {
+        const LMState &st = h->h_state;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+        stats->iterations = st.iter;
+        stats->termination = st.status > 0 ? st.status - 1 : SDV_TERM_NO_CONVERGENCE;
+        stats->num_successful_steps = st.n_ok;
+        stats->num_unsuccessful_steps = st.n_bad;
+        stats->n_reduced = P.n;
+        stats->n_residual_blocks = 0;
+        stats->initial_cost = st.initial_cost;
+        stats->final_cost = st.x_cost;
+        stats->fixed_cost = h->h_acc.fixed_cost;
+        stats->final_radius = st.radius;
+        for (int i = 0; i < SDV_MAX_TRACE; i++) {
+            stats->trace_cost[i] = st.trace_cost[i];
+            stats->trace_radius[i] = st.trace_radius[i];
+            stats->trace_model_change[i] = st.trace_model[i];
+            stats->trace_accepted[i] = st.trace_accepted[i];
+        }
+        stats->ms_solve_device = ms;
+        stats->ms_total_host = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        stats->kernel_launches = h->launches - launches0;
+    }
+    return h->h_state.status == 1 + SDV_TERM_FAILURE ? SDV_ERR_NUMERICAL_FAILURE : SDV_OK;
+}
+
+int sdv_download_delta(sdv_handle *h, sdv_delta *out) {
+    if (!h || !out || !out->dpose || !out->dlmk) return SDV_ERR_INVALID_ARGUMENT;
+    if (!h->resident) return fail(h, SDV_ERR_INVALID_ARGUMENT, "no window uploaded");
+    cudaSetDevice(h->device);
+    const DevProblem &P = h->P;
+    double *d = reinterpret_cast<double *>(h->d_out);
+    double *dpose = d, *dv = d + 6 * P.F, *dba = dv + 3 * P.F, *dbg = dba + 3 * P.F, *dlmk = dbg + 3 * P.F;
+    size_t nd = (size_t)15 * P.F + 3 * (size_t)std::max(P.L, 1);
+    k_gather_solution<<<std::max(1, std::min(1024, (std::max(P.L, P.F) + 255) / 256)), 256, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, dpose, dv, dba,
+                                                                                                        dbg, dlmk);
+    h->launches++;
+    if (h->world > 1) {
+        // each rank only solved its own landmarks: zero the others and sum
+        // (landmark parameters outside [l0,l1) are still zero in xl, so a plain sum is the gather)
+        int rc = allreduce(h, dlmk, 3 * (size_t)P.L);
+        if (rc != SDV_OK) return rc;
+        if (h->rank != 0) {
+        }
+    }
+    CK(cudaMemcpyAsync(h->h_rb, d, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double *hb = reinterpret_cast<const double *>(h->h_rb);
+    std::memcpy(out->dpose, hb, sizeof(double) * 6 * P.F);
+    if (out->dv) std::memcpy(out->dv, hb + 6 * P.F, sizeof(double) * 3 * P.F);
+    if (out->dba) std::memcpy(out->dba, hb + 9 * P.F, sizeof(double) * 3 * P.F);
+    if (out->dbg) std::memcpy(out->dbg, hb + 12 * P.F, sizeof(double) * 3 * P.F);
+    if (P.L > 0) std::memcpy(out->dlmk, hb + 15 * P.F, sizeof(double) * 3 * P.L);
+    return SDV_OK;
+}
+
+int sdv_solve_window(sdv_handle *h, const sdv_window *win, sdv_delta *out, sdv_stats *stats) {
+    if (!h || !win || !out) return SDV_ERR_INVALID_ARGUMENT;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = sdv_upload_window(h, win);
+    if (rc != SDV_OK) return rc;
+    sdv_stats local;
+    sdv_stats *st = stats ? stats : &local;
+    std::memset(st, 0, sizeof(*st));
+    rc = sdv_solve_resident(h, st);
+    if (rc != SDV_OK && rc != SDV_ERR_NUMERICAL_FAILURE) return rc;
+    int rc2 = sdv_download_delta(h, out);
+    if (rc2 != SDV_OK) return rc2;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    st->ms_h2d = ms;
+    st->h2d_bytes = (int64_t)h->h2d_last;
+    st->d2h_bytes = (int64_t)(sizeof(double) * ((size_t)15 * h->P.F + 3 * (size_t)h->P.L) + sizeof(LMState) + sizeof(Accum));
+    st->ms_total_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+// set the linearisation point of buffer 0 from user-supplied parameter blocks
+static int set_point(sdv_handle *h, const sdv_delta *x) {
+    const DevProblem &P = h->P;
+    std::vector<double> xp(P.n_pad, 0.0), xl(3 * (size_t)std::max(P.L, 1), 0.0);
+    std::vector<int> pose_col(P.F), vb_col(P.F), lmk_col(std::max(P.L, 1));
+    CK(cudaMemcpy(pose_col.data(), P.pose_col, 4 * P.F, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(vb_col.data(), P.vb_col, 4 * P.F, cudaMemcpyDeviceToHost));
+    if (P.L) CK(cudaMemcpy(lmk_col.data(), P.lmk_col, 4 * P.L, cudaMemcpyDeviceToHost));
+    if (x) {
+        for (int f = 0; f < P.F; f++) {
+            if (pose_col[f] >= 0 && x->dpose)
+                for (int k = 0; k < 6; k++) xp[pose_col[f] + k] = x->dpose[6 * f + k];
+            if (vb_col[f] >= 0)
+                for (int k = 0; k < 3; k++) {
+                    if (x->dv) xp[vb_col[f] + k] = x->dv[3 * f + k];
+                    if (x->dba) xp[vb_col[f] + 3 + k] = x->dba[3 * f + k];
+                    if (x->dbg) xp[vb_col[f] + 6 + k] = x->dbg[3 * f + k];
+                }
+        }
+        if (x->dlmk)
+            for (int l = 0; l < P.L; l++)
+                for (int k = 0; k < 3; k++) {
+                    if (lmk_col[l] >= 0) xp[lmk_col[l] + k] = x->dlmk[3 * l + k];
+                    else xl[3 * (size_t)l + k] = x->dlmk[3 * l + k];
+                }
+    }
+    CK(cudaMemcpyAsync(h->B[0].xp, xp.data(), sizeof(double) * P.n_pad, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->B[0].xl, xl.data(), sizeof(double) * 3 * std::max(P.L, 1), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_st, 0, sizeof(LMState), h->stream));
+    CK(cudaMemsetAsync(h->d_acc, 0, sizeof(Accum), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SDV_OK;
+}
+
+int sdv_eval_visual(sdv_handle *h, const sdv_delta *x, double *r, double *J_pose, double *J_lmk, double *cost) {
+    if (!h) return SDV_ERR_INVALID_ARGUMENT;
+    if (!h->resident) return fail(h, SDV_ERR_INVALID_ARGUMENT, "no window uploaded");
+    cudaSetDevice(h->device);
+    const DevProblem &P = h->P;
+    int rc = set_point(h, x);
+    if (rc != SDV_OK) return rc;
+    k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, 0);
+    h->launches++;
+    launch_linearize(h, 0);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    const int Oloc = P.o1 - P.o0;
+    std::vector<double> buf((size_t)20 * std::max(Oloc, 1));
+    CK(cudaMemcpy(buf.data(), h->B[0].r, sizeof(double) * 2 * Oloc, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(buf.data() + 2 * (size_t)Oloc, h->B[0].Jp, sizeof(double) * 12 * Oloc, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(buf.data() + 14 * (size_t)Oloc, h->B[0].Jl, sizeof(double) * 6 * Oloc, cudaMemcpyDeviceToHost));
+    for (int ol = 0; ol < Oloc; ol++) {
+        size_t o = (size_t)P.o0 + ol;
+        if (r)
+            for (int k = 0; k < 2; k++) r[2 * o + k] = buf[(size_t)k * Oloc + ol];
+        if (J_pose)
+            for (int k = 0; k < 12; k++) J_pose[12 * o + k] = buf[(size_t)(2 + k) * Oloc + ol];
+        if (J_lmk)
+            for (int k = 0; k < 6; k++) J_lmk[6 * o + k] = buf[(size_t)(14 + k) * Oloc + ol];
+    }
+    if (cost) {
+        Accum a;
+        CK(cudaMemcpy(&a, h->d_acc, sizeof(Accum), cudaMemcpyDeviceToHost));
+        *cost = a.cost[0];
+    }
+    return SDV_OK;
+}
+
+int sdv_eval_imu(sdv_handle *h, const sdv_delta *x, double *r_imu, double *J_imu, double *r_bias) {
+    if (!h) return SDV_ERR_INVALID_ARGUMENT;
+    if (!h->resident) return fail(h, SDV_ERR_INVALID_ARGUMENT, "no window uploaded");
+    cudaSetDevice(h->device);
+    const DevProblem &P = h->P;
+    if (P.P == 0) return SDV_OK;
+    int rc = set_point(h, x);
+    if (rc != SDV_OK) return rc;
+    k_lin_factors<<<h->fac_grid, FAC_WARPS * 32, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, 0);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (r_imu) CK(cudaMemcpy(r_imu, h->B[0].imu_r, sizeof(double) * 9 * P.P, cudaMemcpyDeviceToHost));
+    if (J_imu) CK(cudaMemcpy(J_imu, h->B[0].imu_J, sizeof(double) * 216 * P.P, cudaMemcpyDeviceToHost));
+    if (r_bias) CK(cudaMemcpy(r_bias, h->B[0].bias_r, sizeof(double) * 6 * P.P, cudaMemcpyDeviceToHost));
+    return SDV_OK;
+}
+
+// which: 0 = visual residual+Jacobian kernel, 1 = Schur/assembly kernel, 2 = dense Cholesky (all panels),
+//        3 = landmark back-substitution
+int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_per_launch) {
+    if (!h || !ms_per_launch || repeats <= 0) return SDV_ERR_INVALID_ARGUMENT;
+    if (!h->resident) return fail(h, SDV_ERR_INVALID_ARGUMENT, "no window uploaded");
+    cudaSetDevice(h->device);
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    const int T = P.n_pad / CH_T;
+    // a fresh linearisation at x = 0 so that every kernel has valid inputs
+    int rc = set_point(h, nullptr);
+    if (rc != SDV_OK) return rc;
+    k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, 0);
+    launch_linearize(h, 0);
+    k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
+    CK(cudaStreamSynchronize(s));
+    float total = 0;
+    for (int it = 0; it < repeats + 3; it++) {
+        float ms = 0;
+        if (which == 0) {
+            CK(cudaEventRecord(h->ev[2], s));
+            if (P.kind == SDV_FACTOR_ANGULAR)
+                k_lin_visual<0><<<h->lin_grid, LIN_THREADS, h->lin_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, 0);
+            else
+                k_lin_visual<1><<<h->lin_grid, LIN_THREADS, h->lin_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, 0);
+            CK(cudaEventRecord(h->ev[3], s));
+        } else if (which == 1) {
+            CK(cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s));
+            CK(cudaEventRecord(h->ev[2], s));
+            k_schur<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+            CK(cudaEventRecord(h->ev[3], s));
+        } else if (which == 2) {
+            CK(cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s));
+            k_schur<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+            if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0))
+                k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
+            k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
+            CK(cudaEventRecord(h->ev[2], s));
+            for (int k = 0; k < T; k++) {
+                int npanel = T - k + 1, ntrail = 0;
+                for (int i = k + 1; i <= T; i++) ntrail += std::min(i, T - 1) - k;
+                k_chol_panel<<<npanel + ntrail, CH_THREADS, 0, s>>>(h->d_Sb, h->d_Lo, P.ld, T, k, h->d_st, h->d_acc);
+            }
+            CK(cudaEventRecord(h->ev[3], s));
+        } else {
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "unknown kernel id");
+        }
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+        if (it >= 3) total += ms;
+    }
+    *ms_per_launch = total / repeats;
+    return SDV_OK;
+}
+
+// debugging / test aid: copy an internal device buffer to the host.
+//   what: 0 = reduced system buffer Sb ((n_pad+32) x ld), 1 = factor Lo, 2 = dxp (n_pad), 3 = scale_p, 4 = damp_p
+int sdv_debug_read(sdv_handle *h, int32_t what, double *out, int64_t count) {
+    if (!h || !out || !h->resident) return SDV_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    const double *src = nullptr;
+    size_t avail = 0;
+    switch (what) {
+    case 0: src = h->d_Sb; avail = h->sb_elems; break;
+    case 1: src = h->d_Lo; avail = h->sb_elems; break;
+    case 2: src = h->d_dxp; avail = h->P.n_pad; break;
+    case 3: src = h->d_scale_p; avail = h->P.n_pad; break;
+    case 4: src = h->d_damp_p; avail = h->P.n_pad; break;
+    default: return SDV_ERR_INVALID_ARGUMENT;
+    }
+    size_t nn = std::min<size_t>(avail, (size_t)count);
+    CK(cudaMemcpy(out, src, nn * sizeof(double), cudaMemcpyDeviceToHost));
+    return SDV_OK;
+}
+
+int sdv_debug_dims(sdv_handle *h, int32_t *n, int32_t *n_pad) {
+    if (!h || !h->resident) return SDV_ERR_INVALID_ARGUMENT;
+    if (n) *n = h->P.n;
+    if (n_pad) *n_pad = h->P.n_pad;
+    return SDV_OK;
+}
+
+} // extern "C"

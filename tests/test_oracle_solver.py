@@ -1,0 +1,96 @@
+"""The oracle's restated Ceres LM loop: pinned through the reference's own end-to-end tests and self-consistency."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from sadvio_b200 import abi, synth
+from tests import ref_fixtures as rf
+
+
+def test_reference_inertial_optimisation():  # imu_test.cpp:464-487 (tolerances 1e-2 / 1e-5)
+    win = rf.free_fall_window()
+    for mode in (0, 1):
+        rc, d, st = orc.solve_window(win, mode=mode)
+        assert rc == 0
+        rf.check_free_fall(win, d)
+        assert st["final_cost"] < st["initial_cost"]
+
+
+def test_reference_bias_estimation():  # imu_test.cpp:545-568 (tolerance 1e-5)
+    win = rf.bias_window()
+    rc, d, st = orc.solve_window(win, mode=0)
+    assert rc == 0
+    rf.check_bias(win, d)
+
+
+@pytest.mark.parametrize("name,kind", [("tiny", 0), ("tiny", 1), ("small", 0), ("small", 1)])
+def test_schur_equals_full_normal_equations(name, kind):
+    """Landmark elimination must give the step SPARSE_NORMAL_CHOLESKY computes on the full system."""
+    win = synth.make_window(name, factor_kind=kind)
+    rc0, d0, st0 = orc.solve_window(win, mode=0)
+    rc1, d1, st1 = orc.solve_window(win, mode=1)
+    assert rc0 == rc1 == 0
+    assert st0["iterations"] == st1["iterations"] and st0["termination"] == st1["termination"]
+    assert st0["trace_accepted"] == st1["trace_accepted"]
+    for a, b in ((d0.dpose, d1.dpose), (d0.dv, d1.dv), (d0.dba, d1.dba), (d0.dbg, d1.dbg), (d0.dlmk, d1.dlmk)):
+        assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
+
+
+def test_converges_to_ground_truth():
+    win = synth.make_window("small")
+    cfg = orc.default_config()
+    rc, d, st = orc.solve_window(win, cfg)
+    new = synth.apply_delta(win, d)
+    gt = win.meta
+    assert st["termination"] == "FUNCTION_TOLERANCE" and st["iterations"] <= 20
+    assert np.abs(new["T_f_w"] - gt["T_f_w_gt"]).max() < 0.02 < np.abs(win.T_f_w - gt["T_f_w_gt"]).max()
+    assert np.abs(new["bg"] - gt["bg_true"]).max() < 1e-4
+    assert np.abs(new["ba"] - gt["ba_true"]).max() < 5e-3
+
+
+def test_threads_do_not_change_the_answer():
+    win = synth.make_window("small")
+    _, d1, s1 = orc.solve_window(win, nthreads=1)
+    _, d4, s4 = orc.solve_window(win, nthreads=4)
+    assert s1["iterations"] == s4["iterations"]
+    assert np.abs(d1.dpose - d4.dpose).max() < 1e-10
+
+
+def test_fixed_cost_and_constant_blocks():
+    """A pose prior on a fixed keyframe has only constant blocks: Ceres moves it to fixed_cost."""
+    win = synth.make_window("tiny")
+    # move the fixed frame's prior away from its pose so that the prior has a non-zero residual
+    win.T_prior[-1] = synth.T34(np.vstack([win.T_f_w[-1].reshape(3, 4), [0, 0, 0, 1]]) @ np.diag([1, 1, 1, 1.0]) +
+                                np.array([[0, 0, 0, 0.01]] * 3 + [[0, 0, 0, 0]]))
+    rc, d, st = orc.solve_window(win)
+    assert st["fixed_cost"] > 0
+    assert np.all(d.dpose[-1] == 0) and np.all(d.dv[-1] == 0) and np.all(d.dba[-1] == 0)
+    # with no fixed frame the same prior is part of the cost
+    win.n_fixed = 0
+    rc, d, st2 = orc.solve_window(win)
+    assert st2["fixed_cost"] == 0
+
+
+def test_pre_integration_generator_matches_oracle():
+    """synth.preintegrate (numpy, product side) == oracle processIMU chain, including the stale delta_R quirk."""
+    rng = np.random.default_rng(7)
+    n, dt = 20, 0.005
+    acc = rng.normal(0, 1, (2 * n, 3)) + [0, 0, 9.81]
+    gyr = rng.normal(0, 0.3, (2 * n, 3))
+    ba, bg = np.array([0.02, -0.01, 0.03]), np.array([0.001, 0.002, -0.001])
+    e = rf.eta(200.0)
+    p1 = synth.preintegrate(acc[:n], gyr[:n], dt, ba, bg, e, None)
+    p2 = synth.preintegrate(acc[n:], gyr[n:], dt, ba, bg, e, p1)
+    last = orc.imu_state(acc[0], gyr[0], ba=ba, bg=bg, is_kf=True)
+    for k in range(1, 2 * n + 1):
+        a, g = (acc[k], gyr[k]) if k < 2 * n else (acc[-1], gyr[-1])
+        last = orc.process_imu(last, ba, bg, dt, e, 200.0, a, g, is_kf=(k == n))
+        if k == n:
+            kf1 = last
+    for pre, st in ((p1, kf1), (p2, last)):
+        assert np.allclose(pre.dR.reshape(9), orc.imu_get(st, "dR"), atol=1e-14)
+        assert np.allclose(pre.dv, orc.imu_get(st, "dv"), atol=1e-14)
+        assert np.allclose(pre.dp, orc.imu_get(st, "dp"), atol=1e-14)
+        assert np.allclose(pre.cov.reshape(81), orc.imu_get(st, "Sigma"), rtol=1e-12, atol=1e-22)
+        for nm in ("J_dR_bg", "J_dv_ba", "J_dv_bg", "J_dp_ba", "J_dp_bg"):
+            assert np.allclose(getattr(pre, nm).reshape(9), orc.imu_get(st, nm), atol=1e-14)
