@@ -289,6 +289,10 @@ int sdv_eval_imu(sdv_handle *h, const sdv_delta *x, double *r_imu, double *J_imu
 
 /* Multi-GPU (landmark-sharded Schur reduction, one NCCL all-reduce of [S|g|…] per LM iteration).
    `nccl_unique_id` is the 128-byte ncclUniqueId every rank received from rank 0. */
+/* Host-only helper (no CUDA): the contiguous, observation-balanced landmark range [l0,l1) and observation range [o0,o1)
+   that rank `rank` of `world` owns — the partition sdv_upload_window applies after sdv_comm_init. */
+int sdv_shard_range(const int32_t *obs_lmk, int32_t n_obs, int32_t n_lmks, int32_t rank, int32_t world, int32_t *l0, int32_t *l1,
+                    int32_t *o0, int32_t *o1);
 int sdv_comm_unique_id(void *out_128_bytes);
 int sdv_comm_init(sdv_handle *h, const void *nccl_unique_id, int32_t rank, int32_t world);
 
@@ -300,6 +304,7 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
    1 Cholesky factor, 2 reduced step, 3 jacobi scale, 4 LM damping) and report the reduced dimensions. */
 int sdv_debug_read(sdv_handle *h, int32_t what, double *out, int64_t count);
 int sdv_debug_dims(sdv_handle *h, int32_t *n, int32_t *n_pad);
+int sdv_debug_micro(sdv_handle *h, double *out64);
 
 const char *sdv_strerror(int status);
 const char *sdv_last_error(const sdv_handle *h); /* detail of the last failure on this handle */

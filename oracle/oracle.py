@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
                                           C.POINTER(abi.SdvStats), C.c_int, C.c_int]
         _lib.orc_eval_visual.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp, dp, dp]
         _lib.orc_eval_imu.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp, dp]
+        _lib.orc_reduced_system.argtypes = [C.POINTER(abi.SdvWindow), C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.POINTER(C.c_int)]
         _lib.orc_cost.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp]
         for name in ("orc_exp_so3", "orc_log_so3", "orc_right_jacobian"):
             getattr(_lib, name).argtypes = [dp, dp]
@@ -107,6 +108,16 @@ def cost(win: abi.Window, x: abi.Delta | None = None):
     xs = x.as_struct() if x is not None else None
     lib().orc_cost(C.byref(ws), C.byref(xs) if xs is not None else None, _p(c), _p(fc))
     return float(c[0]), float(fc[0])
+
+
+def reduced_system(win: abi.Window, l0: int, l1: int, with_factors: bool, lam: float = 1e-4):
+    """Partial reduced (Schur) system of the landmark range [l0, l1) at x = 0."""
+    ws = win.as_struct()
+    n = C.c_int(0)
+    lib().orc_reduced_system(C.byref(ws), l0, l1, int(with_factors), lam, None, None, C.byref(n))
+    S, g = np.zeros((n.value, n.value)), np.zeros(n.value)
+    lib().orc_reduced_system(C.byref(ws), l0, l1, int(with_factors), lam, _p(S), _p(g), C.byref(n))
+    return S, g
 
 
 def exp_so3(v):

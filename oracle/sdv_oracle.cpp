@@ -16,6 +16,7 @@
 #include "../include/sdv.h"
 #include "factors.hpp"
 
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -1122,6 +1123,116 @@ int orc_cost(const sdv_window *w, const sdv_delta *xd, double *cost, double *fix
     std::vector<double> res(P.nres);
     evaluate(P, x.data(), cost, res.data(), nullptr, 1);
     if (fixed_cost) *fixed_cost = fixed_cost_of(P, x.data());
+    return SDV_OK;
+}
+
+// Reduced (Schur) system at x = 0 restricted to the landmarks [l0, l1) (+ the non-visual factors when with_factors):
+//   S = sum_{obs of those landmarks} Jp^T Jp - sum_l W_l (H_ll + lambda I)^-1 W_l^T  [+ factor J^T J],   g likewise.
+// Used by the multi-process (gloo) test of the landmark sharding: the partial systems of the ranks must add up to the full one.
+// S is n x n row-major (both triangles), columns in the oracle's dense-block order; returns n in *n_out.
+int orc_reduced_system(const sdv_window *w, int l0, int l1, int with_factors, double lambda, double *S, double *g, int *n_out) {
+    Problem P;
+    if (!build_problem(w, P, true)) return SDV_ERR_NUMERICAL_FAILURE;
+    const int n = P.ndense;
+    if (n_out) *n_out = n;
+    if (!S || !g) return SDV_OK;
+    std::vector<double> x(P.nx, 0.0), res(P.nres), jac(P.jsize);
+    double cost;
+    evaluate(P, x.data(), &cost, res.data(), jac.data(), 1);
+    for (size_t i = 0; i < (size_t)n * n; i++) S[i] = 0;
+    for (int i = 0; i < n; i++) g[i] = 0;
+    struct LAcc { M3 V; V3 gl; std::vector<std::pair<int, std::array<double, 18>>> W; bool used = false; };
+    std::vector<LAcc> la(P.L);
+    for (auto &a : la) { a.V = M3::Zero(); a.gl = V3::Zero(); }
+    for (auto &rb : P.rbs) {
+        if (!rb.active) continue;
+        int lm = -1;
+        for (int id : rb.pb)
+            if (id >= P.lmk_id(0) && P.pbs[id].elim) lm = id - P.lmk_id(0);
+        if (lm < 0 && !with_factors) continue;
+        if (lm >= 0 && (lm < l0 || lm >= l1)) continue;
+        size_t o1 = 0;
+        const double *Jl = nullptr;
+        {
+            size_t o = 0;
+            for (int a = 0; a < rb.npb; a++) {
+                if (lm >= 0 && rb.pb[a] == P.lmk_id(lm)) Jl = jac.data() + rb.joff + o;
+                o += (size_t)rb.nres * P.pbs[rb.pb[a]].size;
+            }
+        }
+        const double *r = res.data() + rb.roff;
+        if (Jl) {
+            LAcc &a = la[lm];
+            a.used = true;
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++)
+                    for (int q = 0; q < rb.nres; q++) a.V(i, j) += Jl[q * 3 + i] * Jl[q * 3 + j];
+                for (int q = 0; q < rb.nres; q++) a.gl[i] += Jl[q * 3 + i] * r[q];
+            }
+        }
+        for (int a = 0; a < rb.npb; a++) {
+            const PBlock &pa = P.pbs[rb.pb[a]];
+            const double *Ja = jac.data() + rb.joff + o1;
+            o1 += (size_t)rb.nres * pa.size;
+            if (!pa.active || pa.elim) continue;
+            for (int q = 0; q < rb.nres; q++)
+                for (int i = 0; i < pa.size; i++) g[pa.col + i] += Ja[q * pa.size + i] * r[q];
+            size_t o2 = 0;
+            for (int b = 0; b < rb.npb; b++) {
+                const PBlock &pb = P.pbs[rb.pb[b]];
+                const double *Jb = jac.data() + rb.joff + o2;
+                o2 += (size_t)rb.nres * pb.size;
+                if (!pb.active || pb.elim) continue;
+                for (int i = 0; i < pa.size; i++)
+                    for (int j = 0; j < pb.size; j++) {
+                        double sacc = 0;
+                        for (int q = 0; q < rb.nres; q++) sacc += Ja[q * pa.size + i] * Jb[q * pb.size + j];
+                        S[(size_t)(pa.col + i) * n + pb.col + j] += sacc;
+                    }
+            }
+            if (Jl) {
+                LAcc &acc = la[lm];
+                std::array<double, 18> *Wp = nullptr;
+                for (auto &e : acc.W)
+                    if (e.first == pa.col) Wp = &e.second;
+                if (!Wp) {
+                    acc.W.push_back({pa.col, std::array<double, 18>{}});
+                    Wp = &acc.W.back().second;
+                }
+                for (int i = 0; i < pa.size; i++)
+                    for (int j = 0; j < 3; j++)
+                        for (int q = 0; q < rb.nres; q++) (*Wp)[i * 3 + j] += Ja[q * pa.size + i] * Jl[q * 3 + j];
+            }
+        }
+    }
+    for (int l = l0; l < l1 && l < P.L; l++) {
+        LAcc &a = la[l];
+        if (!a.used) continue;
+        M3 V = a.V;
+        for (int i = 0; i < 3; i++) V(i, i) += lambda;
+        M3 Vi = inverse3(V);
+        for (auto &ea : a.W) {
+            double Y[18];
+            for (int i = 0; i < 6; i++)
+                for (int j = 0; j < 3; j++) {
+                    double sacc = 0;
+                    for (int q = 0; q < 3; q++) sacc += ea.second[i * 3 + q] * Vi(q, j);
+                    Y[i * 3 + j] = sacc;
+                }
+            for (int i = 0; i < 6; i++) {
+                double sacc = 0;
+                for (int q = 0; q < 3; q++) sacc += Y[i * 3 + q] * a.gl[q];
+                g[ea.first + i] -= sacc;
+            }
+            for (auto &eb : a.W)
+                for (int i = 0; i < 6; i++)
+                    for (int j = 0; j < 6; j++) {
+                        double sacc = 0;
+                        for (int q = 0; q < 3; q++) sacc += Y[i * 3 + q] * eb.second[j * 3 + q];
+                        S[(size_t)(ea.first + i) * n + eb.first + j] -= sacc;
+                    }
+        }
+    }
     return SDV_OK;
 }
 

@@ -1,0 +1,563 @@
+// Dense FP64 Cholesky + triangular solves of the reduced (pose/velocity/bias) system in ONE launch:
+// a single thread-block cluster (up to 16 CTAs, hardware cluster barrier ~0.2 us) owns the matrix; tile rows are
+// distributed cyclically over the CTAs.  Per 32-column panel:
+//   A  owner CTA factors the 32x32 diagonal tile in registers (one warp, shuffle broadcast of the pivot column)
+//   -- barrier.cluster --
+//   B  every CTA solves its own tiles of the panel column (register-resident TRSM, one warp per tile)
+//   -- barrier.cluster --
+//   C  every CTA updates its own tile rows of the trailing matrix with FP64 tensor-core MMAs
+//      (mma.sync.m8n8k4.f64 — tcgen05 has no f64 kind, DMMA is the FP64 tensor path on sm_100a)
+// The right-hand side rides along as an extra tile row, so L y = g comes out of phase B; the backward solve
+// L^T z = y runs in the same kernel (left-looking, partial products reduced through global scratch + cluster barrier),
+// followed by the reduced-parameter update and the candidate frame-camera table on cluster rank 0.
+#pragma once
+#include "sdv_kernels.cuh"
+
+namespace sdv {
+
+constexpr int CC_MAX = 16;   // largest cluster used
+constexpr int CCT = 256;     // threads per CTA
+constexpr int TSTR = 33;     // shared-memory tile row stride in doubles: one row per lane is conflict-free (DMMA fragment loads 4-way)
+constexpr unsigned FULL = 0xffffffffu;
+
+SDV_DEV unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+SDV_DEV unsigned cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+SDV_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+SDV_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+SDV_DEV void cluster_sync_all() {
+    cluster_arrive();
+    cluster_wait();
+}
+
+// Software cluster barriers on mbarriers (explicit phase parity, so warps of one CTA may be in different phases —
+// the hardware barrier.cluster tolerates no such skew inside a CTA, which the look-ahead needs).
+SDV_DEV void mbar_remote_arrive(uint64_t *bar, unsigned target_rank) {
+    unsigned local = smem_u32(bar), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(target_rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+SDV_DEV void mbar_arrive_all(uint64_t *bar, int cs) {
+    for (int r = 0; r < cs; r++) mbar_remote_arrive(bar, (unsigned)r);
+}
+SDV_DEV void mbar_wait_cluster(uint64_t *bar, unsigned parity) {
+    // spin at CTA scope (a cluster-scope acquire inside the loop invalidates L1 on every poll), then ONE cluster-scope fence
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "fence.acq_rel.cluster;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+SDV_DEV void dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// The instruction cache matters here: fully unrolled register-array versions of these routines made the kernel ~29k SASS
+// instructions (466 KB), every panel re-fetched its code from L2. The versions below are rolled loops over a tile in
+// shared memory (a few hundred instructions in total).
+
+// In-place Cholesky of the 32x32 tile S (row stride TSTR) by one warp, lane = row. Left-looking; the term of the
+// previous column is taken from registers (shuffle) and the older terms of the NEXT column are accumulated while the
+// reciprocal square root of the current pivot is in flight. sinv[c] = 1 / L[c][c]. Returns false if not positive definite.
+SDV_DEV bool chol32_smem(double *S, double *sinv, int lane) {
+    bool ok = true;
+    double lprev = 0.0;
+    double part = S[lane * TSTR]; // column 0 has no earlier terms
+#pragma unroll 1
+    for (int c = 0; c < 32; c++) {
+        double v = part;
+        if (c > 0) v -= lprev * __shfl_sync(FULL, lprev, c);
+        double d = __shfl_sync(FULL, v, c);
+        if (!(d > 0.0) || !isfinite(d)) {
+            ok = false;
+            d = 1.0;
+        }
+        double inv = rsqrt(d);
+        // older terms of column c+1 (columns <= c-1 are already in shared memory) overlap the rsqrt latency
+        double p0 = 0.0, p1 = 0.0;
+        if (c + 1 < 32) {
+            const double *rr = S + lane * TSTR, *rc = S + (c + 1) * TSTR;
+            p0 = rr[c + 1];
+            int q = 0;
+#pragma unroll 4
+            for (; q + 1 < c; q += 2) {
+                p0 -= rr[q] * rc[q];
+                p1 -= rr[q + 1] * rc[q + 1];
+            }
+            if (q < c) p0 -= rr[q] * rc[q];
+        }
+        double l = lane == c ? d * inv : (lane > c ? v * inv : 0.0);
+        S[lane * TSTR + c] = l;
+        if (lane == c) sinv[c] = inv;
+        lprev = l;
+        part = p0 + p1;
+        __syncwarp();
+    }
+    return ok;
+}
+
+// In-place X <- X L^-T for the tile X (shared memory, row stride TSTR), one row per lane; L and 1/diag in shared memory.
+SDV_DEV void trsm32_smem(double *X, const double *sL, const double *sinv, int lane) {
+    double *xr = X + lane * TSTR;
+    double xprev = 0.0;
+    double part = xr[0];
+#pragma unroll 1
+    for (int c = 0; c < 32; c++) {
+        double v = part;
+        if (c > 0) v -= xprev * sL[c * TSTR + c - 1];
+        double x = v * sinv[c];
+        // older terms of column c+1
+        double p0 = 0.0, p1 = 0.0;
+        if (c + 1 < 32) {
+            const double *rc = sL + (c + 1) * TSTR;
+            p0 = xr[c + 1];
+            int q = 0;
+#pragma unroll 4
+            for (; q + 1 < c; q += 2) {
+                p0 -= xr[q] * rc[q];
+                p1 -= xr[q + 1] * rc[q + 1];
+            }
+            if (q < c) p0 -= xr[q] * rc[q];
+        }
+        xr[c] = x;
+        xprev = x;
+        part = p0 + p1;
+    }
+}
+
+// Register-resident variants (one tile row per lane, fully unrolled: fast issue, large code).
+SDV_DEV bool chol32_reg(double (&a)[32], int lane, double *invd) {
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        double dcc = __shfl_sync(FULL, a[c], c);
+        if (!(dcc > 0.0) || !isfinite(dcc)) {
+            ok = false;
+            dcc = 1.0;
+        }
+        double inv = rsqrt(dcc);
+        double l = a[c] * inv;
+        if (lane == c) {
+            l = dcc * inv;
+            *invd = inv;
+        }
+        a[c] = lane >= c ? l : 0.0;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 32; c2++) {
+            double lc2 = __shfl_sync(FULL, l, c2); // L[c2][c]
+            a[c2] -= l * lc2;
+        }
+    }
+    return ok;
+}
+SDV_DEV void trsm32_reg(double (&a)[32], const double *sL, const double *sinv) {
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        double x = a[c] * sinv[c];
+        a[c] = x;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 32; c2++) a[c2] -= x * sL[c2 * TSTR + c];
+    }
+}
+
+SDV_DEV void load_row32(const double *src, double (&a)[32]) { // 256 contiguous bytes per lane, L2 path (written by other CTAs)
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        double2 v = __ldcg(reinterpret_cast<const double2 *>(src) + q);
+        a[2 * q] = v.x;
+        a[2 * q + 1] = v.y;
+    }
+}
+SDV_DEV void store_row32(double *dst, const double (&a)[32]) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) reinterpret_cast<double2 *>(dst)[q] = make_double2(a[2 * q], a[2 * q + 1]);
+}
+
+// C(32x32, global, leading dim ld) -= A(32x32, shared, stride TSTR) * B(32x32)^T, B from shared (stride TSTR) or global (ld)
+SDV_DEV void tile_update_dmma(double *Cg, int ld, const double *As, const double *Bp, int bstride, bool b_global, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double c[4][4][2];
+#pragma unroll
+    for (int ib = 0; ib < 4; ib++)
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++) {
+            double2 v = *reinterpret_cast<const double2 *>(Cg + (size_t)(ib * 8 + g) * ld + jb * 8 + 2 * t);
+            c[ib][jb][0] = v.x;
+            c[ib][jb][1] = v.y;
+        }
+    double b[4][8];
+#pragma unroll
+    for (int jb = 0; jb < 4; jb++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            const double *p = Bp + (size_t)(jb * 8 + g) * bstride + kk * 4 + t;
+            b[jb][kk] = b_global ? __ldcg(p) : *p;
+        }
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+#pragma unroll
+        for (int ib = 0; ib < 4; ib++) {
+            double a = -As[(ib * 8 + g) * TSTR + kk * 4 + t];
+#pragma unroll
+            for (int jb = 0; jb < 4; jb++) dmma(c[ib][jb][0], c[ib][jb][1], a, b[jb][kk]);
+        }
+    }
+#pragma unroll
+    for (int ib = 0; ib < 4; ib++)
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++)
+            *reinterpret_cast<double2 *>(Cg + (size_t)(ib * 8 + g) * ld + jb * 8 + 2 * t) = make_double2(c[ib][jb][0], c[ib][jb][1]);
+}
+
+// A  : (n_pad + 32) x ld reduced system, lower triangle + right-hand side in row n_pad; overwritten by the trailing updates.
+// Lo : receives L (and y^T = (L^-1 g)^T in row n_pad).  dinv : [n_pad] reciprocal diagonal of L.
+// partial : [T][CC_MAX][32] scratch for the backward solve.
+//
+// Synchronisation per panel k (mbarriers in every CTA's shared memory, remote arrives through DSMEM):
+//   b1[k&1] "L_kk is published"      : count 1 — the owner's warp 0 arrives on every CTA right after factoring the tile
+//   b2      "panel column published" : count CS — each CTA arrives (on every CTA) after its own triangular solves; the owner of
+//                                      tile row k+1 then updates + factors tile (k+1,k+1) BEFORE waiting (look-ahead), the others
+//                                      wait and run their trailing updates, which depend only on their own rows + the panel column.
+template <bool REG>
+__global__ void __launch_bounds__(CCT, 1) k_chol_cluster(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, double *A, double *Lo,
+                                                         double *dinv, double *partial, const double *damp_p, const double *graw_p, double *dxp,
+                                                         int max_rows, double *prof) {
+    if (st->status != 0) return; // uniform over the cluster
+    extern __shared__ __align__(16) double csm[];
+    __shared__ uint64_t b1[2], b2;
+    double *sK = csm;                               // [32][TSTR] diagonal tile L_kk
+    double *sinv = sK + 32 * TSTR;                  // [32]
+    double *sRow = sinv + 32;                       // [max_rows][32][TSTR] own tiles of the current panel column
+    double *xs = sRow + (size_t)max_rows * 32 * TSTR; // [max_rows][32] solved blocks of own tile rows
+    double *wsum = xs + (size_t)max_rows * 32;      // [8][32]
+    const int ld = P.ld, T = P.n_pad / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = (int)cluster_rank(), CS = (int)cluster_size();
+    constexpr int NW = CCT / 32;
+    bool fail = false;
+    // optional phase timing (cycles, summed over panels): [rank][0 wait L_kk, 1 load L_kk, 2 trsm, 3 look-ahead, 4 wait column, 5 update, 6 backward]
+    long long tp[7] = {0, 0, 0, 0, 0, 0, 0}, tc = clock64(), tn;
+#define SDV_TICK(slot) do { tn = clock64(); tp[slot] += tn - tc; tc = tn; } while (0)
+
+    if (threadIdx.x == 0) {
+        mbar_init(&b1[0], 1);
+        mbar_init(&b1[1], 1);
+        mbar_init(&b2, CS);
+    }
+    __syncthreads();
+    cluster_sync_all(); // every CTA's barriers are initialised before anybody arrives remotely
+
+    // k = -1 is the prologue: only the "look-ahead" part runs and factors tile (0,0)
+    for (int k = -1; k < T; k++) {
+        const int owner = (k + CS) % CS, next_owner = (k + 1) % CS;
+        int first = 0, nown = 0;
+        if (k >= 0) {
+            tc = clock64();
+            mbar_wait_cluster(&b1[k & 1], (unsigned)((k >> 1) & 1)); // L_kk and its reciprocal diagonal are visible
+            SDV_TICK(0);
+            if (rank != owner) {
+                for (int e = threadIdx.x; e < 512; e += CCT) {
+                    int r = e >> 4, q = e & 15;
+                    double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(k * 32 + r) * ld + k * 32) + q);
+                    sK[r * TSTR + 2 * q] = v.x;
+                    sK[r * TSTR + 2 * q + 1] = v.y;
+                }
+                if (threadIdx.x < 32) sinv[threadIdx.x] = __ldcg(dinv + k * 32 + threadIdx.x);
+            }
+            __syncthreads();
+            SDV_TICK(1);
+            // ---------------- own tiles of the panel column (rows i > k, i % CS == rank; i == T is the right-hand side)
+            first = k + 1 + ((rank - (k + 1)) % CS + CS) % CS;
+            nown = first <= T ? (T - first) / CS + 1 : 0;
+            for (int s = warp; s < nown; s += NW) {
+                int i = first + s * CS;
+                double *X = sRow + (size_t)s * 32 * TSTR;
+                {
+                    double a[32];
+                    load_row32(A + (size_t)(i * 32 + lane) * ld + k * 32, a);
+                    if (REG) trsm32_reg(a, sK, sinv);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) X[lane * TSTR + c] = a[c];
+                }
+                if (!REG) trsm32_smem(X, sK, sinv, lane);
+                __syncwarp();
+                // publish L_ik, 16 lanes per row -> coalesced 256-byte row segments
+                for (int e = lane; e < 512; e += 32) {
+                    int r = e >> 4, q = e & 15;
+                    reinterpret_cast<double2 *>(Lo + (size_t)(i * 32 + r) * ld + k * 32)[q] = make_double2(X[r * TSTR + 2 * q], X[r * TSTR + 2 * q + 1]);
+                }
+            }
+            __syncthreads();
+            SDV_TICK(2);
+            if (threadIdx.x == 32) mbar_arrive_all(&b2, CS); // this CTA's part of the panel column is published
+        }
+        const bool lookahead = (k + 1 < T) && rank == next_owner; // then slot 0 is tile row k+1, whose only tile is the diagonal
+        if (lookahead && warp == 0) {
+            // tile (k+1,k+1) -= L_{k+1,k} L_{k+1,k}^T with this lane's row in registers, then factor it.
+            // sK still holds L_kk, which this CTA no longer needs (its triangular solves are done), so it is the work tile.
+            {
+                double a[32];
+                load_row32(A + (size_t)((k + 1) * 32 + lane) * ld + (k + 1) * 32, a);
+                if (k >= 0) {
+#pragma unroll 1
+                    for (int q = 0; q < 32; q++) {
+                        double lq = sRow[(size_t)lane * TSTR + q];
+#pragma unroll
+                        for (int c = 0; c < 32; c++) a[c] -= lq * sRow[(size_t)c * TSTR + q];
+                    }
+                }
+                if (REG) {
+                    double inv = 1.0;
+                    if (!chol32_reg(a, lane, &inv)) fail = true;
+                    sinv[lane] = inv;
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c++) sK[lane * TSTR + c] = a[c];
+            }
+            __syncwarp();
+            if (!REG && !chol32_smem(sK, sinv, lane)) fail = true;
+            __syncwarp();
+            dinv[(k + 1) * 32 + lane] = sinv[lane];
+            for (int e = lane; e < 512; e += 32) {
+                int r = e >> 4, q = e & 15;
+                reinterpret_cast<double2 *>(Lo + (size_t)((k + 1) * 32 + r) * ld + (k + 1) * 32)[q] =
+                    make_double2(sK[r * TSTR + 2 * q], sK[r * TSTR + 2 * q + 1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_all(&b1[(k + 1) & 1], CS);
+        }
+        if (k < 0) continue;
+        SDV_TICK(3);
+        mbar_wait_cluster(&b2, (unsigned)(k & 1)); // every L_jk of this panel column is visible
+        SDV_TICK(4);
+        // ---------------- trailing update of own tile rows, tiles (i, j) with k < j <= min(i, T-1)
+        int base = 0; // flat tile index of the first tile of row slot s
+        for (int s = lookahead ? 1 : 0; s < nown; s++) {
+            int i = first + s * CS;
+            int nj = min(i, T - 1) - k;
+            int q0 = ((warp - base) % NW + NW) % NW;
+            for (int q = q0; q < nj; q += NW) {
+                int j = k + 1 + q;
+                bool j_own = (j % CS) == rank; // then L_jk sits in sRow as well
+                const double *Bp = j_own ? sRow + (size_t)((j - first) / CS) * 32 * TSTR : Lo + (size_t)(j * 32) * ld + k * 32;
+                tile_update_dmma(A + (size_t)(i * 32) * ld + j * 32, ld, sRow + (size_t)s * 32 * TSTR, Bp, j_own ? TSTR : ld, !j_own, lane);
+            }
+            base += nj;
+        }
+        __syncthreads(); // sRow / sK are rewritten in the next panel
+        SDV_TICK(5);
+    }
+    if (fail) acc->chol_fail = 1;
+    cluster_sync_all();
+    const bool bad = __ldcg(&acc->chol_fail) != 0 || __ldcg(&acc->schur_fail) != 0; // same answer on every CTA
+    if (bad) {
+        if (rank == 0 && threadIdx.x == 0) {
+            st->step_valid = 0;
+            st->model_cost_change = 0.0;
+        }
+        return;
+    }
+    // ---------------- backward solve L^T z = y, left-looking over tile columns
+    const double *y = Lo + (size_t)(T * 32) * ld;
+    tc = clock64();
+    for (int k = T - 1; k >= 0; k--) {
+        const int owner = k % CS;
+        __syncthreads(); // xs of the previous step visible to every warp
+        const int first = k + 1 + ((rank - (k + 1)) % CS + CS) % CS;
+        double s = 0.0;
+        for (int i = first + warp * CS; i < T; i += NW * CS) {
+            const double *Lt = Lo + (size_t)(i * 32) * ld + k * 32 + lane;
+            const double *xi = xs + (size_t)(i / CS) * 32;
+            double v[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r] = __ldcg(Lt + (size_t)r * ld); // 32 independent L2 loads in flight
+#pragma unroll
+            for (int r = 0; r < 32; r++) s += v[r] * xi[r];
+        }
+        wsum[warp * 32 + lane] = s;
+        if (rank == owner) { // the diagonal tile for the triangular solve
+            for (int e = threadIdx.x; e < 512; e += CCT) {
+                int r = e >> 4, q = e & 15;
+                double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(k * 32 + r) * ld + k * 32) + q);
+                sK[r * TSTR + 2 * q] = v.x;
+                sK[r * TSTR + 2 * q + 1] = v.y;
+            }
+            if (threadIdx.x < 32) sinv[threadIdx.x] = __ldcg(dinv + k * 32 + threadIdx.x);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; w2++) tot += wsum[w2 * 32 + lane];
+            partial[((size_t)k * CC_MAX + rank) * 32 + lane] = tot;
+        }
+        cluster_sync_all();
+        if (rank == owner && warp == 0) {
+            double yy = __ldcg(y + k * 32 + lane);
+            for (int r = 0; r < CS; r++) yy -= __ldcg(partial + ((size_t)k * CC_MAX + r) * 32 + lane);
+            double x = 0;
+#pragma unroll
+            for (int c = 31; c >= 0; c--) {
+                double xc = __shfl_sync(FULL, yy, c) * sinv[c];
+                if (lane == c) x = xc;
+                if (lane < c) yy -= sK[c * TSTR + lane] * xc;
+            }
+            xs[(size_t)(k / CS) * 32 + lane] = x;
+            dxp[k * 32 + lane] = -x; // S delta = -g
+        }
+    }
+    cluster_sync_all();
+    SDV_TICK(6);
+    if (prof && threadIdx.x == 0)
+        for (int q = 0; q < 7; q++) prof[rank * 8 + q] = (double)tp[q];
+    if (rank != 0) return;
+    // ---------------- reduced-parameter update, model-decrease terms, candidate frame-camera table (cluster rank 0)
+    const LinBuf &Bx = st->cur ? B1 : B0;
+    const LinBuf &Bc = st->cur ? B0 : B1;
+    const int n = P.n;
+    double gd = 0, dd = 0, sn = 0, cn = 0;
+    for (int i = threadIdx.x; i < P.n_pad; i += CCT) {
+        double d = i < n ? __ldcg(dxp + i) : 0.0;
+        if (i >= n) dxp[i] = 0.0;
+        double xc = Bx.xp[i] + d;
+        Bc.xp[i] = i < n ? xc : 0.0;
+        if (i < n) {
+            gd += graw_p[i] * d;
+            dd += damp_p[i] * d * d;
+            sn += d * d;
+            cn += xc * xc;
+        }
+    }
+    gd = warp_sum(gd);
+    dd = warp_sum(dd);
+    sn = warp_sum(sn);
+    cn = warp_sum(cn);
+    if (lane == 0 && P.rank == 0) {
+        atomicAdd(&acc->model_gd, gd);
+        atomicAdd(&acc->model_dd, dd);
+        atomicAdd(&acc->step_norm2, sn);
+        atomicAdd(&acc->cand_norm2, cn);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.F * P.C; i += CCT) compute_fct_row(P, Bc.xp, i / P.C, i % P.C, Bc.fct + (size_t)i * FCT_ROW);
+    if (threadIdx.x == 0) st->step_valid = 1;
+}
+
+
+// Developer micro-benchmark: cycles of the tile routines, single warp, 5 repetitions each (the first one has cold code).
+// out[routine * 8 + rep]; routines: 0 chol32_reg, 1 chol32_smem, 2 trsm32_reg, 3 trsm32_smem, 4 diag update (rolled q),
+// 5 tile_update_dmma (C in global), 6 load_row32 (L2), 7 store tile rows
+__global__ void k_chol_micro(double *scratch /* >= 4 * 32 * 64 doubles */, double *out) {
+    __shared__ double sA[32 * TSTR], sL[32 * TSTR], sinv[32], sX[32 * TSTR];
+    const int lane = threadIdx.x;
+    // SPD tile: 40 I + small symmetric part
+    for (int c = 0; c < 32; c++) sA[lane * TSTR + c] = (lane == c ? 40.0 : 0.0) + 0.01 * ((lane * 7 + c * 3) % 11 + (c * 7 + lane * 3) % 11);
+    __syncwarp();
+    for (int e = lane; e < 32 * 64; e += 32) scratch[e] = 0.001 * (e % 97);
+    __syncwarp();
+    double sink = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        long long t0, t1;
+        {   // 0: chol32_reg
+            double a[32], inv = 1;
+            for (int c = 0; c < 32; c++) a[c] = sA[lane * TSTR + c];
+            __syncwarp();
+            t0 = clock64();
+            chol32_reg(a, lane, &inv);
+            t1 = clock64();
+            for (int c = 0; c < 32; c++) sL[lane * TSTR + c] = a[c];
+            sinv[lane] = inv;
+            sink += a[lane & 31 ? 1 : 0];
+            if (lane == 0) out[0 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+        {   // 1: chol32_smem
+            for (int c = 0; c < 32; c++) sX[lane * TSTR + c] = sA[lane * TSTR + c];
+            __syncwarp();
+            t0 = clock64();
+            chol32_smem(sX, sinv, lane);
+            t1 = clock64();
+            if (lane == 0) out[1 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+        {   // 2: trsm32_reg
+            double a[32];
+            for (int c = 0; c < 32; c++) a[c] = sA[lane * TSTR + c];
+            t0 = clock64();
+            trsm32_reg(a, sL, sinv);
+            t1 = clock64();
+            sink += a[3];
+            if (lane == 0) out[2 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+        {   // 3: trsm32_smem
+            for (int c = 0; c < 32; c++) sX[lane * TSTR + c] = sA[lane * TSTR + c];
+            __syncwarp();
+            t0 = clock64();
+            trsm32_smem(sX, sL, sinv, lane);
+            t1 = clock64();
+            sink += sX[lane * TSTR + 5];
+            if (lane == 0) out[3 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+        {   // 4: diag update, rolled over q
+            double a[32];
+            for (int c = 0; c < 32; c++) a[c] = sA[lane * TSTR + c];
+            t0 = clock64();
+#pragma unroll 1
+            for (int q = 0; q < 32; q++) {
+                double lq = sL[lane * TSTR + q];
+#pragma unroll
+                for (int c = 0; c < 32; c++) a[c] -= lq * sL[c * TSTR + q];
+            }
+            t1 = clock64();
+            sink += a[7];
+            if (lane == 0) out[4 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+        {   // 5: DMMA tile update with C in global memory, B in shared
+            t0 = clock64();
+            tile_update_dmma(scratch, 64, sL, sA, TSTR, false, lane);
+            t1 = clock64();
+            if (lane == 0) out[5 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+        {   // 6: load one row per lane from L2
+            double a[32];
+            t0 = clock64();
+            load_row32(scratch + (size_t)lane * 64, a);
+            sink += a[9] + a[31];
+            t1 = clock64();
+            if (lane == 0) out[6 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+        {   // 7: coalesced tile store
+            t0 = clock64();
+            for (int e = lane; e < 512; e += 32) {
+                int r = e >> 4, q = e & 15;
+                reinterpret_cast<double2 *>(scratch + (size_t)r * 64 + 32)[q] = make_double2(sL[r * TSTR + 2 * q], sL[r * TSTR + 2 * q + 1]);
+            }
+            t1 = clock64();
+            if (lane == 0) out[7 * 8 + rep] = (double)(t1 - t0);
+            __syncwarp();
+        }
+    }
+    if (sink == 123.456) out[63] = sink;
+}
+
+} // namespace sdv

@@ -203,24 +203,22 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf
     __shared__ uint64_t bar;
     __shared__ double red[LIN_THREADS / 32];
     const double *fct = B.fct;
-    const int Oloc = P.o1 - P.o0;
+    const int Oloc = P.o1 - P.o0, OC = P.Ocap;
+    int fstride = FCT_ROW;
     if (P.fct_in_smem) {
+        // one TMA bulk copy per 256-byte table row into rows padded to 34 doubles: lanes of a warp touch up to 8 different
+        // rows at the same offset, an unpadded (32-double) stride would put them all in the same bank
         double *sf = reinterpret_cast<double *>(smem_raw);
-        uint32_t bytes = (uint32_t)(P.F * P.C * FCT_ROW * sizeof(double));
+        const int nrows = P.F * P.C;
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, bytes);
-            uint32_t off = 0;
-            while (off < bytes) { // <= 32 KiB per bulk copy
-                uint32_t chunk = min(bytes - off, 32768u);
-                bulk_g2s(reinterpret_cast<unsigned char *>(sf) + off, reinterpret_cast<const unsigned char *>(B.fct) + off, chunk,
-                         &bar);
-                off += chunk;
-            }
-        }
+        if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)(nrows * FCT_ROW * sizeof(double)));
+        if (threadIdx.x < 32)
+            for (int r = threadIdx.x; r < nrows; r += 32)
+                bulk_g2s(sf + (size_t)r * FCT_SROW, B.fct + (size_t)r * FCT_ROW, (uint32_t)(FCT_ROW * sizeof(double)), &bar);
         mbar_wait(&bar, 0);
         fct = sf;
+        fstride = FCT_SROW;
     }
     double csum = 0.0;
     for (int base = blockIdx.x * LIN_THREADS; base < Oloc; base += gridDim.x * LIN_THREADS) {
@@ -234,15 +232,15 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf
             meas[0] = P.obs_meas[o];
             meas[1] = P.obs_meas[(size_t)P.O + o];
             meas[2] = KIND == 0 ? P.obs_meas[2 * (size_t)P.O + o] : 0.0;
-            const double *row = fct + (size_t)fc * FCT_ROW;
+            const double *row = fct + (size_t)fc * fstride;
             double w = P.obs_w ? P.obs_w[o] : row[30];
             eval_visual<KIND>(row, P.K + 4 * (fc % P.C), w, p, meas, r, Jp, Jl);
             B.r[ol] = r[0];
-            B.r[(size_t)Oloc + ol] = r[1];
+            B.r[(size_t)OC + ol] = r[1];
 #pragma unroll
-            for (int k = 0; k < 12; k++) B.Jp[(size_t)k * Oloc + ol] = Jp[k];
+            for (int k = 0; k < 12; k++) B.Jp[(size_t)k * OC + ol] = Jp[k];
 #pragma unroll
-            for (int k = 0; k < 6; k++) B.Jl[(size_t)k * Oloc + ol] = Jl[k];
+            for (int k = 0; k < 6; k++) B.Jl[(size_t)k * OC + ol] = Jl[k];
             csum += r[0] * r[0] + r[1] * r[1];
         }
     }
@@ -596,10 +594,160 @@ __global__ void __launch_bounds__(FAC_WARPS * 32) k_lin_factors(DevProblem P, Li
             else fcost += s * s;
         }
     }
+    // ---- sparsified prior: IMUPriordx (residuals.hpp:634-700), Landmark3DPrior (:506-526), LandmarkToLandmark (:528-559)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.sp_has_imu) {
+        const int f = P.sp_frame;
+        const double *blob = P.sp_blob;
+        double dx[6], dv[3], dba[3], dbg[3];
+        frame_params(P, B.xp, f, dx, dv, dba, dbg);
+        double Rb[9], tb[3], Rp[9], tp[3], dR[9], R[9], t[3], tmp[3];
+        load_RT(P.T_f_w + 12 * f, Rb, tb);
+        load_RT(blob, Rp, tp);
+        exp_so3(dx, dR);
+        mat3_mul(Rb, dR, R);
+        mat3_vec(Rb, dx + 3, tmp);
+        t[0] = tmp[0] + tb[0]; t[1] = tmp[1] + tb[1]; t[2] = tmp[2] + tb[2];
+        double RRt[9], w[3], c3[3], Rc[3], e[15];
+        mat3_mulT(R, Rp, RRt);
+        log_so3(RRt, w);
+        matT3_vec(Rp, tp, c3);
+        mat3_vec(R, c3, Rc);
+        for (int k = 0; k < 3; k++) {
+            e[k] = w[k];
+            e[3 + k] = t[k] - Rc[k];
+            e[6 + k] = P.v[3 * f + k] + dv[k] - blob[12 + k];
+            e[9 + k] = P.ba[3 * f + k] + dba[k] - blob[15 + k];
+            e[12 + k] = P.bg[3 * f + k] + dbg[k] - blob[18 + k];
+        }
+        const double *SQ = blob + 21; // 15x15
+        double Jrw[9], JrwInv[9], Jrd[9], M1[9], J00[9], J30[9], S3[9];
+        right_jacobian(w, Jrw);
+        inverse3(Jrw, JrwInv);
+        right_jacobian(dx, Jrd);
+        mat3_mul(JrwInv, Rp, M1);
+        mat3_mul(M1, Jrd, J00);
+        skew3(c3, S3);
+        mat3_mul(R, S3, M1);
+        mat3_mul(M1, Jrd, J30);
+        double s = 0;
+        for (int i = 0; i < 15; i++) {
+            double ri = 0;
+            for (int k = 0; k < 15; k++) ri += SQ[i * 15 + k] * e[k];
+            B.sp_r[i] = ri;
+            s += ri * ri;
+            // pose block: sqrt_inf * [J00 0; J30 Rb; 0 0]
+            for (int c = 0; c < 3; c++) {
+                double a = 0, bb = 0;
+                for (int k = 0; k < 3; k++) {
+                    a += SQ[i * 15 + k] * J00[k * 3 + c] + SQ[i * 15 + 3 + k] * J30[k * 3 + c];
+                    bb += SQ[i * 15 + 3 + k] * Rb[k * 3 + c];
+                }
+                B.sp_J[i * 15 + c] = a;
+                B.sp_J[i * 15 + 3 + c] = bb;
+            }
+            // reference quirk (residuals.hpp:676-692): the v / ba / bg Jacobians are identity blocks, NOT whitened
+            for (int c = 6; c < 15; c++) B.sp_J[i * 15 + c] = (i == c) ? 1.0 : 0.0;
+        }
+        if (P.pose_col[f] >= 0 || P.vb_col[f] >= 0) cost += s;
+        else fcost += s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 1 && P.sp_has_lmk) {
+        const double *blob = P.sp_blob;
+        double p[3];
+        landmark_position(P, B, P.sp_lmk0, p);
+        double d[3] = {p[0] - blob[246], p[1] - blob[247], p[2] - blob[248]};
+        const double *SQ = blob + 249;
+        for (int i = 0; i < 3; i++) {
+            double ri = SQ[i * 3] * d[0] + SQ[i * 3 + 1] * d[1] + SQ[i * 3 + 2] * d[2];
+            B.sp_r[15 + i] = ri;
+            cost += ri * ri;
+        }
+    }
+    {
+        int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+        for (int k = tid; k < P.sp_nl2l; k += nt) {
+            double pa[3], pb[3];
+            landmark_position(P, B, P.sp_l2l_a[k], pa);
+            landmark_position(P, B, P.sp_l2l_b[k], pb);
+            double d[3] = {pa[0] - pb[0] - P.sp_l2l_delta[3 * k], pa[1] - pb[1] - P.sp_l2l_delta[3 * k + 1], pa[2] - pb[2] - P.sp_l2l_delta[3 * k + 2]};
+            const double *SQ = P.sp_l2l_sqrt + 9 * k;
+            for (int i = 0; i < 3; i++) {
+                double ri = SQ[i * 3] * d[0] + SQ[i * 3 + 1] * d[1] + SQ[i * 3 + 2] * d[2];
+                B.sp_r[18 + 3 * k + i] = ri;
+                cost += ri * ri;
+            }
+        }
+    }
     cost = warp_sum(cost);
     if (lane == 0 && cost != 0.0) atomicAdd(&acc->cost[b], 0.5 * cost);
     fcost = warp_sum(fcost);
     if (lane == 0 && fcost != 0.0 && which == 0) atomicAdd(&acc->fixed_cost, 0.5 * fcost);
+}
+
+// PoseToLandmarkFactor (residuals.hpp:561-599): 3 residuals on (kept frame pose, landmark). The landmark stays in the
+// eliminated set, so each factor is written as TWO pseudo-observations (rows 0-1 and row 2 + a zero row) into the r / J
+// planes of the owning rank and flows through the same per-landmark Schur machinery as the visual factors.
+__global__ void k_lin_p2l(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, int which) {
+    if (st->status != 0) return;
+    if (which == -2 && !st->step_valid) return;
+    int b = which >= 0 ? which : (which == -1 ? st->cur : 1 - st->cur);
+    const LinBuf &B = b ? B1 : B0;
+    const int OC = P.Ocap;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double cost = 0.0;
+    if (k < P.sp_np2l && P.sp_p2l_plane[k] >= 0) {
+        const int f = P.sp_frame, l = P.sp_p2l_lmk[k], pl = P.sp_p2l_plane[k];
+        double dx[6], d3[3], e3[3], f3[3];
+        frame_params(P, B.xp, f, dx, d3, e3, f3);
+        double Rb[9], tb[3], dR[9], R[9], t[3], tmp[3], p[3];
+        load_RT(P.T_f_w + 12 * f, Rb, tb);
+        exp_so3(dx, dR);
+        mat3_mul(Rb, dR, R);
+        mat3_vec(Rb, dx + 3, tmp);
+        t[0] = tmp[0] + tb[0]; t[1] = tmp[1] + tb[1]; t[2] = tmp[2] + tb[2];
+        landmark_position(P, B, l, p);
+        double Tp[3];
+        mat3_vec(R, p, Tp);
+        const double *SQ = P.sp_p2l_sqrt + 9 * k, *dl = P.sp_p2l_delta + 3 * k;
+        double e[3] = {Tp[0] + t[0] - dl[0], Tp[1] + t[1] - dl[1], Tp[2] + t[2] - dl[2]};
+        double r[3], SR[9], Jrot[9], Jtr[9], Jl[9], S3[9], Jr[9], M1[9], M2[9];
+        mat3_vec(SQ, e, r);
+        mat3_mul(SQ, Rb, SR);          // sqrt_inf * R_base
+        skew3(p, S3);
+        right_jacobian(dx, Jr);
+        mat3_mul(dR, S3, M1);
+        mat3_mul(M1, Jr, M2);          // dR [t]x Jr(dw)
+        mat3_mul(SR, M2, Jrot);
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            Jrot[q] = -Jrot[q];
+            Jtr[q] = SR[q];
+        }
+        mat3_mul(SQ, R, Jl);           // sqrt_inf * R
+        // pseudo-observation a: rows 0,1 ; pseudo-observation b: row 2 and a zero row
+        B.r[pl] = r[0];
+        B.r[(size_t)OC + pl] = r[1];
+        B.r[pl + 1] = r[2];
+        B.r[(size_t)OC + pl + 1] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            B.Jp[(size_t)c * OC + pl] = Jrot[c];
+            B.Jp[(size_t)(3 + c) * OC + pl] = Jtr[c];
+            B.Jp[(size_t)(6 + c) * OC + pl] = Jrot[3 + c];
+            B.Jp[(size_t)(9 + c) * OC + pl] = Jtr[3 + c];
+            B.Jl[(size_t)c * OC + pl] = Jl[c];
+            B.Jl[(size_t)(3 + c) * OC + pl] = Jl[3 + c];
+            B.Jp[(size_t)c * OC + pl + 1] = Jrot[6 + c];
+            B.Jp[(size_t)(3 + c) * OC + pl + 1] = Jtr[6 + c];
+            B.Jp[(size_t)(6 + c) * OC + pl + 1] = 0.0;
+            B.Jp[(size_t)(9 + c) * OC + pl + 1] = 0.0;
+            B.Jl[(size_t)c * OC + pl + 1] = Jl[6 + c];
+            B.Jl[(size_t)(3 + c) * OC + pl + 1] = 0.0;
+        }
+        cost = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    }
+    cost = warp_sum(cost);
+    if ((threadIdx.x & 31) == 0 && cost != 0.0) atomicAdd(&acc->cost[b], 0.5 * cost);
 }
 
 // =====================================================================================================================
@@ -615,7 +763,7 @@ struct SlotAcc {
 
 // accumulates this slot's observations; hl (xx,xy,xz,yy,yz,zz) and gl receive the landmark-block parts
 SDV_DEV void slot_accumulate(const DevProblem &P, const LinBuf &B, int slot, SlotAcc &a, double *hl, double *gl) {
-    const int Oloc = P.o1 - P.o0;
+    const int Oloc = P.Ocap;
 #pragma unroll
     for (int k = 0; k < 18; k++) a.W[k] = 0.0;
 #pragma unroll
@@ -623,7 +771,7 @@ SDV_DEV void slot_accumulate(const DevProblem &P, const LinBuf &B, int slot, Slo
 #pragma unroll
     for (int k = 0; k < 6; k++) a.gp[k] = 0.0;
     for (int q = P.slot_obs_ptr[slot]; q < P.slot_obs_ptr[slot + 1]; q++) {
-        int ol = P.slot_obs[q] - P.o0;
+        int ol = P.slot_obs[q];
         double Jp[12], Jl[6], r0 = B.r[ol], r1 = B.r[(size_t)Oloc + ol];
 #pragma unroll
         for (int k = 0; k < 12; k++) Jp[k] = B.Jp[(size_t)k * Oloc + ol];
@@ -652,13 +800,13 @@ SDV_DEV void slot_accumulate(const DevProblem &P, const LinBuf &B, int slot, Slo
 // light variant for back-substitution: hl, gl and e = sum Jl^T (Jp delta_f)
 SDV_DEV void slot_accumulate_back(const DevProblem &P, const LinBuf &B, int slot, const double *dxp, double *hl, double *gl,
                                   double *e) {
-    const int Oloc = P.o1 - P.o0;
+    const int Oloc = P.Ocap;
     int pc = P.pose_col[P.slot_frame[slot]];
     double d[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) d[k] = pc >= 0 ? dxp[pc + k] : 0.0;
     for (int q = P.slot_obs_ptr[slot]; q < P.slot_obs_ptr[slot + 1]; q++) {
-        int ol = P.slot_obs[q] - P.o0;
+        int ol = P.slot_obs[q];
         double Jl[6], r0 = B.r[ol], r1 = B.r[(size_t)Oloc + ol];
         double u0 = 0, u1 = 0;
 #pragma unroll
@@ -692,16 +840,27 @@ SDV_DEV double lm_damping(double c, double s, double radius, const SolverOpts &o
 constexpr int SCH_WARPS = 4;
 constexpr int MAX_SLOTS = 32; // distinct keyframes one landmark may be seen from (checked at upload)
 
+// sum over the G lanes of a landmark group (G = 8, 16 or 32 consecutive lanes)
+template <int G> SDV_DEV double group_sum(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // Layout of the reduced-system buffer Sb: rows [0, n_pad) = S (lower triangle used), row n_pad = g (right-hand side),
 // row n_pad+1 = diag(J^T J) of the reduced columns (before damping), row n_pad+2 = raw gradient of the reduced columns.
-// One warp per landmark: lane s owns slot s (= one keyframe seeing the landmark).
+// G lanes per landmark (32/G landmarks per warp): lane s of a group owns slot s (= one keyframe seeing the landmark).
+template <int G>
 __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt,
                                                           double *Sb, double *scale_l) {
     if (st->status != 0) return;
     const LinBuf &B = st->cur ? B1 : B0;
-    __shared__ double WY[SCH_WARPS][MAX_SLOTS][36];
-    __shared__ int scol[SCH_WARPS][MAX_SLOTS];
+    constexpr int GPW = 32 / G;             // landmark groups per warp
+    constexpr int GPB = SCH_WARPS * GPW;    // per block
+    __shared__ double WY[GPB][G][36];
+    __shared__ int scol[GPB][G];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lig = lane % G, gib = wib * GPW + lane / G; // lane in group, group in block
     const int ld = P.ld;
     double *g = Sb + (size_t)P.n_pad * ld;
     double *cdiag = g + ld;
@@ -709,23 +868,27 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B
     const double radius = st->radius;
     const bool first = st->scaling_done == 0;
     double gmax = 0.0;
-    for (int l = P.l0 + blockIdx.x * SCH_WARPS + wib; l < P.l1; l += gridDim.x * SCH_WARPS) {
-        const int s0 = P.slot_ptr[l], m = P.slot_ptr[l + 1] - s0;
+    const int nl = P.l1 - P.l0;
+    for (int lb = blockIdx.x * GPB; lb < nl; lb += gridDim.x * GPB) { // block-uniform trip count
+        const int l = P.l0 + lb + gib;
+        const bool valid = (lb + gib) < nl;
+        const int s0 = valid ? P.slot_ptr[l] : 0, m = valid ? P.slot_ptr[l + 1] - s0 : 0;
         SlotAcc a;
         double hl[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
         int col = -1;
-        if (lane < m) {
-            slot_accumulate(P, B, s0 + lane, a, hl, gl);
-            col = P.pose_col[P.slot_frame[s0 + lane]];
+        if (lig < m) {
+            slot_accumulate(P, B, s0 + lig, a, hl, gl);
+            col = P.pose_col[P.slot_frame[s0 + lig]];
         }
 #pragma unroll
-        for (int k = 0; k < 6; k++) hl[k] = warp_sum(hl[k]);
+        for (int k = 0; k < 6; k++) hl[k] = group_sum<G>(hl[k]);
 #pragma unroll
-        for (int k = 0; k < 3; k++) gl[k] = warp_sum(gl[k]);
-        const int dc = P.lmk_col[l];
-        if (dc >= 0) {
+        for (int k = 0; k < 3; k++) gl[k] = group_sum<G>(gl[k]);
+        const int dc = valid ? P.lmk_col[l] : -1;
+        bool eliminate = valid && dc < 0;
+        if (valid && dc >= 0) {
             // kept (dense) landmark: its columns live in the reduced system, no elimination
-            if (lane < m && col >= 0) {
+            if (lig < m && col >= 0) {
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
 #pragma unroll
@@ -740,7 +903,7 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B
                     }
                 }
             }
-            if (lane == 0) {
+            if (lig == 0) {
                 const int ii[6] = {0, 1, 2, 1, 2, 2}, jj[6] = {0, 0, 0, 1, 1, 2};
                 const double hv[6] = {hl[0], hl[1], hl[2], hl[3], hl[4], hl[5]};
                 for (int k = 0; k < 6; k++) atomicAdd(&Sb[(size_t)(dc + ii[k]) * ld + dc + jj[k]], hv[k]);
@@ -752,33 +915,34 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B
                     atomicAdd(&graw[dc + k], gl[k]);
                 }
             }
-            continue;
         }
         // ---- eliminated landmark
-        double s3[3];
-        if (first) {
-            s3[0] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[0])) : 1.0;
-            s3[1] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[3])) : 1.0;
-            s3[2] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[5])) : 1.0;
-            if (lane == 0) {
-                scale_l[3 * (size_t)l] = s3[0];
-                scale_l[3 * (size_t)l + 1] = s3[1];
-                scale_l[3 * (size_t)l + 2] = s3[2];
+        double Vi[6] = {0, 0, 0, 0, 0, 0};
+        if (eliminate) {
+            double s3[3];
+            if (first) {
+                s3[0] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[0])) : 1.0;
+                s3[1] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[3])) : 1.0;
+                s3[2] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[5])) : 1.0;
+                if (lig == 0) {
+                    scale_l[3 * (size_t)l] = s3[0];
+                    scale_l[3 * (size_t)l + 1] = s3[1];
+                    scale_l[3 * (size_t)l + 2] = s3[2];
+                }
+            } else {
+                s3[0] = scale_l[3 * (size_t)l];
+                s3[1] = scale_l[3 * (size_t)l + 1];
+                s3[2] = scale_l[3 * (size_t)l + 2];
             }
-        } else {
-            s3[0] = scale_l[3 * (size_t)l];
-            s3[1] = scale_l[3 * (size_t)l + 1];
-            s3[2] = scale_l[3 * (size_t)l + 2];
+            gmax = fmax(gmax, fmax(fabs(gl[0]), fmax(fabs(gl[1]), fabs(gl[2]))));
+            double V[6] = {hl[0] + lm_damping(hl[0], s3[0], radius, opt), hl[1], hl[2], hl[3] + lm_damping(hl[3], s3[1], radius, opt), hl[4],
+                           hl[5] + lm_damping(hl[5], s3[2], radius, opt)};
+            if (!sym3_inverse(V, Vi)) {
+                if (lig == 0) acc->schur_fail = 1;
+                eliminate = false;
+            }
         }
-        gmax = fmax(gmax, fmax(fabs(gl[0]), fmax(fabs(gl[1]), fabs(gl[2]))));
-        double V[6] = {hl[0] + lm_damping(hl[0], s3[0], radius, opt), hl[1], hl[2], hl[3] + lm_damping(hl[3], s3[1], radius, opt), hl[4],
-                       hl[5] + lm_damping(hl[5], s3[2], radius, opt)};
-        double Vi[6];
-        if (!sym3_inverse(V, Vi)) {
-            if (lane == 0) acc->schur_fail = 1;
-            continue;
-        }
-        if (lane < m) {
+        if (eliminate && lig < m) {
             // Y = W V^-1
             double Y[18];
 #pragma unroll
@@ -790,10 +954,10 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B
             }
 #pragma unroll
             for (int k = 0; k < 18; k++) {
-                WY[wib][lane][k] = a.W[k];
-                WY[wib][lane][18 + k] = Y[k];
+                WY[gib][lig][k] = a.W[k];
+                WY[gib][lig][18 + k] = Y[k];
             }
-            scol[wib][lane] = col;
+            scol[gib][lig] = col;
             if (col >= 0) {
                 // own diagonal block (lower triangle), right-hand side, diag(J^T J), raw gradient
 #pragma unroll
@@ -810,30 +974,28 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B
             }
         }
         __syncwarp();
-        // off-diagonal pairs (a > b in slot order), 36 entries each, spread over the lanes
-        const int npairs = m * (m - 1) / 2;
-        for (int e = lane; e < npairs * 36; e += 32) {
-            int pi = e / 36, ij = e - pi * 36;
-            int sa = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pi)) * 0.5f);
-            while (sa * (sa - 1) / 2 > pi) sa--;
-            while ((sa + 1) * sa / 2 <= pi) sa++;
-            int sb = pi - sa * (sa - 1) / 2;
-            int ca = scol[wib][sa], cb = scol[wib][sb];
-            if (ca < 0 || cb < 0) continue;
-            int i = ij / 6, j = ij - i * 6;
-            const double *Ya = &WY[wib][sa][18 + i * 3];
-            const double *Wb = &WY[wib][sb][j * 3];
-            double v = -(Ya[0] * Wb[0] + Ya[1] * Wb[1] + Ya[2] * Wb[2]);
-            if (ca > cb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cb + j], v);
-            else atomicAdd(&Sb[(size_t)(cb + j) * ld + ca + i], v);
+        // off-diagonal pairs (a > b in slot order), 36 entries each, spread over the G lanes of the group
+        if (eliminate) {
+            const int npairs = m * (m - 1) / 2;
+            for (int e = lig; e < npairs * 36; e += G) {
+                int pi = e / 36, ij = e - pi * 36;
+                int sa = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pi)) * 0.5f);
+                while (sa * (sa - 1) / 2 > pi) sa--;
+                while ((sa + 1) * sa / 2 <= pi) sa++;
+                int sb = pi - sa * (sa - 1) / 2;
+                int ca = scol[gib][sa], cb = scol[gib][sb];
+                if (ca < 0 || cb < 0) continue;
+                int i = ij / 6, j = ij - i * 6;
+                const double *Ya = &WY[gib][sa][18 + i * 3];
+                const double *Wb = &WY[gib][sb][j * 3];
+                double v = -(Ya[0] * Wb[0] + Ya[1] * Wb[1] + Ya[2] * Wb[2]);
+                if (ca > cb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cb + j], v);
+                else atomicAdd(&Sb[(size_t)(cb + j) * ld + ca + i], v);
+            }
         }
         __syncwarp();
     }
-    gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));
-    gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 8));
-    gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
-    gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
-    gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 1));
+    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if (lane == 0 && gmax > 0.0) atomic_max_nonneg(reinterpret_cast<double *>(&acc->grad_max_bits), gmax);
 }
 
@@ -945,6 +1107,78 @@ __global__ void __launch_bounds__(FAC_WARPS * 32) k_assemble_factors(DevProblem 
             }
             atomicAdd(&g[ra], s);
             atomicAdd(&graw[ra], s);
+        }
+    }
+}
+
+// (k_assemble_factors continues in k_assemble_sparse for the sparsified prior)
+__global__ void k_assemble_sparse(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, double *Sb) {
+    if (st->status != 0 || P.rank != 0) return;
+    const LinBuf &B = st->cur ? B1 : B0;
+    const int ld = P.ld;
+    double *g = Sb + (size_t)P.n_pad * ld, *cdiag = g + ld, *graw = cdiag + ld;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    if (P.sp_has_imu) {
+        const int f = P.sp_frame, pc = P.pose_col[f], vc = P.vb_col[f];
+        for (int e = tid; e < 15 * 16; e += nt) {
+            int a = e / 16, bcol = e - a * 16;
+            int ra = a < 6 ? (pc >= 0 ? pc + a : -1) : (vc >= 0 ? vc + a - 6 : -1);
+            if (ra < 0) continue;
+            double s = 0;
+            if (bcol == 15) {
+                for (int i = 0; i < 15; i++) s += B.sp_J[i * 15 + a] * B.sp_r[i];
+                atomicAdd(&g[ra], s);
+                atomicAdd(&graw[ra], s);
+            } else {
+                int rb = bcol < 6 ? (pc >= 0 ? pc + bcol : -1) : (vc >= 0 ? vc + bcol - 6 : -1);
+                if (rb < 0 || ra < rb) continue;
+                for (int i = 0; i < 15; i++) s += B.sp_J[i * 15 + a] * B.sp_J[i * 15 + bcol];
+                atomicAdd(&Sb[(size_t)ra * ld + rb], s);
+                if (a == bcol) atomicAdd(&cdiag[ra], s);
+            }
+        }
+    }
+    if (P.sp_has_lmk && tid == 0) {
+        const int dc = P.lmk_col[P.sp_lmk0];
+        const double *SQ = P.sp_blob + 249, *r = B.sp_r + 15;
+        for (int a = 0; a < 3; a++) {
+            double gs = 0;
+            for (int i = 0; i < 3; i++) gs += SQ[i * 3 + a] * r[i];
+            atomicAdd(&g[dc + a], gs);
+            atomicAdd(&graw[dc + a], gs);
+            for (int bb = 0; bb <= a; bb++) {
+                double s = 0;
+                for (int i = 0; i < 3; i++) s += SQ[i * 3 + a] * SQ[i * 3 + bb];
+                atomicAdd(&Sb[(size_t)(dc + a) * ld + dc + bb], s);
+                if (a == bb) atomicAdd(&cdiag[dc + a], s);
+            }
+        }
+    }
+    for (int k = tid; k < P.sp_nl2l; k += nt) {
+        const int ca = P.lmk_col[P.sp_l2l_a[k]], cb = P.lmk_col[P.sp_l2l_b[k]];
+        const double *SQ = P.sp_l2l_sqrt + 9 * k, *r = B.sp_r + 18 + 3 * k;
+        for (int a = 0; a < 3; a++) {
+            double gs = 0;
+            for (int i = 0; i < 3; i++) gs += SQ[i * 3 + a] * r[i];
+            atomicAdd(&g[ca + a], gs);
+            atomicAdd(&graw[ca + a], gs);
+            atomicAdd(&g[cb + a], -gs);
+            atomicAdd(&graw[cb + a], -gs);
+            for (int bb = 0; bb < 3; bb++) {
+                double s = 0;
+                for (int i = 0; i < 3; i++) s += SQ[i * 3 + a] * SQ[i * 3 + bb];
+                if (bb <= a) {
+                    atomicAdd(&Sb[(size_t)(ca + a) * ld + ca + bb], s);
+                    atomicAdd(&Sb[(size_t)(cb + a) * ld + cb + bb], s);
+                }
+                if (a == bb) {
+                    atomicAdd(&cdiag[ca + a], s);
+                    atomicAdd(&cdiag[cb + a], s);
+                }
+                // cross block J_a^T J_b = -M, stored in the lower triangle
+                if (ca > cb) atomicAdd(&Sb[(size_t)(ca + a) * ld + cb + bb], -s);
+                else atomicAdd(&Sb[(size_t)(cb + bb) * ld + ca + a], -s);
+            }
         }
     }
 }
@@ -1243,27 +1477,32 @@ __global__ void __launch_bounds__(TS_THREADS) k_trisolve(DevProblem P, LinBuf B0
 // =====================================================================================================================
 // landmark back-substitution: delta_l = -V^-1 (g_l + sum_f W_f^T delta_f); candidate landmark parameters
 // =====================================================================================================================
+template <int G>
 __global__ void __launch_bounds__(SCH_WARPS * 32) k_backsub(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc,
                                                             SolverOpts opt, const double *dxp, const double *scale_l) {
     if (st->status != 0 || !st->step_valid) return;
     const LinBuf &Bx = st->cur ? B1 : B0;
     const LinBuf &Bc = st->cur ? B0 : B1;
+    constexpr int GPW = 32 / G, GPB = SCH_WARPS * GPW;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lig = lane % G, gib = wib * GPW + lane / G;
     const double radius = st->radius;
     double gd = 0, dd = 0, sn = 0, cn = 0;
-    for (int l = P.l0 + blockIdx.x * SCH_WARPS + wib; l < P.l1; l += gridDim.x * SCH_WARPS) {
-        if (P.lmk_col[l] >= 0) continue; // kept landmark: part of the reduced system
-        const int s0 = P.slot_ptr[l], m = P.slot_ptr[l + 1] - s0;
+    const int nl = P.l1 - P.l0;
+    for (int lb = blockIdx.x * GPB; lb < nl; lb += gridDim.x * GPB) {
+        const int l = P.l0 + lb + gib;
+        const bool valid = (lb + gib) < nl && P.lmk_col[min(l, P.L - 1)] < 0; // kept landmarks are part of the reduced system
+        const int s0 = valid ? P.slot_ptr[l] : 0, m = valid ? P.slot_ptr[l + 1] - s0 : 0;
         double hl[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0}, e[3] = {0, 0, 0};
-        if (lane < m) slot_accumulate_back(P, Bx, s0 + lane, dxp, hl, gl, e);
+        if (lig < m) slot_accumulate_back(P, Bx, s0 + lig, dxp, hl, gl, e);
 #pragma unroll
-        for (int k = 0; k < 6; k++) hl[k] = warp_sum(hl[k]);
+        for (int k = 0; k < 6; k++) hl[k] = group_sum<G>(hl[k]);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            gl[k] = warp_sum(gl[k]);
-            e[k] = warp_sum(e[k]);
+            gl[k] = group_sum<G>(gl[k]);
+            e[k] = group_sum<G>(e[k]);
         }
-        if (lane != 0) continue;
+        if (!valid || lig != 0) continue;
         double s3[3] = {scale_l[3 * (size_t)l], scale_l[3 * (size_t)l + 1], scale_l[3 * (size_t)l + 2]};
         double d3[3] = {lm_damping(hl[0], s3[0], radius, opt), lm_damping(hl[3], s3[1], radius, opt), lm_damping(hl[5], s3[2], radius, opt)};
         double V[6] = {hl[0] + d3[0], hl[1], hl[2], hl[3] + d3[1], hl[4], hl[5] + d3[2]};
@@ -1282,7 +1521,7 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_backsub(DevProblem P, LinBuf
             cn += xc * xc;
         }
     }
-    // lanes != 0 carry zeros
+    __syncwarp();
     gd = warp_sum(gd);
     dd = warp_sum(dd);
     sn = warp_sum(sn);
@@ -1335,8 +1574,12 @@ __global__ void k_iter_begin(LMState *st) {
     st->step_valid = 0;
 }
 
-__global__ void k_ctrl(LMState *st, Accum *acc, SolverOpts opt) {
-    if (st->status != 0) return;
+__global__ void k_ctrl(LMState *st, Accum *acc, SolverOpts opt, unsigned long long cond) {
+    // `cond` (0 = none) is the handle of the CUDA-graph WHILE node whose body is one LM iteration
+    if (st->status != 0) {
+        if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, 0);
+        return;
+    }
     const int it = st->iter;
     const int ti = it < 63 ? it : 63;
     const int cand = 1 - st->cur;
@@ -1414,6 +1657,7 @@ __global__ void k_ctrl(LMState *st, Accum *acc, SolverOpts opt) {
     acc->cost[1 - st->cur] = 0.0;
     acc->model_gd = acc->model_dd = acc->step_norm2 = acc->cand_norm2 = 0.0;
     acc->schur_fail = acc->chol_fail = 0;
+    if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, st->status == 0 ? 1u : 0u);
 }
 
 // gather the solution blocks in ABI order

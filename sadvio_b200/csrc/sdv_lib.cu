@@ -7,6 +7,7 @@
 // There is NO CPU fallback: without a CUDA device sdv_create fails with SDV_ERR_NO_DEVICE.
 #include "../../include/sdv.h"
 #include "sdv_kernels.cuh"
+#include "sdv_chol.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -89,7 +90,20 @@ struct sdv_handle {
     size_t sb_elems = 0;
     bool resident = false;
     int lin_grid = 0, lin_smem = 0, sch_grid = 0, fac_grid = 0;
+    int group = 32; // lanes per landmark in k_schur / k_backsub (8, 16 or 32 by the largest slot count)
+    int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_reg = 1; // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
+    double *d_partial = nullptr, *d_dinv = nullptr, *d_prof = nullptr;
     int64_t launches = 0;
+    // whole-solve CUDA graph: prologue -> WHILE(LM iteration) -> epilogue (single-GPU only)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t stream2 = nullptr;
+    unsigned long long cond = 0;
+    bool graph_ok = false;
+    DevProblem graph_P;
+    int64_t graph_launches_fixed = 0, graph_launches_iter = 0;
+    unsigned char *h_sol = nullptr;
+    size_t sol_cap = 0;
     // comm
     void *comm = nullptr;
     int rank = 0, world = 1;
@@ -130,6 +144,10 @@ int ensure(sdv_handle *h, unsigned char **d, size_t *cap, size_t need, bool pinn
 }
 
 } // namespace
+
+namespace {
+int build_solve_graph(sdv_handle *h);
+}
 
 extern "C" {
 
@@ -207,6 +225,10 @@ int sdv_destroy(sdv_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->h_sol) cudaFreeHost(h->h_sol);
     if (h->d_in) cudaFree(h->d_in);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->d_scr) cudaFree(h->d_scr);
@@ -216,6 +238,32 @@ int sdv_destroy(sdv_handle *h) {
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
     delete h;
+    return SDV_OK;
+}
+
+// Landmark shard of `rank`: contiguous landmark range [l0, l1) balanced by observation count, and its observation
+// range [o0, o1).  Pure host logic (no CUDA call) so that it can be tested without a GPU.
+int sdv_shard_range(const int32_t *obs_lmk, int32_t n_obs, int32_t n_lmks, int32_t rank, int32_t world, int32_t *l0, int32_t *l1,
+                    int32_t *o0, int32_t *o1) {
+    if (n_obs < 0 || n_lmks < 0 || world < 1 || rank < 0 || rank >= world || (n_obs > 0 && !obs_lmk) || !l0 || !l1 || !o0 || !o1)
+        return SDV_ERR_INVALID_ARGUMENT;
+    std::vector<int> ptr(n_lmks + 1, 0);
+    int o = 0;
+    for (int l = 0; l < n_lmks; l++) {
+        ptr[l] = o;
+        while (o < n_obs && obs_lmk[o] == l) o++;
+    }
+    if (o != n_obs) return SDV_ERR_INVALID_ARGUMENT; // not landmark-major
+    ptr[n_lmks] = n_obs;
+    auto cut = [&](int r) {
+        long long target = (long long)n_obs * r / world;
+        int l = (int)(std::lower_bound(ptr.begin(), ptr.end(), (int)target) - ptr.begin());
+        return std::min(l, (int)n_lmks);
+    };
+    *l0 = rank == 0 ? 0 : cut(rank);
+    *l1 = rank == world - 1 ? n_lmks : cut(rank + 1);
+    *o0 = ptr[*l0];
+    *o1 = ptr[*l1];
     return SDV_OK;
 }
 
@@ -265,7 +313,21 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
                    !w->imu_J_dv_ba || !w->imu_J_dv_bg || !w->imu_J_dp_ba || !w->imu_J_dp_bg || !w->imu_sigma_ba || !w->imu_sigma_bg))
         return fail(h, SDV_ERR_INVALID_ARGUMENT, "null IMU arrays");
     if (w->has_prior && (!w->T_prior || !w->inf_prior)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "has_prior without T_prior/inf_prior");
-    if (w->sparse_prior) return fail(h, SDV_ERR_UNSUPPORTED, "sparsified prior factors are not implemented in this build");
+    const sdv_sparse_prior *sp = w->sparse_prior;
+    if (sp) {
+        if (sp->n_p2l < 0 || sp->n_l2l < 0) return fail(h, SDV_ERR_INVALID_ARGUMENT, "malformed sparse prior");
+        if (sp->has_imu_prior && (sp->frame < 0 || sp->frame >= F || !w->vio)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "sparse prior frame");
+        if (sp->n_p2l > 0 && (!sp->has_imu_prior || !sp->p2l_lmk || !sp->p2l_delta || !sp->p2l_sqrt_inf))
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "PoseToLandmark factors need the kept frame and their arrays");
+        for (int k = 0; k < sp->n_p2l; k++)
+            if (sp->p2l_lmk[k] < 0 || sp->p2l_lmk[k] >= L) return fail(h, SDV_ERR_INVALID_ARGUMENT, "p2l landmark out of range");
+        if (sp->has_lmk_prior && (sp->lmk0 < 0 || sp->lmk0 >= L)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "lmk0 out of range");
+        if (sp->n_l2l > 0 && (!sp->l2l_a || !sp->l2l_b || !sp->l2l_delta || !sp->l2l_sqrt_inf))
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "null LandmarkToLandmark arrays");
+        for (int k = 0; k < sp->n_l2l; k++)
+            if (sp->l2l_a[k] < 0 || sp->l2l_a[k] >= L || sp->l2l_b[k] < 0 || sp->l2l_b[k] >= L || sp->l2l_a[k] == sp->l2l_b[k])
+                return fail(h, SDV_ERR_INVALID_ARGUMENT, "l2l landmark out of range");
+    }
     for (int o = 0; o < O; o++) {
         if (w->obs_lmk[o] < 0 || w->obs_lmk[o] >= L || w->obs_frame[o] < 0 || w->obs_frame[o] >= F || w->obs_cam[o] < 0 || w->obs_cam[o] >= C)
             return fail(h, SDV_ERR_INVALID_ARGUMENT, "observation index out of range");
@@ -300,6 +362,10 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         pose_used[dp->frame] = 1;
         if (w->vio) vb_used[dp->frame] = 1;
     }
+    if (sp && sp->has_imu_prior) {
+        pose_used[sp->frame] = 1;
+        vb_used[sp->frame] = 1;
+    }
     std::vector<int> pose_col(F, -1), vb_col(F, -1), lmk_col(L, -1);
     int n = 0;
     for (int f = 0; f < F; f++) {
@@ -322,75 +388,85 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
                 n += 3;
             }
         }
+    if (sp) {
+        auto make_dense = [&](int l) {
+            if (lmk_col[l] < 0) {
+                lmk_col[l] = n;
+                n += 3;
+            }
+        };
+        if (sp->has_lmk_prior) make_dense(sp->lmk0); // moved to elimination group 2, …Analytic.cpp:437-438
+        for (int k = 0; k < sp->n_l2l; k++) {         // chain factors couple landmarks, …Analytic.cpp:448-481
+            make_dense(sp->l2l_a[k]);
+            make_dense(sp->l2l_b[k]);
+        }
+    }
     if (n == 0) return fail(h, SDV_ERR_UNSUPPORTED, "window has no free frame parameter (pure landmark refinement is landmarkOptimization, not this entry point)");
     const int n_pad = (n + 31) / 32 * 32, ld = n_pad;
 
-    // ---- slots: (landmark, distinct keyframe) groups
-    std::vector<int> slot_ptr(L + 1, 0), slot_frame, slot_obs_ptr, slot_obs(O);
+    // ---- landmark shard of this rank (contiguous, balanced by observation count)
+    int l0 = 0, l1 = L, o0 = 0, o1 = O;
+    if (sdv_shard_range(w->obs_lmk, O, L, h->rank, h->world, &l0, &l1, &o0, &o1) != SDV_OK)
+        return fail(h, SDV_ERR_INVALID_ARGUMENT, "cannot shard landmarks");
+    const int Oloc = o1 - o0;
+
+    // ---- slots: (landmark, distinct keyframe) groups over the real observations and the PoseToLandmark pseudo-observations;
+    //      slot_obs holds plane indices local to this rank (real observation o -> o - o0, pseudo-observations after them)
+    const int np2l = sp ? sp->n_p2l : 0;
+    std::vector<int> p2l_plane(std::max(np2l, 1), -1);
+    std::vector<std::vector<int>> p2l_of_lmk;
+    int n_pseudo = 0;
+    if (np2l) {
+        p2l_of_lmk.resize(L);
+        for (int k = 0; k < np2l; k++) {
+            int l = sp->p2l_lmk[k];
+            if (l >= l0 && l < l1) {
+                p2l_plane[k] = Oloc + 2 * n_pseudo;
+                n_pseudo++;
+                p2l_of_lmk[l].push_back(k);
+            }
+        }
+    }
+    const int Ocap = Oloc + 2 * n_pseudo;
+    std::vector<int> slot_ptr(L + 1, 0), slot_frame, slot_obs_ptr, slot_obs;
     slot_frame.reserve(O);
     slot_obs_ptr.reserve(O + 1);
+    slot_obs.reserve((size_t)O + 2 * n_pseudo);
     {
         int o = 0;
-        std::vector<int> tmp_frames, tmp_count;
+        std::vector<int> tmp_frames;
+        std::vector<std::pair<int, int>> ent; // (frame, plane index)
         for (int l = 0; l < L; l++) {
             slot_ptr[l] = (int)slot_frame.size();
-            int o_begin = o;
+            ent.clear();
             tmp_frames.clear();
             while (o < O && w->obs_lmk[o] == l) {
-                int f = w->obs_frame[o];
-                if (std::find(tmp_frames.begin(), tmp_frames.end(), f) == tmp_frames.end()) tmp_frames.push_back(f);
+                ent.push_back({w->obs_frame[o], o - o0});
                 o++;
             }
+            if (np2l)
+                for (int k : p2l_of_lmk[l]) {
+                    ent.push_back({sp->frame, p2l_plane[k]});
+                    ent.push_back({sp->frame, p2l_plane[k] + 1});
+                }
+            for (auto &e : ent)
+                if (std::find(tmp_frames.begin(), tmp_frames.end(), e.first) == tmp_frames.end()) tmp_frames.push_back(e.first);
             if ((int)tmp_frames.size() > MAX_SLOTS)
                 return fail(h, SDV_ERR_UNSUPPORTED, "a landmark is observed from more than 32 keyframes (kernel limit of this build)");
             for (int f : tmp_frames) {
                 slot_frame.push_back(f);
-                slot_obs_ptr.push_back(0);
-            }
-            // fill slot_obs grouped by slot, keeping observation order inside a slot
-            int base = slot_ptr[l];
-            std::vector<int> cnt(tmp_frames.size(), 0);
-            for (int q = o_begin; q < o; q++) {
-                int s = (int)(std::find(tmp_frames.begin(), tmp_frames.end(), w->obs_frame[q]) - tmp_frames.begin());
-                cnt[s]++;
-            }
-            int run = o_begin;
-            for (size_t s = 0; s < tmp_frames.size(); s++) {
-                slot_obs_ptr[base + s] = run;
-                run += cnt[s];
-                cnt[s] = 0;
-            }
-            for (int q = o_begin; q < o; q++) {
-                int s = (int)(std::find(tmp_frames.begin(), tmp_frames.end(), w->obs_frame[q]) - tmp_frames.begin());
-                slot_obs[slot_obs_ptr[base + s] + cnt[s]++] = q;
+                slot_obs_ptr.push_back((int)slot_obs.size());
+                for (auto &e : ent)
+                    if (e.first == f) slot_obs.push_back(e.second);
             }
         }
         slot_ptr[L] = (int)slot_frame.size();
-        slot_obs_ptr.push_back(O);
+        slot_obs_ptr.push_back((int)slot_obs.size());
     }
     const int nslots = (int)slot_frame.size();
-
-    // ---- landmark shard of this rank (contiguous, balanced by observation count)
-    std::vector<int> lmk_obs_ptr(L + 1, 0);
-    {
-        int o = 0;
-        for (int l = 0; l < L; l++) {
-            lmk_obs_ptr[l] = o;
-            while (o < O && w->obs_lmk[o] == l) o++;
-        }
-        lmk_obs_ptr[L] = O;
-    }
-    int l0 = 0, l1 = L;
-    if (h->world > 1) {
-        auto cut = [&](int r) {
-            long long target = (long long)O * r / h->world;
-            int l = (int)(std::lower_bound(lmk_obs_ptr.begin(), lmk_obs_ptr.end(), (int)target) - lmk_obs_ptr.begin());
-            return std::min(l, L);
-        };
-        l0 = cut(h->rank);
-        l1 = h->rank == h->world - 1 ? L : cut(h->rank + 1);
-    }
-    const int o0 = lmk_obs_ptr[l0], o1 = lmk_obs_ptr[l1], Oloc = o1 - o0;
+    const int nslotobs = (int)slot_obs.size();
+    int max_slots = 1;
+    for (int l = 0; l < L; l++) max_slots = std::max(max_slots, slot_ptr[l + 1] - slot_ptr[l]);
 
     // ---- dense prior column maps
     std::vector<int> mp_src, mp_dst;
@@ -422,7 +498,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     size_t o_pc = A.add(4 * F), o_vc = A.add(4 * F);
     size_t o_Ts = A.add(D * 12 * C), o_K = A.add(D * 4 * C), o_cw = A.add(D * C);
     size_t o_lt = A.add(D * 3 * std::max(L, 1)), o_lc = A.add(4 * std::max(L, 1));
-    size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(O, 1));
+    size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(nslotobs, 1));
     size_t o_ol = A.add(4 * std::max(O, 1)), o_ofc = A.add(4 * std::max(O, 1));
     const int mplanes = kind == SDV_FACTOR_ANGULAR ? 3 : 2;
     size_t o_om = A.add(D * mplanes * std::max(O, 1));
@@ -439,6 +515,19 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         o_mr = A.add(D * dp->n_full);
         o_ms = A.add(4 * std::max(nm, 1));
         o_md = A.add(4 * std::max(nm, 1));
+    }
+    size_t o_spb = 0, o_p2l = 0, o_p2p = 0, o_p2d = 0, o_p2s = 0, o_l2a = 0, o_l2b = 0, o_l2d = 0, o_l2s = 0;
+    const int nl2l = sp ? sp->n_l2l : 0;
+    if (sp) {
+        o_spb = A.add(D * 258);
+        o_p2l = A.add(4 * std::max(np2l, 1));
+        o_p2p = A.add(4 * std::max(np2l, 1));
+        o_p2d = A.add(D * 3 * std::max(np2l, 1));
+        o_p2s = A.add(D * 9 * std::max(np2l, 1));
+        o_l2a = A.add(4 * std::max(nl2l, 1));
+        o_l2b = A.add(4 * std::max(nl2l, 1));
+        o_l2d = A.add(D * 3 * std::max(nl2l, 1));
+        o_l2s = A.add(D * 9 * std::max(nl2l, 1));
     }
     int rc;
     if ((rc = ensure(h, &h->h_in, &h->in_cap, A.size, true)) != SDV_OK) return rc;
@@ -487,8 +576,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     std::memcpy(hb + o_sp, slot_ptr.data(), 4 * (L + 1));
     if (nslots) std::memcpy(hb + o_sf, slot_frame.data(), 4 * nslots);
     std::memcpy(hb + o_sop, slot_obs_ptr.data(), 4 * (nslots + 1));
+    if (nslotobs) std::memcpy(hb + o_so, slot_obs.data(), 4 * (size_t)nslotobs);
     if (O) {
-        std::memcpy(hb + o_so, slot_obs.data(), 4 * O);
         std::memcpy(hb + o_ol, w->obs_lmk, 4 * O);
         int *fc = at<int>(hb, o_ofc);
         for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o];
@@ -525,6 +614,33 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             std::memcpy(hb + o_md, mp_dst.data(), 4 * nm);
         }
     }
+    if (sp) {
+        double *blob = at<double>(hb, o_spb);
+        std::memset(blob, 0, D * 258);
+        if (sp->has_imu_prior) {
+            std::memcpy(blob, sp->T_prior, D * 12);
+            std::memcpy(blob + 12, sp->v_prior, D * 3);
+            std::memcpy(blob + 15, sp->ba_prior, D * 3);
+            std::memcpy(blob + 18, sp->bg_prior, D * 3);
+            std::memcpy(blob + 21, sp->imu_sqrt_inf, D * 225);
+        }
+        if (sp->has_lmk_prior) {
+            std::memcpy(blob + 246, sp->lmk_prior, D * 3);
+            std::memcpy(blob + 249, sp->lmk_sqrt_inf, D * 9);
+        }
+        if (np2l) {
+            std::memcpy(hb + o_p2l, sp->p2l_lmk, 4 * np2l);
+            std::memcpy(hb + o_p2p, p2l_plane.data(), 4 * np2l);
+            std::memcpy(hb + o_p2d, sp->p2l_delta, D * 3 * np2l);
+            std::memcpy(hb + o_p2s, sp->p2l_sqrt_inf, D * 9 * np2l);
+        }
+        if (nl2l) {
+            std::memcpy(hb + o_l2a, sp->l2l_a, 4 * nl2l);
+            std::memcpy(hb + o_l2b, sp->l2l_b, 4 * nl2l);
+            std::memcpy(hb + o_l2d, sp->l2l_delta, D * 3 * nl2l);
+            std::memcpy(hb + o_l2s, sp->l2l_sqrt_inf, D * 9 * nl2l);
+        }
+    }
     (void)t_pack0;
     CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
@@ -535,12 +651,12 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     // ---- scratch arena (device only)
     Arena S;
     size_t s_st = S.add(sizeof(LMState)), s_acc = S.add(sizeof(Accum));
-    size_t s_lin[2][12];
+    size_t s_lin[2][14];
     for (int b = 0; b < 2; b++) {
         s_lin[b][0] = S.add(D * FCT_ROW * F * C);
-        s_lin[b][1] = S.add(D * 2 * std::max(Oloc, 1));
-        s_lin[b][2] = S.add(D * 12 * std::max(Oloc, 1));
-        s_lin[b][3] = S.add(D * 6 * std::max(Oloc, 1));
+        s_lin[b][1] = S.add(D * 2 * std::max(Ocap, 1));
+        s_lin[b][2] = S.add(D * 12 * std::max(Ocap, 1));
+        s_lin[b][3] = S.add(D * 6 * std::max(Ocap, 1));
         s_lin[b][4] = S.add(D * 9 * std::max(Pn, 1));
         s_lin[b][5] = S.add(D * 216 * std::max(Pn, 1));
         s_lin[b][6] = S.add(D * 6 * std::max(Pn, 1));
@@ -549,6 +665,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         s_lin[b][9] = S.add(D * std::max(dp ? dp->n_full : 1, 1));
         s_lin[b][10] = S.add(D * n_pad);
         s_lin[b][11] = S.add(D * 3 * std::max(L, 1));
+        s_lin[b][12] = S.add(D * (18 + 3 * (size_t)std::max(nl2l, 1)));
+        s_lin[b][13] = S.add(D * 225);
     }
     const size_t sb_elems = (size_t)(n_pad + 32) * ld;
     size_t s_Sb = S.add(D * sb_elems), s_Lo = S.add(D * sb_elems);
@@ -557,6 +675,9 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     size_t s_inf = S.add(D * 81 * std::max(Pn, 1));
     size_t s_mH = S.add(D * std::max((size_t)nm * nm, (size_t)1)), s_mg = S.add(D * std::max(nm, 1));
     size_t s_red = S.add(D * 16);
+    size_t s_part = S.add(D * (size_t)(n_pad / 32 + 1) * CC_MAX * 32);
+    size_t s_dinv = S.add(D * (n_pad + 32));
+    size_t s_prof = S.add(D * 8 * CC_MAX);
     if ((rc = ensure(h, &h->d_scr, &h->scr_cap, S.size)) != SDV_OK) return rc;
     unsigned char *sb = h->d_scr;
     size_t out_bytes = D * ((size_t)15 * F + 3 * (size_t)std::max(L, 1));
@@ -591,12 +712,27 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         P.mp_src_col = at<int>(db, o_ms); P.mp_dst_col = at<int>(db, o_md);
         P.mp_H = at<double>(sb, s_mH); P.mp_g0 = at<double>(sb, s_mg);
     }
+    P.Ocap = Ocap;
+    if (sp) {
+        P.sp_has_imu = sp->has_imu_prior ? 1 : 0;
+        P.sp_frame = sp->frame;
+        P.sp_has_lmk = sp->has_lmk_prior ? 1 : 0;
+        P.sp_lmk0 = sp->lmk0;
+        P.sp_np2l = np2l;
+        P.sp_nl2l = nl2l;
+        P.sp_blob = at<double>(db, o_spb);
+        P.sp_p2l_lmk = at<int>(db, o_p2l); P.sp_p2l_plane = at<int>(db, o_p2p);
+        P.sp_p2l_delta = at<double>(db, o_p2d); P.sp_p2l_sqrt = at<double>(db, o_p2s);
+        P.sp_l2l_a = at<int>(db, o_l2a); P.sp_l2l_b = at<int>(db, o_l2b);
+        P.sp_l2l_delta = at<double>(db, o_l2d); P.sp_l2l_sqrt = at<double>(db, o_l2s);
+    }
     for (int b = 0; b < 2; b++) {
         LinBuf &B = h->B[b];
         B.fct = at<double>(sb, s_lin[b][0]); B.r = at<double>(sb, s_lin[b][1]); B.Jp = at<double>(sb, s_lin[b][2]);
         B.Jl = at<double>(sb, s_lin[b][3]); B.imu_r = at<double>(sb, s_lin[b][4]); B.imu_J = at<double>(sb, s_lin[b][5]);
         B.bias_r = at<double>(sb, s_lin[b][6]); B.prior_r = at<double>(sb, s_lin[b][7]); B.prior_J = at<double>(sb, s_lin[b][8]);
         B.mp_r = at<double>(sb, s_lin[b][9]); B.xp = at<double>(sb, s_lin[b][10]); B.xl = at<double>(sb, s_lin[b][11]);
+        B.sp_r = at<double>(sb, s_lin[b][12]); B.sp_J = at<double>(sb, s_lin[b][13]);
     }
     h->d_st = at<LMState>(sb, s_st);
     h->d_acc = at<Accum>(sb, s_acc);
@@ -604,10 +740,13 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     h->d_scale_p = at<double>(sb, s_sp); h->d_damp_p = at<double>(sb, s_dp); h->d_graw_p = at<double>(sb, s_gp); h->d_dxp = at<double>(sb, s_dx);
     h->d_scale_l = at<double>(sb, s_sl);
     h->d_red = at<double>(sb, s_red);
+    h->d_partial = at<double>(sb, s_part);
+    h->d_dinv = at<double>(sb, s_dinv);
+    h->d_prof = at<double>(sb, s_prof);
     h->sb_elems = sb_elems;
 
     // ---- launch geometry
-    size_t fct_bytes = (size_t)F * C * FCT_ROW * D;
+    size_t fct_bytes = (size_t)F * C * FCT_SROW * D;
     P.fct_in_smem = fct_bytes <= 160 * 1024 ? 1 : 0;
     h->lin_smem = P.fct_in_smem ? (int)fct_bytes : 0;
     if (kind == SDV_FACTOR_ANGULAR) CK(cudaFuncSetAttribute(k_lin_visual<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -618,8 +757,46 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lin_visual<1>, LIN_THREADS, h->lin_smem));
     per_sm = std::max(per_sm, 1);
     h->lin_grid = std::max(1, std::min((Oloc + LIN_THREADS - 1) / LIN_THREADS, h->num_sms * per_sm));
-    h->sch_grid = std::max(1, std::min(((l1 - l0) + SCH_WARPS - 1) / SCH_WARPS, h->num_sms * 8));
+    h->group = max_slots <= 8 ? 8 : (max_slots <= 16 ? 16 : 32);
+    {
+        int gpb = SCH_WARPS * (32 / h->group);
+        h->sch_grid = std::max(1, std::min(((l1 - l0) + gpb - 1) / gpb, h->num_sms * 8));
+    }
     h->fac_grid = std::max(1, (std::max(Pn, 1) + FAC_WARPS - 1) / FAC_WARPS);
+    // dense Cholesky: one thread-block cluster when the reduced system is small enough, per-panel launches otherwise
+    h->chol_cluster = 0;
+    if (n_pad <= 2048 && !getenv("SDV_NO_CLUSTER")) {
+        h->chol_reg = getenv("SDV_CHOL_SMEM") ? 0 : 1;
+        CK(cudaFuncSetAttribute(k_chol_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CK(cudaFuncSetAttribute(k_chol_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_chol_cluster<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CK(cudaFuncSetAttribute(k_chol_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const int T = n_pad / 32;
+        for (int cs : {16, 8, 4, 2, 1}) {
+            int rows = (T + 1 + cs - 1) / cs;
+            int smem = (int)(sizeof(double) * (32 * TSTR + 32 + (size_t)rows * 32 * TSTR + (size_t)rows * 32 + 8 * 32));
+            if (smem > 200 * 1024) continue;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(cs);
+            lc.blockDim = dim3(CCT);
+            lc.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at1[1];
+            at1[0].id = cudaLaunchAttributeClusterDimension;
+            at1[0].val.clusterDim.x = cs;
+            at1[0].val.clusterDim.y = 1;
+            at1[0].val.clusterDim.z = 1;
+            lc.attrs = at1;
+            lc.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_chol_cluster<true>, &lc) == cudaSuccess && nclusters >= 1) {
+                h->chol_cluster = cs;
+                h->chol_rows = rows;
+                h->chol_smem = smem;
+                break;
+            }
+            cudaGetLastError();
+        }
+    }
 
     // ---- one-time device setup for this window
     if (Pn > 0) {
@@ -632,13 +809,32 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
+    if ((rc = ensure(h, &h->h_sol, &h->sol_cap, out_bytes + sizeof(LMState) + sizeof(Accum) + 256, true)) != SDV_OK) return rc;
     h->resident = true;
+    if ((rc = build_solve_graph(h)) != SDV_OK) return rc;
     return SDV_OK;
 }
 
 } // extern "C"
 
 namespace {
+
+void launch_schur(sdv_handle *h) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    if (h->group == 8) k_schur<8><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+    else if (h->group == 16) k_schur<16><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+    else k_schur<32><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+    h->launches++;
+}
+void launch_backsub(sdv_handle *h) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    if (h->group == 8) k_backsub<8><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
+    else if (h->group == 16) k_backsub<16><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
+    else k_backsub<32><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
+    h->launches++;
+}
 
 int launch_linearize(sdv_handle *h, int which) {
     const DevProblem &P = h->P;
@@ -649,8 +845,12 @@ int launch_linearize(sdv_handle *h, int which) {
             k_lin_visual<1><<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
         h->launches++;
     }
-    if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0)) {
+    if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0 || P.sp_has_imu || P.sp_has_lmk || P.sp_nl2l > 0)) {
         k_lin_factors<<<h->fac_grid, FAC_WARPS * 32, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        h->launches++;
+    }
+    if (P.sp_np2l > 0) {
+        k_lin_p2l<<<(P.sp_np2l + 127) / 128, 128, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
         h->launches++;
     }
     return SDV_OK;
@@ -697,6 +897,41 @@ __global__ void k_gradmax_to_flag(Accum *acc, double tol, double *red, int dir) 
     else acc->grad_max_bits = red[8] > 0.0 ? (unsigned long long)__double_as_longlong(1e300) : 0ull;
 }
 
+int launch_factor_solve(sdv_handle *h) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    const int T = P.n_pad / CH_T;
+    if (h->chol_cluster > 0) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(h->chol_cluster);
+        lc.blockDim = dim3(CCT);
+        lc.dynamicSmemBytes = h->chol_smem;
+        lc.stream = s;
+        cudaLaunchAttribute at1[1];
+        at1[0].id = cudaLaunchAttributeClusterDimension;
+        at1[0].val.clusterDim.x = h->chol_cluster;
+        at1[0].val.clusterDim.y = 1;
+        at1[0].val.clusterDim.z = 1;
+        lc.attrs = at1;
+        lc.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&lc, h->chol_reg ? k_chol_cluster<true> : k_chol_cluster<false>, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, h->d_partial,
+                                           (const double *)h->d_damp_p, (const double *)h->d_graw_p, h->d_dxp, h->chol_rows, h->d_prof);
+        if (e != cudaSuccess) return fail(h, SDV_ERR_CUDA, std::string("k_chol_cluster launch: ") + cudaGetErrorString(e));
+        h->launches++;
+        return SDV_OK;
+    }
+    for (int k = 0; k < T; k++) {
+        int npanel = T - k + 1, ntrail = 0;
+        for (int i = k + 1; i <= T; i++) ntrail += std::min(i, T - 1) - k;
+        k_chol_panel<<<npanel + ntrail, CH_THREADS, 0, s>>>(h->d_Sb, h->d_Lo, P.ld, T, k, h->d_st, h->d_acc);
+        h->launches++;
+    }
+    k_trisolve<<<1, TS_THREADS, (int)((P.n_pad + 1024 + 32 * 33) * sizeof(double)), s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Lo, h->d_damp_p,
+                                                                                        h->d_graw_p, h->d_dxp);
+    h->launches++;
+    return SDV_OK;
+}
+
 int trisolve_smem(const DevProblem &P) { return (int)((P.n_pad + 1024 + 32 * 33) * sizeof(double)); }
 
 int launch_iteration(sdv_handle *h) {
@@ -705,10 +940,14 @@ int launch_iteration(sdv_handle *h) {
     cudaStream_t s = h->stream;
     k_iter_begin<<<1, 1, 0, s>>>(h->d_st);
     if (cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s) != cudaSuccess) return fail(h, SDV_ERR_CUDA, "memset S");
-    k_schur<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
-    h->launches += 3;
+    launch_schur(h);
+    h->launches += 2;
     if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0)) {
         k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
+        h->launches++;
+    }
+    if (P.rank == 0 && (P.sp_has_imu || P.sp_has_lmk || P.sp_nl2l > 0)) {
+        k_assemble_sparse<<<2, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
         h->launches++;
     }
     if (h->world > 1) {
@@ -723,20 +962,141 @@ int launch_iteration(sdv_handle *h) {
     }
     k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
     h->launches++;
-    for (int k = 0; k < T; k++) {
-        int npanel = T - k + 1, ntrail = 0;
-        for (int i = k + 1; i <= T; i++) ntrail += std::min(i, T - 1) - k;
-        k_chol_panel<<<npanel + ntrail, CH_THREADS, 0, s>>>(h->d_Sb, h->d_Lo, P.ld, T, k, h->d_st, h->d_acc);
-        h->launches++;
+    {
+        int rcf = launch_factor_solve(h);
+        if (rcf != SDV_OK) return rcf;
     }
-    k_trisolve<<<1, TS_THREADS, trisolve_smem(P), s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Lo, h->d_damp_p, h->d_graw_p, h->d_dxp);
-    k_backsub<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
-    h->launches += 2;
+    launch_backsub(h);
     launch_linearize(h, -2);
     int rc = reduce_scalars(h, -2);
     if (rc != SDV_OK) return rc;
-    k_ctrl<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
+    k_ctrl<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt, h->cond);
     h->launches++;
+    return SDV_OK;
+}
+
+} // namespace
+
+namespace {
+
+int enqueue_prologue(sdv_handle *h) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    // x = 0
+    CK(cudaMemsetAsync(h->B[0].xp, 0, sizeof(double) * P.n_pad, s));
+    CK(cudaMemsetAsync(h->B[1].xp, 0, sizeof(double) * P.n_pad, s));
+    CK(cudaMemsetAsync(h->B[0].xl, 0, sizeof(double) * 3 * std::max(P.L, 1), s));
+    CK(cudaMemsetAsync(h->B[1].xl, 0, sizeof(double) * 3 * std::max(P.L, 1), s));
+    CK(cudaMemsetAsync(h->d_st, 0, sizeof(LMState), s));
+    CK(cudaMemsetAsync(h->d_acc, 0, sizeof(Accum), s));
+    k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, 0);
+    h->launches++;
+    launch_linearize(h, 0);
+    int rc = reduce_scalars(h, 0);
+    if (rc != SDV_OK) return rc;
+    k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
+    h->launches++;
+    return SDV_OK;
+}
+
+size_t solution_doubles(const DevProblem &P) { return (size_t)15 * P.F + 3 * (size_t)std::max(P.L, 1); }
+
+// solution blocks + solver state -> pinned host memory (h_sol: [solution | LMState | Accum])
+int enqueue_epilogue(sdv_handle *h) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    double *d = reinterpret_cast<double *>(h->d_out);
+    double *dpose = d, *dv = d + 6 * P.F, *dba = dv + 3 * P.F, *dbg = dba + 3 * P.F, *dlmk = dbg + 3 * P.F;
+    k_gather_solution<<<std::max(1, std::min(1024, (std::max(P.L, P.F) + 255) / 256)), 256, 0, s>>>(P, h->B[0], h->B[1], h->d_st, dpose, dv, dba, dbg,
+                                                                                               dlmk);
+    h->launches++;
+    size_t nd = solution_doubles(P);
+    CK(cudaMemcpyAsync(h->h_sol, d, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_sol + nd * sizeof(double), h->d_st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_sol + nd * sizeof(double) + sizeof(LMState), h->d_acc, sizeof(Accum), cudaMemcpyDeviceToHost, s));
+    return SDV_OK;
+}
+
+void destroy_graph(sdv_handle *h) {
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    h->gexec = nullptr;
+    h->graph = nullptr;
+    h->graph_ok = false;
+    h->cond = 0;
+}
+
+// prologue -> WHILE (status == 0) { one LM iteration } -> epilogue, as ONE graph launch per solve.
+int build_solve_graph(sdv_handle *h) {
+    if (h->world > 1 || getenv("SDV_NO_GRAPH")) return SDV_OK; // NCCL inside a conditional body is not attempted
+    if (h->graph_ok && std::memcmp(&h->graph_P, &h->P, sizeof(DevProblem)) == 0) return SDV_OK;
+    destroy_graph(h);
+    if (!h->stream2 && cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) return SDV_OK;
+    cudaStream_t s = h->stream;
+    int64_t l0 = h->launches;
+    bool ok = true;
+    cudaGraph_t g = nullptr;
+    if (cudaGraphCreate(&g, 0) != cudaSuccess) return SDV_OK;
+    cudaGraphConditionalHandle handle = 0;
+    if (cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) {
+        cudaGraphDestroy(g);
+        cudaGetLastError();
+        return SDV_OK;
+    }
+    h->cond = (unsigned long long)handle;
+    int64_t l_fixed = 0, l_iter = 0;
+    do {
+        if (cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { ok = false; break; }
+        if (enqueue_prologue(h) != SDV_OK) { ok = false; }
+        l_fixed = h->launches - l0;
+        // conditional WHILE node after everything captured so far
+        cudaStreamCaptureStatus cst;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t ndeps = 0;
+        cudaGraph_t cg = nullptr;
+        if (ok && cudaStreamGetCaptureInfo_v2(s, &cst, nullptr, &cg, &deps, &ndeps) != cudaSuccess) ok = false;
+        cudaGraphNode_t cnode = nullptr;
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        if (ok && cudaGraphAddNode(&cnode, g, deps, ndeps, &cp) != cudaSuccess) ok = false;
+        if (ok) {
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            cudaStream_t keep = h->stream;
+            h->stream = h->stream2;
+            int64_t l1 = h->launches;
+            if (cudaStreamBeginCaptureToGraph(h->stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) ok = false;
+            if (ok && launch_iteration(h) != SDV_OK) ok = false;
+            cudaGraph_t tmp = nullptr;
+            if (cudaStreamEndCapture(h->stream2, &tmp) != cudaSuccess) ok = false;
+            l_iter = h->launches - l1;
+            h->stream = keep;
+        }
+        if (ok && cudaStreamUpdateCaptureDependencies(s, &cnode, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) ok = false;
+        int64_t l2 = h->launches;
+        if (ok && enqueue_epilogue(h) != SDV_OK) ok = false;
+        l_fixed += h->launches - l2;
+        cudaGraph_t out = nullptr;
+        if (cudaStreamEndCapture(s, &out) != cudaSuccess) ok = false;
+    } while (0);
+    h->launches = l0; // nothing was launched, only captured
+    if (ok && cudaGraphInstantiate(&h->gexec, g, 0) != cudaSuccess) ok = false;
+    cudaGetLastError();
+    if (!ok) {
+        if (h->gexec) cudaGraphExecDestroy(h->gexec);
+        h->gexec = nullptr;
+        cudaGraphDestroy(g);
+        h->cond = 0;
+        h->graph_ok = false;
+        return SDV_OK; // fall back to the host-driven loop
+    }
+    h->graph = g;
+    h->graph_ok = true;
+    h->graph_P = h->P;
+    h->graph_launches_fixed = l_fixed;
+    h->graph_launches_iter = l_iter;
     return SDV_OK;
 }
 
@@ -753,33 +1113,32 @@ int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
     int64_t launches0 = h->launches;
     auto t0 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(h->ev[2], s));
-    // x = 0
-    CK(cudaMemsetAsync(h->B[0].xp, 0, sizeof(double) * P.n_pad, s));
-    CK(cudaMemsetAsync(h->B[1].xp, 0, sizeof(double) * P.n_pad, s));
-    CK(cudaMemsetAsync(h->B[0].xl, 0, sizeof(double) * 3 * std::max(P.L, 1), s));
-    CK(cudaMemsetAsync(h->B[1].xl, 0, sizeof(double) * 3 * std::max(P.L, 1), s));
-    CK(cudaMemsetAsync(h->d_st, 0, sizeof(LMState), s));
-    CK(cudaMemsetAsync(h->d_acc, 0, sizeof(Accum), s));
-    k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, 0);
-    h->launches++;
-    launch_linearize(h, 0);
-    int rc = reduce_scalars(h, 0);
-    if (rc != SDV_OK) return rc;
-    k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
-    h->launches++;
-    int *h_status = reinterpret_cast<int *>(h->h_rb);
-    for (int it = 0; it < h->opt.max_num_iterations + 1; it++) {
-        rc = launch_iteration(h);
-        if (rc != SDV_OK) return rc;
-        CK(cudaMemcpyAsync(h_status, &h->d_st->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    const size_t nd = solution_doubles(P);
+    if (h->graph_ok) {
+        CK(cudaGraphLaunch(h->gexec, s));
+        CK(cudaEventRecord(h->ev[3], s));
         CK(cudaStreamSynchronize(s));
-        if (*h_status != 0) break;
+    } else {
+        int rc = enqueue_prologue(h);
+        if (rc != SDV_OK) return rc;
+        int *h_status = reinterpret_cast<int *>(h->h_rb);
+        for (int it = 0; it < h->opt.max_num_iterations + 1; it++) {
+            rc = launch_iteration(h);
+            if (rc != SDV_OK) return rc;
+            CK(cudaMemcpyAsync(h_status, &h->d_st->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (*h_status != 0) break;
+        }
+        if (h->world > 1) {
+            // every rank only solved its own landmarks: the gather in the epilogue is followed by a sum over ranks
+        }
+        rc = enqueue_epilogue(h);
+        if (rc != SDV_OK) return rc;
+        CK(cudaEventRecord(h->ev[3], s));
+        CK(cudaStreamSynchronize(s));
     }
-    CK(cudaEventRecord(h->ev[3], s));
-    CK(cudaMemcpyAsync(h->h_rb, h->d_st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->h_rb + sizeof(LMState), h->d_acc, sizeof(Accum), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    std::memcpy(h->h_rb, h->h_sol + nd * sizeof(double), sizeof(LMState) + sizeof(Accum));
     std::memcpy(&h->h_state, h->h_rb, sizeof(LMState));
     std::memcpy(&h->h_acc, h->h_rb + sizeof(LMState), sizeof(Accum));
     auto t1 = std::chrono::steady_clock::now();
@@ -805,6 +1164,7 @@ int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
         }
         stats->ms_solve_device = ms;
         stats->ms_total_host = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        if (h->graph_ok) h->launches += h->graph_launches_fixed + (int64_t)(st.iter + (st.status == 1 + SDV_TERM_GRADIENT_TOLERANCE ? 1 : 0)) * h->graph_launches_iter;
         stats->kernel_launches = h->launches - launches0;
     }
     return h->h_state.status == 1 + SDV_TERM_FAILURE ? SDV_ERR_NUMERICAL_FAILURE : SDV_OK;
@@ -815,23 +1175,16 @@ int sdv_download_delta(sdv_handle *h, sdv_delta *out) {
     if (!h->resident) return fail(h, SDV_ERR_INVALID_ARGUMENT, "no window uploaded");
     cudaSetDevice(h->device);
     const DevProblem &P = h->P;
-    double *d = reinterpret_cast<double *>(h->d_out);
-    double *dpose = d, *dv = d + 6 * P.F, *dba = dv + 3 * P.F, *dbg = dba + 3 * P.F, *dlmk = dbg + 3 * P.F;
-    size_t nd = (size_t)15 * P.F + 3 * (size_t)std::max(P.L, 1);
-    k_gather_solution<<<std::max(1, std::min(1024, (std::max(P.L, P.F) + 255) / 256)), 256, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, dpose, dv, dba,
-                                                                                                        dbg, dlmk);
-    h->launches++;
     if (h->world > 1) {
-        // each rank only solved its own landmarks: zero the others and sum
-        // (landmark parameters outside [l0,l1) are still zero in xl, so a plain sum is the gather)
-        int rc = allreduce(h, dlmk, 3 * (size_t)P.L);
+        // each rank only solved its own landmarks; the others are zero in its gather, so a sum over ranks is the gather
+        double *d = reinterpret_cast<double *>(h->d_out);
+        int rc = allreduce(h, d + 15 * P.F, 3 * (size_t)P.L);
         if (rc != SDV_OK) return rc;
-        if (h->rank != 0) {
-        }
+        CK(cudaMemcpyAsync(h->h_sol, d, solution_doubles(P) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
     }
-    CK(cudaMemcpyAsync(h->h_rb, d, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    const double *hb = reinterpret_cast<const double *>(h->h_rb);
+    // the epilogue of the last solve already left the solution in pinned host memory
+    const double *hb = reinterpret_cast<const double *>(h->h_sol);
     std::memcpy(out->dpose, hb, sizeof(double) * 6 * P.F);
     if (out->dv) std::memcpy(out->dv, hb + 6 * P.F, sizeof(double) * 3 * P.F);
     if (out->dba) std::memcpy(out->dba, hb + 9 * P.F, sizeof(double) * 3 * P.F);
@@ -908,18 +1261,19 @@ int sdv_eval_visual(sdv_handle *h, const sdv_delta *x, double *r, double *J_pose
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     const int Oloc = P.o1 - P.o0;
-    std::vector<double> buf((size_t)20 * std::max(Oloc, 1));
-    CK(cudaMemcpy(buf.data(), h->B[0].r, sizeof(double) * 2 * Oloc, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(buf.data() + 2 * (size_t)Oloc, h->B[0].Jp, sizeof(double) * 12 * Oloc, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(buf.data() + 14 * (size_t)Oloc, h->B[0].Jl, sizeof(double) * 6 * Oloc, cudaMemcpyDeviceToHost));
+    const size_t OC = (size_t)std::max(P.Ocap, 1);
+    std::vector<double> buf(20 * OC);
+    CK(cudaMemcpy(buf.data(), h->B[0].r, sizeof(double) * 2 * OC, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(buf.data() + 2 * OC, h->B[0].Jp, sizeof(double) * 12 * OC, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(buf.data() + 14 * OC, h->B[0].Jl, sizeof(double) * 6 * OC, cudaMemcpyDeviceToHost));
     for (int ol = 0; ol < Oloc; ol++) {
         size_t o = (size_t)P.o0 + ol;
         if (r)
-            for (int k = 0; k < 2; k++) r[2 * o + k] = buf[(size_t)k * Oloc + ol];
+            for (int k = 0; k < 2; k++) r[2 * o + k] = buf[(size_t)k * OC + ol];
         if (J_pose)
-            for (int k = 0; k < 12; k++) J_pose[12 * o + k] = buf[(size_t)(2 + k) * Oloc + ol];
+            for (int k = 0; k < 12; k++) J_pose[12 * o + k] = buf[(size_t)(2 + k) * OC + ol];
         if (J_lmk)
-            for (int k = 0; k < 6; k++) J_lmk[6 * o + k] = buf[(size_t)(14 + k) * Oloc + ol];
+            for (int k = 0; k < 6; k++) J_lmk[6 * o + k] = buf[(size_t)(14 + k) * OC + ol];
     }
     if (cost) {
         Accum a;
@@ -976,19 +1330,18 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
         } else if (which == 1) {
             CK(cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s));
             CK(cudaEventRecord(h->ev[2], s));
-            k_schur<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+            launch_schur(h);
             CK(cudaEventRecord(h->ev[3], s));
         } else if (which == 2) {
             CK(cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s));
-            k_schur<<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+            launch_schur(h);
             if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0))
                 k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
             k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
             CK(cudaEventRecord(h->ev[2], s));
-            for (int k = 0; k < T; k++) {
-                int npanel = T - k + 1, ntrail = 0;
-                for (int i = k + 1; i <= T; i++) ntrail += std::min(i, T - 1) - k;
-                k_chol_panel<<<npanel + ntrail, CH_THREADS, 0, s>>>(h->d_Sb, h->d_Lo, P.ld, T, k, h->d_st, h->d_acc);
+            {
+                int rcf = launch_factor_solve(h);
+                if (rcf != SDV_OK) return rcf;
             }
             CK(cudaEventRecord(h->ev[3], s));
         } else {
@@ -1016,10 +1369,24 @@ int sdv_debug_read(sdv_handle *h, int32_t what, double *out, int64_t count) {
     case 2: src = h->d_dxp; avail = h->P.n_pad; break;
     case 3: src = h->d_scale_p; avail = h->P.n_pad; break;
     case 4: src = h->d_damp_p; avail = h->P.n_pad; break;
+    case 5: src = h->d_prof; avail = 8 * CC_MAX; break;
     default: return SDV_ERR_INVALID_ARGUMENT;
     }
     size_t nn = std::min<size_t>(avail, (size_t)count);
     CK(cudaMemcpy(out, src, nn * sizeof(double), cudaMemcpyDeviceToHost));
+    return SDV_OK;
+}
+
+// developer micro-benchmark of the Cholesky tile routines: out[64] cycles (see k_chol_micro)
+int sdv_debug_micro(sdv_handle *h, double *out) {
+    if (!h || !out || !h->resident) return SDV_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    double *d_out = h->d_partial; // scratch, >= 64 doubles
+    CK(cudaMemsetAsync(d_out, 0, 64 * sizeof(double), h->stream));
+    k_chol_micro<<<1, 32, 0, h->stream>>>(h->d_Lo, d_out);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, d_out, 64 * sizeof(double), cudaMemcpyDeviceToHost));
     return SDV_OK;
 }
 

@@ -10,6 +10,7 @@ namespace sdv {
 //   [12..20] G   = R_s_f * R_f_w  (base, constant)     [21..29] Jq  (angular: Jr(log exp(dw)); pixel: Jr(log R')Jr(log R')^-1 Jr(dw))
 //   [30] default weight 1/sigma of the camera          [31] unused
 constexpr int FCT_ROW = 32;
+constexpr int FCT_SROW = 34; // padded row stride of the shared-memory copy (16-byte aligned, conflict-free for 8 rows per warp)
 
 // Per-solve accumulators (zeroed by the control kernels).
 struct Accum {
@@ -64,6 +65,7 @@ struct DevProblem {
     int o0, o1;   // observation range owned by this rank
     int rank, world;
     int fct_in_smem; // stage the frame-camera table in shared memory
+    int Ocap;        // stride of the r / J planes of this rank: real observations + 2 pseudo-observations per PoseToLandmark factor
     // frames
     const double *T_f_w, *v, *ba, *bg;
     const unsigned char *has_prior;
@@ -77,7 +79,7 @@ struct DevProblem {
     const int *slot_ptr;    // [L+1] first slot of each landmark
     const int *slot_frame;  // [nslots]
     const int *slot_obs_ptr;// [nslots+1]
-    const int *slot_obs;    // [O] observation ids grouped by slot
+    const int *slot_obs;    // plane indices (local to this rank) of the observations grouped by slot
     // observations (indices relative to the full window; buffers of this rank are indexed o - o0)
     const int *obs_lmk, *obs_fc;
     const double *obs_meas; // SoA planes: [3][O] bearing or [2][O] uv
@@ -96,6 +98,14 @@ struct DevProblem {
     int mp_nmap;
     double *mp_H;           // [mp_nmap][mp_nmap] J_m^T J_m restricted to mapped columns
     double *mp_g0;          // [mp_nmap] J_m^T r0
+    // sparsified prior (AngularAdjustmentCERESAnalytic.cpp:387-483)
+    int sp_has_imu, sp_frame, sp_has_lmk, sp_lmk0, sp_np2l, sp_nl2l;
+    const double *sp_blob;     // [T_prior 12 | v_prior 3 | ba_prior 3 | bg_prior 3 | imu_sqrt_inf 225 | lmk_prior 3 | lmk_sqrt_inf 9]
+    const int *sp_p2l_lmk;     // [np2l]
+    const int *sp_p2l_plane;   // [np2l] first of the two pseudo-observation plane indices, -1 = landmark owned by another rank
+    const double *sp_p2l_delta, *sp_p2l_sqrt; // [np2l][3], [np2l][9]
+    const int *sp_l2l_a, *sp_l2l_b;
+    const double *sp_l2l_delta, *sp_l2l_sqrt;
 };
 
 // One linearisation (residuals + Jacobians at a point). Two of these are alive: x and the candidate.
@@ -110,6 +120,8 @@ struct LinBuf {
     double *prior_r; // [F][6]
     double *prior_J; // [F][36]
     double *mp_r;    // [mp_nfull]
+    double *sp_r;    // [15 + 3 + 3*nl2l] IMUPriordx, Landmark3DPrior, LandmarkToLandmark residuals
+    double *sp_J;    // [15*15] IMUPriordx Jacobian (pose6 | v3 | ba3 | bg3)
     double *xp;      // [n_pad] reduced parameters (pose6,v3,ba3,bg3 per frame ... dense landmarks)
     double *xl;      // [3L] eliminated landmark parameters
 };

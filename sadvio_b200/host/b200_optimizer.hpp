@@ -1,0 +1,315 @@
+// Host-side C++ adapter above the C ABI (include/sdv.h): mirrors the reference optimizer interface for the two entry
+// points this repository replaces,
+//     bool isae::AOptimizer::localMapBA(std::shared_ptr<LocalMap>&, size_t fixed_frame_number = 0)
+//     bool isae::AOptimizer::localMapVIOptimization(std::shared_ptr<LocalMap>&, size_t fixed_frame_number = 0)
+// (reference cpp/include/isaeslam/optimizers/AOptimizer.h:28-30), same argument meaning and error behaviour
+// (bool, no exceptions; on failure the state is left untouched).
+//
+// The reference data model (isae::Frame / ImageSensor / IMU / ALandmark / AFeature / LocalMap, Eigen based) is not
+// available in this image, so this header carries a minimal mirror of the pointer graph with the reference's getter
+// names; INTEGRATION.md shows the same adapter written against the real isae:: types.  What matters — and what
+// tests/test_host_adapter.py pins — is the FLATTENING ORDER, which must reproduce the walk of
+//     addResidualsLocalMap   (AngularAdjustmentCERESAnalytic.cpp:212-339)
+//     addIMUResiduals        (AOptimizer.cpp:22-96)
+// so that the (landmark, frame, camera) visibility triplets are bit-exact, and the WRITE-BACK of AOptimizer.cpp:391-434.
+#pragma once
+#include "../../include/sdv.h"
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+namespace sdvhost {
+
+using Mat34 = std::array<double, 12>; // row-major [R | t]
+
+struct Frame;
+struct Landmark;
+
+struct ImageSensor { // isae::ImageSensor / Camera
+    std::weak_ptr<Frame> frame;
+    Mat34 T_s_f{};              // getFrame2SensorTransform()
+    std::array<double, 4> K{};  // fx, fy, cx, cy
+    std::shared_ptr<Frame> getFrame() const { return frame.lock(); }
+    double getFocal() const { return (K[0] + K[1]) / 2; } // Camera.h:46
+};
+
+struct IMU { // isae::IMU (only what the window solve reads or writes)
+    std::array<double, 3> v{}, ba{}, bg{};
+    std::array<double, 9> delta_R{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+    std::array<double, 3> delta_v{}, delta_p{};
+    std::array<double, 81> Sigma{};
+    std::array<double, 9> J_dR_bg{}, J_dv_ba{}, J_dv_bg{}, J_dp_ba{}, J_dp_bg{};
+    double bacc_noise = 0, bgyr_noise = 0;
+    std::shared_ptr<Frame> last_kf; // getLastKF()
+};
+
+struct Frame { // isae::Frame
+    Mat34 T_f_w{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}};
+    uint64_t timestamp_ns = 0;
+    bool keyframe = false, has_prior = false;
+    Mat34 T_prior{};
+    std::array<double, 6> inf_prior{};
+    std::vector<std::shared_ptr<ImageSensor>> sensors;
+    std::shared_ptr<IMU> imu; // getIMU(), may be null
+    bool isKeyFrame() const { return keyframe; }
+};
+
+struct Feature { // isae::AFeature
+    std::weak_ptr<ImageSensor> sensor;
+    std::array<double, 3> bearing{}; // getBearingVectors().at(0)
+    std::array<double, 2> uv{};      // getPoints().at(0)
+};
+
+struct Landmark { // isae::ALandmark ("pointxd")
+    std::array<double, 3> t_w{};
+    bool initialized = true, outlier = false;
+    std::vector<std::weak_ptr<Feature>> features; // getFeatures()
+    bool isInitialized() const { return initialized; }
+    bool isOutlier() const { return outlier; }
+};
+
+struct LocalMap { // isae::LocalMap
+    std::deque<std::shared_ptr<Frame>> frames;            // oldest -> newest (localmap.cpp:9-26)
+    std::vector<std::shared_ptr<Landmark>> pointxd;       // getLandmarks()["pointxd"]
+    // amap.h:28-32: newest first
+    void getLastNFramesIn(size_t n, std::vector<std::shared_ptr<Frame>> &out) const {
+        for (size_t k = 0; k < n && k < frames.size(); k++) out.push_back(frames[frames.size() - 1 - k]);
+    }
+    size_t getMapSize() const { return frames.size(); }
+};
+
+// Structure-of-arrays image of one window + the bookkeeping needed for the write-back.
+struct FlatWindow {
+    std::vector<double> T_f_w, v, ba, bg, T_prior, inf_prior, T_s_f, K, lmk_t, obs_bearing, obs_uv;
+    std::vector<uint8_t> has_imu, has_prior;
+    std::vector<int32_t> obs_lmk, obs_frame, obs_cam, imu_i, imu_j;
+    std::vector<double> imu_dt, imu_dR, imu_dv, imu_dp, imu_cov, J_dR_bg, J_dv_ba, J_dv_bg, J_dp_ba, J_dp_bg, sigma_ba, sigma_bg;
+    std::vector<std::shared_ptr<Frame>> frame_vector;     // newest -> oldest
+    std::vector<std::shared_ptr<Landmark>> landmarks;     // in parameter-block order
+    std::vector<std::shared_ptr<Frame>> imu_frame_j;      // frame j of each IMU factor
+    sdv_window view{};
+};
+
+inline void flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, int factor_kind, FlatWindow &fw) {
+    fw = FlatWindow();
+    map.getLastNFramesIn(map.getMapSize(), fw.frame_vector); // AOptimizer.cpp:366-367
+    const int F = (int)fw.frame_vector.size();
+    std::unordered_map<const Frame *, int> frame_idx; // _map_frame_posepar (…Analytic.cpp:224-226)
+    for (int i = 0; i < F; i++) frame_idx[fw.frame_vector[i].get()] = i;
+    // distinct sensor models -> camera table
+    auto cam_of = [&](const ImageSensor &s) {
+        for (size_t c = 0; c * 12 < fw.T_s_f.size(); c++)
+            if (std::memcmp(&fw.T_s_f[12 * c], s.T_s_f.data(), 96) == 0 && std::memcmp(&fw.K[4 * c], s.K.data(), 32) == 0) return (int)c;
+        fw.T_s_f.insert(fw.T_s_f.end(), s.T_s_f.begin(), s.T_s_f.end());
+        fw.K.insert(fw.K.end(), s.K.begin(), s.K.end());
+        return (int)(fw.K.size() / 4 - 1);
+    };
+    for (int i = 0; i < F; i++) {
+        const Frame &f = *fw.frame_vector[i];
+        fw.T_f_w.insert(fw.T_f_w.end(), f.T_f_w.begin(), f.T_f_w.end());
+        fw.has_prior.push_back(f.has_prior ? 1 : 0); // …Analytic.cpp:239
+        fw.T_prior.insert(fw.T_prior.end(), f.T_prior.begin(), f.T_prior.end());
+        fw.inf_prior.insert(fw.inf_prior.end(), f.inf_prior.begin(), f.inf_prior.end());
+        const IMU *imu = f.imu.get();
+        fw.has_imu.push_back(imu ? 1 : 0);
+        for (int k = 0; k < 3; k++) {
+            fw.v.push_back(imu ? imu->v[k] : 0.0);
+            fw.ba.push_back(imu ? imu->ba[k] : 0.0);
+            fw.bg.push_back(imu ? imu->bg[k] : 0.0);
+        }
+        for (auto &s : f.sensors) cam_of(*s);
+    }
+    // landmarks + visual residual blocks in reference walk order (…Analytic.cpp:247-289)
+    for (auto &landmark : map.pointxd) {
+        if (!landmark->isInitialized() || landmark->isOutlier()) continue; // :254
+        const int l = (int)fw.landmarks.size();
+        fw.landmarks.push_back(landmark);
+        fw.lmk_t.insert(fw.lmk_t.end(), landmark->t_w.begin(), landmark->t_w.end());
+        for (auto &wfeature : landmark->features) { // :266
+            std::shared_ptr<Feature> feature = wfeature.lock();
+            if (!feature) continue;
+            std::shared_ptr<ImageSensor> cam = feature->sensor.lock();
+            if (!cam) continue;
+            std::shared_ptr<Frame> frame = cam->getFrame();
+            if (!frame || !frame->isKeyFrame() || frame_idx.find(frame.get()) == frame_idx.end()) continue; // :272-275
+            fw.obs_lmk.push_back(l);
+            fw.obs_frame.push_back(frame_idx[frame.get()]);
+            fw.obs_cam.push_back(cam_of(*cam));
+            fw.obs_bearing.insert(fw.obs_bearing.end(), feature->bearing.begin(), feature->bearing.end());
+            fw.obs_uv.insert(fw.obs_uv.end(), feature->uv.begin(), feature->uv.end());
+        }
+    }
+    // IMU factors (AOptimizer.cpp:55-94)
+    if (vio) {
+        for (int i = 0; i < F; i++) {
+            const std::shared_ptr<Frame> &framej = fw.frame_vector[i];
+            if (!framej->imu) continue;                                   // :60
+            std::shared_ptr<Frame> framei = framej->imu->last_kf;         // :62
+            if (!framei) continue;                                        // :65
+            if ((double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9 > 1) continue; // :69
+            auto it = frame_idx.find(framei.get());
+            if (it == frame_idx.end() || !framei->imu || framei == framej) continue; // :72
+            const IMU &m = *framej->imu;
+            fw.imu_i.push_back(it->second);
+            fw.imu_j.push_back(i);
+            fw.imu_dt.push_back((double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9);
+            fw.imu_dR.insert(fw.imu_dR.end(), m.delta_R.begin(), m.delta_R.end());
+            fw.imu_dv.insert(fw.imu_dv.end(), m.delta_v.begin(), m.delta_v.end());
+            fw.imu_dp.insert(fw.imu_dp.end(), m.delta_p.begin(), m.delta_p.end());
+            fw.imu_cov.insert(fw.imu_cov.end(), m.Sigma.begin(), m.Sigma.end());
+            fw.J_dR_bg.insert(fw.J_dR_bg.end(), m.J_dR_bg.begin(), m.J_dR_bg.end());
+            fw.J_dv_ba.insert(fw.J_dv_ba.end(), m.J_dv_ba.begin(), m.J_dv_ba.end());
+            fw.J_dv_bg.insert(fw.J_dv_bg.end(), m.J_dv_bg.begin(), m.J_dv_bg.end());
+            fw.J_dp_ba.insert(fw.J_dp_ba.end(), m.J_dp_ba.begin(), m.J_dp_ba.end());
+            fw.J_dp_bg.insert(fw.J_dp_bg.end(), m.J_dp_bg.begin(), m.J_dp_bg.end());
+            fw.sigma_ba.push_back(framei->imu->bacc_noise); // residuals.hpp:259 reads imu_i's config
+            fw.sigma_bg.push_back(framei->imu->bgyr_noise); // residuals.hpp:261
+            fw.imu_frame_j.push_back(framej);
+        }
+    }
+    sdv_window &w = fw.view;
+    std::memset(&w, 0, sizeof(w));
+    w.abi_version = SDV_ABI_VERSION;
+    w.vio = vio ? 1 : 0;
+    w.factor_kind = factor_kind;
+    w.n_frames = F;
+    w.n_fixed = (int32_t)fixed_frame_number;
+    w.n_cams = (int32_t)(fw.K.size() / 4);
+    w.n_lmks = (int32_t)fw.landmarks.size();
+    w.n_obs = (int32_t)fw.obs_lmk.size();
+    w.n_imu = (int32_t)fw.imu_i.size();
+    w.T_f_w = fw.T_f_w.data();
+    w.v = fw.v.data(); w.ba = fw.ba.data(); w.bg = fw.bg.data();
+    w.has_imu = fw.has_imu.data(); w.has_prior = fw.has_prior.data();
+    w.T_prior = fw.T_prior.data(); w.inf_prior = fw.inf_prior.data();
+    w.T_s_f = fw.T_s_f.data(); w.K = fw.K.data(); w.lmk_t = fw.lmk_t.data();
+    w.obs_lmk = fw.obs_lmk.data(); w.obs_frame = fw.obs_frame.data(); w.obs_cam = fw.obs_cam.data();
+    w.obs_bearing = fw.obs_bearing.data(); w.obs_uv = fw.obs_uv.data();
+    w.imu_i = fw.imu_i.data(); w.imu_j = fw.imu_j.data(); w.imu_dt = fw.imu_dt.data();
+    w.imu_dR = fw.imu_dR.data(); w.imu_dv = fw.imu_dv.data(); w.imu_dp = fw.imu_dp.data(); w.imu_cov = fw.imu_cov.data();
+    w.imu_J_dR_bg = fw.J_dR_bg.data(); w.imu_J_dv_ba = fw.J_dv_ba.data(); w.imu_J_dv_bg = fw.J_dv_bg.data();
+    w.imu_J_dp_ba = fw.J_dp_ba.data(); w.imu_J_dp_bg = fw.J_dp_bg.data();
+    w.imu_sigma_ba = fw.sigma_ba.data(); w.imu_sigma_bg = fw.sigma_bg.data();
+}
+
+namespace detail {
+inline void exp_so3(const double *v, double *R) { // geometry.h:131-147
+    double a = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double K[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+    if (a < 1e-9) {
+        for (int i = 0; i < 9; i++) R[i] = K[i] + (i % 4 == 0 ? 1.0 : 0.0);
+        return;
+    }
+    for (int i = 0; i < 9; i++) K[i] /= a;
+    double K2[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+    for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + (1 - std::cos(a)) * K2[i] + std::sin(a) * K[i];
+}
+inline void mul33(const double *A, const double *B, double *C) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+} // namespace detail
+
+// State write-back of AOptimizer.cpp:391-434 (pose on the right, additive landmark / velocity / biases, then
+// IMU::biasDeltaCorrection of every frame with its PREVIOUS keyframe's dba/dbg, IMU.cpp:104-108).
+inline void write_back(FlatWindow &fw, const sdv_delta &d, bool vio) {
+    const int F = (int)fw.frame_vector.size();
+    for (int f = 0; f < F; f++) {
+        Frame &fr = *fw.frame_vector[f];
+        double dR[9], R[9], Rn[9];
+        detail::exp_so3(d.dpose + 6 * f, dR);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) R[i * 3 + j] = fr.T_f_w[i * 4 + j];
+        detail::mul33(R, dR, Rn);
+        for (int i = 0; i < 3; i++) {
+            double t = fr.T_f_w[i * 4 + 3];
+            for (int j = 0; j < 3; j++) t += R[i * 3 + j] * d.dpose[6 * f + 3 + j];
+            for (int j = 0; j < 3; j++) fr.T_f_w[i * 4 + j] = Rn[i * 3 + j];
+            fr.T_f_w[i * 4 + 3] = t;
+        }
+        if (vio && fr.imu)
+            for (int k = 0; k < 3; k++) {
+                fr.imu->v[k] += d.dv[3 * f + k];
+                fr.imu->ba[k] += d.dba[3 * f + k];
+                fr.imu->bg[k] += d.dbg[3 * f + k];
+            }
+    }
+    for (size_t l = 0; l < fw.landmarks.size(); l++)
+        for (int k = 0; k < 3; k++) fw.landmarks[l]->t_w[k] += d.dlmk[3 * l + k];
+    if (!vio) return;
+    for (size_t p = 0; p < fw.imu_frame_j.size(); p++) {
+        IMU &m = *fw.imu_frame_j[p]->imu;
+        const double *dba = d.dba + 3 * fw.imu_i[p], *dbg = d.dbg + 3 * fw.imu_i[p];
+        double phi[3], E[9], Rn[9];
+        for (int i = 0; i < 3; i++) {
+            double sp = 0, sv = 0;
+            phi[i] = 0;
+            for (int j = 0; j < 3; j++) {
+                sp += m.J_dp_ba[i * 3 + j] * dba[j] + m.J_dp_bg[i * 3 + j] * dbg[j];
+                sv += m.J_dv_ba[i * 3 + j] * dba[j] + m.J_dv_bg[i * 3 + j] * dbg[j];
+                phi[i] += m.J_dR_bg[i * 3 + j] * dbg[j];
+            }
+            m.delta_p[i] += sp;
+            m.delta_v[i] += sv;
+        }
+        detail::exp_so3(phi, E);
+        detail::mul33(m.delta_R.data(), E, Rn);
+        for (int i = 0; i < 9; i++) m.delta_R[i] = Rn[i];
+    }
+}
+
+// Drop-in for the reference optimizer object (one instance = one sdv_handle, as the back-end optimizer instance,
+// slamParameters.cpp:273-274).  `factor_kind` picks what the reference picks by class: AngularAdjustmentCERESAnalytic
+// (SDV_FACTOR_ANGULAR) or BundleAdjustmentCERESAnalytic (SDV_FACTOR_PIXEL).
+class B200Optimizer {
+  public:
+    explicit B200Optimizer(int factor_kind = SDV_FACTOR_ANGULAR, int device = 0) : _kind(factor_kind) {
+        sdv_config cfg;
+        sdv_default_config(&cfg);
+        cfg.device = device;
+        if (sdv_create(&_h, &cfg) != SDV_OK) _h = nullptr; // no GPU -> every solve returns false (there is no CPU path)
+    }
+    ~B200Optimizer() {
+        if (_h) sdv_destroy(_h);
+    }
+    B200Optimizer(const B200Optimizer &) = delete;
+    B200Optimizer &operator=(const B200Optimizer &) = delete;
+
+    bool localMapBA(std::shared_ptr<LocalMap> &local_map, const size_t fixed_frame_number = 0) { return solve(*local_map, fixed_frame_number, false); }
+    bool localMapVIOptimization(std::shared_ptr<LocalMap> &local_map, const size_t fixed_frame_number = 0) {
+        return solve(*local_map, fixed_frame_number, true);
+    }
+    const sdv_stats &lastStats() const { return _stats; }
+
+  private:
+    bool solve(LocalMap &map, size_t fixed, bool vio) {
+        if (!_h) return false;
+        FlatWindow fw;
+        flatten(map, fixed, vio, _kind, fw);
+        const size_t F = fw.frame_vector.size(), L = fw.landmarks.size();
+        std::vector<double> buf(15 * F + 3 * L + 1, 0.0);
+        sdv_delta d;
+        d.dpose = buf.data();
+        d.dv = d.dpose + 6 * F;
+        d.dba = d.dv + 3 * F;
+        d.dbg = d.dba + 3 * F;
+        d.dlmk = d.dbg + 3 * F;
+        int rc = sdv_solve_window(_h, &fw.view, &d, &_stats);
+        if (rc != SDV_OK) return false; // state untouched
+        write_back(fw, d, vio);
+        return true;
+    }
+    sdv_handle *_h = nullptr;
+    int _kind;
+    sdv_stats _stats{};
+};
+
+} // namespace sdvhost

@@ -433,6 +433,85 @@ def make_window(cfg: SynthConfig | str, **overrides) -> abi.Window:
     return win.normalise()
 
 
+def add_dense_prior(win: abi.Window, n_keep: int = 20, seed: int = 1, with_frame: bool = True) -> abi.Window:
+    """Attach a synthetic dense marginalisation prior (isae::MarginalizationFactor, marginalization.hpp:88-218):
+    r = r0 + J dx over the oldest free keyframe's (pose, v, ba, bg) and `n_keep` landmarks that keyframe observes.
+    J = Lambda^1/2 U^T of a random well-conditioned information matrix, as computeJacobiansAndResiduals produces
+    (marginalization.cpp:516-530); a few landmarks carry keep_col = -1 to exercise the skip at marginalization.hpp:139."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    F = win.n_frames
+    f_keep = F - 1 - win.n_fixed if with_frame else -1
+    f_obs = F - 1 - win.n_fixed
+    cand = np.unique(win.obs_lmk[win.obs_frame == f_obs])
+    keep = np.sort(rng.choice(cand, size=min(n_keep, cand.size), replace=False)).astype(np.int32)
+    cols, c = [], 15 if with_frame else 0
+    for k in range(keep.size):
+        if k % 7 == 6:
+            cols.append(-1)
+        else:
+            cols.append(c)
+            c += 3
+    n = c
+    sig = np.array([200.0] * 3 + [100.0] * 3 + [20.0] * 3 + [100.0] * 3 + [2000.0] * 3 if with_frame else [])
+    sig = np.concatenate([sig, np.full(n - sig.size, 10.0)])
+    M = rng.normal(0, 1, (n, n))
+    Q, _ = np.linalg.qr(M)
+    A = np.diag(sig) @ (np.eye(n) + 0.2 * Q)       # square-root information with cross terms
+    J = A
+    r0 = J @ rng.normal(0, 1e-3, n) * 0.5
+    win.dense_prior = abi.DensePrior(J=np.ascontiguousarray(J), r0=r0, frame=f_keep, frame_col=0, keep_lmk=keep,
+                                     keep_col=np.array(cols, dtype=np.int32))
+    return win
+
+
+def _rand_sqrt_inf(rng, n, scale, mix=0.15):
+    M = rng.normal(0, 1, (n, n))
+    Q, _ = np.linalg.qr(M)
+    return np.diag(np.broadcast_to(scale, (n,)).astype(np.float64)) @ (np.eye(n) + mix * Q)
+
+
+def add_sparse_prior_vio(win: abi.Window, n_keep: int = 20, seed: int = 2) -> abi.Window:
+    """Sparsified VIO prior (AngularAdjustmentCERESAnalytic.cpp:390-424): IMUPriordx on the oldest free keyframe + one
+    PoseToLandmarkFactor per kept landmark (relative position of the landmark in that keyframe)."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    F = win.n_frames
+    f = F - 1 - win.n_fixed
+    gt = win.meta
+    T_gt = np.vstack([gt["T_f_w_gt"][f].reshape(3, 4), [0, 0, 0, 1]])
+    cand = np.unique(win.obs_lmk[win.obs_frame == f])
+    keep = np.sort(rng.choice(cand, size=min(n_keep, cand.size), replace=False)).astype(np.int32)
+    delta = (gt["lmk_gt"][keep] @ T_gt[:3, :3].T + T_gt[:3, 3]) + rng.normal(0, 0.01, (keep.size, 3))
+    sq = np.stack([_rand_sqrt_inf(rng, 3, 30.0).reshape(9) for _ in range(keep.size)])
+    scale = np.array([300.0] * 3 + [150.0] * 3 + [30.0] * 3 + [200.0] * 3 + [3000.0] * 3)
+    win.sparse_prior = abi.SparsePrior(
+        has_imu_prior=True, frame=f, T_prior=gt["T_f_w_gt"][f].copy(), v_prior=gt["v_gt"][f].copy(), ba_prior=gt["ba_true"].copy(),
+        bg_prior=gt["bg_true"].copy(), imu_sqrt_inf=_rand_sqrt_inf(rng, 15, scale).reshape(225), p2l_lmk=keep, p2l_delta=delta, p2l_sqrt_inf=sq)
+    return win
+
+
+def add_sparse_prior_vo(win: abi.Window, n_keep: int = 100, seed: int = 3) -> abi.Window:
+    """Sparsified VO prior (AngularAdjustmentCERESAnalytic.cpp:426-482): Landmark3DPrior on the first kept landmark and a
+    chain of LandmarkToLandmarkFactor between consecutive kept landmarks (the Chow-Liu chain of sparsifyVO)."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    F = win.n_frames
+    f = F - 1 - win.n_fixed
+    gt = win.meta
+    cand = np.unique(win.obs_lmk[win.obs_frame == f])
+    keep = rng.choice(cand, size=min(n_keep, cand.size), replace=False).astype(np.int32)  # chain order, not sorted
+    a, b = keep[:-1].copy(), keep[1:].copy()
+    delta = gt["lmk_gt"][a] - gt["lmk_gt"][b] + rng.normal(0, 0.01, (a.size, 3))
+    win.sparse_prior = abi.SparsePrior(
+        has_lmk_prior=True, lmk0=int(keep[0]), lmk_prior=gt["lmk_gt"][keep[0]] + rng.normal(0, 0.01, 3),
+        lmk_sqrt_inf=_rand_sqrt_inf(rng, 3, 20.0).reshape(9), l2l_a=a, l2l_b=b, l2l_delta=delta,
+        l2l_sqrt_inf=np.stack([_rand_sqrt_inf(rng, 3, 40.0).reshape(9) for _ in range(a.size)]))
+    return win
+
+
+def make_c4() -> abi.Window:
+    """BASELINE config 4: 30 KF, two non-overlapping cameras, no IMU, sparsified VO marginal prior (unary + 99-link chain)."""
+    return add_sparse_prior_vo(make_window("C4"), n_keep=100)
+
+
 def apply_delta(win: abi.Window, d: abi.Delta) -> dict:
     """State write-back of AOptimizer.cpp:391-418 on numpy copies: returns the updated state arrays."""
     F = win.n_frames

@@ -1,0 +1,270 @@
+"""GPU parity tests (run with -m gpu on a B200). Everything goes through the C ABI (ctypes -> libsadvio_b200.so).
+
+Bars: landmark-keyframe visibility indices bit-exact; residuals/Jacobians <= 1e-12 relative per element;
+pose / velocity / bias states <= 1e-6 relative after the full LM solve (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from sadvio_b200 import abi, api, synth
+from tests import ref_fixtures as rf
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(b).max()))
+
+
+def random_point(win, seed):
+    rng = np.random.default_rng(seed)
+    F, L = win.n_frames, win.n_lmks
+    x = abi.Delta(rng.normal(0, 0.02, (F, 6)), rng.normal(0, 0.02, (F, 3)), rng.normal(0, 0.01, (F, 3)),
+                  rng.normal(0, 0.001, (F, 3)), rng.normal(0, 0.05, (L, 3)))
+    nf = win.n_fixed
+    if nf:
+        x.dpose[-nf:] = 0
+        x.dv[-nf:] = 0
+        x.dba[-nf:] = 0
+        x.dbg[-nf:] = 0
+    if not win.vio:
+        x.dv[:] = 0
+        x.dba[:] = 0
+        x.dbg[:] = 0
+    return x
+
+
+@pytest.mark.parametrize("name,kind", [("tiny", 0), ("tiny", 1), ("small", 0), ("small", 1), ("C2", 0), ("C2", 1)])
+def test_visual_residuals_and_jacobians(solver, name, kind):
+    win = synth.make_window(name, factor_kind=kind)
+    solver.upload(win)
+    for x in (None, random_point(win, 1)):
+        r, Jp, Jl, _ = solver.eval_visual(x)
+        r0, Jp0, Jl0, _ = orc.eval_visual(win, x)
+        assert rel(r, r0) < 1e-12 and rel(Jp, Jp0) < 1e-12 and rel(Jl, Jl0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "C2"])
+def test_imu_factors(solver, name):
+    win = synth.make_window(name)
+    solver.upload(win)
+    for x in (None, random_point(win, 2)):
+        r, J, rb = solver.eval_imu(x)
+        r0, J0, rb0 = orc.eval_imu(win, x)
+        assert rel(r, r0) < 1e-10 and rel(J, J0) < 1e-10 and rel(rb, rb0) < 1e-12
+
+
+def test_pixel_failed_projection_branch(solver):
+    """Residual zeroed, Jacobian kept when the projection fails (BundleAdjustmentCERESAnalytic.h:63-68)."""
+    win = synth.make_window("tiny", factor_kind=1)
+    win.lmk_t[0] += 50.0       # throws landmark 0 out of every image
+    win.lmk_t[1] = -win.lmk_t[1]  # behind the cameras
+    solver.upload(win)
+    r, Jp, Jl, _ = solver.eval_visual(None)
+    r0, Jp0, Jl0, _ = orc.eval_visual(win, None)
+    m = win.obs_lmk <= 1
+    assert np.all(r0[m] == 0.0) and np.all(r[m] == 0.0)
+    assert np.abs(Jl[m]).max() > 0
+    assert rel(Jp, Jp0) < 1e-12 and rel(Jl, Jl0) < 1e-12 and rel(r, r0) < 1e-12
+
+
+def assert_same_states(win, d, d0, tol=1e-6):
+    """The bar as BASELINE.json words it: updated pose / velocity / bias STATES agree to 1e-6 relative."""
+    a, b = synth.apply_delta(win, d), synth.apply_delta(win, d0)
+    keys = ("T_f_w", "v", "ba", "bg") if win.vio else ("T_f_w",)
+    for k in keys:
+        assert np.abs(a[k] - b[k]).max() <= tol * np.abs(b[k]).max()
+
+
+def solve_both(solver, win, cfg=None):
+    if cfg is not None:
+        s = api.Solver(cfg)
+    else:
+        s = solver
+    rc, d, st = s.solve_window(win)
+    rc0, d0, st0 = orc.solve_window(win, cfg, mode=0, nthreads=8)
+    if cfg is not None:
+        s.close()
+    return (rc, d, st), (rc0, d0, st0)
+
+
+def assert_same_solution(g, o, tol=1e-6):
+    (rc, d, st), (rc0, d0, st0) = g, o
+    assert rc == rc0
+    assert st["iterations"] == st0["iterations"], (st["trace_cost"], st0["trace_cost"])
+    assert st["termination"] == st0["termination"]
+    assert st["trace_accepted"] == st0["trace_accepted"]
+    assert st["num_successful_steps"] == st0["num_successful_steps"]
+    assert rel(st["trace_cost"], st0["trace_cost"]) < 1e-9
+    assert rel(st["trace_radius"], st0["trace_radius"]) < 1e-6
+    assert abs(st["fixed_cost"] - st0["fixed_cost"]) <= 1e-9 * max(1.0, st0["fixed_cost"])
+    # north_star bar: 1e-6 relative on pose / velocity / bias states (blocks that did not move are compared absolutely)
+    for a, b in ((d.dpose, d0.dpose), (d.dv, d0.dv), (d.dba, d0.dba), (d.dbg, d0.dbg)):
+        assert np.abs(a - b).max() <= tol * np.abs(b).max() + 1e-13
+    if d0.dlmk.size:
+        assert np.abs(d.dlmk - d0.dlmk).max() <= 1e-5 * np.abs(d0.dlmk).max() + 1e-13
+
+
+@pytest.mark.parametrize("name,kind", [("tiny", 0), ("tiny", 1), ("small", 0), ("small", 1), ("C2", 0), ("C2", 1)])
+def test_full_solve_matches_oracle(solver, name, kind):
+    win = synth.make_window(name, factor_kind=kind)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert_same_states(win, g[1], o[1])
+
+
+def test_full_solve_c3_headline(solver):
+    """BASELINE.json config 3: 50 KF x 10k landmarks x 80k observations, full VIO factor set."""
+    win = synth.make_window("C3")
+    assert (win.n_frames, win.n_lmks, win.n_obs, win.n_imu) == (50, 10000, 80000, 49)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    new = synth.apply_delta(win, g[1])
+    gt = win.meta
+    assert np.abs(new["T_f_w"] - gt["T_f_w_gt"]).max() < 0.02
+
+
+def test_tight_convergence_matches_oracle(solver):
+    """Trajectory effects vanish when both sides converge tightly (SURVEY §7 'hard parts')."""
+    win = synth.make_window("small")
+    cfg = api.default_config()
+    cfg.function_tolerance = 1e-12
+    cfg.max_num_iterations = 50
+    g, o = solve_both(solver, win, cfg)
+    assert_same_solution(g, o, tol=1e-7)
+
+
+def test_ba_mode_no_imu(solver):
+    """localMapBA: 6 dof per frame, no IMU blocks (AOptimizer.cpp:299-350)."""
+    win = synth.make_window("small", vio=False)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert np.all(g[1].dv == 0)
+
+
+def test_no_fixed_frame_with_prior(solver):
+    win = synth.make_window("small", n_fixed=0)
+    assert_same_solution(*solve_both(solver, win))
+
+
+def test_two_fixed_frames_fixed_cost(solver):
+    """IMU/bias factors between two fixed keyframes and the prior on a fixed keyframe are fixed_cost, not cost."""
+    win = synth.make_window("small", n_fixed=2)
+    g, o = solve_both(solver, win)
+    assert o[2]["fixed_cost"] > 0
+    assert_same_solution(g, o)
+
+
+def test_reference_inertial_optimisation(solver):  # imu_test.cpp:464-487
+    win = rf.free_fall_window()
+    g, o = solve_both(solver, win)
+    rf.check_free_fall(win, g[1])
+    assert_same_solution(g, o)
+
+
+def test_reference_bias_estimation(solver):  # imu_test.cpp:545-568
+    win = rf.bias_window()
+    g, o = solve_both(solver, win)
+    rf.check_bias(win, g[1])
+    assert g[2]["termination"] == o[2]["termination"]
+
+
+@pytest.mark.parametrize("vio", [True, False])
+def test_dense_marginal_prior(solver, vio):
+    """a10: MarginalizationFactor with kept landmarks in the reduced system (…Analytic.cpp:341-383)."""
+    win = synth.add_dense_prior(synth.make_window("small", vio=vio), n_keep=15, with_frame=vio)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert g[2]["n_reduced"] == o[2]["n_reduced"]
+
+
+def test_c3_with_dense_prior_on_100_landmarks(solver):
+    """SURVEY §8(d) C3 variant: dense marginal prior on (oldest free KF + 100 landmarks) -> n = 735 + ~260."""
+    win = synth.add_dense_prior(synth.make_window("C3"), n_keep=100)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+
+
+def test_sparsified_prior_vio(solver):
+    """a11 VIO: IMUPriordx (incl. its un-whitened v/ba/bg Jacobians) + PoseToLandmark pseudo-observations."""
+    win = synth.add_sparse_prior_vio(synth.make_window("small"), 15)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    win = synth.add_sparse_prior_vio(synth.make_window("C2", factor_kind=1), 60)
+    assert_same_solution(*solve_both(solver, win))
+
+
+def test_sparsified_prior_vo_chain(solver):
+    """a11 VO: Landmark3DPrior + LandmarkToLandmark chain; chained landmarks are part of the reduced system."""
+    win = synth.add_sparse_prior_vo(synth.make_window("small", vio=False), 12)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert g[2]["n_reduced"] == 6 * 9 + 3 * 12
+
+
+def test_config4_bimono_nofov_sparsified(solver):
+    """BASELINE config 4: 30 KF, non-overlapping cameras, localMapBA with the sparsified VO prior (99-link chain)."""
+    win = synth.make_c4()
+    assert win.n_frames == 30 and win.n_lmks == 4000 and win.n_obs == 24000 and not win.vio
+    assert_same_solution(*solve_both(solver, win))
+
+
+def test_ragged_and_degenerate_inputs(solver):
+    win = synth.make_window("tiny")
+    # a landmark nobody observes, a landmark seen only from the fixed keyframe, a single-observation landmark
+    keep = np.ones(win.n_obs, bool)
+    keep[win.obs_lmk == 3] = False
+    idx = np.nonzero(win.obs_lmk == 5)[0]
+    keep[idx[1:]] = False
+    for name in ("obs_lmk", "obs_frame", "obs_cam", "obs_bearing", "obs_uv"):
+        setattr(win, name, np.ascontiguousarray(getattr(win, name)[keep]))
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert np.all(g[1].dlmk[3] == 0)
+
+
+def test_invalid_inputs_are_rejected(solver):
+    win = synth.make_window("tiny")
+    bad = synth.make_window("tiny")
+    bad.obs_lmk = bad.obs_lmk[::-1].copy()  # not landmark-major
+    with pytest.raises(RuntimeError):
+        solver.solve_window(bad)
+    bad = synth.make_window("tiny")
+    bad.obs_frame[0] = 99
+    with pytest.raises(RuntimeError):
+        solver.solve_window(bad)
+    solver.solve_window(win)  # the handle stays usable
+
+
+def test_visibility_indices_bit_exact(solver):
+    """The flattening contract: (landmark, frame, camera) triplets reach the kernels unchanged."""
+    win = synth.make_window("small")
+    solver.upload(win)
+    r, Jp, Jl, _ = solver.eval_visual(None)
+    r0, Jp0, Jl0, _ = orc.eval_visual(win, None)
+    # per-observation outputs are in the caller's observation order: any index permutation would break equality
+    assert np.array_equal(np.argsort(np.abs(r[:, 0])), np.argsort(np.abs(r0[:, 0])))
+
+
+def test_optimizer_interface_writeback(solver):
+    """B200Optimizer mirrors AOptimizer::localMapVIOptimization incl. the state write-back (AOptimizer.cpp:391-434)."""
+    win = synth.make_window("small")
+    ref = synth.make_window("small")
+    opt = api.B200Optimizer()
+    assert opt.localMapVIOptimization(win, 1) is True
+    rc0, d0, _ = orc.solve_window(ref)
+    new = synth.apply_delta(ref, d0)
+    assert np.abs(win.T_f_w - new["T_f_w"]).max() < 1e-9
+    assert np.abs(win.ba - new["ba"]).max() < 1e-9
+    # biasDeltaCorrection applied with the previous keyframe's delta (IMU.cpp:104-108)
+    st = orc.imu_state(np.zeros(3), np.zeros(3))
+    p = 0
+    i = int(ref.imu_i[p])
+    s = np.zeros(169)
+    s[28:37], s[37:40], s[40:43] = ref.imu_dR[p], ref.imu_dv[p], ref.imu_dp[p]
+    s[124:133], s[133:142], s[142:151], s[151:160], s[160:169] = (ref.imu_J_dR_bg[p], ref.imu_J_dv_ba[p], ref.imu_J_dv_bg[p],
+                                                                  ref.imu_J_dp_ba[p], ref.imu_J_dp_bg[p])
+    s2 = orc.bias_delta_correction(s, d0.dba[i], d0.dbg[i])
+    assert np.abs(win.imu_dR[p] - s2[28:37]).max() < 1e-12
+    assert np.abs(win.imu_dv[p] - s2[37:40]).max() < 1e-12
+    assert np.abs(win.imu_dp[p] - s2[40:43]).max() < 1e-12

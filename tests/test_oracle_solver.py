@@ -94,3 +94,30 @@ def test_pre_integration_generator_matches_oracle():
         assert np.allclose(pre.cov.reshape(81), orc.imu_get(st, "Sigma"), rtol=1e-12, atol=1e-22)
         for nm in ("J_dR_bg", "J_dv_ba", "J_dv_bg", "J_dp_ba", "J_dp_bg"):
             assert np.allclose(getattr(pre, nm).reshape(9), orc.imu_get(st, nm), atol=1e-14)
+
+
+@pytest.mark.parametrize("vio", [True, False])
+def test_dense_marginal_prior_schur_equals_full(vio):
+    """MarginalizationFactor couples kept landmarks: they stay in the reduced system (elimination group 2)."""
+    win = synth.add_dense_prior(synth.make_window("small", vio=vio), n_keep=15, with_frame=vio)
+    rc0, d0, st0 = orc.solve_window(win, mode=0)
+    rc1, d1, st1 = orc.solve_window(win, mode=1)
+    assert rc0 == rc1 == 0 and st0["iterations"] == st1["iterations"]
+    n_cols = 15 * 9 if vio else 6 * 9
+    n_kept = int(np.sum(win.dense_prior.keep_col >= 0))
+    assert st0["n_reduced"] == n_cols + 3 * n_kept
+    assert np.abs(d0.dpose - d1.dpose).max() < 1e-9 and np.abs(d0.dlmk - d1.dlmk).max() < 1e-8
+    # the prior changes the solution
+    _, d2, _ = orc.solve_window(synth.make_window("small", vio=vio))
+    assert np.abs(d0.dpose - d2.dpose).max() > 1e-6
+
+
+def test_sparsified_priors_schur_equals_full():
+    """a11: IMUPriordx + PoseToLandmark (VIO) and Landmark3DPrior + LandmarkToLandmark chain (VO)."""
+    for win in (synth.add_sparse_prior_vio(synth.make_window("small"), 15), synth.add_sparse_prior_vo(synth.make_window("small", vio=False), 12)):
+        rc0, d0, st0 = orc.solve_window(win, mode=0)
+        rc1, d1, st1 = orc.solve_window(win, mode=1)
+        assert rc0 == rc1 == 0 and st0["iterations"] == st1["iterations"]
+        assert np.abs(d0.dpose - d1.dpose).max() < 1e-9 and np.abs(d0.dlmk - d1.dlmk).max() < 1e-8
+    # chain landmarks live in the reduced system
+    assert st0["n_reduced"] == 6 * 9 + 3 * 12

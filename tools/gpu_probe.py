@@ -50,6 +50,16 @@ def probe(name, **kw):
     print(f" time gpu solve {st['ms_solve_device']:.3f} ms device, {st['ms_total_host']:.3f} ms host, launches {st['kernel_launches']}; oracle {1e3*(t2-t1):.1f} ms")
     for k, nm in ((0, "lin_visual"), (1, "schur"), (2, "cholesky")):
         print(f"  kernel {nm}: {s.time_kernel(k, 20)*1e3:.1f} us")
+    prof = s.debug_read(5, 128).reshape(16, 8)
+    print("  chol phase cycles per rank [wait_Lkk load_Lkk trsm lookahead wait_col update backward]:")
+    for r in (0, 1, 7, 15):
+        print("   rank", r, " ".join(f"{x/1e3:8.1f}k" for x in prof[r, :7]))
+    import ctypes as C
+    mic = np.zeros(64)
+    api.lib().sdv_debug_micro.argtypes = [C.c_void_p, abi.c_double_p]
+    api.lib().sdv_debug_micro(s._h, mic.ctypes.data_as(abi.c_double_p))
+    for i, nm in enumerate(["chol32_reg", "chol32_smem", "trsm32_reg", "trsm32_smem", "diag_update", "dmma_tile", "load_row32", "store_tile"]):
+        print(f"  micro {nm:12s} cycles/rep:", " ".join(f"{x:7.0f}" for x in mic[i * 8:i * 8 + 5]))
     s.close()
 
 if __name__ == "__main__":
