@@ -44,6 +44,11 @@ SDV_DEV void mbar_remote_arrive(uint64_t *bar, unsigned target_rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(target_rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// one arrival on the barrier `bar` of EVERY CTA of the cluster; called by a full (converged) warp: lane r signals CTA r
+SDV_DEV void mbar_arrive_all_warp(uint64_t *bar, int cs, int lane) {
+    __syncwarp();
+    if (lane < cs) mbar_remote_arrive(bar, (unsigned)lane);
+}
 SDV_DEV void mbar_arrive_all(uint64_t *bar, int cs) {
     for (int r = 0; r < cs; r++) mbar_remote_arrive(bar, (unsigned)r);
 }
@@ -233,6 +238,115 @@ SDV_DEV void tile_update_dmma(double *Cg, int ld, const double *As, const double
 //   b2      "panel column published" : count CS — each CTA arrives (on every CTA) after its own triangular solves; the owner of
 //                                      tile row k+1 then updates + factors tile (k+1,k+1) BEFORE waiting (look-ahead), the others
 //                                      wait and run their trailing updates, which depend only on their own rows + the panel column.
+#define SDV_TICK(slot) do { tn = clock64(); tp[slot] += tn - tc; tc = tn; } while (0)
+
+// Second half shared by the factorisation kernels: failure vote, backward solve L^T z = y (left-looking over tile columns,
+// partial products reduced through global scratch + hardware cluster barrier), reduced-parameter update, model-decrease
+// terms and the candidate frame-camera table on cluster rank 0.  Called by every thread of the cluster.
+SDV_DEV void chol_backward_and_update(const DevProblem &P, const LinBuf &B0, const LinBuf &B1, LMState *st, Accum *acc, double *Lo,
+                                      double *dinv, double *partial, const double *damp_p, const double *graw_p, double *dxp, double *sK,
+                                      double *sinv, double *xs, double *wsum, bool fail, double *prof, long long *tp, long long tc) {
+    const int ld = P.ld, T = P.n_pad / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = (int)cluster_rank(), CS = (int)cluster_size();
+    constexpr int NW = CCT / 32;
+    long long tn;
+    if (fail) acc->chol_fail = 1;
+    cluster_sync_all();
+    const bool bad = __ldcg(&acc->chol_fail) != 0 || __ldcg(&acc->schur_fail) != 0; // same answer on every CTA
+    if (bad) {
+        if (rank == 0 && threadIdx.x == 0) {
+            st->step_valid = 0;
+            st->model_cost_change = 0.0;
+        }
+        return;
+    }
+    // ---------------- backward solve L^T z = y, left-looking over tile columns
+    const double *y = Lo + (size_t)(T * 32) * ld;
+    tc = clock64();
+    for (int k = T - 1; k >= 0; k--) {
+        const int owner = k % CS;
+        __syncthreads(); // xs of the previous step visible to every warp
+        const int first = k + 1 + ((rank - (k + 1)) % CS + CS) % CS;
+        double s = 0.0;
+        for (int i = first + warp * CS; i < T; i += NW * CS) {
+            const double *Lt = Lo + (size_t)(i * 32) * ld + k * 32 + lane;
+            const double *xi = xs + (size_t)(i / CS) * 32;
+            double v[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r] = __ldcg(Lt + (size_t)r * ld); // 32 independent L2 loads in flight
+#pragma unroll
+            for (int r = 0; r < 32; r++) s += v[r] * xi[r];
+        }
+        wsum[warp * 32 + lane] = s;
+        if (rank == owner) { // the diagonal tile for the triangular solve
+            for (int e = threadIdx.x; e < 512; e += CCT) {
+                int r = e >> 4, q = e & 15;
+                double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(k * 32 + r) * ld + k * 32) + q);
+                sK[r * TSTR + 2 * q] = v.x;
+                sK[r * TSTR + 2 * q + 1] = v.y;
+            }
+            if (threadIdx.x < 32) sinv[threadIdx.x] = __ldcg(dinv + k * 32 + threadIdx.x);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; w2++) tot += wsum[w2 * 32 + lane];
+            partial[((size_t)k * CC_MAX + rank) * 32 + lane] = tot;
+        }
+        cluster_sync_all();
+        if (rank == owner && warp == 0) {
+            double yy = __ldcg(y + k * 32 + lane);
+            for (int r = 0; r < CS; r++) yy -= __ldcg(partial + ((size_t)k * CC_MAX + r) * 32 + lane);
+            double x = 0;
+#pragma unroll
+            for (int c = 31; c >= 0; c--) {
+                double xc = __shfl_sync(FULL, yy, c) * sinv[c];
+                if (lane == c) x = xc;
+                if (lane < c) yy -= sK[c * TSTR + lane] * xc;
+            }
+            xs[(size_t)(k / CS) * 32 + lane] = x;
+            dxp[k * 32 + lane] = -x; // S delta = -g
+        }
+    }
+    cluster_sync_all();
+    SDV_TICK(6);
+    if (prof && threadIdx.x == 0)
+        for (int q = 0; q < 7; q++) prof[rank * 8 + q] = (double)tp[q];
+    if (rank != 0) return;
+    // ---------------- reduced-parameter update, model-decrease terms, candidate frame-camera table (cluster rank 0)
+    const LinBuf &Bx = st->cur ? B1 : B0;
+    const LinBuf &Bc = st->cur ? B0 : B1;
+    const int n = P.n;
+    double gd = 0, dd = 0, sn = 0, cn = 0;
+    for (int i = threadIdx.x; i < P.n_pad; i += CCT) {
+        double d = i < n ? __ldcg(dxp + i) : 0.0;
+        if (i >= n) dxp[i] = 0.0;
+        double xc = Bx.xp[i] + d;
+        Bc.xp[i] = i < n ? xc : 0.0;
+        if (i < n) {
+            gd += graw_p[i] * d;
+            dd += damp_p[i] * d * d;
+            sn += d * d;
+            cn += xc * xc;
+        }
+    }
+    gd = warp_sum(gd);
+    dd = warp_sum(dd);
+    sn = warp_sum(sn);
+    cn = warp_sum(cn);
+    if (lane == 0 && P.rank == 0) {
+        atomicAdd(&acc->model_gd, gd);
+        atomicAdd(&acc->model_dd, dd);
+        atomicAdd(&acc->step_norm2, sn);
+        atomicAdd(&acc->cand_norm2, cn);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.F * P.C; i += CCT) compute_fct_row(P, Bc.xp, i / P.C, i % P.C, Bc.fct + (size_t)i * FCT_ROW);
+    if (threadIdx.x == 0) st->step_valid = 1;
+}
+
 template <bool REG>
 __global__ void __launch_bounds__(CCT, 1) k_chol_cluster(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, double *A, double *Lo,
                                                          double *dinv, double *partial, const double *damp_p, const double *graw_p, double *dxp,
@@ -252,7 +366,6 @@ __global__ void __launch_bounds__(CCT, 1) k_chol_cluster(DevProblem P, LinBuf B0
     bool fail = false;
     // optional phase timing (cycles, summed over panels): [rank][0 wait L_kk, 1 load L_kk, 2 trsm, 3 look-ahead, 4 wait column, 5 update, 6 backward]
     long long tp[7] = {0, 0, 0, 0, 0, 0, 0}, tc = clock64(), tn;
-#define SDV_TICK(slot) do { tn = clock64(); tp[slot] += tn - tc; tc = tn; } while (0)
 
     if (threadIdx.x == 0) {
         mbar_init(&b1[0], 1);
@@ -362,8 +475,93 @@ __global__ void __launch_bounds__(CCT, 1) k_chol_cluster(DevProblem P, LinBuf B0
         __syncthreads(); // sRow / sK are rewritten in the next panel
         SDV_TICK(5);
     }
+    chol_backward_and_update(P, B0, B1, st, acc, Lo, dinv, partial, damp_p, graw_p, dxp, sK, sinv, xs, wsum, fail, prof, tp, tc);
+}
+
+// Hybrid register Cholesky: the pivot column is broadcast through a 32-double shared-memory buffer (one store + broadcast
+// loads per column) instead of 2 SHFL per element — SHFL issue was the throughput limit of chol32_reg (8.3k cycles/tile);
+// only the element of the NEXT pivot column, which sits on the dependency chain, still goes through a shuffle.
+SDV_DEV bool chol32_hyb(double (&a)[32], int lane, double *invd, double *colbuf /* shared, [2][32] */) {
+    // Software-pipelined: the next pivot (shuffle + rsqrt, the dependency chain) is issued BEFORE the bulk of the current
+    // column's rank-1 update, which then fills the latency of the reciprocal square root.
+    bool ok = true;
+    double d = __shfl_sync(FULL, a[0], 0);
+    if (!(d > 0.0) || !isfinite(d)) {
+        ok = false;
+        d = 1.0;
+    }
+    double inv = rsqrt(d);
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        double l = a[c] * inv;
+        if (lane == c) {
+            l = d * inv;
+            *invd = inv;
+        }
+        if (lane < c) l = 0.0;
+        a[c] = l;
+        if (c + 1 < 32) {
+            a[c + 1] -= l * __shfl_sync(FULL, l, c + 1); // the next pivot column first
+            d = __shfl_sync(FULL, a[c + 1], c + 1);
+            if (!(d > 0.0) || !isfinite(d)) {
+                ok = false;
+                d = 1.0;
+            }
+            inv = rsqrt(d);                               // in flight during the updates below
+            if (c + 2 < 32) {
+                double *cb = colbuf + (c & 1) * 32;
+                cb[lane] = l;
+                __syncwarp();
+#pragma unroll
+                for (int c2 = c + 2; c2 < 32; c2++) a[c2] -= l * cb[c2];
+            }
+        }
+    }
+    return ok;
+}
+
+SDV_DEV void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// cluster-scope release: the panel warps read the updated tiles back through L2 (__ldcg)
+SDV_DEV void mbar_arrive_local(uint64_t *bar) { asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+SDV_DEV void mbar_wait_local(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITL_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEL_%=;\n"
+        "bra WAITL_%=;\n"
+        "DONEL_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// DSMEM store of one double into the shared memory of CTA `target_rank` of the cluster
+SDV_DEV void dsmem_store(double *local_addr, unsigned target_rank, double v) {
+    unsigned local = smem_u32(local_addr), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(target_rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+// Backward solve, version 2 (replaces the global-scratch + cluster-barrier scheme of chol_backward_and_update):
+//  * every CTA first inverts the diagonal tiles it owns (X = L_kk^-T by a register TRSM on the identity, all CTAs in
+//    parallel), so that a step is a 32x32 matrix-vector product instead of a 32-step substitution;
+//  * the partial products sum_{own i > k} L_ik^T x_i are sent straight into the owner's shared memory (DSMEM stores)
+//    followed by one remote mbarrier arrive; only the owner of step k waits, the others run ahead.
+// tiles : shared, >= ceil(T/CS) tiles of [32][TSTR] (the sRow region); red : shared [CC_MAX][32]; bk : mbarrier, count CS.
+SDV_DEV void chol_backward_v2(const DevProblem &P, const LinBuf &B0, const LinBuf &B1, LMState *st, Accum *acc, double *Lo, double *dinv,
+                              const double *damp_p, const double *graw_p, double *dxp, double *tiles, double *tinv, double *xs, double *wsum,
+                              double *red, uint64_t *bk, bool fail, double *prof, long long *tp, long long tc) {
+    const int ld = P.ld, T = P.n_pad / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = (int)cluster_rank(), CS = (int)cluster_size();
+    constexpr int NW = CCT / 32;
+    long long tn;
+    if (threadIdx.x == 0) mbar_init(bk, CS);
     if (fail) acc->chol_fail = 1;
-    cluster_sync_all();
+    __syncthreads();
+    cluster_sync_all(); // L complete and visible, failure flag visible, bk initialised everywhere
     const bool bad = __ldcg(&acc->chol_fail) != 0 || __ldcg(&acc->schur_fail) != 0; // same answer on every CTA
     if (bad) {
         if (rank == 0 && threadIdx.x == 0) {
@@ -372,54 +570,74 @@ __global__ void __launch_bounds__(CCT, 1) k_chol_cluster(DevProblem P, LinBuf B0
         }
         return;
     }
-    // ---------------- backward solve L^T z = y, left-looking over tile columns
-    const double *y = Lo + (size_t)(T * 32) * ld;
     tc = clock64();
+    // ---- inverse of the own diagonal tiles: tile q of this CTA is tile row kk = rank + q*CS
+    const int ndiag = rank < T ? (T - 1 - rank) / CS + 1 : 0;
+    for (int q = warp; q < ndiag; q += NW) {
+        const int kk = rank + q * CS;
+        double *Lt = tiles + (size_t)q * 32 * TSTR, *iv = tinv + q * 32;
+        for (int e = lane; e < 512; e += 32) {
+            int r = e >> 4, c2 = e & 15;
+            double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(kk * 32 + r) * ld + kk * 32) + c2);
+            Lt[r * TSTR + 2 * c2] = v.x;
+            Lt[r * TSTR + 2 * c2 + 1] = v.y;
+        }
+        iv[lane] = __ldcg(dinv + kk * 32 + lane);
+        __syncwarp();
+        double a[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) a[c] = (c == lane) ? 1.0 : 0.0;
+        trsm32_reg(a, Lt, iv); // row `lane` of I * L^-T
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; c++) Lt[lane * TSTR + c] = a[c];
+    }
+    __syncthreads();
+    const double *y = Lo + (size_t)(T * 32) * ld;
     for (int k = T - 1; k >= 0; k--) {
         const int owner = k % CS;
-        __syncthreads(); // xs of the previous step visible to every warp
+        // partial product of this CTA for step k over its own rows i > k (their x_i were solved by this CTA)
         const int first = k + 1 + ((rank - (k + 1)) % CS + CS) % CS;
         double s = 0.0;
         for (int i = first + warp * CS; i < T; i += NW * CS) {
-            const double *Lt = Lo + (size_t)(i * 32) * ld + k * 32 + lane;
+            const double *Lc = Lo + (size_t)(i * 32) * ld + k * 32 + lane;
             const double *xi = xs + (size_t)(i / CS) * 32;
             double v[32];
 #pragma unroll
-            for (int r = 0; r < 32; r++) v[r] = __ldcg(Lt + (size_t)r * ld); // 32 independent L2 loads in flight
+            for (int r = 0; r < 32; r++) v[r] = __ldcg(Lc + (size_t)r * ld);
 #pragma unroll
             for (int r = 0; r < 32; r++) s += v[r] * xi[r];
         }
         wsum[warp * 32 + lane] = s;
-        if (rank == owner) { // the diagonal tile for the triangular solve
-            for (int e = threadIdx.x; e < 512; e += CCT) {
-                int r = e >> 4, q = e & 15;
-                double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(k * 32 + r) * ld + k * 32) + q);
-                sK[r * TSTR + 2 * q] = v.x;
-                sK[r * TSTR + 2 * q + 1] = v.y;
-            }
-            if (threadIdx.x < 32) sinv[threadIdx.x] = __ldcg(dinv + k * 32 + threadIdx.x);
-        }
         __syncthreads();
         if (warp == 0) {
             double tot = 0;
 #pragma unroll
             for (int w2 = 0; w2 < NW; w2++) tot += wsum[w2 * 32 + lane];
-            partial[((size_t)k * CC_MAX + rank) * 32 + lane] = tot;
-        }
-        cluster_sync_all();
-        if (rank == owner && warp == 0) {
-            double yy = __ldcg(y + k * 32 + lane);
-            for (int r = 0; r < CS; r++) yy -= __ldcg(partial + ((size_t)k * CC_MAX + r) * 32 + lane);
-            double x = 0;
+            dsmem_store(red + rank * 32 + lane, (unsigned)owner, tot);
+            __syncwarp();
+            if (lane == 0) mbar_remote_arrive(bk, (unsigned)owner);
+            if (rank == owner) {
+                mbar_wait_cluster(bk, (unsigned)(((T - 1 - k) / CS) & 1));
+                double yy = __ldcg(y + k * 32 + lane);
 #pragma unroll
-            for (int c = 31; c >= 0; c--) {
-                double xc = __shfl_sync(FULL, yy, c) * sinv[c];
-                if (lane == c) x = xc;
-                if (lane < c) yy -= sK[c * TSTR + lane] * xc;
+                for (int r = 0; r < CC_MAX; r++)
+                    if (r < CS) yy -= red[r * 32 + lane];
+                wsum[lane] = yy; // y' for the matrix-vector product
+                __syncwarp();
+                const double *X = tiles + (size_t)(k / CS) * 32 * TSTR + lane * TSTR; // row `lane` of L_kk^-T (upper triangular)
+                double x0 = 0, x1 = 0;
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    x0 += X[c] * wsum[c];
+                    x1 += X[c + 1] * wsum[c + 1];
+                }
+                const double x = x0 + x1;
+                xs[(size_t)(k / CS) * 32 + lane] = x;
+                dxp[k * 32 + lane] = -x; // S delta = -g
             }
-            xs[(size_t)(k / CS) * 32 + lane] = x;
-            dxp[k * 32 + lane] = -x; // S delta = -g
         }
+        __syncthreads(); // wsum reuse; xs of this step visible to every warp of the owner
     }
     cluster_sync_all();
     SDV_TICK(6);
@@ -458,6 +676,167 @@ __global__ void __launch_bounds__(CCT, 1) k_chol_cluster(DevProblem P, LinBuf B0
     if (threadIdx.x == 0) st->step_valid = 1;
 }
 
+constexpr int NPW = 2;             // panel warps: triangular solves of the panel column + look-ahead factorisation
+constexpr int NUW = CCT / 32 - NPW; // update warps: trailing tile updates (FP64 tensor-core MMA)
+
+// Warp-specialised variant of the cluster factorisation.  The per-panel critical chain
+//     L_kk published -> load L_kk -> TRSM of tile row k+1 -> update + factor tile (k+1,k+1) -> L_(k+1)(k+1) published
+// runs on the two PANEL warps of the CTAs involved and never waits for the bulk of the trailing update, which the six
+// UPDATE warps of every CTA perform one panel behind.  Each trailing tile is always updated by the same warp (no
+// read-modify-write races across panels); sRow is double-buffered by panel parity; dependencies:
+//   b1[k&1] (cluster) : L_kk published                           owner panel warp 0  -> every panel warp
+//   b2      (cluster) : panel column k published                 every CTA           -> every update warp
+//   udone   (CTA)     : tiles of columns <= k+2 updated for panel k (and all of panel k-1), so tile column k+1 and the
+//                       diagonal tile (k+2,k+2) are final          update warps        -> panel warps of the same CTA
+// HYB selects the shared-memory-broadcast Cholesky of the diagonal tile.
+template <bool HYB>
+__global__ void __launch_bounds__(CCT, 1) k_chol_ws(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, double *A, double *Lo, double *dinv,
+                                                    double *partial, const double *damp_p, const double *graw_p, double *dxp, int max_rows,
+                                                    double *prof) {
+    if (st->status != 0) return; // uniform over the cluster
+    extern __shared__ __align__(16) double csm[];
+    __shared__ uint64_t b1[2], b2, udone, bk;
+    double *sK = csm;                                   // [32][TSTR] diagonal tile L_kk
+    double *sinv = sK + 32 * TSTR;                      // [32]
+    double *colbuf = sinv + 32;                         // [2][32]
+    double *sRow = colbuf + 64;                         // [2][max_rows][32][TSTR] own tiles of the panel column, by panel parity
+    double *xs = sRow + (size_t)2 * max_rows * 32 * TSTR; // [max_rows][32]
+    double *wsum = xs + (size_t)max_rows * 32;          // [8][32]
+    double *red = wsum + 8 * 32;                        // [CC_MAX][32] partial products received from the other CTAs
+    double *tinv = red + CC_MAX * 32;                   // [max_rows][32] reciprocal diagonals of the own diagonal tiles
+    const int ld = P.ld, T = P.n_pad / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = (int)cluster_rank(), CS = (int)cluster_size();
+    const size_t row_buf = (size_t)max_rows * 32 * TSTR;
+    bool fail = false;
+    long long tp[7] = {0, 0, 0, 0, 0, 0, 0}, tc = clock64(), tn;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&b1[0], 1);
+        mbar_init(&b1[1], 1);
+        mbar_init(&b2, CS);
+        mbar_init(&udone, NUW);
+    }
+    __syncthreads();
+    cluster_sync_all(); // every CTA's barriers are initialised before anybody arrives remotely
+
+    // Warps 0 and 4 share SM sub-partition 0: making them the panel warps keeps the critical look-ahead factorisation off the
+    // sub-partitions that run the tensor-core updates.
+    const bool is_panel = (warp & 3) == 0;
+    const int pw = warp >> 2;                  // panel warp index 0 / 1
+    if (is_panel) {
+        // =================================================== panel warps
+        for (int k = -1; k < T; k++) {
+            const int owner = (k + CS) % CS, next_owner = (k + 1) % CS;
+            double *rows = sRow + (size_t)(k & 1) * row_buf;
+            if (k >= 0) {
+                tc = clock64();
+                mbar_wait_cluster(&b1[k & 1], (unsigned)((k >> 1) & 1)); // L_kk and its reciprocal diagonal are visible
+                SDV_TICK(0);
+                if (rank != owner && pw == 0) {
+                    for (int e = lane; e < 512; e += 32) {
+                        int r = e >> 4, q = e & 15;
+                        double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(k * 32 + r) * ld + k * 32) + q);
+                        sK[r * TSTR + 2 * q] = v.x;
+                        sK[r * TSTR + 2 * q + 1] = v.y;
+                    }
+                    sinv[lane] = __ldcg(dinv + k * 32 + lane);
+                }
+                if (k >= 1) mbar_wait_local(&udone, (unsigned)((k - 1) & 1)); // own tile column k is final, sRow[k&1] is free
+                named_bar_sync(1, NPW * 32);
+                SDV_TICK(1);
+                const int first = k + 1 + ((rank - (k + 1)) % CS + CS) % CS;
+                const int nown = first <= T ? (T - first) / CS + 1 : 0;
+                for (int s = pw; s < nown; s += NPW) {
+                    int i = first + s * CS;
+                    double *X = rows + (size_t)s * 32 * TSTR;
+                    {
+                        double a[32];
+                        load_row32(A + (size_t)(i * 32 + lane) * ld + k * 32, a);
+                        trsm32_reg(a, sK, sinv);
+#pragma unroll
+                        for (int c = 0; c < 32; c++) X[lane * TSTR + c] = a[c];
+                    }
+                    __syncwarp();
+                    for (int e = lane; e < 512; e += 32) { // publish L_ik, coalesced 256-byte row segments
+                        int r = e >> 4, q = e & 15;
+                        reinterpret_cast<double2 *>(Lo + (size_t)(i * 32 + r) * ld + k * 32)[q] = make_double2(X[r * TSTR + 2 * q], X[r * TSTR + 2 * q + 1]);
+                    }
+                }
+                named_bar_sync(1, NPW * 32);
+                SDV_TICK(2);
+                if (pw == 0) mbar_arrive_all_warp(&b2, CS, lane); // this CTA's part of the panel column is published
+            }
+            if ((k + 1 < T) && rank == next_owner && pw == 0) {
+                // look-ahead: tile (k+1,k+1) -= L_{k+1,k} L_{k+1,k}^T (row slot 0 of this panel), then factor it.
+                // sK held L_kk, which this CTA no longer needs: it becomes L_{k+1,k+1} for the next panel.
+                double a[32];
+                load_row32(A + (size_t)((k + 1) * 32 + lane) * ld + (k + 1) * 32, a);
+                if (k >= 0) {
+#pragma unroll 1
+                    for (int q = 0; q < 32; q++) {
+                        double lq = rows[(size_t)lane * TSTR + q];
+#pragma unroll
+                        for (int c = 0; c < 32; c++) a[c] -= lq * rows[(size_t)c * TSTR + q];
+                    }
+                }
+                double inv = 1.0;
+                bool ok = HYB ? chol32_hyb(a, lane, &inv, colbuf) : chol32_reg(a, lane, &inv);
+                if (!ok) fail = true;
+#pragma unroll
+                for (int c = 0; c < 32; c++) sK[lane * TSTR + c] = a[c];
+                sinv[lane] = inv;
+                dinv[(k + 1) * 32 + lane] = inv;
+                __syncwarp();
+                for (int e = lane; e < 512; e += 32) {
+                    int r = e >> 4, q = e & 15;
+                    reinterpret_cast<double2 *>(Lo + (size_t)((k + 1) * 32 + r) * ld + (k + 1) * 32)[q] =
+                        make_double2(sK[r * TSTR + 2 * q], sK[r * TSTR + 2 * q + 1]);
+                }
+                mbar_arrive_all_warp(&b1[(k + 1) & 1], CS, lane);
+                SDV_TICK(3);
+            }
+        }
+    } else {
+        // =================================================== update warps
+        const int uw = warp - 1 - (warp >> 2); // warps 1,2,3,5,6,7 -> 0..5
+        for (int k = 0; k < T; k++) {
+            const double *rows = sRow + (size_t)(k & 1) * row_buf;
+            const int first = k + 1 + ((rank - (k + 1)) % CS + CS) % CS;
+            const int nown = first <= T ? (T - first) / CS + 1 : 0;
+            const bool skip0 = (k + 1 < T) && rank == (k + 1) % CS; // tile (k+1,k+1) belongs to the look-ahead
+            tc = clock64();
+            mbar_wait_cluster(&b2, (unsigned)(k & 1)); // every L_jk of this panel column is visible (incl. our own rows in sRow)
+            SDV_TICK(4);
+            bool arrived = false;
+            for (int j = k + 1; j < T; j++) { // tile columns in the order the panel warps will need them
+                if (!arrived && j > k + 2) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_local(&udone);
+                    arrived = true;
+                }
+                for (int s = skip0 ? 1 : 0; s < nown; s++) {
+                    const int i = first + s * CS;
+                    if (i < j) continue;
+                    if ((j + 3 * (i / CS)) % NUW != uw) continue; // a tile is always updated by the same warp
+                    const bool j_own = (j % CS) == rank;      // then L_jk sits in sRow as well
+                    const double *Bp = j_own ? rows + (size_t)((j - first) / CS) * 32 * TSTR : Lo + (size_t)(j * 32) * ld + k * 32;
+                    tile_update_dmma(A + (size_t)(i * 32) * ld + j * 32, ld, rows + (size_t)s * 32 * TSTR, Bp, j_own ? TSTR : ld, !j_own, lane);
+                }
+            }
+            if (!arrived) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(&udone);
+            }
+            SDV_TICK(5);
+        }
+    }
+    __syncthreads();
+    if (partial) // legacy backward solve (global scratch + hardware cluster barrier), kept for A/B timing
+        chol_backward_and_update(P, B0, B1, st, acc, Lo, dinv, partial, damp_p, graw_p, dxp, sK, sinv, xs, wsum, fail, prof, tp, tc);
+    else
+        chol_backward_v2(P, B0, B1, st, acc, Lo, dinv, damp_p, graw_p, dxp, sRow, tinv, xs, wsum, red, &bk, fail, prof, tp, tc);
+}
 
 // Developer micro-benchmark: cycles of the tile routines, single warp, 5 repetitions each (the first one has cold code).
 // out[routine * 8 + rep]; routines: 0 chol32_reg, 1 chol32_smem, 2 trsm32_reg, 3 trsm32_smem, 4 diag update (rolled q),

@@ -974,23 +974,28 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B
             }
         }
         __syncwarp();
-        // off-diagonal pairs (a > b in slot order), 36 entries each, spread over the G lanes of the group
+        // off-diagonal pairs (a > b in slot order): work item = (pair, row i) -> the 6 entries of row i of -Y_a W_b^T
         if (eliminate) {
-            const int npairs = m * (m - 1) / 2;
-            for (int e = lig; e < npairs * 36; e += G) {
-                int pi = e / 36, ij = e - pi * 36;
-                int sa = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pi)) * 0.5f);
-                while (sa * (sa - 1) / 2 > pi) sa--;
-                while ((sa + 1) * sa / 2 <= pi) sa++;
-                int sb = pi - sa * (sa - 1) / 2;
-                int ca = scol[gib][sa], cb = scol[gib][sb];
+            const int nitems = m * (m - 1) / 2 * 6;
+            for (int e = lig; e < nitems; e += G) {
+                const int pi = e / 6, i = e - pi * 6;
+                int sa = 1, base = 0; // pair index -> (sa, sb), sa > sb: pairs are enumerated (1,0),(2,0),(2,1),(3,0)...
+                while (base + sa <= pi) {
+                    base += sa;
+                    sa++;
+                }
+                const int sb = pi - base;
+                const int ca = scol[gib][sa], cb = scol[gib][sb];
                 if (ca < 0 || cb < 0) continue;
-                int i = ij / 6, j = ij - i * 6;
                 const double *Ya = &WY[gib][sa][18 + i * 3];
-                const double *Wb = &WY[gib][sb][j * 3];
-                double v = -(Ya[0] * Wb[0] + Ya[1] * Wb[1] + Ya[2] * Wb[2]);
-                if (ca > cb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cb + j], v);
-                else atomicAdd(&Sb[(size_t)(cb + j) * ld + ca + i], v);
+                const double y0 = Ya[0], y1 = Ya[1], y2 = Ya[2];
+                const double *Wb = &WY[gib][sb][0];
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    double v = -(y0 * Wb[j * 3] + y1 * Wb[j * 3 + 1] + y2 * Wb[j * 3 + 2]);
+                    if (ca > cb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cb + j], v);
+                    else atomicAdd(&Sb[(size_t)(cb + j) * ld + ca + i], v);
+                }
             }
         }
         __syncwarp();

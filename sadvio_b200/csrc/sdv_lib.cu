@@ -91,7 +91,7 @@ struct sdv_handle {
     bool resident = false;
     int lin_grid = 0, lin_smem = 0, sch_grid = 0, fac_grid = 0;
     int group = 32; // lanes per landmark in k_schur / k_backsub (8, 16 or 32 by the largest slot count)
-    int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_reg = 1; // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
+    int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_variant = 2; // 0: k_chol_cluster (register tiles), 1: k_chol_ws + shuffle Cholesky, 2: k_chol_ws + hybrid // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
     double *d_partial = nullptr, *d_dinv = nullptr, *d_prof = nullptr;
     int64_t launches = 0;
     // whole-solve CUDA graph: prologue -> WHILE(LM iteration) -> epilogue (single-GPU only)
@@ -347,6 +347,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
                 return fail(h, SDV_ERR_INVALID_ARGUMENT, "dense prior landmark index/column out of range");
     }
     cudaSetDevice(h->device);
+    const bool timing = getenv("SDV_TIMING") != nullptr;
+    auto tu0 = std::chrono::steady_clock::now();
 
     // ---- reduced-program structure (what Ceres' preprocessor derives: constant blocks dropped, unused blocks dropped)
     std::vector<char> pose_used(F, 0), vb_used(F, 0);
@@ -641,7 +643,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             std::memcpy(hb + o_l2s, sp->l2l_sqrt_inf, D * 9 * nl2l);
         }
     }
-    (void)t_pack0;
+    auto t_pack1 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
@@ -765,16 +767,20 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     h->fac_grid = std::max(1, (std::max(Pn, 1) + FAC_WARPS - 1) / FAC_WARPS);
     // dense Cholesky: one thread-block cluster when the reduced system is small enough, per-panel launches otherwise
     h->chol_cluster = 0;
-    if (n_pad <= 2048 && !getenv("SDV_NO_CLUSTER")) {
-        h->chol_reg = getenv("SDV_CHOL_SMEM") ? 0 : 1;
-        CK(cudaFuncSetAttribute(k_chol_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CK(cudaFuncSetAttribute(k_chol_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(k_chol_cluster<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CK(cudaFuncSetAttribute(k_chol_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (n_pad <= 4096 && !getenv("SDV_NO_CLUSTER")) {
+        if (const char *v = getenv("SDV_CHOL_VARIANT")) h->chol_variant = atoi(v);
+        auto prep = [&](const void *fn) {
+            cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        };
+        prep((const void *)k_chol_cluster<true>);
+        prep((const void *)k_chol_ws<false>);
+        prep((const void *)k_chol_ws<true>);
+        CK(cudaGetLastError());
         const int T = n_pad / 32;
         for (int cs : {16, 8, 4, 2, 1}) {
             int rows = (T + 1 + cs - 1) / cs;
-            int smem = (int)(sizeof(double) * (32 * TSTR + 32 + (size_t)rows * 32 * TSTR + (size_t)rows * 32 + 8 * 32));
+            int smem = (int)(sizeof(double) * (32 * TSTR + 32 + 64 + (size_t)2 * rows * 32 * TSTR + (size_t)rows * 32 + 8 * 32 + CC_MAX * 32 + (size_t)rows * 32));
             if (smem > 200 * 1024) continue;
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3(cs);
@@ -788,7 +794,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             lc.attrs = at1;
             lc.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, k_chol_cluster<true>, &lc) == cudaSuccess && nclusters >= 1) {
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_chol_ws<true>, &lc) == cudaSuccess && nclusters >= 1) {
                 h->chol_cluster = cs;
                 h->chol_rows = rows;
                 h->chol_smem = smem;
@@ -811,7 +817,14 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     CK(cudaStreamSynchronize(h->stream));
     if ((rc = ensure(h, &h->h_sol, &h->sol_cap, out_bytes + sizeof(LMState) + sizeof(Accum) + 256, true)) != SDV_OK) return rc;
     h->resident = true;
+    auto t_g0 = std::chrono::steady_clock::now();
     if ((rc = build_solve_graph(h)) != SDV_OK) return rc;
+    if (timing) {
+        auto t_g1 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[sdv upload] structure %.3f ms, pack %.3f ms, h2d+setup %.3f ms, graph %.3f ms\n", ms(tu0, t_pack0), ms(t_pack0, t_pack1),
+                     ms(t_pack1, t_g0), ms(t_g0, t_g1));
+    }
     return SDV_OK;
 }
 
@@ -914,7 +927,9 @@ int launch_factor_solve(sdv_handle *h) {
         at1[0].val.clusterDim.z = 1;
         lc.attrs = at1;
         lc.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&lc, h->chol_reg ? k_chol_cluster<true> : k_chol_cluster<false>, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, h->d_partial,
+        auto kfn = h->chol_variant == 0 ? k_chol_cluster<true> : (h->chol_variant == 1 ? k_chol_ws<false> : k_chol_ws<true>);
+        double *partial = (h->chol_variant == 0 || getenv("SDV_CHOL_BACK_V1")) ? h->d_partial : nullptr;
+        cudaError_t e = cudaLaunchKernelEx(&lc, kfn, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, partial,
                                            (const double *)h->d_damp_p, (const double *)h->d_graw_p, h->d_dxp, h->chol_rows, h->d_prof);
         if (e != cudaSuccess) return fail(h, SDV_ERR_CUDA, std::string("k_chol_cluster launch: ") + cudaGetErrorString(e));
         h->launches++;
