@@ -229,6 +229,42 @@ SDV_DEV void tile_update_dmma(double *Cg, int ld, const double *As, const double
             *reinterpret_cast<double2 *>(Cg + (size_t)(ib * 8 + g) * ld + jb * 8 + 2 * t) = make_double2(c[ib][jb][0], c[ib][jb][1]);
 }
 
+// C(32x32, global) -= A(32x32) * B(32x32)^T with both operands read from global memory (L2) — used when trailing tiles are
+// spread over every update warp of the cluster and a CTA no longer owns whole tile rows.
+SDV_DEV void tile_update_dmma_gg(double *Cg, const double *Ag, const double *Bg, int ld, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double b[4][8], a[4][8];
+#pragma unroll
+    for (int jb = 0; jb < 4; jb++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            b[jb][kk] = __ldcg(Bg + (size_t)(jb * 8 + g) * ld + kk * 4 + t);
+            a[jb][kk] = __ldcg(Ag + (size_t)(jb * 8 + g) * ld + kk * 4 + t);
+        }
+    double c[4][4][2];
+#pragma unroll
+    for (int ib = 0; ib < 4; ib++)
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++) {
+            double2 v = *reinterpret_cast<const double2 *>(Cg + (size_t)(ib * 8 + g) * ld + jb * 8 + 2 * t);
+            c[ib][jb][0] = v.x;
+            c[ib][jb][1] = v.y;
+        }
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++)
+#pragma unroll
+        for (int ib = 0; ib < 4; ib++) {
+            const double na = -a[ib][kk];
+#pragma unroll
+            for (int jb = 0; jb < 4; jb++) dmma(c[ib][jb][0], c[ib][jb][1], na, b[jb][kk]);
+        }
+#pragma unroll
+    for (int ib = 0; ib < 4; ib++)
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++)
+            *reinterpret_cast<double2 *>(Cg + (size_t)(ib * 8 + g) * ld + jb * 8 + 2 * t) = make_double2(c[ib][jb][0], c[ib][jb][1]);
+}
+
 // A  : (n_pad + 32) x ld reduced system, lower triangle + right-hand side in row n_pad; overwritten by the trailing updates.
 // Lo : receives L (and y^T = (L^-1 g)^T in row n_pad).  dinv : [n_pad] reciprocal diagonal of L.
 // partial : [T][CC_MAX][32] scratch for the backward solve.
@@ -838,6 +874,170 @@ __global__ void __launch_bounds__(CCT, 1) k_chol_ws(DevProblem P, LinBuf B0, Lin
         chol_backward_v2(P, B0, B1, st, acc, Lo, dinv, damp_p, graw_p, dxp, sRow, tinv, xs, wsum, red, &bk, fail, prof, tp, tc);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-level role split.  In k_chol_ws the panel warp shares its SM with six tensor-core update warps; their shared-memory
+// and LSU traffic stretches the critical tile factorisation 2x in the early (update-heavy) panels.  Here the first NP CTAs of
+// the cluster are PANEL CTAs (L_kk factorisation, all triangular solves of the panel column) and the other CS-NP are UPDATE
+// CTAs (trailing tile updates only), so the dependency chain
+//     L_kk published -> load L_kk -> TRSM tile row k+1 -> update + factor tile (k+1,k+1) -> published
+// runs on SMs that do nothing else.
+//   b1[k&1] : count 1      owner panel CTA (k % NP), warp 0          -> every panel CTA      "L_kk published"
+//   b2      : count NP     every panel CTA after its TRSMs           -> every update CTA     "panel column k published"
+//   udone   : count NU*8   every update warp after its urgent tiles  -> every panel CTA      "tile columns <= k+2 final"
+// Tile row i is solved by panel CTA i % NP (warp (i / NP) % 8) and updated by update CTA NP + i % NU; a trailing tile is
+// always updated by the same warp.  Backward solve: chol_backward_v2 on all CS CTAs.
+template <int NP>
+__global__ void __launch_bounds__(CCT, 1) k_chol_roles(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, double *A, double *Lo, double *dinv,
+                                                       const double *damp_p, const double *graw_p, double *dxp, int max_rows, double *prof) {
+    if (st->status != 0) return; // uniform over the cluster
+    extern __shared__ __align__(16) double csm[];
+    __shared__ uint64_t b1[2], b2, udone, bk;
+    constexpr int NW = CCT / 32;
+    double *sK = csm;                                   // [32][TSTR] diagonal tile L_kk (panel CTAs)
+    double *sinv = sK + 32 * TSTR;                      // [32]
+    double *colbuf = sinv + 32;                         // [2][32]
+    double *sDiag = colbuf + 64;                        // [32][TSTR] prefetched tile (k+1,k+1) (panel CTAs)
+    double *sRow = sDiag + 32 * TSTR;                   // [2][max_rows][32][TSTR]: panel CTA: look-ahead operand; backward solve: tile inverses
+    double *xs = sRow + (size_t)2 * max_rows * 32 * TSTR;
+    double *wsum = xs + (size_t)max_rows * 32;
+    double *red = wsum + 8 * 32;
+    double *tinv = red + CC_MAX * 32;
+    const int ld = P.ld, T = P.n_pad / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = (int)cluster_rank(), CS = (int)cluster_size();
+    const int NU = CS - NP;
+    const size_t row_buf = (size_t)max_rows * 32 * TSTR;
+    bool fail = false;
+    long long tp[7] = {0, 0, 0, 0, 0, 0, 0}, tc = clock64(), tn;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&b1[0], 1);
+        mbar_init(&b1[1], 1);
+        mbar_init(&b2, NP);
+        mbar_init(&udone, NU * NW);
+    }
+    __syncthreads();
+    cluster_sync_all();
+
+    if (rank < NP) {
+        // =================================================== panel CTA
+        for (int k = -1; k < T; k++) {
+            const int owner = (k + NP) % NP, next_owner = (k + 1) % NP;
+            const bool lookahead = (k + 1 < T) && rank == next_owner && warp == 0;
+            double *rows = sRow + (size_t)(k & 1) * row_buf;
+            double a[32];
+            if (k >= 0) {
+                // rows i > k with i % NP == rank; slot s handles row first + s*NP; row k+1 (if ours) is slot 0 -> warp 0
+                const int first = k + 1 + ((rank - (k + 1)) % NP + NP) % NP;
+                const int nown = first <= T ? (T - first) / NP + 1 : 0;
+                tc = clock64();
+                if (k >= 1) mbar_wait_cluster(&udone, (unsigned)((k - 1) & 1)); // tile column k and tile (k+1,k+1) are final
+                SDV_TICK(1);
+                // prefetch everything that does not depend on L_kk: the TRSM operand row (registers) and, for the look-ahead,
+                // this lane's row of tile (k+1,k+1) (asynchronous copy into shared memory)
+                if (warp < nown) load_row32(A + (size_t)((first + warp * NP) * 32 + lane) * ld + k * 32, a);
+                if (lookahead) {
+                    const double *src = A + (size_t)((k + 1) * 32 + lane) * ld + (k + 1) * 32;
+                    const unsigned dst = smem_u32(sDiag + lane * TSTR);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(src + c) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                mbar_wait_cluster(&b1[k & 1], (unsigned)((k >> 1) & 1)); // L_kk and its reciprocal diagonal are visible
+                SDV_TICK(0);
+                if (rank != owner) {
+                    for (int e = threadIdx.x; e < 512; e += CCT) {
+                        int r = e >> 4, q = e & 15;
+                        double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(k * 32 + r) * ld + k * 32) + q);
+                        sK[r * TSTR + 2 * q] = v.x;
+                        sK[r * TSTR + 2 * q + 1] = v.y;
+                    }
+                    if (threadIdx.x < 32) sinv[threadIdx.x] = __ldcg(dinv + k * 32 + threadIdx.x);
+                }
+                __syncthreads();
+                for (int s = warp; s < nown; s += NW) {
+                    const int i = first + s * NP;
+                    if (s != warp) load_row32(A + (size_t)(i * 32 + lane) * ld + k * 32, a);
+                    trsm32_reg(a, sK, sinv);
+                    if (s == 0) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) rows[lane * TSTR + c] = a[c]; // the look-ahead operand
+                    }
+                    store_row32(Lo + (size_t)(i * 32 + lane) * ld + k * 32, a);
+                }
+                __syncthreads();
+                SDV_TICK(2);
+                if (warp == 1) { // this CTA's part of the panel column is published -> every update CTA
+                    __syncwarp();
+                    if (lane < NU) mbar_remote_arrive(&b2, (unsigned)(NP + lane));
+                }
+            }
+            if (lookahead) {
+                if (k >= 0) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 32; c++) a[c] = sDiag[lane * TSTR + c];
+#pragma unroll 1
+                    for (int q = 0; q < 32; q++) {
+                        double lq = rows[(size_t)lane * TSTR + q];
+#pragma unroll
+                        for (int c = 0; c < 32; c++) a[c] -= lq * rows[(size_t)c * TSTR + q];
+                    }
+                } else {
+                    load_row32(A + (size_t)lane * ld, a);
+                }
+                SDV_TICK(4); // (panel CTA) diagonal update
+                double inv = 1.0;
+                if (!chol32_hyb(a, lane, &inv, colbuf)) fail = true;
+                SDV_TICK(5); // (panel CTA) tile factorisation alone
+#pragma unroll
+                for (int c = 0; c < 32; c++) sK[lane * TSTR + c] = a[c];
+                sinv[lane] = inv;
+                dinv[(k + 1) * 32 + lane] = inv;
+                store_row32(Lo + (size_t)((k + 1) * 32 + lane) * ld + (k + 1) * 32, a);
+                __syncwarp();
+                if (lane < NP) mbar_remote_arrive(&b1[(k + 1) & 1], (unsigned)lane);
+                SDV_TICK(3); // (panel CTA) publish
+            }
+        }
+    } else {
+        // =================================================== update CTA: every warp is an independent worker
+        // Trailing tile (i, j) belongs to global update warp (5 i + j) mod NUWT for the whole factorisation (no read-modify-write
+        // races between panels, load balanced over all update warps of the cluster); per tile column j a warp owns the rows
+        // i = i0 + m NUWT with 5 i0 + j = gw (mod NUWT). Operands come from L2.
+        const int NUWT = NU * NW;
+        const int gw = (rank - NP) * NW + warp;
+        int inv5 = 1; // modular inverse of 5 (NUWT = 96 -> 77)
+        while ((5 * inv5) % NUWT != 1 % NUWT && inv5 < NUWT) inv5++;
+        for (int k = 0; k < T; k++) {
+            tc = clock64();
+            mbar_wait_cluster(&b2, (unsigned)(k & 1)); // the whole panel column k is in Lo
+            SDV_TICK(4);
+            bool arrived = false;
+            for (int j = k + 1; j < T; j++) { // tile columns in the order the panel CTAs will need them
+                if (!arrived && j > k + 2) {
+                    __syncwarp();
+                    if (lane < NP) mbar_remote_arrive(&udone, (unsigned)lane);
+                    arrived = true;
+                }
+                int i0 = (int)(((long long)((gw - j) % NUWT + NUWT) * inv5) % NUWT);
+                for (int i = i0; i <= T; i += NUWT) {
+                    if (i < j || (i == k + 1 && j == k + 1)) continue; // tile (k+1,k+1) belongs to the look-ahead
+                    tile_update_dmma_gg(A + (size_t)(i * 32) * ld + j * 32, Lo + (size_t)(i * 32) * ld + k * 32, Lo + (size_t)(j * 32) * ld + k * 32, ld, lane);
+                }
+            }
+            if (!arrived) {
+                __syncwarp();
+                if (lane < NP) mbar_remote_arrive(&udone, (unsigned)lane);
+            }
+            SDV_TICK(5);
+        }
+    }
+    __syncthreads();
+    chol_backward_v2(P, B0, B1, st, acc, Lo, dinv, damp_p, graw_p, dxp, sRow, tinv, xs, wsum, red, &bk, fail, prof, tp, tc);
+}
+
 // Developer micro-benchmark: cycles of the tile routines, single warp, 5 repetitions each (the first one has cold code).
 // out[routine * 8 + rep]; routines: 0 chol32_reg, 1 chol32_smem, 2 trsm32_reg, 3 trsm32_smem, 4 diag update (rolled q),
 // 5 tile_update_dmma (C in global), 6 load_row32 (L2), 7 store tile rows
@@ -865,12 +1065,14 @@ __global__ void k_chol_micro(double *scratch /* >= 4 * 32 * 64 doubles */, doubl
             if (lane == 0) out[0 * 8 + rep] = (double)(t1 - t0);
             __syncwarp();
         }
-        {   // 1: chol32_smem
-            for (int c = 0; c < 32; c++) sX[lane * TSTR + c] = sA[lane * TSTR + c];
+        {   // 1: chol32_hyb
+            double a[32], inv = 1;
+            for (int c = 0; c < 32; c++) a[c] = sA[lane * TSTR + c];
             __syncwarp();
             t0 = clock64();
-            chol32_smem(sX, sinv, lane);
+            chol32_hyb(a, lane, &inv, sX);
             t1 = clock64();
+            sink += a[lane & 31 ? 2 : 0] + inv;
             if (lane == 0) out[1 * 8 + rep] = (double)(t1 - t0);
             __syncwarp();
         }
@@ -880,7 +1082,7 @@ __global__ void k_chol_micro(double *scratch /* >= 4 * 32 * 64 doubles */, doubl
             t0 = clock64();
             trsm32_reg(a, sL, sinv);
             t1 = clock64();
-            sink += a[3];
+            for (int c = 0; c < 32; c++) sink += a[c];
             if (lane == 0) out[2 * 8 + rep] = (double)(t1 - t0);
             __syncwarp();
         }

@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf
             int fc = P.obs_fc[o];
             double p[3], meas[3], r[2], Jp[12], Jl[6];
             landmark_position(P, B, l, p);
-            meas[0] = P.obs_meas[o];
-            meas[1] = P.obs_meas[(size_t)P.O + o];
-            meas[2] = KIND == 0 ? P.obs_meas[2 * (size_t)P.O + o] : 0.0;
+            constexpr int MP = KIND == 0 ? 3 : 2; // bearing[3] or uv[2], array-of-structs
+            meas[0] = P.obs_meas[(size_t)o * MP];
+            meas[1] = P.obs_meas[(size_t)o * MP + 1];
+            meas[2] = KIND == 0 ? P.obs_meas[(size_t)o * MP + 2] : 0.0;
             const double *row = fct + (size_t)fc * fstride;
             double w = P.obs_w ? P.obs_w[o] : row[30];
             eval_visual<KIND>(row, P.K + 4 * (fc % P.C), w, p, meas, r, Jp, Jl);

@@ -91,13 +91,15 @@ struct sdv_handle {
     bool resident = false;
     int lin_grid = 0, lin_smem = 0, sch_grid = 0, fac_grid = 0;
     int group = 32; // lanes per landmark in k_schur / k_backsub (8, 16 or 32 by the largest slot count)
-    int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_variant = 2; // 0: k_chol_cluster (register tiles), 1: k_chol_ws + shuffle Cholesky, 2: k_chol_ws + hybrid // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
+    int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_variant = 2, chol_rows_roles = 0, chol_smem_roles = 0; // 0: k_chol_cluster, 1: k_chol_ws + shuffle Cholesky, 2: k_chol_ws + hybrid, 3: k_chol_roles // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
     double *d_partial = nullptr, *d_dinv = nullptr, *d_prof = nullptr;
     int64_t launches = 0;
     // whole-solve CUDA graph: prologue -> WHILE(LM iteration) -> epilogue (single-GPU only)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     cudaStream_t stream2 = nullptr;
+    cudaStream_t side = nullptr;           // fork/join branch for the small factor kernels (runs concurrently with the landmark kernels)
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
     unsigned long long cond = 0;
     bool graph_ok = false;
     DevProblem graph_P;
@@ -107,6 +109,7 @@ struct sdv_handle {
     // comm
     void *comm = nullptr;
     int rank = 0, world = 1;
+    std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs; // reused between uploads
     LMState h_state;
     Accum h_acc;
 };
@@ -215,6 +218,11 @@ int sdv_create(sdv_handle **out, const sdv_config *cfg) {
         return SDV_ERR_CUDA;
     }
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+    }
     std::memset(&h->P, 0, sizeof(h->P));
     *out = h;
     return SDV_OK;
@@ -228,6 +236,11 @@ int sdv_destroy(sdv_handle *h) {
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->graph) cudaGraphDestroy(h->graph);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->side) cudaStreamDestroy(h->side);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
     if (h->h_sol) cudaFreeHost(h->h_sol);
     if (h->d_in) cudaFree(h->d_in);
     if (h->h_in) cudaFreeHost(h->h_in);
@@ -328,11 +341,26 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             if (sp->l2l_a[k] < 0 || sp->l2l_a[k] >= L || sp->l2l_b[k] < 0 || sp->l2l_b[k] >= L || sp->l2l_a[k] == sp->l2l_b[k])
                 return fail(h, SDV_ERR_INVALID_ARGUMENT, "l2l landmark out of range");
     }
-    for (int o = 0; o < O; o++) {
-        if (w->obs_lmk[o] < 0 || w->obs_lmk[o] >= L || w->obs_frame[o] < 0 || w->obs_frame[o] >= F || w->obs_cam[o] < 0 || w->obs_cam[o] >= C)
-            return fail(h, SDV_ERR_INVALID_ARGUMENT, "observation index out of range");
-        if (o > 0 && w->obs_lmk[o] < w->obs_lmk[o - 1])
-            return fail(h, SDV_ERR_INVALID_ARGUMENT, "observations must be landmark-major (reference walk order)");
+    // one pass over the observations: range checks, landmark-major order, CSR pointer per landmark, frames in use
+    std::vector<int> &lmk_ptr = h->tmp_lmk_ptr;
+    lmk_ptr.assign((size_t)L + 1, 0);
+    std::vector<char> pose_used(F, 0), vb_used(F, 0);
+    {
+        const int32_t *ol = w->obs_lmk, *of = w->obs_frame, *oc = w->obs_cam;
+        int prev = -1;
+        unsigned bad = 0;
+        for (int o = 0; o < O; o++) {
+            const int l = ol[o], f = of[o], c = oc[o];
+            bad |= (unsigned)(l < 0) | (unsigned)(l >= L) | (unsigned)(f < 0) | (unsigned)(f >= F) | (unsigned)(c < 0) | (unsigned)(c >= C) | (unsigned)(l < prev);
+            if (bad) break;
+            if (l != prev) {
+                for (int q = prev + 1; q <= l; q++) lmk_ptr[q] = o;
+                prev = l;
+            }
+            pose_used[f] = 1;
+        }
+        if (bad) return fail(h, SDV_ERR_INVALID_ARGUMENT, "observation index out of range or observations not landmark-major (reference walk order)");
+        for (int q = prev + 1; q <= L; q++) lmk_ptr[q] = O;
     }
     for (int p = 0; p < Pn; p++)
         if (w->imu_i[p] < 0 || w->imu_i[p] >= F || w->imu_j[p] < 0 || w->imu_j[p] >= F || w->imu_i[p] == w->imu_j[p])
@@ -351,8 +379,6 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     auto tu0 = std::chrono::steady_clock::now();
 
     // ---- reduced-program structure (what Ceres' preprocessor derives: constant blocks dropped, unused blocks dropped)
-    std::vector<char> pose_used(F, 0), vb_used(F, 0);
-    for (int o = 0; o < O; o++) pose_used[w->obs_frame[o]] = 1;
     for (int p = 0; p < Pn; p++) {
         pose_used[w->imu_i[p]] = pose_used[w->imu_j[p]] = 1;
         vb_used[w->imu_i[p]] = vb_used[w->imu_j[p]] = 1;
@@ -408,8 +434,17 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
 
     // ---- landmark shard of this rank (contiguous, balanced by observation count)
     int l0 = 0, l1 = L, o0 = 0, o1 = O;
-    if (sdv_shard_range(w->obs_lmk, O, L, h->rank, h->world, &l0, &l1, &o0, &o1) != SDV_OK)
-        return fail(h, SDV_ERR_INVALID_ARGUMENT, "cannot shard landmarks");
+    if (h->world > 1) {
+        auto cut = [&](int r) {
+            long long target = (long long)O * r / h->world;
+            int l = (int)(std::lower_bound(lmk_ptr.begin(), lmk_ptr.end(), (int)target) - lmk_ptr.begin());
+            return std::min(l, L);
+        };
+        l0 = h->rank == 0 ? 0 : cut(h->rank);         // identical to sdv_shard_range
+        l1 = h->rank == h->world - 1 ? L : cut(h->rank + 1);
+        o0 = lmk_ptr[l0];
+        o1 = lmk_ptr[l1];
+    }
     const int Oloc = o1 - o0;
 
     // ---- slots: (landmark, distinct keyframe) groups over the real observations and the PoseToLandmark pseudo-observations;
@@ -430,43 +465,93 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         }
     }
     const int Ocap = Oloc + 2 * n_pseudo;
-    std::vector<int> slot_ptr(L + 1, 0), slot_frame, slot_obs_ptr, slot_obs;
-    slot_frame.reserve(O);
-    slot_obs_ptr.reserve(O + 1);
-    slot_obs.reserve((size_t)O + 2 * n_pseudo);
+    std::vector<int> &slot_ptr = h->tmp_slot_ptr, &slot_frame = h->tmp_slot_frame, &slot_obs_ptr = h->tmp_slot_obs_ptr, &slot_obs = h->tmp_slot_obs;
+    slot_ptr.resize((size_t)L + 1);
+    slot_frame.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
+    slot_obs_ptr.resize((size_t)O + 2 * (size_t)n_pseudo + 2);
+    slot_obs.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
+    int ns = 0, nso = 0;
     {
-        int o = 0;
-        std::vector<int> tmp_frames;
-        std::vector<std::pair<int, int>> ent; // (frame, plane index)
+        const int32_t *of = w->obs_frame;
+        std::vector<int> ef, ep; // (frame, plane index) of the landmark's entries, only used when pseudo-observations exist
         for (int l = 0; l < L; l++) {
-            slot_ptr[l] = (int)slot_frame.size();
-            ent.clear();
-            tmp_frames.clear();
-            while (o < O && w->obs_lmk[o] == l) {
-                ent.push_back({w->obs_frame[o], o - o0});
-                o++;
-            }
-            if (np2l)
-                for (int k : p2l_of_lmk[l]) {
-                    ent.push_back({sp->frame, p2l_plane[k]});
-                    ent.push_back({sp->frame, p2l_plane[k] + 1});
+            slot_ptr[l] = ns;
+            const int a0 = lmk_ptr[l], b0 = lmk_ptr[l + 1];
+            const int first_slot = ns;
+            if (!np2l || p2l_of_lmk[l].empty()) {
+                // fast path: observations of one keyframe are normally adjacent (stereo pairs), so one forward pass builds the
+                // slots; a frame that re-appears after another one falls back to the general grouping below
+                bool grouped = true;
+                {
+                    const int ns_save = ns, nso_save = nso;
+                    int cur = -1;
+                    for (int o = a0; o < b0 && grouped; o++) {
+                        const int f = of[o];
+                        if (f != cur) {
+                            for (int q = first_slot; q < ns; q++) grouped &= slot_frame[q] != f;
+                            slot_frame[ns] = f;
+                            slot_obs_ptr[ns] = nso;
+                            ns++;
+                            cur = f;
+                        }
+                        slot_obs[nso++] = o - o0;
+                    }
+                    if (!grouped) {
+                        ns = ns_save;
+                        nso = nso_save;
+                    }
                 }
-            for (auto &e : ent)
-                if (std::find(tmp_frames.begin(), tmp_frames.end(), e.first) == tmp_frames.end()) tmp_frames.push_back(e.first);
-            if ((int)tmp_frames.size() > MAX_SLOTS)
-                return fail(h, SDV_ERR_UNSUPPORTED, "a landmark is observed from more than 32 keyframes (kernel limit of this build)");
-            for (int f : tmp_frames) {
-                slot_frame.push_back(f);
-                slot_obs_ptr.push_back((int)slot_obs.size());
-                for (auto &e : ent)
-                    if (e.first == f) slot_obs.push_back(e.second);
+                if (!grouped) {
+                    // distinct frames in first-appearance order; per-landmark observation counts are small: linear scans
+                    for (int o = a0; o < b0; o++) {
+                        const int f = of[o];
+                        int sidx = -1;
+                        for (int q = first_slot; q < ns; q++)
+                            if (slot_frame[q] == f) {
+                                sidx = q;
+                                break;
+                            }
+                        if (sidx < 0) slot_frame[ns++] = f;
+                    }
+                    for (int q = first_slot; q < ns; q++) {
+                        slot_obs_ptr[q] = nso;
+                        const int f = slot_frame[q];
+                        for (int o = a0; o < b0; o++)
+                            if (of[o] == f) slot_obs[nso++] = o - o0;
+                    }
+                }
+            } else {
+                ef.clear();
+                ep.clear();
+                for (int o = a0; o < b0; o++) {
+                    ef.push_back(of[o]);
+                    ep.push_back(o - o0);
+                }
+                for (int k : p2l_of_lmk[l]) {
+                    ef.push_back(sp->frame);
+                    ep.push_back(p2l_plane[k]);
+                    ef.push_back(sp->frame);
+                    ep.push_back(p2l_plane[k] + 1);
+                }
+                for (size_t e = 0; e < ef.size(); e++) {
+                    bool seen = false;
+                    for (int q = first_slot; q < ns; q++) seen |= slot_frame[q] == ef[e];
+                    if (!seen) slot_frame[ns++] = ef[e];
+                }
+                for (int q = first_slot; q < ns; q++) {
+                    slot_obs_ptr[q] = nso;
+                    for (size_t e = 0; e < ef.size(); e++)
+                        if (ef[e] == slot_frame[q]) slot_obs[nso++] = ep[e];
+                }
             }
+            if (ns - first_slot > MAX_SLOTS)
+                return fail(h, SDV_ERR_UNSUPPORTED, "a landmark is observed from more than 32 keyframes (kernel limit of this build)");
         }
-        slot_ptr[L] = (int)slot_frame.size();
-        slot_obs_ptr.push_back((int)slot_obs.size());
+        slot_ptr[L] = ns;
+        slot_obs_ptr[ns] = nso;
     }
-    const int nslots = (int)slot_frame.size();
-    const int nslotobs = (int)slot_obs.size();
+    const int nslots = ns;
+    const int nslotobs = nso;
     int max_slots = 1;
     for (int l = 0; l < L; l++) max_slots = std::max(max_slots, slot_ptr[l + 1] - slot_ptr[l]);
 
@@ -583,10 +668,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         std::memcpy(hb + o_ol, w->obs_lmk, 4 * O);
         int *fc = at<int>(hb, o_ofc);
         for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o];
-        double *om = at<double>(hb, o_om);
-        const double *src = kind == SDV_FACTOR_ANGULAR ? w->obs_bearing : w->obs_uv;
-        for (int o = 0; o < O; o++)
-            for (int k = 0; k < mplanes; k++) om[(size_t)k * O + o] = src[(size_t)o * mplanes + k];
+        // measurements stay array-of-structs (a warp still reads one contiguous 768 / 512-byte span): no host-side transposition
+        std::memcpy(hb + o_om, kind == SDV_FACTOR_ANGULAR ? w->obs_bearing : w->obs_uv, D * (size_t)mplanes * O);
         if (w->obs_sigma) {
             double *ow = at<double>(hb, o_ow);
             for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
@@ -776,6 +859,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         prep((const void *)k_chol_cluster<true>);
         prep((const void *)k_chol_ws<false>);
         prep((const void *)k_chol_ws<true>);
+        prep((const void *)k_chol_roles<4>);
         CK(cudaGetLastError());
         const int T = n_pad / 32;
         for (int cs : {16, 8, 4, 2, 1}) {
@@ -798,6 +882,11 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
                 h->chol_cluster = cs;
                 h->chol_rows = rows;
                 h->chol_smem = smem;
+                // role-split variant: 4 panel CTAs + (cs - 4) update CTAs, only with a full 16-CTA cluster
+                h->chol_rows_roles = std::max(1, (T + cs - 1) / cs); // shared-memory tiles: look-ahead operand / backward-solve tile inverses
+                h->chol_smem_roles = (int)(sizeof(double) * (32 * TSTR + 32 + 64 + 32 * TSTR + (size_t)2 * h->chol_rows_roles * 32 * TSTR +
+                                                            (size_t)h->chol_rows_roles * 32 + 8 * 32 + CC_MAX * 32 + (size_t)h->chol_rows_roles * 32));
+                if (cs != 16 || h->chol_smem_roles > 200 * 1024) { if (h->chol_variant == 3) h->chol_variant = 2; }
                 break;
             }
             cudaGetLastError();
@@ -849,7 +938,30 @@ void launch_backsub(sdv_handle *h) {
     h->launches++;
 }
 
-int launch_linearize(sdv_handle *h, int which) {
+// fork: work launched on h->side after this call runs concurrently with what follows on h->stream (also under stream capture)
+bool fork_side(sdv_handle *h, int slot) {
+    if (!h->side) return false;
+    if (cudaEventRecord(h->ev_fork[slot], h->stream) != cudaSuccess) return false;
+    return cudaStreamWaitEvent(h->side, h->ev_fork[slot], 0) == cudaSuccess;
+}
+void join_side(sdv_handle *h, int slot) {
+    cudaEventRecord(h->ev_join[slot], h->side);
+    cudaStreamWaitEvent(h->stream, h->ev_join[slot], 0);
+}
+
+bool has_factors(const DevProblem &P) {
+    return P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0 || P.sp_has_imu || P.sp_has_lmk || P.sp_nl2l > 0);
+}
+
+void launch_lin_factors(sdv_handle *h, int which, cudaStream_t s) {
+    const DevProblem &P = h->P;
+    if (has_factors(P)) {
+        k_lin_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        h->launches++;
+    }
+}
+
+void launch_lin_visual(sdv_handle *h, int which) {
     const DevProblem &P = h->P;
     if (P.o1 > P.o0) {
         if (P.kind == SDV_FACTOR_ANGULAR)
@@ -858,14 +970,15 @@ int launch_linearize(sdv_handle *h, int which) {
             k_lin_visual<1><<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
         h->launches++;
     }
-    if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0 || P.sp_has_imu || P.sp_has_lmk || P.sp_nl2l > 0)) {
-        k_lin_factors<<<h->fac_grid, FAC_WARPS * 32, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
-        h->launches++;
-    }
     if (P.sp_np2l > 0) {
         k_lin_p2l<<<(P.sp_np2l + 127) / 128, 128, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
         h->launches++;
     }
+}
+
+int launch_linearize(sdv_handle *h, int which) {
+    launch_lin_visual(h, which);
+    launch_lin_factors(h, which, h->stream);
     return SDV_OK;
 }
 
@@ -927,10 +1040,17 @@ int launch_factor_solve(sdv_handle *h) {
         at1[0].val.clusterDim.z = 1;
         lc.attrs = at1;
         lc.numAttrs = 1;
-        auto kfn = h->chol_variant == 0 ? k_chol_cluster<true> : (h->chol_variant == 1 ? k_chol_ws<false> : k_chol_ws<true>);
-        double *partial = (h->chol_variant == 0 || getenv("SDV_CHOL_BACK_V1")) ? h->d_partial : nullptr;
-        cudaError_t e = cudaLaunchKernelEx(&lc, kfn, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, partial,
-                                           (const double *)h->d_damp_p, (const double *)h->d_graw_p, h->d_dxp, h->chol_rows, h->d_prof);
+        cudaError_t e;
+        if (h->chol_variant == 3) {
+            lc.dynamicSmemBytes = h->chol_smem_roles;
+            e = cudaLaunchKernelEx(&lc, k_chol_roles<4>, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, (const double *)h->d_damp_p,
+                                   (const double *)h->d_graw_p, h->d_dxp, h->chol_rows_roles, h->d_prof);
+        } else {
+            auto kfn = h->chol_variant == 0 ? k_chol_cluster<true> : (h->chol_variant == 1 ? k_chol_ws<false> : k_chol_ws<true>);
+            double *partial = (h->chol_variant == 0 || getenv("SDV_CHOL_BACK_V1")) ? h->d_partial : nullptr;
+            e = cudaLaunchKernelEx(&lc, kfn, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, partial, (const double *)h->d_damp_p,
+                                   (const double *)h->d_graw_p, h->d_dxp, h->chol_rows, h->d_prof);
+        }
         if (e != cudaSuccess) return fail(h, SDV_ERR_CUDA, std::string("k_chol_cluster launch: ") + cudaGetErrorString(e));
         h->launches++;
         return SDV_OK;
@@ -955,15 +1075,23 @@ int launch_iteration(sdv_handle *h) {
     cudaStream_t s = h->stream;
     k_iter_begin<<<1, 1, 0, s>>>(h->d_st);
     if (cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s) != cudaSuccess) return fail(h, SDV_ERR_CUDA, "memset S");
-    launch_schur(h);
     h->launches += 2;
-    if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0)) {
-        k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
-        h->launches++;
-    }
-    if (P.rank == 0 && (P.sp_has_imu || P.sp_has_lmk || P.sp_nl2l > 0)) {
-        k_assemble_sparse<<<2, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
-        h->launches++;
+    {
+        // the non-visual factors accumulate into S with atomics as well: run them beside the landmark Schur kernel
+        const bool fa = P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0);
+        const bool fs = P.rank == 0 && (P.sp_has_imu || P.sp_has_lmk || P.sp_nl2l > 0);
+        const bool forked = (fa || fs) && fork_side(h, 0);
+        cudaStream_t fstream = forked ? h->side : s;
+        launch_schur(h);
+        if (fa) {
+            k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, fstream>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
+            h->launches++;
+        }
+        if (fs) {
+            k_assemble_sparse<<<2, 128, 0, fstream>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
+            h->launches++;
+        }
+        if (forked) join_side(h, 0);
     }
     if (h->world > 1) {
         // one all-reduce of [S | g | diag | grad] per LM iteration, plus the gradient-violation flag
@@ -981,8 +1109,14 @@ int launch_iteration(sdv_handle *h) {
         int rcf = launch_factor_solve(h);
         if (rcf != SDV_OK) return rcf;
     }
-    launch_backsub(h);
-    launch_linearize(h, -2);
+    {
+        // candidate linearisation: the factor kernel only needs the reduced parameters -> beside back-substitution + visual kernel
+        const bool forked = has_factors(P) && fork_side(h, 1);
+        launch_lin_factors(h, -2, forked ? h->side : s);
+        launch_backsub(h);
+        launch_lin_visual(h, -2);
+        if (forked) join_side(h, 1);
+    }
     int rc = reduce_scalars(h, -2);
     if (rc != SDV_OK) return rc;
     k_ctrl<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt, h->cond);

@@ -82,7 +82,7 @@ struct DevProblem {
     const int *slot_obs;    // plane indices (local to this rank) of the observations grouped by slot
     // observations (indices relative to the full window; buffers of this rank are indexed o - o0)
     const int *obs_lmk, *obs_fc;
-    const double *obs_meas; // SoA planes: [3][O] bearing or [2][O] uv
+    const double *obs_meas; // [O][3] bearing or [O][2] uv (array-of-structs as the caller provides it)
     const double *obs_w;    // per-observation 1/sigma or nullptr
     // imu
     const int *imu_i, *imu_j;

@@ -223,6 +223,23 @@ def test_ragged_and_degenerate_inputs(solver):
     assert np.all(g[1].dlmk[3] == 0)
 
 
+def test_interleaved_feature_order(solver):
+    """lmk->getFeatures() order is arbitrary: here all left-camera features come before the right-camera ones, so a keyframe
+    re-appears non-adjacently inside a landmark (general slot grouping path of the upload)."""
+    win = synth.make_window("small")
+    order = np.lexsort((np.arange(win.n_obs), win.obs_cam, win.obs_lmk))
+    for name in ("obs_lmk", "obs_frame", "obs_cam", "obs_bearing", "obs_uv"):
+        setattr(win, name, np.ascontiguousarray(getattr(win, name)[order]))
+    f0 = win.obs_frame[win.obs_lmk == 0]
+    assert len(f0) == 8 and f0[0] == f0[4] and f0[0] != f0[1]  # the keyframe re-appears after three others
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    solver.upload(win)
+    r, Jp, Jl, _ = solver.eval_visual(None)
+    r0, Jp0, Jl0, _ = orc.eval_visual(win, None)
+    assert rel(r, r0) < 1e-12 and rel(Jp, Jp0) < 1e-12
+
+
 def test_invalid_inputs_are_rejected(solver):
     win = synth.make_window("tiny")
     bad = synth.make_window("tiny")

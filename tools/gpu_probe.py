@@ -51,14 +51,14 @@ def probe(name, **kw):
     for k, nm in ((0, "lin_visual"), (1, "schur"), (2, "cholesky")):
         print(f"  kernel {nm}: {s.time_kernel(k, 20)*1e3:.1f} us")
     prof = s.debug_read(5, 128).reshape(16, 8)
-    print("  chol phase cycles per rank [wait_Lkk load_Lkk trsm lookahead wait_col update backward]:")
+    print("  chol phase cycles per rank [wait_Lkk load_Lkk trsm lookahead|publish wait_col|ld+diag update|chol backward]:")
     for r in (0, 1, 7, 15):
         print("   rank", r, " ".join(f"{x/1e3:8.1f}k" for x in prof[r, :7]))
     import ctypes as C
     mic = np.zeros(64)
     api.lib().sdv_debug_micro.argtypes = [C.c_void_p, abi.c_double_p]
     api.lib().sdv_debug_micro(s._h, mic.ctypes.data_as(abi.c_double_p))
-    for i, nm in enumerate(["chol32_reg", "chol32_smem", "trsm32_reg", "trsm32_smem", "diag_update", "dmma_tile", "load_row32", "store_tile"]):
+    for i, nm in enumerate(["chol32_reg", "chol32_hyb", "trsm32_reg", "trsm32_smem", "diag_update", "dmma_tile", "load_row32", "store_tile"]):
         print(f"  micro {nm:12s} cycles/rep:", " ".join(f"{x:7.0f}" for x in mic[i * 8:i * 8 + 5]))
     s.close()
 
