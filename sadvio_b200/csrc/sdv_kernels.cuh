@@ -66,6 +66,8 @@ SDV_DEV void compute_fct_row(const DevProblem &P, const double *xp, int f, int c
     row[11] = tsw[2];
     row[30] = P.cam_w[c];
     row[31] = 0.0;
+    row[32] = 0.0;
+    row[33] = 0.0;
 }
 
 __global__ void k_prep_table(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, int which /* -1: cur, -2: 1-cur, else fixed */) {
@@ -192,7 +194,7 @@ constexpr int LIN_THREADS = 256;
 // Evaluate every visual residual block of this rank at the point held by the chosen linearisation buffer, write
 // r / J_pose / J_lmk as SoA planes, and add 1/2 sum r^2 to Accum::cost[buf].  Persistent grid: each CTA stages the
 // frame-camera table into shared memory once with a TMA bulk copy and then walks observation tiles.
-template <int KIND>
+template <int KIND, bool SMEM, bool EARLY>
 __global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc,
                                                             int which) {
     if (st->status != 0) return;
@@ -204,46 +206,81 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf
     __shared__ double red[LIN_THREADS / 32];
     const double *fct = B.fct;
     const int Oloc = P.o1 - P.o0, OC = P.Ocap;
-    int fstride = FCT_ROW;
-    if (P.fct_in_smem) {
-        // one TMA bulk copy per 256-byte table row into rows padded to 34 doubles: lanes of a warp touch up to 8 different
-        // rows at the same offset, an unpadded (32-double) stride would put them all in the same bank
-        double *sf = reinterpret_cast<double *>(smem_raw);
-        const int nrows = P.F * P.C;
+    constexpr int fstride = FCT_ROW;
+    if constexpr (SMEM) {
+        // stage the whole table with a few large TMA bulk copies (same padded layout in global and shared memory); the wait
+        // comes after the pipeline prologue below so the first index / operand loads overlap the copy
+        const uint32_t total = (uint32_t)(P.F * P.C * FCT_ROW * sizeof(double));
+        constexpr uint32_t CHUNK = 16384;
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
-        if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)(nrows * FCT_ROW * sizeof(double)));
+        if (threadIdx.x == 0) mbar_expect_tx(&bar, total);
         if (threadIdx.x < 32)
-            for (int r = threadIdx.x; r < nrows; r += 32)
-                bulk_g2s(sf + (size_t)r * FCT_SROW, B.fct + (size_t)r * FCT_ROW, (uint32_t)(FCT_ROW * sizeof(double)), &bar);
-        mbar_wait(&bar, 0);
-        fct = sf;
-        fstride = FCT_SROW;
+            for (uint32_t off = threadIdx.x * CHUNK; off < total; off += 32 * CHUNK)
+                bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char *>(B.fct) + off, min(CHUNK, total - off), &bar);
+        fct = reinterpret_cast<const double *>(smem_raw);
     }
+    // Three-stage software pipeline over this thread's observations (stride = grid size): the indices of tile t+2 and the
+    // gathered operands of tile t+1 are in flight while tile t is evaluated, so the two dependent memory round trips
+    // (index -> landmark / measurement) overlap the FP64 work instead of serialising with it.
+    constexpr int MP = KIND == 0 ? 3 : 2; // bearing[3] or uv[2], array-of-structs
+    const int stride = gridDim.x * LIN_THREADS;
     double csum = 0.0;
-    for (int base = blockIdx.x * LIN_THREADS; base < Oloc; base += gridDim.x * LIN_THREADS) {
-        int ol = base + threadIdx.x;
-        if (ol < Oloc) {
-            int o = P.o0 + ol;
-            int l = P.obs_lmk[o];
-            int fc = P.obs_fc[o];
-            double p[3], meas[3], r[2], Jp[12], Jl[6];
-            landmark_position(P, B, l, p);
-            constexpr int MP = KIND == 0 ? 3 : 2; // bearing[3] or uv[2], array-of-structs
-            meas[0] = P.obs_meas[(size_t)o * MP];
-            meas[1] = P.obs_meas[(size_t)o * MP + 1];
-            meas[2] = KIND == 0 ? P.obs_meas[(size_t)o * MP + 2] : 0.0;
-            const double *row = fct + (size_t)fc * fstride;
-            double w = P.obs_w ? P.obs_w[o] : row[30];
-            eval_visual<KIND>(row, P.K + 4 * (fc % P.C), w, p, meas, r, Jp, Jl);
-            B.r[ol] = r[0];
-            B.r[(size_t)OC + ol] = r[1];
+    int ol = blockIdx.x * LIN_THREADS + threadIdx.x;
+    int lA = 0, fcA = 0;                       // stage A: indices
+    int lB = 0, fcB = 0;                       // stage B: gathered operands
+    double mB[3] = {0, 0, 0}, tB[3] = {0, 0, 0}, xB[3] = {0, 0, 0}, wB = 0.0;
+    auto load_idx = [&](int i) {
+        lA = __ldg(P.obs_lmk + P.o0 + i);
+        fcA = __ldg(P.obs_fc + P.o0 + i);
+    };
+    auto gather = [&](int i) {
+        const size_t o = (size_t)P.o0 + i;
+        lB = lA;
+        fcB = fcA;
+        mB[0] = __ldg(P.obs_meas + o * MP);
+        mB[1] = __ldg(P.obs_meas + o * MP + 1);
+        if (KIND == 0) mB[2] = __ldg(P.obs_meas + o * MP + 2);
+        if (P.obs_w) wB = __ldg(P.obs_w + o);
 #pragma unroll
-            for (int k = 0; k < 12; k++) B.Jp[(size_t)k * OC + ol] = Jp[k];
-#pragma unroll
-            for (int k = 0; k < 6; k++) B.Jl[(size_t)k * OC + ol] = Jl[k];
-            csum += r[0] * r[0] + r[1] * r[1];
+        for (int k = 0; k < 3; k++) {
+            tB[k] = __ldg(P.lmk_t + 3 * (size_t)lB + k);
+            xB[k] = B.xl[3 * (size_t)lB + k]; // (k_backsub mirrors the reduced-system entries of kept landmarks into xl)
         }
+    };
+    if (ol < Oloc) {
+        load_idx(ol);
+        gather(ol);
+        if (ol + stride < Oloc) load_idx(ol + stride);
+    }
+    if constexpr (SMEM) mbar_wait(&bar, 0);
+    for (; ol < Oloc; ol += stride) {
+        const int fc = fcB;
+        const double p[3] = {tB[0] + xB[0], tB[1] + xB[1], tB[2] + xB[2]};
+        const double meas[3] = {mB[0], mB[1], mB[2]};
+        double w = wB;
+        double r[2], Jp[12], Jl[6];
+        const double *row = fct + (size_t)fc * fstride;
+        if (!P.obs_w) w = row[30];
+        // request the operands of the next tile and the indices of the one after (every value of the previous requests has
+        // been consumed above: ptxas tracks loads with a few counting scoreboards, a later wait on an old request would
+        // also wait for the new ones)
+        if (EARLY) {
+            if (ol + stride < Oloc) gather(ol + stride);
+            if (ol + 2 * stride < Oloc) load_idx(ol + 2 * stride);
+        }
+        eval_visual<KIND>(row, P.K + 4 * (fc % P.C), w, p, meas, r, Jp, Jl);
+        if (!EARLY) {
+            if (ol + stride < Oloc) gather(ol + stride);
+            if (ol + 2 * stride < Oloc) load_idx(ol + 2 * stride);
+        }
+        B.r[ol] = r[0];
+        B.r[(size_t)OC + ol] = r[1];
+#pragma unroll
+        for (int k = 0; k < 12; k++) B.Jp[(size_t)k * OC + ol] = Jp[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) B.Jl[(size_t)k * OC + ol] = Jl[k];
+        csum += r[0] * r[0] + r[1] * r[1];
     }
     csum = warp_sum(csum);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = csum;
@@ -1507,6 +1544,12 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_backsub(DevProblem P, LinBuf
         for (int k = 0; k < 3; k++) {
             gl[k] = group_sum<G>(gl[k]);
             e[k] = group_sum<G>(e[k]);
+        }
+        if (lig == 0 && (lb + gib) < nl && !valid) {
+            // kept landmark: mirror its reduced-system entries so the visual kernel reads every landmark from xl
+            const int dc = P.lmk_col[l];
+#pragma unroll
+            for (int k = 0; k < 3; k++) Bc.xl[3 * (size_t)l + k] = Bc.xp[dc + k];
         }
         if (!valid || lig != 0) continue;
         double s3[3] = {scale_l[3 * (size_t)l], scale_l[3 * (size_t)l + 1], scale_l[3 * (size_t)l + 2]};

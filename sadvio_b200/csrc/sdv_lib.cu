@@ -63,6 +63,17 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 
 } // namespace
 
+typedef void (*lin_visual_fn_t)(sdv::DevProblem, sdv::LinBuf, sdv::LinBuf, const sdv::LMState *, sdv::Accum *, int);
+static lin_visual_fn_t lin_visual_fn(int kind, bool smem, bool early) {
+    using namespace sdv;
+    if (kind == SDV_FACTOR_ANGULAR) {
+        if (smem) return early ? k_lin_visual<0, true, true> : k_lin_visual<0, true, false>;
+        return early ? k_lin_visual<0, false, true> : k_lin_visual<0, false, false>;
+    }
+    if (smem) return early ? k_lin_visual<1, true, true> : k_lin_visual<1, true, false>;
+    return early ? k_lin_visual<1, false, true> : k_lin_visual<1, false, false>;
+}
+
 struct sdv_handle {
     sdv_config cfg;
     SolverOpts opt;
@@ -90,6 +101,7 @@ struct sdv_handle {
     size_t sb_elems = 0;
     bool resident = false;
     int lin_grid = 0, lin_smem = 0, sch_grid = 0, fac_grid = 0;
+    lin_visual_fn_t lin_fn = nullptr;
     int group = 32; // lanes per landmark in k_schur / k_backsub (8, 16 or 32 by the largest slot count)
     int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_variant = 2, chol_rows_roles = 0, chol_smem_roles = 0; // 0: k_chol_cluster, 1: k_chol_ws + shuffle Cholesky, 2: k_chol_ws + hybrid, 3: k_chol_roles // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
     double *d_partial = nullptr, *d_dinv = nullptr, *d_prof = nullptr;
@@ -831,15 +843,14 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     h->sb_elems = sb_elems;
 
     // ---- launch geometry
-    size_t fct_bytes = (size_t)F * C * FCT_SROW * D;
+    size_t fct_bytes = (size_t)F * C * FCT_ROW * D;
     P.fct_in_smem = fct_bytes <= 160 * 1024 ? 1 : 0;
     h->lin_smem = P.fct_in_smem ? (int)fct_bytes : 0;
-    if (kind == SDV_FACTOR_ANGULAR) CK(cudaFuncSetAttribute(k_lin_visual<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    else CK(cudaFuncSetAttribute(k_lin_visual<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    h->lin_fn = lin_visual_fn(kind, P.fct_in_smem != 0, getenv("SDV_LIN_LATE") == nullptr);
+    CK(cudaFuncSetAttribute(h->lin_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_trisolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 1;
-    if (kind == SDV_FACTOR_ANGULAR) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lin_visual<0>, LIN_THREADS, h->lin_smem));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lin_visual<1>, LIN_THREADS, h->lin_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->lin_fn, LIN_THREADS, h->lin_smem));
     per_sm = std::max(per_sm, 1);
     h->lin_grid = std::max(1, std::min((Oloc + LIN_THREADS - 1) / LIN_THREADS, h->num_sms * per_sm));
     h->group = max_slots <= 8 ? 8 : (max_slots <= 16 ? 16 : 32);
@@ -964,10 +975,7 @@ void launch_lin_factors(sdv_handle *h, int which, cudaStream_t s) {
 void launch_lin_visual(sdv_handle *h, int which) {
     const DevProblem &P = h->P;
     if (P.o1 > P.o0) {
-        if (P.kind == SDV_FACTOR_ANGULAR)
-            k_lin_visual<0><<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
-        else
-            k_lin_visual<1><<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        h->lin_fn<<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
         h->launches++;
     }
     if (P.sp_np2l > 0) {
@@ -1386,7 +1394,7 @@ static int set_point(sdv_handle *h, const sdv_delta *x) {
             for (int l = 0; l < P.L; l++)
                 for (int k = 0; k < 3; k++) {
                     if (lmk_col[l] >= 0) xp[lmk_col[l] + k] = x->dlmk[3 * l + k];
-                    else xl[3 * (size_t)l + k] = x->dlmk[3 * l + k];
+                    xl[3 * (size_t)l + k] = x->dlmk[3 * l + k]; // kept landmarks are mirrored in xl (read by the visual kernel)
                 }
     }
     CK(cudaMemcpyAsync(h->B[0].xp, xp.data(), sizeof(double) * P.n_pad, cudaMemcpyHostToDevice, h->stream));
@@ -1471,10 +1479,7 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
         float ms = 0;
         if (which == 0) {
             CK(cudaEventRecord(h->ev[2], s));
-            if (P.kind == SDV_FACTOR_ANGULAR)
-                k_lin_visual<0><<<h->lin_grid, LIN_THREADS, h->lin_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, 0);
-            else
-                k_lin_visual<1><<<h->lin_grid, LIN_THREADS, h->lin_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, 0);
+            h->lin_fn<<<h->lin_grid, LIN_THREADS, h->lin_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, 0);
             CK(cudaEventRecord(h->ev[3], s));
         } else if (which == 1) {
             CK(cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s));

@@ -9,8 +9,10 @@ namespace sdv {
 //   [0..8]   Rsw = R_s_f * R_f_w * exp(dw)            [9..11]  tsw = R_s_f (R_f_w dt + t_f_w) + t_s_f
 //   [12..20] G   = R_s_f * R_f_w  (base, constant)     [21..29] Jq  (angular: Jr(log exp(dw)); pixel: Jr(log R')Jr(log R')^-1 Jr(dw))
 //   [30] default weight 1/sigma of the camera          [31] unused
-constexpr int FCT_ROW = 32;
-constexpr int FCT_SROW = 34; // padded row stride of the shared-memory copy (16-byte aligned, conflict-free for 8 rows per warp)
+// Row stride of the frame-camera table (32 used + 2 pad doubles): 16-byte aligned, and lanes of a warp that touch up to 8
+// different rows at the same offset hit different shared-memory banks.  Global and shared copies use the same layout so the
+// whole table moves with a handful of large TMA bulk copies.
+constexpr int FCT_ROW = 34;
 
 // Per-solve accumulators (zeroed by the control kernels).
 struct Accum {
