@@ -268,7 +268,7 @@ def main():
         specs = [
             (0, "k_lin_visual (residual+Jacobian, J materialised)", BYTES_PER_OBS * O, "hbm", its_per_step + 1),
             (1, "k_schur (per-landmark Schur complement + assembly)", 160 * O + 8 * n * n // 2, "hbm", its_per_step),
-            (2, "k_chol_ws (dense FP64 Cholesky + triangular solves of the reduced system, one 16-CTA cluster, DMMA)", 8 * n * n, "hbm", its_per_step),
+            (2, "k_chol_chain (structure-aware FP64 Cholesky + triangular solves of the reduced system, one 16-CTA cluster, DMMA updates)", 8 * n * n, "hbm", its_per_step),
         ]
         for which, name, nbytes, bound, per_step in specs:
             ms = solver.time_kernel(which, 20)

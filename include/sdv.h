@@ -304,7 +304,7 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
    1 Cholesky factor, 2 reduced step, 3 jacobi scale, 4 LM damping) and report the reduced dimensions. */
 int sdv_debug_read(sdv_handle *h, int32_t what, double *out, int64_t count);
 int sdv_debug_dims(sdv_handle *h, int32_t *n, int32_t *n_pad);
-int sdv_debug_micro(sdv_handle *h, double *out64);
+int sdv_debug_micro(sdv_handle *h, double *out72); /* developer micro-benchmarks, 72 doubles */
 
 const char *sdv_strerror(int status);
 const char *sdv_last_error(const sdv_handle *h); /* detail of the last failure on this handle */

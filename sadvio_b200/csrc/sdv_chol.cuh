@@ -1038,6 +1038,358 @@ __global__ void __launch_bounds__(CCT, 1) k_chol_roles(DevProblem P, LinBuf B0, 
     chol_backward_v2(P, B0, B1, st, acc, Lo, dinv, damp_p, graw_p, dxp, sRow, tinv, xs, wsum, red, &bk, fail, prof, tp, tc);
 }
 
+// C(32x32) -= A(32x32) B(32x32)^T with plain FP64 FMAs, all three tiles in global memory (L2), one warp: lane r owns row r of C
+// and of A in registers, B is staged transposed in this warp's shared-memory buffer and read back as broadcast 16-byte loads.
+// On B200 mma.sync.m8n8k4.f64 issues at ~1 per 25 cycles per warp and does not scale with the warps of an SM (measured: 3.3k
+// cycles per tile alone, ~18k with 8 warps per SM), the FP64 FMA pipe of each SM sub-partition does.
+constexpr int BTS = 34; // row stride of the transposed B tile (16-byte aligned rows)
+constexpr int CHAIN_SMEM_DOUBLES = 8 * 32 * BTS; // >= 2 * 1024 + 64 + 2 * 1024
+__device__ __noinline__ void tile_update_dfma_gg(double *Cg, const double *Ag, const double *Bg, int ld, int lane, double *Bt) {
+    double a[32], c[32];
+    {
+        double b[32];
+        load_row32(Bg + (size_t)lane * ld, b);
+#pragma unroll
+        for (int q = 0; q < 32; q++) Bt[q * BTS + lane] = b[q];
+    }
+    load_row32(Ag + (size_t)lane * ld, a);
+    load_row32(Cg + (size_t)lane * ld, c);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        const double aq = a[q];
+#pragma unroll
+        for (int c2 = 0; c2 < 32; c2 += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(Bt + q * BTS + c2);
+            c[c2] -= aq * v.x;
+            c[c2 + 1] -= aq * v.y;
+        }
+    }
+    store_row32(Cg + (size_t)lane * ld, c);
+    __syncwarp();
+}
+
+// =====================================================================================================================
+// Variant 4: one "chain" CTA + panel CTAs + update CTAs.
+//
+// The factorisation of an n ~ 750 system is one long dependency chain: tile k's Cholesky -> triangular solve of tile row k+1
+// -> update of tile (k+1,k+1) -> tile k+1's Cholesky ...  Here that chain never leaves one CTA and never touches L2: two warps
+// of the chain CTA alternate.  While warp A factorises tile (k,k) it publishes every finished column in shared memory; warp B
+// holds tile row k+1 (tiles (k+1,k) and (k+1,k+1)) in registers and consumes the columns as they appear (column-oriented
+// triangular solve + rank-1 update of its diagonal tile), so it can start factorising tile (k+1,k+1) ~one column after A ends.
+// A then becomes the B of tile row k+2.  The other tile rows are solved by the panel CTAs (from L2, after the tile is
+// published) and the trailing tiles are updated by the update CTAs with DMMA; the two tiles the chain needs next,
+// (k+2,k+1) and (k+2,k+2), are updated first and signalled separately.
+// =====================================================================================================================
+__host__ __device__ constexpr int mod_inverse(int a, int m) {
+    for (int x = 1; x < m; x++)
+        if ((a * x) % m == 1) return x;
+    return 0;
+}
+// CTA-local mbarrier helpers (SYNCS.ARRIVE / try_wait, no MEMBAR: a st.release.cta flag costs a MEMBAR.ALL.CTA per column)
+SDV_DEV void mbar_arrive_cta(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+SDV_DEV bool mbar_test_cta(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+SDV_DEV void mbar_wait_cta(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITL_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEL_%=;\n"
+        "bra WAITL_%=;\n"
+        "DONEL_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// chol32_hyb that also publishes: colT[c*32 + i] = L[i][c], sinvT[c] = 1/L[c][c], then one arrival on colbar[c]
+SDV_DEV bool chol32_stream(double (&a)[32], int lane, double *colT, double *sinvT, uint64_t *colbar) {
+    bool ok = true;
+    double d = __shfl_sync(FULL, a[0], 0);
+    if (!(d > 0.0) || !isfinite(d)) {
+        ok = false;
+        d = 1.0;
+    }
+    double inv = rsqrt(d);
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        double l = a[c] * inv;
+        if (lane == c) {
+            l = d * inv;
+            sinvT[c] = inv;
+        }
+        if (lane < c) l = 0.0;
+        a[c] = l;
+        colT[c * 32 + lane] = l;
+        if (c + 1 < 32) {
+            a[c + 1] -= l * __shfl_sync(FULL, l, c + 1); // the next pivot column first
+            d = __shfl_sync(FULL, a[c + 1], c + 1);
+            if (!(d > 0.0) || !isfinite(d)) {
+                ok = false;
+                d = 1.0;
+            }
+            inv = rsqrt(d); // in flight during the updates below
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(colbar + c);
+#pragma unroll
+        for (int c2 = c + 2; c2 < 32; c2 += 2) {
+            if (c2 + 1 < 32 && (c2 & 1) == 0) {
+                const double2 v = *reinterpret_cast<const double2 *>(colT + c * 32 + c2);
+                a[c2] -= l * v.x;
+                a[c2 + 1] -= l * v.y;
+            } else {
+                a[c2] -= l * colT[c * 32 + c2];
+                if (c2 + 1 < 32) a[c2 + 1] -= l * colT[c * 32 + c2 + 1];
+            }
+        }
+    }
+    return ok;
+}
+
+// Consumer: t = row `lane` of tile (r, k) (becomes L[r][k]), d = row `lane` of tile (r, r) (receives -= L_rk L_rk^T).
+// xb[c*32 + i] receives L[r][k](i, c) (the finished tile, column-major) for the publishing warp.
+template <bool DIAG>
+SDV_DEV void trsm_stream(double (&t)[32], double (&d)[32], int lane, const double *colT, const double *sinvT, uint64_t *colbar, unsigned parity,
+                         double *xb /* shared [32][32], private to this warp */) {
+    const bool all_done = mbar_test_cta(colbar + 31, parity); // catching up with a finished tile: no per-column waits
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        if (!all_done) mbar_wait_cta(colbar + c, parity);
+        const double x = t[c] * sinvT[c];
+        t[c] = x;
+#pragma unroll
+        for (int j = c + 1; j < 32; j++) t[j] -= x * colT[c * 32 + j];
+        xb[c * 32 + lane] = x;
+        if (DIAG) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(xb + c * 32 + j);
+                d[j] -= x * v.x;
+                d[j + 1] -= x * v.y;
+            }
+        }
+    }
+}
+
+template <int NPC, bool DFMA>
+__global__ void __launch_bounds__(CCT, 1) k_chol_chain(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, double *A, double *Lo, double *dinv,
+                                                       const double *damp_p, const double *graw_p, double *dxp, int max_rows, double *prof) {
+    if (st->status != 0) return; // uniform over the cluster
+    extern __shared__ __align__(16) double csm[];
+    __shared__ uint64_t b1[2], b2, ucol, urg[2], bk; // urg[k&1]: each chain warp waits on its own barrier, phase after phase
+    __shared__ uint64_t colbar[2][32], pubT[2], pubD[2], ackT[2], ackD[2]; // chain CTA only
+    __shared__ uint32_t snz[129 * 4];                                      // structural tile pattern of L (host-side symbolic factorisation)
+    constexpr int NW = CCT / 32;
+    double *sK = csm;                                   // [32][TSTR] diagonal tile L_kk (panel CTAs)
+    double *sinv = sK + 32 * TSTR;                      // [32]
+    double *chain = sinv + 32;                          // chain CTA: colT[2][1024], sinvT[2][32], xb[2][1024]; update CTAs: Bt[8][32][BTS]
+    double *sRow = chain + CHAIN_SMEM_DOUBLES;    // backward solve: tile inverses [max_rows][32][TSTR] (x2 kept for layout parity)
+    double *xs = sRow + (size_t)2 * max_rows * 32 * TSTR;
+    double *wsum = xs + (size_t)max_rows * 32;
+    double *red = wsum + 8 * 32;
+    double *tinv = red + CC_MAX * 32;
+    const int ld = P.ld, T = P.n_pad / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = (int)cluster_rank();
+    constexpr int NU = CC_MAX - 1 - NPC, NUWT = NU * NW; // the host launches this kernel only with a full 16-CTA cluster
+    bool fail = false;
+    long long tp[7] = {0, 0, 0, 0, 0, 0, 0}, tc = clock64(), tn;
+
+    for (int e = threadIdx.x; e < (T + 1) * 4; e += CCT) snz[e] = __ldg(P.tile_nz + e);
+    auto nz = [&](int i, int k) { return ((snz[i * 4 + (k >> 5)] >> (k & 31)) & 1u) != 0; };
+    if (threadIdx.x == 0) {
+        mbar_init(&b1[0], 1);
+        mbar_init(&b1[1], 1);
+        mbar_init(&b2, NPC + 1);
+        mbar_init(&ucol, NUWT);
+        mbar_init(&urg[0], 2);
+        mbar_init(&urg[1], 2);
+        for (int i = 0; i < 64; i++) mbar_init(&colbar[0][0] + i, 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&pubT[i], 1);
+            mbar_init(&pubD[i], 1);
+            mbar_init(&ackT[i], 1);
+            mbar_init(&ackD[i], 1);
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+
+    if (rank == 0) {
+        // =================================================== chain CTA: warps 0 and 1 alternate, warps 2 and 3 publish for them
+        double *colT = chain, *sinvT = chain + 2048;
+        if (warp < 2) {
+            const int w = warp;                       // tile k with k % 2 == w: colT[w], sinvT[w], colbar[w] are produced by this warp
+            double *xb = chain + 2048 + 64 + w * 1024;
+            double t[32], d[32];
+            int nB = 0, nD = 0;                        // solve / factor phases finished by this warp (phases of pubT/ackT, pubD/ackD)
+            for (int k = w; k <= T; k += 2) {          // k == T: only the last triangular solve of the right-hand-side row
+                if (k == 0) {
+                    load_row32(A + (size_t)lane * ld, d);
+                } else {
+                    const int pq = (k - 1) & 1;
+                    tc = clock64();
+                    if (k >= 2) mbar_wait_cluster(&urg[k & 1], (unsigned)(((k - 2) >> 1) & 1)); // tiles (k,k-1), (k,k) final through panel k-2
+                    SDV_TICK(0);
+                    load_row32(A + (size_t)(k * 32 + lane) * ld + (k - 1) * 32, t);
+                    if (k < T) load_row32(A + (size_t)(k * 32 + lane) * ld + k * 32, d);
+                    if (nB > 0) mbar_wait_cta(&ackT[w], (unsigned)((nB - 1) & 1)); // the publisher has copied the previous xb
+                    SDV_TICK(1);
+                    if (k < T) trsm_stream<true>(t, d, lane, colT + pq * 1024, sinvT + pq * 32, &colbar[pq][0], (unsigned)(((k - 1) >> 1) & 1), xb);
+                    else trsm_stream<false>(t, d, lane, colT + pq * 1024, sinvT + pq * 32, &colbar[pq][0], (unsigned)(((k - 1) >> 1) & 1), xb);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(&pubT[w]);
+                    nB++;
+                    SDV_TICK(2);
+                }
+                if (k < T) {
+                    if (nD > 0) mbar_wait_cta(&ackD[w], (unsigned)((nD - 1) & 1)); // the publisher has copied the previous tile
+                    if (!chol32_stream(d, lane, colT + w * 1024, sinvT + w * 32, &colbar[w][0])) fail = true;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(&pubD[w]);
+                    nD++;
+                    SDV_TICK(3);
+                }
+            }
+        } else if (warp < 4) {
+            // publisher of chain warp w: copies finished tiles from shared memory to L2 and signals the other CTAs, so the
+            // chain warps never wait for a global store
+            const int w = warp - 2;
+            const double *xb = chain + 2048 + 64 + w * 1024;
+            double a[32];
+            int nB = 0, nD = 0;
+            for (int k = w; k <= T; k += 2) {
+                if (k >= 1) {
+                    mbar_wait_cta(&pubT[w], (unsigned)(nB & 1));
+#pragma unroll
+                    for (int c = 0; c < 32; c++) a[c] = xb[c * 32 + lane];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(&ackT[w]);
+                    store_row32(Lo + (size_t)(k * 32 + lane) * ld + (k - 1) * 32, a);
+                    __syncwarp();
+                    if (k < T && lane < NU) mbar_remote_arrive(&b2, (unsigned)(1 + NPC + lane)); // chain's part of panel column k-1
+                    nB++;
+                }
+                if (k < T) {
+                    mbar_wait_cta(&pubD[w], (unsigned)(nD & 1));
+#pragma unroll
+                    for (int c = 0; c < 32; c++) a[c] = colT[w * 1024 + c * 32 + lane];
+                    const double inv = sinvT[w * 32 + lane];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(&ackD[w]);
+                    dinv[k * 32 + lane] = inv;
+                    store_row32(Lo + (size_t)(k * 32 + lane) * ld + k * 32, a);
+                    __syncwarp();
+                    if (lane < NPC) mbar_remote_arrive(&b1[w], (unsigned)(1 + lane));
+                    nD++;
+                }
+            }
+        }
+    } else if (rank <= NPC) {
+        // =================================================== panel CTA: tile rows i >= k+2 with i % NPC == rank-1
+        const int pr = rank - 1;
+        for (int k = 0; k + 2 <= T; k++) {
+            double a[32];
+            const int first = k + 2 + ((pr - (k + 2)) % NPC + NPC) % NPC;
+            const int nown = first <= T ? (T - first) / NPC + 1 : 0;
+            tc = clock64();
+            if (k >= 1) mbar_wait_cluster(&ucol, (unsigned)((k - 1) & 1)); // tiles (i,k), i >= k+2, final through panel k-1
+            SDV_TICK(1);
+            const bool mine = warp < nown && nz(first + warp * NPC, k); // structurally zero tiles stay zero in Lo (cleared at upload)
+            if (mine) load_row32(A + (size_t)((first + warp * NPC) * 32 + lane) * ld + k * 32, a);
+            mbar_wait_cluster(&b1[k & 1], (unsigned)((k >> 1) & 1)); // L_kk and its reciprocal diagonal are in L2
+            SDV_TICK(0);
+            for (int e = threadIdx.x; e < 512; e += CCT) {
+                int r = e >> 4, q = e & 15;
+                double2 v = __ldcg(reinterpret_cast<const double2 *>(Lo + (size_t)(k * 32 + r) * ld + k * 32) + q);
+                sK[r * TSTR + 2 * q] = v.x;
+                sK[r * TSTR + 2 * q + 1] = v.y;
+            }
+            if (threadIdx.x < 32) sinv[threadIdx.x] = __ldcg(dinv + k * 32 + threadIdx.x);
+            __syncthreads();
+            for (int s2 = warp; s2 < nown; s2 += NW) {
+                const int i = first + s2 * NPC;
+                if (!nz(i, k)) continue;
+                if (s2 != warp) load_row32(A + (size_t)(i * 32 + lane) * ld + k * 32, a);
+                trsm32_reg(a, sK, sinv);
+                store_row32(Lo + (size_t)(i * 32 + lane) * ld + k * 32, a);
+            }
+            __syncthreads();
+            SDV_TICK(2);
+            if (warp == 1) { // this CTA's part of panel column k is published -> every update CTA
+                __syncwarp();
+                if (lane < NU) mbar_remote_arrive(&b2, (unsigned)(1 + NPC + lane));
+            }
+        }
+    } else {
+        // =================================================== update CTA: every warp is an independent worker
+        // Tile (i, j) belongs to global update warp (5 i + j) mod NUWT for the whole factorisation; operands come from L2.
+        const int gw = (rank - 1 - NPC) * NW + warp;
+        constexpr int inv5 = mod_inverse(5, NUWT); // compile-time constants: no integer division in the tile loops
+        static_assert((5 * inv5) % NUWT == 1, "5 must be invertible modulo the number of update warps");
+        auto owner = [&](int i, int j) { return (5 * i + j) % NUWT; };
+        double *Bt = chain + warp * 32 * BTS;
+        auto update = [&](int i, int j, int k) {
+            if (!nz(i, k) || !nz(j, k)) return; // a structurally zero operand: nothing to subtract
+            if (DFMA)
+                tile_update_dfma_gg(A + (size_t)(i * 32) * ld + j * 32, Lo + (size_t)(i * 32) * ld + k * 32, Lo + (size_t)(j * 32) * ld + k * 32, ld, lane, Bt);
+            else
+                tile_update_dmma_gg(A + (size_t)(i * 32) * ld + j * 32, Lo + (size_t)(i * 32) * ld + k * 32, Lo + (size_t)(j * 32) * ld + k * 32, ld, lane);
+        };
+        for (int k = 0; k + 2 <= T; k++) { // panel T-1 has no trailing tile
+            tc = clock64();
+            mbar_wait_cluster(&b2, (unsigned)(k & 1)); // the whole panel column k is in Lo
+            SDV_TICK(4);
+            // 1. the two tiles the chain needs next
+            if (owner(k + 2, k + 1) == gw) {
+                update(k + 2, k + 1, k);
+                __syncwarp();
+                if (lane == 0) mbar_remote_arrive(&urg[k & 1], 0u);
+            }
+            if (owner(k + 2, k + 2) == gw) {
+                if (k + 2 <= T - 1) update(k + 2, k + 2, k);
+                __syncwarp();
+                if (lane == 0) mbar_remote_arrive(&urg[k & 1], 0u);
+            }
+            // 2. the rest of tile column k+1 (the next panel), then the others in the order they will be needed
+            for (int j = k + 1; j < T; j++) {
+                if (j == k + 2) {
+                    __syncwarp();
+                    if (lane < NPC) mbar_remote_arrive(&ucol, (unsigned)(1 + lane));
+                }
+                const int i0 = (((gw - j) % NUWT + NUWT) * inv5) % NUWT;
+                for (int i = i0; i <= T; i += NUWT) {
+                    if (i < j || i <= k + 1) continue;                    // tile (k+1,k+1) belongs to the chain
+                    if (i == k + 2 && (j == k + 1 || j == k + 2)) continue; // done above
+                    update(i, j, k);
+                }
+            }
+            if (k + 2 >= T) { // column loop did not reach j == k+2
+                __syncwarp();
+                if (lane < NPC) mbar_remote_arrive(&ucol, (unsigned)(1 + lane));
+            }
+            SDV_TICK(5);
+        }
+    }
+    __syncthreads();
+    chol_backward_v2(P, B0, B1, st, acc, Lo, dinv, damp_p, graw_p, dxp, sRow, tinv, xs, wsum, red, &bk, fail, prof, tp, tc);
+}
+
 // Developer micro-benchmark: cycles of the tile routines, single warp, 5 repetitions each (the first one has cold code).
 // out[routine * 8 + rep]; routines: 0 chol32_reg, 1 chol32_smem, 2 trsm32_reg, 3 trsm32_smem, 4 diag update (rolled q),
 // 5 tile_update_dmma (C in global), 6 load_row32 (L2), 7 store tile rows
@@ -1139,6 +1491,25 @@ __global__ void k_chol_micro(double *scratch /* >= 4 * 32 * 64 doubles */, doubl
         }
     }
     if (sink == 123.456) out[63] = sink;
+}
+
+// Developer micro-benchmark: throughput of the two trailing-update kernels when `nact` warps of one CTA run them at once.
+// out[0] = cycles per tile seen by warp 0 (4 tiles per warp, warm).
+__global__ void k_update_micro(double *scratch /* >= 8 * 3 * 32 * 64 doubles */, double *out, int dfma, int nact) {
+    extern __shared__ __align__(16) double usm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *base = scratch + (size_t)warp * 3 * 32 * 64;
+    for (int e = lane; e < 3 * 32 * 64; e += 32) base[e] = 0.001 * ((e + warp) % 97);
+    __syncthreads();
+    if (warp >= nact) return;
+    long long t0 = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        if (rep == 1) t0 = clock64();
+        if (dfma) tile_update_dfma_gg(base, base + 32 * 64, base + 2 * 32 * 64, 64, lane, usm + warp * 32 * BTS);
+        else tile_update_dmma_gg(base, base + 32 * 64, base + 2 * 32 * 64, 64, lane);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = (double)(t1 - t0) / 4.0;
 }
 
 } // namespace sdv

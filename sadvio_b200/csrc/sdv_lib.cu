@@ -103,7 +103,7 @@ struct sdv_handle {
     int lin_grid = 0, lin_smem = 0, sch_grid = 0, fac_grid = 0;
     lin_visual_fn_t lin_fn = nullptr;
     int group = 32; // lanes per landmark in k_schur / k_backsub (8, 16 or 32 by the largest slot count)
-    int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_variant = 2, chol_rows_roles = 0, chol_smem_roles = 0; // 0: k_chol_cluster, 1: k_chol_ws + shuffle Cholesky, 2: k_chol_ws + hybrid, 3: k_chol_roles // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
+    int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_variant = 4, chol_rows_roles = 0, chol_smem_roles = 0, chol_smem_chain = 0; // 0: k_chol_cluster, 1: k_chol_ws + shuffle Cholesky, 2: k_chol_ws + hybrid, 3: k_chol_roles, 4: k_chol_chain (default; needs the 16-CTA cluster, else 2), 5: k_chol_chain with FMA updates // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
     double *d_partial = nullptr, *d_dinv = nullptr, *d_prof = nullptr;
     int64_t launches = 0;
     // whole-solve CUDA graph: prologue -> WHILE(LM iteration) -> epilogue (single-GPU only)
@@ -122,6 +122,8 @@ struct sdv_handle {
     void *comm = nullptr;
     int rank = 0, world = 1;
     std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs; // reused between uploads
+    std::vector<uint32_t> tmp_tile_nz;
+    int chol_tiles_nz = 0, chol_tiles_all = 0; // structurally non-zero tiles of L / all lower tiles
     LMState h_state;
     Accum h_acc;
 };
@@ -589,6 +591,116 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     }
     const int nm = (int)mp_src.size();
 
+    // ---- tile-level structure of the reduced system (32-column tiles) and its symbolic Cholesky fill.  A window whose
+    //      landmarks are seen from a few neighbouring keyframes gives a block-banded reduced system (plus the rows of the kept
+    //      landmarks of a prior); the factorisation kernel skips the tiles that are structurally zero, exactly like the sparse
+    //      solver of the reference does (AOptimizer.cpp:383, SUITE_SPARSE).  A dense window costs what it did before.
+    const int Tt = n_pad / 32;
+    std::vector<uint32_t> &tile_nz = h->tmp_tile_nz; // [(Tt + 1)][4] bit j of row i: tile (i, j) of L may be non-zero
+    tile_nz.assign((size_t)(Tt + 1) * 4, 0u);
+    if (Tt <= 128) {
+        struct TMask {
+            uint64_t w[2];
+            bool operator==(const TMask &o) const { return w[0] == o.w[0] && w[1] == o.w[1]; }
+        };
+        auto add_cols = [&](TMask &m, int c0, int ncols) {
+            if (c0 < 0) return;
+            for (int t = c0 / 32; t <= (c0 + ncols - 1) / 32; t++) m.w[t >> 6] |= 1ull << (t & 63);
+        };
+        std::vector<TMask> low((size_t)Tt + 1, TMask{{0, 0}}); // low[i]: columns j coupled with tile row i
+        auto add_clique = [&](const TMask &m) {
+            for (int wq = 0; wq < 2; wq++) {
+                uint64_t bits = m.w[wq];
+                while (bits) {
+                    const int i = wq * 64 + __builtin_ctzll(bits);
+                    bits &= bits - 1;
+                    low[i].w[0] |= m.w[0];
+                    low[i].w[1] |= m.w[1];
+                }
+            }
+        };
+        if (getenv("SDV_CHOL_DENSE")) {
+            TMask all{{0, 0}};
+            add_cols(all, 0, n_pad);
+            add_clique(all);
+        } else {
+            std::vector<TMask> pose_mask(F, TMask{{0, 0}}), frame_mask(F, TMask{{0, 0}});
+            for (int f = 0; f < F; f++) {
+                add_cols(pose_mask[f], pose_col[f], 6);
+                frame_mask[f] = pose_mask[f];
+                add_cols(frame_mask[f], vb_col[f], 9);
+                add_clique(frame_mask[f]); // diagonal blocks (pose prior, damping)
+            }
+            // visual factors: every landmark couples the poses of the keyframes that see it (and its own columns when kept)
+            std::vector<TMask> uniq;
+            TMask last{{0, 0}};
+            for (int l = 0; l < L; l++) {
+                TMask m{{0, 0}};
+                for (int q = slot_ptr[l]; q < slot_ptr[l + 1]; q++) {
+                    const TMask &pm = pose_mask[slot_frame[q]];
+                    m.w[0] |= pm.w[0];
+                    m.w[1] |= pm.w[1];
+                }
+                if (lmk_col[l] >= 0) add_cols(m, lmk_col[l], 3);
+                if (m == last) continue;
+                last = m;
+                bool seen = false;
+                for (size_t u = uniq.size(); u-- > 0 && uniq.size() - u <= 32;) seen |= uniq[u] == m;
+                if (!seen) uniq.push_back(m);
+            }
+            for (const TMask &m : uniq) add_clique(m);
+            for (int p = 0; p < Pn; p++) { // IMUFactor + IMUBiasFactor couple all 15 parameters of both keyframes
+                TMask m = frame_mask[w->imu_i[p]];
+                m.w[0] |= frame_mask[w->imu_j[p]].w[0];
+                m.w[1] |= frame_mask[w->imu_j[p]].w[1];
+                add_clique(m);
+            }
+            if (dp) { // dense marginalisation prior: one clique over everything it touches
+                TMask m{{0, 0}};
+                for (int c : mp_dst)
+                    if (c >= 0) add_cols(m, c, 1);
+                add_clique(m);
+            }
+            if (sp) {
+                if (sp->has_imu_prior) add_clique(frame_mask[sp->frame]);
+                if (sp->has_lmk_prior) {
+                    TMask m{{0, 0}};
+                    add_cols(m, lmk_col[sp->lmk0], 3);
+                    add_clique(m);
+                }
+                for (int k = 0; k < sp->n_l2l; k++) {
+                    TMask m{{0, 0}};
+                    add_cols(m, lmk_col[sp->l2l_a[k]], 3);
+                    add_cols(m, lmk_col[sp->l2l_b[k]], 3);
+                    add_clique(m);
+                }
+            }
+            for (int t = 0; t < Tt; t++) low[t].w[t >> 6] |= 1ull << (t & 63); // padding columns: identity diagonal
+        }
+        // symbolic right-looking elimination on the tile graph: the rows below pivot k become mutually coupled
+        auto bit = [&](const TMask &m, int j) { return (m.w[j >> 6] >> (j & 63)) & 1ull; };
+        for (int k = 0; k < Tt; k++) {
+            TMask col{{0, 0}}; // rows i > k with (i, k) non-zero
+            for (int i = k + 1; i < Tt; i++)
+                if (bit(low[i], k)) col.w[i >> 6] |= 1ull << (i & 63);
+            for (int i = k + 1; i < Tt; i++)
+                if (bit(col, i)) {
+                    low[i].w[0] |= col.w[0];
+                    low[i].w[1] |= col.w[1];
+                }
+        }
+        int nnz_tiles = 0;
+        for (int i = 0; i < Tt; i++)
+            for (int j = 0; j <= i; j++)
+                if (bit(low[i], j)) {
+                    tile_nz[(size_t)i * 4 + (j >> 5)] |= 1u << (j & 31);
+                    nnz_tiles++;
+                }
+        for (int j = 0; j < Tt; j++) tile_nz[(size_t)Tt * 4 + (j >> 5)] |= 1u << (j & 31); // right-hand-side row: dense
+        h->chol_tiles_nz = nnz_tiles;
+        h->chol_tiles_all = Tt * (Tt + 1) / 2;
+    }
+
     // ---- input arena
     Arena A;
     auto D = sizeof(double);
@@ -597,6 +709,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     size_t o_pc = A.add(4 * F), o_vc = A.add(4 * F);
     size_t o_Ts = A.add(D * 12 * C), o_K = A.add(D * 4 * C), o_cw = A.add(D * C);
     size_t o_lt = A.add(D * 3 * std::max(L, 1)), o_lc = A.add(4 * std::max(L, 1));
+    size_t o_tnz = A.add(4 * tile_nz.size());
     size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(nslotobs, 1));
     size_t o_ol = A.add(4 * std::max(O, 1)), o_ofc = A.add(4 * std::max(O, 1));
     const int mplanes = kind == SDV_FACTOR_ANGULAR ? 3 : 2;
@@ -660,6 +773,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         std::memset(hb + o_hp, 0, F);
     }
     std::memcpy(hb + o_pc, pose_col.data(), 4 * F);
+    std::memcpy(hb + o_tnz, tile_nz.data(), 4 * tile_nz.size());
     std::memcpy(hb + o_vc, vb_col.data(), 4 * F);
     std::memcpy(hb + o_Ts, w->T_s_f, D * 12 * C);
     std::memcpy(hb + o_K, w->K, D * 4 * C);
@@ -794,6 +908,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     P.pose_col = at<int>(db, o_pc); P.vb_col = at<int>(db, o_vc);
     P.T_s_f = at<double>(db, o_Ts); P.K = at<double>(db, o_K); P.cam_w = at<double>(db, o_cw);
     P.lmk_t = at<double>(db, o_lt); P.lmk_col = at<int>(db, o_lc);
+    P.tile_nz = at<uint32_t>(db, o_tnz);
     P.slot_ptr = at<int>(db, o_sp); P.slot_frame = at<int>(db, o_sf); P.slot_obs_ptr = at<int>(db, o_sop); P.slot_obs = at<int>(db, o_so);
     P.obs_lmk = at<int>(db, o_ol); P.obs_fc = at<int>(db, o_ofc); P.obs_meas = at<double>(db, o_om);
     P.obs_w = w->obs_sigma ? at<double>(db, o_ow) : nullptr;
@@ -862,6 +977,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     // dense Cholesky: one thread-block cluster when the reduced system is small enough, per-panel launches otherwise
     h->chol_cluster = 0;
     if (n_pad <= 4096 && !getenv("SDV_NO_CLUSTER")) {
+        h->chol_variant = 4;
         if (const char *v = getenv("SDV_CHOL_VARIANT")) h->chol_variant = atoi(v);
         auto prep = [&](const void *fn) {
             cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -871,6 +987,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         prep((const void *)k_chol_ws<false>);
         prep((const void *)k_chol_ws<true>);
         prep((const void *)k_chol_roles<4>);
+        prep((const void *)k_chol_chain<3, false>);
+        prep((const void *)k_chol_chain<3, true>);
         CK(cudaGetLastError());
         const int T = n_pad / 32;
         for (int cs : {16, 8, 4, 2, 1}) {
@@ -897,13 +1015,16 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
                 h->chol_rows_roles = std::max(1, (T + cs - 1) / cs); // shared-memory tiles: look-ahead operand / backward-solve tile inverses
                 h->chol_smem_roles = (int)(sizeof(double) * (32 * TSTR + 32 + 64 + 32 * TSTR + (size_t)2 * h->chol_rows_roles * 32 * TSTR +
                                                             (size_t)h->chol_rows_roles * 32 + 8 * 32 + CC_MAX * 32 + (size_t)h->chol_rows_roles * 32));
-                if (cs != 16 || h->chol_smem_roles > 200 * 1024) { if (h->chol_variant == 3) h->chol_variant = 2; }
+                h->chol_smem_chain = (int)(sizeof(double) * (32 * TSTR + 32 + CHAIN_SMEM_DOUBLES + (size_t)2 * h->chol_rows_roles * 32 * TSTR +
+                                                            (size_t)h->chol_rows_roles * 32 + 8 * 32 + CC_MAX * 32 + (size_t)h->chol_rows_roles * 32));
+                if (cs != 16 || h->chol_smem_roles > 200 * 1024 || h->chol_smem_chain > 200 * 1024) { if (h->chol_variant >= 3) h->chol_variant = 2; }
                 break;
             }
             cudaGetLastError();
         }
     }
 
+    CK(cudaMemsetAsync(h->d_Lo, 0, sizeof(double) * sb_elems, h->stream)); // tiles outside the structural pattern are never written
     // ---- one-time device setup for this window
     if (Pn > 0) {
         k_imu_inf_sqrt<<<(Pn + 31) / 32, 32, 0, h->stream>>>(P);
@@ -922,6 +1043,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     if (timing) {
         auto t_g1 = std::chrono::steady_clock::now();
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[sdv upload] reduced system n=%d (%d tiles), factor tiles %d of %d structurally non-zero\n", n, n_pad / 32, h->chol_tiles_nz, h->chol_tiles_all);
         std::fprintf(stderr, "[sdv upload] structure %.3f ms, pack %.3f ms, h2d+setup %.3f ms, graph %.3f ms\n", ms(tu0, t_pack0), ms(t_pack0, t_pack1),
                      ms(t_pack1, t_g0), ms(t_g0, t_g1));
     }
@@ -1049,7 +1171,11 @@ int launch_factor_solve(sdv_handle *h) {
         lc.attrs = at1;
         lc.numAttrs = 1;
         cudaError_t e;
-        if (h->chol_variant == 3) {
+        if (h->chol_variant >= 4) {
+            lc.dynamicSmemBytes = h->chol_smem_chain;
+            e = cudaLaunchKernelEx(&lc, h->chol_variant == 4 ? k_chol_chain<3, false> : k_chol_chain<3, true>, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, (const double *)h->d_damp_p,
+                                   (const double *)h->d_graw_p, h->d_dxp, h->chol_rows_roles, h->d_prof);
+        } else if (h->chol_variant == 3) {
             lc.dynamicSmemBytes = h->chol_smem_roles;
             e = cudaLaunchKernelEx(&lc, k_chol_roles<4>, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_dinv, (const double *)h->d_damp_p,
                                    (const double *)h->d_graw_p, h->d_dxp, h->chol_rows_roles, h->d_prof);
@@ -1537,10 +1663,21 @@ int sdv_debug_micro(sdv_handle *h, double *out) {
     cudaSetDevice(h->device);
     double *d_out = h->d_partial; // scratch, >= 64 doubles
     CK(cudaMemsetAsync(d_out, 0, 64 * sizeof(double), h->stream));
-    k_chol_micro<<<1, 32, 0, h->stream>>>(h->d_Lo, d_out);
+    k_chol_micro<<<1, 32, 0, h->stream>>>(h->d_Sb, d_out); // scratch: the reduced-system buffer (rebuilt by every iteration)
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, d_out, 64 * sizeof(double), cudaMemcpyDeviceToHost));
+    // out[64 + 4*dfma + log2(nact)] (the caller's buffer holds 72 doubles): cycles per trailing-update tile with nact = 1, 2, 4, 8 concurrent warps in one CTA
+    if ((size_t)h->P.ld * (h->P.n_pad + 32) >= (size_t)8 * 3 * 32 * 64) {
+        cudaFuncSetAttribute(k_update_micro, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * BTS * 8);
+        for (int dfma = 0; dfma < 2; dfma++)
+            for (int lg = 0; lg < 4; lg++) {
+                k_update_micro<<<1, 256, 8 * 32 * BTS * 8, h->stream>>>(h->d_Sb, d_out, dfma, 1 << lg);
+                CK(cudaStreamSynchronize(h->stream));
+                CK(cudaMemcpy(out + 64 + 4 * dfma + lg, d_out, sizeof(double), cudaMemcpyDeviceToHost));
+            }
+        CK(cudaGetLastError());
+    }
     return SDV_OK;
 }
 

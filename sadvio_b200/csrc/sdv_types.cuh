@@ -78,6 +78,7 @@ struct DevProblem {
     // landmarks
     const double *lmk_t;
     const int *lmk_col;     // column in the reduced system for dense (kept) landmarks, -1 = eliminated
+    const uint32_t *tile_nz; // [(n_pad/32 + 1)][4] bit j of row i: tile (i, j) of the Cholesky factor is structurally non-zero
     const int *slot_ptr;    // [L+1] first slot of each landmark
     const int *slot_frame;  // [nslots]
     const int *slot_obs_ptr;// [nslots+1]

@@ -55,11 +55,12 @@ def probe(name, **kw):
     for r in (0, 1, 7, 15):
         print("   rank", r, " ".join(f"{x/1e3:8.1f}k" for x in prof[r, :7]))
     import ctypes as C
-    mic = np.zeros(64)
+    mic = np.zeros(72)
     api.lib().sdv_debug_micro.argtypes = [C.c_void_p, abi.c_double_p]
     api.lib().sdv_debug_micro(s._h, mic.ctypes.data_as(abi.c_double_p))
     for i, nm in enumerate(["chol32_reg", "chol32_hyb", "trsm32_reg", "trsm32_smem", "diag_update", "dmma_tile", "load_row32", "store_tile"]):
         print(f"  micro {nm:12s} cycles/rep:", " ".join(f"{x:7.0f}" for x in mic[i * 8:i * 8 + 5]))
+    print("  update tile cycles, 1/2/4/8 warps per CTA: dmma", " ".join(f"{x:7.0f}" for x in mic[64:68]), "| dfma", " ".join(f"{x:7.0f}" for x in mic[68:72]))
     s.close()
 
 if __name__ == "__main__":
