@@ -12,8 +12,9 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libsadvio_b200.so")
 SOURCES = ["sdv_lib.cu"]
-HEADERS = ["sdv_kernels.cuh", "sdv_math.cuh", "sdv_types.cuh", os.path.join("..", "..", "include", "sdv.h")]
+HEADERS = ["sdv_kernels.cuh", "sdv_chol.cuh", "sdv_chol_band.cuh", "sdv_math.cuh", "sdv_types.cuh", os.path.join("..", "..", "include", "sdv.h")]
 NVCC_FLAGS = [
+    *(["-DSDV_BAND_PROF"] if os.environ.get("SDV_BAND_PROF") else []),
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
 ]
 

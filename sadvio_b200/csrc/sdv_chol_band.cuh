@@ -1,0 +1,654 @@
+// Banded FP64 Cholesky + triangular solves of the reduced system in ONE CTA (variant 6, the default whenever it applies).
+//
+// Why: the reduced (pose/velocity/bias) system of a sliding window is block-banded — a landmark couples only the keyframes
+// that see it, an IMU factor only consecutive keyframes (AOptimizer.cpp:59-85) — and the envelope of a Cholesky factor is
+// the envelope of the matrix.  For the headline window (n = 735) the half-bandwidth is 59 columns: the whole factorisation
+// is ONE dependency chain of 735 pivots with a working set of 80 x 80 doubles.  Spreading that over a cluster (variants 0-5)
+// pays an L2 / DSMEM round trip per tile step; here the active window never leaves the shared memory of one SM and the
+// pivot chain never leaves the registers of one warp.
+//
+// Blocks are 16 x 16 (BN).  Half-bandwidth bw (in blocks, computed on the host from the factor graph, sdv_lib.cu).
+// Right-looking, per block step k:
+//   C  warp 0 ("chain"): rows of block k AND block k+1 are stacked in its registers (16 lanes each; the two half-warps swap
+//      roles every step, so the rows of block k+1 are already in place when they become pivots).  One pass over the 16
+//      pivots factors D_k, solves P_(k+1,k) = W_(k+1,k) L_kk^-T and applies D_(k+1) -= P P^T on the fly: the next diagonal
+//      block is final the moment the last pivot is done.  Per pivot the chain is  mul -> fma -> shfl -> rsqrt  (the next
+//      pivot is formed on its own lane before the broadcast; rsqrt = rsqrt.approx.f64 + one third-order correction).
+//      Meanwhile the 15 worker warps write the previous panel to global memory (L is needed again by the backward solve),
+//      invert the previous diagonal block, and prefetch the next block row of S with cp.async.
+//   T  workers: P_(k+d,k) = W_(k+d,k) L_kk^-T for d = 2..bw, and the right-hand side row (L y = g rides along).
+//   U  workers: W_(k+di,k+dj) -= P_di P_dj^T with FP64 tensor-core MMAs (mma.sync.m8n8k4.f64, SASS DMMA), g -= P y.
+// Backward solve L^T x = y: one warp, block columns of L streamed back from L2 with TMA bulk copies (4-stage mbarrier
+// ring); with the explicit inverse of every diagonal block a step is two small matrix-vector products.
+#pragma once
+#include "sdv_chol.cuh"
+
+namespace sdv {
+
+constexpr int BN = 16;          // block size
+constexpr int WSTR = 18;        // row stride (doubles) of a window block: 16-byte aligned rows, conflict-free LDS.128 per row
+constexpr int WBLK = BN * WSTR; // doubles per window block
+constexpr int BCT = 512;        // threads of the CTA
+constexpr int BNW = BCT / 32;
+constexpr int BAND_MAX_BW = 7;  // task tables / shared memory are sized for this
+constexpr int BAND_MAX_STAGES = 16; // backward-solve ring (TMA bulk copies in flight)
+
+// shared-memory plan, identical on host and device.  The panel of a step (L_kk and P_(k+1,k) .. P_(k+bw,k), stacked) is
+// stored TRANSPOSED: column c of the stacked panel is contiguous, pan[c * pcs + 16 d + row]; pcs = 16 (bw + 1) + 4 makes the
+// FP64 MMA fragment loads conflict-free and lets the chain warp read "the rest of column c" with one base address.
+struct BandPlan {
+    int nb, bw, R;                 // block rows, half-bandwidth in blocks, window rows kept in shared memory
+    int pcs, pan_doubles;          // panel column stride, doubles per panel buffer
+    int stages;                    // backward ring depth
+    int o_win, o_pan, o_inv, o_ys, o_g, o_end; // offsets in doubles
+};
+__host__ __device__ inline BandPlan band_plan(int n_pad, int bw) {
+    BandPlan p;
+    p.nb = n_pad / BN;
+    p.bw = bw;
+    p.R = p.nb < bw + 3 ? p.nb : bw + 3; // live rows k .. k+bw, plus two slots for the prefetch of block row k+bw+2
+    p.pcs = BN * (bw + 1) + 4;
+    p.pan_doubles = BN * p.pcs + 32; // + slack: the chain warp reads up to 31 doubles past its column
+    const int win = p.R * (bw + 1) * WBLK;
+    int fwd = win + 2 * p.pan_doubles;
+    // the backward ring reuses window + panels; give it up to BAND_MAX_STAGES stages while the CTA stays below ~200 KB
+    const int stage = (bw + 2) * BN * BN;
+    int stages = p.nb < BAND_MAX_STAGES ? p.nb : BAND_MAX_STAGES;
+    while (stages > 2 && (stages * stage + n_pad + 64) * 8 > 200 * 1024) stages--;
+    p.stages = stages;
+    if (fwd < stages * stage) fwd = stages * stage;
+    p.o_win = 0;
+    p.o_pan = win;
+    p.o_inv = fwd;
+    p.o_ys = p.o_inv + 2 * BN;
+    p.o_g = p.o_ys + 2 * BN;
+    p.o_end = p.o_g + n_pad;
+    return p;
+}
+
+// 1/sqrt(d): hardware seed (~2^-22) + one third-order step (error ~ 5/16 e^3), no special cases: a non-positive or
+// non-finite pivot is detected separately and poisons the result, which is then discarded.
+SDV_DEV double band_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);
+    const double q = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, q, y);
+}
+
+// One block step of the chain warp: lanes 0..15 hold row `lane` of the pivot block D_k, lanes 16..31 row `lane - 16` of
+// W_(k+1,k), so the triangular solve of the next block row costs nothing (same instructions, otherwise idle lanes).
+// Measured on B200 (tools/micro/chain2.cu): mul -> fma -> shfl -> rsqrt is 106 cycles per pivot; every shared-memory
+// load issued by this warp adds ~3 cycles, selects on the chain add 19.  Hence: the next pivot is formed on its own lane
+// before the broadcast, the zeroing of the rows above the pivot is kept off the chain, the broadcast of the pivot column
+// uses 16-byte loads (two pivots per loop iteration so the alignment is static), and the update of D_(k+1) is NOT done
+// here but by a worker warp with tensor-core MMAs.  The register file ROTATES by one column per pivot
+// (a[j-1] = a[j] - l v[j]), which keeps this a real loop of ~100 instructions — the fully unrolled triangular version
+// (2 x 1700 instructions) was instruction-fetch bound.
+// Publishes column c of [L_kk ; P_(k+1,k)] at pan[c * pcs + 0..31] and 1/diag in iv[c].
+// ptxas schedules inside a basic block but cannot see the chain across pivots; left to itself it issued the publication of
+// the column AFTER the broadcast + rsqrt of the next pivot, i.e. it serialised the two dependence chains of a pivot.  The
+// memory operations are therefore volatile asm in the order they must be issued: publish, shuffle, sync, reload.
+SDV_DEV void st_shared_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+SDV_DEV double ld_shared_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+SDV_DEV double2 ld_shared_v2f64(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+SDV_DEV double shfl_f64_volatile(double x, int src) {
+    int lo = __double2loint(x), hi = __double2hiint(x);
+    asm volatile("shfl.sync.idx.b32 %0, %0, %2, 0x1f, 0xffffffff;\n\tshfl.sync.idx.b32 %1, %1, %2, 0x1f, 0xffffffff;" : "+r"(hi), "+r"(lo) : "r"(src) : "memory");
+    return __hiloint2double(hi, lo);
+}
+
+template <int C>
+SDV_DEV void band_chain_pivot(double (&a)[16], int lane, uint32_t pan_s, uint32_t iv_s, int pcs, double &d, double &inv, bool &ok) {
+    const double l = a[0] * inv;
+    const double lm = lane < C ? 0.0 : l; // rows above the pivot (upper triangle of the block)
+    st_shared_f64(pan_s + (uint32_t)(C * pcs + lane) * 8u, lm);
+    if (lane == C) st_shared_f64(iv_s + C * 8u, inv);
+    const double pc = fma(-l, l, a[1]); // the next pivot, valid on its own lane (row C+1)
+    const double dn = shfl_f64_volatile(pc, (C + 1) & 31);
+    __syncwarp();
+    // rest of column C of the stacked panel: entries C+1 .. C+15 (those past row 15 feed registers that are already dead)
+    const uint32_t vb = pan_s + (uint32_t)(C * pcs + C) * 8u;
+    double v[16];
+    if (C & 1) {
+#pragma unroll
+        for (int j = 1; j < 16; j += 2) {
+            const double2 w = ld_shared_v2f64(vb + j * 8u);
+            v[j] = w.x;
+            if (j + 1 < 16) v[j + 1] = w.y;
+        }
+    } else {
+        v[1] = ld_shared_f64(vb + 8u);
+#pragma unroll
+        for (int j = 2; j < 16; j += 2) {
+            const double2 w = ld_shared_v2f64(vb + j * 8u);
+            v[j] = w.x;
+            if (j + 1 < 16) v[j + 1] = w.y;
+        }
+    }
+    if (C < 15) ok = ok && (dn > 0.0) && (dn < 1e300);
+    const double invn = band_rsqrt(dn);
+#pragma unroll
+    for (int j = 1; j < 16 - (C >= 8 ? C - 7 : 0); j++) a[j - 1] = fma(-lm, v[j], a[j]); // columns past the block end are dead
+    d = dn;
+    inv = invn;
+}
+
+SDV_DEV void band_chain_step(double (&a)[16], int lane, double *pan, int pcs, double *iv, bool &ok) {
+    const uint32_t pan_s = smem_u32(pan), iv_s = smem_u32(iv);
+    double d = __shfl_sync(FULL, a[0], 0);
+    ok = ok && (d > 0.0) && (d < 1e300);
+    double inv = band_rsqrt(d);
+    band_chain_pivot<0>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<1>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<2>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<3>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<4>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<5>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<6>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<7>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<8>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<9>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<10>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<11>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<12>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<13>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<14>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<15>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+}
+
+// X <- X L_kk^-T for one row per lane (t = the row), L_kk read from the transposed panel (column c at pan[c * pcs ..]);
+// element c of the result goes to dst[c * dstride].  Fully unrolled (the registers rotate, so every index is static) and
+// triangular: measured 98 cycles per pivot as a 2-pivot loop (nothing overlaps across the loop edge), see tools/micro.
+SDV_DEV void band_trsm16(double (&t)[16], const double *pan, int pcs, const double *iv, double *dst, int dstride, double *grow = nullptr) {
+    double xs[16]; // results are stored after the loop: a store into the panel in between would fence the loads behind it
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        const double x = t[0] * iv[c];
+        xs[c] = x;
+        const double *v = pan + c * pcs + c;
+        const int j0 = ((c + 1) & 1) ? 2 : 1, jn = 16 - c; // j0: first j with an even (16-byte aligned) entry index c + j
+        if (j0 == 2 && 1 < jn) t[0] = fma(-x, v[1], t[1]);
+#pragma unroll
+        for (int j = j0; j + 1 < jn; j += 2) {
+            const double2 w = *reinterpret_cast<const double2 *>(v + j);
+            t[j - 1] = fma(-x, w.x, t[j]);
+            t[j] = fma(-x, w.y, t[j + 1]);
+        }
+        if (jn > j0 && ((jn - j0) & 1)) t[jn - 2] = fma(-x, v[jn - 1], t[jn - 1]);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c++) dst[c * dstride] = xs[c];
+    if (grow) // the same row, row-major, into the global band storage of the factor
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(grow + c) = make_double2(xs[c], xs[c + 1]);
+}
+
+// C (16 x 16 window block, row stride WSTR) -= P_i P_j^T, operands = blocks of the transposed panel; one warp
+SDV_DEV void band_update_dmma(double *C, const double *PTi, const double *PTj, int pcs, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double c[2][2][2];
+#pragma unroll
+    for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+        for (int jb = 0; jb < 2; jb++) {
+            const double2 v = *reinterpret_cast<const double2 *>(C + (ib * 8 + g) * WSTR + jb * 8 + 2 * t);
+            c[ib][jb][0] = v.x;
+            c[ib][jb][1] = v.y;
+        }
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        double av[2], bv[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            av[q] = -PTi[(kk * 4 + t) * pcs + q * 8 + g];
+            bv[q] = PTj[(kk * 4 + t) * pcs + q * 8 + g];
+        }
+#pragma unroll
+        for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+            for (int jb = 0; jb < 2; jb++) dmma(c[ib][jb][0], c[ib][jb][1], av[ib], bv[jb]);
+    }
+#pragma unroll
+    for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+        for (int jb = 0; jb < 2; jb++)
+            *reinterpret_cast<double2 *>(C + (ib * 8 + g) * WSTR + jb * 8 + 2 * t) = make_double2(c[ib][jb][0], c[ib][jb][1]);
+}
+
+SDV_DEV void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+SDV_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// A : (n_pad + 32) x ld reduced system (lower triangle, right-hand side in row n_pad), read only.
+// Lb: band storage of the factor, block column k at Lb + k (bw + 2) 256: [L_kk | L_(k+1,k) .. L_(k+bw,k) | L_kk^-1], each
+//     block 16 x 16 row-major.  dxp receives -x (S delta = -g).
+__global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, const double *A, double *Lb,
+                                                      const double *damp_p, const double *graw_p, double *dxp, double *prof) {
+    if (st->status != 0) return;
+    extern __shared__ __align__(16) double bsm[];
+    __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8];
+    __shared__ int s_fail;
+    const BandPlan pl = band_plan(P.n_pad, P.band_bw);
+    const int nb = pl.nb, bw = pl.bw, R = pl.R, ld = P.ld, pcs = pl.pcs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *win = bsm + pl.o_win, *pan0 = bsm + pl.o_pan, *invs = bsm + pl.o_inv, *ysv = bsm + pl.o_ys, *gs = bsm + pl.o_g;
+    const int bwp = bw + 1;
+    // window block (i, j) lives in slot (i mod R, j mod (bw+1)); kr = k mod R and kc = k mod (bw+1) are carried along so that
+    // no integer division is executed inside the factorisation
+    int kr = 0, kc = 0;
+    auto Wk = [&](int di, int dj) { // block (k + di, k + dj), 0 <= dj <= di <= bw + 1
+        int rs = kr + di, cs = kc + dj;
+        rs -= rs >= R ? R : 0;
+        cs -= cs >= bwp ? bwp : 0;
+        return win + (rs * bwp + cs) * WBLK;
+    };
+#ifdef SDV_BAND_PROF
+    auto rdclk = [] { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; };
+    long long tp[6] = {0, 0, 0, 0, 0, 0}, tc = rdclk(), tn;
+#define BAND_TICK(q) do { tn = rdclk(); tp[q] += tn - tc; tc = tn; } while (0)
+#define BAND_BUSY(q) do { tb[q] += rdclk() - tc; } while (0)
+#else
+#define BAND_TICK(q) do { } while (0)
+#define BAND_BUSY(q) do { } while (0)
+#endif
+
+    // block row i of S (blocks max(0, i - bw) .. i) -> window, 16-byte cp.async chunks; threads [t0, t0 + nt)
+    auto load_row = [&](int i, int rs, int c0, int t0, int nt, int tid = -1) { // rs = i mod R, c0 = max(0, i - bw) mod (bw + 1)
+        if (tid < 0) tid = (int)threadIdx.x;
+        const int j0 = i - bw > 0 ? i - bw : 0;
+        const int nchunk = (i - j0 + 1) * 128;
+#pragma unroll 1
+        for (int e = tid - t0; e < nchunk; e += nt) {
+            const int jj = e >> 7, r = (e >> 3) & 15, q = e & 7;
+            int cs = c0 + jj;
+            cs -= cs >= bwp ? bwp : 0;
+            cp_async16(win + (rs * bwp + cs) * WBLK + r * WSTR + 2 * q, A + (size_t)(i * BN + r) * ld + (j0 + jj) * BN + 2 * q);
+        }
+    };
+    // ---- roles (warp-specialised dataflow; every warp runs ONE small loop, the hand-offs are mbarriers in shared memory).
+    // Warp w runs on SM sub-partition w % 4, each with its own FP64 pipe: the FP64-heavy roles are spread over the four.
+    //   warp 0                    chain        factor D_k, solve P_(k+1,k)                      -> bar_panel
+    //   warps 1,2,3,7,11,15       row solve    P_(k+d,k) = W_(k+d,k) L_kk^-T, d = 2..7 (if <= bw) -> bar_p[d]
+    //   warp 5                    right-hand side  y_k, g_(k+d) -= P_d y_k                        -> bar_rhs
+    //   warp 6                    inverse of L_kk (for the backward solve)                       -> bar_copy
+    //   up to 6 of 9,10,13,14,7,11,15  updates  W_(k+di,k+dj) -= P_di P_dj^T (tensor-core MMAs) -> bar_c1, bar_step
+    //   the rest of those         copy         panel blocks 0,1 -> global, prefetch of block row k+bw+2 -> bar_copy
+    //   warps 4, 8, 12            idle (they share the chain's sub-partition)
+    // A CTA-wide barrier per phase was tried first: a warp that sleeps at __syncthreads() while the chain warp runs took
+    // 1.5-2 k cycles to get going again (per-warp clock64 traces), 3 times per step.
+    int role = 6, ridx = 0, ncopy = 1, n_upd = 0; // 0 chain, 1 row solve (ridx = d), 2 rhs, 3 inverse, 4 update (ridx = u), 5 copy, 6 idle
+    {
+        // Warp w runs on SM sub-partition w % 4, each with its own (narrow: 16 lanes) FP64 pipe and instruction cache.
+        //  * sub-partition 0 belongs to the chain warp alone (warps 4, 8, 12 idle): with three other loops next to it the
+        //    ~10 KB of unrolled pivot code ran 45 % slower than alone (tools/micro/roles.cu vs the in-kernel trace);
+        //  * the row solves d = 2, 3 — the updates (2,1), (3,1) that gate the next steps wait for them — share their
+        //    sub-partitions only with update warps, which are idle while the solves run;
+        //  * everything with slack (d = 4 solve, right-hand side, inverse, copy) sits on sub-partition 3.
+        const int solve_warp[6] = {1, 2, 3, 13, 14, 10}; // d = 2 .. 7
+        const int upd_pool[6] = {5, 9, 6, 10, 13, 14};   // minus the ones used as row-solve warps (bw > 4)
+        if (warp == 0) role = 0;
+        else if (warp == 7) role = 2;
+        else if (warp == 11) role = 3;
+        else if (warp == 15) role = 5;
+        n_upd = bw <= 4 ? 6 : 10 - bw;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            if (q < n_upd && warp == upd_pool[q]) {
+                role = 4;
+                ridx = q;
+            }
+            if (q + 2 <= bw && warp == solve_warp[q]) {
+                role = 1;
+                ridx = q + 2;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        s_fail = 0;
+        for (int s = 0; s < BAND_MAX_STAGES; s++) mbar_init(&full[s], 1);
+        for (int q = 0; q < 2; q++) {
+            mbar_init(&bar_panel[q], 1);
+            mbar_init(&bar_step[q], n_upd);
+            mbar_init(&bar_rhs[q], 1);
+            mbar_init(&bar_copy[q], ncopy + 1);
+            for (int d = 0; d < 8; d++) {
+                mbar_init(&bar_p[q][d], 1);
+                mbar_init(&bar_c1[q][d], 1);
+            }
+        }
+    }
+    for (int i = 0; i < nb && i < R; i++) load_row(i, i, i > bw ? (i - bw) % bwp : 0, 0, BCT); // rows 0 .. R-1 (R = bw + 3, or the whole matrix)
+    for (int e = threadIdx.x; e < P.n_pad; e += BCT) gs[e] = A[(size_t)P.n_pad * ld + e];
+    for (int e = threadIdx.x; e < 2 * pl.pan_doubles; e += BCT) pan0[e] = 0.0;
+    cp_async_wait_all();
+    __syncthreads();
+    auto ph = [](int k) { return (unsigned)((k >> 1) & 1); }; // phase parity of the barriers of step k (each is reused every 2 steps)
+    auto next_k = [&] {
+        if (++kr == R) kr = 0;
+        if (++kc == bwp) kc = 0;
+    };
+
+    bool ok = true;
+    BAND_TICK(0);
+    if (role == 0) {
+        // ------------------------------------------------------------------ chain
+        for (int k = 0; k < nb; k++) {
+            const int par = k & 1;
+            const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
+            if (k >= 2) {
+                mbar_wait_cta(&bar_step[par], ph(k - 2)); // every reader of this panel buffer (step k-2) is done
+                mbar_wait_cta(&bar_rhs[par], ph(k - 2));
+                mbar_wait_cta(&bar_copy[par], ph(k - 2)); // ... and it has been written out; block row k+bw is resident
+            }
+            if (k >= 1) { // blocks (k,k) and (k+1,k) updated through step k-1 = tasks (1,1) and (2,1) of that step
+                mbar_wait_cta(&bar_c1[par ^ 1][1], ph(k - 1));
+                if (nd >= 1) mbar_wait_cta(&bar_c1[par ^ 1][2], ph(k - 1));
+            }
+            BAND_TICK(1);
+            double a[16];
+            const double *src = (lane < 16 ? Wk(0, 0) : Wk(nd >= 1 ? 1 : 0, 0)) + (lane & 15) * WSTR; // last block: lanes 16.. redo D_k, unused
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(src + c);
+                a[c] = v.x;
+                a[c + 1] = v.y;
+            }
+            band_chain_step(a, lane, pan0 + par * pl.pan_doubles, pcs, invs + par * BN, ok);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&bar_panel[par]);
+            BAND_TICK(2);
+            next_k();
+        }
+    } else if (role == 1) {
+        // ------------------------------------------------------------------ row solve
+        const int d = ridx;
+        for (int k = 0; k + d < nb; k++) {
+            const int par = k & 1;
+            double *pan = pan0 + par * pl.pan_doubles;
+            mbar_wait_cta(&bar_panel[par], ph(k));
+            if (k >= 1 && d < bw) mbar_wait_cta(&bar_c1[par ^ 1][d + 1], ph(k - 1)); // block (k+d, k) updated through step k-1 (task (d+1, 1)); d = bw: fresh row
+            BAND_TICK(1);
+            if (lane < 16) {
+                double t[16];
+                const double *src = Wk(d, 0) + lane * WSTR;
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(src + c);
+                    t[c] = v.x;
+                    t[c + 1] = v.y;
+                }
+                band_trsm16(t, pan, pcs, invs + par * BN, pan + 16 * d + lane, pcs, Lb + ((size_t)k * (bw + 2) + d) * 256 + lane * 16);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&bar_p[par][d]);
+            BAND_TICK(2);
+            next_k();
+        }
+    } else if (role == 2) {
+        // ------------------------------------------------------------------ right-hand side: L y = g rides along
+        for (int k = 0; k < nb; k++) {
+            const int par = k & 1;
+            const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
+            const double *pan = pan0 + par * pl.pan_doubles;
+            mbar_wait_cta(&bar_panel[par], ph(k));
+            BAND_TICK(1);
+            if (lane == 0) {
+                double t[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) t[c] = gs[k * BN + c];
+                band_trsm16(t, pan, pcs, invs + par * BN, gs + k * BN, 1);
+            }
+            __syncwarp();
+            const int r = lane & 15, hh = lane >> 4;
+            const double *y = gs + k * BN + hh * 8;
+            for (int d = 1; d <= nd; d++) {
+                if (d >= 2) mbar_wait_cta(&bar_p[par][d], ph(k));
+                const double *Pd = pan + hh * 8 * pcs + 16 * d + r;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    s0 += Pd[c * pcs] * y[c];
+                    s1 += Pd[(c + 1) * pcs] * y[c + 1];
+                }
+                double sum = s0 + s1;
+                sum += __shfl_xor_sync(FULL, sum, 16);
+                if (hh == 0) gs[(k + d) * BN + r] -= sum;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&bar_rhs[par]);
+            BAND_TICK(2);
+        }
+    } else if (role == 3) {
+        // ------------------------------------------------------------------ L_kk^-1 -> global (block bw+1 of column k)
+        for (int k = 0; k < nb; k++) {
+            const int par = k & 1;
+            mbar_wait_cta(&bar_panel[par], ph(k));
+            BAND_TICK(1);
+            if (lane < 16) {
+                double t[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) t[c] = c == lane ? 1.0 : 0.0;
+                band_trsm16(t, pan0 + par * pl.pan_doubles, pcs, invs + par * BN, Lb + ((size_t)k * (bw + 2) + bw + 1) * 256 + lane, 16); // Minv[c][r] = (L^-T)[r][c]
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&bar_copy[par]);
+            BAND_TICK(2);
+        }
+    } else if (role == 4) {
+        // ------------------------------------------------------------------ trailing updates
+        // Block (i, j) is updated at steps k = i-bw .. j-1, every time as task (di, dj) = (i-k, j-k).  Ownership goes with the
+        // BLOCK: "virtual worker" (o, s) owns the blocks with i - j = o and j = s mod (bw - o) — exactly one task per step —
+        // and virtual worker v runs on update warp v mod N_UPD.  Successive updates of a block are then program-ordered
+        // inside one warp and need no barrier; only the first block column (dj = 1), which the chain and the row solves of
+        // the next step read, is signalled (bar_c1).
+        const int u = ridx;
+        constexpr int MAXV = (BAND_MAX_BW * (BAND_MAX_BW + 1) / 2 + 2) / 3; // at least 3 update warps (bw = 7)
+        int vo[MAXV], vdj[MAXV], nv = 0; // offset o and current dj of my virtual workers
+        {
+            int v = 0;
+            for (int o = 0; o < bw; o++)
+                for (int sl = 0; sl < bw - o; sl++, v++)
+                    if (v % n_upd == u) {
+#pragma unroll
+                        for (int q = 0; q < MAXV; q++)
+                            if (q == nv) {
+                                vo[q] = o;
+                                vdj[q] = sl == 0 ? bw - o : sl; // step 0: j in [1, bw - o], j = sl mod (bw - o)
+                            }
+                        nv++;
+                    }
+        }
+        for (int k = 0; k < nb; k++) {
+            const int par = k & 1;
+            const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
+            const double *pan = pan0 + par * pl.pan_doubles;
+            mbar_wait_cta(&bar_panel[par], ph(k)); // also keeps a warp without tasks from running ahead of the barrier phases
+            // two passes: first-column tasks (dj = 1) first, the next step waits for them
+#pragma unroll
+            for (int pass = 0; pass < 2; pass++)
+#pragma unroll
+                for (int q = 0; q < MAXV; q++) {
+                    if (q >= nv) continue;
+                    const int dj = vdj[q], di = dj + vo[q];
+                    if ((dj == 1) != (pass == 0) || di > nd) continue;
+                    if (di >= 2) mbar_wait_cta(&bar_p[par][di], ph(k));
+                    if (dj >= 2) mbar_wait_cta(&bar_p[par][dj], ph(k));
+                    BAND_TICK(1);
+                    band_update_dmma(Wk(di, dj), pan + 16 * di, pan + 16 * dj, pcs, lane);
+                    if (dj == 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cta(&bar_c1[par][di]);
+                    }
+                    BAND_TICK(2);
+                }
+#pragma unroll
+            for (int q = 0; q < MAXV; q++)
+                if (q < nv) vdj[q] = vdj[q] == 1 ? bw - vo[q] : vdj[q] - 1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&bar_step[par]);
+            next_k();
+        }
+    } else if (role == 5) {
+        // ------------------------------------------------------------------ copy warps: blocks 0 and 1 of panel k -> global band
+        // storage (transposing), then the prefetch of block row k+bw+2 into the window slot that row k-1 has left
+        const int ct = ridx * 32 + lane, nct = ncopy * 32;
+        for (int k = 0; k < nb; k++) {
+            const int par = k & 1;
+            const double *pan = pan0 + par * pl.pan_doubles;
+            mbar_wait_cta(&bar_panel[par], ph(k));
+            BAND_TICK(1);
+            double *dst = Lb + (size_t)k * (bw + 2) * 256;
+            const int ne = (k + 1 < nb ? 2 : 1) * 256;
+#pragma unroll 1
+            for (int e = ct; e < ne; e += nct) {
+                const int r = e >> 4, c = e & 15; // r = 16 d + row: row of the stacked panel
+                dst[e] = pan[c * pcs + r];
+            }
+            if (k >= 1 && k + bw + 2 < nb) { // row k-1 was last read by the chain of step k-1
+                load_row(k + bw + 2, kr == 0 ? R - 1 : kr - 1, kc + 2 >= bwp ? kc + 2 - bwp : kc + 2, 0, nct, ct);
+                cp_async_wait_all();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&bar_copy[par]);
+            BAND_TICK(2);
+            next_k();
+        }
+    }
+    BAND_TICK(3);
+    if (warp == 0 && !ok) s_fail = 1;
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy writes (Lb, window) before the bulk copies below
+    __syncthreads();
+    if (s_fail) acc->chol_fail = 1; // benign race: every thread writes the same value
+    const bool bad = s_fail != 0 || __ldcg(&acc->schur_fail) != 0;
+    if (bad) {
+        if (threadIdx.x == 0) {
+            st->step_valid = 0;
+            st->model_cost_change = 0.0;
+        }
+        return;
+    }
+    BAND_TICK(4);
+
+    // ---------------------------------------------------------------------- backward solve L^T x = y (warp 0)
+    if (warp == 0) {
+        const int stage_doubles = (bw + 2) * 256, NS = pl.stages;
+        const uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
+        double *ring = bsm;
+        if (lane == 0)
+            for (int s = 0; s < NS && s < nb; s++) {
+                const int k = nb - 1 - s;
+                mbar_expect_tx(&full[s], stage_bytes);
+                bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k * stage_doubles, stage_bytes, &full[s]);
+            }
+        const int c = lane & 15, hh = lane >> 4;
+        double *rvs = invs; // 16 doubles of scratch (the reciprocal diagonals are no longer needed)
+        int s = 0, ph = 0;
+        for (int it = 0; it < nb; it++) {
+            const int k = nb - 1 - it;
+            const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
+            BAND_TICK(5);
+            mbar_wait(&full[s], (unsigned)ph);
+            BAND_TICK(3);
+            const double *sb = ring + s * stage_doubles;
+            // (L_(k+d,k))^T x_(k+d), d = 1..nd: lane (c, hh) sums rows 8 hh .. 8 hh + 7 of every block; four independent chains
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int d = 1; d <= BAND_MAX_BW; d++) {
+                if (d > nd) break;
+                const double *Lc = sb + d * 256 + hh * 128 + c;
+                const double2 *x2 = reinterpret_cast<const double2 *>(gs + (k + d) * BN + hh * 8);
+                const double2 xa = x2[0], xb = x2[1], xc = x2[2], xd = x2[3];
+                s0 = fma(Lc[0], xa.x, s0);
+                s1 = fma(Lc[16], xa.y, s1);
+                s2 = fma(Lc[32], xb.x, s2);
+                s3 = fma(Lc[48], xb.y, s3);
+                s0 = fma(Lc[64], xc.x, s0);
+                s1 = fma(Lc[80], xc.y, s1);
+                s2 = fma(Lc[96], xd.x, s2);
+                s3 = fma(Lc[112], xd.y, s3);
+            }
+            double sum = (s0 + s1) + (s2 + s3);
+            sum += __shfl_xor_sync(FULL, sum, 16);
+            const double rv = gs[k * BN + c] - sum; // both half-warps hold rv[c]
+            if (hh == 0) rvs[c] = rv;               // x_k = L_kk^-T rv = Minv^T rv, broadcast through shared memory
+            __syncwarp();
+            const double *Mi = sb + (bw + 1) * 256 + hh * 128 + c;
+            const double2 *r2 = reinterpret_cast<const double2 *>(rvs + hh * 8);
+            const double2 ra = r2[0], rb = r2[1], rc = r2[2], rd = r2[3];
+            double x0 = Mi[0] * ra.x, x1 = Mi[16] * ra.y, x2v = Mi[32] * rb.x, x3 = Mi[48] * rb.y;
+            x0 = fma(Mi[64], rc.x, x0);
+            x1 = fma(Mi[80], rc.y, x1);
+            x2v = fma(Mi[96], rd.x, x2v);
+            x3 = fma(Mi[112], rd.y, x3);
+            double x = (x0 + x1) + (x2v + x3);
+            x += __shfl_xor_sync(FULL, x, 16);
+            if (hh == 0) {
+                gs[k * BN + c] = x;
+                dxp[k * BN + c] = -x;
+            }
+            __syncwarp();
+            if (lane == 0 && it + NS < nb) {
+                const int k2 = nb - 1 - (it + NS);
+                mbar_expect_tx(&full[s], stage_bytes);
+                bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k2 * stage_doubles, stage_bytes, &full[s]);
+            }
+            if (++s == NS) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+    __syncthreads();
+    BAND_TICK(5);
+#ifdef SDV_BAND_PROF
+    if (prof && lane == 0)
+        for (int q = 0; q < 6; q++) prof[warp * 8 + q] = (double)tp[q]; // warp 0: [setup, wait, chain, -, tail, backward]
+#endif
+
+    // ---------------------------------------------------------------------- reduced-parameter update, model-decrease terms,
+    // candidate frame-camera table (same epilogue as chol_backward_v2)
+    const LinBuf &Bx = st->cur ? B1 : B0;
+    const LinBuf &Bc = st->cur ? B0 : B1;
+    const int n = P.n;
+    double gd = 0, dd = 0, sn = 0, cn = 0;
+    for (int i = threadIdx.x; i < P.n_pad; i += BCT) {
+        const double d = i < n ? -gs[i] : 0.0;
+        if (i >= n) dxp[i] = 0.0;
+        const double xc = Bx.xp[i] + d;
+        Bc.xp[i] = i < n ? xc : 0.0;
+        if (i < n) {
+            gd += graw_p[i] * d;
+            dd += damp_p[i] * d * d;
+            sn += d * d;
+            cn += xc * xc;
+        }
+    }
+    gd = warp_sum(gd);
+    dd = warp_sum(dd);
+    sn = warp_sum(sn);
+    cn = warp_sum(cn);
+    if (lane == 0 && P.rank == 0) {
+        atomicAdd(&acc->model_gd, gd);
+        atomicAdd(&acc->model_dd, dd);
+        atomicAdd(&acc->step_norm2, sn);
+        atomicAdd(&acc->cand_norm2, cn);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.F * P.C; i += BCT) compute_fct_row(P, Bc.xp, i / P.C, i % P.C, Bc.fct + (size_t)i * FCT_ROW);
+    if (threadIdx.x == 0) st->step_valid = 1;
+}
+
+} // namespace sdv

@@ -8,6 +8,7 @@
 #include "../../include/sdv.h"
 #include "sdv_kernels.cuh"
 #include "sdv_chol.cuh"
+#include "sdv_chol_band.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -123,6 +124,7 @@ struct sdv_handle {
     int rank = 0, world = 1;
     std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs; // reused between uploads
     std::vector<uint32_t> tmp_tile_nz;
+    int band_bw = -1, band_smem = 0; // 16-column block half-bandwidth of the reduced system (-1 = not computed), k_chol_band shared memory
     int chol_tiles_nz = 0, chol_tiles_all = 0; // structurally non-zero tiles of L / all lower tiles
     LMState h_state;
     Accum h_acc;
@@ -598,16 +600,18 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     const int Tt = n_pad / 32;
     std::vector<uint32_t> &tile_nz = h->tmp_tile_nz; // [(Tt + 1)][4] bit j of row i: tile (i, j) of L may be non-zero
     tile_nz.assign((size_t)(Tt + 1) * 4, 0u);
-    if (Tt <= 128) {
-        struct TMask {
-            uint64_t w[2];
-            bool operator==(const TMask &o) const { return w[0] == o.w[0] && w[1] == o.w[1]; }
-        };
+    struct TMask {
+        uint64_t w[2];
+        bool operator==(const TMask &o) const { return w[0] == o.w[0] && w[1] == o.w[1]; }
+    };
+    // low[i]: column groups j (of `gs` columns each, at most 128 groups) coupled with group row i before elimination
+    auto build_low = [&](const int gs, std::vector<TMask> &low) {
+        const int ng = n_pad / gs;
         auto add_cols = [&](TMask &m, int c0, int ncols) {
             if (c0 < 0) return;
-            for (int t = c0 / 32; t <= (c0 + ncols - 1) / 32; t++) m.w[t >> 6] |= 1ull << (t & 63);
+            for (int t = c0 / gs; t <= (c0 + ncols - 1) / gs; t++) m.w[t >> 6] |= 1ull << (t & 63);
         };
-        std::vector<TMask> low((size_t)Tt + 1, TMask{{0, 0}}); // low[i]: columns j coupled with tile row i
+        low.assign((size_t)ng + 1, TMask{{0, 0}});
         auto add_clique = [&](const TMask &m) {
             for (int wq = 0; wq < 2; wq++) {
                 uint64_t bits = m.w[wq];
@@ -623,62 +627,66 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             TMask all{{0, 0}};
             add_cols(all, 0, n_pad);
             add_clique(all);
-        } else {
-            std::vector<TMask> pose_mask(F, TMask{{0, 0}}), frame_mask(F, TMask{{0, 0}});
-            for (int f = 0; f < F; f++) {
-                add_cols(pose_mask[f], pose_col[f], 6);
-                frame_mask[f] = pose_mask[f];
-                add_cols(frame_mask[f], vb_col[f], 9);
-                add_clique(frame_mask[f]); // diagonal blocks (pose prior, damping)
-            }
-            // visual factors: every landmark couples the poses of the keyframes that see it (and its own columns when kept)
-            std::vector<TMask> uniq;
-            TMask last{{0, 0}};
-            for (int l = 0; l < L; l++) {
-                TMask m{{0, 0}};
-                for (int q = slot_ptr[l]; q < slot_ptr[l + 1]; q++) {
-                    const TMask &pm = pose_mask[slot_frame[q]];
-                    m.w[0] |= pm.w[0];
-                    m.w[1] |= pm.w[1];
-                }
-                if (lmk_col[l] >= 0) add_cols(m, lmk_col[l], 3);
-                if (m == last) continue;
-                last = m;
-                bool seen = false;
-                for (size_t u = uniq.size(); u-- > 0 && uniq.size() - u <= 32;) seen |= uniq[u] == m;
-                if (!seen) uniq.push_back(m);
-            }
-            for (const TMask &m : uniq) add_clique(m);
-            for (int p = 0; p < Pn; p++) { // IMUFactor + IMUBiasFactor couple all 15 parameters of both keyframes
-                TMask m = frame_mask[w->imu_i[p]];
-                m.w[0] |= frame_mask[w->imu_j[p]].w[0];
-                m.w[1] |= frame_mask[w->imu_j[p]].w[1];
-                add_clique(m);
-            }
-            if (dp) { // dense marginalisation prior: one clique over everything it touches
-                TMask m{{0, 0}};
-                for (int c : mp_dst)
-                    if (c >= 0) add_cols(m, c, 1);
-                add_clique(m);
-            }
-            if (sp) {
-                if (sp->has_imu_prior) add_clique(frame_mask[sp->frame]);
-                if (sp->has_lmk_prior) {
-                    TMask m{{0, 0}};
-                    add_cols(m, lmk_col[sp->lmk0], 3);
-                    add_clique(m);
-                }
-                for (int k = 0; k < sp->n_l2l; k++) {
-                    TMask m{{0, 0}};
-                    add_cols(m, lmk_col[sp->l2l_a[k]], 3);
-                    add_cols(m, lmk_col[sp->l2l_b[k]], 3);
-                    add_clique(m);
-                }
-            }
-            for (int t = 0; t < Tt; t++) low[t].w[t >> 6] |= 1ull << (t & 63); // padding columns: identity diagonal
+            return;
         }
+        std::vector<TMask> pose_mask(F, TMask{{0, 0}}), frame_mask(F, TMask{{0, 0}});
+        for (int f = 0; f < F; f++) {
+            add_cols(pose_mask[f], pose_col[f], 6);
+            frame_mask[f] = pose_mask[f];
+            add_cols(frame_mask[f], vb_col[f], 9);
+            add_clique(frame_mask[f]); // diagonal blocks (pose prior, damping)
+        }
+        // visual factors: every landmark couples the poses of the keyframes that see it (and its own columns when kept)
+        std::vector<TMask> uniq;
+        TMask last{{0, 0}};
+        for (int l = 0; l < L; l++) {
+            TMask m{{0, 0}};
+            for (int q = slot_ptr[l]; q < slot_ptr[l + 1]; q++) {
+                const TMask &pm = pose_mask[slot_frame[q]];
+                m.w[0] |= pm.w[0];
+                m.w[1] |= pm.w[1];
+            }
+            if (lmk_col[l] >= 0) add_cols(m, lmk_col[l], 3);
+            if (m == last) continue;
+            last = m;
+            bool seen = false;
+            for (size_t u = uniq.size(); u-- > 0 && uniq.size() - u <= 32;) seen |= uniq[u] == m;
+            if (!seen) uniq.push_back(m);
+        }
+        for (const TMask &m : uniq) add_clique(m);
+        for (int p = 0; p < Pn; p++) { // IMUFactor + IMUBiasFactor couple all 15 parameters of both keyframes
+            TMask m = frame_mask[w->imu_i[p]];
+            m.w[0] |= frame_mask[w->imu_j[p]].w[0];
+            m.w[1] |= frame_mask[w->imu_j[p]].w[1];
+            add_clique(m);
+        }
+        if (dp) { // dense marginalisation prior: one clique over everything it touches
+            TMask m{{0, 0}};
+            for (int c : mp_dst)
+                if (c >= 0) add_cols(m, c, 1);
+            add_clique(m);
+        }
+        if (sp) {
+            if (sp->has_imu_prior) add_clique(frame_mask[sp->frame]);
+            if (sp->has_lmk_prior) {
+                TMask m{{0, 0}};
+                add_cols(m, lmk_col[sp->lmk0], 3);
+                add_clique(m);
+            }
+            for (int k = 0; k < sp->n_l2l; k++) {
+                TMask m{{0, 0}};
+                add_cols(m, lmk_col[sp->l2l_a[k]], 3);
+                add_cols(m, lmk_col[sp->l2l_b[k]], 3);
+                add_clique(m);
+            }
+        }
+        for (int t = 0; t < ng; t++) low[t].w[t >> 6] |= 1ull << (t & 63); // padding columns: identity diagonal
+    };
+    auto bit = [&](const TMask &m, int j) { return (m.w[j >> 6] >> (j & 63)) & 1ull; };
+    if (Tt <= 128) {
+        std::vector<TMask> low;
+        build_low(32, low);
         // symbolic right-looking elimination on the tile graph: the rows below pivot k become mutually coupled
-        auto bit = [&](const TMask &m, int j) { return (m.w[j >> 6] >> (j & 63)) & 1ull; };
         for (int k = 0; k < Tt; k++) {
             TMask col{{0, 0}}; // rows i > k with (i, k) non-zero
             for (int i = k + 1; i < Tt; i++)
@@ -700,6 +708,21 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         h->chol_tiles_nz = nnz_tiles;
         h->chol_tiles_all = Tt * (Tt + 1) / 2;
     }
+    // ---- block half-bandwidth of the reduced system at 16-column granularity.  The envelope of a Cholesky factor is the
+    //      envelope of the matrix, so max_i (i - first coupled block of row i) bounds the fill: when that band (plus two
+    //      look-ahead block rows) fits in the shared memory of one SM, the whole factorisation runs in ONE CTA (k_chol_band).
+    int band_bw = -1;
+    if (n_pad / 16 <= 128) {
+        std::vector<TMask> low16;
+        build_low(16, low16);
+        const int nb16 = n_pad / 16;
+        band_bw = 0;
+        for (int i = 0; i < nb16; i++) {
+            const int first = low16[i].w[0] ? __builtin_ctzll(low16[i].w[0]) : (low16[i].w[1] ? 64 + __builtin_ctzll(low16[i].w[1]) : i);
+            band_bw = std::max(band_bw, i - std::min(first, i));
+        }
+    }
+    h->band_bw = band_bw;
 
     // ---- input arena
     Arena A;
@@ -900,6 +923,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     P.F = F; P.C = C; P.L = L; P.O = O; P.P = Pn;
     P.vio = w->vio; P.kind = kind;
     P.n = n; P.n_pad = n_pad; P.ld = ld; P.nslots = nslots;
+    P.band_bw = 0;
     P.l0 = l0; P.l1 = l1; P.o0 = o0; P.o1 = o1;
     P.rank = h->rank; P.world = h->world;
     P.T_f_w = at<double>(db, o_T); P.v = at<double>(db, o_v); P.ba = at<double>(db, o_ba); P.bg = at<double>(db, o_bg);
@@ -976,6 +1000,23 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     h->fac_grid = std::max(1, (std::max(Pn, 1) + FAC_WARPS - 1) / FAC_WARPS);
     // dense Cholesky: one thread-block cluster when the reduced system is small enough, per-panel launches otherwise
     h->chol_cluster = 0;
+    h->band_smem = 0;
+    {
+        // banded single-CTA factorisation (variant 6) whenever the band fits in the shared memory of one SM
+        const char *v = getenv("SDV_CHOL_VARIANT");
+        const int bw = std::max(h->band_bw, 1);
+        if (h->band_bw >= 0 && bw <= BAND_MAX_BW && (!v || atoi(v) == 6) && !getenv("SDV_CHOL_DENSE")) {
+            const BandPlan pl = band_plan(n_pad, bw);
+            const size_t bytes = sizeof(double) * (size_t)pl.o_end;
+            if (bytes <= 220 * 1024 && (size_t)pl.nb * (bw + 2) * 256 <= sb_elems) {
+                if (cudaFuncSetAttribute(k_chol_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess) {
+                    h->band_smem = (int)bytes;
+                    P.band_bw = bw;
+                }
+                cudaGetLastError();
+            }
+        }
+    }
     if (n_pad <= 4096 && !getenv("SDV_NO_CLUSTER")) {
         h->chol_variant = 4;
         if (const char *v = getenv("SDV_CHOL_VARIANT")) h->chol_variant = atoi(v);
@@ -1043,7 +1084,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     if (timing) {
         auto t_g1 = std::chrono::steady_clock::now();
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        std::fprintf(stderr, "[sdv upload] reduced system n=%d (%d tiles), factor tiles %d of %d structurally non-zero\n", n, n_pad / 32, h->chol_tiles_nz, h->chol_tiles_all);
+        std::fprintf(stderr, "[sdv upload] reduced system n=%d (%d tiles), factor tiles %d of %d structurally non-zero, half-bandwidth %d blocks of 16 (%s)\n", n, n_pad / 32,
+                     h->chol_tiles_nz, h->chol_tiles_all, h->band_bw, h->band_smem > 0 ? "k_chol_band" : "cluster Cholesky");
         std::fprintf(stderr, "[sdv upload] structure %.3f ms, pack %.3f ms, h2d+setup %.3f ms, graph %.3f ms\n", ms(tu0, t_pack0), ms(t_pack0, t_pack1),
                      ms(t_pack1, t_g0), ms(t_g0, t_g1));
     }
@@ -1157,6 +1199,11 @@ int launch_factor_solve(sdv_handle *h) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
     const int T = P.n_pad / CH_T;
+    if (h->band_smem > 0) {
+        k_chol_band<<<1, BCT, h->band_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_damp_p, h->d_graw_p, h->d_dxp, h->d_prof);
+        h->launches++;
+        return SDV_OK;
+    }
     if (h->chol_cluster > 0) {
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(h->chol_cluster);

@@ -62,6 +62,7 @@ struct DevProblem {
     int n;        // reduced system dimension
     int n_pad;    // n rounded up to a multiple of 32
     int ld;       // leading dimension of S (= n_pad)
+    int band_bw;  // > 0: half-bandwidth of S in 16-column blocks, the banded single-CTA Cholesky (k_chol_band) is used
     int nslots;   // number of (landmark, frame) slots of this rank
     int l0, l1;   // landmark range owned by this rank
     int o0, o1;   // observation range owned by this rank
