@@ -800,7 +800,14 @@ struct SlotAcc {
 };
 
 // accumulates this slot's observations; hl (xx,xy,xz,yy,yz,zz) and gl receive the landmark-block parts
+SDV_DEV void slot_accumulate_range(const DevProblem &P, const LinBuf &B, int qa, int qb, int ol0, int ol1, SlotAcc &a, double *hl, double *gl);
 SDV_DEV void slot_accumulate(const DevProblem &P, const LinBuf &B, int slot, SlotAcc &a, double *hl, double *gl) {
+    const int qa = P.slot_obs_ptr[slot], qb = P.slot_obs_ptr[slot + 1];
+    slot_accumulate_range(P, B, qa, qb, qa < qb ? P.slot_obs[qa] : 0, qa + 1 < qb ? P.slot_obs[qa + 1] : 0, a, hl, gl);
+}
+// observations qa .. qb-1 of the slot; the plane indices of the first two come in registers (k_schur prefetches them one
+// landmark ahead: slot_obs_ptr -> slot_obs -> planes is three dependent L2 round trips otherwise)
+SDV_DEV void slot_accumulate_range(const DevProblem &P, const LinBuf &B, int qa, int qb, int ol0, int ol1, SlotAcc &a, double *hl, double *gl) {
     const int Oloc = P.Ocap;
 #pragma unroll
     for (int k = 0; k < 18; k++) a.W[k] = 0.0;
@@ -808,8 +815,8 @@ SDV_DEV void slot_accumulate(const DevProblem &P, const LinBuf &B, int slot, Slo
     for (int k = 0; k < 21; k++) a.H[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; k++) a.gp[k] = 0.0;
-    for (int q = P.slot_obs_ptr[slot]; q < P.slot_obs_ptr[slot + 1]; q++) {
-        int ol = P.slot_obs[q];
+    for (int q = qa; q < qb; q++) {
+        const int ol = q == qa ? ol0 : (q == qa + 1 ? ol1 : P.slot_obs[q]);
         double Jp[12], Jl[6], r0 = B.r[ol], r1 = B.r[(size_t)Oloc + ol];
 #pragma unroll
         for (int k = 0; k < 12; k++) Jp[k] = B.Jp[(size_t)k * Oloc + ol];
@@ -876,6 +883,7 @@ SDV_DEV double lm_damping(double c, double s, double radius, const SolverOpts &o
 }
 
 constexpr int SCH_WARPS = 4;
+constexpr int SCH_NIT = 5;  // off-diagonal work items a lane may accumulate in registers (k_schur chunks)
 constexpr int MAX_SLOTS = 32; // distinct keyframes one landmark may be seen from (checked at upload)
 
 // sum over the G lanes of a landmark group (G = 8, 16 or 32 consecutive lanes)
@@ -890,13 +898,22 @@ template <int G> SDV_DEV double group_sum(double v) {
 // G lanes per landmark (32/G landmarks per warp): lane s of a group owns slot s (= one keyframe seeing the landmark).
 template <int G>
 __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt,
-                                                          double *Sb, double *scale_l) {
+                                                          double *Sb, double *scale_l, double *prof = nullptr) {
     if (st->status != 0) return;
     const LinBuf &B = st->cur ? B1 : B0;
+#ifdef SDV_SCHUR_PROF
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc, tn;
+    auto rdclk = [] { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; };
+    tc = rdclk();
+#define SCH_TICK(q) do { tn = rdclk(); tp[q] += tn - tc; tc = tn; } while (0)
+#else
+#define SCH_TICK(q) do { } while (0)
+#endif
     constexpr int GPW = 32 / G;             // landmark groups per warp
     constexpr int GPB = SCH_WARPS * GPW;    // per block
     __shared__ double WY[GPB][G][36];
     __shared__ int scol[GPB][G];
+    extern __shared__ double sch_acc[]; // [39][SCH_WARPS * 32]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int lig = lane % G, gib = wib * GPW + lane / G; // lane in group, group in block
     const int ld = P.ld;
@@ -907,137 +924,259 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B
     const bool first = st->scaling_done == 0;
     double gmax = 0.0;
     const int nl = P.l1 - P.l0;
-    for (int lb = blockIdx.x * GPB; lb < nl; lb += gridDim.x * GPB) { // block-uniform trip count
-        const int l = P.l0 + lb + gib;
-        const bool valid = (lb + gib) < nl;
-        const int s0 = valid ? P.slot_ptr[l] : 0, m = valid ? P.slot_ptr[l + 1] - s0 : 0;
-        SlotAcc a;
-        double hl[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
-        int col = -1;
-        if (lig < m) {
-            slot_accumulate(P, B, s0 + lig, a, hl, gl);
-            col = P.pose_col[P.slot_frame[s0 + lig]];
+    // The reduced system receives ~370 FP64 atomics per landmark (4 keyframes), all landing on the few hundred 6x6 blocks of
+    // the co-visible keyframe pairs: at C3 that was 3.7 M L2 atomics per iteration and the whole cost of this kernel.  The
+    // host therefore groups consecutive landmarks seen from the SAME keyframes into chunks (P.chunk_ptr); a lane group walks
+    // its chunk, keeps the contributions in registers and issues the atomics once per chunk.  Landmarks seen from too many
+    // keyframes for the register budget (chunk_acc == false) take the direct path, one landmark per chunk.
+    (void)nl;
+    constexpr int NIT = SCH_NIT;
+    for (int cb = blockIdx.x * GPB; cb < P.nchunks; cb += gridDim.x * GPB) { // block-uniform trip count
+        const int ch = cb + gib;
+        const bool cvalid = ch < P.nchunks;
+        const int lA = cvalid ? P.chunk_ptr[ch] : 0, lB = cvalid ? P.chunk_ptr[ch + 1] : 0;
+        int maxlen = lB - lA;
+#pragma unroll
+        for (int o = 16; o >= G; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o)); // same trip count for the warp
+        const int s00 = cvalid ? P.slot_ptr[lA] : 0, m = cvalid ? P.slot_ptr[lA + 1] - s00 : 0; // same m for the whole chunk
+        const int nitems = m * (m - 1) / 2 * 6;
+        const bool use_acc = nitems <= NIT * G && lB - lA > 1; // else: direct atomics (a chunk of one landmark gains nothing from accumulating)
+        const int col = lig < m ? P.pose_col[P.slot_frame[s00 + lig]] : -1;
+        if (lig < m) scol[gib][lig] = col;
+        // my off-diagonal work items (pair, row i): the 6 entries of row i of -Y_a W_b^T; pairs (1,0),(2,0),(2,1),(3,0)...
+        int it_sa[NIT], it_sb[NIT], it_i[NIT];
+        double accO[NIT][6];
+        // own diagonal block (21) + right-hand side, diag(J^T J), raw gradient (3 x 6): 39 accumulators per lane in shared memory
+        // (k-major, conflict-free) — in registers they pushed the kernel over 255 registers
+        double *accD = sch_acc + threadIdx.x;
+        constexpr int AS = SCH_WARPS * 32;
+#pragma unroll
+        for (int q = 0; q < NIT; q++) {
+            const int e = lig + q * G;
+            int sa = 1, base = 0, pi = e / 6;
+            while (base + sa <= pi) {
+                base += sa;
+                sa++;
+            }
+            it_sa[q] = e < nitems ? sa : -1;
+            it_sb[q] = pi - base;
+            it_i[q] = e - pi * 6;
+#pragma unroll
+            for (int j = 0; j < 6; j++) accO[q][j] = 0.0;
         }
 #pragma unroll
-        for (int k = 0; k < 6; k++) hl[k] = group_sum<G>(hl[k]);
+        for (int k = 0; k < 39; k++) accD[k * AS] = 0.0;
+        __syncwarp();
+        // every landmark of the chunk has m slots, so landmark lA + li owns slots s00 + li m ..; a chunk of several landmarks holds
+        // eliminated landmarks only.  The observation range and the first two plane indices of the NEXT landmark are loaded
+        // while this one is processed.
+        const int dc_chunk = (cvalid && lB - lA == 1) ? P.lmk_col[lA] : -1;
+        int qa = 0, qb = 0, ol0 = 0, ol1 = 0;
+        if (cvalid && lig < m) {
+            qa = P.slot_obs_ptr[s00 + lig];
+            qb = P.slot_obs_ptr[s00 + lig + 1];
+            ol0 = qa < qb ? P.slot_obs[qa] : 0;
+            ol1 = qa + 1 < qb ? P.slot_obs[qa + 1] : 0;
+        }
+        for (int li = 0; li < maxlen; li++) {
+            const int l = lA + li;
+            const bool valid = l < lB;
+            int nqa = 0, nqb = 0;
+            const bool pre = l + 1 < lB && lig < m;
+            if (pre) {
+                nqa = P.slot_obs_ptr[s00 + (li + 1) * m + lig];
+                nqb = P.slot_obs_ptr[s00 + (li + 1) * m + lig + 1];
+            }
+            double sl0 = 1.0, sl1 = 1.0, sl2 = 1.0;
+            if (valid && !first) {
+                sl0 = scale_l[3 * (size_t)l];
+                sl1 = scale_l[3 * (size_t)l + 1];
+                sl2 = scale_l[3 * (size_t)l + 2];
+            }
+            SlotAcc a;
+            double hl[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
+            SCH_TICK(0);
+            if (valid && lig < m) slot_accumulate_range(P, B, qa, qb, ol0, ol1, a, hl, gl);
+            SCH_TICK(1);
+            if (pre) {
+                ol0 = nqa < nqb ? P.slot_obs[nqa] : 0;
+                ol1 = nqa + 1 < nqb ? P.slot_obs[nqa + 1] : 0;
+            }
+            qa = nqa;
+            qb = nqb;
 #pragma unroll
-        for (int k = 0; k < 3; k++) gl[k] = group_sum<G>(gl[k]);
-        const int dc = valid ? P.lmk_col[l] : -1;
-        bool eliminate = valid && dc < 0;
-        if (valid && dc >= 0) {
-            // kept (dense) landmark: its columns live in the reduced system, no elimination
+            for (int k = 0; k < 6; k++) hl[k] = group_sum<G>(hl[k]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) gl[k] = group_sum<G>(gl[k]);
+            SCH_TICK(2);
+            const int dc = valid ? dc_chunk : -1;
+            bool eliminate = valid && dc < 0;
+            if (valid && dc >= 0) {
+                // kept (dense) landmark: its columns live in the reduced system, no elimination
+                if (lig < m && col >= 0) {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+#pragma unroll
+                        for (int j = 0; j <= i; j++) atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], a.H[tri_idx(i, j)]);
+                        atomicAdd(&g[col + i], a.gp[i]);
+                        atomicAdd(&cdiag[col + i], a.H[tri_idx(i, i)]);
+                        atomicAdd(&graw[col + i], a.gp[i]);
+#pragma unroll
+                        for (int j = 0; j < 3; j++) { // dense landmark columns come after every frame column
+                            if (dc > col) atomicAdd(&Sb[(size_t)(dc + j) * ld + col + i], a.W[i * 3 + j]);
+                            else atomicAdd(&Sb[(size_t)(col + i) * ld + dc + j], a.W[i * 3 + j]);
+                        }
+                    }
+                }
+                if (lig == 0) {
+                    const int ii[6] = {0, 1, 2, 1, 2, 2}, jj[6] = {0, 0, 0, 1, 1, 2};
+                    const double hv[6] = {hl[0], hl[1], hl[2], hl[3], hl[4], hl[5]};
+                    for (int k = 0; k < 6; k++) atomicAdd(&Sb[(size_t)(dc + ii[k]) * ld + dc + jj[k]], hv[k]);
+                    atomicAdd(&cdiag[dc + 0], hl[0]);
+                    atomicAdd(&cdiag[dc + 1], hl[3]);
+                    atomicAdd(&cdiag[dc + 2], hl[5]);
+                    for (int k = 0; k < 3; k++) {
+                        atomicAdd(&g[dc + k], gl[k]);
+                        atomicAdd(&graw[dc + k], gl[k]);
+                    }
+                }
+            }
+            // ---- eliminated landmark
+            double Vi[6] = {0, 0, 0, 0, 0, 0};
+            if (eliminate) {
+                double s3[3];
+                if (first) {
+                    s3[0] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[0])) : 1.0;
+                    s3[1] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[3])) : 1.0;
+                    s3[2] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[5])) : 1.0;
+                    if (lig == 0) {
+                        scale_l[3 * (size_t)l] = s3[0];
+                        scale_l[3 * (size_t)l + 1] = s3[1];
+                        scale_l[3 * (size_t)l + 2] = s3[2];
+                    }
+                } else {
+                    s3[0] = sl0;
+                    s3[1] = sl1;
+                    s3[2] = sl2;
+                }
+                gmax = fmax(gmax, fmax(fabs(gl[0]), fmax(fabs(gl[1]), fabs(gl[2]))));
+                double V[6] = {hl[0] + lm_damping(hl[0], s3[0], radius, opt), hl[1], hl[2], hl[3] + lm_damping(hl[3], s3[1], radius, opt), hl[4],
+                               hl[5] + lm_damping(hl[5], s3[2], radius, opt)};
+                if (!sym3_inverse(V, Vi)) {
+                    if (lig == 0) acc->schur_fail = 1;
+                    eliminate = false;
+                }
+            }
+            SCH_TICK(3);
+            if (eliminate && lig < m) {
+                // Y = W V^-1
+                double Y[18];
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    double w0 = a.W[i * 3], w1 = a.W[i * 3 + 1], w2 = a.W[i * 3 + 2];
+                    Y[i * 3] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+                    Y[i * 3 + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+                    Y[i * 3 + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+                }
+#pragma unroll
+                for (int k = 0; k < 18; k++) {
+                    WY[gib][lig][k] = a.W[k];
+                    WY[gib][lig][18 + k] = Y[k];
+                }
+                if (col >= 0) {
+                    // own diagonal block (lower triangle), right-hand side, diag(J^T J), raw gradient
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+#pragma unroll
+                        for (int j = 0; j <= i; j++) {
+                            double sv = a.H[tri_idx(i, j)] - (Y[i * 3] * a.W[j * 3] + Y[i * 3 + 1] * a.W[j * 3 + 1] + Y[i * 3 + 2] * a.W[j * 3 + 2]);
+                            if (use_acc) accD[tri_idx(i, j) * AS] += sv;
+                            else atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], sv);
+                        }
+                        const double gv = a.gp[i] - (Y[i * 3] * gl[0] + Y[i * 3 + 1] * gl[1] + Y[i * 3 + 2] * gl[2]);
+                        if (use_acc) {
+                            accD[(21 + i) * AS] += gv;
+                            accD[(27 + i) * AS] += a.H[tri_idx(i, i)];
+                            accD[(33 + i) * AS] += a.gp[i];
+                        } else {
+                            atomicAdd(&g[col + i], gv);
+                            atomicAdd(&cdiag[col + i], a.H[tri_idx(i, i)]);
+                            atomicAdd(&graw[col + i], a.gp[i]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            SCH_TICK(4);
+            // off-diagonal pairs (a > b in slot order)
+            if (eliminate) {
+                if (use_acc) {
+#pragma unroll
+                    for (int q = 0; q < NIT; q++) {
+                        if (it_sa[q] < 0) continue;
+                        const double *Ya = &WY[gib][it_sa[q]][18 + it_i[q] * 3];
+                        const double y0 = Ya[0], y1 = Ya[1], y2 = Ya[2];
+                        const double *Wb = &WY[gib][it_sb[q]][0];
+#pragma unroll
+                        for (int j = 0; j < 6; j++) accO[q][j] -= y0 * Wb[j * 3] + y1 * Wb[j * 3 + 1] + y2 * Wb[j * 3 + 2];
+                    }
+                } else {
+                    for (int e = lig; e < nitems; e += G) {
+                        const int pi = e / 6, i = e - pi * 6;
+                        int sa = 1, base = 0;
+                        while (base + sa <= pi) {
+                            base += sa;
+                            sa++;
+                        }
+                        const int sb = pi - base;
+                        const int ca = scol[gib][sa], cbb = scol[gib][sb];
+                        if (ca < 0 || cbb < 0) continue;
+                        const double *Ya = &WY[gib][sa][18 + i * 3];
+                        const double y0 = Ya[0], y1 = Ya[1], y2 = Ya[2];
+                        const double *Wb = &WY[gib][sb][0];
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            double v = -(y0 * Wb[j * 3] + y1 * Wb[j * 3 + 1] + y2 * Wb[j * 3 + 2]);
+                            if (ca > cbb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cbb + j], v);
+                            else atomicAdd(&Sb[(size_t)(cbb + j) * ld + ca + i], v);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            SCH_TICK(5);
+        }
+        // ---- one set of atomics per chunk
+        if (use_acc && cvalid) {
             if (lig < m && col >= 0) {
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
 #pragma unroll
-                    for (int j = 0; j <= i; j++) atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], a.H[tri_idx(i, j)]);
-                    atomicAdd(&g[col + i], a.gp[i]);
-                    atomicAdd(&cdiag[col + i], a.H[tri_idx(i, i)]);
-                    atomicAdd(&graw[col + i], a.gp[i]);
-#pragma unroll
-                    for (int j = 0; j < 3; j++) { // dense landmark columns come after every frame column
-                        if (dc > col) atomicAdd(&Sb[(size_t)(dc + j) * ld + col + i], a.W[i * 3 + j]);
-                        else atomicAdd(&Sb[(size_t)(col + i) * ld + dc + j], a.W[i * 3 + j]);
-                    }
+                    for (int j = 0; j <= i; j++) atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], accD[tri_idx(i, j) * AS]);
+                    atomicAdd(&g[col + i], accD[(21 + i) * AS]);
+                    atomicAdd(&cdiag[col + i], accD[(27 + i) * AS]);
+                    atomicAdd(&graw[col + i], accD[(33 + i) * AS]);
                 }
             }
-            if (lig == 0) {
-                const int ii[6] = {0, 1, 2, 1, 2, 2}, jj[6] = {0, 0, 0, 1, 1, 2};
-                const double hv[6] = {hl[0], hl[1], hl[2], hl[3], hl[4], hl[5]};
-                for (int k = 0; k < 6; k++) atomicAdd(&Sb[(size_t)(dc + ii[k]) * ld + dc + jj[k]], hv[k]);
-                atomicAdd(&cdiag[dc + 0], hl[0]);
-                atomicAdd(&cdiag[dc + 1], hl[3]);
-                atomicAdd(&cdiag[dc + 2], hl[5]);
-                for (int k = 0; k < 3; k++) {
-                    atomicAdd(&g[dc + k], gl[k]);
-                    atomicAdd(&graw[dc + k], gl[k]);
-                }
-            }
-        }
-        // ---- eliminated landmark
-        double Vi[6] = {0, 0, 0, 0, 0, 0};
-        if (eliminate) {
-            double s3[3];
-            if (first) {
-                s3[0] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[0])) : 1.0;
-                s3[1] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[3])) : 1.0;
-                s3[2] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[5])) : 1.0;
-                if (lig == 0) {
-                    scale_l[3 * (size_t)l] = s3[0];
-                    scale_l[3 * (size_t)l + 1] = s3[1];
-                    scale_l[3 * (size_t)l + 2] = s3[2];
-                }
-            } else {
-                s3[0] = scale_l[3 * (size_t)l];
-                s3[1] = scale_l[3 * (size_t)l + 1];
-                s3[2] = scale_l[3 * (size_t)l + 2];
-            }
-            gmax = fmax(gmax, fmax(fabs(gl[0]), fmax(fabs(gl[1]), fabs(gl[2]))));
-            double V[6] = {hl[0] + lm_damping(hl[0], s3[0], radius, opt), hl[1], hl[2], hl[3] + lm_damping(hl[3], s3[1], radius, opt), hl[4],
-                           hl[5] + lm_damping(hl[5], s3[2], radius, opt)};
-            if (!sym3_inverse(V, Vi)) {
-                if (lig == 0) acc->schur_fail = 1;
-                eliminate = false;
-            }
-        }
-        if (eliminate && lig < m) {
-            // Y = W V^-1
-            double Y[18];
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                double w0 = a.W[i * 3], w1 = a.W[i * 3 + 1], w2 = a.W[i * 3 + 2];
-                Y[i * 3] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
-                Y[i * 3 + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
-                Y[i * 3 + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
-            }
-#pragma unroll
-            for (int k = 0; k < 18; k++) {
-                WY[gib][lig][k] = a.W[k];
-                WY[gib][lig][18 + k] = Y[k];
-            }
-            scol[gib][lig] = col;
-            if (col >= 0) {
-                // own diagonal block (lower triangle), right-hand side, diag(J^T J), raw gradient
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-#pragma unroll
-                    for (int j = 0; j <= i; j++) {
-                        double s = a.H[tri_idx(i, j)] - (Y[i * 3] * a.W[j * 3] + Y[i * 3 + 1] * a.W[j * 3 + 1] + Y[i * 3 + 2] * a.W[j * 3 + 2]);
-                        atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], s);
-                    }
-                    atomicAdd(&g[col + i], a.gp[i] - (Y[i * 3] * gl[0] + Y[i * 3 + 1] * gl[1] + Y[i * 3 + 2] * gl[2]));
-                    atomicAdd(&cdiag[col + i], a.H[tri_idx(i, i)]);
-                    atomicAdd(&graw[col + i], a.gp[i]);
-                }
-            }
-        }
-        __syncwarp();
-        // off-diagonal pairs (a > b in slot order): work item = (pair, row i) -> the 6 entries of row i of -Y_a W_b^T
-        if (eliminate) {
-            const int nitems = m * (m - 1) / 2 * 6;
-            for (int e = lig; e < nitems; e += G) {
-                const int pi = e / 6, i = e - pi * 6;
-                int sa = 1, base = 0; // pair index -> (sa, sb), sa > sb: pairs are enumerated (1,0),(2,0),(2,1),(3,0)...
-                while (base + sa <= pi) {
-                    base += sa;
-                    sa++;
-                }
-                const int sb = pi - base;
-                const int ca = scol[gib][sa], cb = scol[gib][sb];
-                if (ca < 0 || cb < 0) continue;
-                const double *Ya = &WY[gib][sa][18 + i * 3];
-                const double y0 = Ya[0], y1 = Ya[1], y2 = Ya[2];
-                const double *Wb = &WY[gib][sb][0];
+            for (int q = 0; q < NIT; q++) {
+                if (it_sa[q] < 0) continue;
+                const int ca = scol[gib][it_sa[q]], cbb = scol[gib][it_sb[q]], i = it_i[q];
+                if (ca < 0 || cbb < 0) continue;
 #pragma unroll
                 for (int j = 0; j < 6; j++) {
-                    double v = -(y0 * Wb[j * 3] + y1 * Wb[j * 3 + 1] + y2 * Wb[j * 3 + 2]);
-                    if (ca > cb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cb + j], v);
-                    else atomicAdd(&Sb[(size_t)(cb + j) * ld + ca + i], v);
+                    if (ca > cbb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cbb + j], accO[q][j]);
+                    else atomicAdd(&Sb[(size_t)(cbb + j) * ld + ca + i], accO[q][j]);
                 }
             }
         }
         __syncwarp();
+        SCH_TICK(6);
     }
+#ifdef SDV_SCHUR_PROF
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int q = 0; q < 8; q++) prof[64 + q] = (double)tp[q];
+#endif
     for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if (lane == 0 && gmax > 0.0) atomic_max_nonneg(reinterpret_cast<double *>(&acc->grad_max_bits), gmax);
 }

@@ -101,7 +101,7 @@ struct sdv_handle {
            *d_scale_l = nullptr, *d_red = nullptr;
     size_t sb_elems = 0;
     bool resident = false;
-    int lin_grid = 0, lin_smem = 0, sch_grid = 0, fac_grid = 0;
+    int lin_grid = 0, lin_smem = 0, sch_grid = 0, sch_grid_chunks = 0, fac_grid = 0;
     lin_visual_fn_t lin_fn = nullptr;
     int group = 32; // lanes per landmark in k_schur / k_backsub (8, 16 or 32 by the largest slot count)
     int chol_cluster = 0, chol_rows = 0, chol_smem = 0, chol_variant = 4, chol_rows_roles = 0, chol_smem_roles = 0, chol_smem_chain = 0; // 0: k_chol_cluster, 1: k_chol_ws + shuffle Cholesky, 2: k_chol_ws + hybrid, 3: k_chol_roles, 4: k_chol_chain (default; needs the 16-CTA cluster, else 2), 5: k_chol_chain with FMA updates // cluster size (0 = per-panel launches), own-row capacity, dynamic smem
@@ -122,8 +122,11 @@ struct sdv_handle {
     // comm
     void *comm = nullptr;
     int rank = 0, world = 1;
-    std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs; // reused between uploads
+    std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs, tmp_chunk_ptr; // reused between uploads
     std::vector<uint32_t> tmp_tile_nz;
+    bool attrs_done = false;
+    const void *lin_fn_cached = nullptr;
+    int lin_smem_cached = -1, lin_per_sm = 1;
     int band_bw = -1, band_smem = 0; // 16-column block half-bandwidth of the reduced system (-1 = not computed), k_chol_band shared memory
     int chol_tiles_nz = 0, chol_tiles_all = 0; // structurally non-zero tiles of L / all lower tiles
     LMState h_state;
@@ -571,6 +574,35 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     int max_slots = 1;
     for (int l = 0; l < L; l++) max_slots = std::max(max_slots, slot_ptr[l + 1] - slot_ptr[l]);
 
+    // ---- Schur chunks: runs of consecutive landmarks of this rank that are seen from the same keyframes (in the same slot
+    //      order) and are eliminated; k_schur accumulates a chunk in registers and issues its atomics once.  A landmark seen
+    //      from more keyframes than the register budget of a lane group allows, or kept in the reduced system, stays alone.
+    const int sch_group = max_slots <= 8 ? 8 : (max_slots <= 16 ? 16 : 32);
+    std::vector<int> &chunk_ptr = h->tmp_chunk_ptr;
+    chunk_ptr.clear();
+    {
+        // chunk length: a lane group walks its chunk sequentially (~4.5 us per landmark on B200, latency-bound), so chunks only
+        // pay once there are enough of them to keep every SM sub-partition busy (measured at C3: 73 / 47 / 35 / 37 / 48 us for
+        // chunks of 1 / 2 / 3 / 4 / 8 landmarks; small windows are fastest with one landmark per group)
+        int CH = std::max(1, std::min(8, (l1 - l0) / std::max(1, h->num_sms * 20)));
+        if (const char *e = getenv("SDV_SCHUR_CH")) CH = std::max(1, atoi(e));
+        int l = l0;
+        while (l < l1) {
+            chunk_ptr.push_back(l);
+            int len = 1;
+            const int m = slot_ptr[l + 1] - slot_ptr[l];
+            if (lmk_col[l] < 0 && m * (m - 1) / 2 * 6 <= SCH_NIT * sch_group && !getenv("SDV_SCHUR_NOCHUNK")) {
+                const int *f0 = &slot_frame[slot_ptr[l]];
+                while (l + len < l1 && len < CH && lmk_col[l + len] < 0 && slot_ptr[l + len + 1] - slot_ptr[l + len] == m &&
+                       std::equal(f0, f0 + m, &slot_frame[slot_ptr[l + len]]))
+                    len++;
+            }
+            l += len;
+        }
+        chunk_ptr.push_back(l1);
+    }
+    const int nchunks = (int)chunk_ptr.size() - 1;
+
     // ---- dense prior column maps
     std::vector<int> mp_src, mp_dst;
     if (dp) {
@@ -733,6 +765,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     size_t o_Ts = A.add(D * 12 * C), o_K = A.add(D * 4 * C), o_cw = A.add(D * C);
     size_t o_lt = A.add(D * 3 * std::max(L, 1)), o_lc = A.add(4 * std::max(L, 1));
     size_t o_tnz = A.add(4 * tile_nz.size());
+    size_t o_chk = A.add(4 * chunk_ptr.size());
     size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(nslotobs, 1));
     size_t o_ol = A.add(4 * std::max(O, 1)), o_ofc = A.add(4 * std::max(O, 1));
     const int mplanes = kind == SDV_FACTOR_ANGULAR ? 3 : 2;
@@ -797,6 +830,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     }
     std::memcpy(hb + o_pc, pose_col.data(), 4 * F);
     std::memcpy(hb + o_tnz, tile_nz.data(), 4 * tile_nz.size());
+    std::memcpy(hb + o_chk, chunk_ptr.data(), 4 * chunk_ptr.size());
     std::memcpy(hb + o_vc, vb_col.data(), 4 * F);
     std::memcpy(hb + o_Ts, w->T_s_f, D * 12 * C);
     std::memcpy(hb + o_K, w->K, D * 4 * C);
@@ -933,6 +967,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     P.T_s_f = at<double>(db, o_Ts); P.K = at<double>(db, o_K); P.cam_w = at<double>(db, o_cw);
     P.lmk_t = at<double>(db, o_lt); P.lmk_col = at<int>(db, o_lc);
     P.tile_nz = at<uint32_t>(db, o_tnz);
+    P.chunk_ptr = at<int>(db, o_chk);
+    P.nchunks = nchunks;
     P.slot_ptr = at<int>(db, o_sp); P.slot_frame = at<int>(db, o_sf); P.slot_obs_ptr = at<int>(db, o_sop); P.slot_obs = at<int>(db, o_so);
     P.obs_lmk = at<int>(db, o_ol); P.obs_fc = at<int>(db, o_ofc); P.obs_meas = at<double>(db, o_om);
     P.obs_w = w->obs_sigma ? at<double>(db, o_ow) : nullptr;
@@ -986,16 +1022,30 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     P.fct_in_smem = fct_bytes <= 160 * 1024 ? 1 : 0;
     h->lin_smem = P.fct_in_smem ? (int)fct_bytes : 0;
     h->lin_fn = lin_visual_fn(kind, P.fct_in_smem != 0, getenv("SDV_LIN_LATE") == nullptr);
-    CK(cudaFuncSetAttribute(h->lin_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(k_trisolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->lin_fn, LIN_THREADS, h->lin_smem));
-    per_sm = std::max(per_sm, 1);
+    // function attributes and occupancy answers do not change between windows of the same shape: asked once per handle
+    if (!h->attrs_done) {
+        CK(cudaFuncSetAttribute(k_trisolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_schur<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_schur<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_schur<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(k_chol_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        h->attrs_done = true;
+    }
+    if ((const void *)h->lin_fn != h->lin_fn_cached || h->lin_smem != h->lin_smem_cached) {
+        CK(cudaFuncSetAttribute(h->lin_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int q = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, h->lin_fn, LIN_THREADS, h->lin_smem));
+        h->lin_per_sm = std::max(q, 1);
+        h->lin_fn_cached = (const void *)h->lin_fn;
+        h->lin_smem_cached = h->lin_smem;
+    }
+    const int per_sm = h->lin_per_sm;
     h->lin_grid = std::max(1, std::min((Oloc + LIN_THREADS - 1) / LIN_THREADS, h->num_sms * per_sm));
-    h->group = max_slots <= 8 ? 8 : (max_slots <= 16 ? 16 : 32);
+    h->group = sch_group;
     {
         int gpb = SCH_WARPS * (32 / h->group);
-        h->sch_grid = std::max(1, std::min(((l1 - l0) + gpb - 1) / gpb, h->num_sms * 8));
+        h->sch_grid = std::max(1, std::min(((l1 - l0) + gpb - 1) / gpb, h->num_sms * 8));     // k_backsub: one group per landmark
+        h->sch_grid_chunks = std::max(1, std::min((nchunks + gpb - 1) / gpb, h->num_sms * 8)); // k_schur: one group per chunk
     }
     h->fac_grid = std::max(1, (std::max(Pn, 1) + FAC_WARPS - 1) / FAC_WARPS);
     // dense Cholesky: one thread-block cluster when the reduced system is small enough, per-panel launches otherwise
@@ -1009,15 +1059,12 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             const BandPlan pl = band_plan(n_pad, bw);
             const size_t bytes = sizeof(double) * (size_t)pl.o_end;
             if (bytes <= 220 * 1024 && (size_t)pl.nb * (bw + 2) * 256 <= sb_elems) {
-                if (cudaFuncSetAttribute(k_chol_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess) {
-                    h->band_smem = (int)bytes;
-                    P.band_bw = bw;
-                }
-                cudaGetLastError();
+                h->band_smem = (int)bytes;
+                P.band_bw = bw;
             }
         }
     }
-    if (n_pad <= 4096 && !getenv("SDV_NO_CLUSTER")) {
+    if (h->band_smem == 0 && n_pad <= 4096 && !getenv("SDV_NO_CLUSTER")) { // the cluster variants are only set up when the band kernel does not apply
         h->chol_variant = 4;
         if (const char *v = getenv("SDV_CHOL_VARIANT")) h->chol_variant = atoi(v);
         auto prep = [&](const void *fn) {
@@ -1065,7 +1112,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         }
     }
 
-    CK(cudaMemsetAsync(h->d_Lo, 0, sizeof(double) * sb_elems, h->stream)); // tiles outside the structural pattern are never written
+    if (h->band_smem == 0) CK(cudaMemsetAsync(h->d_Lo, 0, sizeof(double) * sb_elems, h->stream)); // cluster variants: tiles outside the structural pattern are never written
     // ---- one-time device setup for this window
     if (Pn > 0) {
         k_imu_inf_sqrt<<<(Pn + 31) / 32, 32, 0, h->stream>>>(P);
@@ -1096,12 +1143,13 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
 
 namespace {
 
+constexpr int SCH_ACC_BYTES = 39 * SCH_WARPS * 32 * (int)sizeof(double);
 void launch_schur(sdv_handle *h) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
-    if (h->group == 8) k_schur<8><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
-    else if (h->group == 16) k_schur<16><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
-    else k_schur<32><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l);
+    if (h->group == 8) k_schur<8><<<h->sch_grid_chunks, SCH_WARPS * 32, SCH_ACC_BYTES, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_prof);
+    else if (h->group == 16) k_schur<16><<<h->sch_grid_chunks, SCH_WARPS * 32, SCH_ACC_BYTES, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_prof);
+    else k_schur<32><<<h->sch_grid_chunks, SCH_WARPS * 32, SCH_ACC_BYTES, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_prof);
     h->launches++;
 }
 void launch_backsub(sdv_handle *h) {
