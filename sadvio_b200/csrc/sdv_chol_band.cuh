@@ -40,7 +40,7 @@ struct BandPlan {
     int nb, bw, R;                 // block rows, half-bandwidth in blocks, window rows kept in shared memory
     int pcs, pan_doubles;          // panel column stride, doubles per panel buffer
     int stages;                    // backward ring depth
-    int o_win, o_pan, o_inv, o_ys, o_g, o_end; // offsets in doubles
+    int o_win, o_pan, o_inv, o_ys, o_g, o_dmp, o_end; // offsets in doubles
 };
 __host__ __device__ inline BandPlan band_plan(int n_pad, int bw) {
     BandPlan p;
@@ -54,7 +54,7 @@ __host__ __device__ inline BandPlan band_plan(int n_pad, int bw) {
     // the backward ring reuses window + panels; give it up to BAND_MAX_STAGES stages while the CTA stays below ~200 KB
     const int stage = (bw + 2) * BN * BN;
     int stages = p.nb < BAND_MAX_STAGES ? p.nb : BAND_MAX_STAGES;
-    while (stages > 2 && (stages * stage + n_pad + 64) * 8 > 200 * 1024) stages--;
+    while (stages > 2 && (stages * stage + 2 * n_pad + 64) * 8 > 200 * 1024) stages--;
     p.stages = stages;
     if (fwd < stages * stage) fwd = stages * stage;
     p.o_win = 0;
@@ -62,7 +62,8 @@ __host__ __device__ inline BandPlan band_plan(int n_pad, int bw) {
     p.o_inv = fwd;
     p.o_ys = p.o_inv + 2 * BN;
     p.o_g = p.o_ys + 2 * BN;
-    p.o_end = p.o_g + n_pad;
+    p.o_dmp = p.o_g + n_pad; // LM damping of the columns (negative = padding column: unit diagonal)
+    p.o_end = p.o_dmp + n_pad;
     return p;
 }
 
@@ -231,11 +232,70 @@ SDV_DEV void cp_async16(void *dst, const void *src) {
 }
 SDV_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// System preparation for k_chol_band (same arithmetic as k_sysprep): gradient-tolerance test, Jacobi column scales at
+// iteration 0, LM damping -> dmp (negative = padding column), right-hand side -> gs.  Returns true (uniformly) when the
+// gradient tolerance terminates the solve.  Not inlined: its square roots and divisions would otherwise raise the register
+// pressure of the factorisation loops (the kernel is capped at 128 registers).
+__device__ __noinline__ bool band_sysprep(int n, int n_pad, int ld, LMState *st, Accum *acc, int jacobi_scaling, double gradient_tolerance,
+                                          double min_diag, double max_diag, const double *A, double *scale_p, double *damp_p, double *graw_p,
+                                          double *gs, double *dmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *g = A + (size_t)n_pad * ld, *cdiag = g + ld, *graw = cdiag + ld;
+    const bool first = st->scaling_done == 0, check = st->need_grad_check != 0;
+    const double radius = st->radius;
+    if (check) { // gradient tolerance (Ceres: iteration 0 and after every successful step)
+        double m = 0.0;
+        for (int i = threadIdx.x; i < n; i += BCT) m = fmax(m, fabs(graw[i]));
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+        if (lane == 0) dmp[warp] = m;
+    }
+    __syncthreads(); // also: every thread has read the state words before thread 0 changes them
+    if (check) {
+        double mm = __longlong_as_double((long long)acc->grad_max_bits);
+        for (int i = 0; i < BNW; i++) mm = fmax(mm, dmp[i]);
+        if (mm <= gradient_tolerance) { // uniform: every thread evaluates the same values
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                st->status = 1 + 2; // SDV_TERM_GRADIENT_TOLERANCE
+                st->iter -= 1;      // the step Ceres never starts was already counted
+                st->need_grad_check = 0;
+            }
+            return true;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pad; i += BCT) {
+        if (i < n) {
+            const double c = cdiag[i];
+            const double sc = first ? (jacobi_scaling ? 1.0 / (1.0 + sqrt(c)) : 1.0) : scale_p[i];
+            if (first) scale_p[i] = sc;
+            const double d = fmin(fmax(sc * sc * c, min_diag), max_diag) / (radius * sc * sc); // lm_damping()
+            dmp[i] = d;
+            damp_p[i] = d;
+            graw_p[i] = graw[i];
+            gs[i] = g[i];
+        } else {
+            dmp[i] = -1.0; // padding: identity block, zero right-hand side
+            damp_p[i] = 0.0;
+            graw_p[i] = 0.0;
+            gs[i] = 0.0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        st->need_grad_check = 0;
+        st->scaling_done = 1;
+        acc->grad_max_bits = 0ull;
+    }
+    return false;
+}
+
 // A : (n_pad + 32) x ld reduced system (lower triangle, right-hand side in row n_pad), read only.
 // Lb: band storage of the factor, block column k at Lb + k (bw + 2) 256: [L_kk | L_(k+1,k) .. L_(k+bw,k) | L_kk^-1], each
 //     block 16 x 16 row-major.  dxp receives -x (S delta = -g).
-__global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, const double *A, double *Lb,
-                                                      const double *damp_p, const double *graw_p, double *dxp, double *prof) {
+// The preparation of the reduced system (k_sysprep for the other variants: gradient-tolerance test, Jacobi column scales at
+// iteration 0, LM damping of the pose/velocity/bias columns, identity padding) is done here, on the way into shared memory.
+__global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt, const double *A,
+                                                      double *Lb, double *scale_p, double *damp_p, double *graw_p, double *dxp, double *prof) {
     if (st->status != 0) return;
     extern __shared__ __align__(16) double bsm[];
     __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8];
@@ -243,7 +303,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
     const BandPlan pl = band_plan(P.n_pad, P.band_bw);
     const int nb = pl.nb, bw = pl.bw, R = pl.R, ld = P.ld, pcs = pl.pcs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *win = bsm + pl.o_win, *pan0 = bsm + pl.o_pan, *invs = bsm + pl.o_inv, *ysv = bsm + pl.o_ys, *gs = bsm + pl.o_g;
+    double *win = bsm + pl.o_win, *pan0 = bsm + pl.o_pan, *invs = bsm + pl.o_inv, *gs = bsm + pl.o_g, *dmp = bsm + pl.o_dmp;
     const int bwp = bw + 1;
     // window block (i, j) lives in slot (i mod R, j mod (bw+1)); kr = k mod R and kc = k mod (bw+1) are carried along so that
     // no integer division is executed inside the factorisation
@@ -277,6 +337,23 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             cp_async16(win + (rs * bwp + cs) * WBLK + r * WSTR + 2 * q, A + (size_t)(i * BN + r) * ld + (j0 + jj) * BN + 2 * q);
         }
     };
+    // after the copies of block row i have landed: add the damping to the diagonal (unit diagonal for padding columns); every
+    // thread patches the 16-byte chunks it copied itself, so no extra synchronisation is needed
+    auto fix_row = [&](int i, int rs, int c0, int t0, int nt, int tid = -1) {
+        if (tid < 0) tid = (int)threadIdx.x;
+        const int j0 = i - bw > 0 ? i - bw : 0;
+        int cs = c0 + (i - j0);
+        cs -= cs >= bwp ? bwp : 0;
+        double *D = win + (rs * bwp + cs) * WBLK; // diagonal block (i, i): its chunks are e = (i - j0) * 128 + r * 8 + q
+        for (int e = tid - t0; e < (i - j0 + 1) * 128; e += nt) {
+            if ((e >> 7) != i - j0) continue;
+            const int r = (e >> 3) & 15, q = e & 7;
+            if (q != (r >> 1)) continue;
+            const double d = dmp[i * BN + r];
+            double *x = D + r * WSTR + r;
+            *x = d < 0.0 ? 1.0 : *x + d;
+        }
+    };
     // ---- roles (warp-specialised dataflow; every warp runs ONE small loop, the hand-offs are mbarriers in shared memory).
     // Warp w runs on SM sub-partition w % 4, each with its own FP64 pipe: the FP64-heavy roles are spread over the four.
     //   warp 0                    chain        factor D_k, solve P_(k+1,k)                      -> bar_panel
@@ -288,20 +365,25 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
     //   warps 4, 8, 12            idle (they share the chain's sub-partition)
     // A CTA-wide barrier per phase was tried first: a warp that sleeps at __syncthreads() while the chain warp runs took
     // 1.5-2 k cycles to get going again (per-warp clock64 traces), 3 times per step.
-    int role = 6, ridx = 0, ncopy = 1, n_upd = 0; // 0 chain, 1 row solve (ridx = d), 2 rhs, 3 inverse, 4 update (ridx = u), 5 copy, 6 idle
+    constexpr int N_COPY = 4;
+    int role = 6, ridx = 0, n_upd = 0; // 0 chain, 1 row solve (ridx = d), 2 rhs, 3 inverse, 4 update + copy duty (ridx = u), 6 idle
     {
         // Warp w runs on SM sub-partition w % 4, each with its own (narrow: 16 lanes) FP64 pipe and instruction cache.
         //  * sub-partition 0 belongs to the chain warp alone (warps 4, 8, 12 idle): with three other loops next to it the
         //    ~10 KB of unrolled pivot code ran 45 % slower than alone (tools/micro/roles.cu vs the in-kernel trace);
         //  * the row solves d = 2, 3 — the updates (2,1), (3,1) that gate the next steps wait for them — share their
         //    sub-partitions only with update warps, which are idle while the solves run;
-        //  * everything with slack (d = 4 solve, right-hand side, inverse, copy) sits on sub-partition 3.
+        //  * everything with slack (d = 4 solve, right-hand side, inverse) sits on sub-partition 3; the copy duty (panel ->
+        //    global, prefetch of the next block row) is shared by the update warps, which wait most of the time.
         const int solve_warp[6] = {1, 2, 3, 13, 14, 10}; // d = 2 .. 7
         const int upd_pool[6] = {5, 9, 6, 10, 13, 14};   // minus the ones used as row-solve warps (bw > 4)
         if (warp == 0) role = 0;
         else if (warp == 7) role = 2;
         else if (warp == 11) role = 3;
-        else if (warp == 15) role = 5;
+        else if (warp == 15 || (warp & 3) == 0) { // 15, 4, 8, 12: light (copies), so the chain's sub-partition can host three of them
+            role = 5;
+            ridx = warp == 15 ? 0 : warp >> 2;
+        }
         n_upd = bw <= 4 ? 6 : 10 - bw;
 #pragma unroll
         for (int q = 0; q < 6; q++) {
@@ -322,7 +404,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             mbar_init(&bar_panel[q], 1);
             mbar_init(&bar_step[q], n_upd);
             mbar_init(&bar_rhs[q], 1);
-            mbar_init(&bar_copy[q], ncopy + 1);
+            mbar_init(&bar_copy[q], N_COPY + 1); // copy warps + the inverse warp
             for (int d = 0; d < 8; d++) {
                 mbar_init(&bar_p[q][d], 1);
                 mbar_init(&bar_c1[q][d], 1);
@@ -330,14 +412,39 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         }
     }
     for (int i = 0; i < nb && i < R; i++) load_row(i, i, i > bw ? (i - bw) % bwp : 0, 0, BCT); // rows 0 .. R-1 (R = bw + 3, or the whole matrix)
-    for (int e = threadIdx.x; e < P.n_pad; e += BCT) gs[e] = A[(size_t)P.n_pad * ld + e];
     for (int e = threadIdx.x; e < 2 * pl.pan_doubles; e += BCT) pan0[e] = 0.0;
+    if (band_sysprep(P.n, P.n_pad, ld, st, acc, opt.jacobi_scaling, opt.gradient_tolerance, opt.min_diag, opt.max_diag, A, scale_p, damp_p, graw_p, gs, dmp)) { // gradient tolerance reached: no step
+        cp_async_wait_all();
+        return;
+    }
     cp_async_wait_all();
+    __syncthreads();
+    for (int i = 0; i < nb && i < R; i++) fix_row(i, i, i > bw ? (i - bw) % bwp : 0, 0, BCT);
     __syncthreads();
     auto ph = [](int k) { return (unsigned)((k >> 1) & 1); }; // phase parity of the barriers of step k (each is reused every 2 steps)
     auto next_k = [&] {
         if (++kr == R) kr = 0;
         if (++kc == bwp) kc = 0;
+    };
+
+    // copy duty of step k, shared by the copy warps: blocks 0 and 1
+    // of panel k -> global band storage (transposing), then the prefetch of block row k+bw+2 into the window slot that row
+    // k-1 has left (last read by the chain of step k-1), with the damping added on the way in
+    auto copy_share = [&](int k, int ct, int nct) {
+        const double *pan = pan0 + (k & 1) * pl.pan_doubles;
+        double *dst = Lb + (size_t)k * (bw + 2) * 256;
+        const int ne = (k + 1 < nb ? 2 : 1) * 256;
+#pragma unroll 1
+        for (int e = ct; e < ne; e += nct) {
+            const int r = e >> 4, c = e & 15; // r = 16 d + row: row of the stacked panel
+            dst[e] = pan[c * pcs + r];
+        }
+        if (k >= 1 && k + bw + 2 < nb) {
+            const int rs = kr == 0 ? R - 1 : kr - 1, c0 = kc + 2 >= bwp ? kc + 2 - bwp : kc + 2;
+            load_row(k + bw + 2, rs, c0, 0, nct, ct);
+            cp_async_wait_all();
+            fix_row(k + bw + 2, rs, c0, 0, nct, ct);
+        }
     };
 
     bool ok = true;
@@ -479,7 +586,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
 #pragma unroll
             for (int pass = 0; pass < 2; pass++)
 #pragma unroll
-                for (int q = 0; q < MAXV; q++) {
+                for (int q = 0; q < MAXV; q++) { // my virtual workers are sorted by offset, i.e. first-column tasks come in di order
                     if (q >= nv) continue;
                     const int dj = vdj[q], di = dj + vo[q];
                     if ((dj == 1) != (pass == 0) || di > nd) continue;
@@ -501,25 +608,12 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             next_k();
         }
     } else if (role == 5) {
-        // ------------------------------------------------------------------ copy warps: blocks 0 and 1 of panel k -> global band
-        // storage (transposing), then the prefetch of block row k+bw+2 into the window slot that row k-1 has left
-        const int ct = ridx * 32 + lane, nct = ncopy * 32;
+        // ------------------------------------------------------------------ copy warps
         for (int k = 0; k < nb; k++) {
             const int par = k & 1;
-            const double *pan = pan0 + par * pl.pan_doubles;
             mbar_wait_cta(&bar_panel[par], ph(k));
             BAND_TICK(1);
-            double *dst = Lb + (size_t)k * (bw + 2) * 256;
-            const int ne = (k + 1 < nb ? 2 : 1) * 256;
-#pragma unroll 1
-            for (int e = ct; e < ne; e += nct) {
-                const int r = e >> 4, c = e & 15; // r = 16 d + row: row of the stacked panel
-                dst[e] = pan[c * pcs + r];
-            }
-            if (k >= 1 && k + bw + 2 < nb) { // row k-1 was last read by the chain of step k-1
-                load_row(k + bw + 2, kr == 0 ? R - 1 : kr - 1, kc + 2 >= bwp ? kc + 2 - bwp : kc + 2, 0, nct, ct);
-                cp_async_wait_all();
-            }
+            copy_share(k, ridx * 32 + lane, N_COPY * 32);
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&bar_copy[par]);
             BAND_TICK(2);

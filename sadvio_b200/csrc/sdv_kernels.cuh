@@ -1714,11 +1714,20 @@ __global__ void __launch_bounds__(SCH_WARPS * 32) k_backsub(DevProblem P, LinBuf
     dd = warp_sum(dd);
     sn = warp_sum(sn);
     cn = warp_sum(cn);
-    if (lane == 0 && (gd != 0.0 || sn != 0.0 || cn != 0.0)) {
-        atomicAdd(&acc->model_gd, gd);
-        atomicAdd(&acc->model_dd, dd);
-        atomicAdd(&acc->step_norm2, sn);
-        atomicAdd(&acc->cand_norm2, cn);
+    // one set of atomics per CTA: the four scalars are single addresses, thousands of same-address atomics serialise in L2
+    __shared__ double red[SCH_WARPS][4];
+    if (lane == 0) {
+        red[wib][0] = gd;
+        red[wib][1] = dd;
+        red[wib][2] = sn;
+        red[wib][3] = cn;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < SCH_WARPS; w++) v += red[w][threadIdx.x];
+        if (v != 0.0) atomicAdd(threadIdx.x == 0 ? &acc->model_gd : (threadIdx.x == 1 ? &acc->model_dd : (threadIdx.x == 2 ? &acc->step_norm2 : &acc->cand_norm2)), v);
     }
 }
 
@@ -1753,6 +1762,7 @@ __global__ void k_ctrl_init(LMState *st, Accum *acc, SolverOpts opt) {
     acc->grad_max_bits = 0ull;
     acc->schur_fail = acc->chol_fail = 0;
     if (opt.max_num_iterations <= 0) st->status = 1 + 0;
+    else st->iter = 1; // Ceres bumps its iteration counter before computing the step (was a kernel of its own)
 }
 
 // start of an iteration: Ceres bumps its iteration counter before computing the step
@@ -1845,6 +1855,10 @@ __global__ void k_ctrl(LMState *st, Accum *acc, SolverOpts opt, unsigned long lo
     acc->cost[1 - st->cur] = 0.0;
     acc->model_gd = acc->model_dd = acc->step_norm2 = acc->cand_norm2 = 0.0;
     acc->schur_fail = acc->chol_fail = 0;
+    if (st->status == 0) { // start of the next iteration
+        st->iter += 1;
+        st->step_valid = 0;
+    }
     if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, st->status == 0 ? 1u : 0u);
 }
 

@@ -1248,7 +1248,7 @@ int launch_factor_solve(sdv_handle *h) {
     cudaStream_t s = h->stream;
     const int T = P.n_pad / CH_T;
     if (h->band_smem > 0) {
-        k_chol_band<<<1, BCT, h->band_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_Sb, h->d_Lo, h->d_damp_p, h->d_graw_p, h->d_dxp, h->d_prof);
+        k_chol_band<<<1, BCT, h->band_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_Lo, h->d_scale_p, h->d_damp_p, h->d_graw_p, h->d_dxp, h->d_prof);
         h->launches++;
         return SDV_OK;
     }
@@ -1302,9 +1302,7 @@ int launch_iteration(sdv_handle *h) {
     const DevProblem &P = h->P;
     const int T = P.n_pad / CH_T;
     cudaStream_t s = h->stream;
-    k_iter_begin<<<1, 1, 0, s>>>(h->d_st);
     if (cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s) != cudaSuccess) return fail(h, SDV_ERR_CUDA, "memset S");
-    h->launches += 2;
     {
         // the non-visual factors accumulate into S with atomics as well: run them beside the landmark Schur kernel
         const bool fa = P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0);
@@ -1332,8 +1330,10 @@ int launch_iteration(sdv_handle *h) {
         k_gradmax_to_flag<<<1, 1, 0, s>>>(h->d_acc, h->opt.gradient_tolerance, h->d_red, 1);
         h->launches += 2;
     }
-    k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
-    h->launches++;
+    if (h->band_smem == 0) { // k_chol_band prepares the system itself
+        k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
+        h->launches++;
+    }
     {
         int rcf = launch_factor_solve(h);
         if (rcf != SDV_OK) return rcf;
@@ -1712,7 +1712,7 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
             launch_schur(h);
             if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0))
                 k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
-            k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
+            if (h->band_smem == 0) k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
             CK(cudaEventRecord(h->ev[2], s));
             {
                 int rcf = launch_factor_solve(h);
