@@ -262,25 +262,31 @@ def main():
     peak, peak_src = measured_peaks()
     its_per_step = its / args.steps
     kern = []
-    if world == 1:
+    if True:  # per-kernel timings of rank 0 (its landmark shard at N > 1; no collective inside sdv_time_kernel)
         n, npad = solver.debug_dims()
-        O = win.n_obs
+        O = win.n_obs // world  # rank 0's landmark shard (observation-balanced) at N > 1
+        # traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture of this workload
+        # (profiles/r01_ncu_traffic_c3.txt; null for other configs)
+        traffic = {0: 3.09e6, 1: 13.9e6, 2: 0.64e6} if args.config == "C3" else {}
         specs = [
-            (0, "k_lin_visual (residual+Jacobian, J materialised)", BYTES_PER_OBS * O, "hbm", its_per_step + 1),
-            (1, "k_schur (per-landmark Schur complement + assembly)", 160 * O + 8 * n * n // 2, "hbm", its_per_step),
-            (2, "k_chol_chain (structure-aware FP64 Cholesky + triangular solves of the reduced system, one 16-CTA cluster, DMMA updates)", 8 * n * n, "hbm", its_per_step),
+            (0, "k_lin_visual (residual+Jacobian of every visual factor, J materialised as SoA planes)", BYTES_PER_OBS * O, "hbm", its_per_step + 1),
+            (1, "k_schur (per-landmark 3x3 Schur complement + assembly of the reduced system, chunked atomics)", 160 * O + 8 * n * n // 2, "hbm", its_per_step),
+            (2, "k_chol_band (system preparation + banded FP64 Cholesky + triangular solves of the reduced system in one CTA: "
+                "register-resident pivot chain, DMMA trailing updates, TMA-ring backward solve)", 8 * n * n, "hbm", its_per_step),
         ]
         for which, name, nbytes, bound, per_step in specs:
             ms = solver.time_kernel(which, 20)
             kern.append({"name": name, "ms_per_launch": ms, "launches_per_step": per_step, "algorithmic_bytes": int(nbytes),
                          "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
+                         "dram_traffic_bytes": traffic.get(which),
                          "share_of_step": ms * per_step / (1e3 * t_total / args.steps)})
         dom = max(kern, key=lambda k: k["share_of_step"])
         roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_hbm_peak"],
-                    "traffic": None, "kernel": dom["name"], "peak_source": peak_src,
-                    "note": "dominant kernel by share of the step; FP64 latency-bound at this size — see DESIGN.md"}
-    else:
-        roofline = None
+                    "traffic": dom["dram_traffic_bytes"], "kernel": dom["name"], "peak_source": peak_src,
+                    "note": "dominant kernel by share of the step. It is a dependency chain of n = 735 pivots (FP64 latency-bound, "
+                            "one SM by design): the HBM fraction is reported because the contract asks for it, the meaningful "
+                            "figure is ms_per_launch (DESIGN.md section 3). The HBM-bound kernel of the path is k_lin_visual: "
+                            "see jacobian_kernel_c5"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -297,6 +303,8 @@ def main():
             nb = BYTES_PER_OBS * win5.n_obs
             jac_c5 = {"workload": "C5: 200 KF x 100000 landmarks x 800000 obs", "ms_per_launch": ms5, "algorithmic_bytes": int(nb),
                       "achieved_gbs": nb / (ms5 * 1e-3) / 1e9, "peak_gbs": peak, "frac_of_hbm_peak": nb / (ms5 * 1e-3) / 1e9 / peak,
+                      "dram_traffic_bytes": 97.3e6, "traffic_source": "profiles/r01_ncu_traffic_c5.txt (30.5 MB read + 66.8 MB written; "
+                      "part of the 128 MB of Jacobian planes is still in the 126 MB L2 when the kernel ends)",
                       "peak_source": peak_src}
         except Exception as e:  # noqa: BLE001
             jac_c5 = {"error": str(e)}

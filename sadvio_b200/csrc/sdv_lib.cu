@@ -123,6 +123,7 @@ struct sdv_handle {
     void *comm = nullptr;
     int rank = 0, world = 1;
     std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs, tmp_chunk_ptr; // reused between uploads
+    std::vector<char> tmp_same_prev;
     std::vector<uint32_t> tmp_tile_nz;
     bool attrs_done = false;
     const void *lin_fn_cached = nullptr;
@@ -571,6 +572,14 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     }
     const int nslots = ns;
     const int nslotobs = nso;
+    // landmark l is seen from exactly the keyframes of landmark l-1, in the same slot order (the common case: landmarks come
+    // out of the front end grouped by the keyframe that created them): the structure passes below then skip it
+    std::vector<char> &same_prev = h->tmp_same_prev;
+    same_prev.assign((size_t)L + 1, 0);
+    for (int l = 1; l < L; l++) {
+        const int m = slot_ptr[l + 1] - slot_ptr[l];
+        same_prev[l] = m == slot_ptr[l] - slot_ptr[l - 1] && std::equal(&slot_frame[slot_ptr[l]], &slot_frame[slot_ptr[l]] + m, &slot_frame[slot_ptr[l - 1]]);
+    }
     int max_slots = 1;
     for (int l = 0; l < L; l++) max_slots = std::max(max_slots, slot_ptr[l + 1] - slot_ptr[l]);
 
@@ -592,10 +601,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             int len = 1;
             const int m = slot_ptr[l + 1] - slot_ptr[l];
             if (lmk_col[l] < 0 && m * (m - 1) / 2 * 6 <= SCH_NIT * sch_group && !getenv("SDV_SCHUR_NOCHUNK")) {
-                const int *f0 = &slot_frame[slot_ptr[l]];
-                while (l + len < l1 && len < CH && lmk_col[l + len] < 0 && slot_ptr[l + len + 1] - slot_ptr[l + len] == m &&
-                       std::equal(f0, f0 + m, &slot_frame[slot_ptr[l + len]]))
-                    len++;
+                while (l + len < l1 && len < CH && lmk_col[l + len] < 0 && same_prev[l + len]) len++;
             }
             l += len;
         }
@@ -672,6 +678,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         std::vector<TMask> uniq;
         TMask last{{0, 0}};
         for (int l = 0; l < L; l++) {
+            if (same_prev[l] && lmk_col[l] < 0 && lmk_col[l - 1] < 0) continue; // same clique as the previous landmark
             TMask m{{0, 0}};
             for (int q = slot_ptr[l]; q < slot_ptr[l + 1]; q++) {
                 const TMask &pm = pose_mask[slot_frame[q]];

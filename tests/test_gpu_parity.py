@@ -285,3 +285,74 @@ def test_optimizer_interface_writeback(solver):
     assert np.abs(win.imu_dR[p] - s2[28:37]).max() < 1e-12
     assert np.abs(win.imu_dv[p] - s2[37:40]).max() < 1e-12
     assert np.abs(win.imu_dp[p] - s2[40:43]).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the factorisation / assembly variants must agree with each other and with the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _solve_with_env(win, env, cfg=None):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        s = api.Solver(cfg) if cfg is not None else api.Solver()
+        out = s.solve_window(win)   # the environment is read at upload time
+        s.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return out
+
+
+@pytest.mark.parametrize("name", ["small", "C2", "C3"])
+def test_band_cholesky_matches_cluster_cholesky(name):
+    """k_chol_band (single CTA, banded; the default when the band fits) against the 16-CTA cluster factorisation."""
+    win = synth.make_window(name)
+    rc_b, d_b, st_b = _solve_with_env(win, {})
+    rc_c, d_c, st_c = _solve_with_env(win, {"SDV_CHOL_VARIANT": "4"})
+    assert rc_b == rc_c == 0
+    assert st_b["iterations"] == st_c["iterations"] and st_b["termination"] == st_c["termination"]
+    assert st_b["trace_accepted"] == st_c["trace_accepted"]
+    for a, b in ((d_b.dpose, d_c.dpose), (d_b.dv, d_c.dv), (d_b.dba, d_c.dba), (d_b.dbg, d_c.dbg), (d_b.dlmk, d_c.dlmk)):
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max() + 1e-13
+
+
+def test_wide_band_falls_back_to_cluster_cholesky(solver):
+    """Landmarks seen from 10 keyframes: half-bandwidth > 7 blocks of 16, the banded kernel does not apply."""
+    win = synth.make_window("C2", span=10)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert_same_states(win, g[1], o[1])
+
+
+def test_dense_small_window_band_kernel(solver):
+    """A 6-keyframe window whose reduced system is dense inside the band (every landmark seen from 3 of 6 frames)."""
+    win = synth.make_window("tiny")
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_schur_chunks_match_per_landmark_assembly(name):
+    """k_schur accumulating chunks of landmarks in registers against one set of atomics per landmark."""
+    win = synth.make_window(name)
+    rc_a, d_a, st_a = _solve_with_env(win, {"SDV_SCHUR_CH": "4"})
+    rc_b, d_b, st_b = _solve_with_env(win, {"SDV_SCHUR_NOCHUNK": "1"})
+    assert rc_a == rc_b == 0 and st_a["iterations"] == st_b["iterations"]
+    for a, b in ((d_a.dpose, d_b.dpose), (d_a.dv, d_b.dv), (d_a.dlmk, d_b.dlmk)):
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max() + 1e-13
+    rc0, d0, st0 = orc.solve_window(win, mode=0, nthreads=8)
+    assert np.abs(d_a.dpose - d0.dpose).max() <= 1e-6 * np.abs(d0.dpose).max()
+
+
+def test_gradient_tolerance_termination_matches_oracle(solver):
+    """The gradient test lives in the prologue of k_chol_band (and in k_sysprep for the other variants)."""
+    win = synth.make_window("small")
+    cfg = api.default_config()
+    cfg.gradient_tolerance = 1e3   # met at iteration 0 after the first linearisation
+    g, o = solve_both(solver, win, cfg)
+    assert g[2]["termination"] == o[2]["termination"]
+    assert g[2]["iterations"] == o[2]["iterations"]
