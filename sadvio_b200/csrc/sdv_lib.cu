@@ -152,12 +152,13 @@ int fail(sdv_handle *h, int code, const std::string &msg) {
 
 template <class T> T *at(unsigned char *base, size_t off) { return reinterpret_cast<T *>(base + off); }
 
-int ensure(sdv_handle *h, unsigned char **d, size_t *cap, size_t need, bool pinned_host = false) {
+int ensure(sdv_handle *h, unsigned char **d, size_t *cap, size_t need, bool pinned_host = false, bool write_combined = false) {
     if (need <= *cap) return SDV_OK;
     size_t ncap = std::max(need, *cap * 2);
     if (pinned_host) {
         if (*d) cudaFreeHost(*d);
-        CK(cudaMallocHost((void **)d, ncap));
+        // the input arena is only ever written by the CPU (sequentially) and read by the copy engine: write-combined
+        CK(cudaHostAlloc((void **)d, ncap, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
     } else {
         if (*d) cudaFree(*d);
         CK(cudaMalloc((void **)d, ncap));
@@ -452,6 +453,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     if (n == 0) return fail(h, SDV_ERR_UNSUPPORTED, "window has no free frame parameter (pure landmark refinement is landmarkOptimization, not this entry point)");
     const int n_pad = (n + 31) / 32 * 32, ld = n_pad;
 
+    auto t_s1 = std::chrono::steady_clock::now();
     // ---- landmark shard of this rank (contiguous, balanced by observation count)
     int l0 = 0, l1 = L, o0 = 0, o1 = O;
     if (h->world > 1) {
@@ -490,7 +492,9 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     slot_frame.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
     slot_obs_ptr.resize((size_t)O + 2 * (size_t)n_pseudo + 2);
     slot_obs.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
-    int ns = 0, nso = 0;
+    int ns = 0, nso = 0, max_slots = 1, prev_first = 0;
+    std::vector<char> &same_prev = h->tmp_same_prev;
+    same_prev.resize((size_t)L + 1);
     {
         const int32_t *of = w->obs_frame;
         std::vector<int> ef, ep; // (frame, plane index) of the landmark's entries, only used when pseudo-observations exist
@@ -566,23 +570,22 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             }
             if (ns - first_slot > MAX_SLOTS)
                 return fail(h, SDV_ERR_UNSUPPORTED, "a landmark is observed from more than 32 keyframes (kernel limit of this build)");
+            // same keyframes, same slot order as the previous landmark? (the structure passes below skip such landmarks)
+            {
+                const int m = ns - first_slot;
+                max_slots = std::max(max_slots, m);
+                bool same = l > 0 && m == first_slot - prev_first;
+                for (int q = 0; same && q < m; q++) same = slot_frame[first_slot + q] == slot_frame[prev_first + q];
+                same_prev[l] = same;
+                prev_first = first_slot;
+            }
         }
         slot_ptr[L] = ns;
         slot_obs_ptr[ns] = nso;
     }
     const int nslots = ns;
     const int nslotobs = nso;
-    // landmark l is seen from exactly the keyframes of landmark l-1, in the same slot order (the common case: landmarks come
-    // out of the front end grouped by the keyframe that created them): the structure passes below then skip it
-    std::vector<char> &same_prev = h->tmp_same_prev;
-    same_prev.assign((size_t)L + 1, 0);
-    for (int l = 1; l < L; l++) {
-        const int m = slot_ptr[l + 1] - slot_ptr[l];
-        same_prev[l] = m == slot_ptr[l] - slot_ptr[l - 1] && std::equal(&slot_frame[slot_ptr[l]], &slot_frame[slot_ptr[l]] + m, &slot_frame[slot_ptr[l - 1]]);
-    }
-    int max_slots = 1;
-    for (int l = 0; l < L; l++) max_slots = std::max(max_slots, slot_ptr[l + 1] - slot_ptr[l]);
-
+    auto t_s2 = std::chrono::steady_clock::now();
     // ---- Schur chunks: runs of consecutive landmarks of this rank that are seen from the same keyframes (in the same slot
     //      order) and are eliminated; k_schur accumulates a chunk in registers and issues its atomics once.  A landmark seen
     //      from more keyframes than the register budget of a lane group allows, or kept in the reduced system, stays alone.
@@ -595,12 +598,14 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         // chunks of 1 / 2 / 3 / 4 / 8 landmarks; small windows are fastest with one landmark per group)
         int CH = std::max(1, std::min(8, (l1 - l0) / std::max(1, h->num_sms * 20)));
         if (const char *e = getenv("SDV_SCHUR_CH")) CH = std::max(1, atoi(e));
+        const bool chunking = CH > 1 && !getenv("SDV_SCHUR_NOCHUNK");
+        chunk_ptr.reserve((size_t)(l1 - l0) + 2);
         int l = l0;
         while (l < l1) {
             chunk_ptr.push_back(l);
             int len = 1;
             const int m = slot_ptr[l + 1] - slot_ptr[l];
-            if (lmk_col[l] < 0 && m * (m - 1) / 2 * 6 <= SCH_NIT * sch_group && !getenv("SDV_SCHUR_NOCHUNK")) {
+            if (lmk_col[l] < 0 && m * (m - 1) / 2 * 6 <= SCH_NIT * sch_group && chunking) {
                 while (l + len < l1 && len < CH && lmk_col[l + len] < 0 && same_prev[l + len]) len++;
             }
             l += len;
@@ -609,6 +614,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     }
     const int nchunks = (int)chunk_ptr.size() - 1;
 
+    auto t_s3 = std::chrono::steady_clock::now();
     // ---- dense prior column maps
     std::vector<int> mp_src, mp_dst;
     if (dp) {
@@ -805,7 +811,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         o_l2s = A.add(D * 9 * std::max(nl2l, 1));
     }
     int rc;
-    if ((rc = ensure(h, &h->h_in, &h->in_cap, A.size, true)) != SDV_OK) return rc;
+    if ((rc = ensure(h, &h->h_in, &h->in_cap, A.size, true, getenv("SDV_ARENA_WC") != nullptr)) != SDV_OK) return rc; // write-combined measured 15 % slower to fill
     {
         size_t dcap = h->in_bytes;
         unsigned char *dptr = h->d_in;
@@ -1140,8 +1146,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         std::fprintf(stderr, "[sdv upload] reduced system n=%d (%d tiles), factor tiles %d of %d structurally non-zero, half-bandwidth %d blocks of 16 (%s)\n", n, n_pad / 32,
                      h->chol_tiles_nz, h->chol_tiles_all, h->band_bw, h->band_smem > 0 ? "k_chol_band" : "cluster Cholesky");
-        std::fprintf(stderr, "[sdv upload] structure %.3f ms, pack %.3f ms, h2d+setup %.3f ms, graph %.3f ms\n", ms(tu0, t_pack0), ms(t_pack0, t_pack1),
-                     ms(t_pack1, t_g0), ms(t_g0, t_g1));
+        std::fprintf(stderr, "[sdv upload] structure %.3f ms (columns %.3f, slots %.3f, chunks %.3f, masks %.3f), pack %.3f ms, h2d+setup %.3f ms, graph %.3f ms\n",
+                     ms(tu0, t_pack0), ms(tu0, t_s1), ms(t_s1, t_s2), ms(t_s2, t_s3), ms(t_s3, t_pack0), ms(t_pack0, t_pack1), ms(t_pack1, t_g0), ms(t_g0, t_g1));
     }
     return SDV_OK;
 }
