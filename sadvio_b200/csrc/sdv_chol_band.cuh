@@ -32,6 +32,14 @@ constexpr int BCT = 512;        // threads of the CTA
 constexpr int BNW = BCT / 32;
 constexpr int BAND_MAX_BW = 7;  // task tables / shared memory are sized for this
 constexpr int BAND_MAX_STAGES = 16; // backward-solve ring (TMA bulk copies in flight)
+// Streaming of the two updates the chain waits for, (1,1) and (2,1), behind the chain (roles 7 and 1).  Correct (parity tests
+// pass with it) but NOT faster yet at C3: 150 us against 132 us — their own inputs, tasks (2,2), (3,1), (3,2) of the previous
+// step, still come from the tensor-core update warps ~1.5 k cycles after the chain has moved on, so the streaming warps start
+// late and the chain ends up waiting for them.  Pays only once block row k+3 streams as well; kept behind this switch.
+#ifndef SDV_BAND_STREAM_UPDATES
+#define SDV_BAND_STREAM_UPDATES 0
+#endif
+constexpr bool BAND_STREAM_UPDATES = SDV_BAND_STREAM_UPDATES != 0;
 
 // shared-memory plan, identical on host and device.  The panel of a step (L_kk and P_(k+1,k) .. P_(k+bw,k), stacked) is
 // stored TRANSPOSED: column c of the stacked panel is contiguous, pan[c * pcs + 16 d + row]; pcs = 16 (bw + 1) + 4 makes the
@@ -110,7 +118,7 @@ SDV_DEV double shfl_f64_volatile(double x, int src) {
 }
 
 template <int C>
-SDV_DEV void band_chain_pivot(double (&a)[16], int lane, uint32_t pan_s, uint32_t iv_s, int pcs, double &d, double &inv, bool &ok) {
+SDV_DEV void band_chain_pivot(double (&a)[16], int lane, uint32_t pan_s, uint32_t iv_s, uint64_t *colbar, int pcs, double &d, double &inv, bool &ok) {
     const double l = a[0] * inv;
     const double lm = lane < C ? 0.0 : l; // rows above the pivot (upper triangle of the block)
     st_shared_f64(pan_s + (uint32_t)(C * pcs + lane) * 8u, lm);
@@ -137,6 +145,9 @@ SDV_DEV void band_chain_pivot(double (&a)[16], int lane, uint32_t pan_s, uint32_
             if (j + 1 < 16) v[j + 1] = w.y;
         }
     }
+    // columns C-3 .. C of [L_kk ; P_(k+1,k)] and their 1/diag are visible: the row solves stream behind, four columns at a
+    // time (an arrive per pivot cost the chain 29 cycles per pivot), issued after this pivot's own loads
+    if ((C & 3) == 3 && lane == 0) mbar_arrive_cta(colbar + (C >> 2));
     if (C < 15) ok = ok && (dn > 0.0) && (dn < 1e300);
     const double invn = band_rsqrt(dn);
 #pragma unroll
@@ -145,36 +156,44 @@ SDV_DEV void band_chain_pivot(double (&a)[16], int lane, uint32_t pan_s, uint32_
     inv = invn;
 }
 
-SDV_DEV void band_chain_step(double (&a)[16], int lane, double *pan, int pcs, double *iv, bool &ok) {
+SDV_DEV void band_chain_step(double (&a)[16], int lane, double *pan, int pcs, double *iv, uint64_t *colbar, bool &ok) {
     const uint32_t pan_s = smem_u32(pan), iv_s = smem_u32(iv);
     double d = __shfl_sync(FULL, a[0], 0);
     ok = ok && (d > 0.0) && (d < 1e300);
     double inv = band_rsqrt(d);
-    band_chain_pivot<0>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<1>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<2>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<3>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<4>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<5>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<6>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<7>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<8>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<9>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<10>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<11>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<12>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<13>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<14>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
-    band_chain_pivot<15>(a, lane, pan_s, iv_s, pcs, d, inv, ok);
+    band_chain_pivot<0>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<1>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<2>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<3>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<4>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<5>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<6>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<7>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<8>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<9>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<10>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<11>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<12>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<13>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<14>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
+    band_chain_pivot<15>(a, lane, pan_s, iv_s, colbar, pcs, d, inv, ok);
 }
 
 // X <- X L_kk^-T for one row per lane (t = the row), L_kk read from the transposed panel (column c at pan[c * pcs ..]);
 // element c of the result goes to dst[c * dstride].  Fully unrolled (the registers rotate, so every index is static) and
 // triangular: measured 98 cycles per pivot as a 2-pivot loop (nothing overlaps across the loop edge), see tools/micro.
-SDV_DEV void band_trsm16(double (&t)[16], const double *pan, int pcs, const double *iv, double *dst, int dstride, double *grow = nullptr) {
+// colbar != nullptr: STREAMING — column c is consumed as soon as the chain warp has published it (mbarrier per column), so
+// the solve ends a few dozen cycles after the factorisation of the diagonal block instead of ~1 k cycles later.
+// UPD (block row k+2 only): the update W_(k+2,k+1) -= P_(k+2,k) P_(k+1,k)^T is applied on the fly as rank-1 updates with the
+// columns of P_(k+1,k) the chain publishes (w = 8 entries of this lane's row, columns 8 h .. 8 h + 7; the two half-warps
+// duplicate the solve and split the update), so the block the chain needs next is final right behind the factorisation.
+template <bool UPD>
+SDV_DEV void band_trsm16(double (&t)[16], double (&w)[8], int h, const double *pan, int pcs, const double *iv, double *dst, int dstride,
+                         double *grow = nullptr, uint64_t *colbar = nullptr, unsigned parity = 0) {
     double xs[16]; // results are stored after the loop: a store into the panel in between would fence the loads behind it
 #pragma unroll
     for (int c = 0; c < 16; c++) {
+        if (colbar && (c & 3) == 0) mbar_wait_cta(colbar + (c >> 2), parity); // columns c .. c+3
         const double x = t[0] * iv[c];
         xs[c] = x;
         const double *v = pan + c * pcs + c;
@@ -182,14 +201,24 @@ SDV_DEV void band_trsm16(double (&t)[16], const double *pan, int pcs, const doub
         if (j0 == 2 && 1 < jn) t[0] = fma(-x, v[1], t[1]);
 #pragma unroll
         for (int j = j0; j + 1 < jn; j += 2) {
-            const double2 w = *reinterpret_cast<const double2 *>(v + j);
-            t[j - 1] = fma(-x, w.x, t[j]);
-            t[j] = fma(-x, w.y, t[j + 1]);
+            const double2 q = *reinterpret_cast<const double2 *>(v + j);
+            t[j - 1] = fma(-x, q.x, t[j]);
+            t[j] = fma(-x, q.y, t[j + 1]);
         }
         if (jn > j0 && ((jn - j0) & 1)) t[jn - 2] = fma(-x, v[jn - 1], t[jn - 1]);
-    }
+        if (UPD) {
+            const double *p1 = pan + c * pcs + 16 + 8 * h; // P_(k+1,k)[8h .. 8h+7][c]
 #pragma unroll
-    for (int c = 0; c < 16; c++) dst[c * dstride] = xs[c];
+            for (int j = 0; j < 8; j += 2) {
+                const double2 q = *reinterpret_cast<const double2 *>(p1 + j);
+                w[j] = fma(-x, q.x, w[j]);
+                w[j + 1] = fma(-x, q.y, w[j + 1]);
+            }
+        }
+    }
+    if (dst)
+#pragma unroll
+        for (int c = 0; c < 16; c++) dst[c * dstride] = xs[c];
     if (grow) // the same row, row-major, into the global band storage of the factor
 #pragma unroll
         for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(grow + c) = make_double2(xs[c], xs[c + 1]);
@@ -298,7 +327,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                                                       double *Lb, double *scale_p, double *damp_p, double *graw_p, double *dxp, double *prof) {
     if (st->status != 0) return;
     extern __shared__ __align__(16) double bsm[];
-    __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8];
+    __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8], bar_c2[2][8], colbar[2][16];
     __shared__ int s_fail;
     const BandPlan pl = band_plan(P.n_pad, P.band_bw);
     const int nb = pl.nb, bw = pl.bw, R = pl.R, ld = P.ld, pcs = pl.pcs;
@@ -365,8 +394,8 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
     //   warps 4, 8, 12            idle (they share the chain's sub-partition)
     // A CTA-wide barrier per phase was tried first: a warp that sleeps at __syncthreads() while the chain warp runs took
     // 1.5-2 k cycles to get going again (per-warp clock64 traces), 3 times per step.
-    constexpr int N_COPY = 4;
-    int role = 6, ridx = 0, n_upd = 0; // 0 chain, 1 row solve (ridx = d), 2 rhs, 3 inverse, 4 update + copy duty (ridx = u), 6 idle
+    constexpr int N_COPY = BAND_STREAM_UPDATES ? 3 : 4;
+    int role = 6, ridx = 0, n_upd = 0; // 0 chain, 1 row solve (ridx = d), 2 rhs, 3 inverse, 4 update (ridx = u), 5 copy, 6 idle, 7 diagonal update
     {
         // Warp w runs on SM sub-partition w % 4, each with its own (narrow: 16 lanes) FP64 pipe and instruction cache.
         //  * sub-partition 0 belongs to the chain warp alone (warps 4, 8, 12 idle): with three other loops next to it the
@@ -380,9 +409,10 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         if (warp == 0) role = 0;
         else if (warp == 7) role = 2;
         else if (warp == 11) role = 3;
-        else if (warp == 15 || (warp & 3) == 0) { // 15, 4, 8, 12: light (copies), so the chain's sub-partition can host three of them
+        else if (warp == 15 && BAND_STREAM_UPDATES) role = 7; // streaming update of the next diagonal block
+        else if (warp == 15 || (warp & 3) == 0) { // 4, 8, 12 (, 15): light (copies), so the chain's sub-partition can host three of them
             role = 5;
-            ridx = warp == 15 ? 0 : warp >> 2;
+            ridx = warp == 15 ? 3 : (warp >> 2) - 1;
         }
         n_upd = bw <= 4 ? 6 : 10 - bw;
 #pragma unroll
@@ -405,9 +435,11 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             mbar_init(&bar_step[q], n_upd);
             mbar_init(&bar_rhs[q], 1);
             mbar_init(&bar_copy[q], N_COPY + 1); // copy warps + the inverse warp
+            for (int c = 0; c < 16; c++) mbar_init(&colbar[q][c], 1);
             for (int d = 0; d < 8; d++) {
                 mbar_init(&bar_p[q][d], 1);
                 mbar_init(&bar_c1[q][d], 1);
+                mbar_init(&bar_c2[q][d], 1);
             }
         }
     }
@@ -461,7 +493,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             }
             if (k >= 1) { // blocks (k,k) and (k+1,k) updated through step k-1 = tasks (1,1) and (2,1) of that step
                 mbar_wait_cta(&bar_c1[par ^ 1][1], ph(k - 1));
-                if (nd >= 1) mbar_wait_cta(&bar_c1[par ^ 1][2], ph(k - 1));
+                if (bw >= 2 && k + 1 < nb) mbar_wait_cta(&bar_c1[par ^ 1][2], ph(k - 1)); // task (2,1) exists only if row k+1 does and bw >= 2
             }
             BAND_TICK(1);
             double a[16];
@@ -472,7 +504,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                 a[c] = v.x;
                 a[c + 1] = v.y;
             }
-            band_chain_step(a, lane, pan0 + par * pl.pan_doubles, pcs, invs + par * BN, ok);
+            band_chain_step(a, lane, pan0 + par * pl.pan_doubles, pcs, invs + par * BN, &colbar[par][0], ok);
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&bar_panel[par]);
             BAND_TICK(2);
@@ -484,10 +516,38 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         for (int k = 0; k + d < nb; k++) {
             const int par = k & 1;
             double *pan = pan0 + par * pl.pan_doubles;
-            mbar_wait_cta(&bar_panel[par], ph(k));
-            if (k >= 1 && d < bw) mbar_wait_cta(&bar_c1[par ^ 1][d + 1], ph(k - 1)); // block (k+d, k) updated through step k-1 (task (d+1, 1)); d = bw: fresh row
+            // block (k+d, k) is final through step k-1 once task (d+1, 1) of that step is done; d = bw: a fresh row, resident
+            // once the copy of step k-2 is done.  The pivot columns are then consumed as the chain publishes them.
+            if (k >= 1 && d < bw) mbar_wait_cta(&bar_c1[par ^ 1][d + 1], ph(k - 1));
+            if (k >= 2 && d == bw) mbar_wait_cta(&bar_copy[par], ph(k - 2));
             BAND_TICK(1);
-            if (lane < 16) {
+            double wdum[8];
+            if (BAND_STREAM_UPDATES && d == 2) {
+                // block (k+2, k+1) must be final through step k-1: task (3,2) of that step, or a fresh row when bw == 2
+                if (k >= 1 && bw >= 3) mbar_wait_cta(&bar_c2[par ^ 1][3], ph(k - 1));
+                const int r = lane & 15, hh = lane >> 4;
+                double t[16], w8[8];
+                const double *src = Wk(2, 0) + r * WSTR;
+                double *wsrc = Wk(2, 1) + r * WSTR + 8 * hh;
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(src + c);
+                    t[c] = v.x;
+                    t[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(wsrc + c);
+                    w8[c] = v.x;
+                    w8[c + 1] = v.y;
+                }
+                band_trsm16<true>(t, w8, hh, pan, pcs, invs + par * BN, hh == 0 ? pan + 32 + r : nullptr, pcs,
+                                  hh == 0 ? Lb + ((size_t)k * (bw + 2) + 2) * 256 + r * 16 : nullptr, &colbar[par][0], ph(k));
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2 *>(wsrc + c) = make_double2(w8[c], w8[c + 1]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(&bar_c1[par][2]); // task (2,1) of this step is done
+            } else if (lane < 16) {
                 double t[16];
                 const double *src = Wk(d, 0) + lane * WSTR;
 #pragma unroll
@@ -496,7 +556,8 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                     t[c] = v.x;
                     t[c + 1] = v.y;
                 }
-                band_trsm16(t, pan, pcs, invs + par * BN, pan + 16 * d + lane, pcs, Lb + ((size_t)k * (bw + 2) + d) * 256 + lane * 16);
+                band_trsm16<false>(t, wdum, 0, pan, pcs, invs + par * BN, pan + 16 * d + lane, pcs, Lb + ((size_t)k * (bw + 2) + d) * 256 + lane * 16,
+                                   &colbar[par][0], ph(k));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&bar_p[par][d]);
@@ -515,7 +576,8 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                 double t[16];
 #pragma unroll
                 for (int c = 0; c < 16; c++) t[c] = gs[k * BN + c];
-                band_trsm16(t, pan, pcs, invs + par * BN, gs + k * BN, 1);
+                double wdum[8];
+                band_trsm16<false>(t, wdum, 0, pan, pcs, invs + par * BN, gs + k * BN, 1);
             }
             __syncwarp();
             const int r = lane & 15, hh = lane >> 4;
@@ -547,7 +609,8 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                 double t[16];
 #pragma unroll
                 for (int c = 0; c < 16; c++) t[c] = c == lane ? 1.0 : 0.0;
-                band_trsm16(t, pan0 + par * pl.pan_doubles, pcs, invs + par * BN, Lb + ((size_t)k * (bw + 2) + bw + 1) * 256 + lane, 16); // Minv[c][r] = (L^-T)[r][c]
+                double wdum[8];
+                band_trsm16<false>(t, wdum, 0, pan0 + par * pl.pan_doubles, pcs, invs + par * BN, Lb + ((size_t)k * (bw + 2) + bw + 1) * 256 + lane, 16); // Minv[c][r] = (L^-T)[r][c]
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&bar_copy[par]);
@@ -583,20 +646,21 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             const double *pan = pan0 + par * pl.pan_doubles;
             mbar_wait_cta(&bar_panel[par], ph(k)); // also keeps a warp without tasks from running ahead of the barrier phases
             // two passes: first-column tasks (dj = 1) first, the next step waits for them
+            // with BAND_STREAM_UPDATES tasks (1,1) and (2,1) are not done here: the streaming warps (roles 7 and 1) apply them
 #pragma unroll
-            for (int pass = 0; pass < 2; pass++)
+            for (int pass = 0; pass < (BAND_STREAM_UPDATES ? 3 : 2); pass++)
 #pragma unroll
-                for (int q = 0; q < MAXV; q++) { // my virtual workers are sorted by offset, i.e. first-column tasks come in di order
+                for (int q = 0; q < MAXV; q++) { // my virtual workers are sorted by offset, i.e. the tasks of a column come in di order
                     if (q >= nv) continue;
                     const int dj = vdj[q], di = dj + vo[q];
-                    if ((dj == 1) != (pass == 0) || di > nd) continue;
+                    if ((BAND_STREAM_UPDATES ? (dj < 3 ? dj - 1 : 2) : (dj == 1 ? 0 : 1)) != pass || di > nd || (BAND_STREAM_UPDATES && dj == 1 && di <= 2)) continue;
                     if (di >= 2) mbar_wait_cta(&bar_p[par][di], ph(k));
                     if (dj >= 2) mbar_wait_cta(&bar_p[par][dj], ph(k));
                     BAND_TICK(1);
                     band_update_dmma(Wk(di, dj), pan + 16 * di, pan + 16 * dj, pcs, lane);
-                    if (dj == 1) {
+                    if (dj <= (BAND_STREAM_UPDATES ? 2 : 1)) { // the first (two) block column(s) are waited for by the next step
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cta(&bar_c1[par][di]);
+                        if (lane == 0) mbar_arrive_cta(dj == 1 ? &bar_c1[par][di] : &bar_c2[par][di]);
                     }
                     BAND_TICK(2);
                 }
@@ -605,6 +669,45 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                 if (q < nv) vdj[q] = vdj[q] == 1 ? bw - vo[q] : vdj[q] - 1;
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&bar_step[par]);
+            next_k();
+        }
+    } else if (role == 7) {
+        // ------------------------------------------------------------------ D_(k+1) -= P_(k+1,k) P_(k+1,k)^T, streamed behind the chain:
+        // lane (r, hh) holds entries 8 hh .. 8 hh + 7 of row r and applies one rank-1 update per published pivot column
+        const int r = lane & 15, hh = lane >> 4;
+        for (int k = 0; k + 1 < nb; k++) {
+            const int par = k & 1;
+            const double *pan = pan0 + par * pl.pan_doubles;
+            if (k >= 1) { // the block is final through step k-1: task (2,2) of that step, or a fresh row when bw == 1
+                if (bw >= 2) mbar_wait_cta(&bar_c2[par ^ 1][2], ph(k - 1));
+                else if (k >= 2) mbar_wait_cta(&bar_copy[par], ph(k - 2));
+            }
+            BAND_TICK(1);
+            double *dsrc = Wk(1, 1) + r * WSTR + 8 * hh;
+            double dd[8];
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(dsrc + c);
+                dd[c] = v.x;
+                dd[c + 1] = v.y;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                if ((c & 3) == 0) mbar_wait_cta(&colbar[par][c >> 2], ph(k));
+                const double *p1 = pan + c * pcs + 16;
+                const double x = p1[r];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const double2 q = *reinterpret_cast<const double2 *>(p1 + 8 * hh + j);
+                    dd[j] = fma(-x, q.x, dd[j]);
+                    dd[j + 1] = fma(-x, q.y, dd[j + 1]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2 *>(dsrc + c) = make_double2(dd[c], dd[c + 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&bar_c1[par][1]); // task (1,1) of this step is done
+            BAND_TICK(2);
             next_k();
         }
     } else if (role == 5) {

@@ -356,3 +356,12 @@ def test_gradient_tolerance_termination_matches_oracle(solver):
     g, o = solve_both(solver, win, cfg)
     assert g[2]["termination"] == o[2]["termination"]
     assert g[2]["iterations"] == o[2]["iterations"]
+
+
+def test_band_of_one_block(solver):
+    """BA-only window with two-keyframe tracks: consecutive 6-dof poses couple, half-bandwidth of ONE 16-column block —
+    the streaming-update warps of k_chol_band have no (2,1) task to wait for."""
+    win = synth.make_window("C2", span=2, vio=False)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert_same_states(win, g[1], o[1])

@@ -8,12 +8,15 @@ using namespace sdv;
 __device__ __forceinline__ long long rdclk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
 __global__ void __launch_bounds__(512, 1) k(double *out, long long *res, int spinners, int bw) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, colbar[16];
     const int pcs = 16 * (bw + 1) + 4;
     double *pan = sm, *iv = sm + 16 * pcs + 32, *win = iv + 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < 16 * pcs + 64 + 4 * WBLK; e += blockDim.x) sm[e] = 1e-3 * (e % 7);
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        for (int c = 0; c < 16; c++) mbar_init(&colbar[c], 1);
+    }
     __syncthreads();
     if (warp > 0) {
         if (warp <= spinners) mbar_wait_cta(&bar, 0);
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(512, 1) k(double *out, long long *res, int spi
         for (int c = 0; c < 16; c++) a[c] = (c == (lane & 15) ? 50.0 : 0.01) + lane * 1e-3;
         *(volatile double *)&win[lane] = a[3];
         t0 = rdclk();
-        band_chain_step(a, lane, pan, pcs, iv, ok);
+        band_chain_step(a, lane, pan, pcs, iv, colbar, ok);
         *(volatile double *)&win[lane] = a[0] + a[7];
         t1 = rdclk();
         acc += t1 - t0;
@@ -40,7 +43,8 @@ __global__ void __launch_bounds__(512, 1) k(double *out, long long *res, int spi
         for (int c = 0; c < 16; c++) t[c] = 0.5 + c * 0.01 + lane;
         *(volatile double *)&win[lane] = t[3];
         t0 = rdclk();
-        if (lane < 16) band_trsm16(t, pan, pcs, iv, pan + 32 + lane, pcs);
+        double wdum[8];
+        if (lane < 16) band_trsm16<false>(t, wdum, 0, pan, pcs, iv, pan + 32 + lane, pcs);
         __syncwarp();
         *(volatile double *)&win[lane] = t[0] + t[7];
         t1 = rdclk();
