@@ -365,3 +365,18 @@ def test_band_of_one_block(solver):
     g, o = solve_both(solver, win)
     assert_same_solution(g, o)
     assert_same_states(win, g[1], o[1])
+
+
+@pytest.mark.parametrize("name,cfg,kind", [("tiny_vio_angular", "tiny", 0), ("tiny_vio_pixel", "tiny", 1), ("small_vio_angular", "small", 0)])
+def test_golden_solutions(solver, name, cfg, kind):
+    """CUDA path against the committed golden solutions (tests/golden/*.npz, generated by tests/golden/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    win = synth.make_window(cfg, factor_kind=kind)
+    assert np.array_equal(win.obs_lmk, g["obs_lmk"]) and np.array_equal(win.obs_frame, g["obs_frame"])  # visibility bit-exact
+    rc, d, st = solver.solve_window(win)
+    assert rc == 0 and st["iterations"] == int(g["iterations"]) and st["termination"] == str(g["termination"])
+    assert list(st["trace_accepted"]) == list(g["trace_accepted"])
+    for k in ("dpose", "dv", "dba", "dbg"):
+        a, b = getattr(d, k), g[k]
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max() + 1e-13

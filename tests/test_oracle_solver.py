@@ -121,3 +121,35 @@ def test_sparsified_priors_schur_equals_full():
         assert np.abs(d0.dpose - d1.dpose).max() < 1e-9 and np.abs(d0.dlmk - d1.dlmk).max() < 1e-8
     # chain landmarks live in the reduced system
     assert st0["n_reduced"] == 6 * 9 + 3 * 12
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# committed golden solutions (tests/golden/make_golden.py): the oracle must keep reproducing them
+# ---------------------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+import pytest  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = {"tiny_vio_angular": ("tiny", dict(factor_kind=0)), "tiny_vio_pixel": ("tiny", dict(factor_kind=1)),
+                "small_vio_angular": ("small", dict(factor_kind=0))}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_oracle_reproduces_golden_solution(name):
+    import numpy as np
+
+    from oracle import oracle
+    from sadvio_b200 import synth
+
+    cfg, kw = GOLDEN_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    win = synth.make_window(cfg, **kw)
+    # landmark-keyframe visibility indices: bit-exact
+    assert np.array_equal(win.obs_lmk, g["obs_lmk"]) and np.array_equal(win.obs_frame, g["obs_frame"]) and np.array_equal(win.obs_cam, g["obs_cam"])
+    rc, d, st = oracle.solve_window(win, mode=0, nthreads=4)
+    assert rc == 0 and st["iterations"] == int(g["iterations"]) and st["termination"] == str(g["termination"])
+    assert list(st["trace_accepted"]) == list(g["trace_accepted"])
+    for k in ("dpose", "dv", "dba", "dbg", "dlmk"):
+        a, b = getattr(d, k), g[k]
+        assert np.abs(a - b).max() <= 1e-9 * max(1e-12, np.abs(b).max())
