@@ -752,56 +752,35 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             }
         const int c = lane & 15, hh = lane >> 4;
         double *rvs = invs; // 16 doubles of scratch (the reciprocal diagonals are no longer needed)
-        // Step k: x_k = Minv_k^T (y_k - sum_d (L_(k+d,k))^T x_(k+d)).  Only the d = 1 term waits for the previous step; the
-        // terms d >= 2 of step k-1 ("pre") use older x and are computed in the same loop body as step k, so that their loads
-        // and FMAs fill the latency gaps of the dependent chain (shuffle, shared-memory round trip) of step k.
-        // lane (c, hh) sums rows 8 hh .. 8 hh + 7 of every block.
-        auto block_dot = [&](const double *blk, const double *xv, double &s0, double &s1, double &s2, double &s3) {
-            const double *Lc = blk + hh * 128 + c;
-            const double2 *x2 = reinterpret_cast<const double2 *>(xv + hh * 8);
-            const double2 xa = x2[0], xb = x2[1], xc = x2[2], xd = x2[3];
-            s0 = fma(Lc[0], xa.x, s0);
-            s1 = fma(Lc[16], xa.y, s1);
-            s2 = fma(Lc[32], xb.x, s2);
-            s3 = fma(Lc[48], xb.y, s3);
-            s0 = fma(Lc[64], xc.x, s0);
-            s1 = fma(Lc[80], xc.y, s1);
-            s2 = fma(Lc[96], xd.x, s2);
-            s3 = fma(Lc[112], xd.y, s3);
-        };
         int s = 0, ph = 0;
-        double pre = 0.0; // partial (this lane's rows) of the d >= 2 terms of the current step
-        if (nb > 0) mbar_wait(&full[0], 0u);
         for (int it = 0; it < nb; it++) {
             const int k = nb - 1 - it;
             const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
+            BAND_TICK(5);
+            mbar_wait(&full[s], (unsigned)ph);
+            BAND_TICK(3);
             const double *sb = ring + s * stage_doubles;
-            int sn = s + 1, phn = ph;
-            if (sn == NS) {
-                sn = 0;
-                phn ^= 1;
+            // (L_(k+d,k))^T x_(k+d), d = 1..nd: lane (c, hh) sums rows 8 hh .. 8 hh + 7 of every block; four independent chains
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int d = 1; d <= BAND_MAX_BW; d++) {
+                if (d > nd) break;
+                const double *Lc = sb + d * 256 + hh * 128 + c;
+                const double2 *x2 = reinterpret_cast<const double2 *>(gs + (k + d) * BN + hh * 8);
+                const double2 xa = x2[0], xb = x2[1], xc = x2[2], xd = x2[3];
+                s0 = fma(Lc[0], xa.x, s0);
+                s1 = fma(Lc[16], xa.y, s1);
+                s2 = fma(Lc[32], xb.x, s2);
+                s3 = fma(Lc[48], xb.y, s3);
+                s0 = fma(Lc[64], xc.x, s0);
+                s1 = fma(Lc[80], xc.y, s1);
+                s2 = fma(Lc[96], xd.x, s2);
+                s3 = fma(Lc[112], xd.y, s3);
             }
-            // ---- critical: the d = 1 term, then the two small matrix-vector products
-            double s0 = pre, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            if (nd >= 1) block_dot(sb + 256, gs + (k + 1) * BN, s0, s1, s2, s3);
             double sum = (s0 + s1) + (s2 + s3);
             sum += __shfl_xor_sync(FULL, sum, 16);
             const double rv = gs[k * BN + c] - sum; // both half-warps hold rv[c]
             if (hh == 0) rvs[c] = rv;               // x_k = L_kk^-T rv = Minv^T rv, broadcast through shared memory
-            // ---- not critical: "pre" of step k-1 (blocks d = 2 .. of block column k-1, x_(k+1) .. x_(k+bw-1))
-            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-            if (k >= 1) {
-                BAND_TICK(5);
-                mbar_wait(&full[sn], (unsigned)phn);
-                BAND_TICK(3);
-                const double *sbn = ring + sn * stage_doubles;
-                const int ndn = bw < nb - k ? bw : nb - k; // nd of step k-1
-#pragma unroll
-                for (int d = 2; d <= BAND_MAX_BW; d++) {
-                    if (d > ndn) break;
-                    block_dot(sbn + d * 256, gs + (k - 1 + d) * BN, p0, p1, p2, p3);
-                }
-            }
             __syncwarp();
             const double *Mi = sb + (bw + 1) * 256 + hh * 128 + c;
             const double2 *r2 = reinterpret_cast<const double2 *>(rvs + hh * 8);
@@ -817,15 +796,16 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                 gs[k * BN + c] = x;
                 dxp[k * BN + c] = -x;
             }
-            pre = (p0 + p1) + (p2 + p3);
             __syncwarp();
-            if (lane == 0 && it + NS < nb) { // stage s is free again: block column k - NS
+            if (lane == 0 && it + NS < nb) {
                 const int k2 = nb - 1 - (it + NS);
                 mbar_expect_tx(&full[s], stage_bytes);
                 bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k2 * stage_doubles, stage_bytes, &full[s]);
             }
-            s = sn;
-            ph = phn;
+            if (++s == NS) {
+                s = 0;
+                ph ^= 1;
+            }
         }
     }
     __syncthreads();
