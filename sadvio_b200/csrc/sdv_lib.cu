@@ -644,9 +644,15 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     const int Tt = n_pad / 32;
     std::vector<uint32_t> &tile_nz = h->tmp_tile_nz; // [(Tt + 1)][4] bit j of row i: tile (i, j) of L may be non-zero
     tile_nz.assign((size_t)(Tt + 1) * 4, 0u);
-    struct TMask {
-        uint64_t w[2];
-        bool operator==(const TMask &o) const { return w[0] == o.w[0] && w[1] == o.w[1]; }
+    struct TMask { // up to 256 column groups
+        uint64_t w[4];
+        bool operator==(const TMask &o) const { return w[0] == o.w[0] && w[1] == o.w[1] && w[2] == o.w[2] && w[3] == o.w[3]; }
+        void operator|=(const TMask &o) {
+            w[0] |= o.w[0];
+            w[1] |= o.w[1];
+            w[2] |= o.w[2];
+            w[3] |= o.w[3];
+        }
     };
     // low[i]: column groups j (of `gs` columns each, at most 128 groups) coupled with group row i before elimination
     auto build_low = [&](const int gs, std::vector<TMask> &low) {
@@ -655,25 +661,24 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             if (c0 < 0) return;
             for (int t = c0 / gs; t <= (c0 + ncols - 1) / gs; t++) m.w[t >> 6] |= 1ull << (t & 63);
         };
-        low.assign((size_t)ng + 1, TMask{{0, 0}});
+        low.assign((size_t)ng + 1, TMask{{0, 0, 0, 0}});
         auto add_clique = [&](const TMask &m) {
-            for (int wq = 0; wq < 2; wq++) {
+            for (int wq = 0; wq < 4; wq++) {
                 uint64_t bits = m.w[wq];
                 while (bits) {
                     const int i = wq * 64 + __builtin_ctzll(bits);
                     bits &= bits - 1;
-                    low[i].w[0] |= m.w[0];
-                    low[i].w[1] |= m.w[1];
+                    low[i] |= m;
                 }
             }
         };
         if (getenv("SDV_CHOL_DENSE")) {
-            TMask all{{0, 0}};
+            TMask all{{0, 0, 0, 0}};
             add_cols(all, 0, n_pad);
             add_clique(all);
             return;
         }
-        std::vector<TMask> pose_mask(F, TMask{{0, 0}}), frame_mask(F, TMask{{0, 0}});
+        std::vector<TMask> pose_mask(F, TMask{{0, 0, 0, 0}}), frame_mask(F, TMask{{0, 0, 0, 0}});
         for (int f = 0; f < F; f++) {
             add_cols(pose_mask[f], pose_col[f], 6);
             frame_mask[f] = pose_mask[f];
@@ -682,14 +687,13 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         }
         // visual factors: every landmark couples the poses of the keyframes that see it (and its own columns when kept)
         std::vector<TMask> uniq;
-        TMask last{{0, 0}};
+        TMask last{{0, 0, 0, 0}};
         for (int l = 0; l < L; l++) {
             if (same_prev[l] && lmk_col[l] < 0 && lmk_col[l - 1] < 0) continue; // same clique as the previous landmark
-            TMask m{{0, 0}};
+            TMask m{{0, 0, 0, 0}};
             for (int q = slot_ptr[l]; q < slot_ptr[l + 1]; q++) {
                 const TMask &pm = pose_mask[slot_frame[q]];
-                m.w[0] |= pm.w[0];
-                m.w[1] |= pm.w[1];
+                m |= pm;
             }
             if (lmk_col[l] >= 0) add_cols(m, lmk_col[l], 3);
             if (m == last) continue;
@@ -701,12 +705,11 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         for (const TMask &m : uniq) add_clique(m);
         for (int p = 0; p < Pn; p++) { // IMUFactor + IMUBiasFactor couple all 15 parameters of both keyframes
             TMask m = frame_mask[w->imu_i[p]];
-            m.w[0] |= frame_mask[w->imu_j[p]].w[0];
-            m.w[1] |= frame_mask[w->imu_j[p]].w[1];
+            m |= frame_mask[w->imu_j[p]];
             add_clique(m);
         }
         if (dp) { // dense marginalisation prior: one clique over everything it touches
-            TMask m{{0, 0}};
+            TMask m{{0, 0, 0, 0}};
             for (int c : mp_dst)
                 if (c >= 0) add_cols(m, c, 1);
             add_clique(m);
@@ -714,12 +717,12 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         if (sp) {
             if (sp->has_imu_prior) add_clique(frame_mask[sp->frame]);
             if (sp->has_lmk_prior) {
-                TMask m{{0, 0}};
+                TMask m{{0, 0, 0, 0}};
                 add_cols(m, lmk_col[sp->lmk0], 3);
                 add_clique(m);
             }
             for (int k = 0; k < sp->n_l2l; k++) {
-                TMask m{{0, 0}};
+                TMask m{{0, 0, 0, 0}};
                 add_cols(m, lmk_col[sp->l2l_a[k]], 3);
                 add_cols(m, lmk_col[sp->l2l_b[k]], 3);
                 add_clique(m);
@@ -733,13 +736,12 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         build_low(32, low);
         // symbolic right-looking elimination on the tile graph: the rows below pivot k become mutually coupled
         for (int k = 0; k < Tt; k++) {
-            TMask col{{0, 0}}; // rows i > k with (i, k) non-zero
+            TMask col{{0, 0, 0, 0}}; // rows i > k with (i, k) non-zero
             for (int i = k + 1; i < Tt; i++)
                 if (bit(low[i], k)) col.w[i >> 6] |= 1ull << (i & 63);
             for (int i = k + 1; i < Tt; i++)
                 if (bit(col, i)) {
-                    low[i].w[0] |= col.w[0];
-                    low[i].w[1] |= col.w[1];
+                    low[i] |= col;
                 }
         }
         int nnz_tiles = 0;
@@ -757,13 +759,15 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     //      envelope of the matrix, so max_i (i - first coupled block of row i) bounds the fill: when that band (plus two
     //      look-ahead block rows) fits in the shared memory of one SM, the whole factorisation runs in ONE CTA (k_chol_band).
     int band_bw = -1;
-    if (n_pad / 16 <= 128) {
+    if (n_pad / 16 <= 256) {
         std::vector<TMask> low16;
         build_low(16, low16);
         const int nb16 = n_pad / 16;
         band_bw = 0;
         for (int i = 0; i < nb16; i++) {
-            const int first = low16[i].w[0] ? __builtin_ctzll(low16[i].w[0]) : (low16[i].w[1] ? 64 + __builtin_ctzll(low16[i].w[1]) : i);
+            int first = i;
+            for (int wq = 3; wq >= 0; wq--)
+                if (low16[i].w[wq]) first = wq * 64 + __builtin_ctzll(low16[i].w[wq]);
             band_bw = std::max(band_bw, i - std::min(first, i));
         }
     }

@@ -380,3 +380,13 @@ def test_golden_solutions(solver, name, cfg, kind):
     for k in ("dpose", "dv", "dba", "dbg"):
         a, b = getattr(d, k), g[k]
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max() + 1e-13
+
+
+def test_full_solve_c5_band_kernel(solver):
+    """BASELINE.json config 5 on one GPU: 200 KF x 100k landmarks x 800k observations; the reduced system (n = 2985, 187
+    blocks of 16, half-bandwidth 4) is factored by the banded single-CTA kernel."""
+    win = synth.make_window("C5")
+    assert (win.n_frames, win.n_lmks, win.n_obs) == (200, 100000, 800000)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert_same_states(win, g[1], o[1])
