@@ -296,16 +296,21 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf
 // non-visual factors: IMUFactor (a7), IMUBiasFactor (a8), PosePriordx (a9), MarginalizationFactor (a10)
 // =====================================================================================================================
 // Upper-triangular sqrt information U with U^T U = cov^-1 (residuals.hpp:151-154), once per uploaded window.
-__global__ void k_imu_inf_sqrt(DevProblem P) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per IMU pair (4 pairs per CTA); lane j owns column j of the 9 x 18 tableau [cov | I], so every row operation of
+// the elimination is one step for the warp.  Each element sees exactly the operations, in the order, of the sequential
+// algorithm (the result is bit-identical to it); one thread per pair took 44 us per upload.
+__global__ void __launch_bounds__(128) k_imu_inf_sqrt(DevProblem P) {
+    __shared__ double ms[4][9][19], Ls[4][9][9];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int p = blockIdx.x * 4 + wib;
     if (p >= P.P) return;
-    double m[9][18];
+    double(*m)[19] = ms[wib];
+    double(*Lm)[9] = Ls[wib];
     const double *cov = P.imu_cov + 81 * (size_t)p;
-    for (int i = 0; i < 9; i++)
-        for (int j = 0; j < 9; j++) {
-            m[i][j] = cov[i * 9 + j];
-            m[i][9 + j] = (i == j) ? 1.0 : 0.0;
-        }
+    const int j = lane; // my column (lanes 18.. idle)
+    if (j < 18)
+        for (int i = 0; i < 9; i++) m[i][j] = j < 9 ? cov[i * 9 + j] : (i == j - 9 ? 1.0 : 0.0);
+    __syncwarp();
     // Gauss-Jordan with partial pivoting (what Eigen's PartialPivLU-based inverse() amounts to)
     for (int c = 0; c < 9; c++) {
         int piv = c;
@@ -315,44 +320,53 @@ __global__ void k_imu_inf_sqrt(DevProblem P) {
                 best = fabs(m[r][c]);
                 piv = r;
             }
-        if (piv != c)
-            for (int j = 0; j < 18; j++) {
-                double t = m[c][j];
-                m[c][j] = m[piv][j];
-                m[piv][j] = t;
-            }
-        double inv = 1.0 / m[c][c];
-        for (int r = c + 1; r < 9; r++) {
-            double f = m[r][c] * inv;
-            for (int j = c; j < 18; j++) m[r][j] -= f * m[c][j];
+        __syncwarp();
+        if (piv != c && j < 18) {
+            double t = m[c][j];
+            m[c][j] = m[piv][j];
+            m[piv][j] = t;
         }
+        __syncwarp();
+        const double inv = 1.0 / m[c][c];
+        double f[9];
+        for (int r = c + 1; r < 9; r++) f[r] = m[r][c] * inv;
+        __syncwarp();
+        if (j >= c && j < 18)
+            for (int r = c + 1; r < 9; r++) m[r][j] -= f[r] * m[c][j];
+        __syncwarp();
     }
     for (int c = 8; c >= 0; c--) {
-        double inv = 1.0 / m[c][c];
-        for (int j = 0; j < 18; j++) m[c][j] *= inv;
-        for (int r = 0; r < c; r++) {
-            double f = m[r][c];
-            for (int j = 0; j < 18; j++) m[r][j] -= f * m[c][j];
-        }
+        const double inv = 1.0 / m[c][c];
+        __syncwarp();
+        if (j < 18) m[c][j] *= inv;
+        __syncwarp();
+        double f[9];
+        for (int r = 0; r < c; r++) f[r] = m[r][c];
+        __syncwarp();
+        if (j < 18)
+            for (int r = 0; r < c; r++) m[r][j] -= f[r] * m[c][j];
+        __syncwarp();
     }
-    // Cholesky of the inverse: L L^T, store U = L^T
-    double Lm[9][9];
-    for (int i = 0; i < 9; i++)
-        for (int j = 0; j < 9; j++) Lm[i][j] = 0.0;
-    for (int j = 0; j < 9; j++) {
-        double s = m[j][9 + j];
-        for (int k = 0; k < j; k++) s -= Lm[j][k] * Lm[j][k];
-        double d = sqrt(s);
-        Lm[j][j] = d;
-        for (int i = j + 1; i < 9; i++) {
-            double t = m[i][9 + j];
-            for (int k = 0; k < j; k++) t -= Lm[i][k] * Lm[j][k];
-            Lm[i][j] = t / d;
+    // Cholesky of the inverse: L L^T, store U = L^T; lane i owns row i
+    const int i = lane;
+    if (i < 9)
+        for (int q = 0; q < 9; q++) Lm[i][q] = 0.0;
+    __syncwarp();
+    for (int q = 0; q < 9; q++) {
+        double s = m[q][9 + q];
+        for (int k = 0; k < q; k++) s -= Lm[q][k] * Lm[q][k];
+        const double d = sqrt(s);
+        __syncwarp();
+        if (i == q) Lm[q][q] = d;
+        if (i > q && i < 9) {
+            double t = m[i][9 + q];
+            for (int k = 0; k < q; k++) t -= Lm[i][k] * Lm[q][k];
+            Lm[i][q] = t / d;
         }
+        __syncwarp();
     }
     double *U = P.imu_inf_sqrt + 81 * (size_t)p;
-    for (int i = 0; i < 9; i++)
-        for (int j = 0; j < 9; j++) U[i * 9 + j] = Lm[j][i];
+    for (int e = lane; e < 81; e += 32) U[e] = Lm[e % 9][e / 9];
 }
 
 // current value of a frame's parameter blocks

@@ -1132,7 +1132,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     if (h->band_smem == 0) CK(cudaMemsetAsync(h->d_Lo, 0, sizeof(double) * sb_elems, h->stream)); // cluster variants: tiles outside the structural pattern are never written
     // ---- one-time device setup for this window
     if (Pn > 0) {
-        k_imu_inf_sqrt<<<(Pn + 31) / 32, 32, 0, h->stream>>>(P);
+        k_imu_inf_sqrt<<<(Pn + 3) / 4, 128, 0, h->stream>>>(P);
         h->launches++;
     }
     if (dp && nm > 0) {
