@@ -32,10 +32,11 @@ constexpr int BCT = 512;        // threads of the CTA
 constexpr int BNW = BCT / 32;
 constexpr int BAND_MAX_BW = 7;  // task tables / shared memory are sized for this
 constexpr int BAND_MAX_STAGES = 16; // backward-solve ring (TMA bulk copies in flight)
-// Streaming of the two updates the chain waits for, (1,1) and (2,1), behind the chain (roles 7 and 1).  Correct (parity tests
-// pass with it) but NOT faster yet at C3: 150 us against 132 us — their own inputs, tasks (2,2), (3,1), (3,2) of the previous
-// step, still come from the tensor-core update warps ~1.5 k cycles after the chain has moved on, so the streaming warps start
-// late and the chain ends up waiting for them.  Pays only once block row k+3 streams as well; kept behind this switch.
+// EXPERIMENT (off): block rows k+1 .. k+3 apply ALL their updates as rank-1 updates behind the chain ("streaming rows", roles 7
+// and 1), the tensor-core update warps keep rows >= k+4.  Correct (the parity tests pass with -DSDV_BAND_STREAM_UPDATES=1)
+// but slower at C3 (259 us against 135 us): under the 128-register cap of a 512-thread CTA the d = 3 row spills (t[16] +
+// 3 x 8 accumulators + operands) and needs ~430 cycles per pivot where the chain needs 116, so the chain waits for it.
+// To pay it needs 256 threads per CTA (255 registers) or the d = 3 row split over two warps.
 #ifndef SDV_BAND_STREAM_UPDATES
 #define SDV_BAND_STREAM_UPDATES 0
 #endif
@@ -224,6 +225,48 @@ SDV_DEV void band_trsm16(double (&t)[16], double (&w)[8], int h, const double *p
         for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(grow + c) = make_double2(xs[c], xs[c + 1]);
 }
 
+// Streaming block row at distance D (2 or 3) from the pivot block (BAND_STREAM_UPDATES): the solve P_D = W_(k+D,k) L_kk^-T and
+// ALL updates of that row in this step, W_(k+D,k+1+b) -= P_D P_(1+b)^T for b = 0..D-1, applied as rank-1 updates behind the
+// chain, one pivot column at a time.  Lane (r, hh): row r; the two half-warps duplicate the solve and split the 16 columns of
+// every updated block (w[b] = columns 8 hh .. 8 hh + 7 of block b).  Column c of P_D is published right away (the diagonal
+// block b = D-1 needs it from all 16 rows, and the next streaming row needs it too).
+template <int D>
+SDV_DEV void band_stream_row(double (&t)[16], double (&w)[D][8], int r, int hh, int lane, double *pan, int pcs, const double *iv,
+                             uint64_t *colbar, uint64_t *colbar_prev, uint64_t *colbar_own, unsigned parity) {
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        if ((c & 3) == 0) {
+            mbar_wait_cta(colbar + (c >> 2), parity);                       // columns c .. c+3 of L_kk, P_1 (chain)
+            if (colbar_prev) mbar_wait_cta(colbar_prev + (c >> 2), parity); // ... and of P_(D-1) (the streaming row before this one)
+        }
+        const double x = t[0] * iv[c];
+        double *col = pan + c * pcs;
+        if (hh == 0) col[16 * D + r] = x;
+        const double *v = col + c;
+        const int j0 = ((c + 1) & 1) ? 2 : 1, jn = 16 - c;
+        if (j0 == 2 && 1 < jn) t[0] = fma(-x, v[1], t[1]);
+#pragma unroll
+        for (int j = j0; j + 1 < jn; j += 2) {
+            const double2 q = *reinterpret_cast<const double2 *>(v + j);
+            t[j - 1] = fma(-x, q.x, t[j]);
+            t[j] = fma(-x, q.y, t[j + 1]);
+        }
+        if (jn > j0 && ((jn - j0) & 1)) t[jn - 2] = fma(-x, v[jn - 1], t[jn - 1]);
+        __syncwarp(); // column c of P_D is complete
+#pragma unroll
+        for (int b = 0; b < D; b++) {
+            const double *pb = col + 16 * (b + 1) + 8 * hh;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const double2 q = *reinterpret_cast<const double2 *>(pb + j);
+                w[b][j] = fma(-x, q.x, w[b][j]);
+                w[b][j + 1] = fma(-x, q.y, w[b][j + 1]);
+            }
+        }
+        if (colbar_own && (c & 3) == 3 && lane == 0) mbar_arrive_cta(colbar_own + (c >> 2));
+    }
+}
+
 // C (16 x 16 window block, row stride WSTR) -= P_i P_j^T, operands = blocks of the transposed panel; one warp
 SDV_DEV void band_update_dmma(double *C, const double *PTi, const double *PTj, int pcs, int lane) {
     const int g = lane >> 2, t = lane & 3;
@@ -327,7 +370,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                                                       double *Lb, double *scale_p, double *damp_p, double *graw_p, double *dxp, double *prof) {
     if (st->status != 0) return;
     extern __shared__ __align__(16) double bsm[];
-    __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8], bar_c2[2][8], colbar[2][16];
+    __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8], bar_c2[2][8], colbar[2][16], colbar2[2][4], bar_r3[2];
     __shared__ int s_fail;
     const BandPlan pl = band_plan(P.n_pad, P.band_bw);
     const int nb = pl.nb, bw = pl.bw, R = pl.R, ld = P.ld, pcs = pl.pcs;
@@ -435,6 +478,8 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             mbar_init(&bar_step[q], n_upd);
             mbar_init(&bar_rhs[q], 1);
             mbar_init(&bar_copy[q], N_COPY + 1); // copy warps + the inverse warp
+            mbar_init(&bar_r3[q], 1);
+            for (int c = 0; c < 4; c++) mbar_init(&colbar2[q][c], 1);
             for (int c = 0; c < 16; c++) mbar_init(&colbar[q][c], 1);
             for (int d = 0; d < 8; d++) {
                 mbar_init(&bar_p[q][d], 1);
@@ -516,37 +561,65 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         for (int k = 0; k + d < nb; k++) {
             const int par = k & 1;
             double *pan = pan0 + par * pl.pan_doubles;
-            // block (k+d, k) is final through step k-1 once task (d+1, 1) of that step is done; d = bw: a fresh row, resident
-            // once the copy of step k-2 is done.  The pivot columns are then consumed as the chain publishes them.
-            if (k >= 1 && d < bw) mbar_wait_cta(&bar_c1[par ^ 1][d + 1], ph(k - 1));
-            if (k >= 2 && d == bw) mbar_wait_cta(&bar_copy[par], ph(k - 2));
+            const bool streaming = BAND_STREAM_UPDATES && d <= 3;
+            if (!streaming) {
+                // block (k+d, k) is final through step k-1 once task (d+1, 1) of that step is done; d = bw: a fresh row, resident
+                // once the copy of step k-2 is done.  The pivot columns are then consumed as the chain publishes them.
+                if (k >= 1 && d < bw) mbar_wait_cta(&bar_c1[par ^ 1][d + 1], ph(k - 1));
+                if (k >= 2 && d == bw) mbar_wait_cta(&bar_copy[par], ph(k - 2));
+            } else if (k >= 1) {
+                // streaming row: ALL its blocks must be final through step k-1.  d = 2: they were row 3 of step k-1 (the other
+                // streaming warp); d = 3: row 4 of step k-1 (update warps); last row of the band: fresh from the copy of step k-2
+                if (d < bw) mbar_wait_cta(d == 2 ? &bar_r3[par ^ 1] : &bar_step[par ^ 1], ph(k - 1));
+                else if (k >= 2) mbar_wait_cta(&bar_copy[par], ph(k - 2));
+            }
             BAND_TICK(1);
             double wdum[8];
-            if (BAND_STREAM_UPDATES && d == 2) {
-                // block (k+2, k+1) must be final through step k-1: task (3,2) of that step, or a fresh row when bw == 2
-                if (k >= 1 && bw >= 3) mbar_wait_cta(&bar_c2[par ^ 1][3], ph(k - 1));
+            if (streaming) {
                 const int r = lane & 15, hh = lane >> 4;
-                double t[16], w8[8];
-                const double *src = Wk(2, 0) + r * WSTR;
-                double *wsrc = Wk(2, 1) + r * WSTR + 8 * hh;
+                double t[16];
+                const double *src = Wk(d, 0) + r * WSTR;
 #pragma unroll
                 for (int c = 0; c < 16; c += 2) {
                     const double2 v = *reinterpret_cast<const double2 *>(src + c);
                     t[c] = v.x;
                     t[c + 1] = v.y;
                 }
+                if (d == 2) {
+                    double w2[2][8];
 #pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(wsrc + c);
-                    w8[c] = v.x;
-                    w8[c + 1] = v.y;
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int c = 0; c < 8; c++) w2[b][c] = (Wk(2, 1 + b) + r * WSTR + 8 * hh)[c];
+                    band_stream_row<2>(t, w2, r, hh, lane, pan, pcs, invs + par * BN, &colbar[par][0], nullptr, bw >= 3 ? &colbar2[par][0] : nullptr, ph(k));
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+#pragma unroll
+                        for (int c = 0; c < 8; c++) (Wk(2, 1 + b) + r * WSTR + 8 * hh)[c] = w2[b][c];
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive_cta(&bar_c1[par][2]); // (2,1): the chain's next block row
+                        mbar_arrive_cta(&bar_c2[par][2]); // (2,2): the next diagonal block (role 7)
+                    }
+                } else {
+                    double w3[3][8];
+#pragma unroll
+                    for (int b = 0; b < 3; b++)
+#pragma unroll
+                        for (int c = 0; c < 8; c++) w3[b][c] = (Wk(3, 1 + b) + r * WSTR + 8 * hh)[c];
+                    band_stream_row<3>(t, w3, r, hh, lane, pan, pcs, invs + par * BN, &colbar[par][0], &colbar2[par][0], nullptr, ph(k));
+#pragma unroll
+                    for (int b = 0; b < 3; b++)
+#pragma unroll
+                        for (int c = 0; c < 8; c++) (Wk(3, 1 + b) + r * WSTR + 8 * hh)[c] = w3[b][c];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(&bar_r3[par]); // row k+3 final through this step: next step's d = 2 row
                 }
-                band_trsm16<true>(t, w8, hh, pan, pcs, invs + par * BN, hh == 0 ? pan + 32 + r : nullptr, pcs,
-                                  hh == 0 ? Lb + ((size_t)k * (bw + 2) + 2) * 256 + r * 16 : nullptr, &colbar[par][0], ph(k));
+                if (hh == 0) { // the row of P_d, row-major, into the global band storage of the factor
+                    double *grow = Lb + ((size_t)k * (bw + 2) + d) * 256 + r * 16;
 #pragma unroll
-                for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2 *>(wsrc + c) = make_double2(w8[c], w8[c + 1]);
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cta(&bar_c1[par][2]); // task (2,1) of this step is done
+                    for (int c = 0; c < 16; c++) grow[c] = pan[c * pcs + 16 * d + r];
+                }
             } else if (lane < 16) {
                 double t[16];
                 const double *src = Wk(d, 0) + lane * WSTR;
@@ -646,14 +719,14 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             const double *pan = pan0 + par * pl.pan_doubles;
             mbar_wait_cta(&bar_panel[par], ph(k)); // also keeps a warp without tasks from running ahead of the barrier phases
             // two passes: first-column tasks (dj = 1) first, the next step waits for them
-            // with BAND_STREAM_UPDATES tasks (1,1) and (2,1) are not done here: the streaming warps (roles 7 and 1) apply them
+            // with BAND_STREAM_UPDATES the block rows 1..3 are not updated here: the streaming warps (roles 7 and 1) do it
 #pragma unroll
             for (int pass = 0; pass < (BAND_STREAM_UPDATES ? 3 : 2); pass++)
 #pragma unroll
                 for (int q = 0; q < MAXV; q++) { // my virtual workers are sorted by offset, i.e. the tasks of a column come in di order
                     if (q >= nv) continue;
                     const int dj = vdj[q], di = dj + vo[q];
-                    if ((BAND_STREAM_UPDATES ? (dj < 3 ? dj - 1 : 2) : (dj == 1 ? 0 : 1)) != pass || di > nd || (BAND_STREAM_UPDATES && dj == 1 && di <= 2)) continue;
+                    if ((BAND_STREAM_UPDATES ? (dj < 3 ? dj - 1 : 2) : (dj == 1 ? 0 : 1)) != pass || di > nd || (BAND_STREAM_UPDATES && di <= 3)) continue;
                     if (di >= 2) mbar_wait_cta(&bar_p[par][di], ph(k));
                     if (dj >= 2) mbar_wait_cta(&bar_p[par][dj], ph(k));
                     BAND_TICK(1);
