@@ -1786,12 +1786,44 @@ __global__ void k_iter_begin(LMState *st) {
     st->step_valid = 0;
 }
 
-__global__ void k_ctrl(LMState *st, Accum *acc, SolverOpts opt, unsigned long long cond) {
+SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt);
+// One warp: the solver state (1.8 KB) and the accumulators are staged through shared memory with coalesced loads / stores, the
+// control logic itself runs on lane 0 — a single thread walking the structures in global memory took 5.5 us per iteration.
+__global__ void __launch_bounds__(32) k_ctrl(LMState *st_g, Accum *acc_g, SolverOpts opt, unsigned long long cond) {
     // `cond` (0 = none) is the handle of the CUDA-graph WHILE node whose body is one LM iteration
-    if (st->status != 0) {
-        if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, 0);
+    __shared__ LMState st_s;
+    __shared__ Accum acc_s;
+    static_assert(sizeof(LMState) % 8 == 0 && sizeof(Accum) % 8 == 0, "staged as 64-bit words");
+    const int lane = threadIdx.x;
+    if (st_g->status != 0) {
+        if (lane == 0 && cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, 0);
         return;
     }
+    {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(st_g);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&st_s);
+        for (int i = lane; i < (int)(sizeof(LMState) / 8); i += 32) dst[i] = src[i];
+        src = reinterpret_cast<const unsigned long long *>(acc_g);
+        dst = reinterpret_cast<unsigned long long *>(&acc_s);
+        for (int i = lane; i < (int)(sizeof(Accum) / 8); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        ctrl_step(&st_s, &acc_s, opt);
+        if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, st_s.status == 0 ? 1u : 0u);
+    }
+    __syncwarp();
+    {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&st_s);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(st_g);
+        for (int i = lane; i < (int)(sizeof(LMState) / 8); i += 32) dst[i] = src[i];
+        src = reinterpret_cast<const unsigned long long *>(&acc_s);
+        dst = reinterpret_cast<unsigned long long *>(acc_g);
+        for (int i = lane; i < (int)(sizeof(Accum) / 8); i += 32) dst[i] = src[i];
+    }
+}
+
+SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt) {
     const int it = st->iter;
     const int ti = it < 63 ? it : 63;
     const int cand = 1 - st->cur;
@@ -1873,7 +1905,6 @@ __global__ void k_ctrl(LMState *st, Accum *acc, SolverOpts opt, unsigned long lo
         st->iter += 1;
         st->step_valid = 0;
     }
-    if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, st->status == 0 ? 1u : 0u);
 }
 
 // gather the solution blocks in ABI order

@@ -1365,7 +1365,7 @@ int launch_iteration(sdv_handle *h) {
     }
     int rc = reduce_scalars(h, -2);
     if (rc != SDV_OK) return rc;
-    k_ctrl<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt, h->cond);
+    k_ctrl<<<1, 32, 0, s>>>(h->d_st, h->d_acc, h->opt, h->cond);
     h->launches++;
     return SDV_OK;
 }
