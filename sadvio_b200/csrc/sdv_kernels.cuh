@@ -1779,13 +1779,6 @@ __global__ void k_ctrl_init(LMState *st, Accum *acc, SolverOpts opt) {
     else st->iter = 1; // Ceres bumps its iteration counter before computing the step (was a kernel of its own)
 }
 
-// start of an iteration: Ceres bumps its iteration counter before computing the step
-__global__ void k_iter_begin(LMState *st) {
-    if (st->status != 0) return;
-    st->iter += 1;
-    st->step_valid = 0;
-}
-
 SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt);
 // One warp: the solver state (1.8 KB) and the accumulators are staged through shared memory with coalesced loads / stores, the
 // control logic itself runs on lane 0 — a single thread walking the structures in global memory took 5.5 us per iteration.

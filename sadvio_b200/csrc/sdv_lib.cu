@@ -1313,11 +1313,8 @@ int launch_factor_solve(sdv_handle *h) {
     return SDV_OK;
 }
 
-int trisolve_smem(const DevProblem &P) { return (int)((P.n_pad + 1024 + 32 * 33) * sizeof(double)); }
-
 int launch_iteration(sdv_handle *h) {
     const DevProblem &P = h->P;
-    const int T = P.n_pad / CH_T;
     cudaStream_t s = h->stream;
     if (cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s) != cudaSuccess) return fail(h, SDV_ERR_CUDA, "memset S");
     {
@@ -1704,7 +1701,6 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
     cudaSetDevice(h->device);
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
-    const int T = P.n_pad / CH_T;
     // a fresh linearisation at x = 0 so that every kernel has valid inputs
     int rc = set_point(h, nullptr);
     if (rc != SDV_OK) return rc;
