@@ -16,6 +16,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace sdv;
@@ -85,6 +86,8 @@ struct sdv_handle {
     // input arena
     unsigned char *d_in = nullptr, *h_in = nullptr;
     size_t in_cap = 0, in_bytes = 0, h2d_last = 0;
+    unsigned char *d_in2 = nullptr, *h_in2 = nullptr; // bulk data arena (measurements, observation indices, landmarks), packed by a helper thread
+    size_t in2_cap = 0, in2_bytes = 0;
     // scratch
     unsigned char *d_scr = nullptr;
     size_t scr_cap = 0;
@@ -265,6 +268,8 @@ int sdv_destroy(sdv_handle *h) {
     if (h->h_sol) cudaFreeHost(h->h_sol);
     if (h->d_in) cudaFree(h->d_in);
     if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->d_in2) cudaFree(h->d_in2);
+    if (h->h_in2) cudaFreeHost(h->h_in2);
     if (h->d_scr) cudaFree(h->d_scr);
     if (h->h_rb) cudaFreeHost(h->h_rb);
     if (h->d_out) cudaFree(h->d_out);
@@ -361,6 +366,46 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         for (int k = 0; k < sp->n_l2l; k++)
             if (sp->l2l_a[k] < 0 || sp->l2l_a[k] >= L || sp->l2l_b[k] < 0 || sp->l2l_b[k] >= L || sp->l2l_a[k] == sp->l2l_b[k])
                 return fail(h, SDV_ERR_INVALID_ARGUMENT, "l2l landmark out of range");
+    }
+    cudaSetDevice(h->device);
+    // ---- bulk data arena: the arrays that are pure copies (78 % of the bytes at C3) have a layout that depends on the sizes
+    //      only, so a helper thread packs them into pinned memory while this thread validates the indices and derives the
+    //      structure of the reduced system; both arenas then go to the device with one asynchronous copy each.
+    const int mplanes = kind == SDV_FACTOR_ANGULAR ? 3 : 2;
+    Arena A2;
+    const size_t q_om = A2.add(sizeof(double) * mplanes * std::max(O, 1)), q_ol = A2.add(4 * std::max(O, 1)), q_ofc = A2.add(4 * std::max(O, 1));
+    const size_t q_lt = A2.add(sizeof(double) * 3 * std::max(L, 1)), q_ow = w->obs_sigma ? A2.add(sizeof(double) * std::max(O, 1)) : 0;
+    {
+        int rc2;
+        if ((rc2 = ensure(h, &h->h_in2, &h->in2_cap, A2.size, true)) != SDV_OK) return rc2;
+        if (A2.size > h->in2_bytes) {
+            if (h->d_in2) cudaFree(h->d_in2);
+            h->d_in2 = nullptr;
+            CK(cudaMalloc((void **)&h->d_in2, A2.size * 2));
+            h->in2_bytes = A2.size * 2;
+        }
+    }
+    struct Joiner {
+        std::thread t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } packer;
+    {
+        unsigned char *hb2 = h->h_in2;
+        packer.t = std::thread([=] {
+            if (O) {
+                std::memcpy(hb2 + q_om, kind == SDV_FACTOR_ANGULAR ? (const void *)w->obs_bearing : (const void *)w->obs_uv, sizeof(double) * (size_t)mplanes * O);
+                std::memcpy(hb2 + q_ol, w->obs_lmk, 4 * (size_t)O);
+                int *fc = reinterpret_cast<int *>(hb2 + q_ofc);
+                for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o]; // validated by the other thread; only used if that passes
+                if (w->obs_sigma) {
+                    double *ow = reinterpret_cast<double *>(hb2 + q_ow);
+                    for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
+                }
+            }
+            if (L > 0) std::memcpy(hb2 + q_lt, w->lmk_t, sizeof(double) * 3 * (size_t)L);
+        });
     }
     // one pass over the observations: range checks, landmark-major order, CSR pointer per landmark, frames in use
     std::vector<int> &lmk_ptr = h->tmp_lmk_ptr;
@@ -780,14 +825,10 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     size_t o_hp = A.add(F), o_Tp = A.add(D * 12 * F), o_ip = A.add(D * 6 * F);
     size_t o_pc = A.add(4 * F), o_vc = A.add(4 * F);
     size_t o_Ts = A.add(D * 12 * C), o_K = A.add(D * 4 * C), o_cw = A.add(D * C);
-    size_t o_lt = A.add(D * 3 * std::max(L, 1)), o_lc = A.add(4 * std::max(L, 1));
+    size_t o_lc = A.add(4 * std::max(L, 1));
     size_t o_tnz = A.add(4 * tile_nz.size());
     size_t o_chk = A.add(4 * chunk_ptr.size());
     size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(nslotobs, 1));
-    size_t o_ol = A.add(4 * std::max(O, 1)), o_ofc = A.add(4 * std::max(O, 1));
-    const int mplanes = kind == SDV_FACTOR_ANGULAR ? 3 : 2;
-    size_t o_om = A.add(D * mplanes * std::max(O, 1));
-    size_t o_ow = w->obs_sigma ? A.add(D * std::max(O, 1)) : 0;
     size_t o_ii = A.add(4 * std::max(Pn, 1)), o_ij = A.add(4 * std::max(Pn, 1));
     size_t o_idt = A.add(D * std::max(Pn, 1)), o_idR = A.add(D * 9 * std::max(Pn, 1)), o_idv = A.add(D * 3 * std::max(Pn, 1)),
            o_idp = A.add(D * 3 * std::max(Pn, 1)), o_icov = A.add(D * 81 * std::max(Pn, 1));
@@ -856,25 +897,12 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         double sigma = kind == SDV_FACTOR_ANGULAR ? 1.5 / focal : 1.0; // …Analytic.cpp:283 ; BA…Analytic.h:47
         at<double>(hb, o_cw)[c] = 1.0 / sigma;
     }
-    if (L > 0) {
-        std::memcpy(hb + o_lt, w->lmk_t, D * 3 * L);
-        std::memcpy(hb + o_lc, lmk_col.data(), 4 * L);
-    }
+    if (L > 0) std::memcpy(hb + o_lc, lmk_col.data(), 4 * L);
     std::memcpy(hb + o_sp, slot_ptr.data(), 4 * (L + 1));
     if (nslots) std::memcpy(hb + o_sf, slot_frame.data(), 4 * nslots);
     std::memcpy(hb + o_sop, slot_obs_ptr.data(), 4 * (nslots + 1));
     if (nslotobs) std::memcpy(hb + o_so, slot_obs.data(), 4 * (size_t)nslotobs);
-    if (O) {
-        std::memcpy(hb + o_ol, w->obs_lmk, 4 * O);
-        int *fc = at<int>(hb, o_ofc);
-        for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o];
-        // measurements stay array-of-structs (a warp still reads one contiguous 768 / 512-byte span): no host-side transposition
-        std::memcpy(hb + o_om, kind == SDV_FACTOR_ANGULAR ? w->obs_bearing : w->obs_uv, D * (size_t)mplanes * O);
-        if (w->obs_sigma) {
-            double *ow = at<double>(hb, o_ow);
-            for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
-        }
-    }
+    // (observation indices, measurements — array-of-structs as the caller provides them — and landmarks: bulk data arena)
     if (Pn) {
         std::memcpy(hb + o_ii, w->imu_i, 4 * Pn);
         std::memcpy(hb + o_ij, w->imu_j, 4 * Pn);
@@ -929,8 +957,10 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     auto t_pack1 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
+    packer.t.join(); // the bulk data arena is packed
+    CK(cudaMemcpyAsync(h->d_in2, h->h_in2, A2.size, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
-    h->h2d_last = A.size;
+    h->h2d_last = A.size + A2.size;
     unsigned char *db = h->d_in;
 
     // ---- scratch arena (device only)
@@ -982,13 +1012,13 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     P.T_prior = at<double>(db, o_Tp); P.inf_prior = at<double>(db, o_ip);
     P.pose_col = at<int>(db, o_pc); P.vb_col = at<int>(db, o_vc);
     P.T_s_f = at<double>(db, o_Ts); P.K = at<double>(db, o_K); P.cam_w = at<double>(db, o_cw);
-    P.lmk_t = at<double>(db, o_lt); P.lmk_col = at<int>(db, o_lc);
+    P.lmk_t = at<double>(h->d_in2, q_lt); P.lmk_col = at<int>(db, o_lc);
     P.tile_nz = at<uint32_t>(db, o_tnz);
     P.chunk_ptr = at<int>(db, o_chk);
     P.nchunks = nchunks;
     P.slot_ptr = at<int>(db, o_sp); P.slot_frame = at<int>(db, o_sf); P.slot_obs_ptr = at<int>(db, o_sop); P.slot_obs = at<int>(db, o_so);
-    P.obs_lmk = at<int>(db, o_ol); P.obs_fc = at<int>(db, o_ofc); P.obs_meas = at<double>(db, o_om);
-    P.obs_w = w->obs_sigma ? at<double>(db, o_ow) : nullptr;
+    P.obs_lmk = at<int>(h->d_in2, q_ol); P.obs_fc = at<int>(h->d_in2, q_ofc); P.obs_meas = at<double>(h->d_in2, q_om);
+    P.obs_w = w->obs_sigma ? at<double>(h->d_in2, q_ow) : nullptr;
     P.imu_i = at<int>(db, o_ii); P.imu_j = at<int>(db, o_ij); P.imu_dt = at<double>(db, o_idt); P.imu_dR = at<double>(db, o_idR);
     P.imu_dv = at<double>(db, o_idv); P.imu_dp = at<double>(db, o_idp); P.imu_cov = at<double>(db, o_icov);
     P.imu_J_dR_bg = at<double>(db, o_j1); P.imu_J_dv_ba = at<double>(db, o_j2); P.imu_J_dv_bg = at<double>(db, o_j3);
