@@ -393,7 +393,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     } packer;
     {
         unsigned char *hb2 = h->h_in2;
-        packer.t = std::thread([=] {
+        auto pack_bulk = [=] {
             if (O) {
                 std::memcpy(hb2 + q_om, kind == SDV_FACTOR_ANGULAR ? (const void *)w->obs_bearing : (const void *)w->obs_uv, sizeof(double) * (size_t)mplanes * O);
                 std::memcpy(hb2 + q_ol, w->obs_lmk, 4 * (size_t)O);
@@ -405,7 +405,12 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
                 }
             }
             if (L > 0) std::memcpy(hb2 + q_lt, w->lmk_t, sizeof(double) * 3 * (size_t)L);
-        });
+        };
+        try {
+            packer.t = std::thread(pack_bulk);
+        } catch (...) { // no thread available: pack here (no exception may cross the C ABI)
+            pack_bulk();
+        }
     }
     // one pass over the observations: range checks, landmark-major order, CSR pointer per landmark, frames in use
     std::vector<int> &lmk_ptr = h->tmp_lmk_ptr;
@@ -957,7 +962,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     auto t_pack1 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
-    packer.t.join(); // the bulk data arena is packed
+    if (packer.t.joinable()) packer.t.join(); // the bulk data arena is packed
     CK(cudaMemcpyAsync(h->d_in2, h->h_in2, A2.size, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
     h->h2d_last = A.size + A2.size;
