@@ -15,7 +15,7 @@ from sadvio_b200 import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
-_SRCS = ["sdv_oracle.cpp", "factors.hpp", "smallmat.hpp", os.path.join("..", "include", "sdv.h")]
+_SRCS = ["sdv_oracle.cpp", "factors.hpp", "marg.hpp", "smallmat.hpp", os.path.join("..", "include", "sdv.h")]
 
 
 def build(force: bool = False) -> str:
@@ -43,6 +43,8 @@ def lib() -> C.CDLL:
         _lib.orc_eval_imu.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp, dp]
         _lib.orc_reduced_system.argtypes = [C.POINTER(abi.SdvWindow), C.c_int, C.c_int, C.c_int, C.c_double, dp, dp, C.POINTER(C.c_int)]
         _lib.orc_cost.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvDelta), dp, dp]
+        _lib.orc_schur_prior.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, C.POINTER(C.c_int), dp, dp, dp, dp]
+        _lib.orc_schur_prior.restype = C.c_int
         for name in ("orc_exp_so3", "orc_log_so3", "orc_right_jacobian"):
             getattr(_lib, name).argtypes = [dp, dp]
         _lib.orc_angular_eval.argtypes = [dp, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp]
@@ -221,3 +223,20 @@ def bias_delta_correction(state, d_ba, d_bg):
     s = _a(state, 169).copy()
     lib().orc_bias_delta_correction(_p(s), _p(_a(d_ba, 3)), _p(_a(d_bg, 3)))
     return s
+
+
+def schur_prior(A, b, m: int, eps: float = 1e-12):
+    """Dense core of the reference's marginal-prior construction (marginalization.cpp:213-265, 318-342, 516-530): the first m
+    parameters of the information matrix A / gradient b are marginalised.  Returns None when the reference returns false
+    (fewer than 4 kept parameters), else a dict with Ak, bk, U, Lambda, J (= Lambda^1/2 U^T) and r0 (= -Lambda^-1/2 U^T bk)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    N = A.shape[0]
+    n = N - m
+    Ak, bk, U, Lam, J, r0 = np.zeros((max(n, 1), max(n, 1))), np.zeros(max(n, 1)), np.zeros(max(n, 1) ** 2), np.zeros(max(n, 1)), np.zeros(max(n, 1) ** 2), np.zeros(max(n, 1))
+    nf = C.c_int(0)
+    ok = lib().orc_schur_prior(m, n, _p(A), _p(b), eps, _p(Ak), _p(bk), C.byref(nf), _p(U), _p(Lam), _p(J), _p(r0))
+    if not ok:
+        return None
+    k = nf.value
+    return {"Ak": Ak, "bk": bk, "n_full": k, "U": U[:n * k].reshape(n, k).copy(), "Lambda": Lam[:k].copy(), "J": J[:k * n].reshape(k, n).copy(), "r0": r0[:k].copy()}

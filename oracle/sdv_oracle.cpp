@@ -15,6 +15,7 @@
 //     visual factors parity with a real Ceres build is UNPINNED (no Ceres/Eigen in this image).
 #include "../include/sdv.h"
 #include "factors.hpp"
+#include "marg.hpp"
 
 #include <array>
 #include <atomic>
@@ -1375,4 +1376,23 @@ int orc_bias_delta_correction(double *state, const double *d_ba, const double *d
 }
 
 int orc_abi_version(void) { return SDV_ABI_VERSION; }
+}
+
+extern "C" {
+// Dense core of the marginal-prior construction (marg.hpp).  Returns 1 on success, 0 when the reference returns false.
+// Output buffers must hold n*n, n, n*n, n, n*n, n doubles; *n_full receives the rank.
+int orc_schur_prior(int m, int n, const double *A, const double *b, double eps, double *Ak, double *bk, int *n_full, double *U, double *Lambda,
+                    double *Jm, double *r0) {
+    std::vector<double> vAk, vbk, vU, vL, vJ, vr;
+    int nf = 0;
+    if (!orc::schur_prior(m, n, A, b, eps, vAk, vbk, nf, vU, vL, vJ, vr)) return 0;
+    std::copy(vAk.begin(), vAk.end(), Ak);
+    std::copy(vbk.begin(), vbk.end(), bk);
+    std::copy(vU.begin(), vU.end(), U);
+    std::copy(vL.begin(), vL.end(), Lambda);
+    std::copy(vJ.begin(), vJ.end(), Jm);
+    std::copy(vr.begin(), vr.end(), r0);
+    *n_full = nf;
+    return 1;
+}
 }
