@@ -1,0 +1,150 @@
+"""TEST INFRASTRUCTURE (oracle/README.md) — groundwork for SURVEY.md §8 row a15, no CUDA path yet.
+
+Restatement, on the flattened window of the C ABI, of the FIRST marginalisation of a VIO window (no previous prior):
+
+    Marginalization::preMarginalize              cpp/src/optimizers/marginalization.cpp:23-143
+    AngularAdjustmentCERESAnalytic::marginalize  cpp/src/optimizers/AngularAdjustmentCERESAnalytic.cpp:488-739
+    computeInformationAndGradient                cpp/src/optimizers/marginalization.cpp:145-211
+    computeSchurComplement / rankRevealling / computeJacobiansAndResiduals   (oracle/marg.hpp)
+
+frame0 = the oldest keyframe of the window (last index: frames are ordered newest -> oldest, amap.h:28-32), frame1 = the next
+one.  The factors come from the oracle's functor restatements (oracle.angular_eval, imu_factor_eval, pose_prior_eval)."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle
+from sadvio_b200 import abi
+
+
+def pre_marginalize(win: abi.Window):
+    """marginalization.cpp:23-143 for point landmarks: returns (marg, keep, idx) — landmark ids to marginalise / to keep (in
+    landmark order, as getLandmarks() is walked) and the parameter index map {('f0'|'f1'|landmark id): first column}."""
+    F = win.n_frames
+    f0 = F - 1
+    marg, keep = [], []
+    lm_of_f0 = np.unique(win.obs_lmk[win.obs_frame == f0])
+    for l in lm_of_f0:
+        sel = win.obs_lmk == l
+        num_cam = int(np.count_nonzero(sel & (win.obs_frame == f0)))      # :58-71
+        lonely = not np.any(sel & (win.obs_frame != f0))
+        if num_cam != 2:                                                   # no stereo pair, no prior: ignored (:74-77)
+            continue
+        (marg if lonely else keep).append(int(l))                          # :80-89
+    idx = {"f0": 0}
+    last = 6 + (9 if win.vio else 0)                                       # :40-48
+    for l in marg:                                                         # :93-98
+        idx[l] = last
+        last += 3
+    m = last
+    n = 0
+    if win.vio:                                                            # :101-106
+        idx["f1"] = last
+        last += 15
+        n += 15
+    for l in keep:                                                         # :109-114
+        idx[l] = last
+        last += 3
+        n += 3
+    return marg, keep, idx, m, n
+
+
+def information(win: abi.Window, marg, keep, idx, m, n):
+    """The marginalisation blocks of …Analytic.cpp:504-687 evaluated at the current state and accumulated as in
+    marginalization.cpp:145-211.  Returns A [(m+n)^2], b [m+n]."""
+    F = win.n_frames
+    f0, f1 = F - 1, F - 2
+    N = m + n
+    A, b = np.zeros((N, N)), np.zeros(N)
+
+    def add(blocks, r):
+        for i, (ci, Ji) in enumerate(blocks):
+            for cj, Jj in blocks[i:]:
+                A[ci:ci + Ji.shape[1], cj:cj + Jj.shape[1]] += Ji.T @ Jj
+                if cj != ci:
+                    A[cj:cj + Jj.shape[1], ci:ci + Ji.shape[1]] = A[ci:ci + Ji.shape[1], cj:cj + Jj.shape[1]].T
+            b[ci:ci + Ji.shape[1]] += Ji.T @ r
+
+    if win.vio:
+        p = int(np.flatnonzero((win.imu_i == f0) & (win.imu_j == f1))[0])
+        pre = oracle.pack_preint(win.imu_dR[p], win.imu_dv[p], win.imu_dp[p], win.imu_cov[p], win.imu_J_dR_bg[p], win.imu_J_dv_ba[p],
+                                 win.imu_J_dv_bg[p], win.imu_J_dp_ba[p], win.imu_J_dp_bg[p])
+        r, J = oracle.imu_factor_eval(win.T_f_w[f0], win.T_f_w[f1], win.v[f0], win.v[f1], float(win.imu_dt[p]), pre)
+        # parameter blocks in the order of …Analytic.cpp:522-537: pose0, pose1, v0, v1, dba0, dbg0
+        add([(idx["f0"], J[:, 0:6]), (idx["f1"], J[:, 6:12]), (idx["f0"] + 6, J[:, 12:15]), (idx["f1"] + 6, J[:, 15:18]),
+             (idx["f0"] + 9, J[:, 18:21]), (idx["f0"] + 12, J[:, 21:24])], r)
+        # IMUBiasFactor (residuals.hpp:252-296), blocks ba0, bg0, ba1, bg1 (…Analytic.cpp:549-556)
+        dt = float(win.imu_dt[p])
+        wa, wg = 1.0 / (np.sqrt(dt) * float(win.imu_sigma_ba[p])), 1.0 / (np.sqrt(dt) * float(win.imu_sigma_bg[p]))
+        rb = np.concatenate([(win.ba[f1] - win.ba[f0]) * wa, (win.bg[f1] - win.bg[f0]) * wg])
+        Za, Zg = np.zeros((6, 3)), np.zeros((6, 3))
+        Za[0:3] = np.eye(3) * wa
+        Zg[3:6] = np.eye(3) * wg
+        add([(idx["f0"] + 9, -Za), (idx["f0"] + 12, -Zg), (idx["f1"] + 9, Za), (idx["f1"] + 12, Zg)], rb)
+    for l in list(keep) + list(marg):                                      # …Analytic.cpp:565-629, sigma = 1 / focal
+        for o in np.flatnonzero((win.obs_lmk == l) & (win.obs_frame == f0)):
+            c = int(win.obs_cam[o])
+            focal = 0.5 * (win.K[c][0] + win.K[c][1])
+            r, J6, J3 = oracle.angular_eval(win.obs_bearing[o], win.T_s_f[c], win.T_f_w[f0], win.lmk_t[l], 1.0 / focal)
+            add([(idx["f0"], J6), (idx[l], J3)], r)
+    for key, f in (("f0", f0), ("f1", f1)):                                # …Analytic.cpp:664-687
+        if win.has_prior is not None and win.has_prior[f] and key in idx:
+            r, J = oracle.pose_prior_eval(win.T_f_w[f], win.T_prior[f], win.inf_prior[f])
+            add([(idx[key], J)], r)
+    return A, b
+
+
+def marginalize_oldest(win: abi.Window, eps: float = 1e-12):
+    """Returns (prior, info): prior = abi.DensePrior over (frame1's 15 parameters, kept landmarks) expressed for the window
+    WITHOUT its oldest keyframe, or None when the reference's marginalize() returns false; info = the intermediate results."""
+    assert win.factor_kind == 0, "AngularAdjustmentCERESAnalytic::marginalize uses bearing factors"
+    marg, keep, idx, m, n = pre_marginalize(win)
+    A, b = information(win, marg, keep, idx, m, n)
+    out = oracle.schur_prior(A, b, m, eps)
+    if out is None:                                                        # …Analytic.cpp:690-695
+        return None, {"marg": marg, "keep": keep, "idx": idx, "m": m, "n": n, "A": A, "b": b}
+    frame = win.n_frames - 2 if win.vio else -1
+    first = 15 if win.vio else 0
+    prior = abi.DensePrior(J=np.ascontiguousarray(out["J"]), r0=out["r0"].copy(), frame=frame, frame_col=0,
+                           keep_lmk=np.asarray(keep, dtype=np.int32),
+                           keep_col=np.asarray([first + 3 * k for k in range(len(keep))], dtype=np.int32))
+    out.update({"marg": marg, "keep": keep, "idx": idx, "m": m, "n": n, "A": A, "b": b})
+    return prior, out
+
+
+def drop_oldest_frame(win: abi.Window, prior: abi.DensePrior | None) -> abi.Window:
+    """The window the back end optimises next: the oldest keyframe is gone (with its observations, its IMU pair and the
+    landmarks only it saw), the marginal prior takes its place; no keyframe is held constant any more."""
+    import copy
+
+    F = win.n_frames
+    f0 = F - 1
+    keep_obs = win.obs_frame != f0
+    lm_alive = np.zeros(win.n_lmks, dtype=bool)
+    lm_alive[np.unique(win.obs_lmk[keep_obs])] = True
+    remap = np.cumsum(lm_alive) - 1
+    w = copy.copy(win)
+    w.meta = {}
+    w.n_fixed = 0
+    w.T_f_w = win.T_f_w[:f0].copy()
+    for k in ("v", "ba", "bg", "has_imu", "has_prior", "T_prior", "inf_prior"):
+        a = getattr(win, k)
+        setattr(w, k, None if a is None else a[:f0].copy())
+    w.lmk_t = win.lmk_t[lm_alive].copy()
+    w.obs_lmk = remap[win.obs_lmk[keep_obs]].astype(np.int32)
+    w.obs_frame = win.obs_frame[keep_obs].copy()
+    w.obs_cam = win.obs_cam[keep_obs].copy()
+    for k in ("obs_bearing", "obs_uv", "obs_sigma"):
+        a = getattr(win, k)
+        setattr(w, k, None if a is None else a[keep_obs].copy())
+    if win.imu_i is not None:
+        keep_imu = (win.imu_i != f0) & (win.imu_j != f0)
+        for k in ("imu_i", "imu_j", "imu_dt", "imu_dR", "imu_dv", "imu_dp", "imu_cov", "imu_J_dR_bg", "imu_J_dv_ba", "imu_J_dv_bg",
+                  "imu_J_dp_ba", "imu_J_dp_bg", "imu_sigma_ba", "imu_sigma_bg"):
+            setattr(w, k, getattr(win, k)[keep_imu].copy())
+    w.dense_prior = None
+    if prior is not None:
+        assert np.all(lm_alive[prior.keep_lmk])
+        w.dense_prior = abi.DensePrior(J=prior.J, r0=prior.r0, frame=prior.frame, frame_col=prior.frame_col,
+                                       keep_lmk=remap[prior.keep_lmk].astype(np.int32), keep_col=prior.keep_col)
+    return w.normalise()
