@@ -390,3 +390,17 @@ def test_full_solve_c5_band_kernel(solver):
     g, o = solve_both(solver, win)
     assert_same_solution(g, o)
     assert_same_states(win, g[1], o[1])
+
+
+def test_next_window_with_marginal_prior_from_the_oracle(solver):
+    """The prior the restated marginalisation driver (oracle/marginalize.py, row a15 groundwork) produces for the window without
+    its oldest keyframe — 15 + 3 x 43 columns, rank-deficient by the 6-dof gauge — through the CUDA dense-prior path (a10)."""
+    from oracle import marginalize
+
+    win = synth.make_window("small")
+    prior, info = marginalize.marginalize_oldest(win)
+    w2 = marginalize.drop_oldest_frame(win, prior)
+    assert w2.dense_prior is not None and w2.dense_prior.J.shape == (info["n_full"], 15 + 3 * len(info["keep"]))
+    g, o = solve_both(solver, w2)
+    assert_same_solution(g, o)
+    assert_same_states(w2, g[1], o[1])
