@@ -148,3 +148,59 @@ def drop_oldest_frame(win: abi.Window, prior: abi.DensePrior | None) -> abi.Wind
         w.dense_prior = abi.DensePrior(J=prior.J, r0=prior.r0, frame=prior.frame, frame_col=prior.frame_col,
                                        keep_lmk=remap[prior.keep_lmk].astype(np.int32), keep_col=prior.keep_col)
     return w.normalise()
+
+
+def _sym_sqrt(M, eps):
+    """V diag(sqrt(max(w, 0 if w <= eps))) V^T — the SelfAdjointEigenSolver idiom of marginalization.cpp:379-385."""
+    w, V = np.linalg.eigh(0.5 * (M + M.T))
+    return (V * np.sqrt(np.where(w > eps, w, 0.0))) @ V.T
+
+
+def sparsify_vio(win: abi.Window, info: dict, eps: float = 1e-12) -> abi.SparsePrior:
+    """Marginalization::sparsifyVIO (marginalization.cpp:362-411): the dense marginal over (frame1, kept landmarks) is replaced by
+    one absolute factor on frame1 (IMUPriordx) and one relative frame-to-landmark factor per kept landmark
+    (PoseToLandmarkFactor), each with the information of its own measurement function under the marginal covariance
+    U Sigma U^T.  Landmark indices refer to `win`; the prior values of the frame are its current state, as the window wiring
+    does (AngularAdjustmentCERESAnalytic.cpp:391-397)."""
+    f1 = win.n_frames - 2
+    n, U, Sigma = info["n"], info["U"], 1.0 / info["Lambda"]
+    T = win.T_f_w[f1].reshape(3, 4)
+    R, t = T[:, :3], T[:, 3]
+    t_skew = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    keep = info["keep"]
+    deltas, sqrts = [], []
+    for k, l in enumerate(keep):
+        c = 15 + 3 * k                                   # the index map after the shift by m (marginalization.cpp:251-256)
+        J = np.zeros((3, n))
+        J[:, c:c + 3] = R                                # :372
+        J[:, 0:3] = -R @ t_skew                          # :373
+        J[:, 3:6] = R                                    # :374
+        Jt = J @ U
+        inf = np.linalg.inv(Jt @ np.diag(Sigma) @ Jt.T)  # :377
+        sqrts.append(_sym_sqrt(inf, eps).reshape(9))
+        deltas.append(R @ win.lmk_t[l] + t)              # t_f_lmk, :387
+    J = np.zeros((15, n))
+    J[:, 0:15] = np.eye(15)                              # :393
+    J[0:3, 0:3] = R                                      # :394
+    J[0:3, 3:6] = R                                      # :395  (as written in the reference)
+    J[3:6, 3:6] = R                                      # :396
+    Jt = J @ U
+    inf15 = np.linalg.inv(Jt @ np.diag(Sigma) @ Jt.T)
+    return abi.SparsePrior(has_imu_prior=True, frame=f1, T_prior=win.T_f_w[f1].copy(), v_prior=win.v[f1].copy(), ba_prior=win.ba[f1].copy(),
+                           bg_prior=win.bg[f1].copy(), imu_sqrt_inf=_sym_sqrt(inf15, eps).reshape(225),
+                           p2l_lmk=np.asarray(keep, dtype=np.int32), p2l_delta=np.asarray(deltas), p2l_sqrt_inf=np.asarray(sqrts))
+
+
+def with_sparse_prior(win: abi.Window, sp: abi.SparsePrior) -> abi.Window:
+    """drop_oldest_frame + the sparsified prior (landmark indices remapped to the shorter window)."""
+    import copy
+
+    w2 = drop_oldest_frame(win, None)
+    keep_obs = win.obs_frame != win.n_frames - 1
+    alive = np.zeros(win.n_lmks, dtype=bool)
+    alive[np.unique(win.obs_lmk[keep_obs])] = True
+    remap = np.cumsum(alive) - 1
+    sp2 = copy.copy(sp)
+    sp2.p2l_lmk = remap[sp.p2l_lmk].astype(np.int32)
+    w2.sparse_prior = sp2
+    return w2.normalise()

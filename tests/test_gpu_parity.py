@@ -404,3 +404,16 @@ def test_next_window_with_marginal_prior_from_the_oracle(solver):
     g, o = solve_both(solver, w2)
     assert_same_solution(g, o)
     assert_same_states(w2, g[1], o[1])
+
+
+def test_next_window_with_sparsified_prior_from_the_oracle(solver):
+    """sparsifyVIO restated by the oracle (oracle/marginalize.py): IMUPriordx on the oldest remaining keyframe + 43
+    PoseToLandmark factors with the information the marginal covariance gives them, through the CUDA sparse-prior path (a11)."""
+    from oracle import marginalize
+
+    win = synth.make_window("small")
+    prior, info = marginalize.marginalize_oldest(win)
+    w2 = marginalize.with_sparse_prior(win, marginalize.sparsify_vio(win, info))
+    g, o = solve_both(solver, w2)
+    assert_same_solution(g, o)
+    assert_same_states(w2, g[1], o[1])

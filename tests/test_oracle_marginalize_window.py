@@ -153,3 +153,32 @@ def test_marginalising_after_the_solve():
     rc, d2, st2 = oracle.solve_window(w2, cfg, nthreads=4)
     assert rc == 0 and st2["final_cost"] <= st2["initial_cost"]
     assert float(np.abs(d2.dpose[win.n_frames - 2]).max()) < 0.1
+
+
+def test_sparsified_vio_prior(small):
+    """Marginalization::sparsifyVIO restated (oracle/marginalize.py): every factor carries the information of its own
+    measurement function under the marginal covariance; the shorter window solves with the sparsified prior."""
+    win, prior, info = small
+    sp = marginalize.sparsify_vio(win, info)
+    n_keep = len(info["keep"])
+    assert sp.has_imu_prior and sp.frame == win.n_frames - 2
+    assert sp.p2l_lmk.shape == (n_keep,) and sp.p2l_delta.shape == (n_keep, 3) and sp.p2l_sqrt_inf.shape == (n_keep, 9)
+    Sigma_k = info["U"] @ np.diag(1.0 / info["Lambda"]) @ info["U"].T        # marginalization.cpp:262
+    T = win.T_f_w[win.n_frames - 2].reshape(3, 4)
+    for k in (0, n_keep // 2, n_keep - 1):
+        S = sp.p2l_sqrt_inf[k].reshape(3, 3)
+        assert np.abs(S - S.T).max() < 1e-9 * np.abs(S).max() and np.all(np.linalg.eigvalsh(S) > 0)
+        # information of h(x) = R (p + dp) + t + (-R [t]x dw + R dt) under Sigma_k
+        c = 15 + 3 * k
+        J = np.zeros((3, info["n"]))
+        J[:, c:c + 3] = T[:, :3]
+        tx = np.array([[0, -T[2, 3], T[1, 3]], [T[2, 3], 0, -T[0, 3]], [-T[1, 3], T[0, 3], 0]])
+        J[:, 0:3], J[:, 3:6] = -T[:, :3] @ tx, T[:, :3]
+        assert np.abs(S @ S - np.linalg.inv(J @ Sigma_k @ J.T)).max() <= 1e-6 * np.abs(S @ S).max()
+        assert np.allclose(sp.p2l_delta[k], T[:, :3] @ win.lmk_t[info["keep"][k]] + T[:, 3])
+    S15 = sp.imu_sqrt_inf.reshape(15, 15)
+    w15 = np.linalg.eigvalsh(S15)   # positive semi-definite: eigenvalues at or below the reference's threshold are zeroed (:401)
+    assert np.abs(S15 - S15.T).max() < 1e-9 * np.abs(S15).max() and w15[0] > -1e-9 * w15[-1] and w15[-1] > 0
+    w2 = marginalize.with_sparse_prior(win, sp)
+    rc, d2, st = oracle.solve_window(w2, nthreads=4)
+    assert rc == 0 and st["final_cost"] <= st["initial_cost"]
