@@ -191,6 +191,71 @@ def sparsify_vio(win: abi.Window, info: dict, eps: float = 1e-12) -> abi.SparseP
                            p2l_lmk=np.asarray(keep, dtype=np.int32), p2l_delta=np.asarray(deltas), p2l_sqrt_inf=np.asarray(sqrts))
 
 
+def sparsify_vo(win: abi.Window, info: dict, eps: float = 1e-12) -> abi.SparsePrior:
+    """Marginalization::sparsifyVO (marginalization.cpp:410-514): the dense marginal over the kept landmarks is replaced by a
+    chain — the kept landmarks are re-ordered greedily by the coupling |trace(Ak_kl)| of their information blocks
+    (computeOffDiag, :304-316), the landmark with the smallest entropy (:267-274) gets a unary Landmark3DPrior and every
+    consecutive pair of the chain a LandmarkToLandmarkFactor, each with the information of its own measurement function under
+    the marginal covariance.  Landmarks the greedy walk never reaches drop out of the prior, as in the reference (:462-463).
+    Landmark indices refer to `win`."""
+    n, U, Sigma, Ak = info["n"], info["U"], 1.0 / info["Lambda"], info["Ak"]
+    keep = list(info["keep"])
+    K = len(keep)
+    if n == 0 or K < 2:
+        return None
+    first = 15 if win.vio else 0
+    col = {l: first + 3 * k for k, l in enumerate(keep)}                  # the index map after the shift by m (:251-256)
+    mi = np.zeros((K, K))
+    for k in range(K):                                                    # :420-431
+        for l in range(K):
+            if k == l or mi[k, l] != 0:
+                continue
+            mi[k, l] = mi[l, k] = abs(np.trace(Ak[col[keep[k]]:col[keep[k]] + 3, col[keep[l]]:col[keep[l]] + 3]))
+    # Eigen's maxCoeff visits a column-major matrix column by column and keeps the first maximum (:439)
+    flat = int(np.argmax(mi.T.reshape(-1)))
+    max_col, max_row = divmod(flat, K)
+    order = [keep[max_row], keep[max_col]]                                # :440-441
+    mi[:, max_row] = 0                                                    # :444-446
+    mi[max_row, :] = 0
+    mi[:, max_col] = 0
+    cur = max_col
+    while True:                                                           # :451-459
+        c = int(np.argmax(mi[cur]))
+        if mi[cur, c] == 0:
+            break
+        order.append(keep[c])
+        mi[cur, :] = 0
+        mi[:, c] = 0
+        cur = c
+    Sigma_k = U @ np.diag(Sigma) @ U.T                                    # :262
+    # :273 — std::pow(2 pi e, size / 2) with the INTEGER division the reference writes (3 / 2 = 1)
+    ent = [np.log((2 * np.pi * np.e) ** (3 // 2) * np.linalg.det(Sigma_k[col[l]:col[l] + 3, col[l]:col[l] + 3])) for l in order]
+    with_prior = order[int(np.argmin(ent))]                               # :469-470
+
+    def sqrt_inf_of(J):                                                   # :481-487, :501-507
+        Jt = J @ U
+        w, V = np.linalg.eigh(Jt @ np.diag(Sigma) @ Jt.T)
+        s = np.where(w > eps, 1.0 / np.where(w > eps, w, 1.0), 0.0)
+        return (V * np.sqrt(s)) @ V.T
+
+    J = np.zeros((3, n))
+    J[:, col[with_prior]:col[with_prior] + 3] = np.eye(3)                 # :477-478
+    S0 = sqrt_inf_of(J)
+    a, b, deltas, sqrts = [], [], [], []
+    for k in range(len(order) - 1):                                       # :493-511
+        lk, lk1 = order[k], order[k + 1]
+        J = np.zeros((3, n))
+        J[:, col[lk]:col[lk] + 3] = np.eye(3)
+        J[:, col[lk1]:col[lk1] + 3] = -np.eye(3)
+        sqrts.append(sqrt_inf_of(J).reshape(9))
+        deltas.append(win.lmk_t[lk] - win.lmk_t[lk1])
+        a.append(lk)
+        b.append(lk1)
+    return abi.SparsePrior(has_lmk_prior=True, lmk0=int(with_prior), lmk_prior=win.lmk_t[with_prior].copy(), lmk_sqrt_inf=S0.reshape(9),
+                           l2l_a=np.asarray(a, dtype=np.int32), l2l_b=np.asarray(b, dtype=np.int32), l2l_delta=np.asarray(deltas),
+                           l2l_sqrt_inf=np.asarray(sqrts))
+
+
 def with_sparse_prior(win: abi.Window, sp: abi.SparsePrior) -> abi.Window:
     """drop_oldest_frame + the sparsified prior (landmark indices remapped to the shorter window)."""
     import copy
@@ -201,6 +266,11 @@ def with_sparse_prior(win: abi.Window, sp: abi.SparsePrior) -> abi.Window:
     alive[np.unique(win.obs_lmk[keep_obs])] = True
     remap = np.cumsum(alive) - 1
     sp2 = copy.copy(sp)
-    sp2.p2l_lmk = remap[sp.p2l_lmk].astype(np.int32)
+    if sp.p2l_lmk is not None and len(sp.p2l_lmk):
+        sp2.p2l_lmk = remap[sp.p2l_lmk].astype(np.int32)
+    if sp.has_lmk_prior:
+        sp2.lmk0 = int(remap[sp.lmk0])
+    if sp.l2l_a is not None and len(sp.l2l_a):
+        sp2.l2l_a, sp2.l2l_b = remap[sp.l2l_a].astype(np.int32), remap[sp.l2l_b].astype(np.int32)
     w2.sparse_prior = sp2
     return w2.normalise()

@@ -417,3 +417,16 @@ def test_next_window_with_sparsified_prior_from_the_oracle(solver):
     g, o = solve_both(solver, w2)
     assert_same_solution(g, o)
     assert_same_states(w2, g[1], o[1])
+
+
+def test_next_vo_window_with_sparsified_prior_from_the_oracle(solver):
+    """sparsifyVO restated by the oracle: Landmark3DPrior on the landmark of least entropy + the LandmarkToLandmark chain, through
+    the CUDA sparse-prior path (a11), on a window without IMU and without a fixed keyframe (the prior alone holds the gauge)."""
+    from oracle import marginalize
+
+    win = synth.make_window("small", vio=False)
+    prior, info = marginalize.marginalize_oldest(win)
+    w2 = marginalize.with_sparse_prior(win, marginalize.sparsify_vo(win, info))
+    g, o = solve_both(solver, w2)
+    assert_same_solution(g, o)
+    assert_same_states(w2, g[1], o[1])

@@ -182,3 +182,46 @@ def test_sparsified_vio_prior(small):
     w2 = marginalize.with_sparse_prior(win, sp)
     rc, d2, st = oracle.solve_window(w2, nthreads=4)
     assert rc == 0 and st["final_cost"] <= st["initial_cost"]
+
+
+def test_sparsified_vo_prior():
+    """Marginalization::sparsifyVO restated (oracle/marginalize.py): greedy chain over the coupling of the information blocks,
+    unary factor on the landmark of least entropy, relative factors along the chain; the shorter window solves with it."""
+    win = synth.make_window("small", vio=False)
+    prior, info = marginalize.marginalize_oldest(win)
+    assert prior is not None and prior.frame == -1 and info["m"] == 6 + 3 * len(info["marg"]) and info["n"] == 3 * len(info["keep"])
+    sp = marginalize.sparsify_vo(win, info)
+    keep = list(info["keep"])
+    K = len(keep)
+    chain = [int(sp.l2l_a[0])] + [int(x) for x in sp.l2l_b]
+    # a chain: consecutive links share a landmark, no landmark twice, all of them kept landmarks
+    assert np.array_equal(sp.l2l_a[1:], sp.l2l_b[:-1]) and len(set(chain)) == len(chain) <= K and set(chain) <= set(keep)
+    assert sp.has_lmk_prior and sp.lmk0 in chain and not sp.has_imu_prior
+    Ak = info["Ak"]
+    blk = lambda a, b: abs(np.trace(Ak[3 * keep.index(a):3 * keep.index(a) + 3, 3 * keep.index(b):3 * keep.index(b) + 3]))
+    mi = np.array([[0.0 if a == b else blk(a, b) for b in keep] for a in keep])
+    # the first link is the strongest coupling of all; every later link is the strongest coupling of the chain's tail with a
+    # landmark not yet on the chain
+    assert blk(chain[0], chain[1]) == mi.max()
+    for k in range(1, len(chain) - 1):
+        rest = [l for l in keep if l not in chain[:k + 1]]
+        assert blk(chain[k], chain[k + 1]) == max(blk(chain[k], l) for l in rest)
+    Sigma_k = info["U"] @ np.diag(1.0 / info["Lambda"]) @ info["U"].T
+    det = {l: np.linalg.det(Sigma_k[3 * keep.index(l):3 * keep.index(l) + 3, 3 * keep.index(l):3 * keep.index(l) + 3]) for l in chain}
+    assert det[sp.lmk0] == min(det.values())                          # entropy is monotone in the determinant
+    assert np.allclose(sp.lmk_prior, win.lmk_t[sp.lmk0])
+    c0 = 3 * keep.index(sp.lmk0)
+    S0 = sp.lmk_sqrt_inf.reshape(3, 3)
+    assert np.abs(S0 @ S0 - np.linalg.inv(Sigma_k[c0:c0 + 3, c0:c0 + 3])).max() <= 1e-6 * np.abs(S0 @ S0).max()
+    for k in (0, len(chain) // 2, len(chain) - 2):
+        a, b = 3 * keep.index(chain[k]), 3 * keep.index(chain[k + 1])
+        J = np.zeros((3, info["n"]))
+        J[:, a:a + 3], J[:, b:b + 3] = np.eye(3), -np.eye(3)
+        S = sp.l2l_sqrt_inf[k].reshape(3, 3)
+        assert np.abs(S - S.T).max() < 1e-9 * np.abs(S).max()
+        assert np.abs(S @ S - np.linalg.inv(J @ Sigma_k @ J.T)).max() <= 1e-6 * np.abs(S @ S).max()
+        assert np.allclose(sp.l2l_delta[k], win.lmk_t[chain[k]] - win.lmk_t[chain[k + 1]])
+    w2 = marginalize.with_sparse_prior(win, sp)
+    assert w2.sparse_prior.lmk0 >= 0 and w2.sparse_prior.l2l_a.max() < w2.n_lmks
+    rc, d2, st = oracle.solve_window(w2, nthreads=4)
+    assert rc == 0 and st["final_cost"] <= st["initial_cost"]
