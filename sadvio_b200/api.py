@@ -169,6 +169,28 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
+def write_back(win: abi.Window, d: abi.Delta, vio: bool) -> None:
+    """State write-back of the window solves, in place (AOptimizer.cpp:391-434 for VIO, :328-341 for BA)."""
+    for f in range(win.n_frames):
+        T = np.vstack([win.T_f_w[f].reshape(3, 4), [0, 0, 0, 1]])
+        dT = np.eye(4)
+        dT[:3, :3] = exp_so3(d.dpose[f, :3])
+        dT[:3, 3] = d.dpose[f, 3:]
+        win.T_f_w[f] = (T @ dT)[:3, :4].reshape(12)
+    win.lmk_t += d.dlmk
+    if vio:
+        win.v += d.dv
+        win.ba += d.dba
+        win.bg += d.dbg
+        # IMU::biasDeltaCorrection with the PREVIOUS keyframe's dba, dbg (AOptimizer.cpp:421-434, IMU.cpp:104-108)
+        for p in range(win.n_imu):
+            i = int(win.imu_i[p])
+            dba, dbg = d.dba[i], d.dbg[i]
+            win.imu_dp[p] += win.imu_J_dp_ba[p].reshape(3, 3) @ dba + win.imu_J_dp_bg[p].reshape(3, 3) @ dbg
+            win.imu_dv[p] += win.imu_J_dv_ba[p].reshape(3, 3) @ dba + win.imu_J_dv_bg[p].reshape(3, 3) @ dbg
+            win.imu_dR[p] = (win.imu_dR[p].reshape(3, 3) @ exp_so3(win.imu_J_dR_bg[p].reshape(3, 3) @ dbg)).reshape(9)
+
+
 class B200Optimizer:
     """Host-side mirror of ``isae::AOptimizer`` for the window solves (see module docstring)."""
 
@@ -176,33 +198,18 @@ class B200Optimizer:
         self.solver = Solver(cfg, device)
         self.last_stats: dict | None = None
 
+    def _solve(self, win: abi.Window):
+        return self.solver.solve_window(win)
+
     def _run(self, win: abi.Window, fixed_frame_number: int, vio: bool) -> bool:
         win.n_fixed = int(fixed_frame_number)
         win.vio = vio
         try:
-            rc, d, st = self.solver.solve_window(win)
+            rc, d, st = self._solve(win)
         except RuntimeError:
             return False  # the adapter maps a non-zero status to `false` and leaves the state untouched
         self.last_stats = st
-        # state write-back, AOptimizer.cpp:391-418
-        for f in range(win.n_frames):
-            T = np.vstack([win.T_f_w[f].reshape(3, 4), [0, 0, 0, 1]])
-            dT = np.eye(4)
-            dT[:3, :3] = exp_so3(d.dpose[f, :3])
-            dT[:3, 3] = d.dpose[f, 3:]
-            win.T_f_w[f] = (T @ dT)[:3, :4].reshape(12)
-        win.lmk_t += d.dlmk
-        if vio:
-            win.v += d.dv
-            win.ba += d.dba
-            win.bg += d.dbg
-            # IMU::biasDeltaCorrection with the PREVIOUS keyframe's dba, dbg (AOptimizer.cpp:421-434, IMU.cpp:104-108)
-            for p in range(win.n_imu):
-                i = int(win.imu_i[p])
-                dba, dbg = d.dba[i], d.dbg[i]
-                win.imu_dp[p] += win.imu_J_dp_ba[p].reshape(3, 3) @ dba + win.imu_J_dp_bg[p].reshape(3, 3) @ dbg
-                win.imu_dv[p] += win.imu_J_dv_ba[p].reshape(3, 3) @ dba + win.imu_J_dv_bg[p].reshape(3, 3) @ dbg
-                win.imu_dR[p] = (win.imu_dR[p].reshape(3, 3) @ exp_so3(win.imu_J_dR_bg[p].reshape(3, 3) @ dbg)).reshape(9)
+        write_back(win, d, vio)
         return True
 
     def localMapVIOptimization(self, local_map: abi.Window, fixed_frame_number: int = 0) -> bool:  # noqa: N802

@@ -94,3 +94,129 @@ def check_bias(win, d):
     new = apply_delta(win, d)
     assert np.linalg.norm(new["bg"][1] - win.meta["bg"]) < 1e-5
     assert np.linalg.norm(new["ba"][1] - win.meta["ba"]) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# imu_test.cpp:885-945 — the bias-estimation run of simuEuroc: 30 keyframes 0.5 s apart on the EuRoC ground truth,
+# IMU samples differentiated from it and corrupted by constant biases, a pose prior on every keyframe,
+# localMapVIOptimization(local_map, 1) after every new keyframe; the newest keyframe's biases must be the true ones.
+# ----------------------------------------------------------------------------------------------------------------
+EUROC_BA = np.array([0.1, 0.2, -0.1])      # :892
+EUROC_BG = np.array([0.4, -0.2, 0.01])     # :893
+G_W = np.array([0.0, 0.0, -9.81])
+
+
+class OracleOptimizer:
+    """localMapVIOptimization through the CPU oracle with the host mirror's own write-back (sadvio_b200.api.write_back): the
+    checker's counterpart of api.B200Optimizer for tests that drive a sequence of solves."""
+
+    def __init__(self, nthreads=1):
+        self.nthreads, self.last_stats = nthreads, None
+
+    def localMapVIOptimization(self, win, fixed_frame_number=0):  # noqa: N802
+        from sadvio_b200 import api
+        win.n_fixed, win.vio = int(fixed_frame_number), True
+        rc, d, st = orc.solve_window(win, nthreads=self.nthreads)
+        self.last_stats = st
+        api.write_back(win, d, True)
+        return True
+
+
+def _euroc_samples():
+    """meas_vec / pose_vec / vel_vec / ts_vec of imu_test.cpp:741-757 from the committed slice of euroc_gt.csv
+    (tests/golden/make_euroc_slice.py).  Rotations are the polar factors of Quaterniond(w,x,y,z).toRotationMatrix(), which is
+    what Affine3d::rotation() returns for the 6-digit quaternions of the file."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "euroc_gt_slice.npz"))
+    ts = z["timestamp_ns"].astype(np.float64) * 1e-9                          # read_line_euroc, :34
+    q, p, v = z["q_wxyz"], z["p"], z["v"]
+    n = ts.size
+    R = np.zeros((n, 3, 3))
+    for k in range(n):
+        w, x, y, zz = q[k]
+        M = np.array([[1 - 2 * (y * y + zz * zz), 2 * (x * y - w * zz), 2 * (x * zz + w * y)],
+                      [2 * (x * y + w * zz), 1 - 2 * (x * x + zz * zz), 2 * (y * zz - w * x)],
+                      [2 * (x * zz - w * y), 2 * (y * zz + w * x), 1 - 2 * (x * x + y * y)]])
+        U, _, Vt = np.linalg.svd(M)
+        R[k] = U @ Vt
+    acc, gyr = np.zeros((n - 1, 3)), np.zeros((n - 1, 3))
+    for k in range(n - 1):
+        dt = ts[k + 1] - ts[k]
+        acc[k] = (1 / dt) * (R[k + 1].T @ (v[k + 1] - v[k])) - R[k + 1].T @ G_W   # :745
+        gyr[k] = (1 / dt) * orc.log_so3(R[k].T @ R[k + 1])                        # :746
+    ts_ns = (ts * 1e9).astype(np.uint64)                                      # ts_vec (:752) through Frame::init's integer ns
+    return acc, gyr, R[:-1], p[:-1], v[:-1], ts[:-1] * 1e9, ts_ns[:-1]
+
+
+def _T_f_w(R_w_f, t_w_f):
+    return np.hstack([R_w_f.T, (-R_w_f.T @ t_w_f)[:, None]]).reshape(12)
+
+
+def _kf_window(kfs, sigma_ba, sigma_bg):
+    """Flatten the keyframe records (oldest -> newest) the way getLastNFramesIn does: newest first."""
+    fr = kfs[::-1]
+    F = len(fr)
+    g = orc.imu_get
+    pairs = [(j + 1, j) for j in range(F - 1) if (fr[j]["ts"] - fr[j + 1]["ts"]) * 1e-9 <= 1]      # AOptimizer.cpp:62-73
+    col = lambda name, k: np.stack([g(fr[j]["imu"], name) for _, j in pairs]).reshape(len(pairs), k)
+    return abi.Window(
+        vio=True, factor_kind=abi.SDV_FACTOR_ANGULAR, n_fixed=1,
+        T_f_w=np.stack([f["T_f_w"] for f in fr]), T_s_f=np.eye(3, 4).reshape(1, 12), K=np.array([[100.0, 100.0, 400.0, 400.0]]),
+        lmk_t=np.zeros((0, 3)), obs_lmk=np.zeros(0, np.int32), obs_frame=np.zeros(0, np.int32), obs_cam=np.zeros(0, np.int32),
+        obs_bearing=np.zeros((0, 3)), obs_uv=np.zeros((0, 2)),
+        v=np.stack([g(f["imu"], "v") for f in fr]), ba=np.stack([g(f["imu"], "ba") for f in fr]),
+        bg=np.stack([g(f["imu"], "bg") for f in fr]),
+        has_imu=np.ones(F, np.uint8), has_prior=np.ones(F, np.uint8), T_prior=np.stack([f["T_prior"] for f in fr]),
+        inf_prior=np.full((F, 6), 100.0),
+        imu_i=np.array([i for i, _ in pairs], np.int32), imu_j=np.array([j for _, j in pairs], np.int32),
+        imu_dt=np.array([(fr[j]["ts"] - fr[i]["ts"]) * 1e-9 for i, j in pairs]),
+        imu_dR=col("dR", 9), imu_dv=col("dv", 3), imu_dp=col("dp", 3), imu_cov=col("Sigma", 81), imu_J_dR_bg=col("J_dR_bg", 9),
+        imu_J_dv_ba=col("J_dv_ba", 9), imu_J_dv_bg=col("J_dv_bg", 9), imu_J_dp_ba=col("J_dp_ba", 9), imu_J_dp_bg=col("J_dp_bg", 9),
+        imu_sigma_ba=np.full(len(pairs), sigma_ba), imu_sigma_bg=np.full(len(pairs), sigma_bg),
+    ).normalise(), pairs
+
+
+def euroc_bias_run(optimizer, n_kf=30, dt_kf=0.5):
+    """Drives `optimizer.localMapVIOptimization(window, 1)` exactly as imu_test.cpp:885-942 does; returns the keyframe records
+    (oldest first; record["imu"] is the keyframe's IMU object as an oracle state vector) and the per-solve statistics."""
+    acc, gyr, R, p, v, ts_f, ts_ns = _euroc_samples()
+    bgyr_noise, acc_noise, bacc_noise, rate = 1.9393e-03, 3.0e-2, 3.0e-2, 200.0        # :884-886
+    eta6 = (np.array([GYR_NOISE] * 3 + [acc_noise] * 3) ** 2) * rate
+    T0 = _T_f_w(R[0], p[0])
+    imu0 = orc.imu_state(acc[0] + EUROC_BA, gyr[0] + EUROC_BG, T_f_w=T0, v=v[0], is_kf=True)  # :896-906
+    kfs = [dict(T_f_w=T0.copy(), T_prior=T0.copy(), imu=imu0, ts=int(ts_ns[0]))]
+    tsp, last, last_ts = ts_f[0], imu0, int(ts_ns[0])
+    stats = []
+    for i in range(1, acc.shape[0]):
+        dt_vote = (ts_f[i] - tsp) * 1e-9                                                     # :911
+        kf_imu = kfs[-1]["imu"]
+        cur = orc.process_imu(last, orc.imu_get(kf_imu, "ba"), orc.imu_get(kf_imu, "bg"), (int(ts_ns[i]) - last_ts) * 1e-9, eta6, rate,
+                              acc[i] + EUROC_BA, gyr[i] + EUROC_BG)                          # :914-921
+        T = _T_f_w(R[i], p[i])
+        cur[15:27] = T                                                                      # :927 (ground-truth pose)
+        cur[12:15] = v[i]                                                                   # :928
+        last, last_ts = cur, int(ts_ns[i])
+        if dt_vote > dt_kf:                                                                  # :931-937
+            cur[27] = 1.0
+            kfs.append(dict(T_f_w=T.copy(), T_prior=T.copy(), imu=cur, ts=int(ts_ns[i])))
+            win, pairs = _kf_window(kfs, bacc_noise, bgyr_noise)
+            assert optimizer.localMapVIOptimization(win, 1)
+            stats.append(optimizer.last_stats)
+            fr = kfs[::-1]
+            for f, rec in enumerate(fr):                                                     # the write-back lands in the objects
+                rec["T_f_w"] = win.T_f_w[f].copy()
+                rec["imu"][15:27] = win.T_f_w[f]
+                rec["imu"][12:15], rec["imu"][6:9], rec["imu"][9:12] = win.v[f], win.ba[f], win.bg[f]
+            for k, (_, j) in enumerate(pairs):
+                fr[j]["imu"][28:37], fr[j]["imu"][37:40], fr[j]["imu"][40:43] = win.imu_dR[k], win.imu_dv[k], win.imu_dp[k]
+            tsp = ts_f[i]
+        if len(kfs) == n_kf:                                                                 # :940-941
+            break
+    return kfs, stats
+
+
+def check_euroc_bias(kfs):
+    """Assertions of imu_test.cpp:944-945 on the 30th keyframe."""
+    assert len(kfs) == 30
+    assert np.linalg.norm(orc.imu_get(kfs[29]["imu"], "ba") - EUROC_BA) < 0.02
+    assert np.linalg.norm(orc.imu_get(kfs[29]["imu"], "bg") - EUROC_BG) < 0.02

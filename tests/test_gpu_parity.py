@@ -169,6 +169,21 @@ def test_reference_bias_estimation(solver):  # imu_test.cpp:545-568
     assert g[2]["termination"] == o[2]["termination"]
 
 
+def test_reference_euroc_bias_run(solver):  # imu_test.cpp:885-945
+    """29 consecutive solves on the growing EuRoC window through B200Optimizer (solve + write-back + biasDeltaCorrection): the
+    reference's own assertion holds, and every keyframe ends where the oracle-driven run ends."""
+    opt = api.B200Optimizer()
+    kfs, stats = rf.euroc_bias_run(opt)
+    rf.check_euroc_bias(kfs)
+    kfs0, stats0 = rf.euroc_bias_run(rf.OracleOptimizer())
+    assert [s["iterations"] for s in stats] == [s["iterations"] for s in stats0]
+    assert [s["termination"] for s in stats] == [s["termination"] for s in stats0]
+    for a, b in zip(kfs, kfs0):
+        for name in ("ba", "bg", "v", "T_f_w", "dR", "dv", "dp"):
+            x, y = orc.imu_get(a["imu"], name), orc.imu_get(b["imu"], name)
+            assert np.abs(x - y).max() <= 1e-6 * max(np.abs(y).max(), 1e-3), name
+
+
 @pytest.mark.parametrize("vio", [True, False])
 def test_dense_marginal_prior(solver, vio):
     """a10: MarginalizationFactor with kept landmarks in the reduced system (…Analytic.cpp:341-383)."""

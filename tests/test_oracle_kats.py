@@ -219,6 +219,61 @@ def test_predictionPositionVelocity_and_IMUFactor():
     assert np.abs(J - Jn).max() < 1e-6 * scale
 
 
+def _estimate_transform(kf, cur, dt):
+    """IMU::estimateTransform (IMU.cpp:93-102) followed by the pose assignment the reference tests make with it
+    (imu_test.cpp:606-607): T_f_w(cur) = dT^-1 T_f_w(kf), dT = [delta_R | delta_p + R1 v_kf dt + 1/2 R1 g dt^2]."""
+    g = np.array([0.0, 0.0, -9.81])
+    T1 = np.vstack([orc.imu_get(kf, "T_f_w").reshape(3, 4), [0, 0, 0, 1]])
+    R1 = T1[:3, :3]
+    dT = np.eye(4)
+    dT[:3, :3] = orc.imu_get(cur, "dR").reshape(3, 3)
+    dT[:3, 3] = orc.imu_get(cur, "dp") + R1 @ orc.imu_get(kf, "v") * dt + 0.5 * R1 @ g * dt * dt
+    out = cur.copy()
+    out[15:27] = (np.linalg.inv(dT) @ T1)[:3].reshape(12)
+    return out
+
+
+def _aceinna_run(segments):
+    """The loop of predictionWithRotation / predictionWithRotation2 (imu_test.cpp:573-702): constant samples at 200 Hz, the
+    pose of every frame re-estimated from the pre-integrated deltas, a new keyframe at the start of every segment."""
+    T_i_f = np.eye(4)
+    T_i_f[:3, :3] = np.diag([1.0, -1.0, -1.0])                                # :576-577
+    T_f_i = np.linalg.inv(T_i_f)
+    dt, rate = 0.005, 200.0
+    out = []
+    kf = last = None
+    i_kf = 0
+    i = 0
+    for gyr, acc, n in segments:
+        gyr, acc = np.asarray(gyr, float), np.asarray(acc, float)
+        if last is None:
+            last = orc.imu_state(acc, gyr, T_f_w=T_f_i[:3].reshape(12), is_kf=True)
+        else:
+            last[27] = 1.0                                                    # cur_frame->setKeyFrame()
+        kf, i_kf = last, i
+        for _ in range(n):
+            i += 1
+            cur = orc.process_imu(last, np.zeros(3), np.zeros(3), dt, eta(rate), rate, acc, gyr)
+            last = _estimate_transform(kf, cur, (i - i_kf) * dt)
+        T_w_f = np.linalg.inv(np.vstack([orc.imu_get(last, "T_f_w").reshape(3, 4), [0, 0, 0, 1]]))
+        out.append((T_i_f[:3, :3].T @ T_w_f[:3, 3], T_i_f[:3, :3].T @ orc.imu_get(last, "v")))
+    return out
+
+
+def test_predictionWithRotation():  # imu_test.cpp:573-656, expected values from the Aceinna gnss-ins-sim trajectories
+    (p1, v1), (p2, v2) = _aceinna_run([((0.5, 0, 0), (-1, 0, -9.81), 201), ((0.5, 0.2, 0.04), (-1, 0.05, -9.81), 199)])
+    assert np.linalg.norm(p1 - [-0.505, 0.813, 0.1]) < 1e-2                   # :614-618
+    assert np.linalg.norm(v1 - [-1, 2.41, 0.4]) < 1e-2                        # :619
+    assert np.linalg.norm(p2 - [-2.31, 6.18, 1.62]) < 1e-2                    # :646-650
+    assert np.linalg.norm(v2 - [-2.95, 8.91, 3.24]) < 1e-2                    # :651
+
+
+def test_predictionWithRotation2():  # imu_test.cpp:654-703
+    ((p, v),) = _aceinna_run([((0.5, 0.2, 0.04), (-1, 0.05, -9.81), 200)])
+    assert np.linalg.norm(p - [-0.82143062, 0.80412303, 0.15357111]) < 1e-2   # :695-699
+    assert np.linalg.norm(v - [-1.97810799, 2.38035184, 0.5780088]) < 1e-2    # :700-702
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # residual_test.cpp gradient checks (K = diag(100,100), c = (400,400), identity extrinsics)
 # ----------------------------------------------------------------------------------------------------------------

@@ -23,6 +23,16 @@ def test_reference_bias_estimation():  # imu_test.cpp:545-568 (tolerance 1e-5)
     rf.check_bias(win, d)
 
 
+def test_reference_euroc_bias_run():  # imu_test.cpp:885-945 (tolerance 0.02 on both biases of the 30th keyframe)
+    """The reference's longest end-to-end test of the window solve: 29 consecutive localMapVIOptimization calls on a growing
+    window, each followed by the state write-back and biasDeltaCorrection, starting from zero biases."""
+    kfs, stats = rf.euroc_bias_run(rf.OracleOptimizer())
+    rf.check_euroc_bias(kfs)
+    assert len(stats) == 29 and all(s["termination"] in ("FUNCTION_TOLERANCE", "PARAMETER_TOLERANCE", "GRADIENT_TOLERANCE") for s in stats)
+    # the fixed oldest keyframe never moves (AOptimizer.cpp:46-51)
+    assert np.all(orc.imu_get(kfs[0]["imu"], "ba") == 0) and np.all(orc.imu_get(kfs[0]["imu"], "bg") == 0)
+
+
 @pytest.mark.parametrize("name,kind", [("tiny", 0), ("tiny", 1), ("small", 0), ("small", 1)])
 def test_schur_equals_full_normal_equations(name, kind):
     """Landmark elimination must give the step SPARSE_NORMAL_CHOLESKY computes on the full system."""
