@@ -381,3 +381,30 @@ def test_PoseToLandmarkResidual(seed):  # residual_test.cpp:236-274
         J = np.hstack([J6, J3])
         assert abs((J - Jn).sum()) < 1e-5
         assert np.abs(J - Jn).max() < 1e-5
+
+
+def test_simuEuroc_integration_on_the_committed_slice():  # imu_test.cpp:760-806
+    """processIMU dead-reckoning against the test's own "simple integration", every step within 0.1 in Frobenius norm; run on the
+    committed slice of euroc_gt.csv (samples 2000..4929) instead of the whole 28 k-sample file."""
+    from tests import ref_fixtures as rf
+
+    acc, gyr, R, p, v, ts_f, ts_ns = rf._euroc_samples()
+    g = np.array([0.0, 0.0, -9.81])
+    T0 = rf._T_f_w(R[0], p[0])
+    kf = orc.imu_state(acc[0], gyr[0], T_f_w=T0, v=v[0], is_kf=True)
+    last = kf
+    Rp, tp, vp = R[0].copy(), p[0].copy(), v[0].copy()
+    worst = 0.0
+    for i in range(1, acc.shape[0]):
+        dt = (ts_f[i] - ts_f[i - 1]) * 1e-9
+        last = orc.process_imu(last, np.zeros(3), np.zeros(3), (int(ts_ns[i]) - int(ts_ns[i - 1])) * 1e-9, eta(200.0), 200.0, acc[i], gyr[i])
+        vn = vp + g * dt + Rp @ acc[i - 1] * dt                                  # :789-795
+        tp = tp + vp * dt + 0.5 * g * dt * dt + 0.5 * Rp @ acc[i - 1] * dt * dt
+        Rp = Rp @ orc.exp_so3(gyr[i - 1] * dt)
+        vp = vn
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = Rp, tp
+        T_f_w = np.vstack([orc.imu_get(last, "T_f_w").reshape(3, 4), [0, 0, 0, 1]])
+        worst = max(worst, np.linalg.norm(T @ T_f_w - np.eye(4)))
+    assert worst < 0.1                                                           # :799-800
+    assert worst < 1e-6      # the two integrations are the same recursion; only the timestamp rounding differs
