@@ -1,7 +1,8 @@
 // Test driver for sadvio_b200/host/b200_optimizer.hpp: reads a pointer-graph description (text, produced by
 // tests/test_host_adapter.py), rebuilds the graph with shared_ptr / weak_ptr objects exactly as SaDVIO holds it,
-// and either prints the flattened window ("flatten") or runs localMapVIOptimization / localMapBA through the C ABI
-// and prints the updated state ("solve").
+// and either prints the flattened window ("flatten": indices only, "dump": every array of the sdv_window) or runs
+// localMapVIOptimization / localMapBA through the C ABI and prints the updated state ("solve").  An optional trailing
+// section describes the isae::Marginalization object the optimizer holds (dense or sparsified prior).
 #include "b200_optimizer.hpp"
 
 #include <cstdio>
@@ -81,11 +82,101 @@ int main(int argc, char **argv) {
         }
         map->pointxd.push_back(lm);
     }
+    // optional marginal prior: "<sparsif> <frame_to_keep|-1> <frame_col> <n> <n_full> <n_keep>", per kept landmark
+    // "<landmark> <col> <delta 3> <sqrt_inf 9>", then J, r0, the 15x15 frame information, "<lmk_with_prior|-1> <prior 3> <info 9>"
+    auto marg = std::make_shared<Marginalization>();
+    bool sparsif = false;
+    int has_prior_section = 0;
+    if (in >> has_prior_section && has_prior_section) {
+        int sp, ftk, fcol, nkeep;
+        in >> sp >> ftk >> fcol >> marg->n >> marg->n_full >> nkeep;
+        sparsif = sp != 0;
+        if (ftk >= 0) {
+            marg->frame_to_keep = all_frames[ftk];
+            marg->map_frame_idx[all_frames[ftk].get()] = fcol;
+        }
+        for (int k = 0; k < nkeep; k++) {
+            int l, col;
+            in >> l >> col;
+            auto &lm = map->pointxd[l];
+            marg->lmk_to_keep.push_back(lm);
+            marg->map_lmk_idx[lm.get()] = col;
+            rd(in, marg->map_lmk_prior[lm.get()]);
+            rd(in, marg->map_lmk_inf[lm.get()]);
+        }
+        marg->marginalization_jacobian.resize((size_t)marg->n * marg->n_full);
+        marg->marginalization_residual.resize(marg->n_full);
+        for (auto &x : marg->marginalization_jacobian) in >> x;
+        for (auto &x : marg->marginalization_residual) in >> x;
+        if (ftk >= 0) rd(in, marg->map_frame_inf[all_frames[ftk].get()]);
+        int lwp;
+        in >> lwp;
+        if (lwp >= 0) marg->lmk_with_prior = map->pointxd[lwp];
+        rd(in, marg->prior_lmk);
+        rd(in, marg->info_lmk);
+        if (!in) {
+            std::fprintf(stderr, "malformed prior section\n");
+            return 2;
+        }
+    } else {
+        in.clear();
+    }
     if (!in) {
         std::fprintf(stderr, "malformed input\n");
         return 2;
     }
     std::printf("%s\n", mode.c_str());
+    if (mode == "dump") {
+        FlatWindow fw;
+        bool ok = flatten(*map, fixed, vio, kind, fw, marg.get(), sparsif);
+        const sdv_window &w = fw.view;
+        std::printf("ok %d\n", ok ? 1 : 0);
+        if (!ok) return 0;
+        auto pd = [](const char *name, const double *a, size_t n) {
+            std::printf("%s %zu", name, a ? n : 0);
+            for (size_t i = 0; a && i < n; i++) std::printf(" %.17g", a[i]);
+            std::printf("\n");
+        };
+        auto pi = [](const char *name, const int32_t *a, size_t n) {
+            std::printf("%s %zu", name, a ? n : 0);
+            for (size_t i = 0; a && i < n; i++) std::printf(" %d", a[i]);
+            std::printf("\n");
+        };
+        auto pu = [](const char *name, const uint8_t *a, size_t n) {
+            std::printf("%s %zu", name, a ? n : 0);
+            for (size_t i = 0; a && i < n; i++) std::printf(" %d", (int)a[i]);
+            std::printf("\n");
+        };
+        const size_t F = w.n_frames, C = w.n_cams, L = w.n_lmks, O = w.n_obs, P = w.n_imu;
+        std::printf("dims 8 %d %d %d %d %d %d %d %d\n", w.vio, w.factor_kind, w.n_frames, w.n_fixed, w.n_cams, w.n_lmks, w.n_obs, w.n_imu);
+        pd("T_f_w", w.T_f_w, 12 * F); pd("v", w.v, 3 * F); pd("ba", w.ba, 3 * F); pd("bg", w.bg, 3 * F);
+        pu("has_imu", w.has_imu, F); pu("has_prior", w.has_prior, F); pd("T_prior", w.T_prior, 12 * F); pd("inf_prior", w.inf_prior, 6 * F);
+        pd("T_s_f", w.T_s_f, 12 * C); pd("K", w.K, 4 * C); pd("lmk_t", w.lmk_t, 3 * L);
+        pi("obs_lmk", w.obs_lmk, O); pi("obs_frame", w.obs_frame, O); pi("obs_cam", w.obs_cam, O);
+        pd("obs_bearing", w.obs_bearing, 3 * O); pd("obs_uv", w.obs_uv, 2 * O);
+        pi("imu_i", w.imu_i, P); pi("imu_j", w.imu_j, P); pd("imu_dt", w.imu_dt, P); pd("imu_dR", w.imu_dR, 9 * P);
+        pd("imu_dv", w.imu_dv, 3 * P); pd("imu_dp", w.imu_dp, 3 * P); pd("imu_cov", w.imu_cov, 81 * P);
+        pd("imu_J_dR_bg", w.imu_J_dR_bg, 9 * P); pd("imu_J_dv_ba", w.imu_J_dv_ba, 9 * P); pd("imu_J_dv_bg", w.imu_J_dv_bg, 9 * P);
+        pd("imu_J_dp_ba", w.imu_J_dp_ba, 9 * P); pd("imu_J_dp_bg", w.imu_J_dp_bg, 9 * P);
+        pd("imu_sigma_ba", w.imu_sigma_ba, P); pd("imu_sigma_bg", w.imu_sigma_bg, P);
+        if (w.dense_prior) {
+            const sdv_dense_prior &d = *w.dense_prior;
+            std::printf("dense 5 %d %d %d %d %d\n", d.n_full, d.n, d.frame, d.frame_col, d.n_keep);
+            pd("dense_J", d.J, (size_t)d.n_full * d.n); pd("dense_r0", d.r0, d.n_full);
+            pi("dense_keep_lmk", d.keep_lmk, d.n_keep); pi("dense_keep_col", d.keep_col, d.n_keep);
+        }
+        if (w.sparse_prior) {
+            const sdv_sparse_prior &q = *w.sparse_prior;
+            std::printf("sparse 6 %d %d %d %d %d %d\n", q.has_imu_prior, q.frame, q.n_p2l, q.has_lmk_prior, q.lmk0, q.n_l2l);
+            pd("sp_T_prior", q.T_prior, 12); pd("sp_v_prior", q.v_prior, 3); pd("sp_ba_prior", q.ba_prior, 3); pd("sp_bg_prior", q.bg_prior, 3);
+            pd("sp_imu_sqrt_inf", q.imu_sqrt_inf, 225);
+            pi("sp_p2l_lmk", q.p2l_lmk, q.n_p2l); pd("sp_p2l_delta", q.p2l_delta, 3 * (size_t)q.n_p2l); pd("sp_p2l_sqrt_inf", q.p2l_sqrt_inf, 9 * (size_t)q.n_p2l);
+            pd("sp_lmk_prior", q.lmk_prior, 3); pd("sp_lmk_sqrt_inf", q.lmk_sqrt_inf, 9);
+            pi("sp_l2l_a", q.l2l_a, q.n_l2l); pi("sp_l2l_b", q.l2l_b, q.n_l2l); pd("sp_l2l_delta", q.l2l_delta, 3 * (size_t)q.n_l2l);
+            pd("sp_l2l_sqrt_inf", q.l2l_sqrt_inf, 9 * (size_t)q.n_l2l);
+        }
+        return 0;
+    }
     if (mode == "flatten") {
         FlatWindow fw;
         flatten(*map, fixed, vio, kind, fw);
@@ -97,6 +188,8 @@ int main(int argc, char **argv) {
         return 0;
     }
     B200Optimizer opt(kind, 0);
+    opt._marginalization = marg;
+    opt._enable_sparsif = sparsif;
     bool ok = vio ? opt.localMapVIOptimization(map, fixed) : opt.localMapBA(map, fixed);
     std::printf("%d %d\n", ok ? 1 : 0, opt.lastStats().iterations);
     for (auto &fr : map->frames) {

@@ -84,6 +84,24 @@ struct LocalMap { // isae::LocalMap
     size_t getMapSize() const { return frames.size(); }
 };
 
+// isae::Marginalization — only the members addMarginalizationResiduals reads (marginalization.hpp:54-85).  Matrices are
+// row-major here; the Eigen members of the reference are column-major (INTEGRATION.md shows the copy).
+struct Marginalization {
+    int n = 0, n_full = 0;                                              // _n, _n_full
+    std::shared_ptr<Frame> frame_to_keep;                               // _frame_to_keep (null in the VO case)
+    std::vector<std::shared_ptr<Landmark>> lmk_to_keep;                 // _lmk_to_keep["pointxd"]
+    std::unordered_map<const Frame *, int> map_frame_idx;               // _map_frame_idx
+    std::unordered_map<const Landmark *, int> map_lmk_idx;              // _map_lmk_idx
+    std::vector<double> marginalization_jacobian;                       // [n_full][n]
+    std::vector<double> marginalization_residual;                       // [n_full]
+    std::unordered_map<const Frame *, std::array<double, 225>> map_frame_inf;  // _map_frame_inf (sparsifyVIO)
+    std::unordered_map<const Landmark *, std::array<double, 9>> map_lmk_inf;   // _map_lmk_inf
+    std::unordered_map<const Landmark *, std::array<double, 3>> map_lmk_prior; // _map_lmk_prior
+    std::shared_ptr<Landmark> lmk_with_prior;                           // _lmk_with_prior (sparsifyVO)
+    std::array<double, 9> info_lmk{};                                   // _info_lmk
+    std::array<double, 3> prior_lmk{};                                  // _prior_lmk
+};
+
 // Structure-of-arrays image of one window + the bookkeeping needed for the write-back.
 struct FlatWindow {
     std::vector<double> T_f_w, v, ba, bg, T_prior, inf_prior, T_s_f, K, lmk_t, obs_bearing, obs_uv;
@@ -93,10 +111,17 @@ struct FlatWindow {
     std::vector<std::shared_ptr<Frame>> frame_vector;     // newest -> oldest
     std::vector<std::shared_ptr<Landmark>> landmarks;     // in parameter-block order
     std::vector<std::shared_ptr<Frame>> imu_frame_j;      // frame j of each IMU factor
+    std::vector<int32_t> keep_lmk, keep_col, p2l_lmk, l2l_a, l2l_b;  // marginal prior (addMarginalizationResiduals)
+    std::vector<double> p2l_delta, p2l_sqrt_inf, l2l_delta, l2l_sqrt_inf;
+    sdv_dense_prior dense{};
+    sdv_sparse_prior sparse{};
     sdv_window view{};
 };
 
-inline void flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, int factor_kind, FlatWindow &fw) {
+// Returns false where the reference would throw out of an unordered_map::at (a prior that names a frame outside the
+// window, or a sparsified prior with missing per-landmark entries): the caller maps that to `false`, state untouched.
+inline bool flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, int factor_kind, FlatWindow &fw,
+                    const Marginalization *marg = nullptr, bool enable_sparsif = false) {
     fw = FlatWindow();
     map.getLastNFramesIn(map.getMapSize(), fw.frame_vector); // AOptimizer.cpp:366-367
     const int F = (int)fw.frame_vector.size();
@@ -126,9 +151,11 @@ inline void flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
         for (auto &s : f.sensors) cam_of(*s);
     }
     // landmarks + visual residual blocks in reference walk order (…Analytic.cpp:247-289)
+    std::unordered_map<const Landmark *, int> lmk_idx; // _map_lmk_ptpar
     for (auto &landmark : map.pointxd) {
         if (!landmark->isInitialized() || landmark->isOutlier()) continue; // :254
         const int l = (int)fw.landmarks.size();
+        lmk_idx[landmark.get()] = l;
         fw.landmarks.push_back(landmark);
         fw.lmk_t.insert(fw.lmk_t.end(), landmark->t_w.begin(), landmark->t_w.end());
         for (auto &wfeature : landmark->features) { // :266
@@ -173,6 +200,99 @@ inline void flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
             fw.imu_frame_j.push_back(framej);
         }
     }
+    // Marginal prior (addMarginalizationResiduals, AngularAdjustmentCERESAnalytic.cpp:341-486).  A kept landmark that has no
+    // parameter block yet gets one, at zero, with no observation (the "supposed to be in the map" branches, :369-373,
+    // :413-417, :441-445); it is written back like any other landmark.
+    bool have_dense = false, have_sparse = false;
+    if (marg && !marg->lmk_to_keep.empty()) {
+        auto block_of = [&](const std::shared_ptr<Landmark> &lmk) {
+            auto it = lmk_idx.find(lmk.get());
+            if (it != lmk_idx.end()) return it->second;
+            const int l = (int)fw.landmarks.size();
+            lmk_idx[lmk.get()] = l;
+            fw.landmarks.push_back(lmk);
+            fw.lmk_t.insert(fw.lmk_t.end(), lmk->t_w.begin(), lmk->t_w.end());
+            return l;
+        };
+        int keep_frame = -1;
+        if (marg->frame_to_keep) {
+            auto it = frame_idx.find(marg->frame_to_keep.get());
+            if (it == frame_idx.end() || (vio && !marg->frame_to_keep->imu)) return false; // _map_frame_posepar.at / _map_frame_velpar.at
+            keep_frame = it->second;
+        }
+        if (!enable_sparsif) { // dense MarginalizationFactor, :346-384
+            sdv_dense_prior &dp = fw.dense;
+            dp.n_full = marg->n_full;
+            dp.n = marg->n;
+            dp.J = marg->marginalization_jacobian.data();
+            dp.r0 = marg->marginalization_residual.data();
+            dp.frame = keep_frame;
+            dp.frame_col = 0;
+            if (marg->frame_to_keep) {
+                auto it = marg->map_frame_idx.find(marg->frame_to_keep.get());
+                if (it == marg->map_frame_idx.end()) return false;
+                dp.frame_col = it->second;
+            }
+            for (auto &lmk : marg->lmk_to_keep) { // parameter-block order of the factor, marginalization.hpp:101-107
+                auto it = marg->map_lmk_idx.find(lmk.get());
+                if (it == marg->map_lmk_idx.end()) return false;
+                fw.keep_lmk.push_back(block_of(lmk));
+                fw.keep_col.push_back(it->second);
+            }
+            dp.n_keep = (int32_t)fw.keep_lmk.size();
+            dp.keep_lmk = fw.keep_lmk.data();
+            dp.keep_col = fw.keep_col.data();
+            have_dense = true;
+        } else if (marg->frame_to_keep) { // sparsified, VIO case, :390-424
+            const Frame &f = *marg->frame_to_keep;
+            auto inf = marg->map_frame_inf.find(&f);
+            if (inf == marg->map_frame_inf.end() || !f.imu) return false;
+            sdv_sparse_prior &sp = fw.sparse;
+            sp.has_imu_prior = 1;
+            sp.frame = keep_frame;
+            std::memcpy(sp.T_prior, f.T_f_w.data(), sizeof(sp.T_prior)); // IMUPriordx(T_f_w, T_f_w, v, v, ba, ba, bg, bg, …), :396-397
+            std::memcpy(sp.v_prior, f.imu->v.data(), 24);
+            std::memcpy(sp.ba_prior, f.imu->ba.data(), 24);
+            std::memcpy(sp.bg_prior, f.imu->bg.data(), 24);
+            std::memcpy(sp.imu_sqrt_inf, inf->second.data(), sizeof(sp.imu_sqrt_inf));
+            for (auto &lmk : marg->lmk_to_keep) {
+                auto d = marg->map_lmk_prior.find(lmk.get());
+                auto w = marg->map_lmk_inf.find(lmk.get());
+                if (d == marg->map_lmk_prior.end() || w == marg->map_lmk_inf.end()) return false;
+                fw.p2l_lmk.push_back(block_of(lmk));
+                fw.p2l_delta.insert(fw.p2l_delta.end(), d->second.begin(), d->second.end());
+                fw.p2l_sqrt_inf.insert(fw.p2l_sqrt_inf.end(), w->second.begin(), w->second.end());
+            }
+            sp.n_p2l = (int32_t)fw.p2l_lmk.size();
+            have_sparse = true;
+        } else { // sparsified, VO case: unary factor + chain, :427-481
+            if (!marg->lmk_with_prior) return false;
+            sdv_sparse_prior &sp = fw.sparse;
+            sp.has_lmk_prior = 1;
+            sp.lmk0 = block_of(marg->lmk_with_prior);
+            std::memcpy(sp.lmk_prior, marg->prior_lmk.data(), 24);
+            std::memcpy(sp.lmk_sqrt_inf, marg->info_lmk.data(), 72);
+            for (size_t k = 0; k + 1 < marg->lmk_to_keep.size(); k++) {
+                const std::shared_ptr<Landmark> &lmk_k = marg->lmk_to_keep[k], &lmk_kp1 = marg->lmk_to_keep[k + 1];
+                const int a = block_of(lmk_k), b = block_of(lmk_kp1);
+                if (lmk_k == lmk_kp1) continue; // :463-464
+                auto d = marg->map_lmk_prior.find(lmk_kp1.get());
+                auto w = marg->map_lmk_inf.find(lmk_kp1.get());
+                if (d == marg->map_lmk_prior.end() || w == marg->map_lmk_inf.end()) return false;
+                fw.l2l_a.push_back(a);
+                fw.l2l_b.push_back(b);
+                fw.l2l_delta.insert(fw.l2l_delta.end(), d->second.begin(), d->second.end());
+                fw.l2l_sqrt_inf.insert(fw.l2l_sqrt_inf.end(), w->second.begin(), w->second.end());
+            }
+            sp.n_l2l = (int32_t)fw.l2l_a.size();
+            have_sparse = true;
+        }
+        if (have_sparse) {
+            sdv_sparse_prior &sp = fw.sparse;
+            sp.p2l_lmk = fw.p2l_lmk.data(); sp.p2l_delta = fw.p2l_delta.data(); sp.p2l_sqrt_inf = fw.p2l_sqrt_inf.data();
+            sp.l2l_a = fw.l2l_a.data(); sp.l2l_b = fw.l2l_b.data(); sp.l2l_delta = fw.l2l_delta.data(); sp.l2l_sqrt_inf = fw.l2l_sqrt_inf.data();
+        }
+    }
     sdv_window &w = fw.view;
     std::memset(&w, 0, sizeof(w));
     w.abi_version = SDV_ABI_VERSION;
@@ -196,6 +316,9 @@ inline void flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
     w.imu_J_dR_bg = fw.J_dR_bg.data(); w.imu_J_dv_ba = fw.J_dv_ba.data(); w.imu_J_dv_bg = fw.J_dv_bg.data();
     w.imu_J_dp_ba = fw.J_dp_ba.data(); w.imu_J_dp_bg = fw.J_dp_bg.data();
     w.imu_sigma_ba = fw.sigma_ba.data(); w.imu_sigma_bg = fw.sigma_bg.data();
+    w.dense_prior = have_dense ? &fw.dense : nullptr;
+    w.sparse_prior = have_sparse ? &fw.sparse : nullptr;
+    return true;
 }
 
 namespace detail {
@@ -288,12 +411,15 @@ class B200Optimizer {
         return solve(*local_map, fixed_frame_number, true);
     }
     const sdv_stats &lastStats() const { return _stats; }
+    // AOptimizer::_marginalization / _enable_sparsif (AOptimizer.h:88-89): what marginalize() left for the next window solve
+    std::shared_ptr<Marginalization> _marginalization = std::make_shared<Marginalization>();
+    bool _enable_sparsif = false;
 
   private:
     bool solve(LocalMap &map, size_t fixed, bool vio) {
         if (!_h) return false;
         FlatWindow fw;
-        flatten(map, fixed, vio, _kind, fw);
+        if (!flatten(map, fixed, vio, _kind, fw, _marginalization.get(), _enable_sparsif)) return false;
         const size_t F = fw.frame_vector.size(), L = fw.landmarks.size();
         std::vector<double> buf(15 * F + 3 * L + 1, 0.0);
         sdv_delta d;

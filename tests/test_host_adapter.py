@@ -23,7 +23,7 @@ def adapter_exe():
     return exe
 
 
-def graph_text(win, rng, extras=True):
+def graph_text(win, rng, extras=True, force_outlier=()):
     """Serialise a synth window as a SaDVIO-style pointer graph (frames oldest -> newest) and compute, independently,
     the flattening the reference walk produces.  `extras` adds everything the reference filters out."""
     F = win.n_frames
@@ -71,7 +71,7 @@ def graph_text(win, rng, extras=True):
     exp_triplets, exp_lmk_of = [], []
     n_kept = 0
     for l in range(L):
-        outlier = extras and l % 7 == 3
+        outlier = (extras and l % 7 == 3) or l in force_outlier
         uninit = extras and l % 11 == 5
         feats = []
         for o in range(ptr[l], ptr[l + 1]):
@@ -119,6 +119,150 @@ def test_flatten_order_is_bit_exact(adapter_exe, extras):
     assert imu == exp_imu
     tx = np.array([float(ln) for ln in out[2 + O + P:2 + O + P + F]])
     assert np.array_equal(tx, win.T_f_w[:, 3])            # frames newest -> oldest
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the marginal prior the optimizer holds (addMarginalizationResiduals, AngularAdjustmentCERESAnalytic.cpp:341-486)
+# ---------------------------------------------------------------------------------------------------------------------
+def prior_text(win):
+    """The isae::Marginalization members behind win.dense_prior / win.sparse_prior, in adapter_check's text format (only valid
+    with graph_text(..., extras=False): frame f of the window is frame F-1-f of the file, landmark l is landmark l)."""
+    F = win.n_frames
+    fmt = lambda a: " ".join(repr(float(x)) for x in np.asarray(a).reshape(-1))
+    z3, z9 = fmt(np.zeros(3)), fmt(np.zeros(9))
+    dp, sp = win.dense_prior, win.sparse_prior
+    if dp is not None:
+        ftk = F - 1 - dp.frame if dp.frame >= 0 else -1
+        out = [f"1 0 {ftk} {dp.frame_col} {dp.J.shape[1]} {dp.J.shape[0]} {len(dp.keep_lmk)}"]
+        out += [f"{int(l)} {int(c)} {z3} {z9}" for l, c in zip(dp.keep_lmk, dp.keep_col)]
+        out += [fmt(dp.J), fmt(dp.r0)]
+        if ftk >= 0:
+            out.append(fmt(np.zeros(225)))
+        out.append(f"-1 {z3} {z9}")
+    elif sp.has_imu_prior:
+        out = [f"1 1 {F - 1 - sp.frame} 0 0 0 {len(sp.p2l_lmk)}"]
+        out += [f"{int(l)} 0 {fmt(d)} {fmt(w)}" for l, d, w in zip(sp.p2l_lmk, sp.p2l_delta, sp.p2l_sqrt_inf)]
+        out += [fmt(sp.imu_sqrt_inf), f"-1 {z3} {z9}"]
+    else:
+        chain = [int(sp.l2l_a[0])] + [int(b) for b in sp.l2l_b]
+        out = [f"1 1 -1 0 0 0 {len(chain)}", f"{chain[0]} 0 {z3} {z9}"]
+        out += [f"{l} 0 {fmt(d)} {fmt(w)}" for l, d, w in zip(chain[1:], sp.l2l_delta, sp.l2l_sqrt_inf)]   # keyed on lmk_kp1 (:505-506)
+        out.append(f"{int(sp.lmk0)} {fmt(sp.lmk_prior)} {fmt(sp.lmk_sqrt_inf)}")
+    return "\n".join(out) + "\n"
+
+
+def parse_dump(text):
+    """adapter_check "dump" -> abi.Window (with its priors)."""
+    from sadvio_b200 import abi
+
+    lines = text.split("\n")
+    assert lines[0] == "dump" and lines[1] == "ok 1", lines[:2]
+    d = {}
+    for ln in lines[2:]:
+        if not ln:
+            continue
+        tok = ln.split()
+        n = int(tok[1])
+        assert len(tok) == 2 + n, tok[0]
+        d[tok[0]] = np.array([float(x) for x in tok[2:]])
+    i32 = lambda k: d[k].astype(np.int32)
+    vio, kind, F, nfix, C, L, O, P = (int(x) for x in d["dims"])
+    win = abi.Window(
+        vio=bool(vio), factor_kind=kind, n_fixed=nfix, T_f_w=d["T_f_w"].reshape(F, 12), T_s_f=d["T_s_f"].reshape(C, 12), K=d["K"].reshape(C, 4),
+        lmk_t=d["lmk_t"].reshape(L, 3), obs_lmk=i32("obs_lmk"), obs_frame=i32("obs_frame"), obs_cam=i32("obs_cam"),
+        obs_bearing=d["obs_bearing"].reshape(O, 3), obs_uv=d["obs_uv"].reshape(O, 2),
+        v=d["v"].reshape(F, 3), ba=d["ba"].reshape(F, 3), bg=d["bg"].reshape(F, 3), has_imu=d["has_imu"].astype(np.uint8),
+        has_prior=d["has_prior"].astype(np.uint8), T_prior=d["T_prior"].reshape(F, 12), inf_prior=d["inf_prior"].reshape(F, 6),
+        imu_i=i32("imu_i"), imu_j=i32("imu_j"), imu_dt=d["imu_dt"], imu_dR=d["imu_dR"].reshape(P, 9), imu_dv=d["imu_dv"].reshape(P, 3),
+        imu_dp=d["imu_dp"].reshape(P, 3), imu_cov=d["imu_cov"].reshape(P, 81), imu_J_dR_bg=d["imu_J_dR_bg"].reshape(P, 9),
+        imu_J_dv_ba=d["imu_J_dv_ba"].reshape(P, 9), imu_J_dv_bg=d["imu_J_dv_bg"].reshape(P, 9), imu_J_dp_ba=d["imu_J_dp_ba"].reshape(P, 9),
+        imu_J_dp_bg=d["imu_J_dp_bg"].reshape(P, 9), imu_sigma_ba=d["imu_sigma_ba"], imu_sigma_bg=d["imu_sigma_bg"])
+    if "dense" in d:
+        n_full, n, frame, frame_col, n_keep = (int(x) for x in d["dense"])
+        win.dense_prior = abi.DensePrior(J=d["dense_J"].reshape(n_full, n), r0=d["dense_r0"], frame=frame, frame_col=frame_col,
+                                         keep_lmk=i32("dense_keep_lmk"), keep_col=i32("dense_keep_col"))
+    if "sparse" in d:
+        has_imu, frame, n_p2l, has_lmk, lmk0, n_l2l = (int(x) for x in d["sparse"])
+        win.sparse_prior = abi.SparsePrior(
+            has_imu_prior=bool(has_imu), frame=frame, T_prior=d["sp_T_prior"], v_prior=d["sp_v_prior"], ba_prior=d["sp_ba_prior"],
+            bg_prior=d["sp_bg_prior"], imu_sqrt_inf=d["sp_imu_sqrt_inf"], p2l_lmk=i32("sp_p2l_lmk"), p2l_delta=d["sp_p2l_delta"].reshape(n_p2l, 3),
+            p2l_sqrt_inf=d["sp_p2l_sqrt_inf"].reshape(n_p2l, 9), has_lmk_prior=bool(has_lmk), lmk0=lmk0, lmk_prior=d["sp_lmk_prior"],
+            lmk_sqrt_inf=d["sp_lmk_sqrt_inf"], l2l_a=i32("sp_l2l_a"), l2l_b=i32("sp_l2l_b"), l2l_delta=d["sp_l2l_delta"].reshape(n_l2l, 3),
+            l2l_sqrt_inf=d["sp_l2l_sqrt_inf"].reshape(n_l2l, 9))
+    return win.normalise()
+
+
+def _window_with_prior(which):
+    from oracle import marginalize
+
+    win = synth.make_window("small", vio=which != "sparse_vo")
+    prior, info = marginalize.marginalize_oldest(win)
+    if which == "dense":
+        return marginalize.drop_oldest_frame(win, prior)
+    if which == "sparse_vio":
+        return marginalize.with_sparse_prior(win, marginalize.sparsify_vio(win, info))
+    return marginalize.with_sparse_prior(win, marginalize.sparsify_vo(win, info))
+
+
+@pytest.mark.parametrize("which", ["dense", "sparse_vio", "sparse_vo"])
+def test_flatten_carries_the_marginal_prior(adapter_exe, which):
+    """The adapter hands the prior of the isae::Marginalization object to the C ABI exactly as addMarginalizationResiduals wires
+    it: the flattened window equals the abi.Window the oracle's marginalisation produced (bit for bit), and the oracle
+    solves both to the same result."""
+    from oracle import oracle as orc
+
+    win = _window_with_prior(which)
+    vio = which != "sparse_vo"
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), False)
+    out = subprocess.run([adapter_exe, "dump", "1" if vio else "0", "0"], input=txt + prior_text(win), capture_output=True, text=True, check=True).stdout
+    got = parse_dump(out)
+    assert (got.n_frames, got.n_lmks, got.n_obs, got.n_imu) == (win.n_frames, win.n_lmks, win.n_obs, win.n_imu if vio else 0)
+    assert np.array_equal(got.obs_lmk, win.obs_lmk) and np.array_equal(got.obs_frame, win.obs_frame) and np.array_equal(got.lmk_t, win.lmk_t)
+    if which == "dense":
+        a, b = got.dense_prior, win.dense_prior
+        assert got.sparse_prior is None and (a.frame, a.frame_col) == (b.frame, b.frame_col)
+        assert np.array_equal(a.J, b.J) and np.array_equal(a.r0, b.r0)
+        assert np.array_equal(a.keep_lmk, b.keep_lmk) and np.array_equal(a.keep_col, b.keep_col)
+    else:
+        a, b = got.sparse_prior, win.sparse_prior
+        assert got.dense_prior is None and (a.has_imu_prior, a.has_lmk_prior) == (b.has_imu_prior, b.has_lmk_prior)
+        if which == "sparse_vio":
+            assert a.frame == b.frame and np.array_equal(a.imu_sqrt_inf, np.asarray(b.imu_sqrt_inf).reshape(-1))
+            # IMUPriordx is built on the CURRENT state of the kept frame (…Analytic.cpp:391-397)
+            assert np.array_equal(a.T_prior, win.T_f_w[b.frame]) and np.array_equal(a.v_prior, win.v[b.frame])
+            assert np.array_equal(a.ba_prior, win.ba[b.frame]) and np.array_equal(a.bg_prior, win.bg[b.frame])
+            assert np.array_equal(a.p2l_lmk, b.p2l_lmk) and np.array_equal(a.p2l_delta, b.p2l_delta) and np.array_equal(a.p2l_sqrt_inf, b.p2l_sqrt_inf)
+        else:
+            assert a.lmk0 == b.lmk0 and np.array_equal(a.lmk_prior, b.lmk_prior) and np.array_equal(a.lmk_sqrt_inf, np.asarray(b.lmk_sqrt_inf).reshape(-1))
+            assert np.array_equal(a.l2l_a, b.l2l_a) and np.array_equal(a.l2l_b, b.l2l_b)
+            assert np.array_equal(a.l2l_delta, b.l2l_delta) and np.array_equal(a.l2l_sqrt_inf, b.l2l_sqrt_inf)
+    got.vio = win.vio
+    rc0, d0, st0 = orc.solve_window(win)
+    rc1, d1, st1 = orc.solve_window(got)
+    assert rc0 == rc1 == 0 and st0["iterations"] == st1["iterations"] and st0["final_cost"] == st1["final_cost"]
+    assert np.array_equal(d0.dpose, d1.dpose) and np.array_equal(d0.dlmk, d1.dlmk)
+
+
+def test_kept_landmark_without_parameter_block(adapter_exe):
+    """A kept landmark the window walk filtered out (outlier) still gets a parameter block, at the end, with no observation
+    (…Analytic.cpp:369-373); a prior on a frame outside the window makes the solve return false (unordered_map::at throws)."""
+    win = _window_with_prior("dense")
+    kept = int(win.dense_prior.keep_lmk[3])
+    txt, exp, _, n_kept = graph_text(win, np.random.default_rng(0), False, force_outlier={kept})
+    out = subprocess.run([adapter_exe, "dump", "1", "0"], input=txt + prior_text(win), capture_output=True, text=True, check=True).stdout
+    got = parse_dump(out)
+    assert n_kept == win.n_lmks - 1 and got.n_lmks == win.n_lmks
+    assert np.array_equal(got.lmk_t[-1], win.lmk_t[kept]) and not np.any(got.obs_lmk == got.n_lmks - 1)
+    expect = np.array([l - (l > kept) if l != kept else win.n_lmks - 1 for l in win.dense_prior.keep_lmk])
+    assert np.array_equal(got.dense_prior.keep_lmk, expect)
+    # frame_to_keep not in the window
+    bad = prior_text(win).split("\n")
+    head = bad[0].split()
+    head[2] = "0"
+    txt2, _, _, _ = graph_text(win, np.random.default_rng(0), True)        # file frame 0 is an out-of-window frame here
+    out = subprocess.run([adapter_exe, "dump", "1", "0"], input=txt2 + "\n".join([" ".join(head)] + bad[1:]), capture_output=True, text=True,
+                         check=True).stdout.split("\n")
+    assert out[:2] == ["dump", "ok 0"]
 
 
 @pytest.mark.gpu
