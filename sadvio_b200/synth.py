@@ -2,6 +2,7 @@
 
 Produces flattened windows (``abi.Window``) of the shapes SURVEY.md §8(d) fixes:
 
+    C1  10 KF x  1 250 landmarks x  10 000 obs   EuRoC ground truth + the eth.yaml stereo rig (plumbing, CPU only)
     C2  20 KF x  2 000 landmarks x  15 000 obs   stereo + IMU
     C3  50 KF x 10 000 landmarks x  80 000 obs   full VIO factor set          (headline)
     C4  30 KF x  4 000 landmarks x  24 000 obs   two non-overlapping cameras, no IMU (localMapBA)
@@ -16,6 +17,7 @@ This module never imports ``oracle``; tests compare its pre-integration against 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -208,9 +210,13 @@ class SynthConfig:
     seed: int = 20260925
     perturb: bool = True
     prior_on_oldest: bool = True
+    trajectory: str = "circle"     # "circle": the analytic 6-dof curve of SURVEY.md §8d; "euroc": the EuRoC ground truth (C1)
 
 
 CONFIGS = {
+    # BASELINE config 1 (plumbing, CPU only): 10 keyframes 0.5 s apart on the EuRoC ground truth from sample 2000 on, IMU by
+    # differentiating it as cpp/tests/imu_test.cpp:741-757 does, the stereo rig of eth.yaml, landmarks sampled in view.
+    "C1": SynthConfig("C1", 10, 1250, span=4, kf_dt=0.5, seed=20260925 + 1, trajectory="euroc"),
     "tiny": SynthConfig("tiny", 6, 40, span=3, seed=20260925 + 100),
     "small": SynthConfig("small", 10, 300, span=4, seed=20260925 + 101),
     "C2": SynthConfig("C2", 20, 2000, span=4, short_every=8, seed=20260925 + 2),
@@ -220,18 +226,21 @@ CONFIGS = {
 }
 
 
-def make_window(cfg: SynthConfig | str, **overrides) -> abi.Window:
-    if isinstance(cfg, str):
-        cfg = CONFIGS[cfg]
-    if overrides:
-        cfg = SynthConfig(**{**cfg.__dict__, **overrides})
-    rng = np.random.Generator(np.random.MT19937(cfg.seed))
-    F = cfg.n_frames
-    steps = int(round(cfg.kf_dt * RATE_HZ))
-    dt = 1.0 / RATE_HZ
-    n_samples = (F - 1) * steps + 1
+def _integrate(R, acc_clean, p0, v0, dt):
+    """Position / velocity by the recursion of IMU.cpp:35-41 with the true (noise-free, bias-free) specific force."""
+    n = R.shape[0]
+    p = np.zeros((n, 3))
+    v = np.zeros((n, 3))
+    p[0], v[0] = p0, v0
+    for k in range(n - 1):
+        a_b = acc_clean[k]
+        v[k + 1] = v[k] + R[k] @ a_b * dt + GRAVITY * dt
+        p[k + 1] = p[k] + v[k] * dt + R[k] @ a_b * (0.5 * dt * dt) + GRAVITY * (0.5 * dt * dt)
+    return p, v
 
-    # ---- ground-truth orientation (analytic) and IMU-consistent position/velocity (integrated as the reference does)
+
+def _circle_trajectory(n_samples, dt):
+    """Smooth 6-dof curve: circle r = 3 m at 0.5 m/s with +-10 deg roll / pitch oscillation."""
     t = np.arange(n_samples) * dt
     radius, speed = 3.0, 0.5
     yaw_rate = speed / radius
@@ -251,8 +260,6 @@ def make_window(cfg: SynthConfig | str, **overrides) -> abi.Window:
         return a
 
     R = np.stack([R_of(tt) for tt in t])
-    ba_true = np.array([0.02, -0.01, 0.015])
-    bg_true = np.array([0.001, -0.002, 0.0015])
     gyr_clean = np.zeros((n_samples, 3))
     acc_clean = np.zeros((n_samples, 3))
     for k in range(n_samples):
@@ -261,14 +268,61 @@ def make_window(cfg: SynthConfig | str, **overrides) -> abi.Window:
         else:
             gyr_clean[k] = gyr_clean[k - 1]
         acc_clean[k] = R[k].T @ (acc_world(t[k]) - GRAVITY)
-    p = np.zeros((n_samples, 3))
-    v = np.zeros((n_samples, 3))
-    p[0] = np.array([radius, 0.0, 0.0])
-    v[0] = np.array([0.0, speed, 0.2 * 0.8])
-    for k in range(n_samples - 1):  # IMU.cpp:35-41 with true (noise-free, bias-free) specific force
-        a_b = acc_clean[k]
-        v[k + 1] = v[k] + R[k] @ a_b * dt + GRAVITY * dt
-        p[k + 1] = p[k] + v[k] * dt + R[k] @ a_b * (0.5 * dt * dt) + GRAVITY * (0.5 * dt * dt)
+    p, v = _integrate(R, acc_clean, np.array([radius, 0.0, 0.0]), np.array([0.0, speed, 0.2 * 0.8]), dt)
+    return R, p, v, acc_clean, gyr_clean
+
+
+EUROC_SLICE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "euroc_gt_slice.npz")
+
+
+def load_euroc_slice():
+    """The committed rows of the reference's cpp/tests/euroc_gt.csv (tests/golden/make_euroc_slice.py): timestamps [s],
+    rotations body -> world, positions, velocities.  Rotations are the polar factors of Quaterniond(w,x,y,z).toRotationMatrix(),
+    which is what Eigen's Affine3d::rotation() returns for the 6-digit quaternions of the file (imu_test.cpp:21-27)."""
+    z = np.load(EUROC_SLICE)
+    q = z["q_wxyz"]
+    R = np.zeros((q.shape[0], 3, 3))
+    for k, (w, x, y, zz) in enumerate(q):
+        M = np.array([[1 - 2 * (y * y + zz * zz), 2 * (x * y - w * zz), 2 * (x * zz + w * y)],
+                      [2 * (x * y + w * zz), 1 - 2 * (x * x + zz * zz), 2 * (y * zz - w * x)],
+                      [2 * (x * zz - w * y), 2 * (y * zz + w * x), 1 - 2 * (x * x + y * y)]])
+        U, _, Vt = np.linalg.svd(M)
+        R[k] = U @ Vt
+    return z["timestamp_ns"].astype(np.float64) * 1e-9, R, z["p"].copy(), z["v"].copy()
+
+
+def _euroc_trajectory(n_samples, dt):
+    """EuRoC ground truth from sample 2000 on, measurements by differentiating it exactly as the reference's simuEuroc does
+    (imu_test.cpp:741-757: acc from the velocity difference rotated by the CURRENT attitude, gyr from the attitude
+    increment); position / velocity re-integrated from them so that the IMU factors and the poses agree."""
+    ts, R, p_gt, v_gt = load_euroc_slice()
+    assert n_samples + 1 <= ts.size, "the committed EuRoC slice is too short for this window"
+    acc_clean = np.zeros((n_samples, 3))
+    gyr_clean = np.zeros((n_samples, 3))
+    for k in range(n_samples):
+        h = ts[k + 1] - ts[k]
+        acc_clean[k] = (1 / h) * (R[k + 1].T @ (v_gt[k + 1] - v_gt[k])) - R[k + 1].T @ GRAVITY
+        gyr_clean[k] = (1 / h) * log_so3(R[k].T @ R[k + 1])
+    R = R[:n_samples].copy()
+    p, v = _integrate(R, acc_clean, p_gt[0], v_gt[0], dt)
+    return R, p, v, acc_clean, gyr_clean
+
+
+def make_window(cfg: SynthConfig | str, **overrides) -> abi.Window:
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    if overrides:
+        cfg = SynthConfig(**{**cfg.__dict__, **overrides})
+    rng = np.random.Generator(np.random.MT19937(cfg.seed))
+    F = cfg.n_frames
+    steps = int(round(cfg.kf_dt * RATE_HZ))
+    dt = 1.0 / RATE_HZ
+    n_samples = (F - 1) * steps + 1
+
+    # ---- ground-truth orientation and IMU-consistent position/velocity (integrated as the reference does)
+    R, p, v, acc_clean, gyr_clean = (_euroc_trajectory if cfg.trajectory == "euroc" else _circle_trajectory)(n_samples, dt)
+    ba_true = np.array([0.02, -0.01, 0.015])
+    bg_true = np.array([0.001, -0.002, 0.0015])
 
     kf_idx = np.arange(F) * steps               # time order: keyframe k at sample kf_idx[k]
     T_w_f_gt = np.zeros((F, 4, 4))

@@ -124,21 +124,10 @@ class OracleOptimizer:
 
 def _euroc_samples():
     """meas_vec / pose_vec / vel_vec / ts_vec of imu_test.cpp:741-757 from the committed slice of euroc_gt.csv
-    (tests/golden/make_euroc_slice.py).  Rotations are the polar factors of Quaterniond(w,x,y,z).toRotationMatrix(), which is
-    what Affine3d::rotation() returns for the 6-digit quaternions of the file."""
-    import os
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "euroc_gt_slice.npz"))
-    ts = z["timestamp_ns"].astype(np.float64) * 1e-9                          # read_line_euroc, :34
-    q, p, v = z["q_wxyz"], z["p"], z["v"]
+    (tests/golden/make_euroc_slice.py, read by synth.load_euroc_slice)."""
+    from sadvio_b200 import synth
+    ts, R, p, v = synth.load_euroc_slice()                                    # read_line_euroc, :9-39
     n = ts.size
-    R = np.zeros((n, 3, 3))
-    for k in range(n):
-        w, x, y, zz = q[k]
-        M = np.array([[1 - 2 * (y * y + zz * zz), 2 * (x * y - w * zz), 2 * (x * zz + w * y)],
-                      [2 * (x * y + w * zz), 1 - 2 * (x * x + zz * zz), 2 * (y * zz - w * x)],
-                      [2 * (x * zz - w * y), 2 * (y * zz + w * x), 1 - 2 * (x * x + y * y)]])
-        U, _, Vt = np.linalg.svd(M)
-        R[k] = U @ Vt
     acc, gyr = np.zeros((n - 1, 3)), np.zeros((n - 1, 3))
     for k in range(n - 1):
         dt = ts[k + 1] - ts[k]

@@ -23,6 +23,28 @@ def test_reference_bias_estimation():  # imu_test.cpp:545-568 (tolerance 1e-5)
     rf.check_bias(win, d)
 
 
+def test_c1_euroc_plumbing_window():
+    """BASELINE config 1 (CPU only): 10 keyframes 0.5 s apart on the EuRoC ground truth from sample 2000 on, IMU
+    by differentiating it as imu_test.cpp:741-757 does, the stereo rig of eth.yaml, ~10 k observations."""
+    win = synth.make_window("C1")
+    assert (win.n_frames, win.n_lmks, win.n_obs, win.n_imu) == (10, 1250, 10000, 9) and win.vio and win.n_fixed == 1
+    assert np.allclose(win.imu_dt, 0.5)                              # < 1 s: no IMU factor is skipped (AOptimizer.cpp:69)
+    # the pre-integrated deltas of the generator equal the oracle's processIMU chain on this trajectory too
+    ts, R, p_gt, v_gt = synth.load_euroc_slice()
+    gt = win.meta["T_f_w_gt"]
+    R0 = gt[-1].reshape(3, 4)[:, :3].T                               # oldest keyframe = EuRoC sample 2000
+    assert np.abs(R0 - R[0]).max() < 1e-12
+    rc, d, st = orc.solve_window(win, nthreads=4)
+    assert rc == 0 and st["termination"] in ("FUNCTION_TOLERANCE", "PARAMETER_TOLERANCE") and st["final_cost"] < 0.01 * st["initial_cost"]
+    new = synth.apply_delta(win, d)
+    before, after = np.abs(win.T_f_w - gt).max(), np.abs(new["T_f_w"] - gt).max()
+    assert after < 0.1 * before
+    assert np.abs(new["v"] - win.meta["v_gt"]).max() < 0.05
+    # Schur elimination == the full normal equations SPARSE_NORMAL_CHOLESKY factors (the reference's solver for this config)
+    rc1, d1, st1 = orc.solve_window(win, mode=1)
+    assert st1["iterations"] == st["iterations"] and np.abs(d1.dpose - d.dpose).max() < 1e-9 * max(1.0, np.abs(d.dpose).max())
+
+
 def test_reference_euroc_bias_run():  # imu_test.cpp:885-945 (tolerance 0.02 on both biases of the 30th keyframe)
     """The reference's longest end-to-end test of the window solve: 29 consecutive localMapVIOptimization calls on a growing
     window, each followed by the state write-back and biasDeltaCorrection, starting from zero biases."""
