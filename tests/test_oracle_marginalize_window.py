@@ -225,3 +225,52 @@ def test_sparsified_vo_prior():
     assert w2.sparse_prior.lmk0 >= 0 and w2.sparse_prior.l2l_a.max() < w2.n_lmks
     rc, d2, st = oracle.solve_window(w2, nthreads=4)
     assert rc == 0 and st["final_cost"] <= st["initial_cost"]
+
+
+def _toy_window():
+    """The reference's toy graph (marginalization_test.cpp:26-197) as a flattened window: frame 0 at the origin, frame 1 one metre
+    ahead, a stereo pair 0.2 apart on both, landmark 0 seen from frame 0 only, landmarks 1 and 2 from both frames."""
+    from sadvio_b200 import abi
+
+    K = np.array([100.0, 100.0, 400.0, 400.0])
+    T_left, T_right = np.eye(3, 4), np.eye(3, 4)
+    T_right[1, 3] = 0.2                                                     # :47-49
+    T_f0, T_f1 = np.eye(3, 4), np.eye(3, 4)
+    T_f1[2, 3] = -1.0                                                       # T_w_f1.translation = (0, 0, 1), inverted (:64-66)
+    lmk = np.array([[0.5, 0, 2.0], [-1.0, 0, 2.0], [1.0, 0, 2.0]])          # :70, :79, :88
+    T_f_w = np.stack([T_f1.reshape(12), T_f0.reshape(12)])                  # newest first
+    obs = [(0, 1, 0), (0, 1, 1), (1, 1, 0), (1, 1, 1), (1, 0, 0), (1, 0, 1), (2, 1, 0), (2, 1, 1), (2, 0, 0), (2, 0, 1)]
+    uv, bearing = [], []
+    for l, f, c in obs:
+        Tf, Ts = T_f_w[f].reshape(3, 4), (T_left, T_right)[c]
+        pc = Ts[:, :3] @ (Tf[:, :3] @ lmk[l] + Tf[:, 3]) + Ts[:, 3]
+        p = np.array([K[0] * pc[0] / pc[2] + K[2], K[1] * pc[1] / pc[2] + K[3]])
+        uv.append(p)
+        bearing.append(synth.ray_camera(K, p[None])[0])
+    o = np.array(obs, dtype=np.int32)
+    return abi.Window(vio=False, factor_kind=abi.SDV_FACTOR_ANGULAR, n_fixed=0, T_f_w=T_f_w, T_s_f=np.stack([T_left.reshape(12), T_right.reshape(12)]),
+                      K=np.stack([K, K]), lmk_t=lmk, obs_lmk=o[:, 0], obs_frame=o[:, 1], obs_cam=o[:, 2], obs_bearing=np.array(bearing),
+                      obs_uv=np.array(uv), has_prior=np.zeros(2, np.uint8), T_prior=np.tile(np.eye(3, 4).reshape(12), (2, 1)),
+                      inf_prior=np.zeros((2, 6))).normalise()
+
+
+def test_reference_toy_graph_through_the_driver():
+    """preMargTest / margTest of the reference (marginalization_test.cpp:213-317) through oracle/marginalize.py."""
+    win = _toy_window()
+    marg, keep, idx, m, n = marginalize.pre_marginalize(win)
+    assert (n, m) == (6, 9)                                                 # ASSERT_EQ(_marg._n, 6), (_marg._m, 9)      (:219-220)
+    assert marg == [0] and keep == [1, 2]                                   # lmk_to_marg = {lmk_0}, two landmarks kept   (:222-223)
+    assert (idx["f0"], idx[0], idx[1], idx[2]) == (0, 6, 9, 12)             # index map before the Schur complement       (:300-303)
+    prior, info = marginalize.marginalize_oldest(win)
+    assert prior is not None and prior.frame == -1
+    assert list(prior.keep_lmk) == [1, 2] and list(prior.keep_col) == [0, 3]  # shifted by m afterwards                   (:308-309)
+    Ak = info["Ak"]
+    assert Ak.size == 36 and np.linalg.norm(Ak - Ak.T) < 1e-8               #                                              (:312-313)
+    assert abs(np.trace(Ak[0:3, 3:6])) > 0                                  # computeOffDiag(lmk_1, lmk_2) > 0            (:315-317)
+    # computeSchurComplement refuses fewer than 4 kept parameters (marginalization.cpp:215; margFailTest :321-334 reaches it
+    # with an uncorrelated frame, n = 0): here a single kept landmark, n = 3
+    sel = win.obs_lmk != 2
+    for k in ("obs_lmk", "obs_frame", "obs_cam", "obs_bearing", "obs_uv"):
+        setattr(win, k, getattr(win, k)[sel])
+    prior, _ = marginalize.marginalize_oldest(win.normalise())
+    assert prior is None
