@@ -109,6 +109,17 @@ def best_thread_count(win) -> int:
     return best
 
 
+def state_deviation(d_gpu, d_cpu) -> float:
+    """Max relative deviation of the pose / velocity / bias updates of two solves of the same window (the parity figure of
+    SURVEY.md §8d: <= 1e-6), each state group relative to its own largest entry."""
+    worst = 0.0
+    for name in ("dpose", "dv", "dba", "dbg"):
+        a, b = np.asarray(getattr(d_gpu, name)), np.asarray(getattr(d_cpu, name))
+        if b.size:
+            worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)))
+    return worst
+
+
 def cpu_baseline(win, budget_s: float = 12.0, max_solves: int = 8) -> dict:
     """The oracle port (CPU restatement of the reference path) timed on this box's host cores, bounded sample."""
     from oracle import oracle
@@ -121,6 +132,7 @@ def cpu_baseline(win, budget_s: float = 12.0, max_solves: int = 8) -> dict:
         t += time.perf_counter() - t0
         its += st["iterations"]
         n += 1
+    cpu_baseline.last_solution = (d, st)      # the checker's solution of this window, for the parity figures of the line
     return {"value": its / t, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} full solves of the same C3 window ({its} LM iterations, {t:.1f} s), oracle restatement "
                       f"(landmark Schur + dense Cholesky, std::thread x{cores} of {os.cpu_count()} host threads, fastest of a calibration sweep); not Ceres"}
@@ -322,6 +334,17 @@ def main():
 
     gt = win.meta
     new = synth.apply_delta(win, d_res)
+    solution = {"max_abs_pose_error_vs_ground_truth": float(np.abs(new["T_f_w"] - gt["T_f_w_gt"]).max())}
+    if cpu is not None:
+        try:  # parity of this very run: the CUDA solution (resident arm and C-ABI arm) against the CPU port's, same window
+            d_cpu, st_cpu = cpu_baseline.last_solution
+            solution.update({
+                "max_rel_state_deviation_vs_cpu_port": state_deviation(d_res, d_cpu),
+                "max_rel_state_deviation_vs_cpu_port_e2e": state_deviation(d_e2e, d_cpu),
+                "lm_iterations": {"b200": int(round(its_per_step)), "cpu_port": int(st_cpu["iterations"])},
+                "tolerance": 1e-6})
+        except Exception as e:  # noqa: BLE001
+            solution["parity_error"] = str(e)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -332,7 +355,7 @@ def main():
         "device_ms_per_step": dev_ms / args.steps,
         "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "kernels": kern, "jacobian_kernel_c5": jac_c5, "cpu_baseline": cpu,
-        "solution": {"max_abs_pose_error_vs_ground_truth": float(np.abs(new["T_f_w"] - gt["T_f_w_gt"]).max())},
+        "solution": solution,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

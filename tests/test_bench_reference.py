@@ -24,3 +24,23 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_state_deviation_figure():
+    """The parity figure bench.py adds to its line (`solution.max_rel_state_deviation_vs_cpu_port`): per state group, relative to
+    the group's largest entry."""
+    import numpy as np
+
+    import bench
+    from sadvio_b200 import abi
+
+    a, b = abi.Delta.zeros(3, 2), abi.Delta.zeros(3, 2)
+    b.dpose[:] = 1.0
+    b.dv[:] = 1e-3
+    a.dpose[:] = 1.0
+    a.dv[:] = 1e-3
+    assert bench.state_deviation(a, b) == 0.0
+    a.dv[1, 2] += 1e-9                       # 1e-6 of the velocity group's scale, although tiny next to the poses
+    assert abs(bench.state_deviation(a, b) - 1e-6) < 1e-12
+    a.dlmk[:] = 5.0                          # landmarks are not part of the state figure
+    assert abs(bench.state_deviation(a, b) - 1e-6) < 1e-12
