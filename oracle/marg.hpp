@@ -16,6 +16,152 @@
 
 namespace orc {
 
+// Symmetric eigen-decomposition A = V diag(w) V^T by Householder tridiagonalisation followed by the implicit QL iteration
+// (the classical tred2 / tql2 pair of the Handbook for Automatic Computation — the same two stages Eigen's
+// SelfAdjointEigenSolver runs, marginalization.cpp:229,323); row-major n x n, eigenvalues ascending like Eigen.
+// O(n^3) with a small constant: the chained priors of a sliding window reach n ~ 400, where the cyclic Jacobi below needs
+// tens of seconds.  jacobi_eig stays as the independent cross-check (tests/test_oracle_marginalization.py).
+inline void sym_eig(int n, const double *A_in, std::vector<double> &w, std::vector<double> &Vout) {
+    std::vector<double> V(A_in, A_in + (size_t)n * n), d(n, 0.0), e(n, 0.0);
+    auto at = [&](int i, int j) -> double & { return V[(size_t)i * n + j]; };
+    if (n == 0) {
+        w.clear();
+        Vout.clear();
+        return;
+    }
+    for (int j = 0; j < n; j++) d[j] = at(n - 1, j);
+    for (int i = n - 1; i > 0; i--) { // Householder reduction to tridiagonal form
+        double scale = 0.0, h = 0.0;
+        for (int k = 0; k < i; k++) scale += std::fabs(d[k]);
+        if (scale == 0.0) {
+            e[i] = d[i - 1];
+            for (int j = 0; j < i; j++) {
+                d[j] = at(i - 1, j);
+                at(i, j) = 0.0;
+                at(j, i) = 0.0;
+            }
+        } else {
+            for (int k = 0; k < i; k++) {
+                d[k] /= scale;
+                h += d[k] * d[k];
+            }
+            double f = d[i - 1];
+            double g = std::sqrt(h);
+            if (f > 0) g = -g;
+            e[i] = scale * g;
+            h -= f * g;
+            d[i - 1] = f - g;
+            for (int j = 0; j < i; j++) e[j] = 0.0;
+            for (int j = 0; j < i; j++) { // similarity transformation of the remaining columns
+                f = d[j];
+                at(j, i) = f;
+                g = e[j] + at(j, j) * f;
+                for (int k = j + 1; k <= i - 1; k++) {
+                    g += at(k, j) * d[k];
+                    e[k] += at(k, j) * f;
+                }
+                e[j] = g;
+            }
+            f = 0.0;
+            for (int j = 0; j < i; j++) {
+                e[j] /= h;
+                f += e[j] * d[j];
+            }
+            const double hh = f / (h + h);
+            for (int j = 0; j < i; j++) e[j] -= hh * d[j];
+            for (int j = 0; j < i; j++) {
+                f = d[j];
+                g = e[j];
+                for (int k = j; k <= i - 1; k++) at(k, j) -= f * e[k] + g * d[k];
+                d[j] = at(i - 1, j);
+                at(i, j) = 0.0;
+            }
+        }
+        d[i] = h;
+    }
+    for (int i = 0; i < n - 1; i++) { // accumulate the transformations
+        at(n - 1, i) = at(i, i);
+        at(i, i) = 1.0;
+        const double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = 0; k <= i; k++) d[k] = at(k, i + 1) / h;
+            for (int j = 0; j <= i; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += at(k, i + 1) * at(k, j);
+                for (int k = 0; k <= i; k++) at(k, j) -= g * d[k];
+            }
+        }
+        for (int k = 0; k <= i; k++) at(k, i + 1) = 0.0;
+    }
+    for (int j = 0; j < n; j++) {
+        d[j] = at(n - 1, j);
+        at(n - 1, j) = 0.0;
+    }
+    at(n - 1, n - 1) = 1.0;
+    e[0] = 0.0;
+    // implicit QL on the tridiagonal matrix (d, e)
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    double f = 0.0, tst1 = 0.0;
+    const double eps = std::ldexp(1.0, -52);
+    for (int l = 0; l < n; l++) {
+        tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+        int m = l;
+        while (m < n - 1 && std::fabs(e[m]) > eps * tst1) m++;
+        if (m > l) {
+            int iter = 0;
+            do {
+                if (++iter > 200) break;
+                double g = d[l];
+                double p = (d[l + 1] - g) / (2.0 * e[l]);
+                double r = std::hypot(p, 1.0);
+                if (p < 0) r = -r;
+                d[l] = e[l] / (p + r);
+                d[l + 1] = e[l] * (p + r);
+                const double dl1 = d[l + 1];
+                double h = g - d[l];
+                for (int i = l + 2; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+                const double el1 = e[l + 1];
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2;
+                    c2 = c;
+                    s2 = s;
+                    g = c * e[i];
+                    h = c * p;
+                    r = std::hypot(p, e[i]);
+                    e[i + 1] = s * r;
+                    s = e[i] / r;
+                    c = p / r;
+                    p = c * d[i] - s * g;
+                    d[i + 1] = h + s * (c * g + s * d[i]);
+                    for (int k = 0; k < n; k++) {
+                        h = at(k, i + 1);
+                        at(k, i + 1) = s * at(k, i) + c * h;
+                        at(k, i) = c * at(k, i) - s * h;
+                    }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p;
+                d[l] = c * p;
+            } while (std::fabs(e[l]) > eps * tst1);
+        }
+        d[l] += f;
+        e[l] = 0.0;
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return d[a] < d[b]; });
+    w.resize(n);
+    Vout.assign((size_t)n * n, 0.0);
+    for (int c = 0; c < n; c++) {
+        w[c] = d[order[c]];
+        for (int r = 0; r < n; r++) Vout[(size_t)r * n + c] = at(r, order[c]);
+    }
+}
+
 // Symmetric eigen-decomposition A = V diag(w) V^T (cyclic Jacobi, row-major n x n, eigenvalues ascending like Eigen).
 inline void jacobi_eig(int n, const double *A_in, std::vector<double> &w, std::vector<double> &V) {
     std::vector<double> A(A_in, A_in + (size_t)n * n);
@@ -74,7 +220,7 @@ inline bool schur_prior(int m, int n, const double *A, const double *b, double e
     std::vector<double> Amm((size_t)m * m), wm, Vm;
     for (int i = 0; i < m; i++)
         for (int j = 0; j < m; j++) Amm[(size_t)i * m + j] = 0.5 * (A[(size_t)i * N + j] + A[(size_t)j * N + i]);
-    jacobi_eig(m, Amm.data(), wm, Vm);
+    sym_eig(m, Amm.data(), wm, Vm);
     // Ak = Arr - Arm Amm^+ Arm^T, bk = brr - Arm Amm^+ bmm   (:242-248); Arm = A.block(m, 0, n, m).  With
     // Amm^+ = V diag(1/w) V^T the products are formed as (Arm V) diag(1/w) (Arm V)^T: the same algebra, symmetric by
     // construction also when a kept eigenvalue is numerical noise just above eps (the reference's own toy graph has one).
@@ -105,7 +251,7 @@ inline bool schur_prior(int m, int n, const double *A, const double *b, double e
     }
     // rank-revealing decomposition of Ak: eigenvalues > eps kept (:318-342)
     std::vector<double> wk, Vk;
-    jacobi_eig(n, Ak.data(), wk, Vk);
+    sym_eig(n, Ak.data(), wk, Vk);
     n_full = 0;
     for (int k = 0; k < n; k++) n_full += wk[k] > eps ? 1 : 0;
     U.assign((size_t)n * n_full, 0.0);

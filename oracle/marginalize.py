@@ -17,41 +17,52 @@ from oracle import oracle
 from sadvio_b200 import abi
 
 
-def pre_marginalize(win: abi.Window):
+def pre_marginalize(win: abi.Window, last: abi.DensePrior | None = None):
     """marginalization.cpp:23-143 for point landmarks: returns (marg, keep, idx) — landmark ids to marginalise / to keep (in
-    landmark order, as getLandmarks() is walked) and the parameter index map {('f0'|'f1'|landmark id): first column}."""
+    landmark order, as getLandmarks() is walked) and the parameter index map {('f0'|'f1'|landmark id): first column}.
+    `last` is the previous marginalisation (`_marginalization_last`) in this window's indices: its kept landmarks carry the
+    hasPrior() flag (:74) and are appended to the kept set when frame 0 does not bring them in itself (:118-142; the
+    outlier branch :124-127 cannot occur here, outliers never reach a flattened window)."""
     F = win.n_frames
     f0 = F - 1
     marg, keep = [], []
+    with_prior = set(int(l) for l in last.keep_lmk) if last is not None else set()
     lm_of_f0 = np.unique(win.obs_lmk[win.obs_frame == f0])
     for l in lm_of_f0:
         sel = win.obs_lmk == l
         num_cam = int(np.count_nonzero(sel & (win.obs_frame == f0)))      # :58-71
         lonely = not np.any(sel & (win.obs_frame != f0))
-        if num_cam != 2:                                                   # no stereo pair, no prior: ignored (:74-77)
+        if num_cam != 2 and int(l) not in with_prior:                      # no stereo pair, no prior: ignored (:74-77)
             continue
         (marg if lonely else keep).append(int(l))                          # :80-89
     idx = {"f0": 0}
-    last = 6 + (9 if win.vio else 0)                                       # :40-48
+    last_idx = 6 + (9 if win.vio else 0)                                       # :40-48
     for l in marg:                                                         # :93-98
-        idx[l] = last
-        last += 3
-    m = last
+        idx[l] = last_idx
+        last_idx += 3
+    m = last_idx
     n = 0
     if win.vio:                                                            # :101-106
-        idx["f1"] = last
-        last += 15
+        idx["f1"] = last_idx
+        last_idx += 15
         n += 15
     for l in keep:                                                         # :109-114
-        idx[l] = last
-        last += 3
+        idx[l] = last_idx
+        last_idx += 3
         n += 3
+    for l in ([int(q) for q in last.keep_lmk] if last is not None else []):   # "resurrected" landmarks, :118-139
+        if l not in idx:
+            keep.append(l)
+            idx[l] = last_idx
+            last_idx += 3
+            n += 3
     return marg, keep, idx, m, n
 
 
-def information(win: abi.Window, marg, keep, idx, m, n):
+def information(win: abi.Window, marg, keep, idx, m, n, last: abi.DensePrior | None = None):
     """The marginalisation blocks of …Analytic.cpp:504-687 evaluated at the current state and accumulated as in
-    marginalization.cpp:145-211.  Returns A [(m+n)^2], b [m+n]."""
+    marginalization.cpp:145-211.  Returns A [(m+n)^2], b [m+n].  `last`: the previous prior, added as one more block
+    (…Analytic.cpp:631-660) — MarginalizationFactor at dx = 0, i.e. residual r0 and the column slices of its J."""
     F = win.n_frames
     f0, f1 = F - 1, F - 2
     N = m + n
@@ -87,6 +98,17 @@ def information(win: abi.Window, marg, keep, idx, m, n):
             focal = 0.5 * (win.K[c][0] + win.K[c][1])
             r, J6, J3 = oracle.angular_eval(win.obs_bearing[o], win.T_s_f[c], win.T_f_w[f0], win.lmk_t[l], 1.0 / focal)
             add([(idx["f0"], J6), (idx[l], J3)], r)
+    if last is not None and len(last.keep_lmk):                            # …Analytic.cpp:631-660
+        blocks = []
+        if last.frame >= 0:                                                # _marginalization_last->_frame_to_keep is frame 0 now
+            assert last.frame == f0, "the previous prior must sit on the frame that is marginalised now"
+            c = last.frame_col
+            blocks += [(idx["f0"], last.J[:, c:c + 6]), (idx["f0"] + 6, last.J[:, c + 6:c + 9]), (idx["f0"] + 9, last.J[:, c + 9:c + 12]),
+                       (idx["f0"] + 12, last.J[:, c + 12:c + 15])]
+        for l, c in zip(last.keep_lmk, last.keep_col):
+            if c >= 0:                                                     # marginalization.hpp:139
+                blocks.append((idx[int(l)], last.J[:, c:c + 3]))
+        add(blocks, last.r0)
     for key, f in (("f0", f0), ("f1", f1)):                                # …Analytic.cpp:664-687
         if win.has_prior is not None and win.has_prior[f] and key in idx:
             r, J = oracle.pose_prior_eval(win.T_f_w[f], win.T_prior[f], win.inf_prior[f])
@@ -96,10 +118,12 @@ def information(win: abi.Window, marg, keep, idx, m, n):
 
 def marginalize_oldest(win: abi.Window, eps: float = 1e-12):
     """Returns (prior, info): prior = abi.DensePrior over (frame1's 15 parameters, kept landmarks) expressed for the window
-    WITHOUT its oldest keyframe, or None when the reference's marginalize() returns false; info = the intermediate results."""
+    WITHOUT its oldest keyframe, or None when the reference's marginalize() returns false; info = the intermediate results.
+    A dense prior already attached to the window is the previous marginalisation and is folded in (chained marginalisation)."""
     assert win.factor_kind == 0, "AngularAdjustmentCERESAnalytic::marginalize uses bearing factors"
-    marg, keep, idx, m, n = pre_marginalize(win)
-    A, b = information(win, marg, keep, idx, m, n)
+    last = win.dense_prior
+    marg, keep, idx, m, n = pre_marginalize(win, last)
+    A, b = information(win, marg, keep, idx, m, n, last)
     out = oracle.schur_prior(A, b, m, eps)
     if out is None:                                                        # …Analytic.cpp:690-695
         return None, {"marg": marg, "keep": keep, "idx": idx, "m": m, "n": n, "A": A, "b": b}
@@ -122,9 +146,11 @@ def drop_oldest_frame(win: abi.Window, prior: abi.DensePrior | None) -> abi.Wind
     keep_obs = win.obs_frame != f0
     lm_alive = np.zeros(win.n_lmks, dtype=bool)
     lm_alive[np.unique(win.obs_lmk[keep_obs])] = True
+    if prior is not None:
+        lm_alive[prior.keep_lmk] = True       # a kept landmark nobody else observes stays as a prior-only parameter block
     remap = np.cumsum(lm_alive) - 1
     w = copy.copy(win)
-    w.meta = {}
+    w.meta = {"lmk_from": np.flatnonzero(lm_alive)}     # landmark l of the shorter window is landmark lmk_from[l] of `win`
     w.n_fixed = 0
     w.T_f_w = win.T_f_w[:f0].copy()
     for k in ("v", "ba", "bg", "has_imu", "has_prior", "T_prior", "inf_prior"):

@@ -225,6 +225,18 @@ def bias_delta_correction(state, d_ba, d_bg):
     return s
 
 
+def sym_eig(A, method: str = "ql"):
+    """Eigen-decomposition of a symmetric matrix with the oracle's own solvers (marg.hpp): "ql" = Householder + implicit QL,
+    "jacobi" = cyclic Jacobi.  Returns (w ascending, V with eigenvectors in columns)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    w, V = np.zeros(n), np.zeros((n, n))
+    L = lib()
+    L.orc_sym_eig.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.orc_sym_eig(n, _p(A), 0 if method == "ql" else 1, _p(w), _p(V))
+    return w, V
+
+
 def schur_prior(A, b, m: int, eps: float = 1e-12):
     """Dense core of the reference's marginal-prior construction (marginalization.cpp:213-265, 318-342, 516-530): the first m
     parameters of the information matrix A / gradient b are marginalised.  Returns None when the reference returns false

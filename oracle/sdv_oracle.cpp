@@ -1379,6 +1379,16 @@ int orc_abi_version(void) { return SDV_ABI_VERSION; }
 }
 
 extern "C" {
+// Symmetric eigen-decomposition used by the marginal-prior construction: method 0 = Householder + implicit QL (what
+// schur_prior uses), 1 = cyclic Jacobi (independent cross-check).  w [n] ascending, V [n*n] row-major, columns = eigenvectors.
+int orc_sym_eig(int n, const double *A, int method, double *w, double *V) {
+    std::vector<double> vw, vV;
+    if (method == 0) orc::sym_eig(n, A, vw, vV);
+    else orc::jacobi_eig(n, A, vw, vV);
+    std::copy(vw.begin(), vw.end(), w);
+    std::copy(vV.begin(), vV.end(), V);
+    return 0;
+}
 // Dense core of the marginal-prior construction (marg.hpp).  Returns 1 on success, 0 when the reference returns false.
 // Output buffers must hold n*n, n, n*n, n, n*n, n doubles; *n_full receives the rank.
 int orc_schur_prior(int m, int n, const double *A, const double *b, double eps, double *Ak, double *bk, int *n_full, double *U, double *Lambda,

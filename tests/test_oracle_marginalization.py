@@ -106,3 +106,20 @@ def test_rank_deficient_marginal_block_uses_the_pseudo_inverse():
     o1, o2 = oracle.schur_prior(A, b, m=9), oracle.schur_prior(A2, b2, m=10)
     assert np.abs(o1["Ak"] - o2["Ak"]).max() <= 1e-9 * np.abs(o1["Ak"]).max()
     assert np.abs(o1["bk"] - o2["bk"]).max() <= 1e-9 * max(1.0, np.abs(o1["bk"]).max())
+
+
+@pytest.mark.parametrize("n,rank", [(1, 1), (2, 2), (7, 7), (40, 40), (60, 23), (150, 150)])
+def test_symmetric_eigen_solvers(n, rank):
+    """The two eigen-solvers of marg.hpp (Householder + implicit QL — the one schur_prior uses, the same two stages as Eigen's
+    SelfAdjointEigenSolver — and cyclic Jacobi) against numpy.linalg.eigvalsh, on full-rank and rank-deficient matrices."""
+    rng = np.random.default_rng(n * 100 + rank)
+    B = rng.normal(size=(n, rank))
+    A = B @ B.T + (0.0 if rank < n else 1e-3) * np.eye(n)
+    ref = np.linalg.eigvalsh(A)
+    scale = max(1.0, np.abs(ref).max())
+    for method in ("ql", "jacobi"):
+        w, V = oracle.sym_eig(A, method)
+        assert np.all(np.diff(w) >= 0)                                   # ascending, as Eigen returns them
+        assert np.abs(w - ref).max() <= 1e-12 * scale * n
+        assert np.abs(V.T @ V - np.eye(n)).max() <= 1e-12 * n
+        assert np.abs(V @ np.diag(w) @ V.T - A).max() <= 1e-12 * scale * n

@@ -274,3 +274,84 @@ def test_reference_toy_graph_through_the_driver():
         setattr(win, k, getattr(win, k)[sel])
     prior, _ = marginalize.marginalize_oldest(win.normalise())
     assert prior is None
+
+
+def _schur(A, b, m_idx, r_idx):
+    Amm = A[np.ix_(m_idx, m_idx)]
+    Arm = A[np.ix_(r_idx, m_idx)]
+    Ainv = np.linalg.inv(0.5 * (Amm + Amm.T))
+    return A[np.ix_(r_idx, r_idx)] - Arm @ Ainv @ Arm.T, b[r_idx] - Arm @ Ainv @ b[m_idx]
+
+
+def test_chained_marginalisation_conserves_information():
+    """The second marginalisation folds the previous prior in as one more block (…Analytic.cpp:631-660, preMarginalize
+    :118-142).  With the state untouched in between, marginalising frame A and then frame B must give the information the
+    joint elimination of both gives (Schur complements compose) — with the gradient of the first prior entering NEGATED, the
+    reference's r0 sign convention (test_reference_sign_convention_of_r0)."""
+    win = synth.make_window("small")
+    F = win.n_frames
+    prior1, info1 = marginalize.marginalize_oldest(win)
+    w1 = marginalize.drop_oldest_frame(win, prior1)
+    assert w1.dense_prior.frame == w1.n_frames - 1                       # the prior sits on the frame that goes next
+    prior2, info2 = marginalize.marginalize_oldest(w1)                   # chained: w1.dense_prior is _marginalization_last
+    assert prior2 is not None
+    lmk_from = w1.meta["lmk_from"]
+    # every landmark of the first prior is a variable of the second marginalisation: marginalised if frame B was its last
+    # observer, kept otherwise (also when frame B does not see it at all — the "resurrected" branch)
+    for l in w1.dense_prior.keep_lmk:
+        assert int(l) in info2["idx"]
+    # ---- joint information over (frame A, frame B, frame C, landmarks in `win` numbering)
+    w1_plain = marginalize.drop_oldest_frame(win, None)
+    marg2, keep2, idx2, m2, n2 = marginalize.pre_marginalize(w1_plain, w1.dense_prior)
+    assert (marg2, keep2, idx2, m2, n2) == (info2["marg"], info2["keep"], info2["idx"], info2["m"], info2["n"])
+    A2, b2 = marginalize.information(w1_plain, marg2, keep2, idx2, m2, n2, None)      # the factors of step 2 without the prior
+    A1, b1 = info1["A"], info1["b"]
+    col, nxt = {}, 0
+
+    def var(key, size):
+        nonlocal nxt
+        if key not in col:
+            col[key] = nxt
+            nxt += size
+        return col[key]
+
+    maps = []
+    for idx, names in ((info1["idx"], {"f0": "A", "f1": "B"}), (idx2, {"f0": "B", "f1": "C"})):
+        mp = {}
+        for k, c in idx.items():
+            if k in names:
+                mp[c] = (var(names[k], 15), 15)
+            else:
+                g = int(k) if names["f0"] == "A" else int(lmk_from[int(k)])
+                mp[c] = (var(("l", g), 3), 3)
+        maps.append(mp)
+    N = nxt
+    Aj, bj = np.zeros((N, N)), np.zeros(N)
+    for (Ax, bx, sign), mp in (((A1, b1, -1.0), maps[0]), ((A2, b2, 1.0), maps[1])):
+        loc = np.concatenate([np.arange(c, c + s) for c, (g, s) in sorted(mp.items())])
+        glo = np.concatenate([np.arange(g, g + s) for c, (g, s) in sorted(mp.items())])
+        Aj[np.ix_(glo, glo)] += Ax[np.ix_(loc, loc)]
+        bj[glo] += sign * bx[loc]
+    # variables that survive step 2, in the order of the second prior's columns
+    keep_cols = np.concatenate([np.arange(col["C"], col["C"] + 15)] + [np.arange(col[("l", int(lmk_from[l]))], col[("l", int(lmk_from[l]))] + 3) for l in keep2])
+    gone = np.setdiff1d(np.arange(N), keep_cols)
+    Ak_joint, bk_joint = _schur(Aj, bj, gone, keep_cols)
+    scale = np.abs(Ak_joint).max()
+    assert np.abs(info2["Ak"] - Ak_joint).max() <= 1e-7 * scale
+    assert np.abs(info2["bk"] - bk_joint).max() <= 1e-7 * max(1.0, np.abs(bk_joint).max())
+    # and the back end's loop goes on: solve, write back, marginalise, drop — until landmarks that entered a prior while other
+    # keyframes still saw them are marginalised themselves (their last observer becomes the oldest keyframe)
+    from sadvio_b200 import api
+
+    w, from_prior_then_marginalised = marginalize.drop_oldest_frame(w1, prior2), 0
+    assert w.n_frames == F - 2
+    for _ in range(4):
+        rc, d, st = oracle.solve_window(w, nthreads=4)
+        assert rc == 0 and st["final_cost"] <= st["initial_cost"]
+        api.write_back(w, d, True)
+        last_keep = set(int(l) for l in w.dense_prior.keep_lmk)
+        prior, info = marginalize.marginalize_oldest(w)
+        assert prior is not None and np.abs(info["Ak"] - info["Ak"].T).max() <= 1e-9 * np.abs(info["Ak"]).max()
+        from_prior_then_marginalised += len(last_keep & set(info["marg"]))
+        w = marginalize.drop_oldest_frame(w, prior)
+    assert w.n_frames == F - 6 and from_prior_then_marginalised > 0
