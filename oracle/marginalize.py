@@ -1,14 +1,18 @@
 """TEST INFRASTRUCTURE (oracle/README.md) — groundwork for SURVEY.md §8 row a15, no CUDA path yet.
 
-Restatement, on the flattened window of the C ABI, of the FIRST marginalisation of a VIO window (no previous prior):
+Restatement, on the flattened window of the C ABI, of the marginalisation the back end runs before every window solve
+(first and chained: a dense prior already attached to the window is `_marginalization_last`), VIO and VO, for both optimizers:
 
     Marginalization::preMarginalize              cpp/src/optimizers/marginalization.cpp:23-143
-    AngularAdjustmentCERESAnalytic::marginalize  cpp/src/optimizers/AngularAdjustmentCERESAnalytic.cpp:488-739
+    AngularAdjustmentCERESAnalytic::marginalize  cpp/src/optimizers/AngularAdjustmentCERESAnalytic.cpp:488-739   (factor_kind 0)
+    BundleAdjustmentCERESAnalytic::marginalize   cpp/src/optimizers/BundleAdjustmentCERESAnalytic.cpp:431-660    (factor_kind 1)
     computeInformationAndGradient                cpp/src/optimizers/marginalization.cpp:145-211
     computeSchurComplement / rankRevealling / computeJacobiansAndResiduals   (oracle/marg.hpp)
+    sparsifyVIO / sparsifyVO                     cpp/src/optimizers/marginalization.cpp:362-514
 
 frame0 = the oldest keyframe of the window (last index: frames are ordered newest -> oldest, amap.h:28-32), frame1 = the next
-one.  The factors come from the oracle's functor restatements (oracle.angular_eval, imu_factor_eval, pose_prior_eval)."""
+one.  The factors come from the oracle's functor restatements (oracle.angular_eval, reproj_eval, imu_factor_eval,
+pose_prior_eval)."""
 from __future__ import annotations
 
 import numpy as np
@@ -60,7 +64,8 @@ def pre_marginalize(win: abi.Window, last: abi.DensePrior | None = None):
 
 
 def information(win: abi.Window, marg, keep, idx, m, n, last: abi.DensePrior | None = None):
-    """The marginalisation blocks of …Analytic.cpp:504-687 evaluated at the current state and accumulated as in
+    """The marginalisation blocks of AngularAdjustmentCERESAnalytic.cpp:504-687 (bearing factors) or
+    BundleAdjustmentCERESAnalytic.cpp:446-617 (pixel factors; `win.factor_kind`) evaluated at the current state and accumulated as in
     marginalization.cpp:145-211.  Returns A [(m+n)^2], b [m+n].  `last`: the previous prior, added as one more block
     (…Analytic.cpp:631-660) — MarginalizationFactor at dx = 0, i.e. residual r0 and the column slices of its J."""
     F = win.n_frames
@@ -92,11 +97,15 @@ def information(win: abi.Window, marg, keep, idx, m, n, last: abi.DensePrior | N
         Za[0:3] = np.eye(3) * wa
         Zg[3:6] = np.eye(3) * wg
         add([(idx["f0"] + 9, -Za), (idx["f0"] + 12, -Zg), (idx["f1"] + 9, Za), (idx["f1"] + 12, Zg)], rb)
-    for l in list(keep) + list(marg):                                      # …Analytic.cpp:565-629, sigma = 1 / focal
+    pixel = win.factor_kind == abi.SDV_FACTOR_PIXEL
+    for l in list(keep) + list(marg):
         for o in np.flatnonzero((win.obs_lmk == l) & (win.obs_frame == f0)):
             c = int(win.obs_cam[o])
-            focal = 0.5 * (win.K[c][0] + win.K[c][1])
-            r, J6, J3 = oracle.angular_eval(win.obs_bearing[o], win.T_s_f[c], win.T_f_w[f0], win.lmk_t[l], 1.0 / focal)
+            if pixel:                                                      # BundleAdjustmentCERESAnalytic.cpp:512-571, sigma = 1
+                r, J6, J3 = oracle.reproj_eval(win.obs_uv[o], win.K[c], win.T_s_f[c], win.T_f_w[f0], win.lmk_t[l])
+            else:                                                          # AngularAdjustment…Analytic.cpp:565-629, sigma = 1 / focal
+                focal = 0.5 * (win.K[c][0] + win.K[c][1])
+                r, J6, J3 = oracle.angular_eval(win.obs_bearing[o], win.T_s_f[c], win.T_f_w[f0], win.lmk_t[l], 1.0 / focal)
             add([(idx["f0"], J6), (idx[l], J3)], r)
     if last is not None and len(last.keep_lmk):                            # …Analytic.cpp:631-660
         blocks = []
@@ -109,7 +118,9 @@ def information(win: abi.Window, marg, keep, idx, m, n, last: abi.DensePrior | N
             if c >= 0:                                                     # marginalization.hpp:139
                 blocks.append((idx[int(l)], last.J[:, c:c + 3]))
         add(blocks, last.r0)
-    for key, f in (("f0", f0), ("f1", f1)):                                # …Analytic.cpp:664-687
+    # pose priors: the angular optimizer adds frame 0's and frame 1's (…Analytic.cpp:664-687), the pixel one only frame 0's
+    # (BundleAdjustmentCERESAnalytic.cpp:606-617)
+    for key, f in ((("f0", f0),) if pixel else (("f0", f0), ("f1", f1))):
         if win.has_prior is not None and win.has_prior[f] and key in idx:
             r, J = oracle.pose_prior_eval(win.T_f_w[f], win.T_prior[f], win.inf_prior[f])
             add([(idx[key], J)], r)
@@ -120,7 +131,6 @@ def marginalize_oldest(win: abi.Window, eps: float = 1e-12):
     """Returns (prior, info): prior = abi.DensePrior over (frame1's 15 parameters, kept landmarks) expressed for the window
     WITHOUT its oldest keyframe, or None when the reference's marginalize() returns false; info = the intermediate results.
     A dense prior already attached to the window is the previous marginalisation and is folded in (chained marginalisation)."""
-    assert win.factor_kind == 0, "AngularAdjustmentCERESAnalytic::marginalize uses bearing factors"
     last = win.dense_prior
     marg, keep, idx, m, n = pre_marginalize(win, last)
     A, b = information(win, marg, keep, idx, m, n, last)

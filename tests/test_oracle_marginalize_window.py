@@ -37,10 +37,18 @@ def test_index_map_follows_the_reference_order(small):
     assert list(prior.keep_col) == [15 + 3 * k for k in range(len(info["keep"]))]
 
 
-def test_gradient_of_the_marginalised_factor_set(small):
+@pytest.mark.parametrize("kind", [0, 1])
+def test_gradient_of_the_marginalised_factor_set(small, kind):
     """b = sum J^T r must be the gradient of 1/2 sum r^2 of the marginalised factors w.r.t. the stacked parameters: checked by
-    central differences along random directions (exercises the index map and every block of the assembly)."""
+    central differences along random directions (exercises the index map and every block of the assembly); kind 0 = bearing
+    factors (AngularAdjustmentCERESAnalytic::marginalize), 1 = pixel factors (BundleAdjustmentCERESAnalytic::marginalize)."""
     win, prior, info = small
+    if kind == 1:
+        win = synth.make_window("small", factor_kind=1)
+        win.has_prior[win.n_frames - 2] = 1                          # a pose prior on frame 1: the pixel optimizer must ignore it
+        win.T_prior[win.n_frames - 2] = win.T_f_w[win.n_frames - 2] + 0.01
+        win.inf_prior[win.n_frames - 2] = 50.0
+        prior, info = marginalize.marginalize_oldest(win)
     idx, m, n, keep, marg = info["idx"], info["m"], info["n"], info["keep"], info["marg"]
     F = win.n_frames
     f0, f1 = F - 1, F - 2
@@ -62,10 +70,14 @@ def test_gradient_of_the_marginalised_factor_set(small):
             for o in np.flatnonzero((win.obs_lmk == l) & (win.obs_frame == f0)):
                 cam = int(win.obs_cam[o])
                 focal = 0.5 * (win.K[cam][0] + win.K[cam][1])
-                r, _, _ = oracle.angular_eval(win.obs_bearing[o], win.T_s_f[cam], win.T_f_w[f0], win.lmk_t[l], 1.0 / focal,
-                                              dx=x[a:a + 6], dp=x[idx[l]:idx[l] + 3], jac=False)
+                if kind == 1:
+                    r, _, _ = oracle.reproj_eval(win.obs_uv[o], win.K[cam], win.T_s_f[cam], win.T_f_w[f0], win.lmk_t[l], 1.0,
+                                                 dx=x[a:a + 6], dp=x[idx[l]:idx[l] + 3], jac=False)
+                else:
+                    r, _, _ = oracle.angular_eval(win.obs_bearing[o], win.T_s_f[cam], win.T_f_w[f0], win.lmk_t[l], 1.0 / focal,
+                                                  dx=x[a:a + 6], dp=x[idx[l]:idx[l] + 3], jac=False)
                 c += 0.5 * r @ r
-        for key, f in (("f0", f0), ("f1", f1)):
+        for key, f in ((("f0", f0),) if kind == 1 else (("f0", f0), ("f1", f1))):
             if win.has_prior is not None and win.has_prior[f]:
                 r, _ = oracle.pose_prior_eval(win.T_f_w[f], win.T_prior[f], win.inf_prior[f], dx=x[idx[key]:idx[key] + 6], jac=False)
                 c += 0.5 * r @ r
@@ -355,3 +367,20 @@ def test_chained_marginalisation_conserves_information():
         from_prior_then_marginalised += len(last_keep & set(info["marg"]))
         w = marginalize.drop_oldest_frame(w, prior)
     assert w.n_frames == F - 6 and from_prior_then_marginalised > 0
+
+
+def test_pixel_optimizer_marginalisation_feeds_the_next_window():
+    """BundleAdjustmentCERESAnalytic::marginalize (pixel factors, sigma = 1): prior reproduces the marginal information, the next
+    window solves with it."""
+    win = synth.make_window("small", factor_kind=1)
+    rc, d, st = oracle.solve_window(win, nthreads=4)
+    from sadvio_b200 import api
+    api.write_back(win, d, True)
+    prior, info = marginalize.marginalize_oldest(win)
+    assert prior is not None and prior.J.shape[1] == 15 + 3 * len(info["keep"])
+    scale = np.abs(info["Ak"]).max()
+    assert np.abs(prior.J.T @ prior.J - info["Ak"]).max() <= 1e-8 * scale
+    w2 = marginalize.drop_oldest_frame(win, prior)
+    assert w2.factor_kind == 1
+    rc, d2, st2 = oracle.solve_window(w2, nthreads=4)
+    assert rc == 0 and st2["final_cost"] <= st2["initial_cost"]
