@@ -1,0 +1,26 @@
+"""The planning prototypes under tools/ stay runnable (they are cited by DESIGN.md §7)."""
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_two_way_dissection_prototype_matches_a_direct_solve():
+    import numpy as np
+
+    babe = _load("babe_prototype")
+    rng = np.random.default_rng(11)
+    for nb, bw in ((47, 3), (9, 2), (4, 1)):
+        A = babe.banded_spd(nb, bw, rng)
+        b = rng.normal(size=nb * babe.BN)
+        x, nl, nr = babe.solve_babe(A, b, nb, bw)
+        assert nl + nr + bw == nb and abs(nl - nr) <= 1
+        ref = np.linalg.solve(A, b)
+        assert np.abs(x - ref).max() <= 1e-10 * np.abs(ref).max()
