@@ -90,6 +90,7 @@ struct Marginalization {
     int n = 0, n_full = 0;                                              // _n, _n_full
     std::shared_ptr<Frame> frame_to_keep;                               // _frame_to_keep (null in the VO case)
     std::vector<std::shared_ptr<Landmark>> lmk_to_keep;                 // _lmk_to_keep["pointxd"]
+    size_t n_landmark_types = 1;                                        // _lmk_to_keep.size(): landmark TYPES with kept landmarks
     std::unordered_map<const Frame *, int> map_frame_idx;               // _map_frame_idx
     std::unordered_map<const Landmark *, int> map_lmk_idx;              // _map_lmk_idx
     std::vector<double> marginalization_jacobian;                       // [n_full][n]
@@ -204,7 +205,12 @@ inline bool flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
     // parameter block yet gets one, at zero, with no observation (the "supposed to be in the map" branches, :369-373,
     // :413-417, :441-445); it is written back like any other landmark.
     bool have_dense = false, have_sparse = false;
-    if (marg && !marg->lmk_to_keep.empty()) {
+    // BundleAdjustmentCERESAnalytic wires the sparsified factors only if `_lmk_to_keep.size() > 1` — the number of landmark
+    // TYPES in the typed map, not of landmarks (BundleAdjustmentCERESAnalytic.cpp:364): with point landmarks alone the pixel
+    // optimizer adds no prior at all when sparsification is on.  Reproduced as is.
+    const bool wired = marg && !marg->lmk_to_keep.empty() &&
+                       !(enable_sparsif && factor_kind == SDV_FACTOR_PIXEL && marg->n_landmark_types <= 1);
+    if (wired) {
         auto block_of = [&](const std::shared_ptr<Landmark> &lmk) {
             auto it = lmk_idx.find(lmk.get());
             if (it != lmk_idx.end()) return it->second;

@@ -243,6 +243,21 @@ def test_flatten_carries_the_marginal_prior(adapter_exe, which):
     assert np.array_equal(d0.dpose, d1.dpose) and np.array_equal(d0.dlmk, d1.dlmk)
 
 
+def test_pixel_optimizer_skips_the_sparsified_prior_for_point_landmarks(adapter_exe):
+    """BundleAdjustmentCERESAnalytic.cpp:364 tests `_lmk_to_keep.size() > 1` — landmark TYPES, not landmarks — so with point
+    landmarks alone the pixel optimizer adds no prior when sparsification is on; the dense prior is wired for both kinds."""
+    win = _window_with_prior("sparse_vio")
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), False)
+    run = lambda kind, prior: subprocess.run([adapter_exe, "dump", "1", "0", kind], input=txt + prior, capture_output=True, text=True,
+                                             check=True).stdout
+    assert parse_dump(run("0", prior_text(win))).sparse_prior is not None
+    got = parse_dump(run("1", prior_text(win)))
+    assert got.sparse_prior is None and got.dense_prior is None and got.factor_kind == 1
+    dense = _window_with_prior("dense")
+    txt, _, _, _ = graph_text(dense, np.random.default_rng(0), False)
+    assert parse_dump(run("1", prior_text(dense))).dense_prior is not None
+
+
 def test_kept_landmark_without_parameter_block(adapter_exe):
     """A kept landmark the window walk filtered out (outlier) still gets a parameter block, at the end, with no observation
     (…Analytic.cpp:369-373); a prior on a frame outside the window makes the solve return false (unordered_map::at throws)."""
