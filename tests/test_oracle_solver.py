@@ -45,6 +45,24 @@ def test_c1_euroc_plumbing_window():
     assert st1["iterations"] == st["iterations"] and np.abs(d1.dpose - d.dpose).max() < 1e-9 * max(1.0, np.abs(d.dpose).max())
 
 
+def test_keyframe_without_imu_in_a_vio_window():
+    """A keyframe whose getIMU() is null gets no velocity / bias blocks and no IMU factor (AOptimizer.cpp:30-52, 60-73).  On the
+    flattened window its v / ba / bg columns simply carry no factor: their gradient and Hessian are zero, the LM damping keeps
+    them at zero, and norms / costs are what they are without the blocks — so `has_imu` needs no special path."""
+    win = synth.make_window("small")
+    f = 4
+    keep = (win.imu_i != f) & (win.imu_j != f)
+    for k in ("imu_i", "imu_j", "imu_dt", "imu_dR", "imu_dv", "imu_dp", "imu_cov", "imu_J_dR_bg", "imu_J_dv_ba", "imu_J_dv_bg", "imu_J_dp_ba",
+              "imu_J_dp_bg", "imu_sigma_ba", "imu_sigma_bg"):
+        setattr(win, k, getattr(win, k)[keep].copy())
+    win.has_imu[f] = 0
+    rc, d, st = orc.solve_window(win.normalise())
+    assert rc == 0 and st["final_cost"] < 0.01 * st["initial_cost"]
+    assert np.all(d.dv[f] == 0) and np.all(d.dba[f] == 0) and np.all(d.dbg[f] == 0) and np.abs(d.dpose[f]).max() > 0
+    rc1, d1, st1 = orc.solve_window(win, mode=1)                        # full normal equations: same step
+    assert st1["iterations"] == st["iterations"] and np.abs(d1.dpose - d.dpose).max() < 1e-9
+
+
 def test_reference_euroc_bias_run():  # imu_test.cpp:885-945 (tolerance 0.02 on both biases of the 30th keyframe)
     """The reference's longest end-to-end test of the window solve: 29 consecutive localMapVIOptimization calls on a growing
     window, each followed by the state write-back and biasDeltaCorrection, starting from zero biases."""
