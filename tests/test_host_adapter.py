@@ -23,7 +23,7 @@ def adapter_exe():
     return exe
 
 
-def graph_text(win, rng, extras=True, force_outlier=()):
+def graph_text(win, rng, extras=True, force_outlier=(), gap_after=None):
     """Serialise a synth window as a SaDVIO-style pointer graph (frames oldest -> newest) and compute, independently,
     the flattening the reference walk produces.  `extras` adds everything the reference filters out."""
     F = win.n_frames
@@ -45,7 +45,7 @@ def graph_text(win, rng, extras=True, force_outlier=()):
         pos += 1
     for k, f in enumerate(order):             # time order
         frame_time_pos[f] = pos
-        ts = 1_000_000_000 + k * 250_000_000
+        ts = 1_000_000_000 + k * 250_000_000 + (1_000_000_000 if gap_after is not None and k > gap_after else 0)
         has_imu = 1 if win.vio else 0
         lines.append(f"{ts} {0 if f in nonkf else 1} 1 {int(win.has_prior[f])} {has_imu} 2")
         lines.append(fmt(win.T_f_w[f]) + " " + fmt(win.T_prior[f]) + " " + fmt(win.inf_prior[f]))
@@ -97,9 +97,21 @@ def graph_text(win, rng, extras=True, force_outlier=()):
     if win.vio:
         for f in range(F):                    # frame_vector order of j (newest first)
             ps = [p for p in range(win.n_imu) if win.imu_j[p] == f]
-            if ps:
+            if ps and not (gap_after is not None and F - 1 - f == gap_after + 1):   # dt > 1 s: no IMU factor (AOptimizer.cpp:69)
                 exp_imu.append((int(win.imu_i[ps[0]]), f))
     return "\n".join(lines) + "\n", np.array(exp_triplets, dtype=np.int64).reshape(-1, 3), exp_imu, n_kept
+
+
+def test_imu_factor_skipped_across_a_long_gap(adapter_exe):
+    """Keyframes more than 1 s apart get no IMU / bias factor (AOptimizer.cpp:67-70)."""
+    win = synth.make_window("small")
+    txt, exp, exp_imu, n_kept = graph_text(win, np.random.default_rng(0), False, gap_after=3)
+    out = subprocess.run([adapter_exe, "flatten", "1", "1"], input=txt, capture_output=True, text=True, check=True).stdout.split("\n")
+    F, C, L, O, P = (int(x) for x in out[1].split())
+    assert P == win.n_imu - 1 == len(exp_imu)
+    rows = [ln.split() for ln in out[2 + O:2 + O + P]]
+    assert [(int(r[0]), int(r[1])) for r in rows] == exp_imu
+    assert all(abs(float(r[2]) - 0.25) < 1e-12 for r in rows)
 
 
 @pytest.mark.parametrize("extras", [False, True])
