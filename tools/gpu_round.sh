@@ -1,0 +1,40 @@
+#!/bin/bash
+# One gpurun call that collects everything a round needs from a B200 box, bounded in time (run from the repository root):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_round.sh full'
+#   /usr/local/graft/bin/gpurun --timeout 300 -- 'bash tools/gpu_round.sh quick [pytest -k expression]'
+#   /usr/local/graft/bin/gpurun --timeout 300 -- 'bash tools/gpu_round.sh micro backward 47 3'
+# Everything lands in gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/.
+set -u
+mode=${1:-quick}
+out=gpurun_out
+mkdir -p $out
+case "$mode" in
+quick)
+    timeout 200 python -m pytest tests -m gpu -x -q ${2:+-k "$2"} 2>&1 | tail -15 | tee $out/pytest_gpu.log
+    timeout 60 python tools/solve_once.py C3 3 2>&1 | tail -2 | tee $out/solve_once_c3.log
+    ;;
+full)
+    timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $out/pytest_gpu.log
+    timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $out/smoke.log
+    timeout 300 python bench.py --gpus 1 > $out/bench_c3_n1.json 2> $out/bench_c3_n1.err
+    tail -c 600 $out/bench_c3_n1.json
+    # launch list of the same command (times under ncu are cold-cache and serialised: shares only, never bench values)
+    SDV_NO_GRAPH=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_c3.csv \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-c5 > $out/bench_under_ncu.log 2>&1
+    ;;
+ncu)
+    # full capture of one solve's kernels (k_schur, k_chol_band, k_backsub, k_lin_visual): ${2:-C3}
+    SDV_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_schur|k_chol_band|k_backsub|k_lin_visual" -c 8 \
+        -o $out/ncu_full_${2:-C3} -f python tools/solve_once.py ${2:-C3} > $out/ncu_full.log 2>&1
+    tail -3 $out/ncu_full.log
+    ;;
+micro)
+    name=${2:?micro-benchmark name (tools/micro/<name>.cu)}
+    shift 2
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude -o /tmp/micro_$name tools/micro/$name.cu && timeout 120 /tmp/micro_$name "$@" 2>&1 | tee $out/micro_$name.log
+    ;;
+*)
+    echo "usage: gpu_round.sh quick|full|ncu|micro ..."
+    exit 2
+    ;;
+esac
