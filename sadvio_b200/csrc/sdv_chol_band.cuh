@@ -304,6 +304,68 @@ SDV_DEV void cp_async16(void *dst, const void *src) {
 }
 SDV_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+#ifndef SDV_BAND_BACKWARD_V2
+#define SDV_BAND_BACKWARD_V2 0
+#endif
+#if SDV_BAND_BACKWARD_V2
+// EXPERIMENT, off by default and not yet run on a GPU (tools/micro/backward.cu times it alone): one FULL block step of the
+// backward solve (all BW sub-diagonal blocks present) with every load of the step issued up front and the d = 1 block — the
+// only one whose x was produced by the previous step — closing the FMA chains.  Returns x_k[c] in both half-warps.
+template <int BW> SDV_DEV double band_backward_full_step(const double *sb, const double *gs, double *rvs, int k, int lane) {
+    const int c = lane & 15, hh = lane >> 4;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const double *Mi = sb + (BW + 1) * 256 + hh * 128 + c;
+    double m[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) m[q] = Mi[16 * q];
+#pragma unroll
+    for (int d = BW; d >= 2; d--) {
+        const double *Lc = sb + d * 256 + hh * 128 + c;
+        const double2 *x2 = reinterpret_cast<const double2 *>(gs + (k + d) * BN + hh * 8);
+        const double2 xa = x2[0], xb = x2[1], xc = x2[2], xd = x2[3];
+        s0 = fma(Lc[0], xa.x, s0);
+        s1 = fma(Lc[16], xa.y, s1);
+        s2 = fma(Lc[32], xb.x, s2);
+        s3 = fma(Lc[48], xb.y, s3);
+        s0 = fma(Lc[64], xc.x, s0);
+        s1 = fma(Lc[80], xc.y, s1);
+        s2 = fma(Lc[96], xd.x, s2);
+        s3 = fma(Lc[112], xd.y, s3);
+    }
+    {
+        const double *Lc = sb + 256 + hh * 128 + c;
+        double l[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) l[q] = Lc[16 * q];
+        const double2 *x2 = reinterpret_cast<const double2 *>(gs + (k + 1) * BN + hh * 8);
+        const double2 xa = x2[0], xb = x2[1], xc = x2[2], xd = x2[3];
+        s0 = fma(l[0], xa.x, s0);
+        s1 = fma(l[1], xa.y, s1);
+        s2 = fma(l[2], xb.x, s2);
+        s3 = fma(l[3], xb.y, s3);
+        s0 = fma(l[4], xc.x, s0);
+        s1 = fma(l[5], xc.y, s1);
+        s2 = fma(l[6], xd.x, s2);
+        s3 = fma(l[7], xd.y, s3);
+    }
+    double sum = (s0 + s1) + (s2 + s3);
+    sum += __shfl_xor_sync(FULL, sum, 16);
+    const double rv = gs[k * BN + c] - sum;
+    if (hh == 0) rvs[c] = rv;
+    __syncwarp();
+    const double2 *r2 = reinterpret_cast<const double2 *>(rvs + hh * 8);
+    const double2 ra = r2[0], rb = r2[1], rc = r2[2], rd = r2[3];
+    double x0 = m[0] * ra.x, x1 = m[1] * ra.y, x2v = m[2] * rb.x, x3 = m[3] * rb.y;
+    x0 = fma(m[4], rc.x, x0);
+    x1 = fma(m[5], rc.y, x1);
+    x2v = fma(m[6], rd.x, x2v);
+    x3 = fma(m[7], rd.y, x3);
+    double x = (x0 + x1) + (x2v + x3);
+    x += __shfl_xor_sync(FULL, x, 16);
+    return x;
+}
+#endif
+
 // System preparation for k_chol_band (same arithmetic as k_sysprep): gradient-tolerance test, Jacobi column scales at
 // iteration 0, LM damping -> dmp (negative = padding column), right-hand side -> gs.  Returns true (uniformly) when the
 // gradient tolerance terminates the solve.  Not inlined: its square roots and divisions would otherwise raise the register
@@ -833,6 +895,26 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             mbar_wait(&full[s], (unsigned)ph);
             BAND_TICK(3);
             const double *sb = ring + s * stage_doubles;
+#if SDV_BAND_BACKWARD_V2
+            if (nd == bw && (bw == 3 || bw == 4)) { // full step of the common band widths: specialised body
+                const double xf = bw == 3 ? band_backward_full_step<3>(sb, gs, rvs, k, lane) : band_backward_full_step<4>(sb, gs, rvs, k, lane);
+                if (hh == 0) {
+                    gs[k * BN + c] = xf;
+                    dxp[k * BN + c] = -xf;
+                }
+                __syncwarp();
+                if (lane == 0 && it + NS < nb) {
+                    const int k2 = nb - 1 - (it + NS);
+                    mbar_expect_tx(&full[s], stage_bytes);
+                    bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k2 * stage_doubles, stage_bytes, &full[s]);
+                }
+                if (++s == NS) {
+                    s = 0;
+                    ph ^= 1;
+                }
+                continue;
+            }
+#endif
             // (L_(k+d,k))^T x_(k+d), d = 1..nd: lane (c, hh) sums rows 8 hh .. 8 hh + 7 of every block; four independent chains
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
