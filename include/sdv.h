@@ -177,7 +177,10 @@ typedef struct sdv_window {
     const double *v;         /* [F][3]  IMU::getVelocity()   (vio) */
     const double *ba;        /* [F][3]  IMU::getBa()         (vio) */
     const double *bg;        /* [F][3]  IMU::getBg()         (vio) */
-    const uint8_t *has_imu;  /* [F]     frame->getIMU() != nullptr (vio); NULL => all 1 */
+    const uint8_t *has_imu;  /* [F]     frame->getIMU() != nullptr (vio); NULL => all 1.  Informational: a frame
+                                        without IMU appears in no imu[] entry (AOptimizer.cpp:60-73), so its v / ba /
+                                        bg columns carry no factor and their updates stay exactly 0 — the same
+                                        result as not creating the blocks (AOptimizer.cpp:30-52) */
     const uint8_t *has_prior;/* [F]     Frame::hasPrior(); NULL => none */
     const double *T_prior;   /* [F][12] Frame::getPrior()      (used where has_prior) */
     const double *inf_prior; /* [F][6]  Frame::getInfPrior(), used AS sqrt-information
