@@ -41,6 +41,13 @@ constexpr int BAND_MAX_STAGES = 16; // backward-solve ring (TMA bulk copies in f
 #define SDV_BAND_STREAM_UPDATES 0
 #endif
 constexpr bool BAND_STREAM_UPDATES = SDV_BAND_STREAM_UPDATES != 0;
+// First milestone of the two-way dissection, OFF by default and not yet run on a GPU: with
+// -DSDV_BAND_REV=1 the whole kernel factors P S P instead of S (P = index reversal, row i <-> n_pad-1-i, which keeps the
+// 16-column blocks aligned) and scatters the solution back — what the second CTA of the cluster will do on its half.  The
+// band of P S P is the band of S, the solution is the same up to rounding: every parity test applies unchanged.
+#ifndef SDV_BAND_REV
+#define SDV_BAND_REV 0
+#endif
 
 // shared-memory plan, identical on host and device.  The panel of a step (L_kk and P_(k+1,k) .. P_(k+bw,k), stacked) is
 // stored TRANSPOSED: column c of the stacked panel is contiguous, pan[c * pcs + 16 d + row]; pcs = 16 (bw + 1) + 4 makes the
@@ -303,6 +310,11 @@ SDV_DEV void cp_async16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 SDV_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#if SDV_BAND_REV
+SDV_DEV void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+#endif
 
 #ifndef SDV_BAND_BACKWARD_V2
 #define SDV_BAND_BACKWARD_V2 0
@@ -398,6 +410,26 @@ __device__ __noinline__ bool band_sysprep(int n, int n_pad, int ld, LMState *st,
         }
     }
     __syncthreads();
+#if SDV_BAND_REV
+    for (int i = threadIdx.x; i < n_pad; i += BCT) { // shared-memory copies (dmp, gs) in the reversed order, globals as they are
+        const int il = n_pad - 1 - i;
+        if (i < n) {
+            const double c = cdiag[i];
+            const double sc = first ? (jacobi_scaling ? 1.0 / (1.0 + sqrt(c)) : 1.0) : scale_p[i];
+            if (first) scale_p[i] = sc;
+            const double d = fmin(fmax(sc * sc * c, min_diag), max_diag) / (radius * sc * sc); // lm_damping()
+            dmp[il] = d;
+            damp_p[i] = d;
+            graw_p[i] = graw[i];
+            gs[il] = g[i];
+        } else {
+            dmp[il] = -1.0;
+            damp_p[i] = 0.0;
+            graw_p[i] = 0.0;
+            gs[il] = 0.0;
+        }
+    }
+#else
     for (int i = threadIdx.x; i < n_pad; i += BCT) {
         if (i < n) {
             const double c = cdiag[i];
@@ -415,6 +447,7 @@ __device__ __noinline__ bool band_sysprep(int n, int n_pad, int ld, LMState *st,
             gs[i] = 0.0;
         }
     }
+#endif
     if (threadIdx.x == 0) {
         st->need_grad_check = 0;
         st->scaling_done = 1;
@@ -468,7 +501,18 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             const int jj = e >> 7, r = (e >> 3) & 15, q = e & 7;
             int cs = c0 + jj;
             cs -= cs >= bwp ? bwp : 0;
+#if SDV_BAND_REV
+            // element (p, c) of P S P is element (n_pad-1-p, n_pad-1-c) of S, read from the stored (lower) triangle
+            const int np1 = P.n_pad - 1;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int gr = np1 - (i * BN + r), gc = np1 - ((j0 + jj) * BN + 2 * q + h);
+                const int hi = gr > gc ? gr : gc, lo = gr > gc ? gc : gr;
+                cp_async8(win + (rs * bwp + cs) * WBLK + r * WSTR + 2 * q + h, A + (size_t)hi * ld + lo);
+            }
+#else
             cp_async16(win + (rs * bwp + cs) * WBLK + r * WSTR + 2 * q, A + (size_t)(i * BN + r) * ld + (j0 + jj) * BN + 2 * q);
+#endif
         }
     };
     // after the copies of block row i have landed: add the damping to the diagonal (unit diagonal for padding columns); every
@@ -900,7 +944,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                 const double xf = bw == 3 ? band_backward_full_step<3>(sb, gs, rvs, k, lane) : band_backward_full_step<4>(sb, gs, rvs, k, lane);
                 if (hh == 0) {
                     gs[k * BN + c] = xf;
-                    dxp[k * BN + c] = -xf;
+                    dxp[SDV_BAND_REV ? P.n_pad - 1 - (k * BN + c) : k * BN + c] = -xf;
                 }
                 __syncwarp();
                 if (lane == 0 && it + NS < nb) {
@@ -949,7 +993,11 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             x += __shfl_xor_sync(FULL, x, 16);
             if (hh == 0) {
                 gs[k * BN + c] = x;
+#if SDV_BAND_REV
+                dxp[P.n_pad - 1 - (k * BN + c)] = -x;
+#else
                 dxp[k * BN + c] = -x;
+#endif
             }
             __syncwarp();
             if (lane == 0 && it + NS < nb) {
@@ -977,7 +1025,11 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
     const int n = P.n;
     double gd = 0, dd = 0, sn = 0, cn = 0;
     for (int i = threadIdx.x; i < P.n_pad; i += BCT) {
+#if SDV_BAND_REV
+        const double d = i < n ? -gs[P.n_pad - 1 - i] : 0.0;
+#else
         const double d = i < n ? -gs[i] : 0.0;
+#endif
         if (i >= n) dxp[i] = 0.0;
         const double xc = Bx.xp[i] + d;
         Bc.xp[i] = i < n ? xc : 0.0;
