@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     *(["-DSDV_SCHUR_PROF"] if os.environ.get("SDV_SCHUR_PROF") else []),
     *(["-DSDV_BAND_BACKWARD_V2=1"] if os.environ.get("SDV_BAND_BACKWARD_V2") else []),  # experiment, see DESIGN.md section 7
     *(["-DSDV_BAND_REV=1"] if os.environ.get("SDV_BAND_REV") else []),                  # first milestone of the two-way dissection
+    *(["-DSDV_BAND_BABE=1"] if os.environ.get("SDV_BAND_BABE") else []),                # second milestone: the 2-CTA cluster itself
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 

@@ -41,12 +41,41 @@ constexpr int BAND_MAX_STAGES = 16; // backward-solve ring (TMA bulk copies in f
 #define SDV_BAND_STREAM_UPDATES 0
 #endif
 constexpr bool BAND_STREAM_UPDATES = SDV_BAND_STREAM_UPDATES != 0;
+// -DSDV_BAND_BACKWARD_V2=1: specialised full steps in the backward solve (band_backward_full_step below), experiment.
+#ifndef SDV_BAND_BACKWARD_V2
+#define SDV_BAND_BACKWARD_V2 0
+#endif
 // First milestone of the two-way dissection, OFF by default and not yet run on a GPU: with
 // -DSDV_BAND_REV=1 the whole kernel factors P S P instead of S (P = index reversal, row i <-> n_pad-1-i, which keeps the
 // 16-column blocks aligned) and scatters the solution back — what the second CTA of the cluster will do on its half.  The
 // band of P S P is the band of S, the solution is the same up to rounding: every parity test applies unchanged.
 #ifndef SDV_BAND_REV
 #define SDV_BAND_REV 0
+#endif
+// Second milestone, OFF by default and not yet run on a GPU: -DSDV_BAND_BABE=1 adds the two-way dissection itself.  Launched
+// as a 2-CTA cluster (sdv_lib.cu does so when the band is long enough) CTA 0 eliminates block rows 0 .. nl-1 of S, CTA 1 block
+// rows 0 .. nr-1 of P S P, CTA 0 adds CTA 1's separator update (read through distributed shared memory), finishes the
+// separator and the forward substitution, solves the separator unknowns, hands them to CTA 1, and both back-substitute
+// their interiors.  Launched as a single CTA the kernel behaves as before.  tools/babe_prototype.py is the numpy model.
+#ifndef SDV_BAND_BABE
+#define SDV_BAND_BABE 0
+#endif
+#if SDV_BAND_BABE && (SDV_BAND_REV || SDV_BAND_STREAM_UPDATES || SDV_BAND_BACKWARD_V2)
+#error "SDV_BAND_BABE excludes SDV_BAND_REV, SDV_BAND_STREAM_UPDATES and SDV_BAND_BACKWARD_V2"
+#endif
+#if SDV_BAND_BABE
+#define BAND_BNB nbk
+#else
+#define BAND_BNB nb
+#endif
+#if SDV_BAND_BABE
+#define BAND_KBEG kbeg
+#define BAND_KEND kend
+#define BAND_KLIM k < kend &&
+#else
+#define BAND_KBEG 0
+#define BAND_KEND nb
+#define BAND_KLIM
 #endif
 
 // shared-memory plan, identical on host and device.  The panel of a step (L_kk and P_(k+1,k) .. P_(k+bw,k), stacked) is
@@ -310,15 +339,22 @@ SDV_DEV void cp_async16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 SDV_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-#if SDV_BAND_REV
+#if SDV_BAND_REV || SDV_BAND_BABE
 SDV_DEV void cp_async8(void *dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 #endif
-
-#ifndef SDV_BAND_BACKWARD_V2
-#define SDV_BAND_BACKWARD_V2 0
+#if SDV_BAND_BABE
+// one double from the shared memory of CTA `rank` of the cluster (same offset as `local_addr` in this CTA)
+SDV_DEV double dsmem_load(const double *local_addr, unsigned rank) {
+    unsigned local = smem_u32(local_addr), remote;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
 #endif
+
 #if SDV_BAND_BACKWARD_V2
 // EXPERIMENT, off by default and not yet run on a GPU (tools/micro/backward.cu times it alone): one FULL block step of the
 // backward solve (all BW sub-diagonal blocks present) with every load of the step issued up front and the d = 1 block — the
@@ -384,7 +420,11 @@ template <int BW> SDV_DEV double band_backward_full_step(const double *sb, const
 // pressure of the factorisation loops (the kernel is capped at 128 registers).
 __device__ __noinline__ bool band_sysprep(int n, int n_pad, int ld, LMState *st, Accum *acc, int jacobi_scaling, double gradient_tolerance,
                                           double min_diag, double max_diag, const double *A, double *scale_p, double *damp_p, double *graw_p,
-                                          double *gs, double *dmp) {
+                                          double *gs, double *dmp
+#if SDV_BAND_BABE
+                                          , bool babe, bool rev, int nloc, int nsep0 // cluster mode, reversed CTA, local rows, first separator row
+#endif
+) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double *g = A + (size_t)n_pad * ld, *cdiag = g + ld, *graw = cdiag + ld;
     const bool first = st->scaling_done == 0, check = st->need_grad_check != 0;
@@ -401,7 +441,12 @@ __device__ __noinline__ bool band_sysprep(int n, int n_pad, int ld, LMState *st,
         for (int i = 0; i < BNW; i++) mm = fmax(mm, dmp[i]);
         if (mm <= gradient_tolerance) { // uniform: every thread evaluates the same values
             __syncthreads();
+#if SDV_BAND_BABE
+            if (babe) cluster_sync_all(); // the other CTA has read the state words too
+            if (threadIdx.x == 0 && !rev) {
+#else
             if (threadIdx.x == 0) {
+#endif
                 st->status = 1 + 2; // SDV_TERM_GRADIENT_TOLERANCE
                 st->iter -= 1;      // the step Ceres never starts was already counted
                 st->need_grad_check = 0;
@@ -410,7 +455,36 @@ __device__ __noinline__ bool band_sysprep(int n, int n_pad, int ld, LMState *st,
         }
     }
     __syncthreads();
-#if SDV_BAND_REV
+#if SDV_BAND_BABE
+    // every thread of both CTAs has read the state words and the gradient maximum: only now may CTA 0 change them
+    if (babe) cluster_sync_all();
+    for (int i = threadIdx.x; i < n_pad; i += BCT) {
+        const int il = rev ? n_pad - 1 - i : i; // row of this CTA's (possibly reversed) system
+        const bool mine = !babe || il < nloc, sep = babe && rev && il >= nsep0;
+        double d = -1.0, gi = 0.0; // padding: identity block, zero right-hand side
+        if (i < n) {
+            const double c = cdiag[i];
+            const double sc = first ? (jacobi_scaling ? 1.0 / (1.0 + sqrt(c)) : 1.0) : scale_p[i];
+            if (first && !rev) scale_p[i] = sc;
+            d = fmin(fmax(sc * sc * c, min_diag), max_diag) / (radius * sc * sc); // lm_damping()
+            gi = g[i];
+        }
+        if (!rev) {
+            damp_p[i] = i < n ? d : 0.0;
+            graw_p[i] = i < n ? graw[i] : 0.0;
+        }
+        if (mine) {
+            dmp[il] = sep ? 0.0 : d; // CTA 1 carries only its UPDATE of the separator: no damping, no right-hand side there
+            gs[il] = sep ? 0.0 : gi;
+        }
+    }
+    if (threadIdx.x == 0 && !rev) {
+        st->need_grad_check = 0;
+        st->scaling_done = 1;
+        acc->grad_max_bits = 0ull;
+    }
+    return false;
+#elif SDV_BAND_REV
     for (int i = threadIdx.x; i < n_pad; i += BCT) { // shared-memory copies (dmp, gs) in the reversed order, globals as they are
         const int il = n_pad - 1 - i;
         if (i < n) {
@@ -468,7 +542,18 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
     __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8], bar_c2[2][8], colbar[2][16], colbar2[2][4], bar_r3[2];
     __shared__ int s_fail;
     const BandPlan pl = band_plan(P.n_pad, P.band_bw);
+#if SDV_BAND_BABE
+    __shared__ uint64_t bar_xsep; // CTA 1: the separator unknowns have arrived from CTA 0
+    const bool babe = cluster_size() == 2;
+    const bool rev = babe && cluster_rank() == 1;
+    const int bw = pl.bw, R = pl.R, ld = P.ld, pcs = pl.pcs, nbg = pl.nb;
+    const int nl = (nbg - bw + 1) / 2, nr = nbg - bw - nl;  // interior block rows of CTA 0 / CTA 1, separator = bw block rows
+    const int nint = babe ? (rev ? nr : nl) : nbg;          // block steps this CTA runs before the hand-over
+    const int nb = babe ? nint + bw : nbg;                  // block rows of this CTA's system (interior + separator)
+    if (rev) Lb += (size_t)nbg * (bw + 2) * 256;            // CTA 1 keeps its factor in the second half of the band storage
+#else
     const int nb = pl.nb, bw = pl.bw, R = pl.R, ld = P.ld, pcs = pl.pcs;
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *win = bsm + pl.o_win, *pan0 = bsm + pl.o_pan, *invs = bsm + pl.o_inv, *gs = bsm + pl.o_g, *dmp = bsm + pl.o_dmp;
     const int bwp = bw + 1;
@@ -501,7 +586,24 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             const int jj = e >> 7, r = (e >> 3) & 15, q = e & 7;
             int cs = c0 + jj;
             cs -= cs >= bwp ? bwp : 0;
-#if SDV_BAND_REV
+#if SDV_BAND_BABE
+            if (rev) {
+                double *dst = win + (rs * bwp + cs) * WBLK + r * WSTR + 2 * q;
+                if (i >= nint && j0 + jj >= nint) { // separator x separator: CTA 1 accumulates only its update there
+                    dst[0] = 0.0;
+                    dst[1] = 0.0;
+                } else {
+                    const int np1 = P.n_pad - 1;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) { // element (p, c) of P S P = element (n_pad-1-p, n_pad-1-c) of S, from the stored triangle
+                        const int gr = np1 - (i * BN + r), gc = np1 - ((j0 + jj) * BN + 2 * q + h);
+                        const int hi = gr > gc ? gr : gc, lo = gr > gc ? gc : gr;
+                        cp_async8(dst + h, A + (size_t)hi * ld + lo);
+                    }
+                }
+            } else
+                cp_async16(win + (rs * bwp + cs) * WBLK + r * WSTR + 2 * q, A + (size_t)(i * BN + r) * ld + (j0 + jj) * BN + 2 * q);
+#elif SDV_BAND_REV
             // element (p, c) of P S P is element (n_pad-1-p, n_pad-1-c) of S, read from the stored (lower) triangle
             const int np1 = P.n_pad - 1;
 #pragma unroll
@@ -596,7 +698,13 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
     }
     for (int i = 0; i < nb && i < R; i++) load_row(i, i, i > bw ? (i - bw) % bwp : 0, 0, BCT); // rows 0 .. R-1 (R = bw + 3, or the whole matrix)
     for (int e = threadIdx.x; e < 2 * pl.pan_doubles; e += BCT) pan0[e] = 0.0;
+#if SDV_BAND_BABE
+    if (threadIdx.x == 0) mbar_init(&bar_xsep, 1);
+    if (band_sysprep(P.n, P.n_pad, ld, st, acc, opt.jacobi_scaling, opt.gradient_tolerance, opt.min_diag, opt.max_diag, A, scale_p, damp_p, graw_p, gs, dmp,
+                     babe, rev, nb * BN, nint * BN)) {
+#else
     if (band_sysprep(P.n, P.n_pad, ld, st, acc, opt.jacobi_scaling, opt.gradient_tolerance, opt.min_diag, opt.max_diag, A, scale_p, damp_p, graw_p, gs, dmp)) { // gradient tolerance reached: no step
+#endif
         cp_async_wait_all();
         return;
     }
@@ -632,9 +740,39 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
 
     bool ok = true;
     BAND_TICK(0);
+#if SDV_BAND_BABE
+    // CTA 0 of the cluster runs two phases (interior, then — after adding CTA 1's contribution — the separator), everybody else one
+    for (int phase = 0; phase < (babe && !rev ? 2 : 1); phase++) {
+    const int kbeg = phase == 0 ? 0 : nint, kend = babe && phase == 0 ? nint : nb;
+    if (phase == 1) {
+        if (warp == 0 && !ok) s_fail = 1;
+        __syncthreads(); // this CTA's interior steps are complete
+        if (s_fail) acc->chol_fail = 1;
+        __threadfence();
+        cluster_sync_all(); // #1: ... and so are CTA 1's; its window and right-hand side are visible through DSMEM
+        if (__ldcg(&acc->chol_fail) != 0 || __ldcg(&acc->schur_fail) != 0) { // uniform over the cluster (CTA 1 tests the same words after #1)
+            if (threadIdx.x == 0) {
+                st->step_valid = 0;
+                st->model_cost_change = 0.0;
+            }
+            return;
+        }
+        // separator blocks (i, j), nint <= j <= i < nb: S_ij += (CTA 1's update of its block (nbg-1-j, nbg-1-i)) anti-transposed
+        for (int e = threadIdx.x; e < bw * bw * 256; e += BCT) {
+            const int a = (e >> 8) / bw, b = (e >> 8) % bw, r = (e >> 4) & 15, c = e & 15;
+            if (b > a) continue;
+            const int i = nint + a, j = nint + b, i1 = nbg - 1 - j, j1 = nbg - 1 - i;
+            double *dst = win + ((i % R) * bwp + (j % bwp)) * WBLK + r * WSTR + c;
+            const double *src = win + ((i1 % R) * bwp + (j1 % bwp)) * WBLK + (15 - c) * WSTR + (15 - r);
+            *dst += dsmem_load(src, 1);
+        }
+        for (int t = threadIdx.x; t < bw * BN; t += BCT) gs[nint * BN + t] += dsmem_load(gs + (P.n_pad - 1 - (nint * BN + t)), 1);
+        __syncthreads();
+    }
+#endif
     if (role == 0) {
         // ------------------------------------------------------------------ chain
-        for (int k = 0; k < nb; k++) {
+        for (int k = BAND_KBEG; k < BAND_KEND; k++) {
             const int par = k & 1;
             const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
             if (k >= 2) {
@@ -664,7 +802,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
     } else if (role == 1) {
         // ------------------------------------------------------------------ row solve
         const int d = ridx;
-        for (int k = 0; k + d < nb; k++) {
+        for (int k = BAND_KBEG; BAND_KLIM k + d < nb; k++) {
             const int par = k & 1;
             double *pan = pan0 + par * pl.pan_doubles;
             const bool streaming = BAND_STREAM_UPDATES && d <= 3;
@@ -745,7 +883,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         }
     } else if (role == 2) {
         // ------------------------------------------------------------------ right-hand side: L y = g rides along
-        for (int k = 0; k < nb; k++) {
+        for (int k = BAND_KBEG; k < BAND_KEND; k++) {
             const int par = k & 1;
             const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
             const double *pan = pan0 + par * pl.pan_doubles;
@@ -780,7 +918,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         }
     } else if (role == 3) {
         // ------------------------------------------------------------------ L_kk^-1 -> global (block bw+1 of column k)
-        for (int k = 0; k < nb; k++) {
+        for (int k = BAND_KBEG; k < BAND_KEND; k++) {
             const int par = k & 1;
             mbar_wait_cta(&bar_panel[par], ph(k));
             BAND_TICK(1);
@@ -819,7 +957,13 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                         nv++;
                     }
         }
-        for (int k = 0; k < nb; k++) {
+#if SDV_BAND_BABE
+        for (int t = 0; t < kbeg; t++) // second phase: the block ownership rotates with k
+#pragma unroll
+            for (int q = 0; q < MAXV; q++)
+                if (q < nv) vdj[q] = vdj[q] == 1 ? bw - vo[q] : vdj[q] - 1;
+#endif
+        for (int k = BAND_KBEG; k < BAND_KEND; k++) {
             const int par = k & 1;
             const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
             const double *pan = pan0 + par * pl.pan_doubles;
@@ -891,7 +1035,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         }
     } else if (role == 5) {
         // ------------------------------------------------------------------ copy warps
-        for (int k = 0; k < nb; k++) {
+        for (int k = BAND_KBEG; k < BAND_KEND; k++) {
             const int par = k & 1;
             mbar_wait_cta(&bar_panel[par], ph(k));
             BAND_TICK(1);
@@ -902,6 +1046,17 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             next_k();
         }
     }
+#if SDV_BAND_BABE
+    } // phase
+    if (rev) { // CTA 1: interior done; publish, meet CTA 0 at barrier #1 and learn whether either half failed
+        if (warp == 0 && !ok) s_fail = 1;
+        __syncthreads();
+        if (s_fail) acc->chol_fail = 1;
+        __threadfence();
+        cluster_sync_all();
+        if (__ldcg(&acc->chol_fail) != 0 || __ldcg(&acc->schur_fail) != 0) return;
+    }
+#endif
     BAND_TICK(3);
     if (warp == 0 && !ok) s_fail = 1;
     __threadfence();
@@ -914,6 +1069,13 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             st->step_valid = 0;
             st->model_cost_change = 0.0;
         }
+#if SDV_BAND_BABE
+        if (babe) { // only CTA 0 gets here (a separator pivot failed; interior failures returned after barrier #1): release CTA 1
+            __threadfence();
+            if (threadIdx.x == 0) mbar_remote_arrive(&bar_xsep, 1);
+            cluster_sync_all(); // #3
+        }
+#endif
         return;
     }
     BAND_TICK(4);
@@ -923,17 +1085,24 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         const int stage_doubles = (bw + 2) * 256, NS = pl.stages;
         const uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
         double *ring = bsm;
+#if SDV_BAND_BABE
+        int nbk = nb; // block columns this CTA back-substitutes: CTA 1 starts below the separator, once its unknowns are there
+        if (rev) {
+            mbar_wait_cluster(&bar_xsep, 0); // also: CTA 0 has finished reading this CTA's window (the ring overlays it)
+            nbk = __ldcg(&acc->chol_fail) != 0 ? 0 : nint;
+        }
+#endif
         if (lane == 0)
-            for (int s = 0; s < NS && s < nb; s++) {
-                const int k = nb - 1 - s;
+            for (int s = 0; s < NS && s < BAND_BNB; s++) {
+                const int k = BAND_BNB - 1 - s;
                 mbar_expect_tx(&full[s], stage_bytes);
                 bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k * stage_doubles, stage_bytes, &full[s]);
             }
         const int c = lane & 15, hh = lane >> 4;
         double *rvs = invs; // 16 doubles of scratch (the reciprocal diagonals are no longer needed)
         int s = 0, ph = 0;
-        for (int it = 0; it < nb; it++) {
-            const int k = nb - 1 - it;
+        for (int it = 0; it < BAND_BNB; it++) {
+            const int k = BAND_BNB - 1 - it;
             const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
             BAND_TICK(5);
             mbar_wait(&full[s], (unsigned)ph);
@@ -947,8 +1116,8 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
                     dxp[SDV_BAND_REV ? P.n_pad - 1 - (k * BN + c) : k * BN + c] = -xf;
                 }
                 __syncwarp();
-                if (lane == 0 && it + NS < nb) {
-                    const int k2 = nb - 1 - (it + NS);
+                if (lane == 0 && it + NS < BAND_BNB) {
+                    const int k2 = BAND_BNB - 1 - (it + NS);
                     mbar_expect_tx(&full[s], stage_bytes);
                     bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k2 * stage_doubles, stage_bytes, &full[s]);
                 }
@@ -993,15 +1162,26 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             x += __shfl_xor_sync(FULL, x, 16);
             if (hh == 0) {
                 gs[k * BN + c] = x;
-#if SDV_BAND_REV
+#if SDV_BAND_BABE
+                dxp[rev ? P.n_pad - 1 - (k * BN + c) : k * BN + c] = -x;
+                // x also goes to the other CTA: the separator unknowns to CTA 1 (it needs them), CTA 1's interior to CTA 0 (epilogue)
+                if (babe && (rev || k >= nint)) dsmem_store(gs + (P.n_pad - 1 - (k * BN + c)), rev ? 0u : 1u, x);
+#elif SDV_BAND_REV
                 dxp[P.n_pad - 1 - (k * BN + c)] = -x;
 #else
                 dxp[k * BN + c] = -x;
 #endif
             }
+#if SDV_BAND_BABE
+            if (babe && !rev && k == nint) { // last separator block: CTA 1 may start
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_remote_arrive(&bar_xsep, 1);
+            }
+#endif
             __syncwarp();
-            if (lane == 0 && it + NS < nb) {
-                const int k2 = nb - 1 - (it + NS);
+            if (lane == 0 && it + NS < BAND_BNB) {
+                const int k2 = BAND_BNB - 1 - (it + NS);
                 mbar_expect_tx(&full[s], stage_bytes);
                 bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k2 * stage_doubles, stage_bytes, &full[s]);
             }
@@ -1012,6 +1192,13 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
         }
     }
     __syncthreads();
+#if SDV_BAND_BABE
+    if (babe) { // #3: both halves of x are in CTA 0's shared memory and in dxp
+        __threadfence();
+        cluster_sync_all();
+        if (rev) return;
+    }
+#endif
     BAND_TICK(5);
 #ifdef SDV_BAND_PROF
     if (prof && lane == 0)

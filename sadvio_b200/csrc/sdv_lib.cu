@@ -1300,6 +1300,30 @@ int launch_factor_solve(sdv_handle *h) {
     cudaStream_t s = h->stream;
     const int T = P.n_pad / CH_T;
     if (h->band_smem > 0) {
+#if SDV_BAND_BABE
+        // Two-way dissection (experiment, see sdv_chol_band.cuh): a 2-CTA cluster when both interiors are a few block rows
+        // long, the band storage holds two factors and no kept landmark sits behind the frame blocks (a pure band).
+        const int nbg = P.n_pad / BN, bwb = P.band_bw;
+        if (nbg >= 4 * bwb + 8 && (size_t)2 * nbg * (bwb + 2) * 256 <= h->sb_elems && !getenv("SDV_BAND_NO_BABE")) {
+            cudaLaunchConfig_t lc = {};
+            cudaLaunchAttribute at[1];
+            lc.gridDim = dim3(2);
+            lc.blockDim = dim3(BCT);
+            lc.dynamicSmemBytes = h->band_smem;
+            lc.stream = s;
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&lc, k_chol_band, P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, (const double *)h->d_Sb, h->d_Lo, h->d_scale_p, h->d_damp_p,
+                                               h->d_graw_p, h->d_dxp, h->d_prof);
+            if (e != cudaSuccess) return fail(h, SDV_ERR_CUDA, cudaGetErrorString(e));
+            h->launches++;
+            return SDV_OK;
+        }
+#endif
         k_chol_band<<<1, BCT, h->band_smem, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_Lo, h->d_scale_p, h->d_damp_p, h->d_graw_p, h->d_dxp, h->d_prof);
         h->launches++;
         return SDV_OK;
