@@ -3,6 +3,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_round.sh full'
 #   /usr/local/graft/bin/gpurun --timeout 300 -- 'bash tools/gpu_round.sh quick [pytest -k expression]'
 #   /usr/local/graft/bin/gpurun --timeout 300 -- 'bash tools/gpu_round.sh micro backward 47 3'
+#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/gpu_round.sh variant SDV_BAND_REV'
 # Everything lands in gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/.
 set -u
 mode=${1:-quick}
@@ -28,13 +29,24 @@ ncu)
         -o $out/ncu_full_${2:-C3} -f python tools/solve_once.py ${2:-C3} > $out/ncu_full.log 2>&1
     tail -3 $out/ncu_full.log
     ;;
+variant)
+    # build the library with one of the experiment switches of sdv_chol_band.cuh (SDV_BAND_BACKWARD_V2, SDV_BAND_REV,
+    # SDV_BAND_BABE) ON THE BOX (the snapshot's default library is not touched in the repository), run the Cholesky-related
+    # parity tests and a timed C3 solve:   gpu_round.sh variant SDV_BAND_REV [extra env assignments ...]
+    sw=${2:?switch name}
+    shift 2
+    env "$sw=1" python -c "from sadvio_b200 import build; print(build.build(force=True))" 2>&1 | tail -2
+    env "$@" timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "full_solve or band or golden or reference or gradient_tolerance or tight_convergence" 2>&1 | tail -8 | tee $out/variant_$sw.log
+    env "$@" timeout 60 python tools/solve_once.py C3 5 2>&1 | tail -1 | tee -a $out/variant_$sw.log
+    env "$@" timeout 60 python tools/chol_only.py 2>&1 | tail -3 | tee -a $out/variant_$sw.log
+    ;;
 micro)
     name=${2:?micro-benchmark name (tools/micro/<name>.cu)}
     shift 2
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude -o /tmp/micro_$name tools/micro/$name.cu && timeout 120 /tmp/micro_$name "$@" 2>&1 | tee $out/micro_$name.log
     ;;
 *)
-    echo "usage: gpu_round.sh quick|full|ncu|micro ..."
+    echo "usage: gpu_round.sh quick|full|ncu|variant|micro ..."
     exit 2
     ;;
 esac
