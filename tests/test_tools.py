@@ -24,3 +24,12 @@ def test_two_way_dissection_prototype_matches_a_direct_solve():
         assert nl + nr + bw == nb and abs(nl - nr) <= 1
         ref = np.linalg.solve(A, b)
         assert np.abs(x - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+def test_two_way_dissection_index_emulation():
+    """Element-level emulation of the addressing of the -DSDV_BAND_BABE=1 kernel path (loads from the stored triangle, reversed
+    local orders, anti-transposed hand-over, exchange of x, scatter into dxp) against a direct solve."""
+    emu = _load("babe_index_emulation")
+    for nbg, bw, n in ((20, 3, 20 * 16 - 5), (24, 4, 24 * 16 - 15)):
+        e_dxp, e_epi, nl, nr = emu.run(nbg, bw, n)
+        assert nl + nr + bw == nbg and e_dxp < 1e-10 and e_epi < 1e-10

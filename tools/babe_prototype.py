@@ -6,7 +6,7 @@ updates of both halves.  There is no extra fill — the sequential chain of bloc
 
 This file only checks the algebra and the index mapping (reversal at 16-column block granularity, what the second CTA must
 zero-initialise, what crosses between the CTAs) against numpy.linalg.solve on random banded SPD systems of the shapes the
-window solve produces (C3: nb = 47, bw = 3; C5: nb = 187, bw = 3..4).  It is not on any product path.
+window solve produces (C3: nb = 46, bw = 3; C5: nb = 188, bw = 3..4).  It is not on any product path.
 
     python tools/babe_prototype.py
 """

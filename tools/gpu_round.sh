@@ -2,7 +2,7 @@
 # One gpurun call that collects everything a round needs from a B200 box, bounded in time (run from the repository root):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_round.sh full'
 #   /usr/local/graft/bin/gpurun --timeout 300 -- 'bash tools/gpu_round.sh quick [pytest -k expression]'
-#   /usr/local/graft/bin/gpurun --timeout 300 -- 'bash tools/gpu_round.sh micro backward 47 3'
+#   /usr/local/graft/bin/gpurun --timeout 300 -- 'bash tools/gpu_round.sh micro backward 46 3'
 #   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/gpu_round.sh variant SDV_BAND_REV'
 # Everything lands in gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/.
 set -u
