@@ -23,8 +23,10 @@
  *
  * Errors: every function returns an `sdv_status` (0 = ok).  No exception
  * crosses the ABI.  The reference returns `bool` and practically always
- * `true`; the C++ adapter (sadvio_b200/host/b200_optimizer.hpp) maps a
- * non-zero status to `false` and leaves the state untouched.
+ * `true`; the adapters (sadvio_b200/host/b200_optimizer.hpp, sadvio_b200/api.py)
+ * map a status that means "no solve ran" to `false` and leave the state
+ * untouched; SDV_ERR_NUMERICAL_FAILURE (Ceres FAILURE) still carries the last
+ * accepted x, which they write back, returning `true` as the reference does.
  */
 #ifndef SDV_H
 #define SDV_H

@@ -248,6 +248,25 @@ class SparsePrior:
 
 
 @dataclass
+class SkippedPreint:
+    """Pre-integration of the frames that get NO IMUFactor although their getLastKF() is in the window with an IMU
+    (dt > 1 s, AOptimizer.cpp:69, or framei == framej, :72).  They never cross the C ABI — the solve does not see them —
+    but the write-back still corrects their deltas with the previous keyframe's dba / dbg: the loop at
+    AOptimizer.cpp:421-434 has neither test."""
+
+    frame: np.ndarray      # [K] window index of the frame
+    prev: np.ndarray       # [K] window index of its getLastKF()
+    dR: np.ndarray         # [K,9]
+    dv: np.ndarray         # [K,3]
+    dp: np.ndarray         # [K,3]
+    J_dR_bg: np.ndarray    # [K,9]
+    J_dv_ba: np.ndarray
+    J_dv_bg: np.ndarray
+    J_dp_ba: np.ndarray
+    J_dp_bg: np.ndarray
+
+
+@dataclass
 class Window:
     """A flattened sliding window (numpy SoA). ``as_struct`` yields the C view (keeps arrays alive)."""
 
@@ -287,6 +306,7 @@ class Window:
     imu_sigma_bg: Optional[np.ndarray] = None
     dense_prior: Optional[DensePrior] = None
     sparse_prior: Optional[SparsePrior] = None
+    skipped_preint: Optional[SkippedPreint] = None   # host-side only (write-back), see SkippedPreint
     meta: dict = field(default_factory=dict)   # ground truth etc. (never crosses the ABI)
 
     @property

@@ -182,13 +182,22 @@ def write_back(win: abi.Window, d: abi.Delta, vio: bool) -> None:
         win.v += d.dv
         win.ba += d.dba
         win.bg += d.dbg
-        # IMU::biasDeltaCorrection with the PREVIOUS keyframe's dba, dbg (AOptimizer.cpp:421-434, IMU.cpp:104-108)
-        for p in range(win.n_imu):
-            i = int(win.imu_i[p])
+        # IMU::biasDeltaCorrection with the PREVIOUS keyframe's dba, dbg (AOptimizer.cpp:421-434, IMU.cpp:104-108) for EVERY
+        # frame whose getLastKF() owns dba / dbg blocks: the frames with an IMUFactor (their previous keyframe is imu_i) and
+        # the ones the factor loop skipped (dt > 1 s), which the window carries host-side in `skipped_preint`
+        def correct(dR, dv, dp, J_dR_bg, J_dv_ba, J_dv_bg, J_dp_ba, J_dp_bg, k, i):
             dba, dbg = d.dba[i], d.dbg[i]
-            win.imu_dp[p] += win.imu_J_dp_ba[p].reshape(3, 3) @ dba + win.imu_J_dp_bg[p].reshape(3, 3) @ dbg
-            win.imu_dv[p] += win.imu_J_dv_ba[p].reshape(3, 3) @ dba + win.imu_J_dv_bg[p].reshape(3, 3) @ dbg
-            win.imu_dR[p] = (win.imu_dR[p].reshape(3, 3) @ exp_so3(win.imu_J_dR_bg[p].reshape(3, 3) @ dbg)).reshape(9)
+            dp[k] += J_dp_ba[k].reshape(3, 3) @ dba + J_dp_bg[k].reshape(3, 3) @ dbg
+            dv[k] += J_dv_ba[k].reshape(3, 3) @ dba + J_dv_bg[k].reshape(3, 3) @ dbg
+            dR[k] = (dR[k].reshape(3, 3) @ exp_so3(J_dR_bg[k].reshape(3, 3) @ dbg)).reshape(9)
+
+        for p in range(win.n_imu):
+            correct(win.imu_dR, win.imu_dv, win.imu_dp, win.imu_J_dR_bg, win.imu_J_dv_ba, win.imu_J_dv_bg, win.imu_J_dp_ba,
+                    win.imu_J_dp_bg, p, int(win.imu_i[p]))
+        sk = win.skipped_preint
+        if sk is not None:
+            for k in range(len(sk.frame)):
+                correct(sk.dR, sk.dv, sk.dp, sk.J_dR_bg, sk.J_dv_ba, sk.J_dv_bg, sk.J_dp_ba, sk.J_dp_bg, k, int(sk.prev[k]))
 
 
 class B200Optimizer:
@@ -205,11 +214,11 @@ class B200Optimizer:
         win.n_fixed = int(fixed_frame_number)
         win.vio = vio
         try:
-            rc, d, st = self._solve(win)
+            rc, d, st = self._solve(win)  # rc 5 (Ceres FAILURE) still carries the last accepted x
         except RuntimeError:
-            return False  # the adapter maps a non-zero status to `false` and leaves the state untouched
+            return False  # no solve ran (malformed window, CUDA error): state untouched, like the C++ adapter
         self.last_stats = st
-        write_back(win, d, vio)
+        write_back(win, d, vio)  # the reference ignores the summary: write back, return true (AOptimizer.cpp:388-445)
         return True
 
     def localMapVIOptimization(self, local_map: abi.Window, fixed_frame_number: int = 0) -> bool:  # noqa: N802

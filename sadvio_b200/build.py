@@ -10,7 +10,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
-LIB = os.path.join(LIB_DIR, "libsadvio_b200.so")
+# SDV_LIB selects a prebuilt experiment library (tools/gpu_round.sh variant mode); it is never rebuilt from here.
+LIB = os.environ.get("SDV_LIB") or os.path.join(LIB_DIR, "libsadvio_b200.so")
 SOURCES = ["sdv_lib.cu"]
 HEADERS = ["sdv_kernels.cuh", "sdv_chol.cuh", "sdv_chol_band.cuh", "sdv_math.cuh", "sdv_types.cuh", os.path.join("..", "..", "include", "sdv.h")]
 NVCC_FLAGS = [
@@ -24,6 +25,8 @@ NVCC_FLAGS = [
 
 
 def is_stale() -> bool:
+    if os.environ.get("SDV_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

@@ -174,6 +174,7 @@ int ensure(sdv_handle *h, unsigned char **d, size_t *cap, size_t need, bool pinn
 
 namespace {
 int build_solve_graph(sdv_handle *h);
+void destroy_graph(sdv_handle *h);
 }
 
 extern "C" {
@@ -317,6 +318,9 @@ int sdv_comm_unique_id(void *out) {
 
 int sdv_comm_init(sdv_handle *h, const void *uid, int32_t rank, int32_t world) {
     if (!h || !uid || world < 1 || rank < 0 || rank >= world) return SDV_ERR_INVALID_ARGUMENT;
+    // a graph captured before the communicator existed bakes the old window and contains no NCCL call: never reuse it
+    destroy_graph(h);
+    h->resident = false;
     if (world == 1) {
         h->rank = 0;
         h->world = 1;
@@ -338,6 +342,7 @@ int sdv_comm_init(sdv_handle *h, const void *uid, int32_t rank, int32_t world) {
 // ---------------------------------------------------------------------------------------------------------------------
 int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     if (!h || !w) return SDV_ERR_INVALID_ARGUMENT;
+    h->resident = false; // an upload that fails midway must not leave a half-updated problem marked resident
     if (w->abi_version != SDV_ABI_VERSION) return fail(h, SDV_ERR_INVALID_ARGUMENT, "abi_version mismatch");
     const int F = w->n_frames, C = w->n_cams, L = w->n_lmks, O = w->n_obs, Pn = w->vio ? w->n_imu : 0;
     if (F <= 0 || C <= 0 || L < 0 || O < 0 || Pn < 0 || w->n_fixed < 0) return fail(h, SDV_ERR_INVALID_ARGUMENT, "negative or empty sizes");
@@ -1479,7 +1484,10 @@ void destroy_graph(sdv_handle *h) {
 
 // prologue -> WHILE (status == 0) { one LM iteration } -> epilogue, as ONE graph launch per solve.
 int build_solve_graph(sdv_handle *h) {
-    if (h->world > 1 || getenv("SDV_NO_GRAPH")) return SDV_OK; // NCCL inside a conditional body is not attempted
+    if (h->world > 1 || getenv("SDV_NO_GRAPH")) { // NCCL inside a conditional body is not attempted
+        destroy_graph(h);                         // (a graph of an earlier single-GPU window must not survive)
+        return SDV_OK;
+    }
     if (h->graph_ok && std::memcmp(&h->graph_P, &h->P, sizeof(DevProblem)) == 0) return SDV_OK;
     destroy_graph(h);
     if (!h->stream2 && cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) return SDV_OK;

@@ -1,10 +1,12 @@
 // Test driver for sadvio_b200/host/b200_optimizer.hpp: reads a pointer-graph description (text, produced by
 // tests/test_host_adapter.py), rebuilds the graph with shared_ptr / weak_ptr objects exactly as SaDVIO holds it,
 // and either prints the flattened window ("flatten": indices only, "dump": every array of the sdv_window) or runs
-// localMapVIOptimization / localMapBA through the C ABI and prints the updated state ("solve").  An optional trailing
+// localMapVIOptimization / localMapBA through the C ABI and prints the updated state ("solve"), or applies a synthetic
+// solution with the write-back alone ("writeback", no GPU).  An optional trailing
 // section describes the isae::Marginalization object the optimizer holds (dense or sparsified prior).
 #include "b200_optimizer.hpp"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -125,6 +127,15 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "malformed input\n");
         return 2;
     }
+    if (std::getenv("SDV_TEST_NAN_OBS")) { // a NaN measurement makes every step invalid: the solve ends in Ceres' FAILURE termination
+        for (auto &lm : map->pointxd)
+            for (auto &wf : lm->features)
+                if (auto ft = wf.lock()) {
+                    ft->bearing[0] = std::nan("");
+                    goto poisoned;
+                }
+    poisoned:;
+    }
     std::printf("%s\n", mode.c_str());
     if (mode == "dump") {
         FlatWindow fw;
@@ -187,11 +198,29 @@ int main(int argc, char **argv) {
         for (int f = 0; f < w.n_frames; f++) std::printf("%.17g\n", w.T_f_w[12 * f + 3]);
         return 0;
     }
-    B200Optimizer opt(kind, 0);
-    opt._marginalization = marg;
-    opt._enable_sparsif = sparsif;
-    bool ok = vio ? opt.localMapVIOptimization(map, fixed) : opt.localMapBA(map, fixed);
-    std::printf("%d %d\n", ok ? 1 : 0, opt.lastStats().iterations);
+    if (mode == "writeback") {
+        // no GPU needed: flatten, then apply a synthetic solution (entry k of the concatenated blocks = 1e-3 sin(k + 1)) with the
+        // adapter's write-back.  tests/test_host_adapter.py applies the same solution with the Python mirror.
+        FlatWindow fw;
+        if (!flatten(*map, fixed, vio, kind, fw, marg.get(), sparsif)) return 3;
+        const size_t F = fw.frame_vector.size(), L = fw.landmarks.size();
+        std::vector<double> buf(15 * F + 3 * L + 1, 0.0);
+        for (size_t k = 0; k < 15 * F + 3 * L; k++) buf[k] = 1e-3 * std::sin((double)(k + 1));
+        sdv_delta d;
+        d.dpose = buf.data();
+        d.dv = d.dpose + 6 * F;
+        d.dba = d.dv + 3 * F;
+        d.dbg = d.dba + 3 * F;
+        d.dlmk = d.dbg + 3 * F;
+        write_back(fw, d, vio);
+        std::printf("1 0\n");
+    } else {
+        B200Optimizer opt(kind, 0);
+        opt._marginalization = marg;
+        opt._enable_sparsif = sparsif;
+        bool ok = vio ? opt.localMapVIOptimization(map, fixed) : opt.localMapBA(map, fixed);
+        std::printf("%d %d\n", ok ? 1 : 0, opt.lastStats().iterations);
+    }
     for (auto &fr : map->frames) {
         for (double x : fr->T_f_w) std::printf("%.17g ", x);
         if (fr->imu) {
@@ -199,6 +228,8 @@ int main(int argc, char **argv) {
             for (double x : fr->imu->ba) std::printf("%.17g ", x);
             for (double x : fr->imu->bg) std::printf("%.17g ", x);
             for (double x : fr->imu->delta_p) std::printf("%.17g ", x);
+            for (double x : fr->imu->delta_v) std::printf("%.17g ", x);
+            for (double x : fr->imu->delta_R) std::printf("%.17g ", x);
         }
         std::printf("\n");
     }

@@ -3,7 +3,8 @@
 //     bool isae::AOptimizer::localMapBA(std::shared_ptr<LocalMap>&, size_t fixed_frame_number = 0)
 //     bool isae::AOptimizer::localMapVIOptimization(std::shared_ptr<LocalMap>&, size_t fixed_frame_number = 0)
 // (reference cpp/include/isaeslam/optimizers/AOptimizer.h:28-30), same argument meaning and error behaviour
-// (bool, no exceptions; on failure the state is left untouched).
+// (bool, no exceptions; when no solve could run — no device, malformed window — the state is left untouched and the call
+// returns false; a solve that ends in Ceres' FAILURE termination writes back and returns true like the reference).
 //
 // The reference data model (isae::Frame / ImageSensor / IMU / ALandmark / AFeature / LocalMap, Eigen based) is not
 // available in this image, so this header carries a minimal mirror of the pointer graph with the reference's getter
@@ -112,6 +113,10 @@ struct FlatWindow {
     std::vector<std::shared_ptr<Frame>> frame_vector;     // newest -> oldest
     std::vector<std::shared_ptr<Landmark>> landmarks;     // in parameter-block order
     std::vector<std::shared_ptr<Frame>> imu_frame_j;      // frame j of each IMU factor
+    // biasDeltaCorrection list (AOptimizer.cpp:421-434): EVERY frame with an IMU whose getLastKF() owns dba/dbg blocks,
+    // i.e. is in the window with an IMU — no dt <= 1 s test, no framei != framej test (unlike the factor list above)
+    std::vector<std::shared_ptr<Frame>> corr_frame;
+    std::vector<int32_t> corr_prev;                       // window index of its previous keyframe
     std::vector<int32_t> keep_lmk, keep_col, p2l_lmk, l2l_a, l2l_b;  // marginal prior (addMarginalizationResiduals)
     std::vector<double> p2l_delta, p2l_sqrt_inf, l2l_delta, l2l_sqrt_inf;
     sdv_dense_prior dense{};
@@ -199,6 +204,14 @@ inline bool flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
             fw.sigma_ba.push_back(framei->imu->bacc_noise); // residuals.hpp:259 reads imu_i's config
             fw.sigma_bg.push_back(framei->imu->bgyr_noise); // residuals.hpp:261
             fw.imu_frame_j.push_back(framej);
+        }
+        for (int i = 0; i < F; i++) { // AOptimizer.cpp:421-434
+            const std::shared_ptr<Frame> &frame = fw.frame_vector[i];
+            if (!frame->imu || !frame->imu->last_kf) continue;            // :422-426
+            auto it = frame_idx.find(frame->imu->last_kf.get());
+            if (it == frame_idx.end() || !frame->imu->last_kf->imu) continue; // _map_frame_dbapar.find(previous_frame), :430
+            fw.corr_frame.push_back(frame);
+            fw.corr_prev.push_back(it->second);
         }
     }
     // Marginal prior (addMarginalizationResiduals, AngularAdjustmentCERESAnalytic.cpp:341-486).  A kept landmark that has no
@@ -374,9 +387,9 @@ inline void write_back(FlatWindow &fw, const sdv_delta &d, bool vio) {
     for (size_t l = 0; l < fw.landmarks.size(); l++)
         for (int k = 0; k < 3; k++) fw.landmarks[l]->t_w[k] += d.dlmk[3 * l + k];
     if (!vio) return;
-    for (size_t p = 0; p < fw.imu_frame_j.size(); p++) {
-        IMU &m = *fw.imu_frame_j[p]->imu;
-        const double *dba = d.dba + 3 * fw.imu_i[p], *dbg = d.dbg + 3 * fw.imu_i[p];
+    for (size_t p = 0; p < fw.corr_frame.size(); p++) {
+        IMU &m = *fw.corr_frame[p]->imu;
+        const double *dba = d.dba + 3 * fw.corr_prev[p], *dbg = d.dbg + 3 * fw.corr_prev[p];
         double phi[3], E[9], Rn[9];
         for (int i = 0; i < 3; i++) {
             double sp = 0, sv = 0;
@@ -435,7 +448,10 @@ class B200Optimizer {
         d.dbg = d.dba + 3 * F;
         d.dlmk = d.dbg + 3 * F;
         int rc = sdv_solve_window(_h, &fw.view, &d, &_stats);
-        if (rc != SDV_OK) return false; // state untouched
+        // SDV_ERR_NUMERICAL_FAILURE is Ceres' TerminationType FAILURE: the reference ignores the summary, writes back the
+        // last accepted x and returns true (AOptimizer.cpp:388-445); the termination is in lastStats().  Every other
+        // non-zero status means no solve happened: state untouched, false.
+        if (rc != SDV_OK && rc != SDV_ERR_NUMERICAL_FAILURE) return false;
         write_back(fw, d, vio);
         return true;
     }

@@ -580,3 +580,29 @@ def apply_delta(win: abi.Window, d: abi.Delta) -> dict:
     if win.vio:
         out.update(v=win.v + d.dv, ba=win.ba + d.dba, bg=win.bg + d.dbg)
     return out
+
+
+IMU_FACTOR_FIELDS = ("imu_i", "imu_j", "imu_dt", "imu_dR", "imu_dv", "imu_dp", "imu_cov", "imu_J_dR_bg", "imu_J_dv_ba", "imu_J_dv_bg",
+                     "imu_J_dp_ba", "imu_J_dp_bg", "imu_sigma_ba", "imu_sigma_bg")
+
+
+def skip_imu_factor(win: abi.Window, frame_j: int) -> abi.Window:
+    """Models a keyframe more than 1 s after its previous keyframe: the IMUFactor / IMUBiasFactor of `frame_j` disappear
+    from the window (AOptimizer.cpp:69) while its pre-integration stays on the host side for the write-back, which corrects
+    it regardless of the gap (AOptimizer.cpp:421-434)."""
+    win.normalise()
+    ps = [p for p in range(win.n_imu) if int(win.imu_j[p]) == frame_j]
+    assert len(ps) == 1, ps
+    p = ps[0]
+    old = win.skipped_preint
+    cat = lambda a, b: b.copy() if a is None else np.concatenate([a, b])
+    win.skipped_preint = abi.SkippedPreint(
+        frame=cat(old and old.frame, win.imu_j[p:p + 1]), prev=cat(old and old.prev, win.imu_i[p:p + 1]),
+        dR=cat(old and old.dR, win.imu_dR[p:p + 1]), dv=cat(old and old.dv, win.imu_dv[p:p + 1]), dp=cat(old and old.dp, win.imu_dp[p:p + 1]),
+        J_dR_bg=cat(old and old.J_dR_bg, win.imu_J_dR_bg[p:p + 1]), J_dv_ba=cat(old and old.J_dv_ba, win.imu_J_dv_ba[p:p + 1]),
+        J_dv_bg=cat(old and old.J_dv_bg, win.imu_J_dv_bg[p:p + 1]), J_dp_ba=cat(old and old.J_dp_ba, win.imu_J_dp_ba[p:p + 1]),
+        J_dp_bg=cat(old and old.J_dp_bg, win.imu_J_dp_bg[p:p + 1]))
+    keep = np.array([q for q in range(win.n_imu) if q != p], dtype=np.int64)
+    for name in IMU_FACTOR_FIELDS:
+        setattr(win, name, np.ascontiguousarray(getattr(win, name)[keep]))
+    return win

@@ -1,3 +1,4 @@
+import ctypes
 import os
 import sys
 
@@ -10,6 +11,31 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def _cuda_device_count() -> int:
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        if cu.cuInit(0) != 0 or cu.cuDeviceGetCount(ctypes.byref(n)) != 0:
+            return 0
+        return n.value
+    except OSError:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a box without a GPU skips the gpu-marked tests; `-m gpu` asks for them explicitly, and then a
+    missing device or library is a loud failure (BackendUnavailable from the `solver` fixture), never a silent pass."""
+    markexpr = config.getoption("-m") or ""
+    if "gpu" in markexpr and "not gpu" not in markexpr:
+        return
+    if _cuda_device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (the product has no CPU path); run with -m gpu on a B200")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

@@ -302,6 +302,30 @@ def test_optimizer_interface_writeback(solver):
     assert np.abs(win.imu_dp[p] - s2[40:43]).max() < 1e-12
 
 
+def test_writeback_across_a_long_gap(solver):
+    """A keyframe more than 1 s after its previous keyframe: no IMU factor (AOptimizer.cpp:69) but its pre-integrated deltas
+    are still corrected with the previous keyframe's dba / dbg (AOptimizer.cpp:421-434 has no dt test)."""
+    F = synth.make_window("small").n_frames
+    f_gap = F - 5
+    win = synth.skip_imu_factor(synth.make_window("small"), f_gap)
+    ref = synth.skip_imu_factor(synth.make_window("small"), f_gap)
+    orig = synth.skip_imu_factor(synth.make_window("small"), f_gap)
+    opt = api.B200Optimizer()
+    assert opt.localMapVIOptimization(win, 1) is True
+    rc0, d0, st0 = orc.solve_window(ref)
+    assert rc0 == 0 and opt.last_stats["iterations"] == st0["iterations"]
+    api.write_back(ref, d0, True)
+    assert np.abs(win.T_f_w - ref.T_f_w).max() < 1e-9 and np.abs(win.bg - ref.bg).max() < 1e-9
+    sk, sk0, sko = win.skipped_preint, ref.skipped_preint, orig.skipped_preint
+    i = int(sko.prev[0])
+    assert int(sko.frame[0]) == f_gap and np.abs(d0.dbg[i]).max() > 0
+    dp = sko.dp[0] + sko.J_dp_ba[0].reshape(3, 3) @ d0.dba[i] + sko.J_dp_bg[0].reshape(3, 3) @ d0.dbg[i]
+    dR = sko.dR[0].reshape(3, 3) @ synth.exp_so3(sko.J_dR_bg[0].reshape(3, 3) @ d0.dbg[i])
+    assert np.abs(sk0.dp[0] - dp).max() < 1e-15 and np.abs(sk0.dR[0] - dR.reshape(9)).max() < 1e-15
+    assert np.abs(sk.dp[0] - dp).max() < 1e-9 and np.abs(sk.dR[0] - dR.reshape(9)).max() < 1e-9 and np.abs(sk.dv[0] - sk0.dv[0]).max() < 1e-9
+    assert np.abs(sk.dp[0] - sko.dp[0]).max() > 1e-12
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # the factorisation / assembly variants must agree with each other and with the oracle
 # ---------------------------------------------------------------------------------------------------------------------
@@ -445,3 +469,57 @@ def test_next_vo_window_with_sparsified_prior_from_the_oracle(solver):
     g, o = solve_both(solver, w2)
     assert_same_solution(g, o)
     assert_same_states(w2, g[1], o[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cases queued at the end of round 1 (VERDICT r01 "untested on GPU")
+# ---------------------------------------------------------------------------------------------------------------------
+def test_c1_euroc_window(solver):
+    """BASELINE config 1 on the GPU: 10 keyframes 0.5 s apart on the EuRoC ground truth, stereo rig of eth.yaml, 10 k obs."""
+    win = synth.make_window("C1")
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    assert_same_states(win, g[1], o[1])
+    assert g[2]["final_cost"] < 0.01 * g[2]["initial_cost"]
+    win = synth.make_window("C1", factor_kind=1)
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+
+
+def test_keyframe_without_imu_in_a_vio_window(solver):
+    """getIMU() == nullptr on one keyframe of a VIO window: no v / ba / bg blocks, no IMU factor on either side of it
+    (AOptimizer.cpp:30-52, 60-73); its v / ba / bg updates stay exactly zero."""
+    win = synth.make_window("small")
+    f = 4
+    keep = (win.imu_i != f) & (win.imu_j != f)
+    for k in synth.IMU_FACTOR_FIELDS:
+        setattr(win, k, getattr(win, k)[keep].copy())
+    win.has_imu[f] = 0
+    win.normalise()
+    g, o = solve_both(solver, win)
+    assert_same_solution(g, o)
+    d = g[1]
+    assert np.all(d.dv[f] == 0) and np.all(d.dba[f] == 0) and np.all(d.dbg[f] == 0) and np.abs(d.dpose[f]).max() > 0
+
+
+def test_chained_dense_priors_with_resurrected_landmarks(solver):
+    """The back end's loop over several keyframes — solve, write back, marginalise the oldest keyframe (the previous prior is
+    folded in, …Analytic.cpp:631-660), drop it — with the window solves on the GPU and the marginalisation by the oracle.
+    Landmarks kept by a prior while no remaining keyframe sees them ("supposed to be in the map", …Analytic.cpp:369-373) have a
+    parameter block and no observation.  Every solve must match the oracle solve of the same window."""
+    from oracle import marginalize
+
+    w = synth.make_window("small")
+    n_prior_only = 0
+    for step in range(5):
+        prior, info = marginalize.marginalize_oldest(w)
+        assert prior is not None
+        w = marginalize.drop_oldest_frame(w, prior)
+        seen = np.zeros(w.n_lmks, bool)
+        seen[w.obs_lmk] = True
+        n_prior_only += int((~seen[w.dense_prior.keep_lmk]).sum())
+        g, o = solve_both(solver, w)
+        assert_same_solution(g, o)
+        assert_same_states(w, g[1], o[1])
+        api.write_back(w, g[1], True)
+    assert n_prior_only > 0

@@ -8,7 +8,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from sadvio_b200 import build, synth
+from sadvio_b200 import abi, build, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -317,3 +317,87 @@ def test_adapter_solve_matches_python_binding(adapter_exe):
             assert np.abs(row[21:24] - ref.imu_dp[ps[0]]).max() < 1e-9   # biasDeltaCorrection applied
     lm = np.array([[float(x) for x in ln.split()] for ln in out[2 + F:2 + F + win.n_lmks]])
     assert np.abs(lm - ref.lmk_t).max() < 1e-8
+
+
+def _synthetic_delta(F, L):
+    buf = 1e-3 * np.sin(np.arange(15 * F + 3 * L, dtype=np.float64) + 1.0)
+    return abi.Delta(buf[:6 * F].reshape(F, 6).copy(), buf[6 * F:9 * F].reshape(F, 3).copy(), buf[9 * F:12 * F].reshape(F, 3).copy(),
+                     buf[12 * F:15 * F].reshape(F, 3).copy(), buf[15 * F:].reshape(L, 3).copy())
+
+
+@pytest.mark.parametrize("gap_after", [None, 3])
+def test_writeback_corrects_every_frame_with_a_previous_keyframe(adapter_exe, gap_after):
+    """AOptimizer.cpp:421-434: biasDeltaCorrection runs for EVERY frame whose getLastKF() owns dba/dbg blocks — no dt <= 1 s
+    test, unlike the factor loop (:69).  A keyframe 1.25 s after its previous keyframe has no IMU factor but its
+    delta_R / delta_v / delta_p are still corrected.  The C++ adapter and the Python mirror must agree with each other and
+    with a direct restatement of IMU.cpp:104-108."""
+    from sadvio_b200 import api
+
+    win = synth.make_window("small")
+    txt, _, exp_imu, _ = graph_text(win, np.random.default_rng(0), False, gap_after=gap_after)
+    out = subprocess.run([adapter_exe, "writeback", "1", "1"], input=txt, capture_output=True, text=True, check=True).stdout.split("\n")
+    F, L = win.n_frames, win.n_lmks
+    rows = [np.array([float(x) for x in ln.split()]) for ln in out[2:2 + F]]   # oldest -> newest
+    ref = synth.make_window("small")
+    orig = synth.make_window("small")
+    f_gap = None
+    if gap_after is not None:
+        f_gap = F - 1 - (gap_after + 1)          # window index of the keyframe right after the gap
+        synth.skip_imu_factor(ref, f_gap)
+        assert [(int(i), int(j)) for i, j in zip(ref.imu_i, ref.imu_j)] == exp_imu
+    d = _synthetic_delta(F, L)
+    api.write_back(ref, d, True)
+    n_checked = 0
+    for k, row in enumerate(rows):
+        f = F - 1 - k
+        assert np.abs(row[:12] - ref.T_f_w[f]).max() < 1e-12
+        assert np.abs(row[12:15] - ref.v[f]).max() < 1e-15 and np.abs(row[15:18] - ref.ba[f]).max() < 1e-15
+        ps = [p for p in range(orig.n_imu) if orig.imu_j[p] == f]
+        if not ps:
+            continue
+        p, i = ps[0], int(orig.imu_i[ps[0]])
+        # direct restatement of IMU::biasDeltaCorrection with the previous keyframe's dba / dbg
+        J = lambda a: a[p].reshape(3, 3)
+        dp = orig.imu_dp[p] + J(orig.imu_J_dp_ba) @ d.dba[i] + J(orig.imu_J_dp_bg) @ d.dbg[i]
+        dv = orig.imu_dv[p] + J(orig.imu_J_dv_ba) @ d.dba[i] + J(orig.imu_J_dv_bg) @ d.dbg[i]
+        dR = J(orig.imu_dR) @ synth.exp_so3(J(orig.imu_J_dR_bg) @ d.dbg[i])
+        assert np.abs(row[21:24] - dp).max() < 1e-14 and np.abs(row[24:27] - dv).max() < 1e-14 and np.abs(row[27:36] - dR.reshape(9)).max() < 1e-14
+        assert np.abs(dp - orig.imu_dp[p]).max() > 1e-9   # the correction is not a no-op
+        if f == f_gap:
+            k2 = int(np.where(ref.skipped_preint.frame == f)[0][0])
+            mine = (ref.skipped_preint.dp[k2], ref.skipped_preint.dv[k2], ref.skipped_preint.dR[k2])
+        else:
+            q = [q for q in range(ref.n_imu) if ref.imu_j[q] == f][0]
+            mine = (ref.imu_dp[q], ref.imu_dv[q], ref.imu_dR[q])
+        assert np.abs(mine[0] - dp).max() < 1e-14 and np.abs(mine[1] - dv).max() < 1e-14 and np.abs(mine[2] - dR.reshape(9)).max() < 1e-14
+        n_checked += 1
+    assert n_checked == orig.n_imu
+    lm = np.array([[float(x) for x in ln.split()] for ln in out[2 + F:2 + F + L]])
+    assert np.abs(lm - ref.lmk_t).max() < 1e-15
+
+
+@pytest.mark.gpu
+def test_failure_termination_writes_back_and_returns_true_in_both_adapters(adapter_exe):
+    """Ceres FAILURE (5 invalid steps in a row; here: a NaN measurement) is not an error of the entry point: the reference
+    ignores the summary, writes back the last accepted x and returns true (AOptimizer.cpp:388-445).  The C ABI reports
+    SDV_ERR_NUMERICAL_FAILURE; both adapters map it to write-back + true, and the oracle ends the same way."""
+    from oracle import oracle as orc
+    from sadvio_b200 import api
+
+    win = synth.make_window("small")
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), False)
+    env = dict(os.environ, SDV_TEST_NAN_OBS="1")
+    out = subprocess.run([adapter_exe, "solve", "1", "1"], input=txt, capture_output=True, text=True, check=True, env=env).stdout.split("\n")
+    assert out[1].split() == ["1", "5"]                      # returned true after 5 (invalid) iterations
+    bad = synth.make_window("small")
+    bad.obs_bearing[0, 0] = np.nan
+    rc0, d0, st0 = orc.solve_window(bad)
+    assert rc0 == 5 and st0["termination"] == "FAILURE" and st0["iterations"] == 5
+    opt = api.B200Optimizer()
+    before = bad.T_f_w.copy()
+    assert opt.localMapVIOptimization(bad, 1) is True
+    assert opt.last_stats["termination"] == "FAILURE" and opt.last_stats["iterations"] == 5
+    assert np.array_equal(bad.T_f_w, before)                 # the last accepted x is the start: nothing moved
+    rows = [np.array([float(x) for x in ln.split()]) for ln in out[2:2 + win.n_frames]]
+    for k, row in enumerate(rows):
+        assert np.abs(row[:12] - before[win.n_frames - 1 - k]).max() < 1e-15

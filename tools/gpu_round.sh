@@ -40,6 +40,18 @@ variant)
     env "$@" timeout 60 python tools/solve_once.py C3 5 2>&1 | tail -1 | tee -a $out/variant_$sw.log
     env "$@" timeout 60 python tools/chol_only.py 2>&1 | tail -3 | tee -a $out/variant_$sw.log
     ;;
+prebuilt)
+    # same checks as `variant` for experiment libraries built in the container (sadvio_b200/_lib/variants/lib_<switch>.so,
+    # they travel with the snapshot), selected through SDV_LIB:   gpu_round.sh prebuilt SDV_BAND_REV [env assignments ...]
+    sw=${2:?switch name}
+    shift 2
+    tag=$sw$(echo "$@" | tr -c 'A-Za-z0-9=\n' '_')
+    export SDV_LIB=$PWD/sadvio_b200/_lib/variants/lib_$sw.so
+    env "$@" timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "full_solve or band or golden or reference or gradient_tolerance or tight_convergence" 2>&1 | tail -8 | tee $out/variant_$tag.log
+    env "$@" timeout 60 python tools/solve_once.py C3 5 2>&1 | tail -1 | tee -a $out/variant_$tag.log
+    env "$@" timeout 60 python tools/chol_only.py 2>&1 | tail -3 | tee -a $out/variant_$tag.log
+    env "$@" timeout 60 python tools/chol_only.py C5 2>&1 | tail -3 | tee -a $out/variant_$tag.log
+    ;;
 micro)
     name=${2:?micro-benchmark name (tools/micro/<name>.cu)}
     shift 2
