@@ -17,9 +17,9 @@ HEADERS = ["sdv_kernels.cuh", "sdv_chol.cuh", "sdv_chol_band.cuh", "sdv_math.cuh
 NVCC_FLAGS = [
     *(["-DSDV_BAND_PROF"] if os.environ.get("SDV_BAND_PROF") else []),
     *(["-DSDV_SCHUR_PROF"] if os.environ.get("SDV_SCHUR_PROF") else []),
-    *(["-DSDV_BAND_BACKWARD_V2=1"] if os.environ.get("SDV_BAND_BACKWARD_V2") else []),  # experiment, see DESIGN.md section 7
-    *(["-DSDV_BAND_REV=1"] if os.environ.get("SDV_BAND_REV") else []),                  # first milestone of the two-way dissection
-    *(["-DSDV_BAND_BABE=1"] if os.environ.get("SDV_BAND_BABE") else []),                # second milestone: the 2-CTA cluster itself
+    # k_chol_band switches (sdv_chol_band.cuh): SDV_BAND_BABE=0 / SDV_BAND_BACKWARD_V2=0 build the round-1 kernel,
+    # SDV_BAND_REV=1 (with SDV_BAND_BABE=0) the index-reversed debugging variant
+    *([f"-D{k}={os.environ[k]}" for k in ("SDV_BAND_BACKWARD_V2", "SDV_BAND_REV", "SDV_BAND_BABE") if os.environ.get(k)]),
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 

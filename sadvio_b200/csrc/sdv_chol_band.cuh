@@ -41,27 +41,29 @@ constexpr int BAND_MAX_STAGES = 16; // backward-solve ring (TMA bulk copies in f
 #define SDV_BAND_STREAM_UPDATES 0
 #endif
 constexpr bool BAND_STREAM_UPDATES = SDV_BAND_STREAM_UPDATES != 0;
-// -DSDV_BAND_BACKWARD_V2=1: specialised full steps in the backward solve (band_backward_full_step below), experiment.
+// Specialised full steps in the backward solve (band_backward_full_step below).  Default since round 2 (measured on B200:
+// 142 -> 135 us at C3 alone; all parity tests green); -DSDV_BAND_BACKWARD_V2=0 restores the generic loop.
 #ifndef SDV_BAND_BACKWARD_V2
-#define SDV_BAND_BACKWARD_V2 0
+#define SDV_BAND_BACKWARD_V2 1
 #endif
-// First milestone of the two-way dissection, OFF by default and not yet run on a GPU: with
+// First milestone of the two-way dissection, a debugging aid (parity green on B200, round 2): with
 // -DSDV_BAND_REV=1 the whole kernel factors P S P instead of S (P = index reversal, row i <-> n_pad-1-i, which keeps the
 // 16-column blocks aligned) and scatters the solution back — what the second CTA of the cluster will do on its half.  The
 // band of P S P is the band of S, the solution is the same up to rounding: every parity test applies unchanged.
 #ifndef SDV_BAND_REV
 #define SDV_BAND_REV 0
 #endif
-// Second milestone, OFF by default and not yet run on a GPU: -DSDV_BAND_BABE=1 adds the two-way dissection itself.  Launched
+// The two-way dissection itself ("burn at both ends"), DEFAULT since round 2 (B200: 142 -> 113 us at C3, 511 -> 384 us at C5,
+// all parity tests green; -DSDV_BAND_BABE=0 builds the one-CTA kernel of round 1).  Launched
 // as a 2-CTA cluster (sdv_lib.cu does so when the band is long enough) CTA 0 eliminates block rows 0 .. nl-1 of S, CTA 1 block
 // rows 0 .. nr-1 of P S P, CTA 0 adds CTA 1's separator update (read through distributed shared memory), finishes the
 // separator and the forward substitution, solves the separator unknowns, hands them to CTA 1, and both back-substitute
 // their interiors.  Launched as a single CTA the kernel behaves as before.  tools/babe_prototype.py is the numpy model.
 #ifndef SDV_BAND_BABE
-#define SDV_BAND_BABE 0
+#define SDV_BAND_BABE 1
 #endif
-#if SDV_BAND_BABE && (SDV_BAND_REV || SDV_BAND_STREAM_UPDATES || SDV_BAND_BACKWARD_V2)
-#error "SDV_BAND_BABE excludes SDV_BAND_REV, SDV_BAND_STREAM_UPDATES and SDV_BAND_BACKWARD_V2"
+#if SDV_BAND_BABE && (SDV_BAND_REV || SDV_BAND_STREAM_UPDATES)
+#error "SDV_BAND_BABE excludes SDV_BAND_REV and SDV_BAND_STREAM_UPDATES"
 #endif
 #if SDV_BAND_BABE
 #define BAND_BNB nbk
@@ -356,7 +358,7 @@ SDV_DEV double dsmem_load(const double *local_addr, unsigned rank) {
 #endif
 
 #if SDV_BAND_BACKWARD_V2
-// EXPERIMENT, off by default and not yet run on a GPU (tools/micro/backward.cu times it alone): one FULL block step of the
+// (tools/micro/backward.cu times it alone): one FULL block step of the
 // backward solve (all BW sub-diagonal blocks present) with every load of the step issued up front and the d = 1 block — the
 // only one whose x was produced by the previous step — closing the FMA chains.  Returns x_k[c] in both half-warps.
 template <int BW> SDV_DEV double band_backward_full_step(const double *sb, const double *gs, double *rvs, int k, int lane) {
@@ -1108,26 +1110,13 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             mbar_wait(&full[s], (unsigned)ph);
             BAND_TICK(3);
             const double *sb = ring + s * stage_doubles;
+            double x;
 #if SDV_BAND_BACKWARD_V2
             if (nd == bw && (bw == 3 || bw == 4)) { // full step of the common band widths: specialised body
-                const double xf = bw == 3 ? band_backward_full_step<3>(sb, gs, rvs, k, lane) : band_backward_full_step<4>(sb, gs, rvs, k, lane);
-                if (hh == 0) {
-                    gs[k * BN + c] = xf;
-                    dxp[SDV_BAND_REV ? P.n_pad - 1 - (k * BN + c) : k * BN + c] = -xf;
-                }
-                __syncwarp();
-                if (lane == 0 && it + NS < BAND_BNB) {
-                    const int k2 = BAND_BNB - 1 - (it + NS);
-                    mbar_expect_tx(&full[s], stage_bytes);
-                    bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k2 * stage_doubles, stage_bytes, &full[s]);
-                }
-                if (++s == NS) {
-                    s = 0;
-                    ph ^= 1;
-                }
-                continue;
-            }
+                x = bw == 3 ? band_backward_full_step<3>(sb, gs, rvs, k, lane) : band_backward_full_step<4>(sb, gs, rvs, k, lane);
+            } else
 #endif
+            {
             // (L_(k+d,k))^T x_(k+d), d = 1..nd: lane (c, hh) sums rows 8 hh .. 8 hh + 7 of every block; four independent chains
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -1158,8 +1147,9 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, L
             x1 = fma(Mi[80], rc.y, x1);
             x2v = fma(Mi[96], rd.x, x2v);
             x3 = fma(Mi[112], rd.y, x3);
-            double x = (x0 + x1) + (x2v + x3);
+            x = (x0 + x1) + (x2v + x3);
             x += __shfl_xor_sync(FULL, x, 16);
+            }
             if (hh == 0) {
                 gs[k * BN + c] = x;
 #if SDV_BAND_BABE

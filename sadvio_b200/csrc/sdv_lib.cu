@@ -7,6 +7,7 @@
 // There is NO CPU fallback: without a CUDA device sdv_create fails with SDV_ERR_NO_DEVICE.
 #include "../../include/sdv.h"
 #include "sdv_kernels.cuh"
+#include "sdv_fused.cuh"
 #include "sdv_chol.cuh"
 #include "sdv_chol_band.cuh"
 
@@ -127,6 +128,10 @@ struct sdv_handle {
     int rank = 0, world = 1;
     std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs, tmp_chunk_ptr; // reused between uploads
     std::vector<char> tmp_same_prev;
+    std::vector<int> tmp_tile_ptr;
+    double *d_lmk_aux = nullptr; // [L][LMK_AUX]: V^-1, g_l, D_l of every eliminated landmark (k_lin_schur -> k_backsub_cost)
+    int fused_grid = 0;
+    bool legacy_schur = false;   // SDV_LEGACY_SCHUR=1: the round-1 kernels (materialised Jacobians), kept for cross-checks
     std::vector<uint32_t> tmp_tile_nz;
     bool attrs_done = false;
     const void *lin_fn_cached = nullptr;
@@ -668,6 +673,23 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         chunk_ptr.push_back(l1);
     }
     const int nchunks = (int)chunk_ptr.size() - 1;
+    // ---- tiles of the fused kernels: consecutive landmarks of this rank, at most FT slots and FT_LMK landmarks each
+    std::vector<int> &tile_ptr = h->tmp_tile_ptr;
+    tile_ptr.clear();
+    {
+        int l = l0;
+        while (l < l1) {
+            tile_ptr.push_back(l);
+            int nsl = 0, nlm = 0;
+            while (l < l1 && nlm < FT_LMK && nsl + (slot_ptr[l + 1] - slot_ptr[l]) <= FT) {
+                nsl += slot_ptr[l + 1] - slot_ptr[l];
+                nlm++;
+                l++;
+            }
+        }
+        tile_ptr.push_back(l1);
+    }
+    const int ntiles = (int)tile_ptr.size() - 1;
 
     auto t_s3 = std::chrono::steady_clock::now();
     // ---- dense prior column maps
@@ -838,6 +860,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     size_t o_lc = A.add(4 * std::max(L, 1));
     size_t o_tnz = A.add(4 * tile_nz.size());
     size_t o_chk = A.add(4 * chunk_ptr.size());
+    size_t o_tile = A.add(4 * tile_ptr.size());
     size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(nslotobs, 1));
     size_t o_ii = A.add(4 * std::max(Pn, 1)), o_ij = A.add(4 * std::max(Pn, 1));
     size_t o_idt = A.add(D * std::max(Pn, 1)), o_idR = A.add(D * 9 * std::max(Pn, 1)), o_idv = A.add(D * 3 * std::max(Pn, 1)),
@@ -899,6 +922,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     std::memcpy(hb + o_pc, pose_col.data(), 4 * F);
     std::memcpy(hb + o_tnz, tile_nz.data(), 4 * tile_nz.size());
     std::memcpy(hb + o_chk, chunk_ptr.data(), 4 * chunk_ptr.size());
+    std::memcpy(hb + o_tile, tile_ptr.data(), 4 * tile_ptr.size());
     std::memcpy(hb + o_vc, vb_col.data(), 4 * F);
     std::memcpy(hb + o_Ts, w->T_s_f, D * 12 * C);
     std::memcpy(hb + o_K, w->K, D * 4 * C);
@@ -1003,6 +1027,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     size_t s_part = S.add(D * (size_t)(n_pad / 32 + 1) * CC_MAX * 32);
     size_t s_dinv = S.add(D * (n_pad + 32));
     size_t s_prof = S.add(D * 8 * CC_MAX);
+    size_t s_aux = S.add(D * LMK_AUX * std::max(L, 1));
     if ((rc = ensure(h, &h->d_scr, &h->scr_cap, S.size)) != SDV_OK) return rc;
     unsigned char *sb = h->d_scr;
     size_t out_bytes = D * ((size_t)15 * F + 3 * (size_t)std::max(L, 1));
@@ -1026,6 +1051,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     P.tile_nz = at<uint32_t>(db, o_tnz);
     P.chunk_ptr = at<int>(db, o_chk);
     P.nchunks = nchunks;
+    P.tile_ptr = at<int>(db, o_tile);
+    P.ntiles = ntiles;
     P.slot_ptr = at<int>(db, o_sp); P.slot_frame = at<int>(db, o_sf); P.slot_obs_ptr = at<int>(db, o_sop); P.slot_obs = at<int>(db, o_so);
     P.obs_lmk = at<int>(h->d_in2, q_ol); P.obs_fc = at<int>(h->d_in2, q_ofc); P.obs_meas = at<double>(h->d_in2, q_om);
     P.obs_w = w->obs_sigma ? at<double>(h->d_in2, q_ow) : nullptr;
@@ -1072,6 +1099,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     h->d_partial = at<double>(sb, s_part);
     h->d_dinv = at<double>(sb, s_dinv);
     h->d_prof = at<double>(sb, s_prof);
+    h->d_lmk_aux = at<double>(sb, s_aux);
     h->sb_elems = sb_elems;
 
     // ---- launch geometry
@@ -1086,6 +1114,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         CK(cudaFuncSetAttribute(k_schur<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(k_schur<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(k_chol_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CK(cudaFuncSetAttribute(k_lin_schur<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_SCHUR));
+        CK(cudaFuncSetAttribute(k_lin_schur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_SCHUR));
         h->attrs_done = true;
     }
     if ((const void *)h->lin_fn != h->lin_fn_cached || h->lin_smem != h->lin_smem_cached) {
@@ -1105,6 +1135,8 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         h->sch_grid_chunks = std::max(1, std::min((nchunks + gpb - 1) / gpb, h->num_sms * 8)); // k_schur: one group per chunk
     }
     h->fac_grid = std::max(1, (std::max(Pn, 1) + FAC_WARPS - 1) / FAC_WARPS);
+    h->fused_grid = std::max(1, std::min(ntiles, h->num_sms * 3));
+    h->legacy_schur = getenv("SDV_LEGACY_SCHUR") != nullptr;
     // dense Cholesky: one thread-block cluster when the reduced system is small enough, per-panel launches otherwise
     h->chol_cluster = 0;
     h->band_smem = 0;
@@ -1204,6 +1236,14 @@ constexpr int SCH_ACC_BYTES = 39 * SCH_WARPS * 32 * (int)sizeof(double);
 void launch_schur(sdv_handle *h) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
+    if (!h->legacy_schur) {
+        if (P.ntiles > 0) {
+            if (P.kind == SDV_FACTOR_ANGULAR) k_lin_schur<0><<<h->fused_grid, FT, FT_SMEM_SCHUR, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_lmk_aux);
+            else k_lin_schur<1><<<h->fused_grid, FT, FT_SMEM_SCHUR, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_lmk_aux);
+            h->launches++;
+        }
+        return;
+    }
     if (h->group == 8) k_schur<8><<<h->sch_grid_chunks, SCH_WARPS * 32, SCH_ACC_BYTES, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_prof);
     else if (h->group == 16) k_schur<16><<<h->sch_grid_chunks, SCH_WARPS * 32, SCH_ACC_BYTES, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_prof);
     else k_schur<32><<<h->sch_grid_chunks, SCH_WARPS * 32, SCH_ACC_BYTES, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_prof);
@@ -1212,6 +1252,14 @@ void launch_schur(sdv_handle *h) {
 void launch_backsub(sdv_handle *h) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
+    if (!h->legacy_schur) { // back-substitution and the candidate cost of the visual factors in one kernel
+        if (P.ntiles > 0) {
+            if (P.kind == SDV_FACTOR_ANGULAR) k_backsub_cost<0><<<h->fused_grid, FT, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_dxp, h->d_lmk_aux);
+            else k_backsub_cost<1><<<h->fused_grid, FT, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_dxp, h->d_lmk_aux);
+            h->launches++;
+        }
+        return;
+    }
     if (h->group == 8) k_backsub<8><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
     else if (h->group == 16) k_backsub<16><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
     else k_backsub<32><<<h->sch_grid, SCH_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_dxp, h->d_scale_l);
@@ -1241,10 +1289,18 @@ void launch_lin_factors(sdv_handle *h, int which, cudaStream_t s) {
     }
 }
 
-void launch_lin_visual(sdv_handle *h, int which) {
+// materialise = true: residual + Jacobian planes of every observation (sdv_eval_visual, the round-1 solve path);
+// false: the fused solve path only needs the COST of the visual factors here (iteration 0; the candidate cost comes out of
+// k_backsub_cost, the Jacobians are formed inside k_lin_schur)
+void launch_lin_visual(sdv_handle *h, int which, bool materialise) {
     const DevProblem &P = h->P;
-    if (P.o1 > P.o0) {
+    if (P.o1 > P.o0 && materialise) {
         h->lin_fn<<<h->lin_grid, LIN_THREADS, h->lin_smem, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        h->launches++;
+    } else if (P.o1 > P.o0 && which >= 0) {
+        const int grid = std::max(1, std::min((P.o1 - P.o0 + 255) / 256, h->num_sms * 4));
+        if (P.kind == SDV_FACTOR_ANGULAR) k_visual_cost<0><<<grid, 256, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
+        else k_visual_cost<1><<<grid, 256, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, h->d_acc, which);
         h->launches++;
     }
     if (P.sp_np2l > 0) {
@@ -1253,8 +1309,8 @@ void launch_lin_visual(sdv_handle *h, int which) {
     }
 }
 
-int launch_linearize(sdv_handle *h, int which) {
-    launch_lin_visual(h, which);
+int launch_linearize(sdv_handle *h, int which, bool materialise) {
+    launch_lin_visual(h, which, materialise);
     launch_lin_factors(h, which, h->stream);
     return SDV_OK;
 }
@@ -1421,7 +1477,7 @@ int launch_iteration(sdv_handle *h) {
         const bool forked = has_factors(P) && fork_side(h, 1);
         launch_lin_factors(h, -2, forked ? h->side : s);
         launch_backsub(h);
-        launch_lin_visual(h, -2);
+        launch_lin_visual(h, -2, h->legacy_schur); // fused path: only the PoseToLandmark pseudo-observations are linearised here
         if (forked) join_side(h, 1);
     }
     int rc = reduce_scalars(h, -2);
@@ -1447,7 +1503,7 @@ int enqueue_prologue(sdv_handle *h) {
     CK(cudaMemsetAsync(h->d_acc, 0, sizeof(Accum), s));
     k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, 0);
     h->launches++;
-    launch_linearize(h, 0);
+    launch_linearize(h, 0, h->legacy_schur);
     int rc = reduce_scalars(h, 0);
     if (rc != SDV_OK) return rc;
     k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
@@ -1716,7 +1772,7 @@ int sdv_eval_visual(sdv_handle *h, const sdv_delta *x, double *r, double *J_pose
     if (rc != SDV_OK) return rc;
     k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, h->stream>>>(P, h->B[0], h->B[1], h->d_st, 0);
     h->launches++;
-    launch_linearize(h, 0);
+    launch_linearize(h, 0, true);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     const int Oloc = P.o1 - P.o0;
@@ -1772,7 +1828,7 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
     int rc = set_point(h, nullptr);
     if (rc != SDV_OK) return rc;
     k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(P, h->B[0], h->B[1], h->d_st, 0);
-    launch_linearize(h, 0);
+    launch_linearize(h, 0, true);
     k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
     CK(cudaStreamSynchronize(s));
     float total = 0;
@@ -1798,6 +1854,20 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
                 int rcf = launch_factor_solve(h);
                 if (rcf != SDV_OK) return rcf;
             }
+            CK(cudaEventRecord(h->ev[3], s));
+        } else if (which == 3) {
+            // back-substitution (+ candidate cost in the fused path): needs a valid reduced step, so one Schur / factor / solve first
+            if (it == 0) {
+                CK(cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s));
+                launch_schur(h);
+                if (P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0))
+                    k_assemble_factors<<<h->fac_grid, FAC_WARPS * 32, 0, s>>>(P, h->B[0], h->B[1], h->d_st, h->d_Sb);
+                if (h->band_smem == 0) k_sysprep<<<1, 1024, 0, s>>>(P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
+                int rcf = launch_factor_solve(h);
+                if (rcf != SDV_OK) return rcf;
+            }
+            CK(cudaEventRecord(h->ev[2], s));
+            launch_backsub(h);
             CK(cudaEventRecord(h->ev[3], s));
         } else {
             return fail(h, SDV_ERR_INVALID_ARGUMENT, "unknown kernel id");

@@ -83,6 +83,8 @@ struct DevProblem {
     const int *slot_ptr;    // [L+1] first slot of each landmark
     const int *chunk_ptr;   // [nchunks+1] landmark ranges of this rank whose landmarks are seen from the same keyframes (k_schur)
     int nchunks;
+    const int *tile_ptr;    // [ntiles+1] landmark ranges of this rank with <= FT slots and <= FT_LMK landmarks (k_lin_schur, k_backsub_cost)
+    int ntiles;
     const int *slot_frame;  // [nslots]
     const int *slot_obs_ptr;// [nslots+1]
     const int *slot_obs;    // plane indices (local to this rank) of the observations grouped by slot

@@ -18,7 +18,7 @@ for name in (sys.argv[1:] or ["tiny", "small", "C2", "C3"]):
           f"cost {st['final_cost']:.6f}/{st0['final_cost']:.6f} pose {rel(d.dpose, d0.dpose):.2e} lmk {rel(d.dlmk, d0.dlmk):.2e} "
           f"dev {st['ms_solve_device']:.3f} ms", flush=True)
     s.upload(w)
-    print(f"  cholesky {s.time_kernel(2, 20)*1e3:.1f} us  schur {s.time_kernel(1, 20)*1e3:.1f} us  lin {s.time_kernel(0, 20)*1e3:.1f} us")
+    print(f"  cholesky {s.time_kernel(2, 20)*1e3:.1f} us  schur {s.time_kernel(1, 20)*1e3:.1f} us  lin {s.time_kernel(0, 20)*1e3:.1f} us  backsub {s.time_kernel(3, 20)*1e3:.1f} us")
     prof = s.debug_read(5, 128)
     print("  schur block 0 thread 0 [pre acc gsum inv diag pairs flush] kcycles:", " ".join(f"{x/1e3:7.1f}" for x in prof[64:71]))
     print("  warp 0 [setup wait chain bwd_wait tail backward] kcycles:", " ".join(f"{x/1e3:8.1f}" for x in prof[0:6]))
