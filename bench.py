@@ -9,6 +9,11 @@ One "step" = one window solve with the reference's options (<= 20 LM iterations,
 all factors, landmark Schur, dense Cholesky, back-substitution, candidate cost, LM control.  The value is
 LM iterations / second over the timed steps (whole job; at N > 1 the landmark blocks are sharded across ranks and
 the reduced system is all-reduced once per iteration, so this is STRONG scaling of one window).
+
+The end-to-end arm (`e2e`) calls the C-ABI entry point on HOST buffers and cycles through four C3 windows of different
+landmark / observation counts, as a running back end does from keyframe to keyframe, so everything a new window costs
+(structure pass, packing, H2D, CUDA-graph reuse or rebuild) is inside the number.  `c5` is the same solve on BASELINE config 5
+(200 KF x 100k landmarks x 800k obs), the configuration where sharding the landmarks over several GPUs can pay.
 """
 from __future__ import annotations
 
@@ -28,7 +33,42 @@ sys.path.insert(0, ROOT)
 METRIC = "GN iters/sec on 50-KF x 10k-landmark window"
 UNIT = "iter/s"
 WORKLOAD = "C3: synthetic 50 KF x 10000 landmarks x 80000 obs, stereo bearing factors + 49 IMU/bias factors + pose prior, 1 fixed KF"
-BYTES_PER_OBS = 196  # 36 B read + 160 B written per observation, FP64, J materialised
+BYTES_PER_OBS = 196  # 36 B read + 160 B written per observation, FP64, J materialised (k_lin_visual)
+# fused solve path (SURVEY.md §8d "whole iteration, fused"): 32 B per observation are read (bearing 24 + packed frame/camera
+# index 4 + landmark index via the slot lists 4), 24 B per landmark position, 96 B per landmark of V^-1 / g_l / D_l
+FUSED_OBS_BYTES, LMK_BYTES, AUX_BYTES = 32, 24, 96
+
+
+def ncu_traffic(path: str) -> dict:
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) by kernel name, from a committed ncu CSV
+    (`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv`, tools/gpu_round.sh traffic).  {} when absent."""
+    import csv
+    out: dict = {}
+    try:
+        rows = list(csv.reader(open(path)))
+    except OSError:
+        return out
+    hdr = next((r for r in rows if "Kernel Name" in r and "Metric Name" in r), None)
+    if hdr is None:
+        return out
+    ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc: dict = {}
+    for r in rows[rows.index(hdr) + 1:]:
+        if len(r) <= max(ik, im, iv, iu) or not r[im].startswith("dram__bytes_"):
+            continue
+        name = r[ik].split("(")[0].split("<")[0].replace("void ", "").replace("sdv::", "").strip()
+        try:
+            v = float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
+        except ValueError:
+            continue
+        a = acc.setdefault(name, {"bytes": 0.0, "read": 0, "write": 0})
+        a["bytes"] += v
+        a["read" if "read" in r[im] else "write"] += 1
+    for name, a in acc.items():
+        launches = max(a["read"], a["write"], 1)
+        out[name] = a["bytes"] / launches
+    return out
 
 
 def measured_peaks():
@@ -120,6 +160,22 @@ def state_deviation(d_gpu, d_cpu) -> float:
     return worst
 
 
+def trimmed(win, n_drop: int):
+    """The window without its last `n_drop` landmarks and their observations (same keyframes): the e2e arm cycles through
+    several of these, the way the window changes from one keyframe to the next in a running back end."""
+    import copy
+
+    w = copy.copy(win)
+    L = win.n_lmks - n_drop
+    keep = win.obs_lmk < L
+    for name in ("obs_lmk", "obs_frame", "obs_cam", "obs_bearing", "obs_uv"):
+        a = getattr(win, name)
+        if a is not None:
+            setattr(w, name, np.ascontiguousarray(a[keep]))
+    w.lmk_t = np.ascontiguousarray(win.lmk_t[:L])
+    return w
+
+
 def cpu_baseline(win, budget_s: float = 12.0, max_solves: int = 8) -> dict:
     """The oracle port (CPU restatement of the reference path) timed on this box's host cores, bounded sample."""
     from oracle import oracle
@@ -177,7 +233,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-c5", action="store_true", help="skip the C5-sized measurement of the Jacobian kernel")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (solve on config 5, kernel rooflines at C5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -247,34 +303,72 @@ def main():
     # ---------------- end-to-end arm: the reference-facing call with HOST buffers (H2D + solve + D2H inside)
     # The timed call is the C-ABI entry point itself, sdv_solve_window(handle, &window, &delta, &stats), on caller-owned host
     # arrays — what the C++ adapter calls; the ctypes views of the numpy arrays are made once, outside.
+    # It CYCLES through four windows of different landmark / observation counts: whatever a changed window costs (structure
+    # pass, packing, H2D, graph reuse) is inside the number.
     import ctypes as C
     from sadvio_b200 import abi
-    for _ in range(2):
-        solver.solve_window(win)
-    ws = win.as_struct()
-    d_e2e = abi.Delta.zeros(win.n_frames, win.n_lmks)
-    ds = d_e2e.as_struct()
+    e2e_drops = (0, 40, 80, 120) if args.config == "C3" else (0, 4, 8, 12)
+    wins = [win] + [trimmed(win, d) for d in e2e_drops[1:]]
+    views = []
+    for w in wins:
+        d_w = abi.Delta.zeros(w.n_frames, w.n_lmks)
+        views.append((w, w.as_struct(), d_w, d_w.as_struct()))
+    builds0 = solver.graph_builds()
+    for k in range(2 * len(wins)):
+        solver.solve_window(wins[k % len(wins)])
     stc = abi.SdvStats()
     sdv_solve_window = api.lib().sdv_solve_window
     e_t, e_its, h2d, d2h = 0.0, 0, 0, 0
-    e_steps = max(3, args.steps // 2)
-    for _ in range(e_steps):
+    e_steps = max(4, args.steps // 2)
+    for k in range(e_steps):
+        w, ws, d_w, ds = views[k % len(views)]
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
         rc = sdv_solve_window(solver._h, C.byref(ws), C.byref(ds), C.byref(stc))
         dt = time.perf_counter() - t0
         assert rc in (0, 5), rc
-        st = {"iterations": int(stc.iterations), "h2d_bytes": int(stc.h2d_bytes), "d2h_bytes": int(stc.d2h_bytes)}
         if world > 1:
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e_t += dt
-        e_its += st["iterations"]
-        h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
-    e2e = {"value": e_its / e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": 1e3 * e_t / e_steps}
+        e_its += int(stc.iterations)
+        h2d += int(stc.h2d_bytes)
+        d2h += int(stc.d2h_bytes)
+    d_e2e = views[0][2]
+    e2e = {"value": e_its / e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e_steps), "d2h_bytes_per_step": int(d2h / e_steps),
+           "ms_per_step": 1e3 * e_t / e_steps, "windows_cycled": [{"n_lmks": int(w.n_lmks), "n_obs": int(w.n_obs)} for w in wins],
+           "cuda_graph_builds_in_arm": int(solver.graph_builds() - builds0)}
+
+    # ---------------- BASELINE config 5 (200 KF x 100k landmarks x 800k obs): the window where sharding landmarks can pay
+    c5 = None
+    if not args.no_c5:
+        try:
+            win5 = synth.make_window("C5")
+            solver.upload(win5)
+            for _ in range(3):
+                solver.solve_resident()
+            t5, its5 = 0.0, 0
+            n5 = 5
+            for _ in range(n5):
+                flush.zero_()
+                barrier()
+                t0 = time.perf_counter()
+                rc, st5 = solver.solve_resident()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                if world > 1:
+                    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    dt = float(tt.item())
+                t5 += dt
+                its5 += st5["iterations"]
+            c5 = {"workload": "C5: synthetic 200 KF x 100000 landmarks x 800000 obs, full VIO factor set", "value": its5 / t5, "unit": UNIT,
+                  "ms_per_step": 1e3 * t5 / n5, "lm_iterations_per_step": its5 / n5, "steps": n5, "n_gpus": world}
+            d_c5 = solver.download()
+        except Exception as e:  # noqa: BLE001
+            c5 = {"error": str(e)}
 
     if rank != 0:
         if world > 1:
@@ -284,65 +378,83 @@ def main():
     # ---------------- per-kernel timing (CUDA events on the library's stream) and roofline of the dominant kernel
     peak, peak_src = measured_peaks()
     its_per_step = its / args.steps
+    solver.upload(win)
+    n, npad = solver.debug_dims()
+    O, Lr = win.n_obs // world, win.n_lmks // world  # rank 0's landmark shard (observation-balanced) at N > 1
+    traffic_csv = os.path.join(ROOT, "profiles", "r02_ncu_traffic_c3.csv")
+    traffic = ncu_traffic(traffic_csv) if args.config == "C3" and world == 1 else {}
+    band_bytes = 8 * n * 80  # the band of the reduced system the Schur kernel adds into (half-bandwidth ~ 5 blocks of 16)
+    specs = [
+        (1, "k_lin_schur", "fused visual linearisation (Jacobians in registers) + per-landmark 3x3 Schur complement + assembly of S, "
+            "per-run reduction in shared memory", FUSED_OBS_BYTES * O + (LMK_BYTES + AUX_BYTES) * Lr + band_bytes, its_per_step),
+        (2, "k_chol_band", "system preparation + banded FP64 Cholesky + triangular solves of the reduced system: 2-CTA cluster burning the "
+            "band from both ends, register-resident pivot chains, DMMA trailing updates, TMA-ring backward solve", 8 * n * n, its_per_step),
+        (3, "k_backsub_cost", "fused landmark back-substitution (Jacobians recomputed) + residual-only candidate cost",
+            2 * FUSED_OBS_BYTES * O + (2 * LMK_BYTES + AUX_BYTES + 24) * Lr, its_per_step),
+    ]
     kern = []
-    if True:  # per-kernel timings of rank 0 (its landmark shard at N > 1; no collective inside sdv_time_kernel)
-        n, npad = solver.debug_dims()
-        O = win.n_obs // world  # rank 0's landmark shard (observation-balanced) at N > 1
-        # traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture of this workload
-        # (profiles/r01_ncu_traffic_c3.txt; null for other configs)
-        traffic = {0: 3.09e6, 1: 13.9e6, 2: 0.64e6} if args.config == "C3" else {}
-        specs = [
-            (0, "k_lin_visual (residual+Jacobian of every visual factor, J materialised as SoA planes)", BYTES_PER_OBS * O, "hbm", its_per_step + 1),
-            (1, "k_schur (per-landmark 3x3 Schur complement + assembly of the reduced system, chunked atomics)", 160 * O + 8 * n * n // 2, "hbm", its_per_step),
-            (2, "k_chol_band (system preparation + banded FP64 Cholesky + triangular solves of the reduced system in one CTA: "
-                "register-resident pivot chain, DMMA trailing updates, TMA-ring backward solve)", 8 * n * n, "hbm", its_per_step),
-        ]
-        for which, name, nbytes, bound, per_step in specs:
-            ms = solver.time_kernel(which, 20)
-            kern.append({"name": name, "ms_per_launch": ms, "launches_per_step": per_step, "algorithmic_bytes": int(nbytes),
-                         "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
-                         "dram_traffic_bytes": traffic.get(which),
-                         "share_of_step": ms * per_step / (1e3 * t_total / args.steps)})
-        dom = max(kern, key=lambda k: k["share_of_step"])
-        roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_hbm_peak"],
-                    "traffic": dom["dram_traffic_bytes"], "kernel": dom["name"], "peak_source": peak_src,
-                    "note": "dominant kernel by share of the step. It is a dependency chain of n = 735 pivots (FP64 latency-bound, "
-                            "one SM by design): the HBM fraction is reported because the contract asks for it, the meaningful "
-                            "figure is ms_per_launch (DESIGN.md section 3). The HBM-bound kernel of the path is k_lin_visual: "
-                            "see jacobian_kernel_c5"}
+    for which, kname, desc, nbytes, per_step in specs:
+        ms = solver.time_kernel(which, 20)
+        ms_cold = solver.time_kernel(which + 10, 10) if which != 2 else None
+        kern.append({"name": f"{kname} ({desc})", "kernel": kname, "ms_per_launch": ms, "ms_per_launch_cold_l2": ms_cold, "launches_per_step": per_step,
+                     "algorithmic_bytes": int(nbytes), "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
+                     "dram_traffic_bytes": traffic.get(kname), "share_of_step": ms * per_step / (1e3 * t_total / args.steps)})
+    dom = max(kern, key=lambda k: k["share_of_step"])
+    roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_hbm_peak"],
+                "traffic": dom["dram_traffic_bytes"], "traffic_source": "profiles/r02_ncu_traffic_c3.csv (ncu, per launch)" if traffic else None,
+                "kernel": dom["name"], "peak_source": peak_src,
+                "note": "dominant kernel by share of the step. The reduced-system factorisation is a dependency chain of n = 735 pivots "
+                        "(FP64 latency-bound, two SMs by design): the HBM fraction is reported because the contract asks for it, the "
+                        "meaningful figure is ms_per_launch (DESIGN.md section 3). The HBM-bound kernels of the path are k_lin_schur / "
+                        "k_backsub_cost at C5 and the materialising evaluation kernel: see jacobian_kernel_c5"}
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_baseline(win)
+    if not args.no_cpu_baseline:
+        if world == 1:
+            cpu = cpu_baseline(win)
+        else:  # N > 1: the checker's solution of the same window, once, for the parity figures of the line (not a timing)
+            from oracle import oracle
+            cpu_baseline.last_solution = oracle.solve_window(win, nthreads=min(16, os.cpu_count() or 1))[1:]
 
-    # The Jacobian kernel where its HBM roofline is physically meaningful (at C3 one pass moves 15.7 MB and
-    # stays in the 126 MB L2; at C5 it moves 156.8 MB): same kernel, 200 KF x 100k landmarks x 800k observations.
+    # The materialising Jacobian kernel (the evaluation entry point sdv_eval_visual; the solve itself no longer writes J) where
+    # its HBM roofline is physically meaningful (at C3 one pass moves 15.7 MB and stays in the 126 MB L2; at C5
+    # 156.8 MB): warm = relaunched into the same buffer, cold = 256 MiB L2 flush between launches + alternating output buffers.
     jac_c5 = None
     if world == 1 and not args.no_c5:
         try:
-            win5 = synth.make_window("C5")
             solver.upload(win5)
-            ms5 = solver.time_kernel(0, 20)
+            ms5, ms5c = solver.time_kernel(0, 20), solver.time_kernel(10, 10)
             nb = BYTES_PER_OBS * win5.n_obs
-            jac_c5 = {"workload": "C5: 200 KF x 100000 landmarks x 800000 obs", "ms_per_launch": ms5, "algorithmic_bytes": int(nb),
-                      "achieved_gbs": nb / (ms5 * 1e-3) / 1e9, "peak_gbs": peak, "frac_of_hbm_peak": nb / (ms5 * 1e-3) / 1e9 / peak,
-                      "dram_traffic_bytes": 97.3e6, "traffic_source": "profiles/r01_ncu_traffic_c5.txt (30.5 MB read + 66.8 MB written; "
-                      "part of the 128 MB of Jacobian planes is still in the 126 MB L2 when the kernel ends)",
-                      "peak_source": peak_src}
+            t5 = ncu_traffic(os.path.join(ROOT, "profiles", "r02_ncu_traffic_c5.csv"))
+            dram = t5.get("k_lin_visual")
+            jac_c5 = {"workload": "C5: 200 KF x 100000 landmarks x 800000 obs", "kernel": "k_lin_visual (materialises r / J planes)",
+                      "ms_per_launch": ms5, "ms_per_launch_cold_l2": ms5c, "algorithmic_bytes": int(nb),
+                      "achieved_gbs": nb / (ms5 * 1e-3) / 1e9, "achieved_gbs_cold_l2": nb / (ms5c * 1e-3) / 1e9, "peak_gbs": peak,
+                      "frac_algorithmic": nb / (ms5 * 1e-3) / 1e9 / peak, "frac_algorithmic_cold_l2": nb / (ms5c * 1e-3) / 1e9 / peak,
+                      "dram_traffic_bytes": dram, "frac_dram": (dram / (ms5 * 1e-3) / 1e9 / peak) if dram else None,
+                      "traffic_source": "profiles/r02_ncu_traffic_c5.csv (ncu, per launch)" if dram else None, "peak_source": peak_src}
+            fused5 = []
+            for which, kname, per_obs, per_lmk in ((1, "k_lin_schur", FUSED_OBS_BYTES, LMK_BYTES + AUX_BYTES), (3, "k_backsub_cost", 2 * FUSED_OBS_BYTES, 2 * LMK_BYTES + AUX_BYTES + 24)):
+                msf, msfc = solver.time_kernel(which, 10), solver.time_kernel(which + 10, 10)
+                nbf = per_obs * win5.n_obs + per_lmk * win5.n_lmks
+                fused5.append({"kernel": kname, "ms_per_launch": msf, "ms_per_launch_cold_l2": msfc, "algorithmic_bytes": int(nbf),
+                               "frac_algorithmic_cold_l2": nbf / (msfc * 1e-3) / 1e9 / peak, "dram_traffic_bytes": t5.get(kname)})
+            jac_c5["fused_kernels_c5"] = fused5
+            jac_c5["chol_band_c5_ms"] = solver.time_kernel(2, 10)
         except Exception as e:  # noqa: BLE001
             jac_c5 = {"error": str(e)}
 
     gt = win.meta
     new = synth.apply_delta(win, d_res)
     solution = {"max_abs_pose_error_vs_ground_truth": float(np.abs(new["T_f_w"] - gt["T_f_w_gt"]).max())}
-    if cpu is not None:
+    if getattr(cpu_baseline, "last_solution", None) is not None:
         try:  # parity of this very run: the CUDA solution (resident arm and C-ABI arm) against the CPU port's, same window
             d_cpu, st_cpu = cpu_baseline.last_solution
             solution.update({
                 "max_rel_state_deviation_vs_cpu_port": state_deviation(d_res, d_cpu),
                 "max_rel_state_deviation_vs_cpu_port_e2e": state_deviation(d_e2e, d_cpu),
                 "lm_iterations": {"b200": int(round(its_per_step)), "cpu_port": int(st_cpu["iterations"])},
-                "tolerance": 1e-6})
+                "tolerance": 1e-06})
         except Exception as e:  # noqa: BLE001
             solution["parity_error"] = str(e)
     line = {
@@ -354,7 +466,7 @@ def main():
                    "l2": "256 MiB write between timed steps (L2 flush)", "parallelism": f"landmark-sharded x{world}"},
         "device_ms_per_step": dev_ms / args.steps,
         "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "roofline": roofline, "kernels": kern, "jacobian_kernel_c5": jac_c5, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "kernels": kern, "jacobian_kernel_c5": jac_c5, "c5": c5, "cpu_baseline": cpu,
         "solution": solution,
     }
     print(json.dumps(line), flush=True)

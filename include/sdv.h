@@ -301,15 +301,18 @@ int sdv_shard_range(const int32_t *obs_lmk, int32_t n_obs, int32_t n_lmks, int32
 int sdv_comm_unique_id(void *out_128_bytes);
 int sdv_comm_init(sdv_handle *h, const void *nccl_unique_id, int32_t rank, int32_t world);
 
-/* Benchmark helper: time `repeats` launches of the visual residual+Jacobian kernel on the
-   resident window with CUDA events on the handle's stream; returns mean ms per launch. */
+/* Benchmark helper: time `repeats` launches of one kernel of the path on the resident window with CUDA
+   events on the handle's stream; returns mean ms per launch.  which: 0 materialising residual+Jacobian
+   kernel (k_lin_visual), 1 fused linearisation + landmark Schur (k_lin_schur), 2 reduced-system
+   factorisation + solves, 3 fused back-substitution + candidate cost; +10: cold L2 (256 MiB write between
+   launches, alternating output buffers). */
 int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_per_launch);
 
 /* Test / debugging aids: copy an internal device buffer to the host (what: 0 reduced system [S|g|diag|grad],
    1 Cholesky factor, 2 reduced step, 3 jacobi scale, 4 LM damping) and report the reduced dimensions. */
 int sdv_debug_read(sdv_handle *h, int32_t what, double *out, int64_t count);
 int sdv_debug_dims(sdv_handle *h, int32_t *n, int32_t *n_pad);
-int sdv_debug_micro(sdv_handle *h, double *out72); /* developer micro-benchmarks, 72 doubles */
+int sdv_debug_graph_builds(sdv_handle *h, int64_t *count); /* CUDA-graph captures of this handle so far */
 
 const char *sdv_strerror(int status);
 const char *sdv_last_error(const sdv_handle *h); /* detail of the last failure on this handle */

@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
     L.sdv_time_kernel.argtypes = [C.c_void_p, C.c_int32, C.c_int32, dp]
     L.sdv_debug_read.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int64]
     L.sdv_debug_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.sdv_debug_graph_builds.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -150,6 +151,11 @@ class Solver:
         n, npad = C.c_int32(), C.c_int32()
         self._check(lib().sdv_debug_dims(self._h, C.byref(n), C.byref(npad)))
         return n.value, npad.value
+
+    def graph_builds(self) -> int:
+        n = C.c_int64()
+        self._check(lib().sdv_debug_graph_builds(self._h, C.byref(n)))
+        return int(n.value)
 
     def debug_read(self, what: int, count: int) -> np.ndarray:
         out = np.zeros(count)

@@ -537,8 +537,9 @@ __device__ __noinline__ bool band_sysprep(int n, int n_pad, int ld, LMState *st,
 //     block 16 x 16 row-major.  dxp receives -x (S delta = -g).
 // The preparation of the reduced system (k_sysprep for the other variants: gradient-tolerance test, Jacobi column scales at
 // iteration 0, LM damping of the pose/velocity/bias columns, identity padding) is done here, on the way into shared memory.
-__global__ void __launch_bounds__(BCT, 1) k_chol_band(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt, const double *A,
+__global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt, const double *A,
                                                       double *Lb, double *scale_p, double *damp_p, double *graw_p, double *dxp, double *prof) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     extern __shared__ __align__(16) double bsm[];
     __shared__ uint64_t full[BAND_MAX_STAGES], bar_panel[2], bar_step[2], bar_rhs[2], bar_copy[2], bar_p[2][8], bar_c1[2][8], bar_c2[2][8], colbar[2][16], colbar2[2][4], bar_r3[2];

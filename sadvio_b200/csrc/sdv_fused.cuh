@@ -24,7 +24,7 @@
 
 namespace sdv {
 
-constexpr int FT = 128;         // threads per CTA = slots per tile (upper bound)
+constexpr int FT = 160;         // threads per CTA = slots per tile (upper bound)
 constexpr int FT_LMK = 64;      // landmarks per tile (upper bound)
 constexpr int FT_SD = 75;       // doubles per slot in shared memory: W 18 | Y 18 | D 39 (21 block, 6 rhs, 6 diag, 6 raw gradient)
 constexpr int FT_SMEM_SCHUR = (FT * FT_SD + 9 * FT + FT_LMK * 10) * (int)sizeof(double);
@@ -119,8 +119,9 @@ SDV_DEV void tri_ij(int k, int &i, int &j) { // k = i (i + 1) / 2 + j, j <= i < 
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(FT, 2) k_lin_schur(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt, double *Sb,
+__global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt, double *Sb,
                                                      double *scale_l, double *lmk_aux) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     const LinBuf &B = st->cur ? B1 : B0;
     extern __shared__ double fsm[];
@@ -322,13 +323,17 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(DevProblem P, LinBuf B0, Li
             if (rflag[la] == 2) continue; // kept landmark: went straight to S
             const int t0 = sp[la], m = sp[la + 1] - t0;
             const int ediag = 39 * m, etot = ediag + 18 * m * (m - 1);
+            // every landmark of a run has m slots: landmark q of the run starts m * FT_SD doubles after the previous one
+            const int nrun = lb - la, lstride = m * FT_SD;
+            const double *base0 = slotd + t0 * FT_SD;
             for (int e = tid; e < etot; e += FT) {
                 double s = 0.0;
                 double *dst = nullptr;
                 if (e < ediag) {
                     const int sa = e / 39, k = e - sa * 39, ca = scol[t0 + sa];
                     if (ca < 0) continue;
-                    for (int q = la; q < lb; q++) s += slotd[(sp[q] + sa) * FT_SD + 36 + k];
+                    const double *src = base0 + sa * FT_SD + 36 + k;
+                    for (int q = 0; q < nrun; q++, src += lstride) s += *src;
                     if (k < 21) {
                         int i, j;
                         tri_ij(k, i, j);
@@ -346,10 +351,14 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(DevProblem P, LinBuf B0, Li
                     const int sb = pi - base;
                     const int ca = scol[t0 + sa], cb = scol[t0 + sb];
                     if (ca < 0 || cb < 0) continue;
-                    for (int q = la; q < lb; q++) {
-                        const double *Ya = slotd + (sp[q] + sa) * FT_SD + 18 + i * 3, *Wb = slotd + (sp[q] + sb) * FT_SD + j * 3;
-                        s -= Ya[0] * Wb[0] + Ya[1] * Wb[1] + Ya[2] * Wb[2];
+                    const double *Ya = base0 + sa * FT_SD + 18 + i * 3, *Wb = base0 + sb * FT_SD + j * 3;
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int q = 0; q < nrun; q++, Ya += lstride, Wb += lstride) {
+                        s = fma(Ya[0], Wb[0], s);
+                        s1 = fma(Ya[1], Wb[1], s1);
+                        s2 = fma(Ya[2], Wb[2], s2);
                     }
+                    s = -(s + s1 + s2);
                     dst = ca > cb ? &Sb[(size_t)(ca + i) * ld + cb + j] : &Sb[(size_t)(cb + j) * ld + ca + i];
                 }
                 atomicAdd(dst, s);
@@ -369,8 +378,9 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(DevProblem P, LinBuf B0, Li
 // landmark back-substitution delta_l = -V^-1 (g_l + sum_f W_f^T delta_f) with W_f^T delta_f = sum_obs Jl^T (Jp delta_f) recomputed,
 // candidate landmark parameters, model-decrease / norm partial sums, and the cost of the visual factors at the candidate point
 template <int KIND>
-__global__ void __launch_bounds__(FT, 3) k_backsub_cost(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, const double *dxp,
+__global__ void __launch_bounds__(FT, 3) k_backsub_cost(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, const double *dxp,
                                                         const double *lmk_aux) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0 || !st->step_valid) return;
     const int cand = 1 - st->cur;
     const LinBuf &Bx = st->cur ? B1 : B0;
@@ -495,7 +505,8 @@ __global__ void __launch_bounds__(FT, 3) k_backsub_cost(DevProblem P, LinBuf B0,
 
 // cost of the visual factors at the point of one linearisation buffer (iteration 0): residual-only sweep, one thread per
 // observation, nothing written but Accum::cost
-template <int KIND> __global__ void __launch_bounds__(256) k_visual_cost(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, int which) {
+template <int KIND> __global__ void __launch_bounds__(256) k_visual_cost(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, int which) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     const int b = which >= 0 ? which : (which == -1 ? st->cur : 1 - st->cur);
     const LinBuf &B = b ? B1 : B0;

@@ -1,6 +1,6 @@
 // sm_100a kernels of the sliding-window BA/VIO solve.  One LM iteration =
-//   k_schur  -> (NCCL all-reduce of [S|g|diag|grad]) -> k_sysprep -> k_chol_panel x nT -> k_trisolve
-//   -> k_backsub -> k_lin (candidate) -> k_ctrl
+//   k_lin_schur (sdv_fused.cuh) + k_assemble_factors -> (NCCL all-reduce of the reduced system) -> k_chol_band (or k_sysprep +
+//   k_chol_chain / k_chol_panel x nT + k_trisolve) -> k_backsub_cost + k_lin_factors (candidate) -> k_ctrl
 // Every kernel reads LMState::status first and returns when the solve has terminated, so the fixed launch sequence
 // can be replayed (and graph-captured) without host round trips.
 #pragma once
@@ -70,7 +70,8 @@ SDV_DEV void compute_fct_row(const DevProblem &P, const double *xp, int f, int c
     row[33] = 0.0;
 }
 
-__global__ void k_prep_table(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, int which /* -1: cur, -2: 1-cur, else fixed */) {
+__global__ void k_prep_table(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, int which /* -1: cur, -2: 1-cur, else fixed */) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     int b = which >= 0 ? which : (which == -1 ? st->cur : 1 - st->cur);
     LinBuf &B = b ? B1 : B0;
@@ -195,8 +196,9 @@ constexpr int LIN_THREADS = 256;
 // r / J_pose / J_lmk as SoA planes, and add 1/2 sum r^2 to Accum::cost[buf].  Persistent grid: each CTA stages the
 // frame-camera table into shared memory once with a TMA bulk copy and then walks observation tiles.
 template <int KIND, bool SMEM, bool EARLY>
-__global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc,
+__global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc,
                                                             int which) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     if (which == -2 && !st->step_valid) return; // no candidate to evaluate after an invalid step
     int b = which >= 0 ? which : (which == -1 ? st->cur : 1 - st->cur);
@@ -299,7 +301,8 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lin_visual(DevProblem P, LinBuf
 // One warp per IMU pair (4 pairs per CTA); lane j owns column j of the 9 x 18 tableau [cov | I], so every row operation of
 // the elimination is one step for the warp.  Each element sees exactly the operations, in the order, of the sequential
 // algorithm (the result is bit-identical to it); one thread per pair took 44 us per upload.
-__global__ void __launch_bounds__(128) k_imu_inf_sqrt(DevProblem P) {
+__global__ void __launch_bounds__(128) k_imu_inf_sqrt(const DevProblem *__restrict__ Pg) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     __shared__ double ms[4][9][19], Ls[4][9][9];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int p = blockIdx.x * 4 + wib;
@@ -399,8 +402,9 @@ constexpr int FAC_WARPS = 4;
 
 // One warp per IMU pair; then one thread per pose prior; then the dense prior residual.  All lanes redundantly form
 // the 3x3 building blocks, assemble the unwhitened 9x25 [J | r] in shared memory, and lane c whitens column c.
-__global__ void __launch_bounds__(FAC_WARPS * 32) k_lin_factors(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc,
+__global__ void __launch_bounds__(FAC_WARPS * 32) k_lin_factors(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc,
                                                                 int which) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     if (which == -2 && !st->step_valid) return;
     if (P.rank != 0) return; // non-visual factors live on rank 0 only
@@ -739,7 +743,8 @@ __global__ void __launch_bounds__(FAC_WARPS * 32) k_lin_factors(DevProblem P, Li
 // PoseToLandmarkFactor (residuals.hpp:561-599): 3 residuals on (kept frame pose, landmark). The landmark stays in the
 // eliminated set, so each factor is written as TWO pseudo-observations (rows 0-1 and row 2 + a zero row) into the r / J
 // planes of the owning rank and flows through the same per-landmark Schur machinery as the visual factors.
-__global__ void k_lin_p2l(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, int which) {
+__global__ void k_lin_p2l(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, int which) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     if (which == -2 && !st->step_valid) return;
     int b = which >= 0 ? which : (which == -1 ? st->cur : 1 - st->cur);
@@ -813,390 +818,19 @@ struct SlotAcc {
     double gp[6]; // Jp^T r
 };
 
-// accumulates this slot's observations; hl (xx,xy,xz,yy,yz,zz) and gl receive the landmark-block parts
-SDV_DEV void slot_accumulate_range(const DevProblem &P, const LinBuf &B, int qa, int qb, int ol0, int ol1, SlotAcc &a, double *hl, double *gl);
-SDV_DEV void slot_accumulate(const DevProblem &P, const LinBuf &B, int slot, SlotAcc &a, double *hl, double *gl) {
-    const int qa = P.slot_obs_ptr[slot], qb = P.slot_obs_ptr[slot + 1];
-    slot_accumulate_range(P, B, qa, qb, qa < qb ? P.slot_obs[qa] : 0, qa + 1 < qb ? P.slot_obs[qa + 1] : 0, a, hl, gl);
-}
-// observations qa .. qb-1 of the slot; the plane indices of the first two come in registers (k_schur prefetches them one
-// landmark ahead: slot_obs_ptr -> slot_obs -> planes is three dependent L2 round trips otherwise)
-SDV_DEV void slot_accumulate_range(const DevProblem &P, const LinBuf &B, int qa, int qb, int ol0, int ol1, SlotAcc &a, double *hl, double *gl) {
-    const int Oloc = P.Ocap;
-#pragma unroll
-    for (int k = 0; k < 18; k++) a.W[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 21; k++) a.H[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) a.gp[k] = 0.0;
-    for (int q = qa; q < qb; q++) {
-        const int ol = q == qa ? ol0 : (q == qa + 1 ? ol1 : P.slot_obs[q]);
-        double Jp[12], Jl[6], r0 = B.r[ol], r1 = B.r[(size_t)Oloc + ol];
-#pragma unroll
-        for (int k = 0; k < 12; k++) Jp[k] = B.Jp[(size_t)k * Oloc + ol];
-#pragma unroll
-        for (int k = 0; k < 6; k++) Jl[k] = B.Jl[(size_t)k * Oloc + ol];
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) a.W[i * 3 + j] += Jp[i] * Jl[j] + Jp[6 + i] * Jl[3 + j];
-#pragma unroll
-            for (int j = 0; j <= i; j++) a.H[tri_idx(i, j)] += Jp[i] * Jp[j] + Jp[6 + i] * Jp[6 + j];
-            a.gp[i] += Jp[i] * r0 + Jp[6 + i] * r1;
-        }
-        hl[0] += Jl[0] * Jl[0] + Jl[3] * Jl[3];
-        hl[1] += Jl[0] * Jl[1] + Jl[3] * Jl[4];
-        hl[2] += Jl[0] * Jl[2] + Jl[3] * Jl[5];
-        hl[3] += Jl[1] * Jl[1] + Jl[4] * Jl[4];
-        hl[4] += Jl[1] * Jl[2] + Jl[4] * Jl[5];
-        hl[5] += Jl[2] * Jl[2] + Jl[5] * Jl[5];
-        gl[0] += Jl[0] * r0 + Jl[3] * r1;
-        gl[1] += Jl[1] * r0 + Jl[4] * r1;
-        gl[2] += Jl[2] * r0 + Jl[5] * r1;
-    }
-}
-
-// light variant for back-substitution: hl, gl and e = sum Jl^T (Jp delta_f)
-SDV_DEV void slot_accumulate_back(const DevProblem &P, const LinBuf &B, int slot, const double *dxp, double *hl, double *gl,
-                                  double *e) {
-    const int Oloc = P.Ocap;
-    int pc = P.pose_col[P.slot_frame[slot]];
-    double d[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) d[k] = pc >= 0 ? dxp[pc + k] : 0.0;
-    for (int q = P.slot_obs_ptr[slot]; q < P.slot_obs_ptr[slot + 1]; q++) {
-        int ol = P.slot_obs[q];
-        double Jl[6], r0 = B.r[ol], r1 = B.r[(size_t)Oloc + ol];
-        double u0 = 0, u1 = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            u0 += B.Jp[(size_t)k * Oloc + ol] * d[k];
-            u1 += B.Jp[(size_t)(6 + k) * Oloc + ol] * d[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 6; k++) Jl[k] = B.Jl[(size_t)k * Oloc + ol];
-        hl[0] += Jl[0] * Jl[0] + Jl[3] * Jl[3];
-        hl[1] += Jl[0] * Jl[1] + Jl[3] * Jl[4];
-        hl[2] += Jl[0] * Jl[2] + Jl[3] * Jl[5];
-        hl[3] += Jl[1] * Jl[1] + Jl[4] * Jl[4];
-        hl[4] += Jl[1] * Jl[2] + Jl[4] * Jl[5];
-        hl[5] += Jl[2] * Jl[2] + Jl[5] * Jl[5];
-        gl[0] += Jl[0] * r0 + Jl[3] * r1;
-        gl[1] += Jl[1] * r0 + Jl[4] * r1;
-        gl[2] += Jl[2] * r0 + Jl[5] * r1;
-        e[0] += Jl[0] * u0 + Jl[3] * u1;
-        e[1] += Jl[1] * u0 + Jl[4] * u1;
-        e[2] += Jl[2] * u0 + Jl[5] * u1;
-    }
-}
-
 // LM damping of one column in UNSCALED variables: clamp(s^2 c, lo, hi) / (radius s^2)
 SDV_DEV double lm_damping(double c, double s, double radius, const SolverOpts &o) {
     double d = fmin(fmax(s * s * c, o.min_diag), o.max_diag);
     return d / (radius * s * s);
 }
 
-constexpr int SCH_WARPS = 4;
-constexpr int SCH_NIT = 5;  // off-diagonal work items a lane may accumulate in registers (k_schur chunks)
 constexpr int MAX_SLOTS = 32; // distinct keyframes one landmark may be seen from (checked at upload)
-
-// sum over the G lanes of a landmark group (G = 8, 16 or 32 consecutive lanes)
-template <int G> SDV_DEV double group_sum(double v) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // Layout of the reduced-system buffer Sb: rows [0, n_pad) = S (lower triangle used), row n_pad = g (right-hand side),
 // row n_pad+1 = diag(J^T J) of the reduced columns (before damping), row n_pad+2 = raw gradient of the reduced columns.
-// G lanes per landmark (32/G landmarks per warp): lane s of a group owns slot s (= one keyframe seeing the landmark).
-template <int G>
-__global__ void __launch_bounds__(SCH_WARPS * 32) k_schur(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt,
-                                                          double *Sb, double *scale_l, double *prof = nullptr) {
-    if (st->status != 0) return;
-    const LinBuf &B = st->cur ? B1 : B0;
-#ifdef SDV_SCHUR_PROF
-    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc, tn;
-    auto rdclk = [] { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; };
-    tc = rdclk();
-#define SCH_TICK(q) do { tn = rdclk(); tp[q] += tn - tc; tc = tn; } while (0)
-#else
-#define SCH_TICK(q) do { } while (0)
-#endif
-    constexpr int GPW = 32 / G;             // landmark groups per warp
-    constexpr int GPB = SCH_WARPS * GPW;    // per block
-    __shared__ double WY[GPB][G][36];
-    __shared__ int scol[GPB][G];
-    extern __shared__ double sch_acc[]; // [39][SCH_WARPS * 32]
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int lig = lane % G, gib = wib * GPW + lane / G; // lane in group, group in block
-    const int ld = P.ld;
-    double *g = Sb + (size_t)P.n_pad * ld;
-    double *cdiag = g + ld;
-    double *graw = cdiag + ld;
-    const double radius = st->radius;
-    const bool first = st->scaling_done == 0;
-    double gmax = 0.0;
-    const int nl = P.l1 - P.l0;
-    // The reduced system receives ~370 FP64 atomics per landmark (4 keyframes), all landing on the few hundred 6x6 blocks of
-    // the co-visible keyframe pairs: at C3 that was 3.7 M L2 atomics per iteration and the whole cost of this kernel.  The
-    // host therefore groups consecutive landmarks seen from the SAME keyframes into chunks (P.chunk_ptr); a lane group walks
-    // its chunk, keeps the contributions in registers and issues the atomics once per chunk.  Landmarks seen from too many
-    // keyframes for the register budget (chunk_acc == false) take the direct path, one landmark per chunk.
-    (void)nl;
-    constexpr int NIT = SCH_NIT;
-    for (int cb = blockIdx.x * GPB; cb < P.nchunks; cb += gridDim.x * GPB) { // block-uniform trip count
-        const int ch = cb + gib;
-        const bool cvalid = ch < P.nchunks;
-        const int lA = cvalid ? P.chunk_ptr[ch] : 0, lB = cvalid ? P.chunk_ptr[ch + 1] : 0;
-        int maxlen = lB - lA;
-#pragma unroll
-        for (int o = 16; o >= G; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o)); // same trip count for the warp
-        const int s00 = cvalid ? P.slot_ptr[lA] : 0, m = cvalid ? P.slot_ptr[lA + 1] - s00 : 0; // same m for the whole chunk
-        const int nitems = m * (m - 1) / 2 * 6;
-        const bool use_acc = nitems <= NIT * G && lB - lA > 1; // else: direct atomics (a chunk of one landmark gains nothing from accumulating)
-        const int col = lig < m ? P.pose_col[P.slot_frame[s00 + lig]] : -1;
-        if (lig < m) scol[gib][lig] = col;
-        // my off-diagonal work items (pair, row i): the 6 entries of row i of -Y_a W_b^T; pairs (1,0),(2,0),(2,1),(3,0)...
-        int it_sa[NIT], it_sb[NIT], it_i[NIT];
-        double accO[NIT][6];
-        // own diagonal block (21) + right-hand side, diag(J^T J), raw gradient (3 x 6): 39 accumulators per lane in shared memory
-        // (k-major, conflict-free) — in registers they pushed the kernel over 255 registers
-        double *accD = sch_acc + threadIdx.x;
-        constexpr int AS = SCH_WARPS * 32;
-#pragma unroll
-        for (int q = 0; q < NIT; q++) {
-            const int e = lig + q * G;
-            int sa = 1, base = 0, pi = e / 6;
-            while (base + sa <= pi) {
-                base += sa;
-                sa++;
-            }
-            it_sa[q] = e < nitems ? sa : -1;
-            it_sb[q] = pi - base;
-            it_i[q] = e - pi * 6;
-#pragma unroll
-            for (int j = 0; j < 6; j++) accO[q][j] = 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 39; k++) accD[k * AS] = 0.0;
-        __syncwarp();
-        // every landmark of the chunk has m slots, so landmark lA + li owns slots s00 + li m ..; a chunk of several landmarks holds
-        // eliminated landmarks only.  The observation range and the first two plane indices of the NEXT landmark are loaded
-        // while this one is processed.
-        const int dc_chunk = (cvalid && lB - lA == 1) ? P.lmk_col[lA] : -1;
-        int qa = 0, qb = 0, ol0 = 0, ol1 = 0;
-        if (cvalid && lig < m) {
-            qa = P.slot_obs_ptr[s00 + lig];
-            qb = P.slot_obs_ptr[s00 + lig + 1];
-            ol0 = qa < qb ? P.slot_obs[qa] : 0;
-            ol1 = qa + 1 < qb ? P.slot_obs[qa + 1] : 0;
-        }
-        for (int li = 0; li < maxlen; li++) {
-            const int l = lA + li;
-            const bool valid = l < lB;
-            int nqa = 0, nqb = 0;
-            const bool pre = l + 1 < lB && lig < m;
-            if (pre) {
-                nqa = P.slot_obs_ptr[s00 + (li + 1) * m + lig];
-                nqb = P.slot_obs_ptr[s00 + (li + 1) * m + lig + 1];
-            }
-            double sl0 = 1.0, sl1 = 1.0, sl2 = 1.0;
-            if (valid && !first) {
-                sl0 = scale_l[3 * (size_t)l];
-                sl1 = scale_l[3 * (size_t)l + 1];
-                sl2 = scale_l[3 * (size_t)l + 2];
-            }
-            SlotAcc a;
-            double hl[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
-            SCH_TICK(0);
-            if (valid && lig < m) slot_accumulate_range(P, B, qa, qb, ol0, ol1, a, hl, gl);
-            SCH_TICK(1);
-            if (pre) {
-                ol0 = nqa < nqb ? P.slot_obs[nqa] : 0;
-                ol1 = nqa + 1 < nqb ? P.slot_obs[nqa + 1] : 0;
-            }
-            qa = nqa;
-            qb = nqb;
-#pragma unroll
-            for (int k = 0; k < 6; k++) hl[k] = group_sum<G>(hl[k]);
-#pragma unroll
-            for (int k = 0; k < 3; k++) gl[k] = group_sum<G>(gl[k]);
-            SCH_TICK(2);
-            const int dc = valid ? dc_chunk : -1;
-            bool eliminate = valid && dc < 0;
-            if (valid && dc >= 0) {
-                // kept (dense) landmark: its columns live in the reduced system, no elimination
-                if (lig < m && col >= 0) {
-#pragma unroll
-                    for (int i = 0; i < 6; i++) {
-#pragma unroll
-                        for (int j = 0; j <= i; j++) atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], a.H[tri_idx(i, j)]);
-                        atomicAdd(&g[col + i], a.gp[i]);
-                        atomicAdd(&cdiag[col + i], a.H[tri_idx(i, i)]);
-                        atomicAdd(&graw[col + i], a.gp[i]);
-#pragma unroll
-                        for (int j = 0; j < 3; j++) { // dense landmark columns come after every frame column
-                            if (dc > col) atomicAdd(&Sb[(size_t)(dc + j) * ld + col + i], a.W[i * 3 + j]);
-                            else atomicAdd(&Sb[(size_t)(col + i) * ld + dc + j], a.W[i * 3 + j]);
-                        }
-                    }
-                }
-                if (lig == 0) {
-                    const int ii[6] = {0, 1, 2, 1, 2, 2}, jj[6] = {0, 0, 0, 1, 1, 2};
-                    const double hv[6] = {hl[0], hl[1], hl[2], hl[3], hl[4], hl[5]};
-                    for (int k = 0; k < 6; k++) atomicAdd(&Sb[(size_t)(dc + ii[k]) * ld + dc + jj[k]], hv[k]);
-                    atomicAdd(&cdiag[dc + 0], hl[0]);
-                    atomicAdd(&cdiag[dc + 1], hl[3]);
-                    atomicAdd(&cdiag[dc + 2], hl[5]);
-                    for (int k = 0; k < 3; k++) {
-                        atomicAdd(&g[dc + k], gl[k]);
-                        atomicAdd(&graw[dc + k], gl[k]);
-                    }
-                }
-            }
-            // ---- eliminated landmark
-            double Vi[6] = {0, 0, 0, 0, 0, 0};
-            if (eliminate) {
-                double s3[3];
-                if (first) {
-                    s3[0] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[0])) : 1.0;
-                    s3[1] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[3])) : 1.0;
-                    s3[2] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(hl[5])) : 1.0;
-                    if (lig == 0) {
-                        scale_l[3 * (size_t)l] = s3[0];
-                        scale_l[3 * (size_t)l + 1] = s3[1];
-                        scale_l[3 * (size_t)l + 2] = s3[2];
-                    }
-                } else {
-                    s3[0] = sl0;
-                    s3[1] = sl1;
-                    s3[2] = sl2;
-                }
-                gmax = fmax(gmax, fmax(fabs(gl[0]), fmax(fabs(gl[1]), fabs(gl[2]))));
-                double V[6] = {hl[0] + lm_damping(hl[0], s3[0], radius, opt), hl[1], hl[2], hl[3] + lm_damping(hl[3], s3[1], radius, opt), hl[4],
-                               hl[5] + lm_damping(hl[5], s3[2], radius, opt)};
-                if (!sym3_inverse(V, Vi)) {
-                    if (lig == 0) acc->schur_fail = 1;
-                    eliminate = false;
-                }
-            }
-            SCH_TICK(3);
-            if (eliminate && lig < m) {
-                // Y = W V^-1
-                double Y[18];
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    double w0 = a.W[i * 3], w1 = a.W[i * 3 + 1], w2 = a.W[i * 3 + 2];
-                    Y[i * 3] = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
-                    Y[i * 3 + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
-                    Y[i * 3 + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
-                }
-#pragma unroll
-                for (int k = 0; k < 18; k++) {
-                    WY[gib][lig][k] = a.W[k];
-                    WY[gib][lig][18 + k] = Y[k];
-                }
-                if (col >= 0) {
-                    // own diagonal block (lower triangle), right-hand side, diag(J^T J), raw gradient
-#pragma unroll
-                    for (int i = 0; i < 6; i++) {
-#pragma unroll
-                        for (int j = 0; j <= i; j++) {
-                            double sv = a.H[tri_idx(i, j)] - (Y[i * 3] * a.W[j * 3] + Y[i * 3 + 1] * a.W[j * 3 + 1] + Y[i * 3 + 2] * a.W[j * 3 + 2]);
-                            if (use_acc) accD[tri_idx(i, j) * AS] += sv;
-                            else atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], sv);
-                        }
-                        const double gv = a.gp[i] - (Y[i * 3] * gl[0] + Y[i * 3 + 1] * gl[1] + Y[i * 3 + 2] * gl[2]);
-                        if (use_acc) {
-                            accD[(21 + i) * AS] += gv;
-                            accD[(27 + i) * AS] += a.H[tri_idx(i, i)];
-                            accD[(33 + i) * AS] += a.gp[i];
-                        } else {
-                            atomicAdd(&g[col + i], gv);
-                            atomicAdd(&cdiag[col + i], a.H[tri_idx(i, i)]);
-                            atomicAdd(&graw[col + i], a.gp[i]);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            SCH_TICK(4);
-            // off-diagonal pairs (a > b in slot order)
-            if (eliminate) {
-                if (use_acc) {
-#pragma unroll
-                    for (int q = 0; q < NIT; q++) {
-                        if (it_sa[q] < 0) continue;
-                        const double *Ya = &WY[gib][it_sa[q]][18 + it_i[q] * 3];
-                        const double y0 = Ya[0], y1 = Ya[1], y2 = Ya[2];
-                        const double *Wb = &WY[gib][it_sb[q]][0];
-#pragma unroll
-                        for (int j = 0; j < 6; j++) accO[q][j] -= y0 * Wb[j * 3] + y1 * Wb[j * 3 + 1] + y2 * Wb[j * 3 + 2];
-                    }
-                } else {
-                    for (int e = lig; e < nitems; e += G) {
-                        const int pi = e / 6, i = e - pi * 6;
-                        int sa = 1, base = 0;
-                        while (base + sa <= pi) {
-                            base += sa;
-                            sa++;
-                        }
-                        const int sb = pi - base;
-                        const int ca = scol[gib][sa], cbb = scol[gib][sb];
-                        if (ca < 0 || cbb < 0) continue;
-                        const double *Ya = &WY[gib][sa][18 + i * 3];
-                        const double y0 = Ya[0], y1 = Ya[1], y2 = Ya[2];
-                        const double *Wb = &WY[gib][sb][0];
-#pragma unroll
-                        for (int j = 0; j < 6; j++) {
-                            double v = -(y0 * Wb[j * 3] + y1 * Wb[j * 3 + 1] + y2 * Wb[j * 3 + 2]);
-                            if (ca > cbb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cbb + j], v);
-                            else atomicAdd(&Sb[(size_t)(cbb + j) * ld + ca + i], v);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            SCH_TICK(5);
-        }
-        // ---- one set of atomics per chunk
-        if (use_acc && cvalid) {
-            if (lig < m && col >= 0) {
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-#pragma unroll
-                    for (int j = 0; j <= i; j++) atomicAdd(&Sb[(size_t)(col + i) * ld + col + j], accD[tri_idx(i, j) * AS]);
-                    atomicAdd(&g[col + i], accD[(21 + i) * AS]);
-                    atomicAdd(&cdiag[col + i], accD[(27 + i) * AS]);
-                    atomicAdd(&graw[col + i], accD[(33 + i) * AS]);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NIT; q++) {
-                if (it_sa[q] < 0) continue;
-                const int ca = scol[gib][it_sa[q]], cbb = scol[gib][it_sb[q]], i = it_i[q];
-                if (ca < 0 || cbb < 0) continue;
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    if (ca > cbb) atomicAdd(&Sb[(size_t)(ca + i) * ld + cbb + j], accO[q][j]);
-                    else atomicAdd(&Sb[(size_t)(cbb + j) * ld + ca + i], accO[q][j]);
-                }
-            }
-        }
-        __syncwarp();
-        SCH_TICK(6);
-    }
-#ifdef SDV_SCHUR_PROF
-    if (prof && blockIdx.x == 0 && threadIdx.x == 0)
-        for (int q = 0; q < 8; q++) prof[64 + q] = (double)tp[q];
-#endif
-    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    if (lane == 0 && gmax > 0.0) atomic_max_nonneg(reinterpret_cast<double *>(&acc->grad_max_bits), gmax);
-}
-
 // J^T J / J^T r of the non-visual factors into the reduced system (rank 0 only). One warp per IMU pair.
-__global__ void __launch_bounds__(FAC_WARPS * 32) k_assemble_factors(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, double *Sb) {
+__global__ void __launch_bounds__(FAC_WARPS * 32) k_assemble_factors(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, double *Sb) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0 || P.rank != 0) return;
     const LinBuf &B = st->cur ? B1 : B0;
     __shared__ double Js[FAC_WARPS][9 * 25];
@@ -1308,7 +942,8 @@ __global__ void __launch_bounds__(FAC_WARPS * 32) k_assemble_factors(DevProblem 
 }
 
 // (k_assemble_factors continues in k_assemble_sparse for the sparsified prior)
-__global__ void k_assemble_sparse(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, double *Sb) {
+__global__ void k_assemble_sparse(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, double *Sb) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0 || P.rank != 0) return;
     const LinBuf &B = st->cur ? B1 : B0;
     const int ld = P.ld;
@@ -1380,7 +1015,8 @@ __global__ void k_assemble_sparse(DevProblem P, LinBuf B0, LinBuf B1, const LMSt
 }
 
 // H_m = J_m^T J_m and g0 = J_m^T r0 restricted to the mapped columns; once per upload.
-__global__ void k_prior_setup(DevProblem P) {
+__global__ void k_prior_setup(const DevProblem *__restrict__ Pg) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     const int nm = P.mp_nmap;
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (int e = tid; e < nm * nm + nm; e += nt) {
@@ -1402,8 +1038,9 @@ __global__ void k_prior_setup(DevProblem P) {
 // =====================================================================================================================
 // reduced system preparation: jacobi scaling (iteration 0), gradient test, LM damping, padding
 // =====================================================================================================================
-__global__ void __launch_bounds__(1024) k_sysprep(DevProblem P, LMState *st, Accum *acc, SolverOpts opt, double *Sb, double *scale_p,
+__global__ void __launch_bounds__(1024) k_sysprep(const DevProblem *__restrict__ Pg, LMState *st, Accum *acc, SolverOpts opt, double *Sb, double *scale_p,
                                                   double *damp_p, double *graw_p) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     __shared__ double red[32];
     __shared__ int s_stop;
@@ -1590,8 +1227,9 @@ __global__ void __launch_bounds__(CH_THREADS) k_chol_panel(double *A, double *Lo
 // columns; frame-camera table of the candidate.  Single CTA.
 // =====================================================================================================================
 constexpr int TS_THREADS = 1024;
-__global__ void __launch_bounds__(TS_THREADS) k_trisolve(DevProblem P, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, const double *Lo,
+__global__ void __launch_bounds__(TS_THREADS) k_trisolve(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, const double *Lo,
                                                          const double *damp_p, const double *graw_p, double *dxp) {
+    const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0) return;
     extern __shared__ double sh[];
     double *z = sh;                 // [n_pad]
@@ -1668,81 +1306,6 @@ __global__ void __launch_bounds__(TS_THREADS) k_trisolve(DevProblem P, LinBuf B0
     // frame-camera table of the candidate point
     for (int i = threadIdx.x; i < P.F * P.C; i += blockDim.x) compute_fct_row(P, Bc.xp, i / P.C, i % P.C, Bc.fct + (size_t)i * FCT_ROW);
     if (threadIdx.x == 0) st->step_valid = 1;
-}
-
-// =====================================================================================================================
-// landmark back-substitution: delta_l = -V^-1 (g_l + sum_f W_f^T delta_f); candidate landmark parameters
-// =====================================================================================================================
-template <int G>
-__global__ void __launch_bounds__(SCH_WARPS * 32) k_backsub(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc,
-                                                            SolverOpts opt, const double *dxp, const double *scale_l) {
-    if (st->status != 0 || !st->step_valid) return;
-    const LinBuf &Bx = st->cur ? B1 : B0;
-    const LinBuf &Bc = st->cur ? B0 : B1;
-    constexpr int GPW = 32 / G, GPB = SCH_WARPS * GPW;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int lig = lane % G, gib = wib * GPW + lane / G;
-    const double radius = st->radius;
-    double gd = 0, dd = 0, sn = 0, cn = 0;
-    const int nl = P.l1 - P.l0;
-    for (int lb = blockIdx.x * GPB; lb < nl; lb += gridDim.x * GPB) {
-        const int l = P.l0 + lb + gib;
-        const bool valid = (lb + gib) < nl && P.lmk_col[min(l, P.L - 1)] < 0; // kept landmarks are part of the reduced system
-        const int s0 = valid ? P.slot_ptr[l] : 0, m = valid ? P.slot_ptr[l + 1] - s0 : 0;
-        double hl[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0}, e[3] = {0, 0, 0};
-        if (lig < m) slot_accumulate_back(P, Bx, s0 + lig, dxp, hl, gl, e);
-#pragma unroll
-        for (int k = 0; k < 6; k++) hl[k] = group_sum<G>(hl[k]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            gl[k] = group_sum<G>(gl[k]);
-            e[k] = group_sum<G>(e[k]);
-        }
-        if (lig == 0 && (lb + gib) < nl && !valid) {
-            // kept landmark: mirror its reduced-system entries so the visual kernel reads every landmark from xl
-            const int dc = P.lmk_col[l];
-#pragma unroll
-            for (int k = 0; k < 3; k++) Bc.xl[3 * (size_t)l + k] = Bc.xp[dc + k];
-        }
-        if (!valid || lig != 0) continue;
-        double s3[3] = {scale_l[3 * (size_t)l], scale_l[3 * (size_t)l + 1], scale_l[3 * (size_t)l + 2]};
-        double d3[3] = {lm_damping(hl[0], s3[0], radius, opt), lm_damping(hl[3], s3[1], radius, opt), lm_damping(hl[5], s3[2], radius, opt)};
-        double V[6] = {hl[0] + d3[0], hl[1], hl[2], hl[3] + d3[1], hl[4], hl[5] + d3[2]};
-        double Vi[6];
-        if (!sym3_inverse(V, Vi)) continue;
-        double t[3] = {gl[0] + e[0], gl[1] + e[1], gl[2] + e[2]};
-        double dl[3] = {-(Vi[0] * t[0] + Vi[1] * t[1] + Vi[2] * t[2]), -(Vi[1] * t[0] + Vi[3] * t[1] + Vi[4] * t[2]),
-                        -(Vi[2] * t[0] + Vi[4] * t[1] + Vi[5] * t[2])};
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            double xc = Bx.xl[3 * (size_t)l + k] + dl[k];
-            Bc.xl[3 * (size_t)l + k] = xc;
-            gd += gl[k] * dl[k];
-            dd += d3[k] * dl[k] * dl[k];
-            sn += dl[k] * dl[k];
-            cn += xc * xc;
-        }
-    }
-    __syncwarp();
-    gd = warp_sum(gd);
-    dd = warp_sum(dd);
-    sn = warp_sum(sn);
-    cn = warp_sum(cn);
-    // one set of atomics per CTA: the four scalars are single addresses, thousands of same-address atomics serialise in L2
-    __shared__ double red[SCH_WARPS][4];
-    if (lane == 0) {
-        red[wib][0] = gd;
-        red[wib][1] = dd;
-        red[wib][2] = sn;
-        red[wib][3] = cn;
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < SCH_WARPS; w++) v += red[w][threadIdx.x];
-        if (v != 0.0) atomicAdd(threadIdx.x == 0 ? &acc->model_gd : (threadIdx.x == 1 ? &acc->model_dd : (threadIdx.x == 2 ? &acc->step_norm2 : &acc->cand_norm2)), v);
-    }
 }
 
 // =====================================================================================================================
@@ -1900,10 +1463,33 @@ SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt) {
     }
 }
 
-// gather the solution blocks in ABI order
-__global__ void k_gather_solution(DevProblem P, LinBuf B0, LinBuf B1, const LMState *st, double *dpose, double *dv, double *dba, double *dbg,
-                                  double *dlmk) {
+// start of a solve: x = 0 in both linearisation buffers, solver state and accumulators cleared (one launch instead of six
+// memset nodes whose sizes would tie the CUDA graph to the window)
+__global__ void k_reset(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc) {
+    const DevProblem &P = *Pg;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < P.n_pad; i += nt) {
+        B0.xp[i] = 0.0;
+        B1.xp[i] = 0.0;
+    }
+    const int n3 = 3 * (P.L > 0 ? P.L : 1);
+    for (int i = tid; i < n3; i += nt) {
+        B0.xl[i] = 0.0;
+        B1.xl[i] = 0.0;
+    }
+    static_assert(sizeof(LMState) % 8 == 0 && sizeof(Accum) % 8 == 0, "cleared as 64-bit words");
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(st);
+    for (int i = tid; i < (int)(sizeof(LMState) / 8); i += nt) w[i] = 0ull;
+    w = reinterpret_cast<unsigned long long *>(acc);
+    for (int i = tid; i < (int)(sizeof(Accum) / 8); i += nt) w[i] = 0ull;
+}
+
+// gather the solution blocks in ABI order, followed by the solver state and the accumulators:
+// out = [dpose 6F | dv 3F | dba 3F | dbg 3F | dlmk 3 max(L,1) | LMState | Accum] — ONE device-to-host copy per solve
+__global__ void k_gather_solution(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, const Accum *acc, double *out) {
+    const DevProblem &P = *Pg;
     const LinBuf &B = st->cur ? B1 : B0;
+    double *dpose = out, *dv = out + 6 * P.F, *dba = dv + 3 * P.F, *dbg = dba + 3 * P.F, *dlmk = dbg + 3 * P.F;
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (int f = tid; f < P.F; f += nt) {
         int pc = P.pose_col[f], vc = P.vb_col[f];
@@ -1919,6 +1505,12 @@ __global__ void k_gather_solution(DevProblem P, LinBuf B0, LinBuf B1, const LMSt
         // kept landmarks are replicated on every rank (count them once); eliminated ones are owned by one rank
         for (int k = 0; k < 3; k++) dlmk[3 * (size_t)l + k] = dc >= 0 ? (P.rank == 0 ? B.xp[dc + k] : 0.0) : B.xl[3 * (size_t)l + k];
     }
+    unsigned long long *tail = reinterpret_cast<unsigned long long *>(dlmk + 3 * (size_t)(P.L > 0 ? P.L : 1));
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(st);
+    for (int i = tid; i < (int)(sizeof(LMState) / 8); i += nt) tail[i] = src[i];
+    tail += sizeof(LMState) / 8;
+    src = reinterpret_cast<const unsigned long long *>(acc);
+    for (int i = tid; i < (int)(sizeof(Accum) / 8); i += nt) tail[i] = src[i];
 }
 
 } // namespace sdv

@@ -81,8 +81,6 @@ struct DevProblem {
     const int *lmk_col;     // column in the reduced system for dense (kept) landmarks, -1 = eliminated
     const uint32_t *tile_nz; // [(n_pad/32 + 1)][4] bit j of row i: tile (i, j) of the Cholesky factor is structurally non-zero
     const int *slot_ptr;    // [L+1] first slot of each landmark
-    const int *chunk_ptr;   // [nchunks+1] landmark ranges of this rank whose landmarks are seen from the same keyframes (k_schur)
-    int nchunks;
     const int *tile_ptr;    // [ntiles+1] landmark ranges of this rank with <= FT slots and <= FT_LMK landmarks (k_lin_schur, k_backsub_cost)
     int ntiles;
     const int *slot_frame;  // [nslots]

@@ -374,12 +374,14 @@ def test_dense_small_window_band_kernel(solver):
     assert_same_solution(g, o)
 
 
-@pytest.mark.parametrize("name", ["C2", "C3"])
-def test_schur_chunks_match_per_landmark_assembly(name):
-    """k_schur accumulating chunks of landmarks in registers against one set of atomics per landmark."""
+@pytest.mark.parametrize("name", ["small", "C2", "C3"])
+def test_fused_schur_does_not_depend_on_the_tiling(name):
+    """k_lin_schur sums the landmarks of a tile in shared memory before its atomics reach S, and finds the runs of landmarks
+    seen from the same keyframes inside each tile: tiles of at most 8 slots (one or two landmarks, hardly any run) against the
+    default tiling."""
     win = synth.make_window(name)
-    rc_a, d_a, st_a = _solve_with_env(win, {"SDV_SCHUR_CH": "4"})
-    rc_b, d_b, st_b = _solve_with_env(win, {"SDV_SCHUR_NOCHUNK": "1"})
+    rc_a, d_a, st_a = _solve_with_env(win, {})
+    rc_b, d_b, st_b = _solve_with_env(win, {"SDV_FUSED_TILE_SLOTS": "8"})
     assert rc_a == rc_b == 0 and st_a["iterations"] == st_b["iterations"]
     for a, b in ((d_a.dpose, d_b.dpose), (d_a.dv, d_b.dv), (d_a.dlmk, d_b.dlmk)):
         assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max() + 1e-13
@@ -529,11 +531,30 @@ def test_chained_dense_priors_with_resurrected_landmarks(solver):
     assert n_prior_only > 0
 
 
-@pytest.mark.parametrize("name", ["small", "C2", "C3"])
-def test_fused_schur_matches_materialised_jacobian_path(name):
-    """The fused kernels (Jacobians formed in registers inside k_lin_schur / k_backsub_cost, per-run reduction in shared
-    memory) against the round-1 path that materialises r / J planes (SDV_LEGACY_SCHUR=1): same LM trace, same solution."""
-    win = synth.make_window(name)
-    a = _solve_with_env(win, {})
-    b = _solve_with_env(win, {"SDV_LEGACY_SCHUR": "1"})
-    assert_same_solution(a, b, tol=1e-8)
+def _trim_landmarks(win, n_drop):
+    """The same window with its last `n_drop` landmarks (and their observations) gone: what a back end sees from one keyframe
+    to the next — same keyframes, a few landmarks more or less."""
+    L = win.n_lmks - n_drop
+    keep = win.obs_lmk < L
+    for name in ("obs_lmk", "obs_frame", "obs_cam", "obs_bearing", "obs_uv"):
+        setattr(win, name, np.ascontiguousarray(getattr(win, name)[keep]))
+    win.lmk_t = np.ascontiguousarray(win.lmk_t[:L])
+    return win
+
+
+def test_one_cuda_graph_serves_consecutive_windows():
+    """The whole solve is one CUDA graph whose kernel arguments do not depend on the window (the problem description is read
+    from device memory, scratch is laid out from capacities, grids are persistent upper bounds): windows of different
+    landmark / observation counts replay the graph captured for the first one, and each still matches the oracle."""
+    s = api.Solver()
+    drops = [0, 37, 5, 120, 64, 0]
+    for n_drop in drops:
+        win = _trim_landmarks(synth.make_window("C2"), n_drop)
+        g = s.solve_window(win)
+        o = orc.solve_window(win, mode=0, nthreads=8)
+        assert_same_solution(g, o)
+    assert s.graph_builds() == 1, s.graph_builds()
+    # a different keyframe count is a different graph
+    s.solve_window(synth.make_window("small"))
+    assert s.graph_builds() == 2
+    s.close()

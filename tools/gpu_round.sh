@@ -15,7 +15,7 @@ quick)
     timeout 60 python tools/solve_once.py C3 3 2>&1 | tail -2 | tee $out/solve_once_c3.log
     ;;
 full)
-    timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $out/pytest_gpu.log
+    timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $out/pytest_gpu.log
     timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $out/smoke.log
     timeout 300 python bench.py --gpus 1 > $out/bench_c3_n1.json 2> $out/bench_c3_n1.err
     tail -c 600 $out/bench_c3_n1.json
@@ -39,6 +39,13 @@ variant)
     env "$@" timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "full_solve or band or golden or reference or gradient_tolerance or tight_convergence" 2>&1 | tail -8 | tee $out/variant_$sw.log
     env "$@" timeout 60 python tools/solve_once.py C3 5 2>&1 | tail -1 | tee -a $out/variant_$sw.log
     env "$@" timeout 60 python tools/chol_only.py 2>&1 | tail -3 | tee -a $out/variant_$sw.log
+    ;;
+traffic)
+    # DRAM bytes per launch of every kernel of one solve (bench.py reads profiles/r02_ncu_traffic_*.csv by kernel name)
+    SDV_NO_GRAPH=1 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
+        --log-file $out/ncu_traffic_c3.csv python tools/solve_once.py C3 > $out/ncu_traffic_c3.log 2>&1
+    SDV_NO_GRAPH=1 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
+        -k regex:"k_lin_visual|k_lin_schur|k_backsub_cost|k_chol_band" -c 12 --log-file $out/ncu_traffic_c5.csv python tools/lin_c5.py C5 3 > $out/ncu_traffic_c5.log 2>&1
     ;;
 prebuilt)
     # same checks as `variant` for experiment libraries built in the container (sadvio_b200/_lib/variants/lib_<switch>.so,

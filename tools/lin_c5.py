@@ -8,7 +8,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 w = synth.make_window(name)
 s = api.Solver()
 s.upload(w)
-for k, nm in ((0, "lin_visual"), (1, "schur")):
+for k, nm in ((0, "lin_visual"), (1, "lin_schur"), (3, "backsub_cost"), (2, "chol_band")):
     ms = s.time_kernel(k, reps)
     print(f"{name} {nm}: {ms*1e3:.1f} us", end="")
     if k == 0:
