@@ -13,6 +13,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -66,6 +69,65 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 
 } // namespace
 
+// A few persistent host threads per handle: the structure pass of an upload (validation, slot lists) runs on them in parallel
+// and one of them packs the bulk arena and issues its H2D copy, so the transfer overlaps the structure pass.
+struct HostPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    std::vector<std::function<void()>> jobs;
+    size_t next = 0;
+    int pending = 0;
+    bool stop = false;
+    bool start(int n) {
+        try {
+            for (int i = (int)th.size(); i < n; i++) th.emplace_back([this] { loop(); });
+        } catch (...) {
+            return !th.empty();
+        }
+        return true;
+    }
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return stop || next < jobs.size(); });
+                if (stop) return;
+                f = std::move(jobs[next++]);
+            }
+            f();
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void submit(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            jobs.push_back(std::move(f));
+            pending++;
+        }
+        cv.notify_one();
+    }
+    void wait_all() {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [this] { return pending == 0; });
+        jobs.clear();
+        next = 0;
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : th)
+            if (t.joinable()) t.join();
+    }
+};
+
 typedef void (*lin_visual_fn_t)(const sdv::DevProblem *, sdv::LinBuf, sdv::LinBuf, const sdv::LMState *, sdv::Accum *, int);
 static lin_visual_fn_t lin_visual_fn(int kind, bool smem, bool early) {
     using namespace sdv;
@@ -95,6 +157,9 @@ struct sdv_handle {
     // small pinned readback
     unsigned char *h_rb = nullptr;
     size_t rb_cap = 0;
+    HostPool pool;                        // see HostPool
+    cudaStream_t copy_stream = nullptr;   // H2D of the bulk arena, issued by a pool thread while the structure pass runs
+    cudaEvent_t ev_bulk = nullptr;
     unsigned char *d_flush = nullptr; // 256 MiB L2-flush buffer of sdv_time_kernel's cold variants (allocated on first use)
     unsigned char *d_out = nullptr; // solution blocks
     size_t out_cap = 0;
@@ -259,6 +324,8 @@ int sdv_create(sdv_handle **out, const sdv_config *cfg) {
     }
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
     cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_bulk, cudaEventDisableTiming);
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
@@ -277,6 +344,8 @@ int sdv_destroy(sdv_handle *h) {
     if (h->graph) cudaGraphDestroy(h->graph);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_bulk) cudaEventDestroy(h->ev_bulk);
     for (int i = 0; i < 2; i++) {
         if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
         if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -356,8 +425,13 @@ int sdv_comm_init(sdv_handle *h, const void *uid, int32_t rank, int32_t world) {
 // ---------------------------------------------------------------------------------------------------------------------
 // upload: validate, derive the reduced-program structure, pack one pinned arena, one H2D copy
 // ---------------------------------------------------------------------------------------------------------------------
-int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
+static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync);
+int sdv_upload_window(sdv_handle *h, const sdv_window *w) { return upload_impl(h, w, true); }
+
+// sync = false (sdv_solve_window): the solve is stream-ordered behind the copies and the set-up kernels, the host does not wait
+static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     if (!h || !w) return SDV_ERR_INVALID_ARGUMENT;
+    auto t_entry = std::chrono::steady_clock::now();
     h->resident = false; // an upload that fails midway must not leave a half-updated problem marked resident
     if (w->abi_version != SDV_ABI_VERSION) return fail(h, SDV_ERR_INVALID_ARGUMENT, "abi_version mismatch");
     const int F = w->n_frames, C = w->n_cams, L = w->n_lmks, O = w->n_obs, Pn = w->vio ? w->n_imu : 0;
@@ -406,37 +480,214 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
             h->in2_bytes = A2.size * 2;
         }
     }
-    struct Joiner {
-        std::thread t;
-        ~Joiner() {
-            if (t.joinable()) t.join();
-        }
-    } packer;
+    const bool have_pool = h->pool.start(4) && !getenv("SDV_NO_HOST_POOL");
+    bool bulk_copy_issued = false, bulk_copy_failed = false; // written by the packing job, read after pool.wait_all()
     {
-        unsigned char *hb2 = h->h_in2;
-        auto pack_bulk = [=] {
+        unsigned char *hb2 = h->h_in2, *db2 = h->d_in2;
+        const size_t bytes2 = A2.size;
+        const int dev = h->device;
+        cudaStream_t cs = h->copy_stream;
+        cudaEvent_t evb = h->ev_bulk;
+        auto pack_bulk = [=, &bulk_copy_issued, &bulk_copy_failed](bool issue_copy) {
             if (O) {
                 std::memcpy(hb2 + q_om, kind == SDV_FACTOR_ANGULAR ? (const void *)w->obs_bearing : (const void *)w->obs_uv, sizeof(double) * (size_t)mplanes * O);
                 std::memcpy(hb2 + q_ol, w->obs_lmk, 4 * (size_t)O);
                 int *fc = reinterpret_cast<int *>(hb2 + q_ofc);
-                for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o]; // validated by the other thread; only used if that passes
+                for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o]; // validated by the other threads; only used if that passes
                 if (w->obs_sigma) {
                     double *ow = reinterpret_cast<double *>(hb2 + q_ow);
                     for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
                 }
             }
             if (L > 0) std::memcpy(hb2 + q_lt, w->lmk_t, sizeof(double) * 3 * (size_t)L);
+            if (issue_copy) { // the transfer of the bulk data overlaps the structure pass of the other threads
+                bool ok = cudaSetDevice(dev) == cudaSuccess && cudaMemcpyAsync(db2, hb2, bytes2, cudaMemcpyHostToDevice, cs) == cudaSuccess &&
+                          cudaEventRecord(evb, cs) == cudaSuccess;
+                bulk_copy_issued = ok;
+                bulk_copy_failed = !ok;
+            }
         };
-        try {
-            packer.t = std::thread(pack_bulk);
-        } catch (...) { // no thread available: pack here (no exception may cross the C ABI)
-            pack_bulk();
-        }
+        if (have_pool) h->pool.submit([pack_bulk] { pack_bulk(true); });
+        else pack_bulk(false);
     }
-    // one pass over the observations: range checks, landmark-major order, CSR pointer per landmark, frames in use
+    struct PoolGuard { // every exit path waits for the jobs that reference this frame's variables
+        HostPool *p;
+        ~PoolGuard() {
+            if (p) p->wait_all();
+        }
+    } pool_guard{have_pool ? &h->pool : nullptr};
     std::vector<int> &lmk_ptr = h->tmp_lmk_ptr;
     lmk_ptr.assign((size_t)L + 1, 0);
     std::vector<char> pose_used(F, 0), vb_used(F, 0);
+    std::vector<int> &slot_ptr = h->tmp_slot_ptr, &slot_frame = h->tmp_slot_frame, &slot_obs_ptr = h->tmp_slot_obs_ptr, &slot_obs = h->tmp_slot_obs;
+    std::vector<char> &same_prev = h->tmp_same_prev;
+    int ns = 0, nso = 0, max_slots = 1;
+    // ---- parallel structure pass (single GPU, no PoseToLandmark pseudo-observations, enough observations to pay): the
+    //      observation list is cut at landmark boundaries into one part per thread; every part validates its observations,
+    //      fills its stretch of the CSR pointer and builds the slot lists of its landmarks; a short serial step turns the
+    //      per-part slot counts into offsets and the parts copy their lists into place.
+    const bool par_struct = have_pool && h->world == 1 && O >= 16384 && !(w->sparse_prior && w->sparse_prior->n_p2l > 0);
+    if (par_struct) {
+        constexpr int NPART = 4;
+        struct Part {
+            int ob = 0, oe = 0;          // observation range, starting at the first observation of a landmark
+            int l_lo = 0, l_hi = -1;     // landmarks whose CSR pointer / slot count this part owns: (last landmark before ob, last landmark in range]
+            std::vector<int> sf, sop, cnt; // slot frames, slot observation pointers (global: slot_obs is written in place), slots per landmark
+            std::vector<char> used, same;
+            int max_slots = 1, bad = 0;
+        } part[NPART];
+        const int32_t *ol = w->obs_lmk, *of = w->obs_frame, *oc = w->obs_cam;
+        slot_obs.resize((size_t)O + 1);
+        same_prev.resize((size_t)L + 1);
+        int cutp[NPART + 1];
+        cutp[0] = 0;
+        cutp[NPART] = O;
+        for (int t = 1; t < NPART; t++) {
+            int c0 = (int)((long long)O * t / NPART);
+            while (c0 < O && c0 > 0 && ol[c0] == ol[c0 - 1]) c0++;
+            cutp[t] = std::max(c0, cutp[t - 1]);
+        }
+        int *slot_obs_g = slot_obs.data(), *lmk_ptr_g = lmk_ptr.data();
+        auto run_part = [&, slot_obs_g, lmk_ptr_g](int t) {
+            Part &pt = part[t];
+            pt.ob = cutp[t];
+            pt.oe = cutp[t + 1];
+            pt.used.assign(F, 0);
+            int prev = pt.ob > 0 ? ol[pt.ob - 1] : -1;
+            if (prev < -1 || prev >= L) { // the neighbour reports it; keep the writes below in range
+                pt.bad = 1;
+                return;
+            }
+            pt.l_lo = prev + 1;
+            // pass 1: validation + CSR pointer
+            unsigned bad = 0;
+            for (int o = pt.ob; o < pt.oe; o++) {
+                const int l = ol[o], f = of[o], c = oc[o];
+                bad |= (unsigned)(l < 0) | (unsigned)(l >= L) | (unsigned)(f < 0) | (unsigned)(f >= F) | (unsigned)(c < 0) | (unsigned)(c >= C) | (unsigned)(l < prev);
+                if (bad) break;
+                if (l != prev) {
+                    for (int q = prev + 1; q <= l; q++) lmk_ptr_g[q] = o;
+                    prev = l;
+                }
+                pt.used[f] = 1;
+            }
+            if (bad) {
+                pt.bad = 1;
+                return;
+            }
+            pt.l_hi = prev;
+            // pass 2: slots of landmarks l_lo .. l_hi (distinct keyframes in first-appearance order)
+            const int nl = pt.l_hi - pt.l_lo + 1;
+            pt.cnt.assign(std::max(nl, 0), 0);
+            pt.same.assign(std::max(nl, 0), 0);
+            pt.sf.clear();
+            pt.sop.clear();
+            pt.sf.reserve((size_t)(pt.oe - pt.ob));
+            pt.sop.reserve((size_t)(pt.oe - pt.ob));
+            int nso_l = pt.ob, prev_first = 0, prev_m = -1;
+            for (int l = pt.l_lo; l <= pt.l_hi; l++) {
+                const int a0 = lmk_ptr_g[l], b0 = l < pt.l_hi ? lmk_ptr_g[l + 1] : pt.oe;
+                const int first = (int)pt.sf.size();
+                bool grouped = true;
+                {
+                    const int nso_save = nso_l;
+                    int cur = -1;
+                    for (int o = a0; o < b0 && grouped; o++) {
+                        const int f = of[o];
+                        if (f != cur) {
+                            for (int q = first; q < (int)pt.sf.size(); q++) grouped &= pt.sf[q] != f;
+                            pt.sf.push_back(f);
+                            pt.sop.push_back(nso_l);
+                            cur = f;
+                        }
+                        slot_obs_g[nso_l++] = o;
+                    }
+                    if (!grouped) {
+                        pt.sf.resize(first);
+                        pt.sop.resize(first);
+                        nso_l = nso_save;
+                    }
+                }
+                if (!grouped) {
+                    for (int o = a0; o < b0; o++) {
+                        const int f = of[o];
+                        bool seen = false;
+                        for (int q = first; q < (int)pt.sf.size(); q++) seen |= pt.sf[q] == f;
+                        if (!seen) pt.sf.push_back(f);
+                    }
+                    for (int q = first; q < (int)pt.sf.size(); q++) {
+                        pt.sop.push_back(nso_l);
+                        const int f = pt.sf[q];
+                        for (int o = a0; o < b0; o++)
+                            if (of[o] == f) slot_obs_g[nso_l++] = o;
+                    }
+                }
+                const int m = (int)pt.sf.size() - first;
+                pt.cnt[l - pt.l_lo] = m;
+                pt.max_slots = std::max(pt.max_slots, m);
+                bool same = prev_m == m && l > pt.l_lo;
+                for (int q = 0; same && q < m; q++) same = pt.sf[first + q] == pt.sf[prev_first + q];
+                pt.same[l - pt.l_lo] = same;
+                prev_first = first;
+                prev_m = m;
+            }
+        };
+        for (int t = 1; t < NPART; t++) h->pool.submit([&run_part, t] { run_part(t); });
+        run_part(0);
+        h->pool.wait_all(); // (also the bulk packing job)
+        int any_bad = 0, tot_slots = 0, off[NPART + 1];
+        for (int t = 0; t < NPART; t++) {
+            any_bad |= part[t].bad;
+            off[t] = tot_slots;
+            tot_slots += (int)part[t].sf.size();
+            max_slots = std::max(max_slots, part[t].max_slots);
+        }
+        off[NPART] = tot_slots;
+        if (any_bad) return fail(h, SDV_ERR_INVALID_ARGUMENT, "observation index out of range or observations not landmark-major (reference walk order)");
+        if (max_slots > MAX_SLOTS) return fail(h, SDV_ERR_UNSUPPORTED, "a landmark is observed from more than 32 keyframes (kernel limit of this build)");
+        {
+            const int last = part[NPART - 1].l_hi; // (every part passed: l_hi is the last landmark seen so far)
+            int lastl = -1;
+            for (int t = 0; t < NPART; t++) lastl = std::max(lastl, part[t].l_hi);
+            (void)last;
+            for (int q = lastl + 1; q <= L; q++) lmk_ptr[q] = O;
+        }
+        for (int t = 0; t < NPART; t++)
+            for (int f = 0; f < F; f++) pose_used[f] |= part[t].used[f];
+        ns = tot_slots;
+        nso = O;
+        slot_ptr.resize((size_t)L + 1);
+        slot_frame.resize((size_t)O + 1);
+        slot_obs_ptr.resize((size_t)O + 2);
+        int *slot_ptr_g = slot_ptr.data(), *slot_frame_g = slot_frame.data(), *slot_obs_ptr_g = slot_obs_ptr.data();
+        char *same_g = same_prev.data();
+        auto place_part = [&, slot_ptr_g, slot_frame_g, slot_obs_ptr_g, same_g](int t) {
+            const Part &pt = part[t];
+            int sidx = off[t];
+            for (int l = pt.l_lo; l <= pt.l_hi; l++) {
+                slot_ptr_g[l] = sidx;
+                sidx += pt.cnt[l - pt.l_lo];
+                same_g[l] = pt.same[l - pt.l_lo];
+            }
+            if (!pt.sf.empty()) {
+                std::memcpy(slot_frame_g + off[t], pt.sf.data(), 4 * pt.sf.size());
+                std::memcpy(slot_obs_ptr_g + off[t], pt.sop.data(), 4 * pt.sop.size());
+            }
+        };
+        for (int t = 1; t < NPART; t++) h->pool.submit([&place_part, t] { place_part(t); });
+        place_part(0);
+        h->pool.wait_all();
+        {
+            int lastl = -1;
+            for (int t = 0; t < NPART; t++) lastl = std::max(lastl, part[t].l_hi);
+            for (int q = lastl + 1; q <= L; q++) {
+                slot_ptr[q] = tot_slots;
+                if (q < L) same_prev[q] = 0;
+            }
+        }
+        slot_obs_ptr[ns] = nso;
+    } else
+    // one pass over the observations: range checks, landmark-major order, CSR pointer per landmark, frames in use
     {
         const int32_t *ol = w->obs_lmk, *of = w->obs_frame, *oc = w->obs_cam;
         int prev = -1;
@@ -558,15 +809,15 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         }
     }
     const int Ocap = Oloc + 2 * n_pseudo;
-    std::vector<int> &slot_ptr = h->tmp_slot_ptr, &slot_frame = h->tmp_slot_frame, &slot_obs_ptr = h->tmp_slot_obs_ptr, &slot_obs = h->tmp_slot_obs;
-    slot_ptr.resize((size_t)L + 1);
-    slot_frame.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
-    slot_obs_ptr.resize((size_t)O + 2 * (size_t)n_pseudo + 2);
-    slot_obs.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
-    int ns = 0, nso = 0, max_slots = 1, prev_first = 0;
-    std::vector<char> &same_prev = h->tmp_same_prev;
-    same_prev.resize((size_t)L + 1);
-    {
+    int prev_first = 0;
+    if (!par_struct) {
+        slot_ptr.resize((size_t)L + 1);
+        slot_frame.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
+        slot_obs_ptr.resize((size_t)O + 2 * (size_t)n_pseudo + 2);
+        slot_obs.resize((size_t)O + 2 * (size_t)n_pseudo + 1);
+        same_prev.resize((size_t)L + 1);
+    }
+    if (!par_struct) {
         const int32_t *of = w->obs_frame;
         std::vector<int> ef, ep; // (frame, plane index) of the landmark's entries, only used when pseudo-observations exist
         for (int l = 0; l < L; l++) {
@@ -1183,8 +1434,10 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
     auto t_pack1 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
-    if (packer.t.joinable()) packer.t.join(); // the bulk data arena is packed
-    CK(cudaMemcpyAsync(h->d_in2, h->h_in2, A2.size, cudaMemcpyHostToDevice, h->stream));
+    if (have_pool) h->pool.wait_all(); // the bulk data arena is packed (and its copy issued on the copy stream)
+    if (bulk_copy_failed) return fail(h, SDV_ERR_CUDA, "H2D copy of the bulk arena failed");
+    if (bulk_copy_issued) CK(cudaStreamWaitEvent(h->stream, h->ev_bulk, 0));
+    else CK(cudaMemcpyAsync(h->d_in2, h->h_in2, A2.size, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
     h->h2d_last = A.size + A2.size;
     if (h->band_smem == 0) CK(cudaMemsetAsync(h->d_Lo, 0, sizeof(double) * sb_elems, h->stream)); // cluster Cholesky: tiles outside the structural pattern are never written
@@ -1198,7 +1451,7 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         h->launches++;
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    if (sync) CK(cudaStreamSynchronize(h->stream));
     h->resident = true;
     auto t_g0 = std::chrono::steady_clock::now();
     if ((rc = build_solve_graph(h)) != SDV_OK) return rc;
@@ -1207,8 +1460,10 @@ int sdv_upload_window(sdv_handle *h, const sdv_window *w) {
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         std::fprintf(stderr, "[sdv upload] reduced system n=%d (%d tiles), factor tiles %d of %d structurally non-zero, half-bandwidth %d blocks of 16 (%s)\n", n, n_pad / 32,
                      h->chol_tiles_nz, h->chol_tiles_all, h->band_bw, h->band_smem > 0 ? "k_chol_band" : "cluster Cholesky");
-        std::fprintf(stderr, "[sdv upload] structure %.3f ms (columns %.3f, slots %.3f, chunks %.3f, masks %.3f), pack %.3f ms, h2d+setup %.3f ms, graph %.3f ms\n",
-                     ms(tu0, t_pack0), ms(tu0, t_s1), ms(t_s1, t_s2), ms(t_s2, t_s3), ms(t_s3, t_pack0), ms(t_pack0, t_pack1), ms(t_pack1, t_g0), ms(t_g0, t_g1));
+        std::fprintf(stderr, "[sdv upload] total %.3f ms: validation pass %.3f, structure %.3f (columns %.3f, slots %.3f, tiles %.3f, masks %.3f), pack + scratch layout %.3f, "
+                             "h2d + setup kernels + sync %.3f, graph %.3f\n",
+                     ms(t_entry, t_g1), ms(t_entry, tu0), ms(tu0, t_pack0), ms(tu0, t_s1), ms(t_s1, t_s2), ms(t_s2, t_s3), ms(t_s3, t_pack0), ms(t_pack0, t_pack1), ms(t_pack1, t_g0),
+                     ms(t_g0, t_g1));
     }
     return SDV_OK;
 }
@@ -1672,7 +1927,7 @@ int sdv_download_delta(sdv_handle *h, sdv_delta *out) {
 int sdv_solve_window(sdv_handle *h, const sdv_window *win, sdv_delta *out, sdv_stats *stats) {
     if (!h || !win || !out) return SDV_ERR_INVALID_ARGUMENT;
     auto t0 = std::chrono::steady_clock::now();
-    int rc = sdv_upload_window(h, win);
+    int rc = upload_impl(h, win, false);
     if (rc != SDV_OK) return rc;
     sdv_stats local;
     sdv_stats *st = stats ? stats : &local;
@@ -1687,6 +1942,7 @@ int sdv_solve_window(sdv_handle *h, const sdv_window *win, sdv_delta *out, sdv_s
     st->h2d_bytes = (int64_t)h->h2d_last;
     st->d2h_bytes = (int64_t)(sizeof(double) * ((size_t)15 * h->P.F + 3 * (size_t)h->P.L) + sizeof(LMState) + sizeof(Accum));
     st->ms_total_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("SDV_TIMING")) std::fprintf(stderr, "[sdv solve_window] total %.3f ms, device solve %.3f ms, h2d %.3f ms\n", st->ms_total_host, st->ms_solve_device, st->ms_h2d);
     return rc;
 }
 

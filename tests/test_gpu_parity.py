@@ -558,3 +558,30 @@ def test_one_cuda_graph_serves_consecutive_windows():
     s.solve_window(synth.make_window("small"))
     assert s.graph_builds() == 2
     s.close()
+
+
+def test_parallel_host_structure_pass_matches_the_serial_one():
+    """Windows with >= 16384 observations build their slot lists on four host threads (observation list cut at landmark
+    boundaries); SDV_NO_HOST_POOL=1 forces the serial pass.  Same LM trace and solution, also when a keyframe re-appears
+    non-adjacently inside a landmark (general grouping path) and when some landmarks have no observation at all."""
+    win = synth.make_window("C3")
+    order = np.lexsort((np.arange(win.n_obs), win.obs_cam, win.obs_lmk))      # left-camera features first inside every landmark
+    keep = np.ones(win.n_obs, bool)
+    keep[np.isin(win.obs_lmk, [0, 1, 4999, 5000, 9999])] = False              # empty landmarks, also at the part boundaries
+    order = order[keep[order]]
+    for name in ("obs_lmk", "obs_frame", "obs_cam", "obs_bearing", "obs_uv"):
+        setattr(win, name, np.ascontiguousarray(getattr(win, name)[order]))
+    a = _solve_with_env(win, {})
+    b = _solve_with_env(win, {"SDV_NO_HOST_POOL": "1"})
+    assert_same_solution(a, b, tol=1e-9)
+    o = orc.solve_window(win, mode=0, nthreads=8)
+    assert_same_solution(a, o)
+    # invalid input is still rejected by the parallel pass
+    bad = synth.make_window("C3")
+    bad.obs_frame[41234] = bad.n_frames
+    with pytest.raises(RuntimeError):
+        api.Solver().solve_window(bad)
+    bad = synth.make_window("C3")
+    bad.obs_lmk[60000] = 3                                                     # not landmark-major
+    with pytest.raises(RuntimeError):
+        api.Solver().solve_window(bad)
