@@ -292,6 +292,42 @@ int sdv_eval_visual(sdv_handle *h, const sdv_delta *x, double *r, double *J_pose
    concatenated column-wise), r_bias[P][6]. */
 int sdv_eval_imu(sdv_handle *h, const sdv_delta *x, double *r_imu, double *J_imu, double *r_bias);
 
+/*
+ * IMU pre-integration — replaces: isae::IMU::processIMU (cpp/src/data/sensors/IMU.cpp:5-91) chained over
+ * the IMU samples of every keyframe interval of a window: the producer of the imu_* arrays of sdv_window.
+ * Sample s of an interval is the measurement held by `_last_IMU` at that step (IMU.cpp:28-31); the first sample of an
+ * interval belongs to the keyframe itself (pre-integration restarts there, IMU.cpp:50-61).
+ */
+typedef struct sdv_imu_intervals {
+    int32_t n_intervals;
+    int32_t n_samples;
+    const int32_t *sample_ptr; /* [n_intervals + 1]: samples of interval k are sample_ptr[k] .. sample_ptr[k+1]-1 */
+    const double *acc;         /* [S][3] IMU::getAcc() of the previous measurement */
+    const double *gyr;         /* [S][3] IMU::getGyr() */
+    const double *dt;          /* [S]    (ts_cur - ts_last) * 1e-9; > 1 s is replaced by 1 / rate_hz (IMU.cpp:23-25) */
+    const double *T_f_w;       /* [n][12] keyframe pose at the start of the interval */
+    const double *v;           /* [n][3]  keyframe velocity */
+    const double *ba;          /* [n][3]  keyframe biases: every measurement of the interval carries them (IMU.cpp:17-18) */
+    const double *bg;          /* [n][3] */
+    const double *dR_stale;    /* [n][9] or NULL (identity): the keyframe IMU's OWN _delta_R, which the reference reads for
+                                          the noise matrix of the first step before restarting (IMU.cpp:44-47) */
+    double eta[6];             /* IMU::_eta: (gyr_noise^2 x3, acc_noise^2 x3) * rate_hz (IMU.h:39-41) */
+    double rate_hz;
+} sdv_imu_intervals;
+
+typedef struct sdv_preint { /* per interval, the state of the LAST measurement's isae::IMU; any pointer but the first five may be NULL */
+    double *dR;      /* [n][9]  getDeltaR() */
+    double *dv;      /* [n][3]  getDeltaV() */
+    double *dp;      /* [n][3]  getDeltaP() */
+    double *cov;     /* [n][81] getCov() */
+    double *J_dR_bg; /* [n][9] */
+    double *J_dv_ba, *J_dv_bg, *J_dp_ba, *J_dp_bg; /* [n][9] each */
+    double *T_pred;  /* [n][12] dead-reckoned Frame::getWorld2FrameTransform() (IMU.cpp:38-41) */
+    double *v_pred;  /* [n][3]  dead-reckoned velocity (IMU.cpp:35) */
+} sdv_preint;
+
+int sdv_preintegrate(sdv_handle *h, const sdv_imu_intervals *in, sdv_preint *out);
+
 /* Multi-GPU (landmark-sharded Schur reduction, one NCCL all-reduce of [S|g|…] per LM iteration).
    `nccl_unique_id` is the 128-byte ncclUniqueId every rank received from rank 0. */
 /* Host-only helper (no CUDA): the contiguous, observation-balanced landmark range [l0,l1) and observation range [o0,o1)

@@ -177,6 +177,28 @@ class SdvStats(C.Structure):
     ]
 
 
+class SdvImuIntervals(C.Structure):
+    _fields_ = [
+        ("n_intervals", C.c_int32),
+        ("n_samples", C.c_int32),
+        ("sample_ptr", c_int32_p),
+        ("acc", c_double_p),
+        ("gyr", c_double_p),
+        ("dt", c_double_p),
+        ("T_f_w", c_double_p),
+        ("v", c_double_p),
+        ("ba", c_double_p),
+        ("bg", c_double_p),
+        ("dR_stale", c_double_p),
+        ("eta", C.c_double * 6),
+        ("rate_hz", C.c_double),
+    ]
+
+
+class SdvPreint(C.Structure):
+    _fields_ = [(n, c_double_p) for n in ("dR", "dv", "dp", "cov", "J_dR_bg", "J_dv_ba", "J_dv_bg", "J_dp_ba", "J_dp_bg", "T_pred", "v_pred")]
+
+
 def _dp(a: Optional[np.ndarray]):
     if a is None:
         return c_double_p()

@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
     L.sdv_debug_read.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int64]
     L.sdv_debug_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sdv_debug_graph_builds.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.sdv_preintegrate.argtypes = [C.c_void_p, C.POINTER(abi.SdvImuIntervals), C.POINTER(abi.SdvPreint)]
     _lib = L
     return L
 
@@ -151,6 +152,30 @@ class Solver:
         n, npad = C.c_int32(), C.c_int32()
         self._check(lib().sdv_debug_dims(self._h, C.byref(n), C.byref(npad)))
         return n.value, npad.value
+
+    def preintegrate(self, sample_ptr, acc, gyr, dt, T_f_w, v, ba, bg, eta, rate_hz, dR_stale=None) -> dict:
+        """IMU::processIMU (IMU.cpp:5-91) over the samples of every keyframe interval, on the GPU (sdv_preintegrate)."""
+        f64 = lambda a, shape: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape))
+        sp = np.ascontiguousarray(sample_ptr, dtype=np.int32)
+        n, S = len(sp) - 1, int(sp[-1])
+        ins = abi.SdvImuIntervals()
+        ins.n_intervals, ins.n_samples = n, S
+        keep = [sp, f64(acc, (S, 3)), f64(gyr, (S, 3)), f64(dt, (S,)), f64(T_f_w, (n, 12)), f64(v, (n, 3)), f64(ba, (n, 3)), f64(bg, (n, 3))]
+        ins.sample_ptr = keep[0].ctypes.data_as(abi.c_int32_p)
+        for name, a in zip(("acc", "gyr", "dt", "T_f_w", "v", "ba", "bg"), keep[1:]):
+            setattr(ins, name, a.ctypes.data_as(abi.c_double_p))
+        if dR_stale is not None:
+            keep.append(f64(dR_stale, (n, 9)))
+            ins.dR_stale = keep[-1].ctypes.data_as(abi.c_double_p)
+        ins.eta[:] = [float(x) for x in np.asarray(eta).reshape(6)]
+        ins.rate_hz = float(rate_hz)
+        out = {k: np.zeros((n, w)) for k, w in (("dR", 9), ("dv", 3), ("dp", 3), ("cov", 81), ("J_dR_bg", 9), ("J_dv_ba", 9), ("J_dv_bg", 9),
+                                              ("J_dp_ba", 9), ("J_dp_bg", 9), ("T_pred", 12), ("v_pred", 3))}
+        outs = abi.SdvPreint()
+        for k, a in out.items():
+            setattr(outs, k, a.ctypes.data_as(abi.c_double_p))
+        self._check(lib().sdv_preintegrate(self._h, C.byref(ins), C.byref(outs)))
+        return out
 
     def graph_builds(self) -> int:
         n = C.c_int64()

@@ -10,8 +10,10 @@
 #include "sdv_fused.cuh"
 #include "sdv_chol.cuh"
 #include "sdv_chol_band.cuh"
+#include "sdv_preint.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -72,12 +74,12 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 // A few persistent host threads per handle: the structure pass of an upload (validation, slot lists) runs on them in parallel
 // and one of them packs the bulk arena and issues its H2D copy, so the transfer overlaps the structure pass.
 struct HostPool {
+    struct Group { int pending = 0; }; // jobs submitted together; guarded by the pool mutex
     std::vector<std::thread> th;
     std::mutex m;
     std::condition_variable cv, cv_done;
-    std::vector<std::function<void()>> jobs;
+    std::vector<std::pair<std::function<void()>, Group *>> jobs;
     size_t next = 0;
-    int pending = 0;
     bool stop = false;
     bool start(int n) {
         try {
@@ -89,33 +91,35 @@ struct HostPool {
     }
     void loop() {
         for (;;) {
-            std::function<void()> f;
+            std::pair<std::function<void()>, Group *> job;
             {
                 std::unique_lock<std::mutex> lk(m);
                 cv.wait(lk, [this] { return stop || next < jobs.size(); });
                 if (stop) return;
-                f = std::move(jobs[next++]);
+                job = std::move(jobs[next++]);
             }
-            f();
+            job.first();
             {
                 std::lock_guard<std::mutex> lk(m);
-                if (--pending == 0) cv_done.notify_all();
+                if (--job.second->pending == 0) cv_done.notify_all();
             }
         }
     }
-    void submit(std::function<void()> f) {
+    void submit(Group &g, std::function<void()> f) {
         {
             std::lock_guard<std::mutex> lk(m);
-            jobs.push_back(std::move(f));
-            pending++;
+            jobs.emplace_back(std::move(f), &g);
+            g.pending++;
         }
         cv.notify_one();
     }
-    void wait_all() {
+    void wait(Group &g) {
         std::unique_lock<std::mutex> lk(m);
-        cv_done.wait(lk, [this] { return pending == 0; });
-        jobs.clear();
-        next = 0;
+        cv_done.wait(lk, [&g] { return g.pending == 0; });
+        if (next == jobs.size()) { // nothing queued: recycle the job list
+            jobs.clear();
+            next = 0;
+        }
     }
     ~HostPool() {
         {
@@ -480,42 +484,57 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
             h->in2_bytes = A2.size * 2;
         }
     }
-    const bool have_pool = h->pool.start(4) && !getenv("SDV_NO_HOST_POOL");
-    bool bulk_copy_issued = false, bulk_copy_failed = false; // written by the packing job, read after pool.wait_all()
+    const bool have_pool = h->pool.start(6) && !getenv("SDV_NO_HOST_POOL");
+    HostPool::Group g_bulk, g_struct;
+    bool bulk_copy_issued = false, bulk_copy_failed = false; // written by the packing job that finishes last, read after pool.wait(g_bulk)
+    std::atomic<int> bulk_left{3};
     {
         unsigned char *hb2 = h->h_in2, *db2 = h->d_in2;
         const size_t bytes2 = A2.size;
         const int dev = h->device;
         cudaStream_t cs = h->copy_stream;
         cudaEvent_t evb = h->ev_bulk;
-        auto pack_bulk = [=, &bulk_copy_issued, &bulk_copy_failed](bool issue_copy) {
-            if (O) {
-                std::memcpy(hb2 + q_om, kind == SDV_FACTOR_ANGULAR ? (const void *)w->obs_bearing : (const void *)w->obs_uv, sizeof(double) * (size_t)mplanes * O);
-                std::memcpy(hb2 + q_ol, w->obs_lmk, 4 * (size_t)O);
-                int *fc = reinterpret_cast<int *>(hb2 + q_ofc);
-                for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o]; // validated by the other threads; only used if that passes
-                if (w->obs_sigma) {
-                    double *ow = reinterpret_cast<double *>(hb2 + q_ow);
-                    for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
+        // three pieces of similar size (measurements in two halves; indices + landmarks); the piece that finishes last issues the
+        // H2D copy on the copy stream, so packing AND transfer of the bulk data overlap the structure pass of the other threads
+        auto pack_bulk = [=, &bulk_copy_issued, &bulk_copy_failed, &bulk_left](int piece, bool issue_copy) {
+            const size_t mbytes = sizeof(double) * (size_t)mplanes * O, half = (mbytes / 2) & ~size_t(63);
+            const unsigned char *msrc = reinterpret_cast<const unsigned char *>(kind == SDV_FACTOR_ANGULAR ? (const void *)w->obs_bearing : (const void *)w->obs_uv);
+            if (piece == 0 && O) std::memcpy(hb2 + q_om, msrc, half);
+            if (piece == 1 && O) std::memcpy(hb2 + q_om + half, msrc + half, mbytes - half);
+            if (piece == 2) {
+                if (O) {
+                    std::memcpy(hb2 + q_ol, w->obs_lmk, 4 * (size_t)O);
+                    int *fc = reinterpret_cast<int *>(hb2 + q_ofc);
+                    for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o]; // validated by the other threads; only used if that passes
+                    if (w->obs_sigma) {
+                        double *ow = reinterpret_cast<double *>(hb2 + q_ow);
+                        for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
+                    }
                 }
+                if (L > 0) std::memcpy(hb2 + q_lt, w->lmk_t, sizeof(double) * 3 * (size_t)L);
             }
-            if (L > 0) std::memcpy(hb2 + q_lt, w->lmk_t, sizeof(double) * 3 * (size_t)L);
-            if (issue_copy) { // the transfer of the bulk data overlaps the structure pass of the other threads
+            if (issue_copy && bulk_left.fetch_sub(1) == 1) {
                 bool ok = cudaSetDevice(dev) == cudaSuccess && cudaMemcpyAsync(db2, hb2, bytes2, cudaMemcpyHostToDevice, cs) == cudaSuccess &&
                           cudaEventRecord(evb, cs) == cudaSuccess;
                 bulk_copy_issued = ok;
                 bulk_copy_failed = !ok;
             }
         };
-        if (have_pool) h->pool.submit([pack_bulk] { pack_bulk(true); });
-        else pack_bulk(false);
+        for (int piece = 0; piece < 3; piece++) {
+            if (have_pool) h->pool.submit(g_bulk, [pack_bulk, piece] { pack_bulk(piece, true); });
+            else pack_bulk(piece, false);
+        }
     }
     struct PoolGuard { // every exit path waits for the jobs that reference this frame's variables
         HostPool *p;
+        HostPool::Group *a, *b;
         ~PoolGuard() {
-            if (p) p->wait_all();
+            if (p) {
+                p->wait(*a);
+                p->wait(*b);
+            }
         }
-    } pool_guard{have_pool ? &h->pool : nullptr};
+    } pool_guard{have_pool ? &h->pool : nullptr, &g_bulk, &g_struct};
     std::vector<int> &lmk_ptr = h->tmp_lmk_ptr;
     lmk_ptr.assign((size_t)L + 1, 0);
     std::vector<char> pose_used(F, 0), vb_used(F, 0);
@@ -632,9 +651,9 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
                 prev_m = m;
             }
         };
-        for (int t = 1; t < NPART; t++) h->pool.submit([&run_part, t] { run_part(t); });
+        for (int t = 1; t < NPART; t++) h->pool.submit(g_struct, [&run_part, t] { run_part(t); });
         run_part(0);
-        h->pool.wait_all(); // (also the bulk packing job)
+        h->pool.wait(g_struct);
         int any_bad = 0, tot_slots = 0, off[NPART + 1];
         for (int t = 0; t < NPART; t++) {
             any_bad |= part[t].bad;
@@ -674,9 +693,9 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
                 std::memcpy(slot_obs_ptr_g + off[t], pt.sop.data(), 4 * pt.sop.size());
             }
         };
-        for (int t = 1; t < NPART; t++) h->pool.submit([&place_part, t] { place_part(t); });
+        for (int t = 1; t < NPART; t++) h->pool.submit(g_struct, [&place_part, t] { place_part(t); });
         place_part(0);
-        h->pool.wait_all();
+        h->pool.wait(g_struct);
         {
             int lastl = -1;
             for (int t = 0; t < NPART; t++) lastl = std::max(lastl, part[t].l_hi);
@@ -1434,7 +1453,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     auto t_pack1 = std::chrono::steady_clock::now();
     CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
-    if (have_pool) h->pool.wait_all(); // the bulk data arena is packed (and its copy issued on the copy stream)
+    if (have_pool) h->pool.wait(g_bulk); // the bulk data arena is packed (and its copy issued on the copy stream)
     if (bulk_copy_failed) return fail(h, SDV_ERR_CUDA, "H2D copy of the bulk arena failed");
     if (bulk_copy_issued) CK(cudaStreamWaitEvent(h->stream, h->ev_bulk, 0));
     else CK(cudaMemcpyAsync(h->d_in2, h->h_in2, A2.size, cudaMemcpyHostToDevice, h->stream));
@@ -2030,6 +2049,78 @@ int sdv_eval_imu(sdv_handle *h, const sdv_delta *x, double *r_imu, double *J_imu
     if (r_imu) CK(cudaMemcpy(r_imu, h->B[0].imu_r, sizeof(double) * 9 * P.P, cudaMemcpyDeviceToHost));
     if (J_imu) CK(cudaMemcpy(J_imu, h->B[0].imu_J, sizeof(double) * 216 * P.P, cudaMemcpyDeviceToHost));
     if (r_bias) CK(cudaMemcpy(r_bias, h->B[0].bias_r, sizeof(double) * 6 * P.P, cudaMemcpyDeviceToHost));
+    return SDV_OK;
+}
+
+// IMU::processIMU over every keyframe interval (sdv_preint.cuh), host buffers in and out
+int sdv_preintegrate(sdv_handle *h, const sdv_imu_intervals *in, sdv_preint *out) {
+    if (!h || !in || !out) return SDV_ERR_INVALID_ARGUMENT;
+    const int n = in->n_intervals, S = in->n_samples;
+    if (n < 0 || S < 0) return fail(h, SDV_ERR_INVALID_ARGUMENT, "negative sizes");
+    if (n == 0) return SDV_OK;
+    if (!in->sample_ptr || !in->T_f_w || !in->v || !in->ba || !in->bg || (S > 0 && (!in->acc || !in->gyr || !in->dt)))
+        return fail(h, SDV_ERR_INVALID_ARGUMENT, "null pre-integration inputs");
+    if (!out->dR || !out->dv || !out->dp || !out->cov || !out->J_dR_bg || !out->J_dv_ba || !out->J_dv_bg || !out->J_dp_ba || !out->J_dp_bg)
+        return fail(h, SDV_ERR_INVALID_ARGUMENT, "null pre-integration outputs");
+    if (in->sample_ptr[0] != 0 || in->sample_ptr[n] != S) return fail(h, SDV_ERR_INVALID_ARGUMENT, "sample_ptr does not cover the samples");
+    for (int k = 0; k < n; k++)
+        if (in->sample_ptr[k + 1] < in->sample_ptr[k]) return fail(h, SDV_ERR_INVALID_ARGUMENT, "sample_ptr not monotonic");
+    if (!(in->rate_hz > 0)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "rate_hz must be positive");
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    const size_t D = sizeof(double);
+    Arena A;
+    const size_t i_sp = A.add(4 * (size_t)(n + 1)), i_acc = A.add(D * 3 * std::max(S, 1)), i_gyr = A.add(D * 3 * std::max(S, 1)), i_dt = A.add(D * std::max(S, 1));
+    const size_t i_T = A.add(D * 12 * n), i_v = A.add(D * 3 * n), i_ba = A.add(D * 3 * n), i_bg = A.add(D * 3 * n), i_st = A.add(D * 9 * n);
+    const size_t in_bytes = A.size;
+    const size_t o_dR = A.add(D * 9 * n), o_dv = A.add(D * 3 * n), o_dp = A.add(D * 3 * n), o_cov = A.add(D * 81 * n), o_j1 = A.add(D * 9 * n), o_j2 = A.add(D * 9 * n),
+                 o_j3 = A.add(D * 9 * n), o_j4 = A.add(D * 9 * n), o_j5 = A.add(D * 9 * n), o_T = A.add(D * 12 * n), o_v = A.add(D * 3 * n);
+    std::vector<unsigned char> hb(A.size);
+    std::memcpy(&hb[i_sp], in->sample_ptr, 4 * (size_t)(n + 1));
+    if (S > 0) {
+        std::memcpy(&hb[i_acc], in->acc, D * 3 * S);
+        std::memcpy(&hb[i_gyr], in->gyr, D * 3 * S);
+        std::memcpy(&hb[i_dt], in->dt, D * S);
+    }
+    std::memcpy(&hb[i_T], in->T_f_w, D * 12 * n);
+    std::memcpy(&hb[i_v], in->v, D * 3 * n);
+    std::memcpy(&hb[i_ba], in->ba, D * 3 * n);
+    std::memcpy(&hb[i_bg], in->bg, D * 3 * n);
+    if (in->dR_stale) std::memcpy(&hb[i_st], in->dR_stale, D * 9 * n);
+    unsigned char *d = nullptr;
+    CK(cudaMalloc((void **)&d, A.size));
+    struct Free {
+        unsigned char *p;
+        ~Free() { cudaFree(p); }
+    } guard{d};
+    CK(cudaMemcpyAsync(d, hb.data(), in_bytes, cudaMemcpyHostToDevice, s));
+    PreintArgs a;
+    a.n_intervals = n;
+    a.sample_ptr = at<int>(d, i_sp);
+    a.acc = at<double>(d, i_acc); a.gyr = at<double>(d, i_gyr); a.dt = at<double>(d, i_dt);
+    a.T_f_w = at<double>(d, i_T); a.v = at<double>(d, i_v); a.ba = at<double>(d, i_ba); a.bg = at<double>(d, i_bg);
+    a.dR_stale = in->dR_stale ? at<double>(d, i_st) : nullptr;
+    for (int k = 0; k < 6; k++) a.eta[k] = in->eta[k];
+    a.rate_hz = in->rate_hz;
+    a.dR = at<double>(d, o_dR); a.dv = at<double>(d, o_dv); a.dp = at<double>(d, o_dp); a.cov = at<double>(d, o_cov);
+    a.J_dR_bg = at<double>(d, o_j1); a.J_dv_ba = at<double>(d, o_j2); a.J_dv_bg = at<double>(d, o_j3); a.J_dp_ba = at<double>(d, o_j4); a.J_dp_bg = at<double>(d, o_j5);
+    a.T_pred = at<double>(d, o_T); a.v_pred = at<double>(d, o_v);
+    k_preintegrate<<<(n + PRE_WARPS - 1) / PRE_WARPS, PRE_WARPS * 32, 0, s>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&hb[o_dR], d + o_dR, A.size - o_dR, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::memcpy(out->dR, &hb[o_dR], D * 9 * n);
+    std::memcpy(out->dv, &hb[o_dv], D * 3 * n);
+    std::memcpy(out->dp, &hb[o_dp], D * 3 * n);
+    std::memcpy(out->cov, &hb[o_cov], D * 81 * n);
+    std::memcpy(out->J_dR_bg, &hb[o_j1], D * 9 * n);
+    std::memcpy(out->J_dv_ba, &hb[o_j2], D * 9 * n);
+    std::memcpy(out->J_dv_bg, &hb[o_j3], D * 9 * n);
+    std::memcpy(out->J_dp_ba, &hb[o_j4], D * 9 * n);
+    std::memcpy(out->J_dp_bg, &hb[o_j5], D * 9 * n);
+    if (out->T_pred) std::memcpy(out->T_pred, &hb[o_T], D * 12 * n);
+    if (out->v_pred) std::memcpy(out->v_pred, &hb[o_v], D * 3 * n);
     return SDV_OK;
 }
 

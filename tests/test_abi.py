@@ -43,6 +43,7 @@ def test_ctypes_mirror_matches_c_layout():
              offsetof(sdv_window, sparse_prior));
       printf("%zu %zu %zu\n", offsetof(sdv_stats, trace_accepted), offsetof(sdv_stats, kernel_launches),
              offsetof(sdv_sparse_prior, l2l_sqrt_inf));
+      printf("%zu %zu %zu %zu\n", sizeof(sdv_imu_intervals), sizeof(sdv_preint), offsetof(sdv_imu_intervals, eta), offsetof(sdv_imu_intervals, rate_hz));
       return 0; }
     """
     with tempfile.TemporaryDirectory() as td:
@@ -55,7 +56,8 @@ def test_ctypes_mirror_matches_c_layout():
     want = [C.sizeof(abi.SdvConfig), C.sizeof(abi.SdvDensePrior), C.sizeof(abi.SdvSparsePrior), C.sizeof(abi.SdvWindow),
             C.sizeof(abi.SdvDelta), C.sizeof(abi.SdvStats),
             abi.SdvWindow.T_f_w.offset, abi.SdvWindow.obs_lmk.offset, abi.SdvWindow.imu_cov.offset, abi.SdvWindow.sparse_prior.offset,
-            abi.SdvStats.trace_accepted.offset, abi.SdvStats.kernel_launches.offset, abi.SdvSparsePrior.l2l_sqrt_inf.offset]
+            abi.SdvStats.trace_accepted.offset, abi.SdvStats.kernel_launches.offset, abi.SdvSparsePrior.l2l_sqrt_inf.offset,
+            C.sizeof(abi.SdvImuIntervals), C.sizeof(abi.SdvPreint), abi.SdvImuIntervals.eta.offset, abi.SdvImuIntervals.rate_hz.offset]
     assert got == want
 
 

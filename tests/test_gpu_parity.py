@@ -585,3 +585,55 @@ def test_parallel_host_structure_pass_matches_the_serial_one():
     bad.obs_lmk[60000] = 3                                                     # not landmark-major
     with pytest.raises(RuntimeError):
         api.Solver().solve_window(bad)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# IMU pre-integration on the device: sdv_preintegrate against the oracle's processIMU chain
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_preint_chain(T_kf, v_kf, ba, bg, acc, gyr, dts, eta, rate, dR_stale=None):
+    kf = orc.imu_state(acc[0], gyr[0], T_f_w=T_kf, v=v_kf, ba=ba, bg=bg, is_kf=True)
+    if dR_stale is not None:
+        kf[28:37] = dR_stale
+    last = kf
+    for k in range(len(dts)):
+        nxt_acc, nxt_gyr = (acc[k + 1], gyr[k + 1]) if k + 1 < len(dts) else (acc[k], gyr[k])
+        last = orc.process_imu(last, ba, bg, dts[k], eta, rate, nxt_acc, nxt_gyr)
+    return last
+
+
+def test_preintegration_kernel_matches_the_oracle(solver):
+    rng = np.random.default_rng(5)
+    n, rate = 49, 200.0
+    counts = rng.integers(30, 70, n)
+    counts[3], counts[7] = 1, 0                                     # a one-sample interval and an empty one
+    sp = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    S = int(sp[-1])
+    acc = rng.normal(0, 2.0, (S, 3)) + [0, 0, 9.81]
+    gyr = rng.normal(0, 0.3, (S, 3))
+    gyr[sp[5]:sp[6]] = 0.0                                          # zero rotation: the small-angle branches of exp / Jr
+    dts = np.full(S, 1.0 / rate)
+    dts[sp[10] + 4] = 1.7                                           # > 1 s: replaced by 1 / rate (IMU.cpp:23-25)
+    T = np.stack([synth.T34(np.vstack([np.hstack([synth.exp_so3(rng.normal(0, 0.5, 3)), rng.normal(0, 2, (3, 1))]), [0, 0, 0, 1]])) for _ in range(n)])
+    v, ba, bg = rng.normal(0, 1, (n, 3)), rng.normal(0, 0.05, (n, 3)), rng.normal(0, 0.01, (n, 3))
+    stale = np.stack([synth.exp_so3(rng.normal(0, 0.2, 3)).reshape(9) for _ in range(n)])
+    eta = rf.eta(rate)
+    out = solver.preintegrate(sp, acc, gyr, dts, T, v, ba, bg, eta, rate, dR_stale=stale)
+    names = (("dR", "dR"), ("dv", "dv"), ("dp", "dp"), ("cov", "Sigma"), ("J_dR_bg", "J_dR_bg"), ("J_dv_ba", "J_dv_ba"), ("J_dv_bg", "J_dv_bg"),
+             ("J_dp_ba", "J_dp_ba"), ("J_dp_bg", "J_dp_bg"), ("T_pred", "T_f_w"), ("v_pred", "v"))
+    for k in range(n):
+        if counts[k] == 0:
+            assert np.all(out["cov"][k] == 0) and np.allclose(out["dR"][k], np.eye(3).reshape(9)) and np.all(out["dp"][k] == 0)
+            continue
+        a, b = sp[k], sp[k + 1]
+        ref = _oracle_preint_chain(T[k], v[k], ba[k], bg[k], acc[a:b], gyr[a:b], dts[a:b], eta, rate, stale[k])
+        for mine, theirs in names:
+            r = orc.imu_get(ref, theirs)
+            assert np.abs(out[mine][k] - r).max() <= 1e-11 * max(1.0, np.abs(r).max()), (k, mine)
+    # the reference's own known-answer test, imu_test.cpp:948-995 (two half-second steps)
+    acc2, gyr2 = np.array([[0.1, 9.81, 0.0]] * 2), np.array([[0.0, 0.0, 0.1]] * 2)
+    o2 = solver.preintegrate([0, 2], acc2, gyr2, [0.5, 0.5], np.eye(3, 4).reshape(1, 12), np.zeros((1, 3)), np.zeros((1, 3)), np.zeros((1, 3)), rf.eta(200), 200)
+    imu0 = orc.imu_state(acc2[0], gyr2[0], is_kf=True)
+    imu1 = orc.process_imu(imu0, np.zeros(3), np.zeros(3), 0.5, rf.eta(200), 200, acc2[1], gyr2[1])
+    imu2 = orc.process_imu(imu1, np.zeros(3), np.zeros(3), 0.5, rf.eta(200), 200, acc2[1], gyr2[1])
+    assert np.abs(o2["dp"][0] - orc.imu_get(imu2, "dp")).max() < 1e-13
+    assert np.abs(o2["cov"][0] - orc.imu_get(imu2, "Sigma")).max() <= 1e-11 * np.abs(orc.imu_get(imu2, "Sigma")).max()
