@@ -74,13 +74,18 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 // A few persistent host threads per handle: the structure pass of an upload (validation, slot lists) runs on them in parallel
 // and one of them packs the bulk arena and issues its H2D copy, so the transfer overlaps the structure pass.
 struct HostPool {
-    struct Group { int pending = 0; }; // jobs submitted together; guarded by the pool mutex
+    // Jobs are short (tens of microseconds) and arrive in bursts at the start of an upload; a futex wake-up costs as much as a
+    // job (more inside a VM).  Hence: the submitting thread SPINS on the group counter, and a worker keeps polling for ~1.5 ms
+    // after its last job before it blocks on the condition variable — back-to-back solves never pay a wake-up, an idle handle
+    // burns no CPU.
+    struct Group { std::atomic<int> pending{0}; }; // jobs submitted together
     std::vector<std::thread> th;
     std::mutex m;
-    std::condition_variable cv, cv_done;
-    std::vector<std::pair<std::function<void()>, Group *>> jobs;
-    size_t next = 0;
-    bool stop = false;
+    std::condition_variable cv;
+    std::vector<std::pair<std::function<void()>, Group *>> jobs; // guarded by m
+    size_t next = 0;                                              // guarded by m
+    std::atomic<int> avail{0};                                    // queued, not yet taken
+    std::atomic<bool> stop{false};
     bool start(int n) {
         try {
             for (int i = (int)th.size(); i < n; i++) th.emplace_back([this] { loop(); });
@@ -90,41 +95,56 @@ struct HostPool {
         return true;
     }
     void loop() {
+        auto idle_since = std::chrono::steady_clock::now();
         for (;;) {
             std::pair<std::function<void()>, Group *> job;
-            {
+            bool have = false;
+            if (avail.load(std::memory_order_acquire) > 0 || std::chrono::steady_clock::now() - idle_since > std::chrono::microseconds(1500)) {
                 std::unique_lock<std::mutex> lk(m);
-                cv.wait(lk, [this] { return stop || next < jobs.size(); });
-                if (stop) return;
-                job = std::move(jobs[next++]);
+                if (avail.load(std::memory_order_acquire) == 0) cv.wait(lk, [this] { return stop.load() || next < jobs.size(); });
+                if (stop.load()) return;
+                if (next < jobs.size()) {
+                    job = std::move(jobs[next++]);
+                    avail.fetch_sub(1, std::memory_order_acq_rel);
+                    have = true;
+                }
+            } else {
+                if (stop.load(std::memory_order_relaxed)) return;
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
             }
-            job.first();
-            {
-                std::lock_guard<std::mutex> lk(m);
-                if (--job.second->pending == 0) cv_done.notify_all();
+            if (have) {
+                job.first();
+                job.second->pending.fetch_sub(1, std::memory_order_acq_rel);
+                idle_since = std::chrono::steady_clock::now();
             }
         }
     }
     void submit(Group &g, std::function<void()> f) {
+        g.pending.fetch_add(1, std::memory_order_acq_rel);
         {
             std::lock_guard<std::mutex> lk(m);
+            if (next == jobs.size()) { // nothing queued: recycle the job list
+                jobs.clear();
+                next = 0;
+            }
             jobs.emplace_back(std::move(f), &g);
-            g.pending++;
+            avail.fetch_add(1, std::memory_order_acq_rel);
         }
         cv.notify_one();
     }
     void wait(Group &g) {
-        std::unique_lock<std::mutex> lk(m);
-        cv_done.wait(lk, [&g] { return g.pending == 0; });
-        if (next == jobs.size()) { // nothing queued: recycle the job list
-            jobs.clear();
-            next = 0;
+        while (g.pending.load(std::memory_order_acquire) != 0) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
         }
     }
     ~HostPool() {
         {
             std::lock_guard<std::mutex> lk(m);
-            stop = true;
+            stop.store(true);
         }
         cv.notify_all();
         for (auto &t : th)
@@ -209,6 +229,8 @@ struct sdv_handle {
     std::vector<int> tmp_lmk_ptr, tmp_slot_ptr, tmp_slot_frame, tmp_slot_obs_ptr, tmp_slot_obs; // reused between uploads
     std::vector<char> tmp_same_prev;
     std::vector<int> tmp_tile_ptr;
+    double *d_xchg = nullptr;    // multi-GPU exchange buffer (k_band_exchange)
+    int last_iters = 3;          // LM iterations of the previous solve: how many the host enqueues before it first looks at the status (N > 1)
     double *d_lmk_aux = nullptr; // [L][LMK_AUX]: V^-1, g_l, D_l of every eliminated landmark (k_lin_schur -> k_backsub_cost)
     int fused_grid = 0, fused_grid_back = 0;
     std::vector<uint32_t> tmp_tile_nz;
@@ -548,7 +570,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     const bool par_struct = have_pool && h->world == 1 && O >= 16384 && !(w->sparse_prior && w->sparse_prior->n_p2l > 0);
     if (par_struct) {
         constexpr int NPART = 4;
-        struct Part {
+        struct alignas(128) Part { // (one cache line pair each: the threads update their own counters all the time)
             int ob = 0, oe = 0;          // observation range, starting at the first observation of a landmark
             int l_lo = 0, l_hi = -1;     // landmarks whose CSR pointer / slot count this part owns: (last landmark before ob, last landmark in range]
             std::vector<int> sf, sop, cnt; // slot frames, slot observation pointers (global: slot_obs is written in place), slots per landmark
@@ -568,7 +590,11 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         }
         int *slot_obs_g = slot_obs.data(), *lmk_ptr_g = lmk_ptr.data();
         auto run_part = [&, slot_obs_g, lmk_ptr_g](int t) {
-            Part &pt = part[t];
+            Part pt; // worked on locally (vector bookkeeping included), published once at the end
+            struct Publish {
+                Part &dst, &src;
+                ~Publish() { dst = std::move(src); }
+            } publish{part[t], pt};
             pt.ob = cutp[t];
             pt.oe = cutp[t + 1];
             pt.used.assign(F, 0);
@@ -1070,7 +1096,30 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         for (int t = 0; t < ng; t++) low[t].w[t >> 6] |= 1ull << (t & 63); // padding columns: identity diagonal
     };
     auto bit = [&](const TMask &m, int j) { return (m.w[j >> 6] >> (j & 63)) & 1ull; };
-    if (Tt <= 128) {
+    // ---- block half-bandwidth of the reduced system at 16-column granularity.  The envelope of a Cholesky factor is the
+    //      envelope of the matrix, so max_i (i - first coupled block of row i) bounds the fill: when that band (plus two
+    //      look-ahead block rows) fits in the shared memory of one SM, the whole factorisation runs in ONE CTA (k_chol_band).
+    int band_bw = -1;
+    if (n_pad / 16 <= 256) {
+        std::vector<TMask> low16;
+        build_low(16, low16);
+        const int nb16 = n_pad / 16;
+        band_bw = 0;
+        for (int i = 0; i < nb16; i++) {
+            int first = i;
+            for (int wq = 3; wq >= 0; wq--)
+                if (low16[i].w[wq]) first = wq * 64 + __builtin_ctzll(low16[i].w[wq]);
+            band_bw = std::max(band_bw, i - std::min(first, i));
+        }
+    }
+    h->band_bw = band_bw;
+    // (the 32-column tile pattern only serves the wide-band fallback k_chol_chain: skipped whenever k_chol_band will run)
+    bool band_applies = false;
+    if (band_bw >= 0 && std::max(band_bw, 1) <= BAND_MAX_BW && !getenv("SDV_CHOL_VARIANT") && !getenv("SDV_CHOL_DENSE")) {
+        const BandPlan plb = band_plan(n_pad, std::max(band_bw, 1));
+        band_applies = sizeof(double) * (size_t)plb.o_end <= 220 * 1024 && (size_t)plb.nb * (std::max(band_bw, 1) + 2) * 256 <= (size_t)(n_pad + 32) * ld;
+    }
+    if (Tt <= 128 && !band_applies) {
         std::vector<TMask> low;
         build_low(32, low);
         // symbolic right-looking elimination on the tile graph: the rows below pivot k become mutually coupled
@@ -1094,23 +1143,6 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         h->chol_tiles_nz = nnz_tiles;
         h->chol_tiles_all = Tt * (Tt + 1) / 2;
     }
-    // ---- block half-bandwidth of the reduced system at 16-column granularity.  The envelope of a Cholesky factor is the
-    //      envelope of the matrix, so max_i (i - first coupled block of row i) bounds the fill: when that band (plus two
-    //      look-ahead block rows) fits in the shared memory of one SM, the whole factorisation runs in ONE CTA (k_chol_band).
-    int band_bw = -1;
-    if (n_pad / 16 <= 256) {
-        std::vector<TMask> low16;
-        build_low(16, low16);
-        const int nb16 = n_pad / 16;
-        band_bw = 0;
-        for (int i = 0; i < nb16; i++) {
-            int first = i;
-            for (int wq = 3; wq >= 0; wq--)
-                if (low16[i].w[wq]) first = wq * 64 + __builtin_ctzll(low16[i].w[wq]);
-            band_bw = std::max(band_bw, i - std::min(first, i));
-        }
-    }
-    h->band_bw = band_bw;
 
     // ---- input arena
     Arena A;
@@ -1293,6 +1325,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     size_t s_dinv = S.add(D * (n_pad + 32));
     size_t s_prof = S.add(D * 8 * CC_MAX);
     size_t s_aux = S.add(D * LMK_AUX * cL);
+    size_t s_xchg = h->world > 1 ? S.add(D * ((size_t)n_pad * n_pad + 3 * (size_t)n_pad + 8)) : 0; // upper bound (no band); the band case uses the head
     if ((rc = ensure(h, &h->d_scr, &h->scr_cap, S.size)) != SDV_OK) return rc;
     unsigned char *sb = h->d_scr;
     // solution buffer: [solution blocks | LMState | Accum] (k_gather_solution), one device-to-host copy per solve
@@ -1365,6 +1398,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     h->d_dinv = at<double>(sb, s_dinv);
     h->d_prof = at<double>(sb, s_prof);
     h->d_lmk_aux = at<double>(sb, s_aux);
+    h->d_xchg = h->world > 1 ? at<double>(sb, s_xchg) : nullptr;
     h->sb_elems = sb_elems;
 
     // ---- launch geometry
@@ -1563,6 +1597,35 @@ int allreduce(sdv_handle *h, double *buf, size_t count) {
     return SDV_OK;
 }
 
+// Multi-GPU exchange buffer of one LM iteration: the BAND of S (row i: its last W = 16 (bw + 1) columns up to the diagonal — every
+// structurally non-zero entry of the stored lower triangle), the three rows [g | diag | raw gradient], and the gradient-violation
+// flag of this rank's landmark columns — ONE ncclAllReduce instead of the full (n_pad + 3) x n_pad buffer (0.47 MB instead of
+// 4.3 MB at C3, 1.9 MB instead of 72 MB at C5).  dir 0: pack, dir 1: unpack the sums.
+__global__ void k_band_exchange(double *Sb, double *pack, Accum *acc, int n_pad, int ld, int W, double grad_tol, int dir) {
+    const size_t nband = (size_t)n_pad * W, ntot = nband + 3 * (size_t)n_pad;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = tid; e < ntot; e += nt) {
+        double *p;
+        if (e < nband) {
+            const int i = (int)(e / W), c = (int)(e - (size_t)i * W), col = i - W + 1 + c;
+            if (col < 0) {
+                if (dir == 0) pack[e] = 0.0;
+                continue;
+            }
+            p = Sb + (size_t)i * ld + col;
+        } else {
+            p = Sb + (size_t)n_pad * ld + (e - nband); // rows n_pad .. n_pad + 2 are contiguous (ld == n_pad)
+        }
+        if (dir == 0) pack[e] = *p;
+        else *p = pack[e];
+    }
+    if (tid == 0) {
+        // grad_max over the landmark columns is a MAX across ranks: exchanged as a count of ranks above the tolerance
+        if (dir == 0) pack[ntot] = (__longlong_as_double((long long)acc->grad_max_bits) > grad_tol) ? 1.0 : 0.0;
+        else acc->grad_max_bits = pack[ntot] > 0.0 ? (unsigned long long)__double_as_longlong(1e300) : 0ull;
+    }
+}
+
 __global__ void k_pack_scalars(const LMState *st, Accum *acc, double *red, int dir, int which /* buffer: -2 candidate, 0 initial */) {
     int b = which >= 0 ? which : 1 - st->cur;
     if (dir == 0) {
@@ -1571,31 +1634,27 @@ __global__ void k_pack_scalars(const LMState *st, Accum *acc, double *red, int d
         red[2] = acc->model_dd;
         red[3] = acc->step_norm2;
         red[4] = acc->cand_norm2;
-        red[5] = acc->fixed_cost;
+        red[5] = which == 0 ? acc->fixed_cost : 0.0; // accumulated on rank 0 during the first linearisation only: reduced once
+        red[6] = acc->schur_fail ? 1.0 : 0.0; // a 3x3 block that failed on ONE shard invalidates the step on every rank
     } else {
         acc->cost[b] = red[0];
         acc->model_gd = red[1];
         acc->model_dd = red[2];
         acc->step_norm2 = red[3];
         acc->cand_norm2 = red[4];
-        acc->fixed_cost = red[5];
+        if (which == 0) acc->fixed_cost = red[5];
+        acc->schur_fail = red[6] > 0.0 ? 1 : 0;
     }
 }
 
 int reduce_scalars(sdv_handle *h, int which) {
     if (h->world <= 1) return SDV_OK;
     k_pack_scalars<<<1, 1, 0, h->stream>>>(h->d_st, h->d_acc, h->d_red, 0, which);
-    int rc = allreduce(h, h->d_red, 6);
+    int rc = allreduce(h, h->d_red, 7);
     if (rc != SDV_OK) return rc;
     k_pack_scalars<<<1, 1, 0, h->stream>>>(h->d_st, h->d_acc, h->d_red, 1, which);
     h->launches += 2;
     return SDV_OK;
-}
-
-// grad_max over landmark columns must be a MAX across ranks: reduce it as a count of violations instead
-__global__ void k_gradmax_to_flag(Accum *acc, double tol, double *red, int dir) {
-    if (dir == 0) red[8] = (__longlong_as_double((long long)acc->grad_max_bits) > tol) ? 1.0 : 0.0;
-    else acc->grad_max_bits = red[8] > 0.0 ? (unsigned long long)__double_as_longlong(1e300) : 0ull;
 }
 
 int launch_factor_solve(sdv_handle *h) {
@@ -1685,13 +1744,15 @@ int launch_iteration(sdv_handle *h) {
         if (forked) join_side(h, 0);
     }
     if (h->world > 1) {
-        // one all-reduce of [S | g | diag | grad] per LM iteration, plus the gradient-violation flag
-        k_gradmax_to_flag<<<1, 1, 0, s>>>(h->d_acc, h->opt.gradient_tolerance, h->d_red, 0);
-        int rc = allreduce(h, h->d_Sb, (size_t)(P.n_pad + 3) * P.ld);
+        // ONE all-reduce per LM iteration: the band of S + [g | diag | grad] + the gradient flag, packed (k_band_exchange).  A
+        // reduced system without a band (dense prior over kept landmarks: wide-band fallback) exchanges all its rows.
+        const int W = h->band_smem > 0 ? std::min(P.n_pad, 16 * (P.band_bw + 1)) : P.n_pad;
+        const size_t count = (size_t)P.n_pad * W + 3 * (size_t)P.n_pad + 1;
+        const int grid = (int)std::min<size_t>((count + 255) / 256, (size_t)h->num_sms * 8);
+        k_band_exchange<<<grid, 256, 0, s>>>(h->d_Sb, h->d_xchg, h->d_acc, P.n_pad, P.ld, W, h->opt.gradient_tolerance, 0);
+        int rc = allreduce(h, h->d_xchg, count);
         if (rc != SDV_OK) return rc;
-        rc = allreduce(h, h->d_red + 8, 1);
-        if (rc != SDV_OK) return rc;
-        k_gradmax_to_flag<<<1, 1, 0, s>>>(h->d_acc, h->opt.gradient_tolerance, h->d_red, 1);
+        k_band_exchange<<<grid, 256, 0, s>>>(h->d_Sb, h->d_xchg, h->d_acc, P.n_pad, P.ld, W, h->opt.gradient_tolerance, 1);
         h->launches += 2;
     }
     if (h->band_smem == 0) { // k_chol_band prepares the system itself
@@ -1874,13 +1935,22 @@ int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
     } else {
         int rc = enqueue_prologue(h);
         if (rc != SDV_OK) return rc;
+        // No CUDA graph here (NCCL inside a conditional WHILE body is not attempted).  Every kernel returns at once when the solve
+        // has terminated and the collectives are issued by all ranks alike, so iterations can be enqueued AHEAD of the status:
+        // as many as the previous solve took, then the status is read, then one more at a time.  A steady back end pays one
+        // host round trip per solve instead of one per iteration.
         int *h_status = reinterpret_cast<int *>(h->h_rb);
-        for (int it = 0; it < h->opt.max_num_iterations + 1; it++) {
-            rc = launch_iteration(h);
-            if (rc != SDV_OK) return rc;
+        const int max_it = h->opt.max_num_iterations + 1;
+        int it = 0, ahead = std::max(1, std::min(h->last_iters, max_it));
+        while (it < max_it) {
+            for (int q = 0; q < ahead && it < max_it; q++, it++) {
+                rc = launch_iteration(h);
+                if (rc != SDV_OK) return rc;
+            }
             CK(cudaMemcpyAsync(h_status, &h->d_st->status, sizeof(int), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             if (*h_status != 0) break;
+            ahead = 1;
         }
         rc = enqueue_epilogue(h);
         if (rc != SDV_OK) return rc;
@@ -1900,6 +1970,7 @@ int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
     std::memcpy(&h->h_state, h->h_rb, sizeof(LMState));
     std::memcpy(&h->h_acc, h->h_rb + sizeof(LMState), sizeof(Accum));
     auto t1 = std::chrono::steady_clock::now();
+    h->last_iters = std::max(1, h->h_state.iter);
     if (stats) {
         const LMState &st = h->h_state;
         float ms = 0;
