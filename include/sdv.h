@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SDV_ABI_VERSION 1
+#define SDV_ABI_VERSION 2
 #define SDV_MAX_TRACE 64
 
 typedef enum sdv_status {
@@ -172,7 +172,7 @@ typedef struct sdv_window {
     int32_t n_lmks;
     int32_t n_obs;
     int32_t n_imu;
-    int32_t reserved0;
+    int32_t reserved0;           /* 0 */
 
     /* frames */
     const double *T_f_w;     /* [F][12] Frame::getWorld2FrameTransform() */
@@ -222,7 +222,32 @@ typedef struct sdv_window {
     /* priors injected by addMarginalizationResiduals (…Analytic.cpp:341-486); either may be NULL */
     const sdv_dense_prior *dense_prior;
     const sdv_sparse_prior *sparse_prior;
+
+    /* --- the other AOptimizer solves as masks of the window solve --- */
+    double visual_loss_huber_a;  /* 0: loss_function = nullptr (localMapBA, localMapVIOptimization, singleFrameOptimization);
+                                    a > 0: ceres::HuberLoss(a) on every VISUAL residual block — landmarkOptimization
+                                    (AOptimizer.cpp:102) and singleFrameVIOptimization (:223) pass sqrt(1.345); the IMU
+                                    factors of the latter are added with a null loss (:239) */
+    int32_t landmarks_constant;  /* 1: every landmark block is SetParameterBlockConstant — the single-frame solves
+                                    (addSingleFrameResiduals, …Analytic.cpp:38-43) */
+    int32_t max_num_iterations;  /* > 0 overrides sdv_config::max_num_iterations for this window: 10 in landmarkOptimization
+                                    (AOptimizer.cpp:113), 5 in the single-frame solves (:166, :247) */
 } sdv_window;
+/*
+ * How the four solves map onto sdv_window (the adapters sadvio_b200/host/b200_optimizer.hpp and sadvio_b200/api.py do this):
+ *   localMapVIOptimization / localMapBA   n_fixed = fixed_frame_number, everything above zero
+ *   landmarkOptimization(frame)           frames = the keyframes that see the frame's landmarks, n_fixed = n_frames (all poses
+ *                                         constant, AngularAdjustmentCERESAnalytic.cpp:141-145), vio = 0, Huber sqrt(1.345),
+ *                                         10 iterations; the reduced system is empty, every landmark is a 3x3 problem under
+ *                                         ONE trust region
+ *   singleFrameOptimization(frame)        frames = { frame }, landmarks_constant = 1, obs_sigma = 1 / focal (…Analytic.cpp:48),
+ *                                         5 iterations
+ *   singleFrameVIOptimization(frame)      frames = { frame, frame->getIMU()->getLastKF() }, vio = 1, one IMU pair,
+ *                                         landmarks_constant = 1, Huber sqrt(1.345), 5 iterations (the 5 ms wall-clock budget
+ *                                         of AOptimizer.cpp:254 is not modelled: a solve of this size takes well under 1 ms)
+ * VIInit (AOptimizer.cpp:448-581) uses the IMUFactorInit functors with gravity / scale blocks and is out of scope (SURVEY.md
+ * section 2).
+ */
 
 /*
  * Solution = the values of the Ceres parameter blocks after the solve

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
+#include <limits>
 #include <vector>
 
 using namespace orc;
@@ -104,6 +105,7 @@ static bool build_problem(const sdv_window *w, Problem &P, bool schur) {
         PBlock &p = P.pbs[P.lmk_id(l)];
         p.size = 3;
         p.elim = schur;
+        p.constant = w->landmarks_constant != 0; // single-frame solves: SetParameterBlockConstant, AngularAdjustmentCERESAnalytic.cpp:41-43
     }
     for (auto &p : P.pbs) {
         p.off = off;
@@ -397,7 +399,27 @@ template <class Fn> static void parallel_for(int n, int nthreads, Fn fn) {
     for (auto &t : th) t.join();
 }
 
-// Evaluate all active blocks. Returns cost = 1/2 sum r^2 over active blocks; residuals/jacobians stored.
+// ceres::HuberLoss(a)::Evaluate followed by ceres::internal::Corrector (Ceres 2.2, not part of /root/reference: loss_function.cc,
+// corrector.cc, residual_block.cc as remembered): rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond; rho'' <= 0 always, so the
+// corrector scales residuals AND Jacobian by sqrt(rho') and the block's cost is rho(s) / 2.  Returns rho(s).
+static double huber_correct(double a, int nres, double *r, double *jac, int jcount) {
+    double s = 0;
+    for (int k = 0; k < nres; k++) s += r[k] * r[k];
+    const double b = a * a;
+    double rho0 = s, rho1 = 1.0;
+    if (s > b) {
+        const double rr = std::sqrt(s);
+        rho0 = 2.0 * a * rr - b;
+        rho1 = std::max(std::numeric_limits<double>::min(), a / rr);
+    }
+    const double sc = std::sqrt(rho1);
+    for (int k = 0; k < nres; k++) r[k] *= sc;
+    if (jac)
+        for (int k = 0; k < jcount; k++) jac[k] *= sc;
+    return rho0;
+}
+
+// Evaluate all active blocks. Returns cost = 1/2 sum rho(r^2) over active blocks; residuals/jacobians stored (robustified).
 static bool evaluate(const Problem &P, const double *x, double *cost, double *residuals, double *jac, int nthreads) {
     int n = (int)P.rbs.size();
     std::vector<double> partial(std::max(1, nthreads), 0.0);
@@ -410,7 +432,12 @@ static bool evaluate(const Problem &P, const double *x, double *cost, double *re
             if (!rb.active) continue;
             double *r = residuals + rb.roff;
             if (!eval_block(P, rb, x, r, jac ? jac + rb.joff : nullptr)) ok = false;
-            for (int k = 0; k < rb.nres; k++) c += r[k] * r[k];
+            if (rb.kind == K_VISUAL && P.w->visual_loss_huber_a > 0) {
+                int width = 0;
+                for (int id : rb.pb) width += P.pbs[id].size;
+                c += huber_correct(P.w->visual_loss_huber_a, rb.nres, r, jac ? jac + rb.joff : nullptr, rb.nres * width);
+            } else
+                for (int k = 0; k < rb.nres; k++) c += r[k] * r[k];
         }
         partial[t] = c;
     });
@@ -427,7 +454,9 @@ static double fixed_cost_of(const Problem &P, const double *x) {
         if (rb.active) continue;
         r.assign(rb.nres, 0.0);
         eval_block(P, rb, x, r.data(), nullptr);
-        for (double v : r) c += v * v;
+        if (rb.kind == K_VISUAL && P.w->visual_loss_huber_a > 0) c += huber_correct(P.w->visual_loss_huber_a, rb.nres, r.data(), nullptr, 0);
+        else
+            for (double v : r) c += v * v;
     }
     return 0.5 * c;
 }
@@ -862,7 +891,7 @@ static int solve_lm(const sdv_window *w, const sdv_config *cfg, sdv_delta *out, 
     }
     while (!done) {
         // FinalizeIterationAndCheckIfMinimizerCanContinue: max iterations / min radius
-        if (iteration >= cfg->max_num_iterations) {
+        if (iteration >= (w->max_num_iterations > 0 ? w->max_num_iterations : cfg->max_num_iterations)) {
             term = SDV_TERM_NO_CONVERGENCE;
             break;
         }

@@ -11,7 +11,7 @@ from typing import Optional
 
 import numpy as np
 
-SDV_ABI_VERSION = 1
+SDV_ABI_VERSION = 2
 SDV_MAX_TRACE = 64
 
 SDV_FACTOR_ANGULAR = 0
@@ -138,6 +138,9 @@ class SdvWindow(C.Structure):
         ("imu_sigma_bg", c_double_p),
         ("dense_prior", C.POINTER(SdvDensePrior)),
         ("sparse_prior", C.POINTER(SdvSparsePrior)),
+        ("visual_loss_huber_a", C.c_double),
+        ("landmarks_constant", C.c_int32),
+        ("max_num_iterations", C.c_int32),
     ]
 
 
@@ -329,6 +332,9 @@ class Window:
     dense_prior: Optional[DensePrior] = None
     sparse_prior: Optional[SparsePrior] = None
     skipped_preint: Optional[SkippedPreint] = None   # host-side only (write-back), see SkippedPreint
+    visual_loss_huber_a: float = 0.0           # ceres::HuberLoss(a) on the visual residual blocks, 0 = none
+    landmarks_constant: bool = False           # single-frame solves: every landmark block constant
+    max_num_iterations: int = 0                # > 0: overrides the configuration for this window
     meta: dict = field(default_factory=dict)   # ground truth etc. (never crosses the ABI)
 
     @property
@@ -398,6 +404,9 @@ class Window:
             "imu_J_dp_ba", "imu_J_dp_bg", "imu_sigma_ba", "imu_sigma_bg",
         ):
             setattr(w, name, _dp(getattr(self, name)))
+        w.visual_loss_huber_a = float(self.visual_loss_huber_a)
+        w.landmarks_constant = 1 if self.landmarks_constant else 0
+        w.max_num_iterations = int(self.max_num_iterations)
         keep = [self]
         if self.dense_prior is not None:
             d = self.dense_prior

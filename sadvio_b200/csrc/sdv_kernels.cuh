@@ -1485,11 +1485,14 @@ __global__ void k_reset(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1,
 }
 
 // gather the solution blocks in ABI order, followed by the solver state and the accumulators:
-// out = [dpose 6F | dv 3F | dba 3F | dbg 3F | dlmk 3 max(L,1) | LMState | Accum] — ONE device-to-host copy per solve
+// out = [dpose 6F | dv 3F | dba 3F | dbg 3F | LMState | Accum | dlmk 3 max(L,1)] — ONE device-to-host copy per solve; the landmark
+// block comes last so that the multi-GPU gather (a sum over ranks of that block) can run over its CAPACITY
 __global__ void k_gather_solution(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, const Accum *acc, double *out) {
     const DevProblem &P = *Pg;
     const LinBuf &B = st->cur ? B1 : B0;
-    double *dpose = out, *dv = out + 6 * P.F, *dba = dv + 3 * P.F, *dbg = dba + 3 * P.F, *dlmk = dbg + 3 * P.F;
+    double *dpose = out, *dv = out + 6 * P.F, *dba = dv + 3 * P.F, *dbg = dba + 3 * P.F;
+    unsigned long long *tail = reinterpret_cast<unsigned long long *>(dbg + 3 * P.F);
+    double *dlmk = reinterpret_cast<double *>(tail + (sizeof(LMState) + sizeof(Accum)) / 8);
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (int f = tid; f < P.F; f += nt) {
         int pc = P.pose_col[f], vc = P.vb_col[f];
@@ -1505,7 +1508,6 @@ __global__ void k_gather_solution(const DevProblem *__restrict__ Pg, LinBuf B0, 
         // kept landmarks are replicated on every rank (count them once); eliminated ones are owned by one rank
         for (int k = 0; k < 3; k++) dlmk[3 * (size_t)l + k] = dc >= 0 ? (P.rank == 0 ? B.xp[dc + k] : 0.0) : B.xl[3 * (size_t)l + k];
     }
-    unsigned long long *tail = reinterpret_cast<unsigned long long *>(dlmk + 3 * (size_t)(P.L > 0 ? P.L : 1));
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(st);
     for (int i = tid; i < (int)(sizeof(LMState) / 8); i += nt) tail[i] = src[i];
     tail += sizeof(LMState) / 8;

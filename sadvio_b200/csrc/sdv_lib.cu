@@ -1803,6 +1803,12 @@ size_t solution_bytes(const DevProblem &P) { return solution_doubles(P) * sizeof
 int enqueue_epilogue(sdv_handle *h) {
     k_gather_solution<<<64, 256, 0, h->stream>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc, reinterpret_cast<double *>(h->d_out));
     h->launches++;
+    if (h->world > 1) {
+        // every rank only solved its own landmarks and left zeros for the others: a sum over ranks is the gather.  Done ONCE,
+        // here, so that sdv_download_delta is a plain host copy (no hidden collective, idempotent).  The capacity of the landmark
+        // block is reduced (zeros beyond L), so the count does not tie the CUDA graph to the window.
+        return allreduce(h, reinterpret_cast<double *>(h->d_out + sizeof(double) * 15 * (size_t)h->P.F + sizeof(LMState) + sizeof(Accum)), 3 * (size_t)h->cap_L);
+    }
     return SDV_OK;
 }
 // ... and ONE copy to pinned host memory, issued behind the graph: its size depends on the window, the graph does not
@@ -1822,8 +1828,10 @@ void destroy_graph(sdv_handle *h) {
 
 // prologue -> WHILE (status == 0) { one LM iteration } -> epilogue, as ONE graph launch per solve.
 int build_solve_graph(sdv_handle *h) {
-    if (h->world > 1 || getenv("SDV_NO_GRAPH")) { // NCCL inside a conditional body is not attempted
-        destroy_graph(h);                         // (a graph of an earlier single-GPU window must not survive)
+    // N > 1: the NCCL all-reduces are captured into the WHILE body like any other node (NCCL >= 2.9 supports stream capture);
+    // SDV_MGPU_NO_GRAPH=1 or a failed capture / instantiation falls back to the host loop that enqueues iterations ahead
+    if ((h->world > 1 && getenv("SDV_MGPU_NO_GRAPH")) || getenv("SDV_NO_GRAPH")) {
+        destroy_graph(h); // (a graph of an earlier window must not survive)
         return SDV_OK;
     }
     sdv_handle::GraphSig sig;
@@ -1954,19 +1962,14 @@ int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
         }
         rc = enqueue_epilogue(h);
         if (rc != SDV_OK) return rc;
-        if (h->world > 1) {
-            // every rank only solved its own landmarks and left zeros for the others: a sum over ranks is the gather.  Done ONCE,
-            // here, so that sdv_download_delta is a plain host copy (no hidden collective, idempotent)
-            rc = allreduce(h, reinterpret_cast<double *>(h->d_out) + 15 * P.F, 3 * (size_t)P.L);
-            if (rc != SDV_OK) return rc;
-        }
         CK(cudaEventRecord(h->ev[3], s));
         rc = enqueue_readback(h);
         if (rc != SDV_OK) return rc;
         CK(cudaStreamSynchronize(s));
     }
     CK(cudaGetLastError());
-    std::memcpy(h->h_rb, h->h_sol + nd * sizeof(double), sizeof(LMState) + sizeof(Accum));
+    (void)nd;
+    std::memcpy(h->h_rb, h->h_sol + sizeof(double) * 15 * (size_t)P.F, sizeof(LMState) + sizeof(Accum));
     std::memcpy(&h->h_state, h->h_rb, sizeof(LMState));
     std::memcpy(&h->h_acc, h->h_rb + sizeof(LMState), sizeof(Accum));
     auto t1 = std::chrono::steady_clock::now();
@@ -2010,7 +2013,7 @@ int sdv_download_delta(sdv_handle *h, sdv_delta *out) {
     if (out->dv) std::memcpy(out->dv, hb + 6 * P.F, sizeof(double) * 3 * P.F);
     if (out->dba) std::memcpy(out->dba, hb + 9 * P.F, sizeof(double) * 3 * P.F);
     if (out->dbg) std::memcpy(out->dbg, hb + 12 * P.F, sizeof(double) * 3 * P.F);
-    if (P.L > 0) std::memcpy(out->dlmk, hb + 15 * P.F, sizeof(double) * 3 * P.L);
+    if (P.L > 0) std::memcpy(out->dlmk, h->h_sol + sizeof(double) * 15 * (size_t)P.F + sizeof(LMState) + sizeof(Accum), sizeof(double) * 3 * P.L);
     return SDV_OK;
 }
 

@@ -41,7 +41,7 @@ def main():
             rel = lambda a, b: float(np.abs(a - b).max() / max(1e-300, np.abs(b).max()))
             print(f"{name} x{world}: iters {st['iterations']} vs {st0['iterations']} term {st['termination']} cost {st['final_cost']:.6f} vs {st0['final_cost']:.6f} "
                   f"pose {rel(d.dpose, d0.dpose):.2e} v {rel(d.dv, d0.dv) if win.vio else 0:.2e} lmk {rel(d.dlmk, d0.dlmk):.2e} "
-                  f"solve {dt*1e3:.3f} ms ({st['iterations']/dt:.0f} it/s)", flush=True)
+                  f"solve {dt*1e3:.3f} ms ({st['iterations']/dt:.0f} it/s) cuda graph builds {s.graph_builds()}", flush=True)
             assert st["iterations"] == st0["iterations"] and rel(d.dpose, d0.dpose) < 1e-6 and rel(d.dlmk, d0.dlmk) < 1e-5
     dist.destroy_process_group()
 
