@@ -3,13 +3,14 @@
 The product path is the CUDA library only: if ``libsadvio_b200.so`` is missing or no sm_100 GPU is visible, calls fail
 loudly (``BackendUnavailable``); there is no CPU fallback and this module never imports ``oracle``.
 
-``B200Optimizer`` mirrors ``isae::AOptimizer`` for the two entry points this repository replaces
-(reference cpp/include/isaeslam/optimizers/AOptimizer.h:28-30):
+``B200Optimizer`` mirrors ``isae::AOptimizer`` for the entry points this repository replaces
+(reference cpp/include/isaeslam/optimizers/AOptimizer.h:22-30):
     bool localMapBA(local_map, fixed_frame_number = 0)
     bool localMapVIOptimization(local_map, fixed_frame_number = 0)
+    bool landmarkOptimization(frame) / singleFrameOptimization(frame) / singleFrameVIOptimization(frame)
 operating on a flattened ``abi.Window`` (the C++ adapter sadvio_b200/host/b200_optimizer.hpp does the flattening of the
-pointer graph).  Both return ``True``/``False`` like the reference and update the window state in place exactly as
-AOptimizer.cpp:391-434 does.
+pointer graph; here a frame is an index into the window).  All return ``True``/``False`` like the reference and update
+the window state in place exactly as AOptimizer.cpp:122-146, :199-216, :262-296, :391-434 do.
 """
 from __future__ import annotations
 
@@ -231,6 +232,60 @@ def write_back(win: abi.Window, d: abi.Delta, vio: bool) -> None:
                 correct(sk.dR, sk.dv, sk.dp, sk.J_dR_bg, sk.J_dv_ba, sk.J_dv_bg, sk.J_dp_ba, sk.J_dp_bg, k, int(sk.prev[k]))
 
 
+HUBER_A = float(np.sqrt(1.345))  # AOptimizer.cpp:102, :223
+
+
+def _subset(win: abi.Window, frames: list[int], lmks: np.ndarray, obs: np.ndarray, **kw) -> abi.Window:
+    """The window restricted to `frames` (new order), `lmks` and the observations `obs` (landmark-major already)."""
+    fmap = -np.ones(win.n_frames, dtype=np.int64)
+    fmap[frames] = np.arange(len(frames))
+    lmap = -np.ones(win.n_lmks, dtype=np.int64)
+    lmap[lmks] = np.arange(len(lmks))
+    pick = lambda a, idx: None if a is None else np.ascontiguousarray(a[idx])
+    return abi.Window(
+        vio=False, factor_kind=win.factor_kind, n_fixed=0, T_f_w=pick(win.T_f_w, frames), T_s_f=win.T_s_f.copy(), K=win.K.copy(),
+        lmk_t=pick(win.lmk_t, lmks), obs_lmk=lmap[win.obs_lmk[obs]].astype(np.int32), obs_frame=fmap[win.obs_frame[obs]].astype(np.int32),
+        obs_cam=pick(win.obs_cam, obs), obs_bearing=pick(win.obs_bearing, obs), obs_uv=pick(win.obs_uv, obs),
+        v=pick(win.v, frames), ba=pick(win.ba, frames), bg=pick(win.bg, frames), has_imu=pick(win.has_imu, frames), **kw)
+
+
+def landmark_window(win: abi.Window, frame: int) -> tuple[abi.Window, np.ndarray]:
+    """landmarkOptimization(frame) as a window (addLandmarkResiduals, AngularAdjustmentCERESAnalytic.cpp:106-209): the
+    landmarks `frame` observes, all their observations on the keyframes of `win`, every pose constant, Huber loss, 10
+    iterations.  Returns the window and the indices of its landmarks in `win`."""
+    lmks = np.unique(win.obs_lmk[win.obs_frame == frame])
+    obs = np.flatnonzero(np.isin(win.obs_lmk, lmks))
+    frames = list(dict.fromkeys(int(f) for f in win.obs_frame[obs]))  # first-appearance order
+    sub = _subset(win, frames, lmks, obs, visual_loss_huber_a=HUBER_A, max_num_iterations=10)
+    sub.n_fixed = len(frames)
+    return sub, lmks
+
+
+def single_frame_window(win: abi.Window, frame: int, vi: bool) -> tuple[abi.Window, list[int]]:
+    """singleFrameOptimization / singleFrameVIOptimization(frame) as a window (addSingleFrameResiduals,
+    AngularAdjustmentCERESAnalytic.cpp:6-102; AOptimizer.cpp:152-297): the frame (and, VI, its previous keyframe = the i of
+    its IMU pair) with free poses, the frame's landmarks constant, sigma 1 / focal, 5 iterations."""
+    pair = np.flatnonzero(win.imu_j == frame) if (vi and win.vio and win.imu_j is not None) else np.zeros(0, dtype=np.int64)
+    frames = [frame] + ([int(win.imu_i[pair[0]])] if len(pair) else [])
+    lmks = np.unique(win.obs_lmk[win.obs_frame == frame])
+    sel = np.isin(win.obs_lmk, lmks) & np.isin(win.obs_frame, frames)
+    # landmark-major; within a landmark the moving frame's features first, then the previous keyframe's
+    obs = np.flatnonzero(sel)
+    obs = obs[np.lexsort((obs, win.obs_frame[obs] != frame, win.obs_lmk[obs]))]
+    sub = _subset(win, frames, lmks, obs, landmarks_constant=True, max_num_iterations=5, visual_loss_huber_a=HUBER_A if vi else 0.0)
+    if win.factor_kind == abi.SDV_FACTOR_ANGULAR:
+        focal = (win.K[:, 0] + win.K[:, 1]) / 2
+        sub.obs_sigma = np.ascontiguousarray(1.0 / focal[sub.obs_cam])  # …Analytic.cpp:48
+    if len(pair):
+        p = pair[:1]
+        sub.vio = True
+        sub.imu_i, sub.imu_j = np.array([1], dtype=np.int32), np.array([0], dtype=np.int32)
+        for name in ("imu_dt", "imu_dR", "imu_dv", "imu_dp", "imu_cov", "imu_J_dR_bg", "imu_J_dv_ba", "imu_J_dv_bg", "imu_J_dp_ba", "imu_J_dp_bg",
+                     "imu_sigma_ba", "imu_sigma_bg"):
+            setattr(sub, name, np.ascontiguousarray(getattr(win, name)[p]))
+    return sub, frames
+
+
 class B200Optimizer:
     """Host-side mirror of ``isae::AOptimizer`` for the window solves (see module docstring)."""
 
@@ -257,3 +312,45 @@ class B200Optimizer:
 
     def localMapBA(self, local_map: abi.Window, fixed_frame_number: int = 0) -> bool:  # noqa: N802
         return self._run(local_map, fixed_frame_number, False)
+
+    def landmarkOptimization(self, local_map: abi.Window, frame: int, sanity_check=None) -> bool:  # noqa: N802
+        """AOptimizer.cpp:98-150.  `sanity_check(l) -> bool` stands for ALandmark::sanityCheck (a data-model method outside the
+        optimizer): only landmarks that pass it are updated (:132-140); None = all pass."""
+        sub, lmks = landmark_window(local_map, frame)
+        if sub.n_obs == 0:
+            return True
+        try:
+            rc, d, st = self._solve(sub)
+        except RuntimeError:
+            return False
+        self.last_stats = st
+        for k, l in enumerate(lmks):
+            if sanity_check is None or sanity_check(int(l)):
+                local_map.lmk_t[l] += d.dlmk[k]
+        return True
+
+    def _single(self, local_map: abi.Window, frame: int, vi: bool) -> bool:
+        sub, frames = single_frame_window(local_map, frame, vi)
+        if sub.n_obs == 0 and sub.n_imu == 0:
+            return True
+        try:
+            rc, d, st = self._solve(sub)
+        except RuntimeError:
+            return False
+        self.last_stats = st
+        if vi and rc == 5:
+            return False  # !summary.IsSolutionUsable(), AOptimizer.cpp:259
+        sub.lmk_t = np.zeros((0, 3))
+        d.dlmk = np.zeros((0, 3))
+        sub.imu_i = sub.imu_j = None  # no biasDeltaCorrection in the single-frame solves (AOptimizer.cpp:262-285)
+        write_back(sub, d, bool(sub.vio))
+        local_map.T_f_w[frames] = sub.T_f_w
+        if sub.vio:
+            local_map.v[frames], local_map.ba[frames], local_map.bg[frames] = sub.v, sub.ba, sub.bg
+        return True
+
+    def singleFrameOptimization(self, local_map: abi.Window, frame: int) -> bool:  # noqa: N802
+        return self._single(local_map, frame, False)
+
+    def singleFrameVIOptimization(self, local_map: abi.Window, frame: int) -> bool:  # noqa: N802
+        return self._single(local_map, frame, True)

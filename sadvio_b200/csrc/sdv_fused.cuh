@@ -68,6 +68,26 @@ template <int KIND> SDV_DEV void eval_residual(const double *row, const double *
     }
 }
 
+// ceres::HuberLoss(a)::Evaluate + ceres::internal::Corrector for one visual residual block (Ceres 2.2 loss_function.cc /
+// corrector.cc; AOptimizer.cpp:102,223 pass a = sqrt(1.345)): rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond; rho'' <= 0, so the
+// corrector scales the residual AND the Jacobians by sqrt(rho') and the block's cost is rho(s) / 2.
+SDV_DEV double huber_rho(double a, double s) {
+    const double b = a * a;
+    return s > b ? 2.0 * a * sqrt(s) - b : s;
+}
+SDV_DEV void huber_correct(double a, double *r, double *Jp, double *Jl) {
+    const double s = r[0] * r[0] + r[1] * r[1];
+    if (s > a * a) {
+        const double sc = sqrt(fmax(2.2250738585072014e-308, a / sqrt(s)));
+        r[0] *= sc;
+        r[1] *= sc;
+#pragma unroll
+        for (int k = 0; k < 12; k++) Jp[k] *= sc;
+#pragma unroll
+        for (int k = 0; k < 6; k++) Jl[k] *= sc;
+    }
+}
+
 // operands of one real observation (plane index ol < Oloc)
 template <int KIND> struct ObsOperands {
     double meas[3], w;
@@ -91,6 +111,7 @@ template <int KIND> SDV_DEV void obs_eval(const DevProblem &P, const LinBuf &B, 
         load_obs<KIND>(P, ol, q);
         const double *row = B.fct + (size_t)q.fc * FCT_ROW;
         eval_visual<KIND>(row, P.K + 4 * (q.fc % P.C), q.w < 0.0 ? row[30] : q.w, p, q.meas, r, Jp, Jl);
+        if (P.huber_a > 0.0) huber_correct(P.huber_a, r, Jp, Jl); // the loss wraps the VISUAL blocks only
     } else {
         const size_t OC = (size_t)P.Ocap;
         r[0] = B.r[ol];
@@ -212,7 +233,17 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
             rflag[tid] = start ? (kept ? 2 : 1) : 0;
             double Vi[6] = {0, 0, 0, 0, 0, 0};
             bool elim = false;
-            if (kept) {
+            if (P.lmk_const) {
+                // SetParameterBlockConstant on every landmark (addSingleFrameResiduals, …Analytic.cpp:41-43): no columns, no
+                // elimination — with V^-1 = 0 and g_l = 0 the slot's Schur products reduce to H_f and Jp^T r, and the
+                // back-substitution leaves the landmark where it is
+                elim = true;
+#pragma unroll
+                for (int k = 0; k < 3; k++) g3[k] = 0.0;
+                double *ax = lmk_aux + (size_t)LMK_AUX * l;
+#pragma unroll
+                for (int k = 0; k < LMK_AUX; k++) ax[k] = 0.0;
+            } else if (kept) {
                 // kept (dense) landmark: its columns live in the reduced system, no elimination
                 const int ii[6] = {0, 1, 2, 1, 2, 2}, jj[6] = {0, 0, 0, 1, 1, 2};
                 for (int k = 0; k < 6; k++) atomicAdd(&Sb[(size_t)(dcl + ii[k]) * ld + dcl + jj[k]], h6[k]);
@@ -322,7 +353,7 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
             const int la = rbeg[r], lb = rbeg[r + 1];
             if (rflag[la] == 2) continue; // kept landmark: went straight to S
             const int t0 = sp[la], m = sp[la + 1] - t0;
-            const int ediag = 39 * m, etot = ediag + 18 * m * (m - 1);
+            const int ediag = 39 * m, etot = P.lmk_const ? ediag : ediag + 18 * m * (m - 1); // constant landmarks couple nothing
             // every landmark of a run has m slots: landmark q of the run starts m * FT_SD doubles after the previous one
             const int nrun = lb - la, lstride = m * FT_SD;
             const double *base0 = slotd + t0 * FT_SD;
@@ -404,7 +435,7 @@ __global__ void __launch_bounds__(FT, 3) k_backsub_cost(const DevProblem *__rest
             const int l = lA + li, s = s0 + tid;
             qa = P.slot_obs_ptr[s];
             qb = P.slot_obs_ptr[s + 1];
-            if (P.lmk_col[l] < 0) {
+            if (P.lmk_col[l] < 0 && !P.lmk_const) {
                 const int pcol = P.pose_col[P.slot_frame[s]];
                 if (pcol >= 0) { // a constant keyframe does not move: no contribution
                     double d[6], p[3];
@@ -473,9 +504,11 @@ __global__ void __launch_bounds__(FT, 3) k_backsub_cost(const DevProblem *__rest
                 ObsOperands<KIND> o;
                 load_obs<KIND>(P, ol, o);
                 const double *row = Bc.fct + (size_t)o.fc * FCT_ROW;
+                if (P.lmk_const && P.pose_col[o.fc / P.C] < 0) continue; // every block constant: part of fixed_cost, not of the cost
                 double r[2];
                 eval_residual<KIND>(row, P.K + 4 * (o.fc % P.C), o.w < 0.0 ? row[30] : o.w, p, o.meas, r);
-                cost += r[0] * r[0] + r[1] * r[1];
+                const double s2 = r[0] * r[0] + r[1] * r[1];
+                cost += P.huber_a > 0.0 ? huber_rho(P.huber_a, s2) : s2;
             }
         }
         __syncthreads();
@@ -510,9 +543,9 @@ template <int KIND> __global__ void __launch_bounds__(256) k_visual_cost(const D
     if (st->status != 0) return;
     const int b = which >= 0 ? which : (which == -1 ? st->cur : 1 - st->cur);
     const LinBuf &B = b ? B1 : B0;
-    __shared__ double red[8];
+    __shared__ double red[8], redf[8];
     const int Oloc = P.o1 - P.o0;
-    double cost = 0.0;
+    double cost = 0.0, fixed = 0.0;
     for (int ol = blockIdx.x * blockDim.x + threadIdx.x; ol < Oloc; ol += gridDim.x * blockDim.x) {
         ObsOperands<KIND> o;
         load_obs<KIND>(P, ol, o);
@@ -522,15 +555,27 @@ template <int KIND> __global__ void __launch_bounds__(256) k_visual_cost(const D
         const double *row = B.fct + (size_t)o.fc * FCT_ROW;
         double r[2];
         eval_residual<KIND>(row, P.K + 4 * (o.fc % P.C), o.w < 0.0 ? row[30] : o.w, p, o.meas, r);
-        cost += r[0] * r[0] + r[1] * r[1];
+        double s2 = r[0] * r[0] + r[1] * r[1];
+        if (P.huber_a > 0.0) s2 = huber_rho(P.huber_a, s2);
+        // constant landmark seen from a constant keyframe: the residual block has no free parameter block (Ceres fixed_cost)
+        if (P.lmk_const && P.pose_col[o.fc / P.C] < 0) fixed += s2;
+        else cost += s2;
     }
     cost = warp_sum(cost);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cost;
+    fixed = warp_sum(fixed);
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = cost;
+        redf[threadIdx.x >> 5] = fixed;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += red[i];
+        double s = 0, sf = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) {
+            s += red[i];
+            sf += redf[i];
+        }
         if (s != 0.0) atomicAdd(&acc->cost[b], 0.5 * s);
+        if (sf != 0.0 && which == 0) atomicAdd(&acc->fixed_cost, 0.5 * sf); // accumulated during the first linearisation only
     }
 }
 

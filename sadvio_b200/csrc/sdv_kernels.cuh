@@ -1311,7 +1311,7 @@ __global__ void __launch_bounds__(TS_THREADS) k_trisolve(const DevProblem *__res
 // =====================================================================================================================
 // LM control (Ceres 2.2 TrustRegionMinimizer + LevenbergMarquardtStrategy), single thread
 // =====================================================================================================================
-__global__ void k_ctrl_init(LMState *st, Accum *acc, SolverOpts opt) {
+__global__ void k_ctrl_init(const DevProblem *__restrict__ Pg, LMState *st, Accum *acc, SolverOpts opt) {
     // after the iteration-0 linearisation into buffer 0
     st->iter = 0;
     st->status = 0;
@@ -1338,14 +1338,14 @@ __global__ void k_ctrl_init(LMState *st, Accum *acc, SolverOpts opt) {
     acc->model_gd = acc->model_dd = acc->step_norm2 = acc->cand_norm2 = 0.0;
     acc->grad_max_bits = 0ull;
     acc->schur_fail = acc->chol_fail = 0;
-    if (opt.max_num_iterations <= 0) st->status = 1 + 0;
+    if ((Pg->max_iter > 0 ? Pg->max_iter : opt.max_num_iterations) <= 0) st->status = 1 + 0;
     else st->iter = 1; // Ceres bumps its iteration counter before computing the step (was a kernel of its own)
 }
 
-SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt);
+SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt, int max_iter);
 // One warp: the solver state (1.8 KB) and the accumulators are staged through shared memory with coalesced loads / stores, the
 // control logic itself runs on lane 0 — a single thread walking the structures in global memory took 5.5 us per iteration.
-__global__ void __launch_bounds__(32) k_ctrl(LMState *st_g, Accum *acc_g, SolverOpts opt, unsigned long long cond) {
+__global__ void __launch_bounds__(32) k_ctrl(const DevProblem *__restrict__ Pg, LMState *st_g, Accum *acc_g, SolverOpts opt, unsigned long long cond) {
     // `cond` (0 = none) is the handle of the CUDA-graph WHILE node whose body is one LM iteration
     __shared__ LMState st_s;
     __shared__ Accum acc_s;
@@ -1365,7 +1365,7 @@ __global__ void __launch_bounds__(32) k_ctrl(LMState *st_g, Accum *acc_g, Solver
     }
     __syncwarp();
     if (lane == 0) {
-        ctrl_step(&st_s, &acc_s, opt);
+        ctrl_step(&st_s, &acc_s, opt, Pg->max_iter > 0 ? Pg->max_iter : opt.max_num_iterations); // per-window cap: 10 / 5 in the f2 solves (AOptimizer.cpp:113,166,247)
         if (cond) cudaGraphSetConditional((cudaGraphConditionalHandle)cond, st_s.status == 0 ? 1u : 0u);
     }
     __syncwarp();
@@ -1379,7 +1379,7 @@ __global__ void __launch_bounds__(32) k_ctrl(LMState *st_g, Accum *acc_g, Solver
     }
 }
 
-SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt) {
+SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt, int max_iter) {
     const int it = st->iter;
     const int ti = it < 63 ? it : 63;
     const int cand = 1 - st->cur;
@@ -1450,7 +1450,7 @@ SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt) {
     }
     // FinalizeIterationAndCheckIfMinimizerCanContinue for the next trip
     if (st->status == 0) {
-        if (it >= opt.max_num_iterations) st->status = 1 + 0;
+        if (it >= max_iter) st->status = 1 + 0;
         else if (st->radius <= opt.min_radius) st->status = 1 + 4;
     }
     // reset accumulators for the next iteration

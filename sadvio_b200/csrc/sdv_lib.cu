@@ -817,8 +817,12 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
             make_dense(sp->l2l_b[k]);
         }
     }
-    if (n == 0) return fail(h, SDV_ERR_UNSUPPORTED, "window has no free frame parameter (pure landmark refinement is landmarkOptimization, not this entry point)");
-    const int n_pad = (n + 31) / 32 * 32, ld = n_pad;
+    // n == 0: every keyframe constant — landmarkOptimization (AOptimizer.cpp:98-150): the reduced system is one block of padding
+    // (identity), every landmark is a 3x3 problem and they all share ONE trust region
+    if (n == 0 && (L == 0 || w->landmarks_constant)) return fail(h, SDV_ERR_INVALID_ARGUMENT, "window has no free parameter block");
+    if (w->landmarks_constant && (dp || sp)) return fail(h, SDV_ERR_UNSUPPORTED, "landmarks_constant with a marginalisation prior (the single-frame solves carry none)");
+    if (w->visual_loss_huber_a < 0.0 || w->max_num_iterations < 0) return fail(h, SDV_ERR_INVALID_ARGUMENT, "negative Huber parameter or iteration cap");
+    const int n_pad = std::max(32, (n + 31) / 32 * 32), ld = n_pad;
 
     auto t_s1 = std::chrono::steady_clock::now();
     // ---- landmark shard of this rank (contiguous, balanced by observation count)
@@ -1367,6 +1371,9 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         P.mp_H = at<double>(sb, s_mH); P.mp_g0 = at<double>(sb, s_mg);
     }
     P.Ocap = Ocap;
+    P.lmk_const = w->landmarks_constant ? 1 : 0;
+    P.max_iter = w->max_num_iterations;
+    P.huber_a = w->visual_loss_huber_a;
     if (sp) {
         P.sp_has_imu = sp->has_imu_prior ? 1 : 0;
         P.sp_frame = sp->frame;
@@ -1773,7 +1780,7 @@ int launch_iteration(sdv_handle *h) {
     }
     int rc = reduce_scalars(h, -2);
     if (rc != SDV_OK) return rc;
-    k_ctrl<<<1, 32, 0, s>>>(h->d_st, h->d_acc, h->opt, h->cond);
+    k_ctrl<<<1, 32, 0, s>>>(h->d_P, h->d_st, h->d_acc, h->opt, h->cond);
     h->launches++;
     return SDV_OK;
 }
@@ -1791,7 +1798,7 @@ int enqueue_prologue(sdv_handle *h) {
     launch_linearize(h, 0, false);
     int rc = reduce_scalars(h, 0);
     if (rc != SDV_OK) return rc;
-    k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
+    k_ctrl_init<<<1, 1, 0, s>>>(h->d_P, h->d_st, h->d_acc, h->opt);
     h->launches++;
     return SDV_OK;
 }
@@ -1948,7 +1955,7 @@ int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
         // as many as the previous solve took, then the status is read, then one more at a time.  A steady back end pays one
         // host round trip per solve instead of one per iteration.
         int *h_status = reinterpret_cast<int *>(h->h_rb);
-        const int max_it = h->opt.max_num_iterations + 1;
+        const int max_it = (P.max_iter > 0 ? P.max_iter : h->opt.max_num_iterations) + 1;
         int it = 0, ahead = std::max(1, std::min(h->last_iters, max_it));
         while (it < max_it) {
             for (int q = 0; q < ahead && it < max_it; q++, it++) {
@@ -2215,7 +2222,7 @@ int sdv_time_kernel(sdv_handle *h, int32_t which, int32_t repeats, double *ms_pe
     CK(cudaMemsetAsync(h->B[1].xl, 0, sizeof(double) * 3 * std::max(P.L, 1), s));
     k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, 1);
     launch_linearize(h, 0, true);
-    k_ctrl_init<<<1, 1, 0, s>>>(h->d_st, h->d_acc, h->opt);
+    k_ctrl_init<<<1, 1, 0, s>>>(h->d_P, h->d_st, h->d_acc, h->opt);
     CK(cudaStreamSynchronize(s));
     // which + 10: COLD variant — a 256 MiB write (twice the 126 MB L2) between launches, and for the materialising kernel the
     // two linearisation buffers alternate, so neither inputs nor outputs of the previous launch are L2-resident

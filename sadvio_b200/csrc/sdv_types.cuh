@@ -69,6 +69,10 @@ struct DevProblem {
     int rank, world;
     int fct_in_smem; // stage the frame-camera table in shared memory
     int Ocap;        // stride of the r / J planes of this rank: real observations + 2 pseudo-observations per PoseToLandmark factor
+    // the other AOptimizer solves as masks of the window solve (sdv_window::visual_loss_huber_a / landmarks_constant / max_num_iterations)
+    int lmk_const;   // every landmark block is constant (single-frame solves): no elimination, no landmark update
+    int max_iter;    // > 0: iteration cap of this window (overrides SolverOpts::max_num_iterations)
+    double huber_a;  // > 0: ceres::HuberLoss(a) + Corrector on every visual residual block
     // frames
     const double *T_f_w, *v, *ba, *bg;
     const unsigned char *has_prior;

@@ -2,7 +2,9 @@
 // tests/test_host_adapter.py), rebuilds the graph with shared_ptr / weak_ptr objects exactly as SaDVIO holds it,
 // and either prints the flattened window ("flatten": indices only, "dump": every array of the sdv_window) or runs
 // localMapVIOptimization / localMapBA through the C ABI and prints the updated state ("solve"), or applies a synthetic
-// solution with the write-back alone ("writeback", no GPU).  An optional trailing
+// solution with the write-back alone ("writeback", no GPU).  "dump_lmkopt" / "dump_single" / "dump_singlevi" print the window
+// of landmarkOptimization / singleFrameOptimization / singleFrameVIOptimization(frame), "lmkopt" / "single" / "singlevi" run
+// them (frame = argv[5], a position in the file).  An optional trailing
 // section describes the isae::Marginalization object the optimizer holds (dense or sparsified prior).
 #include "b200_optimizer.hpp"
 
@@ -27,6 +29,7 @@ int main(int argc, char **argv) {
     bool vio = std::atoi(argv[2]) != 0;
     size_t fixed = (size_t)std::atoi(argv[3]);
     int kind = argc > 4 ? std::atoi(argv[4]) : 0;
+    int f2_frame = argc > 5 ? std::atoi(argv[5]) : 0;
     std::istream &in = std::cin;
     int NF;
     in >> NF;
@@ -80,7 +83,11 @@ int main(int argc, char **argv) {
             in >> alive;
             ft->sensor = all_frames[fi]->sensors[si];
             lm->features.push_back(ft);
-            if (alive) keep_alive.push_back(ft); // a dead weak_ptr models a feature whose frame was dropped
+            if (alive) {
+                keep_alive.push_back(ft); // a dead weak_ptr models a feature whose frame was dropped
+                auto &cloud = all_frames[fi]->pointxd; // frame->getLandmarks()["pointxd"]: the landmarks the frame observes
+                if (cloud.empty() || cloud.back() != lm) cloud.push_back(lm);
+            }
         }
         map->pointxd.push_back(lm);
     }
@@ -137,12 +144,10 @@ int main(int argc, char **argv) {
     poisoned:;
     }
     std::printf("%s\n", mode.c_str());
-    if (mode == "dump") {
-        FlatWindow fw;
-        bool ok = flatten(*map, fixed, vio, kind, fw, marg.get(), sparsif);
+    auto dump_view = [](const FlatWindow &fw, bool ok) {
         const sdv_window &w = fw.view;
         std::printf("ok %d\n", ok ? 1 : 0);
-        if (!ok) return 0;
+        if (!ok) return;
         auto pd = [](const char *name, const double *a, size_t n) {
             std::printf("%s %zu", name, a ? n : 0);
             for (size_t i = 0; a && i < n; i++) std::printf(" %.17g", a[i]);
@@ -160,11 +165,12 @@ int main(int argc, char **argv) {
         };
         const size_t F = w.n_frames, C = w.n_cams, L = w.n_lmks, O = w.n_obs, P = w.n_imu;
         std::printf("dims 8 %d %d %d %d %d %d %d %d\n", w.vio, w.factor_kind, w.n_frames, w.n_fixed, w.n_cams, w.n_lmks, w.n_obs, w.n_imu);
+        std::printf("masks 3 %.17g %d %d\n", w.visual_loss_huber_a, w.landmarks_constant, w.max_num_iterations);
         pd("T_f_w", w.T_f_w, 12 * F); pd("v", w.v, 3 * F); pd("ba", w.ba, 3 * F); pd("bg", w.bg, 3 * F);
         pu("has_imu", w.has_imu, F); pu("has_prior", w.has_prior, F); pd("T_prior", w.T_prior, 12 * F); pd("inf_prior", w.inf_prior, 6 * F);
         pd("T_s_f", w.T_s_f, 12 * C); pd("K", w.K, 4 * C); pd("lmk_t", w.lmk_t, 3 * L);
         pi("obs_lmk", w.obs_lmk, O); pi("obs_frame", w.obs_frame, O); pi("obs_cam", w.obs_cam, O);
-        pd("obs_bearing", w.obs_bearing, 3 * O); pd("obs_uv", w.obs_uv, 2 * O);
+        pd("obs_bearing", w.obs_bearing, 3 * O); pd("obs_uv", w.obs_uv, 2 * O); pd("obs_sigma", w.obs_sigma, O);
         pi("imu_i", w.imu_i, P); pi("imu_j", w.imu_j, P); pd("imu_dt", w.imu_dt, P); pd("imu_dR", w.imu_dR, 9 * P);
         pd("imu_dv", w.imu_dv, 3 * P); pd("imu_dp", w.imu_dp, 3 * P); pd("imu_cov", w.imu_cov, 81 * P);
         pd("imu_J_dR_bg", w.imu_J_dR_bg, 9 * P); pd("imu_J_dv_ba", w.imu_J_dv_ba, 9 * P); pd("imu_J_dv_bg", w.imu_J_dv_bg, 9 * P);
@@ -186,6 +192,24 @@ int main(int argc, char **argv) {
             pi("sp_l2l_a", q.l2l_a, q.n_l2l); pi("sp_l2l_b", q.l2l_b, q.n_l2l); pd("sp_l2l_delta", q.l2l_delta, 3 * (size_t)q.n_l2l);
             pd("sp_l2l_sqrt_inf", q.l2l_sqrt_inf, 9 * (size_t)q.n_l2l);
         }
+    };
+    if (mode == "dump") {
+        FlatWindow fw;
+        bool ok = flatten(*map, fixed, vio, kind, fw, marg.get(), sparsif);
+        dump_view(fw, ok);
+        return 0;
+    }
+    if (mode == "dump_lmkopt" || mode == "dump_single" || mode == "dump_singlevi") {
+        FlatWindow fw;
+        if (mode == "dump_lmkopt") flatten_landmark_cloud(*all_frames[f2_frame], kind, fw);
+        else flatten_single_frame(all_frames[f2_frame], mode == "dump_singlevi", kind, fw);
+        dump_view(fw, true);
+        // the frames of the sub-window as positions in the file (the Python mirror works with window indices)
+        std::printf("frames %zu", fw.frame_vector.size());
+        for (auto &fr : fw.frame_vector)
+            for (int f = 0; f < NF; f++)
+                if (all_frames[f] == fr) std::printf(" %d", f);
+        std::printf("\n");
         return 0;
     }
     if (mode == "flatten") {
@@ -214,6 +238,11 @@ int main(int argc, char **argv) {
         d.dlmk = d.dbg + 3 * F;
         write_back(fw, d, vio);
         std::printf("1 0\n");
+    } else if (mode == "lmkopt" || mode == "single" || mode == "singlevi") {
+        B200Optimizer opt(kind, 0);
+        bool ok = mode == "lmkopt" ? opt.landmarkOptimization(all_frames[f2_frame])
+                                   : (mode == "single" ? opt.singleFrameOptimization(all_frames[f2_frame]) : opt.singleFrameVIOptimization(all_frames[f2_frame]));
+        std::printf("%d %d\n", ok ? 1 : 0, opt.lastStats().iterations);
     } else {
         B200Optimizer opt(kind, 0);
         opt._marginalization = marg;
@@ -233,6 +262,6 @@ int main(int argc, char **argv) {
         }
         std::printf("\n");
     }
-    for (auto &lm : map->pointxd) std::printf("%.17g %.17g %.17g\n", lm->t_w[0], lm->t_w[1], lm->t_w[2]);
+    for (auto &lm : map->pointxd) std::printf("%.17g %.17g %.17g %d\n", lm->t_w[0], lm->t_w[1], lm->t_w[2], lm->outlier ? 1 : 0);
     return 0;
 }

@@ -1,8 +1,11 @@
-// Host-side C++ adapter above the C ABI (include/sdv.h): mirrors the reference optimizer interface for the two entry
+// Host-side C++ adapter above the C ABI (include/sdv.h): mirrors the reference optimizer interface for the entry
 // points this repository replaces,
 //     bool isae::AOptimizer::localMapBA(std::shared_ptr<LocalMap>&, size_t fixed_frame_number = 0)
 //     bool isae::AOptimizer::localMapVIOptimization(std::shared_ptr<LocalMap>&, size_t fixed_frame_number = 0)
-// (reference cpp/include/isaeslam/optimizers/AOptimizer.h:28-30), same argument meaning and error behaviour
+//     bool isae::AOptimizer::landmarkOptimization(std::shared_ptr<Frame>&)          (masks of the window solve)
+//     bool isae::AOptimizer::singleFrameOptimization(std::shared_ptr<Frame>&)
+//     bool isae::AOptimizer::singleFrameVIOptimization(std::shared_ptr<Frame>&)
+// (reference cpp/include/isaeslam/optimizers/AOptimizer.h:22-30), same argument meaning and error behaviour
 // (bool, no exceptions; when no solve could run — no device, malformed window — the state is left untouched and the call
 // returns false; a solve that ends in Ceres' FAILURE termination writes back and returns true like the reference).
 //
@@ -58,6 +61,7 @@ struct Frame { // isae::Frame
     std::array<double, 6> inf_prior{};
     std::vector<std::shared_ptr<ImageSensor>> sensors;
     std::shared_ptr<IMU> imu; // getIMU(), may be null
+    std::vector<std::shared_ptr<Landmark>> pointxd; // getLandmarks()["pointxd"]: the landmarks this frame observes
     bool isKeyFrame() const { return keyframe; }
 };
 
@@ -65,6 +69,7 @@ struct Feature { // isae::AFeature
     std::weak_ptr<ImageSensor> sensor;
     std::array<double, 3> bearing{}; // getBearingVectors().at(0)
     std::array<double, 2> uv{};      // getPoints().at(0)
+    double sigma = 1.0;              // getSigma()
 };
 
 struct Landmark { // isae::ALandmark ("pointxd")
@@ -73,6 +78,7 @@ struct Landmark { // isae::ALandmark ("pointxd")
     std::vector<std::weak_ptr<Feature>> features; // getFeatures()
     bool isInitialized() const { return initialized; }
     bool isOutlier() const { return outlier; }
+    inline bool sanityCheck(); // ALandmark.cpp:130-147 (defined below)
 };
 
 struct LocalMap { // isae::LocalMap
@@ -106,7 +112,7 @@ struct Marginalization {
 
 // Structure-of-arrays image of one window + the bookkeeping needed for the write-back.
 struct FlatWindow {
-    std::vector<double> T_f_w, v, ba, bg, T_prior, inf_prior, T_s_f, K, lmk_t, obs_bearing, obs_uv;
+    std::vector<double> T_f_w, v, ba, bg, T_prior, inf_prior, T_s_f, K, lmk_t, obs_bearing, obs_uv, obs_sigma;
     std::vector<uint8_t> has_imu, has_prior;
     std::vector<int32_t> obs_lmk, obs_frame, obs_cam, imu_i, imu_j;
     std::vector<double> imu_dt, imu_dR, imu_dv, imu_dp, imu_cov, J_dR_bg, J_dv_ba, J_dv_bg, J_dp_ba, J_dp_bg, sigma_ba, sigma_bg;
@@ -124,6 +130,90 @@ struct FlatWindow {
     sdv_window view{};
 };
 
+namespace detail {
+// distinct sensor models -> camera table
+inline int cam_of(FlatWindow &fw, const ImageSensor &s) {
+    for (size_t c = 0; c * 12 < fw.T_s_f.size(); c++)
+        if (std::memcmp(&fw.T_s_f[12 * c], s.T_s_f.data(), 96) == 0 && std::memcmp(&fw.K[4 * c], s.K.data(), 32) == 0) return (int)c;
+    fw.T_s_f.insert(fw.T_s_f.end(), s.T_s_f.begin(), s.T_s_f.end());
+    fw.K.insert(fw.K.end(), s.K.begin(), s.K.end());
+    return (int)(fw.K.size() / 4 - 1);
+}
+// per-frame arrays of one frame (the caller appends it to frame_vector)
+inline void push_frame_state(FlatWindow &fw, const Frame &f, bool with_prior) {
+    fw.T_f_w.insert(fw.T_f_w.end(), f.T_f_w.begin(), f.T_f_w.end());
+    fw.has_prior.push_back(with_prior && f.has_prior ? 1 : 0); // …Analytic.cpp:239
+    fw.T_prior.insert(fw.T_prior.end(), f.T_prior.begin(), f.T_prior.end());
+    fw.inf_prior.insert(fw.inf_prior.end(), f.inf_prior.begin(), f.inf_prior.end());
+    const IMU *imu = f.imu.get();
+    fw.has_imu.push_back(imu ? 1 : 0);
+    for (int k = 0; k < 3; k++) {
+        fw.v.push_back(imu ? imu->v[k] : 0.0);
+        fw.ba.push_back(imu ? imu->ba[k] : 0.0);
+        fw.bg.push_back(imu ? imu->bg[k] : 0.0);
+    }
+    for (auto &s : f.sensors) cam_of(fw, *s);
+}
+// IMUFactor + IMUBiasFactor list of addIMUResiduals (AOptimizer.cpp:55-94) over fw.frame_vector
+inline void imu_factors(FlatWindow &fw, const std::unordered_map<const Frame *, int> &frame_idx) {
+    const int F = (int)fw.frame_vector.size();
+    for (int i = 0; i < F; i++) {
+        const std::shared_ptr<Frame> &framej = fw.frame_vector[i];
+        if (!framej->imu) continue;                                   // :60
+        std::shared_ptr<Frame> framei = framej->imu->last_kf;         // :62
+        if (!framei) continue;                                        // :65
+        if ((double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9 > 1) continue; // :69
+        auto it = frame_idx.find(framei.get());
+        if (it == frame_idx.end() || !framei->imu || framei == framej) continue; // :72
+        const IMU &m = *framej->imu;
+        fw.imu_i.push_back(it->second);
+        fw.imu_j.push_back(i);
+        fw.imu_dt.push_back((double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9);
+        fw.imu_dR.insert(fw.imu_dR.end(), m.delta_R.begin(), m.delta_R.end());
+        fw.imu_dv.insert(fw.imu_dv.end(), m.delta_v.begin(), m.delta_v.end());
+        fw.imu_dp.insert(fw.imu_dp.end(), m.delta_p.begin(), m.delta_p.end());
+        fw.imu_cov.insert(fw.imu_cov.end(), m.Sigma.begin(), m.Sigma.end());
+        fw.J_dR_bg.insert(fw.J_dR_bg.end(), m.J_dR_bg.begin(), m.J_dR_bg.end());
+        fw.J_dv_ba.insert(fw.J_dv_ba.end(), m.J_dv_ba.begin(), m.J_dv_ba.end());
+        fw.J_dv_bg.insert(fw.J_dv_bg.end(), m.J_dv_bg.begin(), m.J_dv_bg.end());
+        fw.J_dp_ba.insert(fw.J_dp_ba.end(), m.J_dp_ba.begin(), m.J_dp_ba.end());
+        fw.J_dp_bg.insert(fw.J_dp_bg.end(), m.J_dp_bg.begin(), m.J_dp_bg.end());
+        fw.sigma_ba.push_back(framei->imu->bacc_noise); // residuals.hpp:259 reads imu_i's config
+        fw.sigma_bg.push_back(framei->imu->bgyr_noise); // residuals.hpp:261
+        fw.imu_frame_j.push_back(framej);
+    }
+}
+// the sdv_window view over the arrays of fw
+inline void fill_view(FlatWindow &fw, bool vio, int factor_kind, size_t fixed_frame_number, bool have_dense, bool have_sparse) {
+    sdv_window &w = fw.view;
+    std::memset(&w, 0, sizeof(w));
+    w.abi_version = SDV_ABI_VERSION;
+    w.vio = vio ? 1 : 0;
+    w.factor_kind = factor_kind;
+    w.n_frames = (int32_t)fw.frame_vector.size();
+    w.n_fixed = (int32_t)fixed_frame_number;
+    w.n_cams = (int32_t)(fw.K.size() / 4);
+    w.n_lmks = (int32_t)fw.landmarks.size();
+    w.n_obs = (int32_t)fw.obs_lmk.size();
+    w.n_imu = (int32_t)fw.imu_i.size();
+    w.T_f_w = fw.T_f_w.data();
+    w.v = fw.v.data(); w.ba = fw.ba.data(); w.bg = fw.bg.data();
+    w.has_imu = fw.has_imu.data(); w.has_prior = fw.has_prior.data();
+    w.T_prior = fw.T_prior.data(); w.inf_prior = fw.inf_prior.data();
+    w.T_s_f = fw.T_s_f.data(); w.K = fw.K.data(); w.lmk_t = fw.lmk_t.data();
+    w.obs_lmk = fw.obs_lmk.data(); w.obs_frame = fw.obs_frame.data(); w.obs_cam = fw.obs_cam.data();
+    w.obs_bearing = fw.obs_bearing.data(); w.obs_uv = fw.obs_uv.data();
+    w.obs_sigma = fw.obs_sigma.empty() ? nullptr : fw.obs_sigma.data();
+    w.imu_i = fw.imu_i.data(); w.imu_j = fw.imu_j.data(); w.imu_dt = fw.imu_dt.data();
+    w.imu_dR = fw.imu_dR.data(); w.imu_dv = fw.imu_dv.data(); w.imu_dp = fw.imu_dp.data(); w.imu_cov = fw.imu_cov.data();
+    w.imu_J_dR_bg = fw.J_dR_bg.data(); w.imu_J_dv_ba = fw.J_dv_ba.data(); w.imu_J_dv_bg = fw.J_dv_bg.data();
+    w.imu_J_dp_ba = fw.J_dp_ba.data(); w.imu_J_dp_bg = fw.J_dp_bg.data();
+    w.imu_sigma_ba = fw.sigma_ba.data(); w.imu_sigma_bg = fw.sigma_bg.data();
+    w.dense_prior = have_dense ? &fw.dense : nullptr;
+    w.sparse_prior = have_sparse ? &fw.sparse : nullptr;
+}
+} // namespace detail
+
 // Returns false where the reference would throw out of an unordered_map::at (a prior that names a frame outside the
 // window, or a sparsified prior with missing per-landmark entries): the caller maps that to `false`, state untouched.
 inline bool flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, int factor_kind, FlatWindow &fw,
@@ -133,29 +223,8 @@ inline bool flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
     const int F = (int)fw.frame_vector.size();
     std::unordered_map<const Frame *, int> frame_idx; // _map_frame_posepar (…Analytic.cpp:224-226)
     for (int i = 0; i < F; i++) frame_idx[fw.frame_vector[i].get()] = i;
-    // distinct sensor models -> camera table
-    auto cam_of = [&](const ImageSensor &s) {
-        for (size_t c = 0; c * 12 < fw.T_s_f.size(); c++)
-            if (std::memcmp(&fw.T_s_f[12 * c], s.T_s_f.data(), 96) == 0 && std::memcmp(&fw.K[4 * c], s.K.data(), 32) == 0) return (int)c;
-        fw.T_s_f.insert(fw.T_s_f.end(), s.T_s_f.begin(), s.T_s_f.end());
-        fw.K.insert(fw.K.end(), s.K.begin(), s.K.end());
-        return (int)(fw.K.size() / 4 - 1);
-    };
-    for (int i = 0; i < F; i++) {
-        const Frame &f = *fw.frame_vector[i];
-        fw.T_f_w.insert(fw.T_f_w.end(), f.T_f_w.begin(), f.T_f_w.end());
-        fw.has_prior.push_back(f.has_prior ? 1 : 0); // …Analytic.cpp:239
-        fw.T_prior.insert(fw.T_prior.end(), f.T_prior.begin(), f.T_prior.end());
-        fw.inf_prior.insert(fw.inf_prior.end(), f.inf_prior.begin(), f.inf_prior.end());
-        const IMU *imu = f.imu.get();
-        fw.has_imu.push_back(imu ? 1 : 0);
-        for (int k = 0; k < 3; k++) {
-            fw.v.push_back(imu ? imu->v[k] : 0.0);
-            fw.ba.push_back(imu ? imu->ba[k] : 0.0);
-            fw.bg.push_back(imu ? imu->bg[k] : 0.0);
-        }
-        for (auto &s : f.sensors) cam_of(*s);
-    }
+    auto cam_of = [&](const ImageSensor &s) { return detail::cam_of(fw, s); };
+    for (int i = 0; i < F; i++) detail::push_frame_state(fw, *fw.frame_vector[i], true);
     // landmarks + visual residual blocks in reference walk order (…Analytic.cpp:247-289)
     std::unordered_map<const Landmark *, int> lmk_idx; // _map_lmk_ptpar
     for (auto &landmark : map.pointxd) {
@@ -180,31 +249,7 @@ inline bool flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
     }
     // IMU factors (AOptimizer.cpp:55-94)
     if (vio) {
-        for (int i = 0; i < F; i++) {
-            const std::shared_ptr<Frame> &framej = fw.frame_vector[i];
-            if (!framej->imu) continue;                                   // :60
-            std::shared_ptr<Frame> framei = framej->imu->last_kf;         // :62
-            if (!framei) continue;                                        // :65
-            if ((double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9 > 1) continue; // :69
-            auto it = frame_idx.find(framei.get());
-            if (it == frame_idx.end() || !framei->imu || framei == framej) continue; // :72
-            const IMU &m = *framej->imu;
-            fw.imu_i.push_back(it->second);
-            fw.imu_j.push_back(i);
-            fw.imu_dt.push_back((double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9);
-            fw.imu_dR.insert(fw.imu_dR.end(), m.delta_R.begin(), m.delta_R.end());
-            fw.imu_dv.insert(fw.imu_dv.end(), m.delta_v.begin(), m.delta_v.end());
-            fw.imu_dp.insert(fw.imu_dp.end(), m.delta_p.begin(), m.delta_p.end());
-            fw.imu_cov.insert(fw.imu_cov.end(), m.Sigma.begin(), m.Sigma.end());
-            fw.J_dR_bg.insert(fw.J_dR_bg.end(), m.J_dR_bg.begin(), m.J_dR_bg.end());
-            fw.J_dv_ba.insert(fw.J_dv_ba.end(), m.J_dv_ba.begin(), m.J_dv_ba.end());
-            fw.J_dv_bg.insert(fw.J_dv_bg.end(), m.J_dv_bg.begin(), m.J_dv_bg.end());
-            fw.J_dp_ba.insert(fw.J_dp_ba.end(), m.J_dp_ba.begin(), m.J_dp_ba.end());
-            fw.J_dp_bg.insert(fw.J_dp_bg.end(), m.J_dp_bg.begin(), m.J_dp_bg.end());
-            fw.sigma_ba.push_back(framei->imu->bacc_noise); // residuals.hpp:259 reads imu_i's config
-            fw.sigma_bg.push_back(framei->imu->bgyr_noise); // residuals.hpp:261
-            fw.imu_frame_j.push_back(framej);
-        }
+        detail::imu_factors(fw, frame_idx);
         for (int i = 0; i < F; i++) { // AOptimizer.cpp:421-434
             const std::shared_ptr<Frame> &frame = fw.frame_vector[i];
             if (!frame->imu || !frame->imu->last_kf) continue;            // :422-426
@@ -312,31 +357,7 @@ inline bool flatten(const LocalMap &map, size_t fixed_frame_number, bool vio, in
             sp.l2l_a = fw.l2l_a.data(); sp.l2l_b = fw.l2l_b.data(); sp.l2l_delta = fw.l2l_delta.data(); sp.l2l_sqrt_inf = fw.l2l_sqrt_inf.data();
         }
     }
-    sdv_window &w = fw.view;
-    std::memset(&w, 0, sizeof(w));
-    w.abi_version = SDV_ABI_VERSION;
-    w.vio = vio ? 1 : 0;
-    w.factor_kind = factor_kind;
-    w.n_frames = F;
-    w.n_fixed = (int32_t)fixed_frame_number;
-    w.n_cams = (int32_t)(fw.K.size() / 4);
-    w.n_lmks = (int32_t)fw.landmarks.size();
-    w.n_obs = (int32_t)fw.obs_lmk.size();
-    w.n_imu = (int32_t)fw.imu_i.size();
-    w.T_f_w = fw.T_f_w.data();
-    w.v = fw.v.data(); w.ba = fw.ba.data(); w.bg = fw.bg.data();
-    w.has_imu = fw.has_imu.data(); w.has_prior = fw.has_prior.data();
-    w.T_prior = fw.T_prior.data(); w.inf_prior = fw.inf_prior.data();
-    w.T_s_f = fw.T_s_f.data(); w.K = fw.K.data(); w.lmk_t = fw.lmk_t.data();
-    w.obs_lmk = fw.obs_lmk.data(); w.obs_frame = fw.obs_frame.data(); w.obs_cam = fw.obs_cam.data();
-    w.obs_bearing = fw.obs_bearing.data(); w.obs_uv = fw.obs_uv.data();
-    w.imu_i = fw.imu_i.data(); w.imu_j = fw.imu_j.data(); w.imu_dt = fw.imu_dt.data();
-    w.imu_dR = fw.imu_dR.data(); w.imu_dv = fw.imu_dv.data(); w.imu_dp = fw.imu_dp.data(); w.imu_cov = fw.imu_cov.data();
-    w.imu_J_dR_bg = fw.J_dR_bg.data(); w.imu_J_dv_ba = fw.J_dv_ba.data(); w.imu_J_dv_bg = fw.J_dv_bg.data();
-    w.imu_J_dp_ba = fw.J_dp_ba.data(); w.imu_J_dp_bg = fw.J_dp_bg.data();
-    w.imu_sigma_ba = fw.sigma_ba.data(); w.imu_sigma_bg = fw.sigma_bg.data();
-    w.dense_prior = have_dense ? &fw.dense : nullptr;
-    w.sparse_prior = have_sparse ? &fw.sparse : nullptr;
+    detail::fill_view(fw, vio, factor_kind, fixed_frame_number, have_dense, have_sparse);
     return true;
 }
 
@@ -408,6 +429,120 @@ inline void write_back(FlatWindow &fw, const sdv_delta &d, bool vio) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The other three visual solves of AOptimizer as masks of the window solve (include/sdv.h, the
+// table under sdv_window).
+// ---------------------------------------------------------------------------------------------------------------------
+
+// ALandmark::sanityCheck (ALandmark.cpp:130-147): fewer than two features -> outlier; average over the features of the mean
+// squared pixel error / sigma^2 (chi2err, :98-116; 1000 when Camera::project fails, Camera.cpp:27-52) above 2 -> outlier.
+inline bool Landmark::sanityCheck() {
+    if (features.size() < 2) {
+        outlier = true;
+        return false;
+    }
+    double mean = 0.0;
+    for (auto &wf : features) {
+        double chi2 = 1000.0;
+        std::shared_ptr<Feature> f = wf.lock();
+        std::shared_ptr<ImageSensor> cam = f ? f->sensor.lock() : nullptr;
+        std::shared_ptr<Frame> fr = cam ? cam->getFrame() : nullptr;
+        if (fr) {
+            double pf[3], pc[3];
+            for (int i = 0; i < 3; i++) pf[i] = fr->T_f_w[4 * i] * t_w[0] + fr->T_f_w[4 * i + 1] * t_w[1] + fr->T_f_w[4 * i + 2] * t_w[2] + fr->T_f_w[4 * i + 3];
+            for (int i = 0; i < 3; i++) pc[i] = cam->T_s_f[4 * i] * pf[0] + cam->T_s_f[4 * i + 1] * pf[1] + cam->T_s_f[4 * i + 2] * pf[2] + cam->T_s_f[4 * i + 3];
+            const double u = (cam->K[0] * pc[0] + cam->K[2] * pc[2]) / pc[2], v = (cam->K[1] * pc[1] + cam->K[3] * pc[2]) / pc[2];
+            const bool ok = !(pc[2] < 0.1) && !(u < 0 || v < 0 || u > 2 * cam->K[2] || v > 2 * cam->K[3]) && std::isfinite(u) && std::isfinite(v);
+            if (ok) {
+                const double e0 = (u - f->uv[0]) / f->sigma, e1 = (v - f->uv[1]) / f->sigma;
+                chi2 = e0 * e0 + e1 * e1;
+            }
+        }
+        mean += chi2;
+    }
+    outlier = mean / (double)features.size() > 2.0;
+    return !outlier;
+}
+
+// landmarkOptimization(frame): addLandmarkResiduals (AngularAdjustmentCERESAnalytic.cpp:106-209) — a parameter block per
+// initialised inlier landmark of frame->getLandmarks(), one visual block per live feature on ANY keyframe, every pose block
+// constant (:141-145), sigma 1.5 / focal (:152).  Frames enter frame_vector in first-appearance order.
+inline void flatten_landmark_cloud(const Frame &frame, int factor_kind, FlatWindow &fw) {
+    fw = FlatWindow();
+    std::unordered_map<const Frame *, int> frame_idx;
+    for (auto &landmark : frame.pointxd) {
+        if (!landmark->isInitialized() || landmark->isOutlier()) continue; // :117
+        const int l = (int)fw.landmarks.size();
+        fw.landmarks.push_back(landmark);
+        fw.lmk_t.insert(fw.lmk_t.end(), landmark->t_w.begin(), landmark->t_w.end());
+        for (auto &wfeature : landmark->features) {
+            std::shared_ptr<Feature> feature = wfeature.lock();
+            if (!feature) continue; // (the reference dereferences before it tests, :129-134: an expired feature is undefined behaviour there)
+            std::shared_ptr<ImageSensor> cam = feature->sensor.lock();
+            std::shared_ptr<Frame> fr = cam ? cam->getFrame() : nullptr;
+            if (!fr || !fr->isKeyFrame()) continue; // :134
+            auto it = frame_idx.find(fr.get());
+            if (it == frame_idx.end()) { // :138-142
+                it = frame_idx.emplace(fr.get(), (int)fw.frame_vector.size()).first;
+                fw.frame_vector.push_back(fr);
+                detail::push_frame_state(fw, *fr, false);
+            }
+            fw.obs_lmk.push_back(l);
+            fw.obs_frame.push_back(it->second);
+            fw.obs_cam.push_back(detail::cam_of(fw, *cam));
+            fw.obs_bearing.insert(fw.obs_bearing.end(), feature->bearing.begin(), feature->bearing.end());
+            fw.obs_uv.insert(fw.obs_uv.end(), feature->uv.begin(), feature->uv.end());
+        }
+    }
+    detail::fill_view(fw, false, factor_kind, fw.frame_vector.size(), false, false); // n_fixed = n_frames: every pose constant
+    fw.view.visual_loss_huber_a = std::sqrt(1.345); // AOptimizer.cpp:102
+    fw.view.max_num_iterations = 10;                // :113
+}
+
+// singleFrameOptimization / singleFrameVIOptimization: addSingleFrameResiduals (…Analytic.cpp:6-102) for the moving frame
+// and — VI, when both frames carry an IMU (AOptimizer.cpp:231-240) — for its previous keyframe over the SAME cloud (the moving
+// frame's landmarks): a free pose block per frame, every landmark block constant, sigma 1 / focal (:48).  The reference adds
+// the blocks frame by frame; the C ABI wants observations landmark-major, so each landmark lists its features on the moving
+// frame, then those on the previous keyframe — the same residual blocks, summed in another order.
+inline void flatten_single_frame(const std::shared_ptr<Frame> &moving, bool vi, int factor_kind, FlatWindow &fw) {
+    fw = FlatWindow();
+    fw.frame_vector.push_back(moving);
+    const bool with_imu = vi && moving->imu && moving->imu->last_kf && moving->imu->last_kf->imu; // AOptimizer.cpp:231
+    if (with_imu) fw.frame_vector.push_back(moving->imu->last_kf);
+    std::unordered_map<const Frame *, int> frame_idx;
+    for (size_t i = 0; i < fw.frame_vector.size(); i++) {
+        frame_idx[fw.frame_vector[i].get()] = (int)i;
+        detail::push_frame_state(fw, *fw.frame_vector[i], false);
+    }
+    for (auto &landmark : moving->pointxd) {
+        if (!landmark->isInitialized() || landmark->isOutlier()) continue; // :20
+        int l = -1;
+        for (size_t i = 0; i < fw.frame_vector.size(); i++)
+            for (auto &wfeature : landmark->features) {
+                std::shared_ptr<Feature> feature = wfeature.lock();
+                if (!feature) continue; // :29
+                std::shared_ptr<ImageSensor> cam = feature->sensor.lock();
+                if (!cam || cam->getFrame() != fw.frame_vector[i]) continue; // :36
+                if (l < 0) { // :38-42
+                    l = (int)fw.landmarks.size();
+                    fw.landmarks.push_back(landmark);
+                    fw.lmk_t.insert(fw.lmk_t.end(), landmark->t_w.begin(), landmark->t_w.end());
+                }
+                fw.obs_lmk.push_back(l);
+                fw.obs_frame.push_back((int)i);
+                fw.obs_cam.push_back(detail::cam_of(fw, *cam));
+                fw.obs_bearing.insert(fw.obs_bearing.end(), feature->bearing.begin(), feature->bearing.end());
+                fw.obs_uv.insert(fw.obs_uv.end(), feature->uv.begin(), feature->uv.end());
+                if (factor_kind == SDV_FACTOR_ANGULAR) fw.obs_sigma.push_back(1.0 / cam->getFocal()); // :48 (the pixel functor has sigma 1)
+            }
+    }
+    if (with_imu) detail::imu_factors(fw, frame_idx); // addIMUResiduals(problem, nullptr, ordering, frame_vec, 0), AOptimizer.cpp:239
+    detail::fill_view(fw, with_imu, factor_kind, 0, false, false);
+    fw.view.landmarks_constant = 1;
+    fw.view.visual_loss_huber_a = vi ? std::sqrt(1.345) : 0.0; // AOptimizer.cpp:223 / :156
+    fw.view.max_num_iterations = 5;                            // :166, :247
+}
+
 // Drop-in for the reference optimizer object (one instance = one sdv_handle, as the back-end optimizer instance,
 // slamParameters.cpp:273-274).  `factor_kind` picks what the reference picks by class: AngularAdjustmentCERESAnalytic
 // (SDV_FACTOR_ANGULAR) or BundleAdjustmentCERESAnalytic (SDV_FACTOR_PIXEL).
@@ -429,25 +564,73 @@ class B200Optimizer {
     bool localMapVIOptimization(std::shared_ptr<LocalMap> &local_map, const size_t fixed_frame_number = 0) {
         return solve(*local_map, fixed_frame_number, true);
     }
+    // Landmark refinement with every pose constant and a Huber loss (AOptimizer.cpp:98-150).  Only landmarks that pass
+    // ALandmark::sanityCheck are updated (:132-140); always true, like the reference (false only when no solve could run).
+    bool landmarkOptimization(std::shared_ptr<Frame> &frame) {
+        if (!_h) return false;
+        FlatWindow fw;
+        flatten_landmark_cloud(*frame, _kind, fw);
+        std::vector<double> buf;
+        sdv_delta d;
+        if (fw.view.n_obs > 0) { // (an empty ceres::Problem solves to itself)
+            const int rc = run(fw, buf, d);
+            if (rc != SDV_OK && rc != SDV_ERR_NUMERICAL_FAILURE) return false;
+        }
+        size_t l = 0;
+        for (auto &ldmk : frame->pointxd) {
+            if (!ldmk->isInitialized() || ldmk->isOutlier()) continue; // same check as in addLandmarkResiduals, :128
+            const bool can_be_updated = ldmk->sanityCheck();           // :132 (marks the landmark inlier / outlier)
+            if (can_be_updated && fw.view.n_obs > 0)
+                for (int k = 0; k < 3; k++) ldmk->t_w[k] += d.dlmk[3 * l + k]; // :136
+            l++;
+        }
+        return true;
+    }
+    // Pose-only refinement of one frame against constant landmarks (AOptimizer.cpp:152-217): always writes back, returns true.
+    bool singleFrameOptimization(std::shared_ptr<Frame> &moving_frame) { return single_frame(moving_frame, false); }
+    // The same with the IMU factor to the previous keyframe and a Huber loss on the visual blocks (AOptimizer.cpp:219-297):
+    // false without write-back when the summary is not usable (Ceres FAILURE, :259), else poses, velocities and biases.
+    bool singleFrameVIOptimization(std::shared_ptr<Frame> &moving_frame) { return single_frame(moving_frame, true); }
     const sdv_stats &lastStats() const { return _stats; }
     // AOptimizer::_marginalization / _enable_sparsif (AOptimizer.h:88-89): what marginalize() left for the next window solve
     std::shared_ptr<Marginalization> _marginalization = std::make_shared<Marginalization>();
     bool _enable_sparsif = false;
 
   private:
-    bool solve(LocalMap &map, size_t fixed, bool vio) {
-        if (!_h) return false;
-        FlatWindow fw;
-        if (!flatten(map, fixed, vio, _kind, fw, _marginalization.get(), _enable_sparsif)) return false;
+    int run(FlatWindow &fw, std::vector<double> &buf, sdv_delta &d) {
         const size_t F = fw.frame_vector.size(), L = fw.landmarks.size();
-        std::vector<double> buf(15 * F + 3 * L + 1, 0.0);
-        sdv_delta d;
+        buf.assign(15 * F + 3 * L + 1, 0.0);
         d.dpose = buf.data();
         d.dv = d.dpose + 6 * F;
         d.dba = d.dv + 3 * F;
         d.dbg = d.dba + 3 * F;
         d.dlmk = d.dbg + 3 * F;
-        int rc = sdv_solve_window(_h, &fw.view, &d, &_stats);
+        return sdv_solve_window(_h, &fw.view, &d, &_stats);
+    }
+    bool single_frame(std::shared_ptr<Frame> &moving_frame, bool vi) {
+        if (!_h) return false;
+        FlatWindow fw;
+        flatten_single_frame(moving_frame, vi, _kind, fw);
+        if (fw.view.n_obs == 0 && fw.view.n_imu == 0) return true; // nothing to optimise: Ceres returns at once, the state stays
+        std::vector<double> buf;
+        sdv_delta d;
+        const int rc = run(fw, buf, d);
+        if (vi && rc == SDV_ERR_NUMERICAL_FAILURE) return false; // !summary.IsSolutionUsable(), AOptimizer.cpp:259
+        if (rc != SDV_OK && rc != SDV_ERR_NUMERICAL_FAILURE) return false;
+        // poses of _map_frame_posepar, and — VI with both IMUs — v / ba / bg (:263-285); no biasDeltaCorrection here
+        FlatWindow only_state = std::move(fw);
+        only_state.landmarks.clear();
+        only_state.corr_frame.clear();
+        write_back(only_state, d, only_state.view.vio != 0);
+        return true;
+    }
+    bool solve(LocalMap &map, size_t fixed, bool vio) {
+        if (!_h) return false;
+        FlatWindow fw;
+        if (!flatten(map, fixed, vio, _kind, fw, _marginalization.get(), _enable_sparsif)) return false;
+        std::vector<double> buf;
+        sdv_delta d;
+        int rc = run(fw, buf, d);
         // SDV_ERR_NUMERICAL_FAILURE is Ceres' TerminationType FAILURE: the reference ignores the summary, writes back the
         // last accepted x and returns true (AOptimizer.cpp:388-445); the termination is in lastStats().  Every other
         // non-zero status means no solve happened: state untouched, false.

@@ -168,7 +168,7 @@ def parse_dump(text):
     from sadvio_b200 import abi
 
     lines = text.split("\n")
-    assert lines[0] == "dump" and lines[1] == "ok 1", lines[:2]
+    assert lines[0].startswith("dump") and lines[1] == "ok 1", lines[:2]
     d = {}
     for ln in lines[2:]:
         if not ln:
@@ -189,6 +189,12 @@ def parse_dump(text):
         imu_dp=d["imu_dp"].reshape(P, 3), imu_cov=d["imu_cov"].reshape(P, 81), imu_J_dR_bg=d["imu_J_dR_bg"].reshape(P, 9),
         imu_J_dv_ba=d["imu_J_dv_ba"].reshape(P, 9), imu_J_dv_bg=d["imu_J_dv_bg"].reshape(P, 9), imu_J_dp_ba=d["imu_J_dp_ba"].reshape(P, 9),
         imu_J_dp_bg=d["imu_J_dp_bg"].reshape(P, 9), imu_sigma_ba=d["imu_sigma_ba"], imu_sigma_bg=d["imu_sigma_bg"])
+    if len(d.get("obs_sigma", ())):
+        win.obs_sigma = d["obs_sigma"]
+    if "masks" in d:
+        win.visual_loss_huber_a, win.landmarks_constant, win.max_num_iterations = float(d["masks"][0]), bool(d["masks"][1]), int(d["masks"][2])
+    if "frames" in d:
+        win.meta["frames_in_file"] = d["frames"].astype(int)
     if "dense" in d:
         n_full, n, frame, frame_col, n_keep = (int(x) for x in d["dense"])
         win.dense_prior = abi.DensePrior(J=d["dense_J"].reshape(n_full, n), r0=d["dense_r0"], frame=frame, frame_col=frame_col,
@@ -315,7 +321,7 @@ def test_adapter_solve_matches_python_binding(adapter_exe):
         ps = [p for p in range(ref.n_imu) if ref.imu_j[p] == f]
         if ps:
             assert np.abs(row[21:24] - ref.imu_dp[ps[0]]).max() < 1e-9   # biasDeltaCorrection applied
-    lm = np.array([[float(x) for x in ln.split()] for ln in out[2 + F:2 + F + win.n_lmks]])
+    lm = np.array([[float(x) for x in ln.split()[:3]] for ln in out[2 + F:2 + F + win.n_lmks]])
     assert np.abs(lm - ref.lmk_t).max() < 1e-8
 
 
@@ -372,7 +378,7 @@ def test_writeback_corrects_every_frame_with_a_previous_keyframe(adapter_exe, ga
         assert np.abs(mine[0] - dp).max() < 1e-14 and np.abs(mine[1] - dv).max() < 1e-14 and np.abs(mine[2] - dR.reshape(9)).max() < 1e-14
         n_checked += 1
     assert n_checked == orig.n_imu
-    lm = np.array([[float(x) for x in ln.split()] for ln in out[2 + F:2 + F + L]])
+    lm = np.array([[float(x) for x in ln.split()[:3]] for ln in out[2 + F:2 + F + L]])
     assert np.abs(lm - ref.lmk_t).max() < 1e-15
 
 
@@ -401,3 +407,96 @@ def test_failure_termination_writes_back_and_returns_true_in_both_adapters(adapt
     rows = [np.array([float(x) for x in ln.split()]) for ln in out[2:2 + win.n_frames]]
     for k, row in enumerate(rows):
         assert np.abs(row[:12] - before[win.n_frames - 1 - k]).max() < 1e-15
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# landmarkOptimization / singleFrameOptimization / singleFrameVIOptimization (AOptimizer.cpp:98-297) through the C++ adapter
+# ------------------------------------------------------------------------------------------------------------------------
+def _file_pos(win, f, n_extra=0):
+    return n_extra + (win.n_frames - 1 - f)      # frames are listed oldest -> newest, window index 0 = newest
+
+
+@pytest.mark.parametrize("mode,kind", [("lmkopt", 0), ("single", 0), ("single", 1), ("singlevi", 0)])
+def test_f2_flatten_matches_the_python_mirror(adapter_exe, mode, kind):
+    """The window the C++ adapter builds for the three frame-level solves (addLandmarkResiduals / addSingleFrameResiduals walks,
+    AngularAdjustmentCERESAnalytic.cpp:6-209) equals the sub-window the Python mirror cuts out of the flattened local map."""
+    from sadvio_b200 import api
+
+    win = synth.make_window("small", factor_kind=kind)
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), False)
+    frame = 3
+    out = subprocess.run([adapter_exe, "dump_" + mode, "1", "0", str(kind), str(_file_pos(win, frame))], input=txt, capture_output=True, text=True,
+                         check=True).stdout
+    got = parse_dump(out)
+    if mode == "lmkopt":
+        exp, _ = api.landmark_window(win, frame)
+        frames = list(dict.fromkeys(int(f) for f in win.obs_frame[np.isin(win.obs_lmk, np.unique(win.obs_lmk[win.obs_frame == frame]))]))
+    else:
+        exp, frames = api.single_frame_window(win, frame, vi=mode == "singlevi")
+    assert [win.n_frames - 1 - int(p) for p in got.meta["frames_in_file"]] == frames
+    assert (got.vio, got.n_fixed, got.n_frames, got.n_lmks, got.n_obs, got.n_imu) == (exp.vio, exp.n_fixed, exp.n_frames, exp.n_lmks, exp.n_obs, exp.n_imu)
+    assert (got.visual_loss_huber_a, got.landmarks_constant, got.max_num_iterations) == (exp.visual_loss_huber_a, exp.landmarks_constant, exp.max_num_iterations)
+    for k in ("T_f_w", "lmk_t", "obs_lmk", "obs_frame", "obs_cam", "obs_bearing", "obs_uv", "obs_sigma", "v", "ba", "bg", "imu_i", "imu_j", "imu_dt",
+              "imu_dR", "imu_dv", "imu_dp", "imu_cov", "imu_J_dp_bg", "imu_sigma_ba"):
+        a, b = getattr(got, k), getattr(exp, k)
+        if b is None or (k.startswith("imu") and exp.n_imu == 0):
+            assert a is None or len(a) == 0 or k in ("v", "ba", "bg"), k
+            continue
+        assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["lmkopt", "single", "singlevi"])
+def test_f2_adapter_solve_matches_python_binding(adapter_exe, mode):
+    from sadvio_b200 import api
+
+    def make():
+        # poses at the ground truth and most landmarks close to it, so that ALandmark::sanityCheck (mean squared reprojection
+        # error of the estimate <= 2 at 1 px noise) passes for some landmarks and fails for others
+        w = synth.make_window("small")
+        if mode == "lmkopt":
+            w.T_f_w = w.meta["T_f_w_gt"].copy()
+            near = np.arange(w.n_lmks) % 3 != 0
+            w.lmk_t[near] = w.meta["lmk_gt"][near] + 0.02 * (w.lmk_t[near] - w.meta["lmk_gt"][near])
+        return w.normalise()
+
+    win = make()
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), False)
+    frame = 2
+    out = subprocess.run([adapter_exe, mode, "1", "0", "0", str(_file_pos(win, frame))], input=txt, capture_output=True, text=True, check=True).stdout.split("\n")
+    ok, iters = (int(x) for x in out[1].split())
+    assert ok == 1
+    opt = api.B200Optimizer()
+    ref = make()
+    # ALandmark::sanityCheck of the C++ mirror, restated: mean squared reprojection error of the CURRENT estimate over the features
+    def sanity(l):
+        sel = np.flatnonzero(ref.obs_lmk == l)
+        if len(sel) < 2:
+            return False
+        chi2 = []
+        for o in sel:
+            T = np.vstack([ref.T_f_w[ref.obs_frame[o]].reshape(3, 4), [0, 0, 0, 1]])
+            Ts = np.vstack([ref.T_s_f[ref.obs_cam[o]].reshape(3, 4), [0, 0, 0, 1]])
+            pc = (Ts @ T @ np.r_[ref.lmk_t[l], 1.0])[:3]
+            K = ref.K[ref.obs_cam[o]]
+            uv = np.array([K[0] * pc[0] / pc[2] + K[2], K[1] * pc[1] / pc[2] + K[3]])
+            okp = pc[2] >= 0.1 and 0 <= uv[0] <= 2 * K[2] and 0 <= uv[1] <= 2 * K[3]
+            chi2.append(((uv - ref.obs_uv[o]) ** 2).sum() if okp else 1000.0)
+        return np.mean(chi2) <= 2.0
+    if mode == "lmkopt":
+        assert opt.landmarkOptimization(ref, frame, sanity_check=sanity)
+    elif mode == "single":
+        assert opt.singleFrameOptimization(ref, frame)
+    else:
+        assert opt.singleFrameVIOptimization(ref, frame)
+    assert iters == opt.last_stats["iterations"]
+    F = win.n_frames
+    rows = [np.array([float(x) for x in ln.split()]) for ln in out[2:2 + F]]   # oldest -> newest
+    for k, row in enumerate(rows):
+        f = F - 1 - k
+        assert np.abs(row[:12] - ref.T_f_w[f]).max() < 1e-9 and np.abs(row[12:15] - ref.v[f]).max() < 1e-9 and np.abs(row[15:18] - ref.ba[f]).max() < 1e-9
+    lm = np.array([[float(x) for x in ln.split()] for ln in out[2 + F:2 + F + win.n_lmks]])
+    assert np.abs(lm[:, :3] - ref.lmk_t).max() < 1e-8
+    if mode == "lmkopt":
+        moved = np.abs(ref.lmk_t - win.lmk_t).max(axis=1) > 0
+        assert moved.any() and not moved.all()
