@@ -353,6 +353,61 @@ typedef struct sdv_preint { /* per interval, the state of the LAST measurement's
 
 int sdv_preintegrate(sdv_handle *h, const sdv_imu_intervals *in, sdv_preint *out);
 
+/*
+ * Marginal-prior construction — replaces: AngularAdjustmentCERESAnalytic::marginalize
+ * (cpp/src/optimizers/AngularAdjustmentCERESAnalytic.cpp:488-739) / BundleAdjustmentCERESAnalytic::marginalize
+ * (BundleAdjustmentCERESAnalytic.cpp:431-660) with everything they call in isae::Marginalization: preMarginalize
+ * (marginalization.cpp:23-143), computeInformationAndGradient (:145-211), computeSchurComplement (:213-265),
+ * rankReveallingDecomposition (:318-342), computeJacobiansAndResiduals (:516-530), sparsifyVIO (:362-411), sparsifyVO (:410-514).
+ *
+ * `win` is the window BEFORE its oldest keyframe leaves: frame 0 of the reference = the LAST frame of `win` (frames are ordered
+ * newest -> oldest), frame 1 = the one before it; `win->dense_prior` is the previous marginalisation (_marginalization_last,
+ * always propagated in its dense form, …Analytic.cpp:631-660) or NULL; `win->n_fixed` is ignored (a marginalisation block has
+ * no constant parameter).  The prior is over frame 1's (pose6, v3, ba3, bg3) at column 0 — VIO only — followed by the kept
+ * landmarks, 3 columns each, in `keep_lmk` order (landmark indices of `win`).  Two calls: sdv_marginalize computes and reports
+ * the sizes, sdv_marginal_fetch copies the result into caller-allocated buffers of those sizes.
+ */
+typedef struct sdv_marginal_sizes {
+    int32_t ok;            /* 0: computeSchurComplement returned false (n < 4, marginalization.cpp:215) — marginalize() returns
+                              false and the caller clears its marginalisation scheme (…Analytic.cpp:690-695); nothing to fetch */
+    int32_t m, n;          /* _m, _n: marginalised / kept parameters */
+    int32_t n_full;        /* _n_full: rows of J (eigenvalues of Ak above 1e-12) */
+    int32_t n_marg, n_keep;/* landmarks marginalised / kept */
+    int32_t frame;         /* index in `win` of _frame_to_keep (frame 1), -1 in the VO case */
+    int32_t n_chain;       /* sparsifyVO: landmarks on the chain (n_chain - 1 LandmarkToLandmark factors) */
+    int32_t eig_sweeps_m, eig_sweeps_n; /* block-Jacobi sweeps of the two eigen-decompositions */
+    double ms_device;      /* CUDA events around assembly + decompositions + sparsification */
+    double ms_total_host;
+} sdv_marginal_sizes;
+
+typedef struct sdv_marginal { /* caller-allocated from sdv_marginal_sizes; any pointer may be NULL (not wanted) */
+    double *J;             /* [n_full][n]   _marginalization_jacobian = Lambda^1/2 U^T */
+    double *r0;            /* [n_full]      _marginalization_residual = -Lambda^-1/2 U^T bk */
+    int32_t *keep_lmk;     /* [n_keep]      _lmk_to_keep; column of landmark k = (frame >= 0 ? 15 : 0) + 3 k */
+    int32_t *marg_lmk;     /* [n_marg]      _lmk_to_marg */
+    double *Ak, *bk;       /* [n][n], [n]   _Ak, _bk */
+    double *U, *Lambda;    /* [n][n_full], [n_full] */
+    double *A, *b;         /* [m+n][m+n], [m+n]: information and gradient before the Schur complement (not for sdv_schur_prior) */
+    /* sparsifyVIO: IMUPriordx on frame 1 (prior values = its current state) + one PoseToLandmarkFactor per kept landmark */
+    double *imu_sqrt_inf;  /* [225]         _map_frame_inf */
+    double *p2l_delta;     /* [n_keep][3]   _map_lmk_prior (t_f_lmk) */
+    double *p2l_sqrt_inf;  /* [n_keep][9]   _map_lmk_inf */
+    /* sparsifyVO: Landmark3DPrior on lmk_with_prior (prior value = its current position) + a chain of LandmarkToLandmark factors */
+    int32_t *chain;        /* [n_chain]     _lmk_to_keep re-ordered by the greedy coupling walk */
+    int32_t lmk_with_prior;/* out: _lmk_with_prior (landmark index of `win`), -1 if none */
+    int32_t reserved0;
+    double lmk_sqrt_inf[9];/* out: _info_lmk */
+    double *l2l_delta;     /* [n_chain-1][3] t_k - t_k+1 */
+    double *l2l_sqrt_inf;  /* [n_chain-1][9] */
+} sdv_marginal;
+
+int sdv_marginalize(sdv_handle *h, const sdv_window *win, int32_t sparsify, sdv_marginal_sizes *sizes);
+int sdv_marginal_fetch(sdv_handle *h, sdv_marginal *out);
+/* The dense core alone (computeSchurComplement + rankReveallingDecomposition + computeJacobiansAndResiduals) on a caller-provided
+   information matrix A (row-major (m+n)^2, the m marginalised parameters first) and gradient b: the entry point the reference's
+   own KAT (cpp/tests/marginalization_test.cpp:219-223, :300-313) is pinned through. */
+int sdv_schur_prior(sdv_handle *h, const double *A, const double *b, int32_t m, int32_t n, double eps, sdv_marginal_sizes *sizes);
+
 /* Multi-GPU (landmark-sharded Schur reduction, one NCCL all-reduce of [S|g|…] per LM iteration).
    `nccl_unique_id` is the 128-byte ncclUniqueId every rank received from rank 0. */
 /* Host-only helper (no CUDA): the contiguous, observation-balanced landmark range [l0,l1) and observation range [o0,o1)

@@ -180,6 +180,24 @@ class SdvStats(C.Structure):
     ]
 
 
+class SdvMarginalSizes(C.Structure):
+    _fields_ = [
+        ("ok", C.c_int32), ("m", C.c_int32), ("n", C.c_int32), ("n_full", C.c_int32), ("n_marg", C.c_int32), ("n_keep", C.c_int32),
+        ("frame", C.c_int32), ("n_chain", C.c_int32), ("eig_sweeps_m", C.c_int32), ("eig_sweeps_n", C.c_int32),
+        ("ms_device", C.c_double), ("ms_total_host", C.c_double),
+    ]
+
+
+class SdvMarginal(C.Structure):
+    _fields_ = [
+        ("J", c_double_p), ("r0", c_double_p), ("keep_lmk", c_int32_p), ("marg_lmk", c_int32_p), ("Ak", c_double_p), ("bk", c_double_p),
+        ("U", c_double_p), ("Lambda", c_double_p), ("A", c_double_p), ("b", c_double_p),
+        ("imu_sqrt_inf", c_double_p), ("p2l_delta", c_double_p), ("p2l_sqrt_inf", c_double_p),
+        ("chain", c_int32_p), ("lmk_with_prior", C.c_int32), ("reserved0", C.c_int32), ("lmk_sqrt_inf", C.c_double * 9),
+        ("l2l_delta", c_double_p), ("l2l_sqrt_inf", c_double_p),
+    ]
+
+
 class SdvImuIntervals(C.Structure):
     _fields_ = [
         ("n_intervals", C.c_int32),

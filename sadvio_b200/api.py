@@ -60,6 +60,9 @@ def lib() -> C.CDLL:
     L.sdv_debug_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.sdv_debug_graph_builds.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.sdv_preintegrate.argtypes = [C.c_void_p, C.POINTER(abi.SdvImuIntervals), C.POINTER(abi.SdvPreint)]
+    L.sdv_marginalize.argtypes = [C.c_void_p, C.POINTER(abi.SdvWindow), C.c_int32, C.POINTER(abi.SdvMarginalSizes)]
+    L.sdv_marginal_fetch.argtypes = [C.c_void_p, C.POINTER(abi.SdvMarginal)]
+    L.sdv_schur_prior.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32, C.c_double, C.POINTER(abi.SdvMarginalSizes)]
     _lib = L
     return L
 
@@ -176,6 +179,75 @@ class Solver:
         for k, a in out.items():
             setattr(outs, k, a.ctypes.data_as(abi.c_double_p))
         self._check(lib().sdv_preintegrate(self._h, C.byref(ins), C.byref(outs)))
+        return out
+
+    # -- marginal-prior construction (AngularAdjustmentCERESAnalytic::marginalize and what it calls, on the GPU)
+    def _fetch_marginal(self, sz, with_A: bool):
+        n, nf, N, K = sz.n, sz.n_full, sz.m + sz.n, sz.n_keep
+        out = dict(J=np.zeros((nf, n)), r0=np.zeros(nf), keep=np.zeros(K, dtype=np.int32), marg=np.zeros(sz.n_marg, dtype=np.int32), Ak=np.zeros((n, n)),
+                   bk=np.zeros(n), U=np.zeros((n, nf)), Lambda=np.zeros(nf), imu_sqrt_inf=np.zeros(225), p2l_delta=np.zeros((K, 3)),
+                   p2l_sqrt_inf=np.zeros((K, 9)), chain=np.zeros(max(sz.n_chain, 1), dtype=np.int32), l2l_delta=np.zeros((max(sz.n_chain - 1, 1), 3)),
+                   l2l_sqrt_inf=np.zeros((max(sz.n_chain - 1, 1), 9)))
+        if with_A:
+            out.update(A=np.zeros((N, N)), b=np.zeros(N))
+        ms = abi.SdvMarginal()
+        for k, name in (("J", "J"), ("r0", "r0"), ("Ak", "Ak"), ("bk", "bk"), ("U", "U"), ("Lambda", "Lambda"), ("A", "A"), ("b", "b"),
+                        ("imu_sqrt_inf", "imu_sqrt_inf"), ("p2l_delta", "p2l_delta"), ("p2l_sqrt_inf", "p2l_sqrt_inf"), ("l2l_delta", "l2l_delta"),
+                        ("l2l_sqrt_inf", "l2l_sqrt_inf")):
+            if name in out:
+                setattr(ms, k, out[name].ctypes.data_as(abi.c_double_p))
+        ms.keep_lmk = out["keep"].ctypes.data_as(abi.c_int32_p)
+        ms.marg_lmk = out["marg"].ctypes.data_as(abi.c_int32_p)
+        ms.chain = out["chain"].ctypes.data_as(abi.c_int32_p)
+        self._check(lib().sdv_marginal_fetch(self._h, C.byref(ms)))
+        out["lmk_with_prior"] = int(ms.lmk_with_prior)
+        out["lmk_sqrt_inf"] = np.array(ms.lmk_sqrt_inf[:])
+        out["chain"] = out["chain"][:sz.n_chain]
+        out["l2l_delta"], out["l2l_sqrt_inf"] = out["l2l_delta"][:max(sz.n_chain - 1, 0)], out["l2l_sqrt_inf"][:max(sz.n_chain - 1, 0)]
+        return out
+
+    def marginalize(self, win: abi.Window, sparsify: bool = False):
+        """marginalize(frame0 = oldest keyframe of `win`, frame1 = the next one, enable_sparsif) on the GPU.  Returns
+        (dense, sparse, info): abi.DensePrior over (frame 1, kept landmarks) in the landmark indices of `win` — None when the
+        reference's marginalize() returns false —, the abi.SparsePrior of sparsifyVIO / sparsifyVO when asked for, and a dict
+        with the intermediate results (A, b, Ak, bk, U, Lambda, keep, marg, sizes)."""
+        ws = win.as_struct()
+        sz = abi.SdvMarginalSizes()
+        self._check(lib().sdv_marginalize(self._h, C.byref(ws), 1 if sparsify else 0, C.byref(sz)))
+        self._win = win
+        info = {k: getattr(sz, k) for k, _ in abi.SdvMarginalSizes._fields_}
+        if not sz.ok:
+            return None, None, info
+        out = self._fetch_marginal(sz, True)
+        info.update(out)
+        first = 15 if sz.frame >= 0 else 0
+        dense = abi.DensePrior(J=out["J"], r0=out["r0"], frame=int(sz.frame), frame_col=0, keep_lmk=out["keep"].copy(),
+                               keep_col=np.asarray([first + 3 * k for k in range(sz.n_keep)], dtype=np.int32))
+        sparse = None
+        if sparsify and sz.n_full > 0:
+            f1 = int(sz.frame)
+            if f1 >= 0:
+                sparse = abi.SparsePrior(has_imu_prior=True, frame=f1, T_prior=win.T_f_w[f1].copy(), v_prior=win.v[f1].copy(), ba_prior=win.ba[f1].copy(),
+                                         bg_prior=win.bg[f1].copy(), imu_sqrt_inf=out["imu_sqrt_inf"], p2l_lmk=out["keep"].copy(),
+                                         p2l_delta=out["p2l_delta"], p2l_sqrt_inf=out["p2l_sqrt_inf"])
+            elif sz.n_chain >= 2:
+                wp = out["lmk_with_prior"]
+                sparse = abi.SparsePrior(has_lmk_prior=True, lmk0=wp, lmk_prior=win.lmk_t[wp].copy(), lmk_sqrt_inf=out["lmk_sqrt_inf"],
+                                         l2l_a=out["chain"][:-1].copy(), l2l_b=out["chain"][1:].copy(), l2l_delta=out["l2l_delta"],
+                                         l2l_sqrt_inf=out["l2l_sqrt_inf"])
+        return dense, sparse, info
+
+    def schur_prior(self, A, b, m: int, eps: float = 1e-12):
+        """computeSchurComplement + rankReveallingDecomposition + computeJacobiansAndResiduals on a given information matrix."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        n = A.shape[0] - m
+        sz = abi.SdvMarginalSizes()
+        self._check(lib().sdv_schur_prior(self._h, A.ctypes.data_as(abi.c_double_p), b.ctypes.data_as(abi.c_double_p), m, n, eps, C.byref(sz)))
+        if not sz.ok:
+            return None
+        out = self._fetch_marginal(sz, False)
+        out.update({k: getattr(sz, k) for k, _ in abi.SdvMarginalSizes._fields_})
         return out
 
     def graph_builds(self) -> int:

@@ -11,6 +11,7 @@
 #include "sdv_chol.cuh"
 #include "sdv_chol_band.cuh"
 #include "sdv_preint.cuh"
+#include "sdv_marg.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -163,6 +164,8 @@ static lin_visual_fn_t lin_visual_fn(int kind, bool smem, bool early) {
     return early ? k_lin_visual<1, false, true> : k_lin_visual<1, false, false>;
 }
 
+struct MargState;
+
 struct sdv_handle {
     sdv_config cfg;
     SolverOpts opt;
@@ -241,6 +244,7 @@ struct sdv_handle {
     int chol_tiles_nz = 0, chol_tiles_all = 0; // structurally non-zero tiles of L / all lower tiles
     LMState h_state;
     Accum h_acc;
+    MargState *marg = nullptr; // scratch and result of the last sdv_marginalize (sdv_marg_host.cuh)
 };
 
 namespace {
@@ -281,6 +285,7 @@ int ensure(sdv_handle *h, unsigned char **d, size_t *cap, size_t need, bool pinn
 namespace {
 int build_solve_graph(sdv_handle *h);
 void destroy_graph(sdv_handle *h);
+void free_marg_state(sdv_handle *h);
 }
 
 extern "C" {
@@ -385,6 +390,7 @@ int sdv_destroy(sdv_handle *h) {
     if (h->h_rb) cudaFreeHost(h->h_rb);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_flush) cudaFree(h->d_flush);
+    free_marg_state(h);
     for (int i = 0; i < 4; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
@@ -2319,3 +2325,15 @@ int sdv_debug_dims(sdv_handle *h, int32_t *n, int32_t *n_pad) {
 }
 
 } // extern "C"
+
+#include "sdv_marg_host.cuh"
+
+namespace {
+void free_marg_state(sdv_handle *h) {
+    if (!h->marg) return;
+    if (h->marg->d) cudaFree(h->marg->d);
+    if (h->marg->hp) cudaFreeHost(h->marg->hp);
+    delete h->marg;
+    h->marg = nullptr;
+}
+} // namespace
