@@ -232,6 +232,9 @@ typedef struct sdv_window {
                                     (addSingleFrameResiduals, …Analytic.cpp:38-43) */
     int32_t max_num_iterations;  /* > 0 overrides sdv_config::max_num_iterations for this window: 10 in landmarkOptimization
                                     (AOptimizer.cpp:113), 5 in the single-frame solves (:166, :247) */
+    const uint8_t *lmk_has_prior;/* [L] or NULL — read by sdv_marginalize only: ALandmark::hasPrior(), the sticky flag earlier
+                                    marginalisations set on the landmarks they kept (marginalization.cpp:72-79,
+                                    ALandmark.h:100-107); NULL = the landmarks kept by `dense_prior` */
 } sdv_window;
 /*
  * How the four solves map onto sdv_window (the adapters sadvio_b200/host/b200_optimizer.hpp and sadvio_b200/api.py do this):

@@ -141,6 +141,7 @@ class SdvWindow(C.Structure):
         ("visual_loss_huber_a", C.c_double),
         ("landmarks_constant", C.c_int32),
         ("max_num_iterations", C.c_int32),
+        ("lmk_has_prior", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -353,6 +354,7 @@ class Window:
     visual_loss_huber_a: float = 0.0           # ceres::HuberLoss(a) on the visual residual blocks, 0 = none
     landmarks_constant: bool = False           # single-frame solves: every landmark block constant
     max_num_iterations: int = 0                # > 0: overrides the configuration for this window
+    lmk_has_prior: Optional[np.ndarray] = None # [L] uint8, ALandmark::hasPrior() (sdv_marginalize only)
     meta: dict = field(default_factory=dict)   # ground truth etc. (never crosses the ABI)
 
     @property
@@ -425,6 +427,9 @@ class Window:
         w.visual_loss_huber_a = float(self.visual_loss_huber_a)
         w.landmarks_constant = 1 if self.landmarks_constant else 0
         w.max_num_iterations = int(self.max_num_iterations)
+        if self.lmk_has_prior is not None:
+            self.lmk_has_prior = np.ascontiguousarray(self.lmk_has_prior, dtype=np.uint8)
+            w.lmk_has_prior = self.lmk_has_prior.ctypes.data_as(C.POINTER(C.c_uint8))
         keep = [self]
         if self.dense_prior is not None:
             d = self.dense_prior

@@ -211,9 +211,12 @@ int sdv_marginalize(sdv_handle *h, const sdv_window *win, int32_t sparsify, sdv_
     const bool vio = win->vio != 0;
     const sdv_dense_prior *last = win->dense_prior;
     // ---- Marginalization::preMarginalize for point landmarks (marginalization.cpp:23-143)
-    std::vector<char> with_prior(std::max(L, 1), 0);
-    if (last)
+    std::vector<char> with_prior(std::max(L, 1), 0); // ALandmark::hasPrior()
+    if (win->lmk_has_prior) {
+        for (int l = 0; l < L; l++) with_prior[l] = win->lmk_has_prior[l] != 0;
+    } else if (last) {
         for (int k = 0; k < last->n_keep; k++) with_prior[last->keep_lmk[k]] = 1;
+    }
     ms.keep.clear();
     ms.marg.clear();
     std::vector<int> col(std::max(L, 1), -1);

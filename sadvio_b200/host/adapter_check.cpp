@@ -238,6 +238,32 @@ int main(int argc, char **argv) {
         d.dlmk = d.dbg + 3 * F;
         write_back(fw, d, vio);
         std::printf("1 0\n");
+    } else if (mode == "marg") {
+        // marginalize(frame0 = oldest keyframe of the window, frame1 = the next one, enable_sparsif = argv[5]), then the window
+        // without frame 0 (and without the landmarks only frame 0 saw, unless the prior keeps them) is solved with the prior
+        B200Optimizer opt(kind, 0);
+        std::shared_ptr<Frame> frame0 = map->frames[0], frame1 = map->frames[1];
+        const bool okm = opt.marginalize(frame0, frame1, f2_frame != 0);
+        const sdv_marginal_sizes &sz = opt.lastMarginalSizes();
+        std::printf("%d %d %d %d %d %d\n", okm ? 1 : 0, sz.m, sz.n, sz.n_full, sz.n_keep, sz.n_marg);
+        map->frames.pop_front();
+        std::vector<std::shared_ptr<Landmark>> alive;
+        for (auto &lm : map->pointxd) {
+            bool seen = false;
+            for (auto &wf : lm->features)
+                if (auto ft = wf.lock())
+                    if (auto cam = ft->sensor.lock())
+                        for (auto &fr : map->frames) seen |= cam->getFrame() == fr;
+            for (auto &k : opt._marginalization->lmk_to_keep) seen |= k == lm;
+            if (seen) alive.push_back(lm);
+            else lm->t_w = {1e300, 1e300, 1e300}; // (printed below: marks a landmark that left the map)
+        }
+        auto all_lmks = map->pointxd;
+        map->pointxd = alive;
+        bool ok = vio ? opt.localMapVIOptimization(map, fixed) : opt.localMapBA(map, fixed);
+        map->pointxd = all_lmks;
+        map->frames.push_front(frame0);
+        std::printf("%d %d\n", ok ? 1 : 0, opt.lastStats().iterations);
     } else if (mode == "lmkopt" || mode == "single" || mode == "singlevi") {
         B200Optimizer opt(kind, 0);
         bool ok = mode == "lmkopt" ? opt.landmarkOptimization(all_frames[f2_frame])

@@ -5,6 +5,7 @@
 //     bool isae::AOptimizer::landmarkOptimization(std::shared_ptr<Frame>&)          (masks of the window solve)
 //     bool isae::AOptimizer::singleFrameOptimization(std::shared_ptr<Frame>&)
 //     bool isae::AOptimizer::singleFrameVIOptimization(std::shared_ptr<Frame>&)
+//     bool isae::AOptimizer::marginalize(std::shared_ptr<Frame>& frame0, std::shared_ptr<Frame>& frame1, bool enable_sparsif)
 // (reference cpp/include/isaeslam/optimizers/AOptimizer.h:22-30), same argument meaning and error behaviour
 // (bool, no exceptions; when no solve could run — no device, malformed window — the state is left untouched and the call
 // returns false; a solve that ends in Ceres' FAILURE termination writes back and returns true like the reference).
@@ -75,6 +76,7 @@ struct Feature { // isae::AFeature
 struct Landmark { // isae::ALandmark ("pointxd")
     std::array<double, 3> t_w{};
     bool initialized = true, outlier = false;
+    bool in_map = true, has_prior = false, is_marg = false; // isInMap(), hasPrior() / setPrior(), isMarg() / setMarg() (ALandmark.h:96-117)
     std::vector<std::weak_ptr<Feature>> features; // getFeatures()
     bool isInitialized() const { return initialized; }
     bool isOutlier() const { return outlier; }
@@ -543,6 +545,118 @@ inline void flatten_single_frame(const std::shared_ptr<Frame> &moving, bool vi, 
     fw.view.max_num_iterations = 5;                            // :166, :247
 }
 
+// marginalize(frame0, frame1, enable_sparsif) (AngularAdjustmentCERESAnalytic.cpp:488-739): the window sdv_marginalize wants —
+// every landmark of frame 0 that preMarginalize looks at (marginalization.cpp:51-56) with ALL its live features, whatever frame
+// they sit on (a feature outside frame 0 makes the landmark "not lonely", :60-68), then the landmarks of the previous prior
+// that frame 0 no longer sees ("resurrected", :118-139), frames in first-appearance order with frame 1 and frame 0 LAST.
+// Returns false where the reference would throw (previous prior on another frame).  `discard_last`: an outlier among the
+// resurrected landmarks makes the reference drop the previous prior altogether (:124-127, :141-142).
+inline bool flatten_marginalization(const std::shared_ptr<Frame> &frame0, const std::shared_ptr<Frame> &frame1, int factor_kind, const Marginalization *last,
+                                    FlatWindow &fw, std::vector<uint8_t> &lmk_has_prior, bool &discard_last) {
+    fw = FlatWindow();
+    discard_last = false;
+    lmk_has_prior.clear();
+    const bool vio = frame0->imu && frame1->imu;
+    std::vector<std::shared_ptr<Frame>> others;
+    std::unordered_map<const Frame *, int> tmp_idx;
+    std::unordered_map<const Landmark *, int> lmk_idx;
+    struct Obs { int l; const Frame *f; std::shared_ptr<ImageSensor> cam; std::shared_ptr<Feature> ft; };
+    std::vector<Obs> obs;
+    for (auto &lmk : frame0->pointxd) {
+        if (lmk->isOutlier() || !lmk->in_map || !lmk->isInitialized()) continue; // marginalization.cpp:53
+        const int l = (int)fw.landmarks.size();
+        lmk_idx[lmk.get()] = l;
+        fw.landmarks.push_back(lmk);
+        fw.lmk_t.insert(fw.lmk_t.end(), lmk->t_w.begin(), lmk->t_w.end());
+        lmk_has_prior.push_back(lmk->has_prior ? 1 : 0);
+        for (auto &wf : lmk->features) {
+            std::shared_ptr<Feature> ft = wf.lock();
+            std::shared_ptr<ImageSensor> cam = ft ? ft->sensor.lock() : nullptr;
+            std::shared_ptr<Frame> fr = cam ? cam->getFrame() : nullptr;
+            if (!fr) continue; // (the reference dereferences unconditionally, :60)
+            if (fr != frame0 && fr != frame1 && tmp_idx.emplace(fr.get(), (int)others.size()).second) others.push_back(fr);
+            obs.push_back({l, fr.get(), cam, ft});
+        }
+    }
+    const bool have_last = last && !last->lmk_to_keep.empty();
+    if (have_last) {
+        for (auto &lmk : last->lmk_to_keep)
+            if (lmk_idx.find(lmk.get()) == lmk_idx.end()) {
+                if (lmk->isOutlier()) { // :124-127
+                    discard_last = true;
+                    break;
+                }
+                lmk_idx[lmk.get()] = (int)fw.landmarks.size();
+                fw.landmarks.push_back(lmk);
+                fw.lmk_t.insert(fw.lmk_t.end(), lmk->t_w.begin(), lmk->t_w.end());
+                lmk_has_prior.push_back(lmk->has_prior ? 1 : 0);
+            }
+    }
+    fw.frame_vector = others;
+    fw.frame_vector.push_back(frame1);
+    fw.frame_vector.push_back(frame0);
+    std::unordered_map<const Frame *, int> frame_idx;
+    const int F = (int)fw.frame_vector.size();
+    for (int i = 0; i < F; i++) {
+        frame_idx[fw.frame_vector[i].get()] = i;
+        detail::push_frame_state(fw, *fw.frame_vector[i], i >= F - 2); // only the pose priors of frame 0 / frame 1 matter (:664-687)
+    }
+    for (auto &o : obs) {
+        fw.obs_lmk.push_back(o.l);
+        fw.obs_frame.push_back(frame_idx[o.f]);
+        fw.obs_cam.push_back(detail::cam_of(fw, *o.cam));
+        fw.obs_bearing.insert(fw.obs_bearing.end(), o.ft->bearing.begin(), o.ft->bearing.end());
+        fw.obs_uv.insert(fw.obs_uv.end(), o.ft->uv.begin(), o.ft->uv.end());
+    }
+    if (vio) { // IMUFactor(frame0->getIMU(), frame1->getIMU()) (…Analytic.cpp:539-547): frame 1's pre-integration, whatever the distance
+        const IMU &m = *frame1->imu;
+        fw.imu_i.push_back(F - 1);
+        fw.imu_j.push_back(F - 2);
+        fw.imu_dt.push_back((double)(frame1->timestamp_ns - frame0->timestamp_ns) * 1e-9);
+        fw.imu_dR.insert(fw.imu_dR.end(), m.delta_R.begin(), m.delta_R.end());
+        fw.imu_dv.insert(fw.imu_dv.end(), m.delta_v.begin(), m.delta_v.end());
+        fw.imu_dp.insert(fw.imu_dp.end(), m.delta_p.begin(), m.delta_p.end());
+        fw.imu_cov.insert(fw.imu_cov.end(), m.Sigma.begin(), m.Sigma.end());
+        fw.J_dR_bg.insert(fw.J_dR_bg.end(), m.J_dR_bg.begin(), m.J_dR_bg.end());
+        fw.J_dv_ba.insert(fw.J_dv_ba.end(), m.J_dv_ba.begin(), m.J_dv_ba.end());
+        fw.J_dv_bg.insert(fw.J_dv_bg.end(), m.J_dv_bg.begin(), m.J_dv_bg.end());
+        fw.J_dp_ba.insert(fw.J_dp_ba.end(), m.J_dp_ba.begin(), m.J_dp_ba.end());
+        fw.J_dp_bg.insert(fw.J_dp_bg.end(), m.J_dp_bg.begin(), m.J_dp_bg.end());
+        fw.sigma_ba.push_back(frame0->imu->bacc_noise);
+        fw.sigma_bg.push_back(frame0->imu->bgyr_noise);
+    }
+    bool have_dense = false;
+    if (have_last && !discard_last) { // the previous prior, always in its dense form (…Analytic.cpp:631-660)
+        sdv_dense_prior &dp = fw.dense;
+        dp.n_full = last->n_full;
+        dp.n = last->n;
+        dp.J = last->marginalization_jacobian.data();
+        dp.r0 = last->marginalization_residual.data();
+        dp.frame = -1;
+        dp.frame_col = 0;
+        if (last->frame_to_keep) {
+            if (last->frame_to_keep != frame0) return false; // _map_frame_posepar.at(_frame_to_keep) throws
+            auto it = last->map_frame_idx.find(frame0.get());
+            if (it == last->map_frame_idx.end()) return false;
+            dp.frame = F - 1;
+            dp.frame_col = it->second;
+        }
+        for (auto &lmk : last->lmk_to_keep) {
+            auto it = last->map_lmk_idx.find(lmk.get());
+            if (it == last->map_lmk_idx.end()) return false;
+            fw.keep_lmk.push_back(lmk_idx.at(lmk.get()));
+            fw.keep_col.push_back(it->second);
+        }
+        dp.n_keep = (int32_t)fw.keep_lmk.size();
+        dp.keep_lmk = fw.keep_lmk.data();
+        dp.keep_col = fw.keep_col.data();
+        have_dense = true;
+    }
+    detail::fill_view(fw, vio, factor_kind, 0, have_dense, false);
+    fw.view.lmk_has_prior = lmk_has_prior.data();
+    return true;
+}
+
 // Drop-in for the reference optimizer object (one instance = one sdv_handle, as the back-end optimizer instance,
 // slamParameters.cpp:273-274).  `factor_kind` picks what the reference picks by class: AngularAdjustmentCERESAnalytic
 // (SDV_FACTOR_ANGULAR) or BundleAdjustmentCERESAnalytic (SDV_FACTOR_PIXEL).
@@ -591,6 +705,97 @@ class B200Optimizer {
     // The same with the IMU factor to the previous keyframe and a Huber loss on the visual blocks (AOptimizer.cpp:219-297):
     // false without write-back when the summary is not usable (Ceres FAILURE, :259), else poses, velocities and biases.
     bool singleFrameVIOptimization(std::shared_ptr<Frame> &moving_frame) { return single_frame(moving_frame, true); }
+    // Marginal prior of the keyframe that leaves the window (AngularAdjustmentCERESAnalytic.cpp:488-739 /
+    // BundleAdjustmentCERESAnalytic.cpp:431-660) on the GPU; fills _marginalization (what the next window solve wires in) and
+    // _marginalization_last (what the next marginalisation folds in) like the reference does (:714-736).
+    bool marginalize(std::shared_ptr<Frame> &frame0, std::shared_ptr<Frame> &frame1, bool enable_sparsif) {
+        _enable_sparsif = enable_sparsif; // :491
+        if (!_h || !frame0 || !frame1) return false;
+        if ((frame0->imu != nullptr) != (frame1->imu != nullptr)) return false; // (one IMU only: not a configuration the back ends produce)
+        FlatWindow fw;
+        std::vector<uint8_t> has_prior;
+        bool discard_last = false;
+        if (!flatten_marginalization(frame0, frame1, _kind, _marginalization_last.get(), fw, has_prior, discard_last)) return false;
+        if (discard_last) _marginalization_last->lmk_to_keep.clear(); // marginalization.cpp:141-142
+        sdv_marginal_sizes sz;
+        if (sdv_marginalize(_h, &fw.view, enable_sparsif ? 1 : 0, &sz) != SDV_OK) return false;
+        _marg_sizes = sz;
+        Marginalization &M = *_marginalization;
+        M = Marginalization();
+        if (!sz.ok) { // computeSchurComplement() == false: the scheme is reset (…Analytic.cpp:690-695)
+            _marginalization_last->lmk_to_keep.clear();
+            return false;
+        }
+        std::vector<int32_t> keep(std::max(sz.n_keep, 1)), marg(std::max(sz.n_marg, 1)), chain(std::max(sz.n_chain, 1));
+        std::vector<double> p2d(3 * (size_t)std::max(sz.n_keep, 1)), p2s(9 * (size_t)std::max(sz.n_keep, 1)), l2d(3 * (size_t)std::max(sz.n_chain, 1)),
+            l2s(9 * (size_t)std::max(sz.n_chain, 1));
+        std::array<double, 225> imu_inf{};
+        M.n = sz.n;
+        M.n_full = sz.n_full;
+        M.marginalization_jacobian.assign((size_t)sz.n_full * sz.n, 0.0);
+        M.marginalization_residual.assign(sz.n_full, 0.0);
+        sdv_marginal out;
+        std::memset(&out, 0, sizeof(out));
+        out.J = M.marginalization_jacobian.data();
+        out.r0 = M.marginalization_residual.data();
+        out.keep_lmk = keep.data();
+        out.marg_lmk = marg.data();
+        out.imu_sqrt_inf = imu_inf.data();
+        out.p2l_delta = p2d.data();
+        out.p2l_sqrt_inf = p2s.data();
+        out.chain = chain.data();
+        out.l2l_delta = l2d.data();
+        out.l2l_sqrt_inf = l2s.data();
+        if (sdv_marginal_fetch(_h, &out) != SDV_OK) return false;
+        // flags preMarginalize leaves on the landmarks (marginalization.cpp:72-86)
+        for (int k = 0; k < sz.n_marg; k++) fw.landmarks[marg[k]]->is_marg = true;
+        for (auto &lmk : frame0->pointxd) {
+            if (lmk->isOutlier() || !lmk->in_map || !lmk->isInitialized()) continue;
+            int num_cam = 0;
+            for (auto &wf : lmk->features) {
+                std::shared_ptr<Feature> ft = wf.lock();
+                std::shared_ptr<ImageSensor> cam = ft ? ft->sensor.lock() : nullptr;
+                if (cam && cam->getFrame() == frame0) num_cam++;
+            }
+            if (num_cam != 2 && !lmk->has_prior) lmk->is_marg = true; // :72-75
+        }
+        const int first = sz.frame >= 0 ? 15 : 0;
+        if (sz.frame >= 0) {
+            M.frame_to_keep = frame1;
+            M.map_frame_idx[frame1.get()] = 0; // after the shift by _m (marginalization.cpp:251-256)
+        }
+        for (int k = 0; k < sz.n_keep; k++) {
+            const std::shared_ptr<Landmark> &lmk = fw.landmarks[keep[k]];
+            lmk->has_prior = true; // setPrior(), :79 (resurrected landmarks carry it already)
+            M.lmk_to_keep.push_back(lmk);
+            M.map_lmk_idx[lmk.get()] = first + 3 * k;
+        }
+        if (enable_sparsif && sz.n_full > 0) { // :703-708
+            if (sz.frame >= 0) { // sparsifyVIO
+                M.map_frame_inf[frame1.get()] = imu_inf;
+                for (int k = 0; k < sz.n_keep; k++) {
+                    const Landmark *l = fw.landmarks[keep[k]].get();
+                    std::memcpy(M.map_lmk_prior[l].data(), &p2d[3 * (size_t)k], 24);
+                    std::memcpy(M.map_lmk_inf[l].data(), &p2s[9 * (size_t)k], 72);
+                }
+            } else if (sz.n_chain >= 2) { // sparsifyVO: _lmk_to_keep becomes the chain (marginalization.cpp:461-462)
+                M.lmk_to_keep.clear();
+                for (int k = 0; k < sz.n_chain; k++) M.lmk_to_keep.push_back(fw.landmarks[chain[k]]);
+                M.lmk_with_prior = fw.landmarks[out.lmk_with_prior];
+                M.prior_lmk = M.lmk_with_prior->t_w;
+                std::memcpy(M.info_lmk.data(), out.lmk_sqrt_inf, 72);
+                for (int k = 0; k + 1 < sz.n_chain; k++) { // keyed on lmk_kp1 (:505-506)
+                    const Landmark *l = fw.landmarks[chain[k + 1]].get();
+                    std::memcpy(M.map_lmk_prior[l].data(), &l2d[3 * (size_t)k], 24);
+                    std::memcpy(M.map_lmk_inf[l].data(), &l2s[9 * (size_t)k], 72);
+                }
+            }
+        }
+        *_marginalization_last = M; // …Analytic.cpp:714-736
+        return true;
+    }
+    const sdv_marginal_sizes &lastMarginalSizes() const { return _marg_sizes; }
+    std::shared_ptr<Marginalization> _marginalization_last = std::make_shared<Marginalization>(); // AOptimizer::_marginalization_last
     const sdv_stats &lastStats() const { return _stats; }
     // AOptimizer::_marginalization / _enable_sparsif (AOptimizer.h:88-89): what marginalize() left for the next window solve
     std::shared_ptr<Marginalization> _marginalization = std::make_shared<Marginalization>();
@@ -641,6 +846,7 @@ class B200Optimizer {
     sdv_handle *_h = nullptr;
     int _kind;
     sdv_stats _stats{};
+    sdv_marginal_sizes _marg_sizes{};
 };
 
 } // namespace sdvhost

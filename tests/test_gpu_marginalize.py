@@ -155,7 +155,10 @@ def test_chained_marginalisation_with_resurrected_landmarks(solver):
         # both chains continue with their OWN prior (the comparison above is per step, on identical inputs)
         assert np.array_equal(win.lmk_t, win_o.lmk_t)
         nxt = marginalize.drop_oldest_frame(win, prior0)
-        _next_window_parity(solver, win, dense, prior0, tol=2e-5)   # (noise eigenpairs of two chained rank-deficient priors, see there)
+        # chained: Amm now holds the weakly constrained velocity / bias directions the previous prior left (cond ~ 1e9, printed
+        # by _compare_with_oracle's tolerance): Arm Amm^+ Arm^T is uncertain at ~cond eps |Ak| for ANY solver, which is as large as
+        # the smallest informative eigenvalues of Ak — the weak directions of the next solve move by ~1e-5 relative
+        _next_window_parity(solver, win, dense, prior0, tol=2e-4)
         win = nxt
         win.n_fixed = 0
         win_o = marginalize.drop_oldest_frame(win_o, prior0)
