@@ -419,6 +419,12 @@ int sdv_shard_range(const int32_t *obs_lmk, int32_t n_obs, int32_t n_lmks, int32
                     int32_t *o0, int32_t *o1);
 int sdv_comm_unique_id(void *out_128_bytes);
 int sdv_comm_init(sdv_handle *h, const void *nccl_unique_id, int32_t rank, int32_t world);
+/* Optional, after sdv_comm_init on one NVLink / NVSwitch node (2..8 ranks): the per-iteration exchanges run as ONE kernel over
+   peer memory instead of pack -> ncclAllReduce -> unpack (sadvio_b200/csrc/sdv_peer.cuh), and the whole solve stays one CUDA
+   graph at N > 1.  Every rank exports its exchange area as a 64-byte cudaIpcMemHandle; the host all-gathers the handles (rank
+   order) and every rank opens its peers'.  Payloads above the area's capacity keep using NCCL. */
+int sdv_comm_peer_handle(sdv_handle *h, void *out_64_bytes);
+int sdv_comm_peer_open(sdv_handle *h, const void *handles /* [world][64] */);
 
 /* Benchmark helper: time `repeats` launches of one kernel of the path on the resident window with CUDA
    events on the handle's stream; returns mean ms per launch.  which: 0 materialising residual+Jacobian

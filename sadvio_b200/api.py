@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
     L.sdv_eval_imu.argtypes = [C.c_void_p, C.POINTER(abi.SdvDelta), dp, dp, dp]
     L.sdv_comm_unique_id.argtypes = [C.c_void_p]
     L.sdv_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    L.sdv_comm_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.sdv_comm_peer_open.argtypes = [C.c_void_p, C.c_void_p]
     L.sdv_time_kernel.argtypes = [C.c_void_p, C.c_int32, C.c_int32, dp]
     L.sdv_debug_read.argtypes = [C.c_void_p, C.c_int32, dp, C.c_int64]
     L.sdv_debug_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -264,6 +266,35 @@ class Solver:
         buf = C.create_string_buffer(uid, 128)
         self._check(lib().sdv_comm_init(self._h, buf, rank, world))
 
+    def comm_peer_handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange area (sdv_comm_peer_handle)."""
+        buf = C.create_string_buffer(64)
+        self._check(lib().sdv_comm_peer_handle(self._h, buf))
+        return buf.raw
+
+    def comm_peer_open(self, handles: bytes):
+        """`handles`: the 64-byte handles of all ranks, concatenated in rank order."""
+        buf = C.create_string_buffer(handles, len(handles))
+        self._check(lib().sdv_comm_peer_open(self._h, buf))
+
+
+def comm_setup(solver: "Solver", dist, device) -> None:
+    """The whole multi-GPU setup of a handle through torch.distributed (backend nccl): the NCCL unique id from rank 0, then the
+    all-gather of the CUDA IPC handles of the peer-memory exchange areas.  `SDV_NO_PEER=1` keeps the exchanges on NCCL."""
+    import torch
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).to(device)
+    dist.broadcast(uid, 0)
+    solver.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    if world <= 8 and not os.environ.get("SDV_NO_PEER_SETUP"):
+        mine = torch.frombuffer(bytearray(solver.comm_peer_handle()), dtype=torch.uint8).to(device)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        solver.comm_peer_open(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
+
 
 def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
@@ -364,6 +395,8 @@ class B200Optimizer:
     def __init__(self, device: int = 0, cfg: abi.SdvConfig | None = None):
         self.solver = Solver(cfg, device)
         self.last_stats: dict | None = None
+        self.marginalization = (None, None)
+        self.last_marginal_info: dict | None = None
 
     def _solve(self, win: abi.Window):
         return self.solver.solve_window(win)
@@ -384,6 +417,19 @@ class B200Optimizer:
 
     def localMapBA(self, local_map: abi.Window, fixed_frame_number: int = 0) -> bool:  # noqa: N802
         return self._run(local_map, fixed_frame_number, False)
+
+    def marginalize(self, local_map: abi.Window, enable_sparsif: bool = False) -> bool:
+        """AOptimizer::marginalize(frame0 = the oldest keyframe of the window, frame1 = the next one, enable_sparsif)
+        (AngularAdjustmentCERESAnalytic.cpp:488-739) on the GPU.  The result stays on the optimizer like `_marginalization`:
+        `self.marginalization = (dense, sparse)` in the landmark indices of `local_map`; `local_map.dense_prior` is read as
+        `_marginalization_last`.  False (and the scheme reset) when the reference's marginalize() returns false."""
+        try:
+            dense, sparse, info = self.solver.marginalize(local_map, enable_sparsif)
+        except RuntimeError:
+            return False
+        self.last_marginal_info = info
+        self.marginalization = (dense, sparse)
+        return dense is not None
 
     def landmarkOptimization(self, local_map: abi.Window, frame: int, sanity_check=None) -> bool:  # noqa: N802
         """AOptimizer.cpp:98-150.  `sanity_check(l) -> bool` stands for ALandmark::sanityCheck (a data-model method outside the

@@ -12,6 +12,7 @@
 #include "sdv_chol_band.cuh"
 #include "sdv_preint.cuh"
 #include "sdv_marg.cuh"
+#include "sdv_peer.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -245,6 +246,12 @@ struct sdv_handle {
     LMState h_state;
     Accum h_acc;
     MargState *marg = nullptr; // scratch and result of the last sdv_marginalize (sdv_marg_host.cuh)
+    // peer-memory exchange (sdv_peer.cuh): own area, the peers' areas opened through CUDA IPC
+    unsigned char *d_peer = nullptr;
+    void *peer_base[PEER_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    PeerXchg peer{};
+    bool peer_ok = false;
+    size_t peer_bytes = 0;
 };
 
 namespace {
@@ -391,6 +398,9 @@ int sdv_destroy(sdv_handle *h) {
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_flush) cudaFree(h->d_flush);
     free_marg_state(h);
+    for (int p = 0; p < PEER_MAX_WORLD; p++)
+        if (h->peer_base[p] && p != h->rank) cudaIpcCloseMemHandle(h->peer_base[p]);
+    if (h->d_peer) cudaFree(h->d_peer);
     for (int i = 0; i < 4; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
@@ -450,6 +460,71 @@ int sdv_comm_init(sdv_handle *h, const void *uid, int32_t rank, int32_t world) {
     if (g_nccl.init_rank(&h->comm, world, id, rank) != 0) return fail(h, SDV_ERR_COMM, "ncclCommInitRank failed");
     h->rank = rank;
     h->world = world;
+    h->resident = false;
+    return SDV_OK;
+}
+
+// Peer-memory exchange (sdv_peer.cuh).  Layout of an exchange area, identical on every rank:
+//   [data 2 x world x cap doubles | flags 2 x world x PEER_MAX_CHUNKS u64 | epoch 8 u64]
+static size_t peer_layout(int world, size_t cap, size_t *o_flags, size_t *o_epoch) {
+    const size_t data = sizeof(double) * 2 * (size_t)world * cap;
+    *o_flags = data;
+    *o_epoch = data + sizeof(unsigned long long) * 2 * (size_t)world * PEER_MAX_CHUNKS;
+    return *o_epoch + 64;
+}
+static size_t peer_cap_doubles() {
+    const char *e = getenv("SDV_PEER_CAP_DOUBLES");
+    return e ? (size_t)std::max(1024ll, atoll(e)) : ((size_t)1 << 20); // 8 MB per (parity, source) slot
+}
+
+int sdv_comm_peer_handle(sdv_handle *h, void *out_64_bytes) {
+    if (!h || !out_64_bytes) return SDV_ERR_INVALID_ARGUMENT;
+    if (h->world < 2 || h->world > PEER_MAX_WORLD) return fail(h, SDV_ERR_INVALID_ARGUMENT, "peer exchange needs 2..8 ranks (call sdv_comm_init first)");
+    cudaSetDevice(h->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!h->d_peer) {
+        size_t of, oe;
+        h->peer_bytes = peer_layout(h->world, peer_cap_doubles(), &of, &oe);
+        CK(cudaMalloc((void **)&h->d_peer, h->peer_bytes));
+        CK(cudaMemset(h->d_peer, 0, h->peer_bytes));
+    }
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, h->d_peer));
+    std::memcpy(out_64_bytes, &hd, 64);
+    return SDV_OK;
+}
+
+int sdv_comm_peer_open(sdv_handle *h, const void *handles) {
+    if (!h || !handles) return SDV_ERR_INVALID_ARGUMENT;
+    if (!h->d_peer) return fail(h, SDV_ERR_INVALID_ARGUMENT, "sdv_comm_peer_handle first");
+    cudaSetDevice(h->device);
+    size_t of, oe;
+    const size_t cap = peer_cap_doubles();
+    peer_layout(h->world, cap, &of, &oe);
+    PeerXchg X;
+    std::memset(&X, 0, sizeof(X));
+    X.rank = h->rank;
+    X.world = h->world;
+    X.cap = cap;
+    for (int p = 0; p < h->world; p++) {
+        void *base = h->d_peer;
+        if (p != h->rank) {
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, static_cast<const unsigned char *>(handles) + 64 * (size_t)p, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(h, SDV_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+        }
+        h->peer_base[p] = base;
+        X.data[p] = reinterpret_cast<double *>(base);
+        X.flags[p] = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(base) + of);
+    }
+    X.epoch = reinterpret_cast<unsigned long long *>(h->d_peer + oe);
+    h->peer = X;
+    h->peer_ok = getenv("SDV_NO_PEER") == nullptr;
+    destroy_graph(h);
     h->resident = false;
     return SDV_OK;
 }
@@ -1604,8 +1679,23 @@ int launch_linearize(sdv_handle *h, int which, bool materialise) {
     return SDV_OK;
 }
 
+// one kernel over NVLink peer memory (sdv_peer.cuh) when the areas are open and the payload fits; false = use NCCL
+template <int MODE> bool peer_allreduce(sdv_handle *h, const PeerMap &m, size_t count) {
+    if (!h->peer_ok || count > h->peer.cap) return false;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 4095) / 4096, (size_t)std::min(PEER_MAX_CHUNKS, h->num_sms)));
+    k_peer_allreduce<MODE><<<grid, PEER_THREADS, 0, h->stream>>>(h->peer, m, (unsigned long long)count);
+    h->launches++;
+    return true;
+}
+
 int allreduce(sdv_handle *h, double *buf, size_t count) {
     if (h->world <= 1) return SDV_OK;
+    {
+        PeerMap m;
+        std::memset(&m, 0, sizeof(m));
+        m.buf = buf;
+        if (peer_allreduce<0>(h, m, count)) return SDV_OK;
+    }
     if (g_nccl.allreduce(buf, buf, count, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream) != 0) return fail(h, SDV_ERR_COMM, "ncclAllReduce failed");
     return SDV_OK;
 }
@@ -1662,6 +1752,14 @@ __global__ void k_pack_scalars(const LMState *st, Accum *acc, double *red, int d
 
 int reduce_scalars(sdv_handle *h, int which) {
     if (h->world <= 1) return SDV_OK;
+    {
+        PeerMap m;
+        std::memset(&m, 0, sizeof(m));
+        m.acc = h->d_acc;
+        m.st = h->d_st;
+        m.which = which;
+        if (peer_allreduce<2>(h, m, 7)) return SDV_OK;
+    }
     k_pack_scalars<<<1, 1, 0, h->stream>>>(h->d_st, h->d_acc, h->d_red, 0, which);
     int rc = allreduce(h, h->d_red, 7);
     if (rc != SDV_OK) return rc;
@@ -1761,12 +1859,22 @@ int launch_iteration(sdv_handle *h) {
         // reduced system without a band (dense prior over kept landmarks: wide-band fallback) exchanges all its rows.
         const int W = h->band_smem > 0 ? std::min(P.n_pad, 16 * (P.band_bw + 1)) : P.n_pad;
         const size_t count = (size_t)P.n_pad * W + 3 * (size_t)P.n_pad + 1;
-        const int grid = (int)std::min<size_t>((count + 255) / 256, (size_t)h->num_sms * 8);
-        k_band_exchange<<<grid, 256, 0, s>>>(h->d_Sb, h->d_xchg, h->d_acc, P.n_pad, P.ld, W, h->opt.gradient_tolerance, 0);
-        int rc = allreduce(h, h->d_xchg, count);
-        if (rc != SDV_OK) return rc;
-        k_band_exchange<<<grid, 256, 0, s>>>(h->d_Sb, h->d_xchg, h->d_acc, P.n_pad, P.ld, W, h->opt.gradient_tolerance, 1);
-        h->launches += 2;
+        PeerMap pm;
+        std::memset(&pm, 0, sizeof(pm));
+        pm.buf = h->d_Sb;
+        pm.n_pad = P.n_pad;
+        pm.ld = P.ld;
+        pm.W = W;
+        pm.acc = h->d_acc;
+        pm.grad_tol = h->opt.gradient_tolerance;
+        if (!peer_allreduce<1>(h, pm, count)) { // NCCL: pack -> all-reduce -> unpack
+            const int grid = (int)std::min<size_t>((count + 255) / 256, (size_t)h->num_sms * 8);
+            k_band_exchange<<<grid, 256, 0, s>>>(h->d_Sb, h->d_xchg, h->d_acc, P.n_pad, P.ld, W, h->opt.gradient_tolerance, 0);
+            int rc = g_nccl.allreduce(h->d_xchg, h->d_xchg, count, NCCL_DOUBLE, NCCL_SUM, h->comm, s) != 0 ? fail(h, SDV_ERR_COMM, "ncclAllReduce failed") : SDV_OK;
+            if (rc != SDV_OK) return rc;
+            k_band_exchange<<<grid, 256, 0, s>>>(h->d_Sb, h->d_xchg, h->d_acc, P.n_pad, P.ld, W, h->opt.gradient_tolerance, 1);
+            h->launches += 2;
+        }
     }
     if (h->band_smem == 0) { // k_chol_band prepares the system itself
         k_sysprep<<<1, 1024, 0, s>>>(h->d_P, h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_p, h->d_damp_p, h->d_graw_p);
@@ -1827,6 +1935,8 @@ int enqueue_epilogue(sdv_handle *h) {
 // ... and ONE copy to pinned host memory, issued behind the graph: its size depends on the window, the graph does not
 int enqueue_readback(sdv_handle *h) {
     CK(cudaMemcpyAsync(h->h_sol, h->d_out, solution_bytes(h->P), cudaMemcpyDeviceToHost, h->stream));
+    if (h->world > 1 && h->peer_ok) // the time-out word of the peer exchange rides along (a peer that never arrived: SDV_ERR_COMM)
+        CK(cudaMemcpyAsync(h->h_rb + sizeof(LMState) + sizeof(Accum) + 64, h->peer.epoch + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     return SDV_OK;
 }
 
@@ -1982,6 +2092,11 @@ int sdv_solve_resident(sdv_handle *h, sdv_stats *stats) {
     }
     CK(cudaGetLastError());
     (void)nd;
+    if (h->world > 1 && h->peer_ok) {
+        unsigned long long timed_out = 0;
+        std::memcpy(&timed_out, h->h_rb + sizeof(LMState) + sizeof(Accum) + 64, sizeof(timed_out));
+        if (timed_out) return fail(h, SDV_ERR_COMM, "peer-memory exchange timed out (a rank did not take part in the solve)");
+    }
     std::memcpy(h->h_rb, h->h_sol + sizeof(double) * 15 * (size_t)P.F, sizeof(LMState) + sizeof(Accum));
     std::memcpy(&h->h_state, h->h_rb, sizeof(LMState));
     std::memcpy(&h->h_acc, h->h_rb + sizeof(LMState), sizeof(Accum));

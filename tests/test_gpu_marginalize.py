@@ -122,7 +122,7 @@ def _next_window_parity(solver, win, prior_gpu, prior_orc, tol=5e-6):
     for a, b in ((d.dpose, d0.dpose), (d.dv, d0.dv), (d.dba, d0.dba), (d.dbg, d0.dbg)):
         if np.abs(b).max() > 0:
             assert _rel(a, b) <= tol, _rel(a, b)
-    assert abs(st["final_cost"] - st0["final_cost"]) <= 1e-6 * st0["final_cost"]
+    assert abs(st["final_cost"] - st0["final_cost"]) <= tol * st0["final_cost"]
 
 
 @pytest.mark.parametrize("name,kind,vio", [("small", 0, True), ("small", 1, True), ("small", 0, False), ("C2", 0, True)])

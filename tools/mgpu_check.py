@@ -19,13 +19,10 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     names = sys.argv[1:] or ["small", "C2", "C3"]
     s = api.Solver(device=local)
-    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-    if rank == 0:
-        uid = torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8).to(dev)
-    dist.broadcast(uid, 0)
-    s.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    api.comm_setup(s, dist, dev)
     for name in names:
         win = synth.make_c4() if name == "C4" else synth.make_window(name)
+        dist.barrier()                          # (rank 0 runs the oracle between windows: start every window together)
         rc, d, st = s.solve_window(win)
         s.upload(win)
         torch.cuda.synchronize()
