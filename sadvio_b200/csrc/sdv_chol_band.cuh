@@ -41,6 +41,28 @@ constexpr int BAND_MAX_STAGES = 16; // backward-solve ring (TMA bulk copies in f
 #define SDV_BAND_STREAM_UPDATES 0
 #endif
 constexpr bool BAND_STREAM_UPDATES = SDV_BAND_STREAM_UPDATES != 0;
+// FIRST-COLUMN STREAMING (-DSDV_BAND_STREAM1=1; parity green on B200, OFF by default: measured 117.7 us against 112.4 us at C3).
+// Idea: what gates a block step is not only the pivot chain but the two tensor-core tasks behind it — per-warp clock64 traces
+// (SDV_BAND_PROF, round 2, 26 steps on CTA 0): chain 2.4 k cycles per step, and per step the chain waits 0.75 k for (1,1), 0.5 k
+// for (2,1), 0.26 k for the update warps of step k-2, 0.5 k once for the hand-over of the two-way dissection.  With this switch
+// every first-column task is applied as rank-1 updates behind the chain, one pivot column at a time, by a warp that has its
+// operands anyway (measured: the two waits shrink to 0.46 k each — the streaming warps consume the pivot columns in groups of
+// four, so they still end ~0.5 k cycles after the last pivot — while the chain itself slows from 2.4 k to 3.0 k cycles per
+// step under the extra shared-memory traffic of five more warps reading every published column: a net loss):
+//   (1,1)  D_(k+1) -= P_1 P_1^T          warp 15 (role 7): 8 FMAs per lane and pivot
+//   (d,1)  W_(k+d,k+1) -= P_d P_1^T      the row-solve warp of distance d, whose lanes produce P_d[r][c] one column at a time; the
+//                                        two half-warps duplicate the solve and split the 16 columns (band_trsm16<true>)
+// Both accumulate from zero and are added to the window block at the end of the step, so they never wait at its start.  The
+// blocks the next step reads first are final ~100 cycles after the last pivot; the tensor-core warps keep the tasks (di, dj >= 2),
+// which nobody needs before the step after the next.  Unlike SDV_BAND_STREAM_UPDATES (all blocks of rows k+1 .. k+3 streamed:
+// the d = 3 row could not keep the chain's pace under the 128-register cap) every warp adds 8 FMAs per pivot to what it did.
+#ifndef SDV_BAND_STREAM1
+#define SDV_BAND_STREAM1 0
+#endif
+#if SDV_BAND_STREAM1 && SDV_BAND_STREAM_UPDATES
+#error "SDV_BAND_STREAM1 excludes SDV_BAND_STREAM_UPDATES"
+#endif
+constexpr bool BAND_STREAM1 = SDV_BAND_STREAM1 != 0;
 // Specialised full steps in the backward solve (band_backward_full_step below).  Default since round 2 (measured on B200:
 // 142 -> 135 us at C3 alone; all parity tests green); -DSDV_BAND_BACKWARD_V2=0 restores the generic loop.
 #ifndef SDV_BAND_BACKWARD_V2
@@ -550,7 +572,10 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
     const bool babe = cluster_size() == 2;
     const bool rev = babe && cluster_rank() == 1;
     const int bw = pl.bw, R = pl.R, ld = P.ld, pcs = pl.pcs, nbg = pl.nb;
-    const int nl = (nbg - bw + 1) / 2, nr = nbg - bw - nl;  // interior block rows of CTA 0 / CTA 1, separator = bw block rows
+#ifndef SDV_BAND_SKEW
+#define SDV_BAND_SKEW 0
+#endif
+    const int nl = (nbg - bw + 1) / 2 + SDV_BAND_SKEW, nr = nbg - bw - nl;  // interior block rows of CTA 0 / CTA 1, separator = bw block rows
     const int nint = babe ? (rev ? nr : nl) : nbg;          // block steps this CTA runs before the hand-over
     const int nb = babe ? nint + bw : nbg;                  // block rows of this CTA's system (interior + separator)
     if (rev) Lb += (size_t)nbg * (bw + 2) * 256;            // CTA 1 keeps its factor in the second half of the band storage
@@ -572,6 +597,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
 #ifdef SDV_BAND_PROF
     auto rdclk = [] { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; };
     long long tp[6] = {0, 0, 0, 0, 0, 0}, tc = rdclk(), tn;
+    long long tw[5] = {0, 0, 0, 0, 0}; // chain warp: its wait split by barrier [step, rhs, copy, (1,1), (2,1)]
 #define BAND_TICK(q) do { tn = rdclk(); tp[q] += tn - tc; tc = tn; } while (0)
 #define BAND_BUSY(q) do { tb[q] += rdclk() - tc; } while (0)
 #else
@@ -648,7 +674,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
     //   warps 4, 8, 12            idle (they share the chain's sub-partition)
     // A CTA-wide barrier per phase was tried first: a warp that sleeps at __syncthreads() while the chain warp runs took
     // 1.5-2 k cycles to get going again (per-warp clock64 traces), 3 times per step.
-    constexpr int N_COPY = BAND_STREAM_UPDATES ? 3 : 4;
+    constexpr int N_COPY = (BAND_STREAM_UPDATES || BAND_STREAM1) ? 3 : 4;
     int role = 6, ridx = 0, n_upd = 0; // 0 chain, 1 row solve (ridx = d), 2 rhs, 3 inverse, 4 update (ridx = u), 5 copy, 6 idle, 7 diagonal update
     {
         // Warp w runs on SM sub-partition w % 4, each with its own (narrow: 16 lanes) FP64 pipe and instruction cache.
@@ -663,7 +689,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
         if (warp == 0) role = 0;
         else if (warp == 7) role = 2;
         else if (warp == 11) role = 3;
-        else if (warp == 15 && BAND_STREAM_UPDATES) role = 7; // streaming update of the next diagonal block
+        else if (warp == 15 && (BAND_STREAM_UPDATES || BAND_STREAM1)) role = 7; // streaming update of the next diagonal block
         else if (warp == 15 || (warp & 3) == 0) { // 4, 8, 12 (, 15): light (copies), so the chain's sub-partition can host three of them
             role = 5;
             ridx = warp == 15 ? 3 : (warp >> 2) - 1;
@@ -752,7 +778,14 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
         __syncthreads(); // this CTA's interior steps are complete
         if (s_fail) acc->chol_fail = 1;
         __threadfence();
+#ifdef SDV_BAND_PROF
+        const long long th0 = rdclk();
+#endif
         cluster_sync_all(); // #1: ... and so are CTA 1's; its window and right-hand side are visible through DSMEM
+#ifdef SDV_BAND_PROF
+        if (threadIdx.x == 0 && prof) prof[23] = (double)(rdclk() - th0); // time CTA 0 waited for CTA 1 at the hand-over
+        const long long th1 = rdclk();
+#endif
         if (__ldcg(&acc->chol_fail) != 0 || __ldcg(&acc->schur_fail) != 0) { // uniform over the cluster (CTA 1 tests the same words after #1)
             if (threadIdx.x == 0) {
                 st->step_valid = 0;
@@ -771,6 +804,9 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
         }
         for (int t = threadIdx.x; t < bw * BN; t += BCT) gs[nint * BN + t] += dsmem_load(gs + (P.n_pad - 1 - (nint * BN + t)), 1);
         __syncthreads();
+#ifdef SDV_BAND_PROF
+        if (threadIdx.x == 0 && prof) prof[31] = (double)(rdclk() - th1); // separator hand-over (flags + DSMEM reads)
+#endif
     }
 #endif
     if (role == 0) {
@@ -778,14 +814,25 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
         for (int k = BAND_KBEG; k < BAND_KEND; k++) {
             const int par = k & 1;
             const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
+#ifdef SDV_BAND_PROF
+#define BAND_WTICK(q) do { long long t_ = rdclk(); tw[q] += t_ - twc; twc = t_; } while (0)
+            long long twc = rdclk();
+#else
+#define BAND_WTICK(q) do { } while (0)
+#endif
             if (k >= 2) {
                 mbar_wait_cta(&bar_step[par], ph(k - 2)); // every reader of this panel buffer (step k-2) is done
+                BAND_WTICK(0);
                 mbar_wait_cta(&bar_rhs[par], ph(k - 2));
+                BAND_WTICK(1);
                 mbar_wait_cta(&bar_copy[par], ph(k - 2)); // ... and it has been written out; block row k+bw is resident
+                BAND_WTICK(2);
             }
             if (k >= 1) { // blocks (k,k) and (k+1,k) updated through step k-1 = tasks (1,1) and (2,1) of that step
                 mbar_wait_cta(&bar_c1[par ^ 1][1], ph(k - 1));
+                BAND_WTICK(3);
                 if (bw >= 2 && k + 1 < nb) mbar_wait_cta(&bar_c1[par ^ 1][2], ph(k - 1)); // task (2,1) exists only if row k+1 does and bw >= 2
+                BAND_WTICK(4);
             }
             BAND_TICK(1);
             double a[16];
@@ -867,6 +914,34 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
 #pragma unroll
                     for (int c = 0; c < 16; c++) grow[c] = pan[c * pcs + 16 * d + r];
                 }
+            } else if (BAND_STREAM1) {
+                // solve + first-column update (d,1), streamed behind the chain: lane (r, h) = row r, columns 8 h .. 8 h + 7 of the update
+                const int r = lane & 15, h = lane >> 4;
+                double t[16], w[8];
+                const double *src = Wk(d, 0) + r * WSTR;
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(src + c);
+                    t[c] = v.x;
+                    t[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) w[c] = 0.0;
+                band_trsm16<true>(t, w, h, pan, pcs, invs + par * BN, h == 0 ? pan + 16 * d + r : nullptr, pcs,
+                                  h == 0 ? Lb + ((size_t)k * (bw + 2) + d) * 256 + r * 16 : nullptr, &colbar[par][0], ph(k));
+                // W_(k+d,k+1) += w: the block is final through step k-1 once task (d+1, 2) of that step is done (a tensor-core warp);
+                // d = bw: a fresh row (waited for above)
+                if (k >= 1 && d < bw) mbar_wait_cta(&bar_c2[par ^ 1][d + 1], ph(k - 1));
+                double *tgt = Wk(d, 1) + r * WSTR + 8 * h;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    double2 v = *reinterpret_cast<double2 *>(tgt + c);
+                    v.x += w[c];
+                    v.y += w[c + 1];
+                    *reinterpret_cast<double2 *>(tgt + c) = v;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(&bar_c1[par][d]); // task (d,1) of this step is done
             } else if (lane < 16) {
                 double t[16];
                 const double *src = Wk(d, 0) + lane * WSTR;
@@ -974,17 +1049,21 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
             // two passes: first-column tasks (dj = 1) first, the next step waits for them
             // with BAND_STREAM_UPDATES the block rows 1..3 are not updated here: the streaming warps (roles 7 and 1) do it
 #pragma unroll
+            // with BAND_STREAM1 the first block column (dj = 1) is not updated here at all (role 7 and the row-solve warps do it); the
+            // second one (dj = 2) goes first and is signalled: those blocks are the targets of the next step's streamed updates
             for (int pass = 0; pass < (BAND_STREAM_UPDATES ? 3 : 2); pass++)
 #pragma unroll
                 for (int q = 0; q < MAXV; q++) { // my virtual workers are sorted by offset, i.e. the tasks of a column come in di order
                     if (q >= nv) continue;
                     const int dj = vdj[q], di = dj + vo[q];
-                    if ((BAND_STREAM_UPDATES ? (dj < 3 ? dj - 1 : 2) : (dj == 1 ? 0 : 1)) != pass || di > nd || (BAND_STREAM_UPDATES && di <= 3)) continue;
+                    if ((BAND_STREAM_UPDATES ? (dj < 3 ? dj - 1 : 2) : (BAND_STREAM1 ? (dj == 2 ? 0 : 1) : (dj == 1 ? 0 : 1))) != pass || di > nd ||
+                        (BAND_STREAM_UPDATES && di <= 3) || (BAND_STREAM1 && dj == 1))
+                        continue;
                     if (di >= 2) mbar_wait_cta(&bar_p[par][di], ph(k));
                     if (dj >= 2) mbar_wait_cta(&bar_p[par][dj], ph(k));
                     BAND_TICK(1);
                     band_update_dmma(Wk(di, dj), pan + 16 * di, pan + 16 * dj, pcs, lane);
-                    if (dj <= (BAND_STREAM_UPDATES ? 2 : 1)) { // the first (two) block column(s) are waited for by the next step
+                    if (dj <= ((BAND_STREAM_UPDATES || BAND_STREAM1) ? 2 : 1)) { // the first (two) block column(s) are waited for by the next step
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cta(dj == 1 ? &bar_c1[par][di] : &bar_c2[par][di]);
                     }
@@ -1001,10 +1080,14 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
         // ------------------------------------------------------------------ D_(k+1) -= P_(k+1,k) P_(k+1,k)^T, streamed behind the chain:
         // lane (r, hh) holds entries 8 hh .. 8 hh + 7 of row r and applies one rank-1 update per published pivot column
         const int r = lane & 15, hh = lane >> 4;
-        for (int k = 0; k + 1 < nb; k++) {
+        for (int k = BAND_KBEG; k < BAND_KEND; k++) {
+            if (k + 1 >= nb) { // no next diagonal block
+                next_k();
+                continue;
+            }
             const int par = k & 1;
             const double *pan = pan0 + par * pl.pan_doubles;
-            if (k >= 1) { // the block is final through step k-1: task (2,2) of that step, or a fresh row when bw == 1
+            if (!BAND_STREAM1 && k >= 1) { // the block is final through step k-1: task (2,2) of that step, or a fresh row when bw == 1
                 if (bw >= 2) mbar_wait_cta(&bar_c2[par ^ 1][2], ph(k - 1));
                 else if (k >= 2) mbar_wait_cta(&bar_copy[par], ph(k - 2));
             }
@@ -1013,7 +1096,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
             double dd[8];
 #pragma unroll
             for (int c = 0; c < 8; c += 2) {
-                const double2 v = *reinterpret_cast<const double2 *>(dsrc + c);
+                const double2 v = BAND_STREAM1 ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2 *>(dsrc + c);
                 dd[c] = v.x;
                 dd[c + 1] = v.y;
             }
@@ -1029,8 +1112,23 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
                     dd[j + 1] = fma(-x, q.y, dd[j + 1]);
                 }
             }
+            if (BAND_STREAM1) {
+                // accumulated from zero: add to the block once it is final through step k-1 (task (2,2) of that step: long done)
+                if (k >= 1) {
+                    if (bw >= 2) mbar_wait_cta(&bar_c2[par ^ 1][2], ph(k - 1));
+                    else if (k >= 2) mbar_wait_cta(&bar_copy[par], ph(k - 2));
+                }
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2 *>(dsrc + c) = make_double2(dd[c], dd[c + 1]);
+                for (int c = 0; c < 8; c += 2) {
+                    double2 v = *reinterpret_cast<double2 *>(dsrc + c);
+                    v.x += dd[c];
+                    v.y += dd[c + 1];
+                    *reinterpret_cast<double2 *>(dsrc + c) = v;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2 *>(dsrc + c) = make_double2(dd[c], dd[c + 1]);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&bar_c1[par][1]); // task (1,1) of this step is done
             BAND_TICK(2);
@@ -1194,6 +1292,8 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
 #ifdef SDV_BAND_PROF
     if (prof && lane == 0)
         for (int q = 0; q < 6; q++) prof[warp * 8 + q] = (double)tp[q]; // warp 0: [setup, wait, chain, -, tail, backward]
+    if (prof && lane == 0 && warp == 0)
+        for (int q = 0; q < 5; q++) prof[(q >> 1) * 8 + 6 + (q & 1)] = (double)tw[q]; // free slots 6, 7 of warps 0, 1, 2
 #endif
 
     // ---------------------------------------------------------------------- reduced-parameter update, model-decrease terms,
