@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE (see oracle/README.md).  CPU restatement of the dense core of the marginal-prior construction of the
-// reference — groundwork for SURVEY.md §8 row a15 ("next"): the checker comes before the CUDA path.
+// reference — the checker of sdv_marginalize / sdv_schur_prior.
 //
 //   Marginalization::computeInformationAndGradient   cpp/src/optimizers/marginalization.cpp:145-211
 //   Marginalization::computeSchurComplement          cpp/src/optimizers/marginalization.cpp:213-265

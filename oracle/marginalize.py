@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE (oracle/README.md) — groundwork for SURVEY.md §8 row a15, no CUDA path yet.
+"""TEST INFRASTRUCTURE (oracle/README.md) — the checker of sdv_marginalize.
 
 Restatement, on the flattened window of the C ABI, of the marginalisation the back end runs before every window solve
 (first and chained: a dense prior already attached to the window is `_marginalization_last`), VIO and VO, for both optimizers:
