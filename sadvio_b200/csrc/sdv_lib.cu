@@ -587,7 +587,9 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
             h->in2_bytes = A2.size * 2;
         }
     }
-    const bool have_pool = h->pool.start(6) && !getenv("SDV_NO_HOST_POOL");
+    // 3 packing jobs + 3 structure parts beside this thread (SDV_HOST_PARTS up to 8 was measured on the 16-thread box of the pool:
+    // no gain over 4 — more spinning workers cost what the shorter parts save)
+    const bool have_pool = h->pool.start(getenv("SDV_HOST_PARTS") ? 10 : 6) && !getenv("SDV_NO_HOST_POOL");
     HostPool::Group g_bulk, g_struct;
     bool bulk_copy_issued = false, bulk_copy_failed = false; // written by the packing job that finishes last, read after pool.wait(g_bulk)
     std::atomic<int> bulk_left{3};
@@ -650,18 +652,22 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     //      per-part slot counts into offsets and the parts copy their lists into place.
     const bool par_struct = have_pool && h->world == 1 && O >= 16384 && !(w->sparse_prior && w->sparse_prior->n_p2l > 0);
     if (par_struct) {
-        constexpr int NPART = 4;
+        static constexpr int MAXPART = 8;
+        static const int NPART = [] { // parts of the structure pass (this thread + pool threads); SDV_HOST_PARTS for A/B measurements
+            const char *e = getenv("SDV_HOST_PARTS");
+            return std::max(1, std::min(MAXPART, e ? atoi(e) : 4));
+        }();
         struct alignas(128) Part { // (one cache line pair each: the threads update their own counters all the time)
             int ob = 0, oe = 0;          // observation range, starting at the first observation of a landmark
             int l_lo = 0, l_hi = -1;     // landmarks whose CSR pointer / slot count this part owns: (last landmark before ob, last landmark in range]
             std::vector<int> sf, sop, cnt; // slot frames, slot observation pointers (global: slot_obs is written in place), slots per landmark
             std::vector<char> used, same;
             int max_slots = 1, bad = 0;
-        } part[NPART];
+        } part[MAXPART];
         const int32_t *ol = w->obs_lmk, *of = w->obs_frame, *oc = w->obs_cam;
         slot_obs.resize((size_t)O + 1);
         same_prev.resize((size_t)L + 1);
-        int cutp[NPART + 1];
+        int cutp[MAXPART + 1];
         cutp[0] = 0;
         cutp[NPART] = O;
         for (int t = 1; t < NPART; t++) {
@@ -761,7 +767,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         for (int t = 1; t < NPART; t++) h->pool.submit(g_struct, [&run_part, t] { run_part(t); });
         run_part(0);
         h->pool.wait(g_struct);
-        int any_bad = 0, tot_slots = 0, off[NPART + 1];
+        int any_bad = 0, tot_slots = 0, off[MAXPART + 1];
         for (int t = 0; t < NPART; t++) {
             any_bad |= part[t].bad;
             off[t] = tot_slots;
