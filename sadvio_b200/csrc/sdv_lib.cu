@@ -13,6 +13,7 @@
 #include "sdv_preint.cuh"
 #include "sdv_marg.cuh"
 #include "sdv_peer.cuh"
+#include "sdv_struct.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -252,6 +253,10 @@ struct sdv_handle {
     PeerXchg peer{};
     bool peer_ok = false;
     size_t peer_bytes = 0;
+    cudaGraphExec_t sgraph_exec = nullptr; // the eight launches of the device structure pass, replayed per upload
+    const void *sgraph_dP = nullptr;
+    int sgraph_capO = 0, sgraph_capL = 0;
+    bool force_host_slots = false; // upload: the device structure pass (sdv_struct.cuh) does not apply to this window, redo on the host
 };
 
 namespace {
@@ -380,6 +385,7 @@ int sdv_destroy(sdv_handle *h) {
     if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->graph) cudaGraphDestroy(h->graph);
+    if (h->sgraph_exec) cudaGraphExecDestroy(h->sgraph_exec);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -589,43 +595,57 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     }
     // 3 packing jobs + 3 structure parts beside this thread (SDV_HOST_PARTS up to 8 was measured on the 16-thread box of the pool:
     // no gain over 4 — more spinning workers cost what the shorter parts save)
-    const bool have_pool = h->pool.start(getenv("SDV_HOST_PARTS") ? 10 : 6) && !getenv("SDV_NO_HOST_POOL");
+    const bool have_pool = h->pool.start(getenv("SDV_HOST_PARTS") ? 12 : 8) && !getenv("SDV_NO_HOST_POOL");
     HostPool::Group g_bulk, g_struct;
-    bool bulk_copy_issued = false, bulk_copy_failed = false; // written by the packing job that finishes last, read after pool.wait(g_bulk)
-    std::atomic<int> bulk_left{3};
+    bool bulk_copy_issued = false; // written by the packing job that finishes last, read after pool.wait(g_bulk)
+    std::atomic<int> bulk_failed{0};
+    constexpr int NPIECE = 5;
+    std::atomic<int> bulk_left{NPIECE};
     {
         unsigned char *hb2 = h->h_in2, *db2 = h->d_in2;
-        const size_t bytes2 = A2.size;
         const int dev = h->device;
         cudaStream_t cs = h->copy_stream;
         cudaEvent_t evb = h->ev_bulk;
-        // three pieces of similar size (measurements in two halves; indices + landmarks); the piece that finishes last issues the
-        // H2D copy on the copy stream, so packing AND transfer of the bulk data overlap the structure pass of the other threads
-        auto pack_bulk = [=, &bulk_copy_issued, &bulk_copy_failed, &bulk_left](int piece, bool issue_copy) {
-            const size_t mbytes = sizeof(double) * (size_t)mplanes * O, half = (mbytes / 2) & ~size_t(63);
+        // five pieces of similar size (measurements in three parts; observation indices; landmarks + weights).  Every piece issues
+        // the H2D copy of ITS OWN byte range on the copy stream as soon as it is packed — packing and transfer overlap each other
+        // and the structure pass of the other threads —; the piece that finishes last records the event the solve stream waits for.
+        auto pack_bulk = [=, &bulk_copy_issued, &bulk_failed, &bulk_left](int piece, bool issue_copy) {
+            const size_t mbytes = sizeof(double) * (size_t)mplanes * O, third = (mbytes / 3) & ~size_t(63);
             const unsigned char *msrc = reinterpret_cast<const unsigned char *>(kind == SDV_FACTOR_ANGULAR ? (const void *)w->obs_bearing : (const void *)w->obs_uv);
-            if (piece == 0 && O) std::memcpy(hb2 + q_om, msrc, half);
-            if (piece == 1 && O) std::memcpy(hb2 + q_om + half, msrc + half, mbytes - half);
-            if (piece == 2) {
-                if (O) {
-                    std::memcpy(hb2 + q_ol, w->obs_lmk, 4 * (size_t)O);
-                    int *fc = reinterpret_cast<int *>(hb2 + q_ofc);
-                    for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o]; // validated by the other threads; only used if that passes
-                    if (w->obs_sigma) {
-                        double *ow = reinterpret_cast<double *>(hb2 + q_ow);
-                        for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
-                    }
-                }
-                if (L > 0) std::memcpy(hb2 + q_lt, w->lmk_t, sizeof(double) * 3 * (size_t)L);
+            size_t c0 = 0, c1 = 0; // byte range of the arena this piece fills
+            if (piece < 3 && O) {
+                const size_t m0 = third * piece, m1 = piece == 2 ? mbytes : third * (piece + 1);
+                std::memcpy(hb2 + q_om + m0, msrc + m0, m1 - m0);
+                c0 = q_om + m0;
+                c1 = q_om + m1;
             }
-            if (issue_copy && bulk_left.fetch_sub(1) == 1) {
-                bool ok = cudaSetDevice(dev) == cudaSuccess && cudaMemcpyAsync(db2, hb2, bytes2, cudaMemcpyHostToDevice, cs) == cudaSuccess &&
-                          cudaEventRecord(evb, cs) == cudaSuccess;
-                bulk_copy_issued = ok;
-                bulk_copy_failed = !ok;
+            if (piece == 3 && O) {
+                std::memcpy(hb2 + q_ol, w->obs_lmk, 4 * (size_t)O);
+                int *fc = reinterpret_cast<int *>(hb2 + q_ofc);
+                for (int o = 0; o < O; o++) fc[o] = w->obs_frame[o] * C + w->obs_cam[o]; // validated by the other threads; only used if that passes
+                c0 = q_ol;
+                c1 = q_ofc + 4 * (size_t)O; // (q_ol and q_ofc are adjacent in the arena)
+            }
+            if (piece == 4) {
+                if (L > 0) std::memcpy(hb2 + q_lt, w->lmk_t, sizeof(double) * 3 * (size_t)L);
+                c0 = q_lt;
+                c1 = q_lt + sizeof(double) * 3 * (size_t)std::max(L, 1);
+                if (O && w->obs_sigma) {
+                    double *ow = reinterpret_cast<double *>(hb2 + q_ow);
+                    for (int o = 0; o < O; o++) ow[o] = 1.0 / w->obs_sigma[o];
+                    c1 = q_ow + sizeof(double) * (size_t)O; // (q_lt and q_ow are adjacent in the arena)
+                }
+            }
+            if (!issue_copy) return;
+            bool ok = cudaSetDevice(dev) == cudaSuccess;
+            if (ok && c1 > c0) ok = cudaMemcpyAsync(db2 + c0, hb2 + c0, c1 - c0, cudaMemcpyHostToDevice, cs) == cudaSuccess;
+            if (!ok) bulk_failed.store(1);
+            if (bulk_left.fetch_sub(1) == 1) { // every piece has issued its copy: the event closes them all
+                if (cudaEventRecord(evb, cs) != cudaSuccess) bulk_failed.store(1);
+                bulk_copy_issued = true;
             }
         };
-        for (int piece = 0; piece < 3; piece++) {
+        for (int piece = 0; piece < NPIECE; piece++) {
             if (have_pool) h->pool.submit(g_bulk, [pack_bulk, piece] { pack_bulk(piece, true); });
             else pack_bulk(piece, false);
         }
@@ -651,7 +671,96 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     //      fills its stretch of the CSR pointer and builds the slot lists of its landmarks; a short serial step turns the
     //      per-part slot counts into offsets and the parts copy their lists into place.
     const bool par_struct = have_pool && h->world == 1 && O >= 16384 && !(w->sparse_prior && w->sparse_prior->n_p2l > 0);
-    if (par_struct) {
+    // ---- device structure pass (sdv_struct.cuh): the slot lists and tiles are derived on the GPU from the observation arrays of
+    //      the bulk arena; the host only validates, counts slots and records the keyframe span of every landmark (the band of the
+    //      reduced system).  Windows with landmarks in the reduced system (dense / sparsified-VO priors) and observation lists
+    //      that are not grouped by keyframe keep the host path below.
+    bool gpu_struct = par_struct && !h->force_host_slots && !getenv("SDV_HOST_SLOTS") && !w->dense_prior &&
+                      !(w->sparse_prior && (w->sparse_prior->has_lmk_prior || w->sparse_prior->n_l2l > 0));
+    std::vector<int> span_max; // [F]: largest free keyframe index among the landmarks whose smallest free keyframe is f (-1: none)
+    if (gpu_struct) {
+        constexpr int GP = 4;
+        struct alignas(128) GPart {
+            std::vector<char> used;
+            std::vector<int> span;
+            int nslots = 0, max_slots = 1, bad = 0, ungrouped = 0;
+        } gp[GP];
+        const int32_t *ol = w->obs_lmk, *of = w->obs_frame, *oc = w->obs_cam;
+        int cutp[GP + 1];
+        cutp[0] = 0;
+        cutp[GP] = O;
+        for (int t = 1; t < GP; t++) {
+            int c0 = (int)((long long)O * t / GP);
+            while (c0 < O && c0 > 0 && ol[c0] == ol[c0 - 1]) c0++;
+            cutp[t] = std::max(c0, cutp[t - 1]);
+        }
+        const int first_fixed = F - w->n_fixed; // frames >= first_fixed are constant (no column)
+        auto light_part = [&](int t) {
+            GPart pt;
+            pt.used.assign(F, 0);
+            pt.span.assign(F, -1);
+            const int ob = cutp[t], oe = cutp[t + 1];
+            int prev = ob > 0 ? ol[ob - 1] : -1;
+            unsigned bad = (unsigned)(prev < -1) | (unsigned)(prev >= L);
+            int frs[MAX_SLOTS + 1], nfr = 0, cur = -1, fmin = F, fmax = -1;
+            auto close = [&] {
+                pt.max_slots = std::max(pt.max_slots, nfr);
+                if (fmax >= 0) pt.span[fmin] = std::max(pt.span[fmin], fmax);
+            };
+            for (int o = ob; o < oe && !bad; o++) {
+                const int l = ol[o], f = of[o], c = oc[o];
+                bad |= (unsigned)(l < 0) | (unsigned)(l >= L) | (unsigned)(f < 0) | (unsigned)(f >= F) | (unsigned)(c < 0) | (unsigned)(c >= C) | (unsigned)(l < prev);
+                if (bad) break;
+                if (l != prev) {
+                    close();
+                    prev = l;
+                    nfr = 0;
+                    cur = -1;
+                    fmin = F;
+                    fmax = -1;
+                }
+                if (f != cur) { // a new slot — unless this keyframe appeared before in the landmark's list (host grouping then)
+                    for (int q = 0; q < nfr && q < MAX_SLOTS; q++) pt.ungrouped |= frs[q] == f;
+                    if (nfr < MAX_SLOTS + 1) frs[nfr] = f;
+                    nfr = std::min(nfr + 1, MAX_SLOTS + 1);
+                    pt.nslots++;
+                    cur = f;
+                    pt.used[f] = 1;
+                    if (f < first_fixed) {
+                        fmin = std::min(fmin, f);
+                        fmax = std::max(fmax, f);
+                    }
+                }
+            }
+            close();
+            pt.bad = bad ? 1 : 0;
+            gp[t] = std::move(pt);
+        };
+        for (int t = 1; t < GP; t++) h->pool.submit(g_struct, [&light_part, t] { light_part(t); });
+        light_part(0);
+        h->pool.wait(g_struct);
+        span_max.assign(F, -1);
+        int ungrouped = 0;
+        for (int t = 0; t < GP; t++) {
+            if (gp[t].bad) return fail(h, SDV_ERR_INVALID_ARGUMENT, "observation index out of range or observations not landmark-major (reference walk order)");
+            ungrouped |= gp[t].ungrouped;
+            ns += gp[t].nslots;
+            max_slots = std::max(max_slots, gp[t].max_slots);
+            for (int f = 0; f < F; f++) {
+                pose_used[f] |= gp[t].used[f];
+                span_max[f] = std::max(span_max[f], gp[t].span[f]);
+            }
+        }
+        if (max_slots > MAX_SLOTS) return fail(h, SDV_ERR_UNSUPPORTED, "a landmark is observed from more than 32 keyframes (kernel limit of this build)");
+        nso = O;
+        if (ungrouped) { // a keyframe re-appears after another one inside a landmark's list: general grouping, on the host
+            h->force_host_slots = true;
+            const int rc2 = upload_impl(h, w, sync);
+            h->force_host_slots = false;
+            return rc2;
+        }
+    }
+    if (par_struct && !gpu_struct) {
         static constexpr int MAXPART = 8;
         static const int NPART = [] { // parts of the structure pass (this thread + pool threads); SDV_HOST_PARTS for A/B measurements
             const char *e = getenv("SDV_HOST_PARTS");
@@ -818,7 +927,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
             }
         }
         slot_obs_ptr[ns] = nso;
-    } else
+    } else if (!gpu_struct)
     // one pass over the observations: range checks, landmark-major order, CSR pointer per landmark, frames in use
     {
         const int32_t *ol = w->obs_lmk, *of = w->obs_frame, *oc = w->obs_cam;
@@ -1047,17 +1156,19 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     // ---- tiles of the fused kernels: consecutive landmarks of this rank, at most FT slots and FT_LMK landmarks each
     std::vector<int> &tile_ptr = h->tmp_tile_ptr;
     tile_ptr.clear();
+    int tile_capq = 1;
     {
         // tile capacity: the fused kernels run 2 CTAs per SM; when the whole rank fits in ONE wave of tiles of at most FT slots the
         // tiles are sized for exactly that (a second, nearly empty wave would double the kernel time: everything here is
         // latency-bound), otherwise full tiles
-        const int nsl_rank = slot_ptr[l1] - slot_ptr[l0], waves1 = h->num_sms * 2;
+        const int nsl_rank = gpu_struct ? nslots : slot_ptr[l1] - slot_ptr[l0], waves1 = h->num_sms * 2;
         int cap = FT;
         if (const char *e = getenv("SDV_FUSED_TILE_SLOTS")) cap = std::max(1, std::min(FT, atoi(e))); // tests: the result must not depend on the tiling
         else if (nsl_rank <= (long long)waves1 * (FT - max_slots)) cap = std::max(32, (nsl_rank + waves1 - 1) / waves1 + max_slots);
         cap = std::min(cap, FT);
+        tile_capq = std::max(1, cap - max_slots + 1); // device tiling: buckets of this many slots (sdv_struct.cuh)
         int l = l0;
-        while (l < l1) {
+        while (!gpu_struct && l < l1) {
             tile_ptr.push_back(l);
             int nsl = 0, nlm = 0;
             while (l < l1 && nlm < FT_LMK && nsl + (slot_ptr[l + 1] - slot_ptr[l]) <= (nlm == 0 ? FT : cap)) {
@@ -1068,7 +1179,8 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         }
         tile_ptr.push_back(l1);
     }
-    const int ntiles = (int)tile_ptr.size() - 1;
+    // (device tiling: an upper bound — one tile per bucket, plus the cuts every FT_LMK landmarks; only used to size grids and buffers)
+    const int ntiles = gpu_struct ? (nslots > 0 ? nslots / tile_capq + (l1 - l0) / FT_LMK + 2 : 0) : (int)tile_ptr.size() - 1;
 
     auto t_s3 = std::chrono::steady_clock::now();
     // ---- dense prior column maps
@@ -1191,7 +1303,29 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     //      envelope of the matrix, so max_i (i - first coupled block of row i) bounds the fill: when that band (plus two
     //      look-ahead block rows) fits in the shared memory of one SM, the whole factorisation runs in ONE CTA (k_chol_band).
     int band_bw = -1;
-    if (n_pad / 16 <= 256) {
+    if (gpu_struct) {
+        // every factor couples a contiguous column range [cmin, cmax]: the half-bandwidth is the widest range in 16-column blocks
+        band_bw = 0;
+        auto clique = [&](int cmin, int cmax) {
+            if (cmin >= 0 && cmax >= cmin) band_bw = std::max(band_bw, cmax / 16 - cmin / 16);
+        };
+        auto frame_lo = [&](int f) { return pose_col[f] >= 0 ? pose_col[f] : vb_col[f]; };
+        auto frame_hi = [&](int f) { return vb_col[f] >= 0 ? vb_col[f] + 8 : (pose_col[f] >= 0 ? pose_col[f] + 5 : -1); };
+        for (int f = 0; f < F; f++) {
+            clique(frame_lo(f), frame_hi(f));                                   // diagonal blocks (pose prior, damping)
+            if (span_max[f] >= 0) clique(pose_col[f], pose_col[span_max[f]] + 5); // landmarks couple the POSES of the keyframes that see them
+        }
+        for (int p = 0; p < Pn; p++) { // IMUFactor + IMUBiasFactor couple all 15 parameters of both keyframes
+            const int a = w->imu_i[p], b = w->imu_j[p];
+            int lo = -1, hi = -1;
+            for (int f : {a, b}) {
+                if (frame_lo(f) >= 0) lo = lo < 0 ? frame_lo(f) : std::min(lo, frame_lo(f));
+                hi = std::max(hi, frame_hi(f));
+            }
+            clique(lo, hi);
+        }
+        // (the sparsified VIO prior without PoseToLandmark factors is one more diagonal clique of its keyframe)
+    } else if (n_pad / 16 <= 256) {
         std::vector<TMask> low16;
         build_low(16, low16);
         const int nb16 = n_pad / 16;
@@ -1209,6 +1343,12 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     if (band_bw >= 0 && std::max(band_bw, 1) <= BAND_MAX_BW && !getenv("SDV_CHOL_VARIANT") && !getenv("SDV_CHOL_DENSE")) {
         const BandPlan plb = band_plan(n_pad, std::max(band_bw, 1));
         band_applies = sizeof(double) * (size_t)plb.o_end <= 220 * 1024 && (size_t)plb.nb * (std::max(band_bw, 1) + 2) * 256 <= (size_t)(n_pad + 32) * ld;
+    }
+    if (gpu_struct && !band_applies) { // wide band: the cluster Cholesky wants the tile pattern, which is built from the host's slot lists
+        h->force_host_slots = true;
+        const int rc2 = upload_impl(h, w, sync);
+        h->force_host_slots = false;
+        return rc2;
     }
     if (Tt <= 128 && !band_applies) {
         std::vector<TMask> low;
@@ -1245,8 +1385,14 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     size_t o_Ts = A.add(D * 12 * C), o_K = A.add(D * 4 * C), o_cw = A.add(D * C);
     size_t o_lc = A.add(4 * std::max(L, 1));
     size_t o_tnz = A.add(4 * tile_nz.size());
-    size_t o_tile = A.add(4 * tile_ptr.size());
-    size_t o_sp = A.add(4 * (L + 1)), o_sf = A.add(4 * std::max(nslots, 1)), o_sop = A.add(4 * (nslots + 1)), o_so = A.add(4 * std::max(nslotobs, 1));
+    size_t o_tile = 0, o_sp = 0, o_sf = 0, o_sop = 0, o_so = 0;
+    if (!gpu_struct) {
+        o_tile = A.add(4 * tile_ptr.size());
+        o_sp = A.add(4 * (L + 1));
+        o_sf = A.add(4 * std::max(nslots, 1));
+        o_sop = A.add(4 * (nslots + 1));
+        o_so = A.add(4 * std::max(nslotobs, 1));
+    }
     size_t o_ii = A.add(4 * std::max(Pn, 1)), o_ij = A.add(4 * std::max(Pn, 1));
     size_t o_idt = A.add(D * std::max(Pn, 1)), o_idR = A.add(D * 9 * std::max(Pn, 1)), o_idv = A.add(D * 3 * std::max(Pn, 1)),
            o_idp = A.add(D * 3 * std::max(Pn, 1)), o_icov = A.add(D * 81 * std::max(Pn, 1));
@@ -1306,7 +1452,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     }
     std::memcpy(hb + o_pc, pose_col.data(), 4 * F);
     std::memcpy(hb + o_tnz, tile_nz.data(), 4 * tile_nz.size());
-    std::memcpy(hb + o_tile, tile_ptr.data(), 4 * tile_ptr.size());
+    if (!gpu_struct) std::memcpy(hb + o_tile, tile_ptr.data(), 4 * tile_ptr.size());
     std::memcpy(hb + o_vc, vb_col.data(), 4 * F);
     std::memcpy(hb + o_Ts, w->T_s_f, D * 12 * C);
     std::memcpy(hb + o_K, w->K, D * 4 * C);
@@ -1316,10 +1462,12 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         at<double>(hb, o_cw)[c] = 1.0 / sigma;
     }
     if (L > 0) std::memcpy(hb + o_lc, lmk_col.data(), 4 * L);
-    std::memcpy(hb + o_sp, slot_ptr.data(), 4 * (L + 1));
-    if (nslots) std::memcpy(hb + o_sf, slot_frame.data(), 4 * nslots);
-    std::memcpy(hb + o_sop, slot_obs_ptr.data(), 4 * (nslots + 1));
-    if (nslotobs) std::memcpy(hb + o_so, slot_obs.data(), 4 * (size_t)nslotobs);
+    if (!gpu_struct) {
+        std::memcpy(hb + o_sp, slot_ptr.data(), 4 * (L + 1));
+        if (nslots) std::memcpy(hb + o_sf, slot_frame.data(), 4 * nslots);
+        std::memcpy(hb + o_sop, slot_obs_ptr.data(), 4 * (nslots + 1));
+        if (nslotobs) std::memcpy(hb + o_so, slot_obs.data(), 4 * (size_t)nslotobs);
+    }
     // (observation indices, measurements — array-of-structs as the caller provides them — and landmarks: bulk data arena)
     if (Pn) {
         std::memcpy(hb + o_ii, w->imu_i, 4 * Pn);
@@ -1416,6 +1564,10 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     size_t s_dinv = S.add(D * (n_pad + 32));
     size_t s_prof = S.add(D * 8 * CC_MAX);
     size_t s_aux = S.add(D * LMK_AUX * cL);
+    // device structure pass (sdv_struct.cuh): scan scratch and the slot / tile lists themselves, sized from the capacities
+    const size_t nblkO = cO / SCAN_BLOCK + 2, nblkL = cL / SCAN_BLOCK + 2;
+    size_t s_head = S.add(4 * cO), s_sidx = S.add(4 * cO), s_ssum = S.add(4 * nblkO), s_thead = S.add(4 * cL), s_tidx = S.add(4 * cL), s_tsum = S.add(4 * nblkL),
+           s_tot = S.add(64), s_gsp = S.add(4 * (cL + 2)), s_gsf = S.add(4 * (cO + 2)), s_gsop = S.add(4 * (cO + 2)), s_gso = S.add(4 * (cO + 2)), s_gtile = S.add(4 * (cL + 4));
     size_t s_xchg = h->world > 1 ? S.add(D * ((size_t)n_pad * n_pad + 3 * (size_t)n_pad + 8)) : 0; // upper bound (no band); the band case uses the head
     if ((rc = ensure(h, &h->d_scr, &h->scr_cap, S.size)) != SDV_OK) return rc;
     unsigned char *sb = h->d_scr;
@@ -1440,9 +1592,18 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     P.T_s_f = at<double>(db, o_Ts); P.K = at<double>(db, o_K); P.cam_w = at<double>(db, o_cw);
     P.lmk_t = at<double>(h->d_in2, q_lt); P.lmk_col = at<int>(db, o_lc);
     P.tile_nz = at<uint32_t>(db, o_tnz);
-    P.tile_ptr = at<int>(db, o_tile);
     P.ntiles = ntiles;
-    P.slot_ptr = at<int>(db, o_sp); P.slot_frame = at<int>(db, o_sf); P.slot_obs_ptr = at<int>(db, o_sop); P.slot_obs = at<int>(db, o_so);
+    P.st_on = gpu_struct ? 1 : 0;
+    P.st_capq = tile_capq;
+    P.st_head = at<int>(sb, s_head); P.st_sidx = at<int>(sb, s_sidx); P.st_ssum = at<int>(sb, s_ssum); P.st_thead = at<int>(sb, s_thead);
+    P.st_tidx = at<int>(sb, s_tidx); P.st_tsum = at<int>(sb, s_tsum); P.st_tot = at<int>(sb, s_tot);
+    if (gpu_struct) {
+        P.tile_ptr = at<int>(sb, s_gtile);
+        P.slot_ptr = at<int>(sb, s_gsp); P.slot_frame = at<int>(sb, s_gsf); P.slot_obs_ptr = at<int>(sb, s_gsop); P.slot_obs = at<int>(sb, s_gso);
+    } else {
+        P.tile_ptr = at<int>(db, o_tile);
+        P.slot_ptr = at<int>(db, o_sp); P.slot_frame = at<int>(db, o_sf); P.slot_obs_ptr = at<int>(db, o_sop); P.slot_obs = at<int>(db, o_so);
+    }
     P.obs_lmk = at<int>(h->d_in2, q_ol); P.obs_fc = at<int>(h->d_in2, q_ofc); P.obs_meas = at<double>(h->d_in2, q_om);
     P.obs_w = w->obs_sigma ? at<double>(h->d_in2, q_ow) : nullptr;
     P.imu_i = at<int>(db, o_ii); P.imu_j = at<int>(db, o_ij); P.imu_dt = at<double>(db, o_idt); P.imu_dR = at<double>(db, o_idR);
@@ -1582,11 +1743,41 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
     CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemcpyAsync(h->d_in, hb, A.size, cudaMemcpyHostToDevice, h->stream));
     if (have_pool) h->pool.wait(g_bulk); // the bulk data arena is packed (and its copy issued on the copy stream)
-    if (bulk_copy_failed) return fail(h, SDV_ERR_CUDA, "H2D copy of the bulk arena failed");
+    if (bulk_failed.load()) return fail(h, SDV_ERR_CUDA, "H2D copy of the bulk arena failed");
     if (bulk_copy_issued) CK(cudaStreamWaitEvent(h->stream, h->ev_bulk, 0));
     else CK(cudaMemcpyAsync(h->d_in2, h->h_in2, A2.size, cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev[1], h->stream));
     h->h2d_last = A.size + A2.size;
+    if (gpu_struct && Oloc > 0) {
+        // slot lists and tiles on the device, from the observation arrays that just arrived (sdv_struct.cuh): eight small launches,
+        // captured once per handle (everything they need is read from the device-resident problem description) and replayed
+        if (!h->stream2) CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        if (!h->sgraph_exec || h->sgraph_dP != (const void *)h->d_P || h->sgraph_capO != h->cap_O || h->sgraph_capL != h->cap_L) {
+            if (h->sgraph_exec) cudaGraphExecDestroy(h->sgraph_exec);
+            h->sgraph_exec = nullptr;
+            cudaStream_t s2 = h->stream2;
+            const int gO = std::min(h->num_sms * 8, (h->cap_O + 255) / 256), nbO = h->cap_O / SCAN_BLOCK + 1;
+            const int gL = std::min(h->num_sms * 8, (h->cap_L + 255) / 256), nbL = h->cap_L / SCAN_BLOCK + 1;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(s2, cudaStreamCaptureModeThreadLocal));
+            k_struct_heads<<<gO, 256, 0, s2>>>(h->d_P);
+            k_scan_blocks<<<nbO, SCAN_T, 0, s2>>>(h->d_P, 0);
+            k_scan_sums<<<1, 1024, 0, s2>>>(h->d_P, 0);
+            k_struct_slots<<<gO, 256, 0, s2>>>(h->d_P);
+            k_struct_tile_heads<<<gL, 256, 0, s2>>>(h->d_P, FT_LMK);
+            k_scan_blocks<<<nbL, SCAN_T, 0, s2>>>(h->d_P, 1);
+            k_scan_sums<<<1, 1024, 0, s2>>>(h->d_P, 1);
+            k_struct_tiles<<<gL, 256, 0, s2>>>(h->d_P);
+            CK(cudaStreamEndCapture(s2, &g));
+            CK(cudaGraphInstantiate(&h->sgraph_exec, g, 0));
+            cudaGraphDestroy(g);
+            h->sgraph_dP = (const void *)h->d_P;
+            h->sgraph_capO = h->cap_O;
+            h->sgraph_capL = h->cap_L;
+        }
+        CK(cudaGraphLaunch(h->sgraph_exec, h->stream));
+        h->launches += 8;
+    }
     if (h->band_smem == 0) CK(cudaMemsetAsync(h->d_Lo, 0, sizeof(double) * sb_elems, h->stream)); // cluster Cholesky: tiles outside the structural pattern are never written
     // ---- one-time device setup for this window
     if (Pn > 0) {

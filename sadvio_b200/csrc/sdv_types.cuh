@@ -73,6 +73,9 @@ struct DevProblem {
     int lmk_const;   // every landmark block is constant (single-frame solves): no elimination, no landmark update
     int max_iter;    // > 0: iteration cap of this window (overrides SolverOpts::max_num_iterations)
     double huber_a;  // > 0: ceres::HuberLoss(a) + Corrector on every visual residual block
+    // device structure pass (sdv_struct.cuh): scratch of the scans and the bucket size of the tiling; st_on = 0: the host built the lists
+    int *st_head, *st_sidx, *st_ssum, *st_thead, *st_tidx, *st_tsum, *st_tot;
+    int st_capq, st_on;
     // frames
     const double *T_f_w, *v, *ba, *bg;
     const unsigned char *has_prior;
