@@ -468,6 +468,12 @@ def main():
                 f2[name] = {"ms_call_host_buffers": 1e3 * (time.perf_counter() - t0) / 5, "lm_iterations": st_f["iterations"], "n_lmks": int(sub.n_lmks),
                             "n_obs": int(sub.n_obs)}
             extras["frame_level_solves"] = f2
+            solver.viinit(win, True)                   # AOptimizer::VIInit over the window's keyframes / IMU pairs (one kernel)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                rc, res_v, st_v = solver.viinit(win, True)
+            extras["VIInit"] = {"ms_call_host_buffers": 1e3 * (time.perf_counter() - t0) / 5, "ms_device": st_v["ms_solve_device"],
+                                "lm_iterations": st_v["iterations"], "n": st_v["n_reduced"], "n_imu_pairs": int(win.n_imu)}
         except Exception as e:  # noqa: BLE001
             extras = {"error": str(e)}
         solver.upload(win)

@@ -248,8 +248,7 @@ typedef struct sdv_window {
  *   singleFrameVIOptimization(frame)      frames = { frame, frame->getIMU()->getLastKF() }, vio = 1, one IMU pair,
  *                                         landmarks_constant = 1, Huber sqrt(1.345), 5 iterations (the 5 ms wall-clock budget
  *                                         of AOptimizer.cpp:254 is not modelled: a solve of this size takes well under 1 ms)
- * VIInit (AOptimizer.cpp:448-581) uses the IMUFactorInit functors with gravity / scale blocks and is out of scope (SURVEY.md
- * section 2).
+ * VIInit (AOptimizer.cpp:448-581) has parameter blocks of its own (gravity direction, scale): sdv_viinit below.
  */
 
 /*
@@ -355,6 +354,27 @@ typedef struct sdv_preint { /* per interval, the state of the LAST measurement's
 } sdv_preint;
 
 int sdv_preintegrate(sdv_handle *h, const sdv_imu_intervals *in, sdv_preint *out);
+
+/*
+ * Visual-inertial initialisation — replaces: the problem build + ceres::Solve of AOptimizer::VIInit
+ * (cpp/src/optimizers/AOptimizer.cpp:448-529) with its functor IMUFactorInit (cpp/include/isaeslam/optimizers/residuals.hpp:302-410).
+ * Read from `win`: n_frames, T_f_w, v (every frame of the local map, newest -> oldest; all of them carry an IMU) and the imu_*
+ * arrays — one entry per frame j whose getIMU()->getLastKF() is another frame i of the map (AOptimizer.cpp:485-502: NO dt test
+ * here); imu_J_*, imu_sigma_* are not read (the shared dba / dbg blocks are constant at zero, :472-477, and the two
+ * Landmark3DPrior blocks on them, :504-515, have zero residual).  win->max_num_iterations > 0 overrides the 50 steps of :449.
+ * Parameter blocks: r_wi (2), one dv per frame, lambda (constant unless optim_scale).  The caller applies the result as
+ * AOptimizer.cpp:531-567 does (the adapters do): v += dv; R_w_i = Exp(r_wi0, r_wi1, 0); T_f_w <- [R_f_w R_w_i | exp(lambda) t_f_w];
+ * priors re-set on the new poses; landmarks <- exp(lambda) R_w_i^T t_w_lmk.
+ */
+typedef struct sdv_viinit_result {
+    double *dv;        /* [F][3] velocity blocks (caller-allocated) */
+    double r_wi[2];    /* r_wi_par */
+    double lambda;     /* log-scale; 0 when !optim_scale */
+    double R_w_i[9];   /* geometry::exp_so3(r_wi[0], r_wi[1], 0), row-major */
+    double scale;      /* exp(lambda): the value VIInit returns (AOptimizer.cpp:580) */
+} sdv_viinit_result;
+
+int sdv_viinit(sdv_handle *h, const sdv_window *win, int32_t optim_scale, sdv_viinit_result *out, sdv_stats *stats);
 
 /*
  * Marginal-prior construction — replaces: AngularAdjustmentCERESAnalytic::marginalize

@@ -308,6 +308,98 @@ struct ImuFactor {
 };
 
 // ---------------------------------------------------------------------------------------------
+// IMUFactorInit — residuals.hpp:302-410, SizedCostFunction<9, 2,3,3,3,3,1>, the functor of AOptimizer::VIInit
+// parameters: (w_x, w_y) of the gravity alignment R_w_i = Exp(w_x, w_y, 0), dv_i, dv_j, dba, dbg, log-scale lambda
+// ---------------------------------------------------------------------------------------------
+struct ImuFactorInit {
+    Aff T_fi_w, T_fj_w;     // poses are NOT parameters here (:316-317)
+    V3 v_i_base, v_j_base;
+    double dtij;
+    Mat<9, 9> cov;
+    M3 delta_R;
+    V3 delta_v, delta_p;
+    M3 J_dR_bg, J_dv_ba, J_dv_bg, J_dp_ba, J_dp_bg;
+    bool Evaluate(double const *const *parameters, double *residuals, double **jacobians) const {
+        V3 w_w_i = vec3(parameters[0][0], parameters[0][1], 0);                                       // :309
+        M3 R_w_i = exp_so3(w_w_i);
+        V3 v_i = v_i_base + V3::From(parameters[1]);                                                  // :311-312
+        V3 v_j = v_j_base + V3::From(parameters[2]);
+        V3 d_ba = V3::From(parameters[3]);
+        V3 d_bg = V3::From(parameters[4]);
+        double lambda = parameters[5][0];
+        V3 g = V3::From(kGravity);
+        Mat<9, 9> inf_sqrt;
+        if (!ImuFactor::InfSqrt(cov, inf_sqrt)) return false;                                         // :321-323
+        M3 dR = (delta_R * exp_so3(J_dR_bg * d_bg)).T() * T_fi_w.R * T_fj_w.R.T();                    // :326-327
+        V3 r_dr = log_so3(dR);
+        M3 RiRw = T_fi_w.R * R_w_i;
+        V3 a_v = (v_j - v_i) - g * dtij;
+        V3 dpos = T_fj_w.inverse().t - T_fi_w.inverse().t;
+        V3 a_p = std::exp(lambda) * dpos - v_i * dtij - (0.5 * dtij * dtij) * g;
+        V3 r_dv = RiRw * a_v - (delta_v + J_dv_bg * d_bg + J_dv_ba * d_ba);                           // :329-330
+        V3 r_dp = RiRw * a_p - (delta_p + J_dp_bg * d_bg + J_dp_ba * d_ba);                           // :331-335
+        Mat<9, 1> err;
+        for (int k = 0; k < 3; k++) {
+            err[k] = r_dr[k];
+            err[3 + k] = r_dv[k];
+            err[6 + k] = r_dp[k];
+        }
+        err = inf_sqrt * err;                                                                         // :340
+        err.to(residuals);
+        if (jacobians != nullptr) {
+            if (jacobians[0] != nullptr) {                                                            // :345-356
+                Mat<9, 2> J = Mat<9, 2>::Zero();
+                M3 Jr = so3_rightJacobian(w_w_i);
+                M3 Bv = -(RiRw * skewMatrix(a_v) * Jr), Bp = -(RiRw * skewMatrix(a_p) * Jr);
+                for (int r = 0; r < 3; r++)
+                    for (int c = 0; c < 2; c++) {
+                        J(3 + r, c) = Bv(r, c);
+                        J(6 + r, c) = Bp(r, c);
+                    }
+                J = inf_sqrt * J;
+                J.to(jacobians[0]);
+            }
+            if (jacobians[1] != nullptr) {                                                            // :359-365
+                Mat<9, 3> J = Mat<9, 3>::Zero();
+                J.setBlock(3, 0, -RiRw);
+                J.setBlock(6, 0, -(RiRw * dtij));
+                J = inf_sqrt * J;
+                J.to(jacobians[1]);
+            }
+            if (jacobians[2] != nullptr) {                                                            // :368-373
+                Mat<9, 3> J = Mat<9, 3>::Zero();
+                J.setBlock(3, 0, RiRw);
+                J = inf_sqrt * J;
+                J.to(jacobians[2]);
+            }
+            if (jacobians[3] != nullptr) {                                                            // :376-382
+                Mat<9, 3> J = Mat<9, 3>::Zero();
+                J.setBlock(3, 0, -J_dv_ba);
+                J.setBlock(6, 0, -J_dp_ba);
+                J = inf_sqrt * J;
+                J.to(jacobians[3]);
+            }
+            if (jacobians[4] != nullptr) {                                                            // :385-393
+                Mat<9, 3> J = Mat<9, 3>::Zero();
+                J.setBlock(0, 0, -(inverse3(so3_rightJacobian(r_dr)) * dR.T() * so3_rightJacobian(J_dR_bg * d_bg) * J_dR_bg));
+                J.setBlock(3, 0, -J_dv_bg);
+                J.setBlock(6, 0, -J_dp_bg);
+                J = inf_sqrt * J;
+                J.to(jacobians[4]);
+            }
+            if (jacobians[5] != nullptr) {                                                            // :396-402
+                Mat<9, 1> J = Mat<9, 1>::Zero();
+                V3 s = RiRw * dpos;   // NOTE: the reference's derivative omits the exp(lambda) factor (:399-400); reproduced
+                for (int r = 0; r < 3; r++) J[6 + r] = s[r];
+                J = inf_sqrt * J;
+                J.to(jacobians[5]);
+            }
+        }
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // IMUBiasFactor — residuals.hpp:247-300, SizedCostFunction<6, 3,3,3,3>
 // parameters: dba_i, dbg_i, dba_j, dbg_j
 // ---------------------------------------------------------------------------------------------

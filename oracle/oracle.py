@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
         _lib.orc_pose_prior_eval.argtypes = [dp, dp, dp, dp, dp, dp]
         _lib.orc_p2l_eval.argtypes = [dp, dp, dp, dp, dp, dp, dp, dp, dp]
         _lib.orc_imu_factor_eval.argtypes = [dp, dp, dp, dp, C.c_double, dp, dp, dp, dp]
+        _lib.orc_imu_init_eval.argtypes = [dp, dp, dp, dp, C.c_double, dp, dp, dp, dp]
+        _lib.orc_viinit.argtypes = [C.POINTER(abi.SdvWindow), C.POINTER(abi.SdvConfig), C.c_int, dp, dp, C.POINTER(abi.SdvStats)]
         _lib.orc_process_imu.argtypes = [dp, dp, dp, C.c_double, dp, C.c_double, dp]
         _lib.orc_bias_delta_correction.argtypes = [dp, dp, dp]
     return _lib
@@ -187,6 +189,28 @@ def imu_factor_eval(T_i, T_j, v_i, v_j, dt, pre, params=None, jac=True):
                                    _p(_a(pre, 141)), _p(params), _p(r), _p(J) if jac else None)
     assert rc == 0
     return r, J.reshape(9, 24)
+
+
+def imu_init_eval(T_i, T_j, v_i, v_j, dt, pre, params=None, jac=True):
+    """IMUFactorInit::Evaluate (residuals.hpp:302-410); params = (w_x, w_y, dv_i, dv_j, dba, dbg, lambda), J is 9 x 15."""
+    params = _a(np.zeros(15) if params is None else params, 15)
+    r, J = np.zeros(9), np.zeros(9 * 15)
+    rc = lib().orc_imu_init_eval(_p(_a(T_i, 12)), _p(_a(T_j, 12)), _p(_a(v_i, 3)), _p(_a(v_j, 3)), float(dt),
+                                 _p(_a(pre, 141)), _p(params), _p(r), _p(J) if jac else None)
+    assert rc == 0
+    return r, J.reshape(9, 15)
+
+
+def viinit(win: abi.Window, optim_scale: bool = True, cfg: abi.SdvConfig | None = None):
+    """The solve of AOptimizer::VIInit (AOptimizer.cpp:448-529) over the frames / IMU pairs of `win`.
+    Returns rc, dict(dv[F][3], r_wi[2], lam, R_w_i, scale), stats."""
+    cfg = cfg or default_config()
+    ws = win.as_struct()
+    dv, extra = np.zeros((win.n_frames, 3)), np.zeros(3)
+    st = abi.SdvStats()
+    rc = lib().orc_viinit(C.byref(ws), C.byref(cfg), int(bool(optim_scale)), _p(dv), _p(extra), C.byref(st))
+    return rc, dict(dv=dv, r_wi=extra[:2].copy(), lam=float(extra[2]), R_w_i=exp_so3([extra[0], extra[1], 0.0]),
+                    scale=float(np.exp(extra[2]))), abi.stats_to_dict(st)
 
 
 IMU_STATE = dict(acc=(0, 3), gyr=(3, 6), ba=(6, 9), bg=(9, 12), v=(12, 15), T_f_w=(15, 27), is_kf=(27, 28),

@@ -33,7 +33,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // Problem description (what ceres::Problem holds after the reference's add*Residuals calls)
 // ------------------------------------------------------------------------------------------------
-enum Kind { K_VISUAL = 0, K_POSE_PRIOR, K_IMU, K_IMU_BIAS, K_MARG, K_IMU_PRIOR, K_P2L, K_LMK_PRIOR, K_L2L };
+enum Kind { K_VISUAL = 0, K_POSE_PRIOR, K_IMU, K_IMU_BIAS, K_MARG, K_IMU_PRIOR, K_P2L, K_LMK_PRIOR, K_L2L, K_IMU_INIT };
 
 struct PBlock {
     int size = 0;
@@ -71,6 +71,10 @@ struct Problem {
     int ba_id(int f) const { return 2 * F + f; }
     int bg_id(int f) const { return 3 * F + f; }
     int lmk_id(int l) const { return 4 * F + l; }
+    // AOptimizer::VIInit (AOptimizer.cpp:448-581): 0 = a window solve, 1 = VIInit with the scale constant, 2 = scale free
+    int viinit = 0;
+    int rwi_id() const { return 4 * F + L; }     // r_wi_par, size 2 (:467-468)
+    int lam_id() const { return 4 * F + L + 1; } // lambda, size 1 (:480-483)
 };
 
 static double sigma_of_obs(const sdv_window *w, int o) {
@@ -82,8 +86,51 @@ static double sigma_of_obs(const sdv_window *w, int o) {
     return 1.0; // BundleAdjustmentCERESAnalytic.h:47 default sigma
 }
 
-static bool build_problem(const sdv_window *w, Problem &P, bool schur) {
+static void reduce_program(Problem &P) {
+    // ---- Ceres reduced program: drop constant blocks, drop residual blocks with only constant blocks,
+    //      drop parameter blocks no remaining residual block uses.
+    for (auto &r : P.rbs) {
+        r.active = false;
+        for (int id : r.pb)
+            if (!P.pbs[id].constant) r.active = true;
+        if (r.active)
+            for (int id : r.pb)
+                if (!P.pbs[id].constant) P.pbs[id].active = true;
+    }
+    int col = 0;
+    for (auto &p : P.pbs)
+        if (p.active && !p.elim) {
+            p.col = col;
+            col += p.size;
+        }
+    P.ndense = col;
+    for (auto &p : P.pbs)
+        if (p.active && p.elim) {
+            p.col = col;
+            col += p.size;
+        }
+    P.ncols = col;
+    size_t joff = 0;
+    int roff = 0;
+    for (auto &r : P.rbs) {
+        if (!r.active) continue;
+        r.joff = joff;
+        r.roff = roff;
+        int width = 0;
+        for (int id : r.pb) width += P.pbs[id].size;
+        joff += (size_t)r.nres * width;
+        roff += r.nres;
+    }
+    P.jsize = joff;
+    P.nres = roff;
+}
+
+static bool build_problem_viinit(const sdv_window *w, Problem &P);
+
+static bool build_problem(const sdv_window *w, Problem &P, bool schur, int viinit = 0) {
     P.w = w;
+    P.viinit = viinit;
+    if (viinit) return build_problem_viinit(w, P);
     const int F = P.F = w->n_frames, L = P.L = w->n_lmks;
     P.pbs.assign(4 * F + L, PBlock());
     int off = 0;
@@ -175,42 +222,50 @@ static bool build_problem(const sdv_window *w, Problem &P, bool schur) {
             P.pbs[P.lmk_id(sp->l2l_b[k])].elim = false;
         }
     }
-    // ---- Ceres reduced program: drop constant blocks, drop residual blocks with only constant blocks,
-    //      drop parameter blocks no remaining residual block uses.
-    for (auto &r : P.rbs) {
-        r.active = false;
-        for (int id : r.pb)
-            if (!P.pbs[id].constant) r.active = true;
-        if (r.active)
-            for (int id : r.pb)
-                if (!P.pbs[id].constant) P.pbs[id].active = true;
-    }
-    int col = 0;
-    for (auto &p : P.pbs)
-        if (p.active && !p.elim) {
-            p.col = col;
-            col += p.size;
+    reduce_program(P);
+    return true;
+}
+
+// The problem AOptimizer::VIInit builds (AOptimizer.cpp:448-529): one velocity block per frame with an IMU (:459-464), the 2-dof
+// gravity alignment (:467-468), the log-scale (:480-483, constant unless optim_scale), ONE shared dba / dbg pair that is set
+// constant (:472-477) and therefore stays at zero; one IMUFactorInit per (getLastKF(), frame) pair (:485-502, no dt test).  The
+// two Landmark3DPrior blocks on dba / dbg (:504-515) only touch constant blocks (Ceres drops them; their residual is zero).
+static bool build_problem_viinit(const sdv_window *w, Problem &P) {
+    const int F = P.F = w->n_frames, L = P.L = w->n_lmks;
+    P.pbs.assign(4 * F + L + 2, PBlock());
+    for (int f = 0; f < F; f++) {
+        P.pbs[P.pose_id(f)].size = 6;
+        P.pbs[P.pose_id(f)].constant = true; // poses are not parameters of VIInit
+        for (int k = 1; k <= 3; k++) {
+            P.pbs[k * F + f].size = 3;
+            P.pbs[k * F + f].constant = k != 1;
         }
-    P.ndense = col;
-    for (auto &p : P.pbs)
-        if (p.active && p.elim) {
-            p.col = col;
-            col += p.size;
-        }
-    P.ncols = col;
-    size_t joff = 0;
-    int roff = 0;
-    for (auto &r : P.rbs) {
-        if (!r.active) continue;
-        r.joff = joff;
-        r.roff = roff;
-        int width = 0;
-        for (int id : r.pb) width += P.pbs[id].size;
-        joff += (size_t)r.nres * width;
-        roff += r.nres;
     }
-    P.jsize = joff;
-    P.nres = roff;
+    for (int l = 0; l < L; l++) {
+        P.pbs[P.lmk_id(l)].size = 3;
+        P.pbs[P.lmk_id(l)].constant = true;
+    }
+    P.pbs[P.rwi_id()].size = 2;
+    P.pbs[P.lam_id()].size = 1;
+    P.pbs[P.lam_id()].constant = P.viinit != 2;
+    int off = 0;
+    for (auto &p : P.pbs) {
+        p.off = off;
+        off += p.size;
+    }
+    P.nx = off;
+    P.imu_inf_sqrt.resize(w->n_imu);
+    for (int p = 0; p < w->n_imu; p++) {
+        RBlock r;
+        r.kind = K_IMU_INIT;
+        r.idx = p;
+        r.nres = 9;
+        r.pb = {P.rwi_id(), P.vel_id(w->imu_i[p]), P.vel_id(w->imu_j[p]), P.lam_id()};
+        r.npb = 4;
+        P.rbs.push_back(r);
+        if (!ImuFactor::InfSqrt(Mat<9, 9>::From(w->imu_cov + 81 * p), P.imu_inf_sqrt[p])) return false;
+    }
+    reduce_program(P);
     return true;
 }
 
@@ -287,6 +342,29 @@ static bool eval_block(const Problem &P, const RBlock &rb, const double *x, doub
         e.J_dp_ba = M3::From(w->imu_J_dp_ba + 9 * p);
         e.J_dp_bg = M3::From(w->imu_J_dp_bg + 9 * p);
         return e.Evaluate(pp, res, J);
+    }
+    case K_IMU_INIT: {
+        int p = rb.idx, i = w->imu_i[p], j = w->imu_j[p];
+        ImuFactorInit e;
+        e.T_fi_w = Aff::From(w->T_f_w + 12 * i);
+        e.T_fj_w = Aff::From(w->T_f_w + 12 * j);
+        e.v_i_base = V3::From(w->v + 3 * i);
+        e.v_j_base = V3::From(w->v + 3 * j);
+        e.dtij = w->imu_dt[p];
+        e.cov = Mat<9, 9>::From(w->imu_cov + 81 * p);
+        e.delta_R = M3::From(w->imu_dR + 9 * p);
+        e.delta_v = V3::From(w->imu_dv + 3 * p);
+        e.delta_p = V3::From(w->imu_dp + 3 * p);
+        e.J_dR_bg = M3::From(w->imu_J_dR_bg + 9 * p);
+        e.J_dv_ba = M3::From(w->imu_J_dv_ba + 9 * p);
+        e.J_dv_bg = M3::From(w->imu_J_dv_bg + 9 * p);
+        e.J_dp_ba = M3::From(w->imu_J_dp_ba + 9 * p);
+        e.J_dp_bg = M3::From(w->imu_J_dp_bg + 9 * p);
+        // the shared dba / dbg blocks are constant at zero: Ceres passes their values and a NULL Jacobian pointer
+        static const double zero3[3] = {0, 0, 0};
+        const double *p6[6] = {pp[0], pp[1], pp[2], zero3, zero3, pp[3]};
+        double *j6[6] = {J ? jj[0] : nullptr, J ? jj[1] : nullptr, J ? jj[2] : nullptr, nullptr, nullptr, J ? jj[3] : nullptr};
+        return e.Evaluate(p6, res, J ? j6 : nullptr);
     }
     case K_IMU_BIAS: {
         int p = rb.idx, i = w->imu_i[p], j = w->imu_j[p];
@@ -771,9 +849,9 @@ static bool solve_linear(const Problem &P, const double *jac, const double *res,
 // Ceres 2.2 TrustRegionMinimizer + LevenbergMarquardtStrategy, restated.
 // ------------------------------------------------------------------------------------------------
 static int solve_lm(const sdv_window *w, const sdv_config *cfg, sdv_delta *out, sdv_stats *st, int mode, int nthreads,
-                    double *S_out, double *g_out) {
+                    double *S_out, double *g_out, int viinit = 0, double *extra_out = nullptr) {
     Problem P;
-    if (!build_problem(w, P, mode == 0)) return SDV_ERR_NUMERICAL_FAILURE;
+    if (!build_problem(w, P, mode == 0, viinit)) return SDV_ERR_NUMERICAL_FAILURE;
     const int N = P.ncols;
     std::vector<std::vector<int>> elim_rbs;
     std::vector<int> elim_ids, elim_index(P.pbs.size(), -1);
@@ -1033,6 +1111,11 @@ static int solve_lm(const sdv_window *w, const sdv_config *cfg, sdv_delta *out, 
     }
     for (int l = 0; l < P.L; l++)
         for (int k = 0; k < 3; k++) out->dlmk[3 * l + k] = x[P.pbs[P.lmk_id(l)].off + k];
+    if (P.viinit && extra_out) {
+        extra_out[0] = x[P.pbs[P.rwi_id()].off];
+        extra_out[1] = x[P.pbs[P.rwi_id()].off + 1];
+        extra_out[2] = x[P.pbs[P.lam_id()].off];
+    }
     return term == SDV_TERM_FAILURE ? SDV_ERR_NUMERICAL_FAILURE : SDV_OK;
 }
 
@@ -1085,6 +1168,59 @@ int orc_solve_window(const sdv_window *w, const sdv_config *cfg, sdv_delta *out,
     auto t1 = std::chrono::steady_clock::now();
     st->ms_total_host = std::chrono::duration<double, std::milli>(t1 - t0).count();
     return rc;
+}
+
+// AOptimizer::VIInit's solve (AOptimizer.cpp:448-529) on the frames / IMU pairs of `w`: dv[F][3] = the velocity blocks,
+// extra[3] = (r_wi_par[0], r_wi_par[1], lambda).  50 iterations (:449, :521) unless the window overrides it; dense normal equations.
+int orc_viinit(const sdv_window *w, const sdv_config *cfg, int optim_scale, double *dv, double *extra, sdv_stats *st) {
+    auto t0 = std::chrono::steady_clock::now();
+    sdv_window ww = *w;
+    if (ww.max_num_iterations <= 0) ww.max_num_iterations = 50;
+    std::vector<double> dpose(6 * (size_t)w->n_frames), dba(3 * (size_t)w->n_frames), dbg(3 * (size_t)w->n_frames), dl(3 * (size_t)w->n_lmks + 3);
+    sdv_delta d;
+    d.dpose = dpose.data();
+    d.dv = dv;
+    d.dba = dba.data();
+    d.dbg = dbg.data();
+    d.dlmk = dl.data();
+    int rc = solve_lm(&ww, cfg, &d, st, 1, 1, nullptr, nullptr, optim_scale ? 2 : 1, extra);
+    st->ms_total_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+// One IMUFactorInit::Evaluate (residuals.hpp:302-410): par = (w_x, w_y, dv_i[3], dv_j[3], dba[3], dbg[3], lambda), pre as in
+// orc_imu_factor_eval; r[9], J[9][15] row-major over the concatenated parameter vector.
+int orc_imu_init_eval(const double *T_i, const double *T_j, const double *v_i, const double *v_j, double dt, const double *pre,
+                      const double *par, double *r, double *J) {
+    ImuFactorInit e;
+    e.T_fi_w = Aff::From(T_i);
+    e.T_fj_w = Aff::From(T_j);
+    e.v_i_base = V3::From(v_i);
+    e.v_j_base = V3::From(v_j);
+    e.dtij = dt;
+    e.delta_R = M3::From(pre);
+    e.delta_v = V3::From(pre + 9);
+    e.delta_p = V3::From(pre + 12);
+    e.cov = Mat<9, 9>::From(pre + 15);
+    e.J_dR_bg = M3::From(pre + 96);
+    e.J_dv_ba = M3::From(pre + 105);
+    e.J_dv_bg = M3::From(pre + 114);
+    e.J_dp_ba = M3::From(pre + 123);
+    e.J_dp_bg = M3::From(pre + 132);
+    const int sz[6] = {2, 3, 3, 3, 3, 1}, off[6] = {0, 2, 5, 8, 11, 14};
+    const double *pp[6];
+    double jb[6][27];
+    double *jp[6];
+    for (int k = 0; k < 6; k++) {
+        pp[k] = par + off[k];
+        jp[k] = jb[k];
+    }
+    if (!e.Evaluate(pp, r, J ? jp : nullptr)) return 1;
+    if (J)
+        for (int k = 0; k < 6; k++)
+            for (int q = 0; q < 9; q++)
+                for (int c = 0; c < sz[k]; c++) J[q * 15 + off[k] + c] = jb[k][q * sz[k] + c];
+    return 0;
 }
 
 // Evaluate every visual residual block at x (NULL = 0): r[O][2], Jp[O][12], Jl[O][6]; returns 1/2 sum r^2 in *cost.

@@ -221,6 +221,10 @@ class SdvPreint(C.Structure):
     _fields_ = [(n, c_double_p) for n in ("dR", "dv", "dp", "cov", "J_dR_bg", "J_dv_ba", "J_dv_bg", "J_dp_ba", "J_dp_bg", "T_pred", "v_pred")]
 
 
+class SdvViinitResult(C.Structure):
+    _fields_ = [("dv", c_double_p), ("r_wi", C.c_double * 2), ("lambda_", C.c_double), ("R_w_i", C.c_double * 9), ("scale", C.c_double)]
+
+
 def _dp(a: Optional[np.ndarray]):
     if a is None:
         return c_double_p()

@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
     L.sdv_preintegrate.argtypes = [C.c_void_p, C.POINTER(abi.SdvImuIntervals), C.POINTER(abi.SdvPreint)]
     L.sdv_marginalize.argtypes = [C.c_void_p, C.POINTER(abi.SdvWindow), C.c_int32, C.POINTER(abi.SdvMarginalSizes)]
     L.sdv_marginal_fetch.argtypes = [C.c_void_p, C.POINTER(abi.SdvMarginal)]
+    L.sdv_viinit.argtypes = [C.c_void_p, C.POINTER(abi.SdvWindow), C.c_int32, C.POINTER(abi.SdvViinitResult), C.POINTER(abi.SdvStats)]
     L.sdv_schur_prior.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32, C.c_double, C.POINTER(abi.SdvMarginalSizes)]
     _lib = L
     return L
@@ -252,6 +253,18 @@ class Solver:
         out.update({k: getattr(sz, k) for k, _ in abi.SdvMarginalSizes._fields_})
         return out
 
+    def viinit(self, win: abi.Window, optim_scale: bool = True):
+        """sdv_viinit: the solve of AOptimizer::VIInit over the frames / IMU pairs of `win`.
+        Returns rc, dict(dv[F][3], r_wi[2], lam, R_w_i[3][3], scale), stats."""
+        ws = win.as_struct()
+        dv = np.zeros((win.n_frames, 3))
+        res = abi.SdvViinitResult()
+        res.dv = dv.ctypes.data_as(abi.c_double_p)
+        st = abi.SdvStats()
+        rc = self._check(lib().sdv_viinit(self._h, C.byref(ws), int(bool(optim_scale)), C.byref(res), C.byref(st)), allow=(0, 5))
+        return rc, dict(dv=dv, r_wi=np.array(res.r_wi[:]), lam=float(res.lambda_), R_w_i=np.array(res.R_w_i[:]).reshape(3, 3),
+                        scale=float(res.scale)), abi.stats_to_dict(st)
+
     def graph_builds(self) -> int:
         n = C.c_int64()
         self._check(lib().sdv_debug_graph_builds(self._h, C.byref(n)))
@@ -333,6 +346,24 @@ def write_back(win: abi.Window, d: abi.Delta, vio: bool) -> None:
         if sk is not None:
             for k in range(len(sk.frame)):
                 correct(sk.dR, sk.dv, sk.dp, sk.J_dR_bg, sk.J_dv_ba, sk.J_dv_bg, sk.J_dp_ba, sk.J_dp_bg, k, int(sk.prev[k]))
+
+
+def viinit_write_back(win: abi.Window, res: dict) -> None:
+    """State update of AOptimizer::VIInit, in place (AOptimizer.cpp:531-567): velocities, poses rotated into the inertial frame
+    and re-scaled, priors re-set on the new poses, landmarks transformed.  (The reference adds dba — a constant block, zero —
+    to the accelerometer bias twice and never touches the gyroscope bias, :535-536: a no-op.)"""
+    win.v += res["dv"]                                                     # :533-534
+    R_w_i, s = res["R_w_i"], float(np.exp(res["lam"]))                     # :540
+    for f in range(win.n_frames):                                          # :545-556
+        T = win.T_f_w[f].reshape(3, 4).copy()
+        T[:, 3] *= s                                                       # :549
+        T[:, :3] = T[:, :3] @ R_w_i                                        # :550 (T_w_i has no translation)
+        win.T_f_w[f] = T.reshape(12)
+        if win.has_prior is not None and win.has_prior[f]:                 # :553-555
+            win.T_prior[f] = win.T_f_w[f]
+            win.inf_prior[f] = 100.0
+    if win.n_lmks:                                                         # :559-567
+        win.lmk_t[:] = s * (win.lmk_t @ R_w_i)                             # exp(lambda) R_w_i^T t, row-wise
 
 
 HUBER_A = float(np.sqrt(1.345))  # AOptimizer.cpp:102, :223
@@ -430,6 +461,14 @@ class B200Optimizer:
         self.last_marginal_info = info
         self.marginalization = (dense, sparse)
         return dense is not None
+
+    def VIInit(self, local_map: abi.Window, optim_scale: bool = False):  # noqa: N802
+        """AOptimizer::VIInit(local_map, R_w_i, optim_scale) (AOptimizer.cpp:448-581): returns (exp(lambda), R_w_i) and updates
+        the map in place.  `local_map.imu_*` must list every (getLastKF(), frame) pair — VIInit has no dt test (:485-502)."""
+        rc, res, st = self.solver.viinit(local_map, optim_scale)
+        self.last_stats = st
+        viinit_write_back(local_map, res)   # the reference ignores the summary here too
+        return res["scale"], res["R_w_i"]
 
     def landmarkOptimization(self, local_map: abi.Window, frame: int, sanity_check=None) -> bool:  # noqa: N802
         """AOptimizer.cpp:98-150.  `sanity_check(l) -> bool` stands for ALandmark::sanityCheck (a data-model method outside the

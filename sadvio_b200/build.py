@@ -13,7 +13,7 @@ LIB_DIR = os.path.join(_HERE, "_lib")
 # SDV_LIB selects a prebuilt experiment library (tools/gpu_round.sh variant mode); it is never rebuilt from here.
 LIB = os.environ.get("SDV_LIB") or os.path.join(LIB_DIR, "libsadvio_b200.so")
 SOURCES = ["sdv_lib.cu"]
-HEADERS = ["sdv_kernels.cuh", "sdv_fused.cuh", "sdv_chol.cuh", "sdv_chol_band.cuh", "sdv_math.cuh", "sdv_types.cuh", "sdv_preint.cuh", "sdv_marg.cuh", "sdv_marg_host.cuh", os.path.join("..", "..", "include", "sdv.h")]
+HEADERS = ["sdv_kernels.cuh", "sdv_fused.cuh", "sdv_chol.cuh", "sdv_chol_band.cuh", "sdv_math.cuh", "sdv_types.cuh", "sdv_preint.cuh", "sdv_marg.cuh", "sdv_marg_host.cuh", "sdv_viinit.cuh", "sdv_peer.cuh", "sdv_struct.cuh", os.path.join("..", "..", "include", "sdv.h")]
 NVCC_FLAGS = [
     *(["-DSDV_BAND_PROF"] if os.environ.get("SDV_BAND_PROF") else []),
     *(["-DSDV_SCHUR_PROF"] if os.environ.get("SDV_SCHUR_PROF") else []),

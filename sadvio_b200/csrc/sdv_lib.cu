@@ -14,6 +14,7 @@
 #include "sdv_marg.cuh"
 #include "sdv_peer.cuh"
 #include "sdv_struct.cuh"
+#include "sdv_viinit.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -2521,6 +2522,136 @@ int sdv_preintegrate(sdv_handle *h, const sdv_imu_intervals *in, sdv_preint *out
     if (out->T_pred) std::memcpy(out->T_pred, &hb[o_T], D * 12 * n);
     if (out->v_pred) std::memcpy(out->v_pred, &hb[o_v], D * 3 * n);
     return SDV_OK;
+}
+
+// AOptimizer::VIInit's problem build + ceres::Solve (AOptimizer.cpp:448-529) as ONE kernel (sdv_viinit.cuh); host buffers in and out
+int sdv_viinit(sdv_handle *h, const sdv_window *w, int32_t optim_scale, sdv_viinit_result *out, sdv_stats *stats) {
+    if (!h || !w || !out) return SDV_ERR_INVALID_ARGUMENT;
+    if (w->abi_version != SDV_ABI_VERSION) return fail(h, SDV_ERR_INVALID_ARGUMENT, "sdv_window.abi_version mismatch");
+    const int F = w->n_frames, Pn = w->n_imu;
+    if (F <= 0 || Pn < 0) return fail(h, SDV_ERR_INVALID_ARGUMENT, "VIInit needs at least one frame");
+    if (!w->T_f_w || !w->v || !out->dv) return fail(h, SDV_ERR_INVALID_ARGUMENT, "null frame arrays");
+    if (Pn > 0 && (!w->imu_i || !w->imu_j || !w->imu_dt || !w->imu_dR || !w->imu_dv || !w->imu_dp || !w->imu_cov))
+        return fail(h, SDV_ERR_INVALID_ARGUMENT, "null IMU arrays");
+    for (int p = 0; p < Pn; p++)
+        if (w->imu_i[p] < 0 || w->imu_i[p] >= F || w->imu_j[p] < 0 || w->imu_j[p] >= F || w->imu_i[p] == w->imu_j[p])
+            return fail(h, SDV_ERR_INVALID_ARGUMENT, "IMU pair index out of range");
+    auto t0 = std::chrono::steady_clock::now();
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    const size_t D = sizeof(double);
+    const int n = 3 * F + 2 + (optim_scale ? 1 : 0), Pc = std::max(Pn, 1);
+    Arena A;
+    const size_t i_P = A.add(sizeof(DevProblem)), i_T = A.add(D * 12 * F), i_v = A.add(D * 3 * F), i_ii = A.add(4 * (size_t)Pc), i_ij = A.add(4 * (size_t)Pc),
+                 i_dt = A.add(D * Pc), i_dR = A.add(D * 9 * Pc), i_dv = A.add(D * 3 * Pc), i_dp = A.add(D * 3 * Pc), i_cov = A.add(D * 81 * Pc);
+    const size_t in_bytes = A.size;
+    const size_t s_inf = A.add(D * 81 * Pc), s_Jw = A.add(D * 81 * Pc), s_rw = A.add(D * 9 * Pc), s_A = A.add(D * (size_t)n * n), s_vec = A.add(D * 8 * (size_t)n);
+    const size_t o_out = A.add(D * (3 * (size_t)F + 3)), o_st = A.add(sizeof(LMState)), o_acc = A.add(sizeof(Accum));
+    std::vector<unsigned char> hb(A.size);
+    unsigned char *d = nullptr;
+    CK(cudaMalloc((void **)&d, A.size));
+    struct Free {
+        unsigned char *p;
+        ~Free() { cudaFree(p); }
+    } guard{d};
+    DevProblem Pd;
+    std::memset(&Pd, 0, sizeof(Pd));
+    Pd.P = Pn;
+    Pd.imu_cov = at<double>(d, i_cov);
+    Pd.imu_inf_sqrt = at<double>(d, s_inf);
+    std::memcpy(&hb[i_P], &Pd, sizeof(Pd));
+    std::memcpy(&hb[i_T], w->T_f_w, D * 12 * F);
+    std::memcpy(&hb[i_v], w->v, D * 3 * F);
+    if (Pn > 0) {
+        std::memcpy(&hb[i_ii], w->imu_i, 4 * (size_t)Pn);
+        std::memcpy(&hb[i_ij], w->imu_j, 4 * (size_t)Pn);
+        std::memcpy(&hb[i_dt], w->imu_dt, D * Pn);
+        std::memcpy(&hb[i_dR], w->imu_dR, D * 9 * Pn);
+        std::memcpy(&hb[i_dv], w->imu_dv, D * 3 * Pn);
+        std::memcpy(&hb[i_dp], w->imu_dp, D * 3 * Pn);
+        std::memcpy(&hb[i_cov], w->imu_cov, D * 81 * Pn);
+    }
+    CK(cudaMemcpyAsync(d, hb.data(), in_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(h->ev[2], s));
+    const int64_t launches0 = h->launches;
+    if (Pn > 0) {
+        k_imu_inf_sqrt<<<(Pn + 3) / 4, 128, 0, s>>>(at<DevProblem>(d, i_P));
+        h->launches++;
+    }
+    VIInitArgs a;
+    a.F = F; a.P = Pn; a.n = n; a.optim_scale = optim_scale ? 1 : 0;
+    a.max_iter = w->max_num_iterations > 0 ? w->max_num_iterations : 50; // int steps = 50 (AOptimizer.cpp:449, :521)
+    if (a.max_iter > SDV_MAX_TRACE - 1) a.max_iter = SDV_MAX_TRACE - 1;
+    const size_t a_bytes = D * (size_t)n * n;
+    a.a_in_smem = a_bytes <= 200 * 1024 ? 1 : 0;
+    a.T_f_w = at<double>(d, i_T); a.v = at<double>(d, i_v);
+    a.imu_i = at<int>(d, i_ii); a.imu_j = at<int>(d, i_ij);
+    a.imu_dt = at<double>(d, i_dt); a.imu_dR = at<double>(d, i_dR); a.imu_dv = at<double>(d, i_dv); a.imu_dp = at<double>(d, i_dp);
+    a.inf_sqrt = at<double>(d, s_inf);
+    a.Jw = at<double>(d, s_Jw); a.rw = at<double>(d, s_rw); a.A = at<double>(d, s_A); a.vecs = at<double>(d, s_vec);
+    a.out = at<double>(d, o_out); a.st = at<LMState>(d, o_st); a.acc = at<Accum>(d, o_acc);
+    a.opt = h->opt;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_viinit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    k_viinit<<<1, VI_THREADS, a.a_in_smem ? a_bytes : 0, s>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], s));
+    CK(cudaMemcpyAsync(&hb[o_out], d + o_out, A.size - o_out, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const double *o = reinterpret_cast<const double *>(&hb[o_out]);
+    std::memcpy(out->dv, o, D * 3 * F);
+    out->r_wi[0] = o[3 * F];
+    out->r_wi[1] = o[3 * F + 1];
+    out->lambda = optim_scale ? o[3 * F + 2] : 0.0;
+    out->scale = std::exp(out->lambda);                                   // the value VIInit returns (AOptimizer.cpp:580)
+    {   // R_w_i = exp_so3(r_wi[0], r_wi[1], 0)  (AOptimizer.cpp:540, geometry.h:131-147)
+        const double wx = out->r_wi[0], wy = out->r_wi[1], ang = std::sqrt(wx * wx + wy * wy);
+        double K[9] = {0, 0, wy, 0, 0, -wx, -wy, wx, 0}, *R = out->R_w_i;
+        if (ang < 1e-9) {
+            for (int k = 0; k < 9; k++) R[k] = K[k] + (k % 4 == 0 ? 1.0 : 0.0);
+        } else {
+            for (int k = 0; k < 9; k++) K[k] /= ang;
+            const double sn = std::sin(ang), cs = std::cos(ang);
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) {
+                    double k2 = 0;
+                    for (int q = 0; q < 3; q++) k2 += K[r * 3 + q] * K[q * 3 + c];
+                    R[r * 3 + c] = (r == c ? 1.0 : 0.0) + (1.0 - cs) * k2 + sn * K[r * 3 + c];
+                }
+        }
+    }
+    LMState st;
+    std::memcpy(&st, &hb[o_st], sizeof(LMState));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+        stats->iterations = st.iter;
+        stats->termination = st.status > 0 ? st.status - 1 : SDV_TERM_NO_CONVERGENCE;
+        stats->num_successful_steps = st.n_ok;
+        stats->num_unsuccessful_steps = st.n_bad;
+        stats->n_reduced = n;
+        stats->n_residual_blocks = Pn;
+        stats->initial_cost = st.initial_cost;
+        stats->final_cost = st.x_cost;
+        stats->final_radius = st.radius;
+        for (int i = 0; i < SDV_MAX_TRACE; i++) {
+            stats->trace_cost[i] = st.trace_cost[i];
+            stats->trace_radius[i] = st.trace_radius[i];
+            stats->trace_model_change[i] = st.trace_model[i];
+            stats->trace_accepted[i] = st.trace_accepted[i];
+        }
+        stats->ms_solve_device = ms;
+        stats->ms_total_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stats->kernel_launches = h->launches - launches0;
+        stats->h2d_bytes = (int64_t)in_bytes;
+        stats->d2h_bytes = (int64_t)(A.size - o_out);
+    }
+    return st.status == 1 + SDV_TERM_FAILURE ? SDV_ERR_NUMERICAL_FAILURE : SDV_OK;
 }
 
 // which: 0 = materialising visual residual+Jacobian kernel (k_lin_visual, the evaluation entry point), 1 = fused linearisation +

@@ -212,6 +212,11 @@ int main(int argc, char **argv) {
         std::printf("\n");
         return 0;
     }
+    if (mode == "dump_viinit") {
+        FlatWindow fw;
+        dump_view(fw, flatten_viinit(*map, fw));
+        return 0;
+    }
     if (mode == "flatten") {
         FlatWindow fw;
         flatten(*map, fixed, vio, kind, fw);
@@ -238,6 +243,30 @@ int main(int argc, char **argv) {
         d.dlmk = d.dbg + 3 * F;
         write_back(fw, d, vio);
         std::printf("1 0\n");
+    } else if (mode == "viinit_writeback") {
+        // no GPU needed: VIInit's state update with a synthetic result (dv entry k = 1e-2 sin(k + 1), r_wi = (0.1, -0.05), lambda = log 2)
+        FlatWindow fw;
+        if (!flatten_viinit(*map, fw)) return 3;
+        std::vector<double> dv(3 * fw.frame_vector.size());
+        for (size_t k = 0; k < dv.size(); k++) dv[k] = 1e-2 * std::sin((double)(k + 1));
+        sdv_viinit_result r;
+        std::memset(&r, 0, sizeof(r));
+        r.dv = dv.data();
+        r.r_wi[0] = 0.1;
+        r.r_wi[1] = -0.05;
+        r.lambda = std::log(2.0);
+        const double w3[3] = {0.1, -0.05, 0.0};
+        detail::exp_so3(w3, r.R_w_i);
+        viinit_write_back(*map, fw, r);
+        std::printf("1 0\n");
+    } else if (mode == "viinit") {
+        // VIInit(local_map, R_w_i, optim_scale = argv[5])
+        B200Optimizer opt(kind, 0);
+        double Rwi[9] = {0};
+        const double scale = opt.VIInit(map, Rwi, f2_frame != 0);
+        std::printf("%d %d %.17g", std::isnan(scale) ? 0 : 1, opt.lastStats().iterations, scale);
+        for (double x : Rwi) std::printf(" %.17g", x);
+        std::printf("\n");
     } else if (mode == "marg") {
         // marginalize(frame0 = oldest keyframe of the window, frame1 = the next one, enable_sparsif = argv[5]), then the window
         // without frame 0 (and without the landmarks only frame 0 saw, unless the prior keeps them) is solved with the prior

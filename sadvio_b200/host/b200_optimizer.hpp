@@ -157,14 +157,15 @@ inline void push_frame_state(FlatWindow &fw, const Frame &f, bool with_prior) {
     for (auto &s : f.sensors) cam_of(fw, *s);
 }
 // IMUFactor + IMUBiasFactor list of addIMUResiduals (AOptimizer.cpp:55-94) over fw.frame_vector
-inline void imu_factors(FlatWindow &fw, const std::unordered_map<const Frame *, int> &frame_idx) {
+// (dt_test = false: the pair list of VIInit, AOptimizer.cpp:485-502, which has no dt <= 1 s test)
+inline void imu_factors(FlatWindow &fw, const std::unordered_map<const Frame *, int> &frame_idx, bool dt_test = true) {
     const int F = (int)fw.frame_vector.size();
     for (int i = 0; i < F; i++) {
         const std::shared_ptr<Frame> &framej = fw.frame_vector[i];
         if (!framej->imu) continue;                                   // :60
         std::shared_ptr<Frame> framei = framej->imu->last_kf;         // :62
         if (!framei) continue;                                        // :65
-        if ((double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9 > 1) continue; // :69
+        if (dt_test && (double)(framej->timestamp_ns - framei->timestamp_ns) * 1e-9 > 1) continue; // :69
         auto it = frame_idx.find(framei.get());
         if (it == frame_idx.end() || !framei->imu || framei == framej) continue; // :72
         const IMU &m = *framej->imu;
@@ -657,6 +658,54 @@ inline bool flatten_marginalization(const std::shared_ptr<Frame> &frame0, const 
     return true;
 }
 
+// VIInit (AOptimizer.cpp:448-529): every frame of the local map newest -> oldest (:456-457), one velocity block per frame with an
+// IMU (:459-464), one IMUFactorInit per frame whose getLastKF() is another frame of the map with an IMU (:485-502, no dt test).
+// No landmark, no observation crosses the ABI: the solve is inertial only.  False when a frame has no IMU (the reference
+// dereferences getIMU() unconditionally at :487).
+inline bool flatten_viinit(const LocalMap &map, FlatWindow &fw) {
+    fw = FlatWindow();
+    map.getLastNFramesIn(map.getMapSize(), fw.frame_vector);
+    const int F = (int)fw.frame_vector.size();
+    std::unordered_map<const Frame *, int> frame_idx;
+    for (int i = 0; i < F; i++) {
+        if (!fw.frame_vector[i]->imu) return false;
+        frame_idx[fw.frame_vector[i].get()] = i;
+        detail::push_frame_state(fw, *fw.frame_vector[i], true);
+    }
+    detail::imu_factors(fw, frame_idx, false);
+    detail::fill_view(fw, true, SDV_FACTOR_ANGULAR, 0, false, false);
+    return F > 0;
+}
+
+// State update of VIInit (AOptimizer.cpp:531-567).  The reference adds dba — a constant block, zero — to the accelerometer bias
+// twice and never touches the gyroscope bias (:535-536): nothing to do for the biases.
+inline void viinit_write_back(LocalMap &map, FlatWindow &fw, const sdv_viinit_result &r) {
+    const int F = (int)fw.frame_vector.size();
+    const double s = std::exp(r.lambda), *Rw = r.R_w_i;
+    for (int f = 0; f < F; f++) {
+        Frame &fr = *fw.frame_vector[f];
+        for (int k = 0; k < 3; k++) fr.imu->v[k] += r.dv[3 * f + k];                     // :533-534
+        double R[9], Rn[9];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) R[i * 3 + j] = fr.T_f_w[i * 4 + j];
+        detail::mul33(R, Rw, Rn);                                                            // :550, T_w_i = [R_w_i | 0]
+        for (int i = 0; i < 3; i++) {
+            for (int j = 0; j < 3; j++) fr.T_f_w[i * 4 + j] = Rn[i * 3 + j];
+            fr.T_f_w[i * 4 + 3] *= s;                                                   // :549
+        }
+        if (fr.has_prior) {                                                             // :553-555
+            fr.T_prior = fr.T_f_w;
+            fr.inf_prior.fill(100.0);
+        }
+    }
+    for (auto &lm : map.pointxd) {                                                      // :559-567
+        if (lm->isOutlier()) continue;
+        double t[3];
+        for (int i = 0; i < 3; i++) t[i] = Rw[0 * 3 + i] * lm->t_w[0] + Rw[1 * 3 + i] * lm->t_w[1] + Rw[2 * 3 + i] * lm->t_w[2]; // R_w_i^T t
+        for (int i = 0; i < 3; i++) lm->t_w[i] = s * t[i];
+    }
+}
+
 // Drop-in for the reference optimizer object (one instance = one sdv_handle, as the back-end optimizer instance,
 // slamParameters.cpp:273-274).  `factor_kind` picks what the reference picks by class: AngularAdjustmentCERESAnalytic
 // (SDV_FACTOR_ANGULAR) or BundleAdjustmentCERESAnalytic (SDV_FACTOR_PIXEL).
@@ -705,6 +754,22 @@ class B200Optimizer {
     // The same with the IMU factor to the previous keyframe and a Huber loss on the visual blocks (AOptimizer.cpp:219-297):
     // false without write-back when the summary is not usable (Ceres FAILURE, :259), else poses, velocities and biases.
     bool singleFrameVIOptimization(std::shared_ptr<Frame> &moving_frame) { return single_frame(moving_frame, true); }
+    // Visual-inertial initialisation (AOptimizer.cpp:448-581): gravity direction R_w_i (row-major 3x3 out), keyframe velocities and —
+    // with optim_scale — the metric scale; velocities, poses, priors and landmarks of the map are updated as the reference does
+    // (:531-567) and exp(lambda) is returned.  NaN with the state untouched when no solve could run (no GPU, a frame without IMU).
+    double VIInit(std::shared_ptr<LocalMap> &local_map, double *R_w_i, bool optim_scale) {
+        FlatWindow fw;
+        if (!_h || !flatten_viinit(*local_map, fw)) return std::nan("");
+        std::vector<double> dv(3 * fw.frame_vector.size(), 0.0);
+        sdv_viinit_result res;
+        std::memset(&res, 0, sizeof(res));
+        res.dv = dv.data();
+        const int rc = sdv_viinit(_h, &fw.view, optim_scale ? 1 : 0, &res, &_stats);
+        if (rc != SDV_OK && rc != SDV_ERR_NUMERICAL_FAILURE) return std::nan(""); // (the reference ignores the summary: FAILURE still writes back)
+        viinit_write_back(*local_map, fw, res);
+        if (R_w_i) std::memcpy(R_w_i, res.R_w_i, sizeof(res.R_w_i));
+        return res.scale;
+    }
     // Marginal prior of the keyframe that leaves the window (AngularAdjustmentCERESAnalytic.cpp:488-739 /
     // BundleAdjustmentCERESAnalytic.cpp:431-660) on the GPU; fills _marginalization (what the next window solve wires in) and
     // _marginalization_last (what the next marginalisation folds in) like the reference does (:714-736).

@@ -209,3 +209,54 @@ def check_euroc_bias(kfs):
     assert len(kfs) == 30
     assert np.linalg.norm(orc.imu_get(kfs[29]["imu"], "ba") - EUROC_BA) < 0.02
     assert np.linalg.norm(orc.imu_get(kfs[29]["imu"], "bg") - EUROC_BG) < 0.02
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# imu_test.cpp:813-880 — the initialisation part of simuEuroc: 10 keyframes 0.5 s apart on the EuRoC ground truth from sample
+# 2000 on, IMU samples differentiated from it (no bias), poses and velocities scaled by 0.5; VIInit(local_map, R_w_i, true)
+# must bring every keyframe pose back onto the ground truth (0.02).
+# ----------------------------------------------------------------------------------------------------------------
+def euroc_viinit_window(n_kf=10, dt_kf=0.5, scale_factor=0.5):
+    """Returns (window, ground-truth T_w_f 4x4 per frame of the window, newest first)."""
+    acc, gyr, R, p, v, ts_f, ts_ns = _euroc_samples()
+    rate = 200.0
+    eta6 = eta(rate)                                                                        # SetUp(), :60-66
+    T0 = _T_f_w(R[0], scale_factor * p[0])                                                   # :826-828
+    imu0 = orc.imu_state(acc[0], gyr[0], T_f_w=T0, v=scale_factor * v[0], is_kf=True)        # :823-831
+    kfs = [dict(T_f_w=T0.copy(), imu=imu0, ts=int(ts_ns[0]), k=0)]
+    tsp, last, last_ts = ts_f[0], imu0, int(ts_ns[0])
+    for i in range(1, acc.shape[0]):
+        dt_vote = (ts_f[i] - tsp) * 1e-9                                                     # :838
+        kf_imu = kfs[-1]["imu"]
+        cur = orc.process_imu(last, orc.imu_get(kf_imu, "ba"), orc.imu_get(kf_imu, "bg"), (int(ts_ns[i]) - last_ts) * 1e-9, eta6, rate,
+                              acc[i], gyr[i])                                                # :841-846
+        T = _T_f_w(R[i], scale_factor * p[i])                                                # :849-852
+        cur[15:27] = T
+        cur[12:15] = scale_factor * v[i]                                                     # :853
+        last, last_ts = cur, int(ts_ns[i])
+        if dt_vote > dt_kf:                                                                  # :856-861
+            cur[27] = 1.0
+            kfs.append(dict(T_f_w=T.copy(), imu=cur, ts=int(ts_ns[i]), k=i))
+            tsp = ts_f[i]
+        if len(kfs) == n_kf:                                                                 # :864-865
+            break
+    for rec in kfs:
+        rec["T_prior"] = rec["T_f_w"]
+    win, pairs = _kf_window(kfs, BACC_NOISE, BGYR_NOISE)
+    win.n_fixed = 0
+    win.has_prior = np.zeros(win.n_frames, np.uint8)                                         # no setPrior in this part of the test
+    # VIInit pairs every frame with its getLastKF() — no dt test (AOptimizer.cpp:485-502); at 0.5 s spacing _kf_window kept them all
+    assert len(pairs) == len(kfs) - 1
+    gt = []
+    for rec in kfs[::-1]:
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R[rec["k"]], p[rec["k"]]
+        gt.append(T)
+    return win, gt
+
+
+def check_euroc_viinit(win, gt, tol=0.02):
+    """Assertions of imu_test.cpp:873-878 on the updated window."""
+    for f in range(win.n_frames):
+        T_f_w = np.vstack([win.T_f_w[f].reshape(3, 4), [0, 0, 0, 1]])
+        assert np.linalg.norm(gt[f] @ T_f_w - np.eye(4)) < tol, (f, np.linalg.norm(gt[f] @ T_f_w - np.eye(4)))

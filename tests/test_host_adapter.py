@@ -545,3 +545,84 @@ def test_adapter_marginalize_then_solve_matches_python_binding(adapter_exe, vio,
     remap = {int(l): k for k, l in enumerate(src)}
     got = np.array([lm[l] for l in src])
     assert np.abs(got - w2.lmk_t).max() < tol * max(1.0, np.abs(w2.lmk_t).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# VIInit (AOptimizer.cpp:448-581)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_viinit_pairs_have_no_dt_test(adapter_exe):
+    """VIInit pairs every frame with its getLastKF() (AOptimizer.cpp:485-502): the keyframe more than 1 s after its previous one
+    that the window solve leaves without IMU factor (:69) still gets its IMUFactorInit; no observation crosses the ABI."""
+    win = synth.make_window("small")
+    txt, _, exp_imu, _ = graph_text(win, np.random.default_rng(0), False, gap_after=3)
+    got = parse_dump(subprocess.run([adapter_exe, "dump_viinit", "1", "0"], input=txt, capture_output=True, text=True, check=True).stdout)
+    assert got.n_imu == win.n_imu == len(exp_imu) + 1 and got.n_obs == 0 and got.n_lmks == 0 and got.vio
+    assert np.array_equal(got.imu_i, win.imu_i) and np.array_equal(got.imu_j, win.imu_j)
+    assert np.sum(got.imu_dt > 1.0) == 1 and np.array_equal(got.imu_cov, win.imu_cov) and np.array_equal(got.T_f_w, win.T_f_w)
+    assert np.array_equal(got.v, win.v)
+
+
+def _parse_state(out, F, L):
+    rows = [np.array([float(x) for x in ln.split()]) for ln in out[2:2 + F]]      # oldest -> newest
+    lm = np.array([[float(x) for x in ln.split()[:3]] for ln in out[2 + F:2 + F + L]])
+    return rows, lm
+
+
+def test_viinit_writeback_matches_python_mirror(adapter_exe):
+    from oracle import oracle as orc
+    from sadvio_b200 import api
+
+    win = synth.make_window("small")
+    win.has_prior[:] = 0
+    win.has_prior[-1] = 1
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), False, force_outlier={5})
+    out = subprocess.run([adapter_exe, "viinit_writeback", "1", "0"], input=txt, capture_output=True, text=True, check=True).stdout.split("\n")
+    F, L = win.n_frames, win.n_lmks
+    ref = synth.make_window("small")
+    res = dict(dv=(1e-2 * np.sin(np.arange(3 * F) + 1.0)).reshape(F, 3), R_w_i=orc.exp_so3([0.1, -0.05, 0.0]), lam=np.log(2.0))
+    lm5 = ref.lmk_t[5].copy()
+    api.viinit_write_back(ref, res)
+    ref.lmk_t[5] = lm5                                                            # outliers keep their position (AOptimizer.cpp:561)
+    rows, lm = _parse_state(out, F, L)
+    for k, row in enumerate(rows):
+        f = F - 1 - k
+        assert np.abs(row[:12] - ref.T_f_w[f]).max() < 1e-12 and np.abs(row[12:15] - ref.v[f]).max() < 1e-14
+        assert np.array_equal(row[15:18], ref.ba[f]) and np.array_equal(row[18:21], ref.bg[f])   # biases untouched
+    assert np.abs(lm - ref.lmk_t).max() < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optim_scale", [0, 1])
+def test_adapter_viinit_matches_python_binding(adapter_exe, optim_scale):
+    import copy
+
+    from oracle import oracle as orc
+    from sadvio_b200 import api
+
+    base = synth.make_window("small")
+    Rg = orc.exp_so3([0.1, -0.15, 0.0])
+    sc = 0.6 if optim_scale else 1.0
+    for f in range(base.n_frames):                   # a rotated, shrunk world: what VIInit is there to undo
+        T = base.T_f_w[f].reshape(3, 4).copy()
+        T[:, :3] = T[:, :3] @ Rg.T
+        T[:, 3] *= sc
+        base.T_f_w[f] = T.reshape(12)
+        base.v[f] = sc * (Rg @ base.v[f])
+    base.lmk_t = sc * (base.lmk_t @ Rg.T)
+    base.normalise()
+    txt, _, _, _ = graph_text(base, np.random.default_rng(0), False)
+    out = subprocess.run([adapter_exe, "viinit", "1", "0", "0", str(optim_scale)], input=txt, capture_output=True, text=True, check=True).stdout.split("\n")
+    head = [float(x) for x in out[1].split()]
+    ref = copy.deepcopy(base)
+    opt = api.B200Optimizer()
+    scale, R_w_i = opt.VIInit(ref, bool(optim_scale))
+    assert head[0] == 1 and int(head[1]) == opt.last_stats["iterations"] and abs(head[2] - scale) <= 1e-12 * scale
+    assert np.abs(np.array(head[3:12]).reshape(3, 3) - R_w_i).max() < 1e-12
+    rc0, res0, st0 = orc.viinit(base, bool(optim_scale))
+    assert st0["iterations"] == opt.last_stats["iterations"] and abs(res0["scale"] - scale) <= 1e-6 * scale
+    F, L = base.n_frames, base.n_lmks
+    rows, lm = _parse_state(out, F, L)
+    for k, row in enumerate(rows):
+        f = F - 1 - k
+        assert np.abs(row[:12] - ref.T_f_w[f]).max() < 1e-9 and np.abs(row[12:15] - ref.v[f]).max() < 1e-9
+    assert np.abs(lm - ref.lmk_t).max() < 1e-9
