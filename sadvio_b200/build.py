@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     *(["-DSDV_SCHUR_PROF"] if os.environ.get("SDV_SCHUR_PROF") else []),
     # k_chol_band switches (sdv_chol_band.cuh): SDV_BAND_BABE=0 / SDV_BAND_BACKWARD_V2=0 build the round-1 kernel,
     # SDV_BAND_REV=1 (with SDV_BAND_BABE=0) the index-reversed debugging variant, SDV_BAND_STREAM1=0 the tensor-core first-column updates
-    *([f"-D{k}={os.environ[k]}" for k in ("SDV_BAND_BACKWARD_V2", "SDV_BAND_REV", "SDV_BAND_BABE", "SDV_BAND_STREAM1", "SDV_BAND_SKEW") if os.environ.get(k)]),
+    *([f"-D{k}={os.environ[k]}" for k in ("SDV_BAND_BACKWARD_V2", "SDV_BAND_BACKWARD_V3", "SDV_BAND_REV", "SDV_BAND_BABE", "SDV_BAND_STREAM1", "SDV_BAND_SKEW", "SDV_FT", "SDV_FT_LMK", "SDV_FUSED_CPS") if os.environ.get(k)]),
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
 ]
 

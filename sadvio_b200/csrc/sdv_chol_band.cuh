@@ -68,6 +68,17 @@ constexpr bool BAND_STREAM1 = SDV_BAND_STREAM1 != 0;
 #ifndef SDV_BAND_BACKWARD_V2
 #define SDV_BAND_BACKWARD_V2 1
 #endif
+// EXPERIMENT (-DSDV_BAND_BACKWARD_V3=1; parity green on B200, OFF by default: no gain).  Software-pipelined full steps of the
+// backward solve (band_backward_pipe_step below): the products with x_(k+2) .. x_(k+bw) of step k are formed during step k+1, in
+// the shadow of its shuffles and its trip through shared memory, so that the dependence chain of a step is the d = 1 block, one
+// reduction and the product with the inverse.  Measured (tools/micro/backward.cu, one warp alone on the SM, cycles per block
+// step at bw = 4): shipped loop 683-706, V2 658-668, V3 669-679 with the TMA ring; with the factor resident in shared memory
+// V2 517, V3 485, and 386 for the d = 1 block + inverse alone — i.e. the dependence chain itself (two shared-memory round trips,
+// two reductions, the publication of x) is ~390 cycles, the blocks d >= 2 cost ~100-130 either way, and the ring (one mbarrier
+// try_wait, 90 cycles even when complete, + one expect_tx / bulk-copy issue per step) ~170.  In the kernel: 112.5 us against 112.7 us.
+#ifndef SDV_BAND_BACKWARD_V3
+#define SDV_BAND_BACKWARD_V3 0
+#endif
 // First milestone of the two-way dissection, a debugging aid (parity green on B200, round 2): with
 // -DSDV_BAND_REV=1 the whole kernel factors P S P instead of S (P = index reversal, row i <-> n_pad-1-i, which keeps the
 // 16-column blocks aligned) and scatters the solution back — what the second CTA of the cluster will do on its half.  The
@@ -438,6 +449,93 @@ template <int BW> SDV_DEV double band_backward_full_step(const double *sb, const
 }
 #endif
 
+#if SDV_BAND_BACKWARD_V3
+// This lane's partial (rows 8 hh .. 8 hh + 7) of sum_{d = 2 .. BW} (L_(k+d,k))^T x_(k+d), column c, from the ring stage `sb` of block column k.
+template <int BW> SDV_DEV double band_backward_partial(const double *sb, const double *gs, int k, int lane) {
+    const int c = lane & 15, hh = lane >> 4;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int d = BW; d >= 2; d--) {
+        const double *Lc = sb + d * 256 + hh * 128 + c;
+        const double2 *x2 = reinterpret_cast<const double2 *>(gs + (k + d) * BN + hh * 8);
+        const double2 xa = x2[0], xb = x2[1], xc = x2[2], xd = x2[3];
+        s0 = fma(Lc[0], xa.x, s0);
+        s1 = fma(Lc[16], xa.y, s1);
+        s2 = fma(Lc[32], xb.x, s2);
+        s3 = fma(Lc[48], xb.y, s3);
+        s0 = fma(Lc[64], xc.x, s0);
+        s1 = fma(Lc[80], xc.y, s1);
+        s2 = fma(Lc[96], xd.x, s2);
+        s3 = fma(Lc[112], xd.y, s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+// One FULL block step k with qp = band_backward_partial of column k already known; returns x_k[c] in both half-warps and — NEXT —
+// leaves the partial of column k-1 (stage `sbn`) in qp: its d = 2 block multiplies x_(k+1), which this step loads anyway, the
+// blocks d >= 3 fill the two latency holes of the chain (after the reduction shuffle, after the trip of rv through shared memory).
+template <int BW, bool NEXT> SDV_DEV double band_backward_pipe_step(const double *sb, const double *sbn, const double *gs, double *rvs, int k, int lane, double &qp) {
+    const int c = lane & 15, hh = lane >> 4;
+    const double *Lc = sb + 256 + hh * 128 + c, *Mi = sb + (BW + 1) * 256 + hh * 128 + c;
+    double l[8], m[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) l[q] = Lc[16 * q];
+    const double2 *x2 = reinterpret_cast<const double2 *>(gs + (k + 1) * BN + hh * 8);
+    const double2 xa = x2[0], xb = x2[1], xc = x2[2], xd = x2[3];
+    const double yk = gs[k * BN + c];
+    double s0 = fma(l[0], xa.x, qp), s1 = l[1] * xa.y, s2 = l[2] * xb.x, s3 = l[3] * xb.y;
+    s0 = fma(l[4], xc.x, s0);
+    s1 = fma(l[5], xc.y, s1);
+    s2 = fma(l[6], xd.x, s2);
+    s3 = fma(l[7], xd.y, s3);
+    double sum = (s0 + s1) + (s2 + s3);
+    sum += __shfl_xor_sync(FULL, sum, 16);
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+    if (NEXT) { // column k-1, d = 2: x_(k+1) is in registers
+        const double *Ln = sbn + 2 * 256 + hh * 128 + c;
+        n0 = Ln[0] * xa.x;
+        n1 = Ln[16] * xa.y;
+        n2 = Ln[32] * xb.x;
+        n3 = Ln[48] * xb.y;
+        n0 = fma(Ln[64], xc.x, n0);
+        n1 = fma(Ln[80], xc.y, n1);
+        n2 = fma(Ln[96], xd.x, n2);
+        n3 = fma(Ln[112], xd.y, n3);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) m[q] = Mi[16 * q];
+    const double rv = yk - sum;
+    if (hh == 0) rvs[c] = rv;
+    __syncwarp();
+    const double2 *r2 = reinterpret_cast<const double2 *>(rvs + hh * 8);
+    const double2 ra = r2[0], rb = r2[1], rc = r2[2], rd = r2[3];
+    if (NEXT) { // column k-1, d = 3 .. BW: x_(k+2) .. x_(k+BW-1)
+#pragma unroll
+        for (int d = 3; d <= BW; d++) {
+            const double *Ln = sbn + d * 256 + hh * 128 + c;
+            const double2 *y2 = reinterpret_cast<const double2 *>(gs + (k - 1 + d) * BN + hh * 8);
+            const double2 ya = y2[0], yb = y2[1], yc = y2[2], yd = y2[3];
+            n0 = fma(Ln[0], ya.x, n0);
+            n1 = fma(Ln[16], ya.y, n1);
+            n2 = fma(Ln[32], yb.x, n2);
+            n3 = fma(Ln[48], yb.y, n3);
+            n0 = fma(Ln[64], yc.x, n0);
+            n1 = fma(Ln[80], yc.y, n1);
+            n2 = fma(Ln[96], yd.x, n2);
+            n3 = fma(Ln[112], yd.y, n3);
+        }
+    }
+    double x0 = m[0] * ra.x, x1 = m[1] * ra.y, x2v = m[2] * rb.x, x3 = m[3] * rb.y;
+    x0 = fma(m[4], rc.x, x0);
+    x1 = fma(m[5], rc.y, x1);
+    x2v = fma(m[6], rd.x, x2v);
+    x3 = fma(m[7], rd.y, x3);
+    double x = (x0 + x1) + (x2v + x3);
+    x += __shfl_xor_sync(FULL, x, 16);
+    qp = (n0 + n1) + (n2 + n3);
+    return x;
+}
+#endif
+
 // System preparation for k_chol_band (same arithmetic as k_sysprep): gradient-tolerance test, Jacobi column scales at
 // iteration 0, LM damping -> dmp (negative = padding column), right-hand side -> gs.  Returns true (uniformly) when the
 // gradient tolerance terminates the solve.  Not inlined: its square roots and divisions would otherwise raise the register
@@ -600,9 +698,12 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
     long long tw[5] = {0, 0, 0, 0, 0}; // chain warp: its wait split by barrier [step, rhs, copy, (1,1), (2,1)]
 #define BAND_TICK(q) do { tn = rdclk(); tp[q] += tn - tc; tc = tn; } while (0)
 #define BAND_BUSY(q) do { tb[q] += rdclk() - tc; } while (0)
+    long long tbk[4] = {0, 0, 0, 0}, tbc = 0, t_xsep = 0; // backward solve, warp 0: [stage wait, compute, publish, refill]
+#define BAND_TICKB(q) do { long long t_ = rdclk(); tbk[q] += t_ - tbc; tbc = t_; } while (0)
 #else
 #define BAND_TICK(q) do { } while (0)
 #define BAND_BUSY(q) do { } while (0)
+#define BAND_TICKB(q) do { } while (0)
 #endif
 
     // block row i of S (blocks max(0, i - bw) .. i) -> window, 16-byte cp.async chunks; threads [t0, t0 + nt)
@@ -1189,7 +1290,13 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
 #if SDV_BAND_BABE
         int nbk = nb; // block columns this CTA back-substitutes: CTA 1 starts below the separator, once its unknowns are there
         if (rev) {
+#ifdef SDV_BAND_PROF
+            const long long t_x0 = rdclk();
+#endif
             mbar_wait_cluster(&bar_xsep, 0); // also: CTA 0 has finished reading this CTA's window (the ring overlays it)
+#ifdef SDV_BAND_PROF
+            t_xsep = rdclk() - t_x0;
+#endif
             nbk = __ldcg(&acc->chol_fail) != 0 ? 0 : nint;
         }
 #endif
@@ -1202,15 +1309,36 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
         const int c = lane & 15, hh = lane >> 4;
         double *rvs = invs; // 16 doubles of scratch (the reciprocal diagonals are no longer needed)
         int s = 0, ph = 0;
+#if SDV_BAND_BACKWARD_V3
+        bool have_qp = false;
+        double qp = 0.0;
+#endif
         for (int it = 0; it < BAND_BNB; it++) {
             const int k = BAND_BNB - 1 - it;
             const int nd = bw < nb - 1 - k ? bw : nb - 1 - k;
             BAND_TICK(5);
+#ifdef SDV_BAND_PROF
+            tbc = rdclk();
+#endif
             mbar_wait(&full[s], (unsigned)ph);
             BAND_TICK(3);
+            BAND_TICKB(0);
             const double *sb = ring + s * stage_doubles;
             double x;
-#if SDV_BAND_BACKWARD_V2
+#if SDV_BAND_BACKWARD_V3
+            if (nd == bw && (bw == 3 || bw == 4)) { // full step of the common band widths, software-pipelined with the next one
+                const bool next = it + 1 < BAND_BNB; // block column k-1 exists (and its step is full, too)
+                const int sn = s + 1 == NS ? 0 : s + 1;
+                const double *sbn = ring + sn * stage_doubles;
+                if (!have_qp) qp = bw == 3 ? band_backward_partial<3>(sb, gs, k, lane) : band_backward_partial<4>(sb, gs, k, lane);
+                if (next) {
+                    mbar_wait(&full[sn], (unsigned)(sn == 0 ? ph ^ 1 : ph));
+                    x = bw == 3 ? band_backward_pipe_step<3, true>(sb, sbn, gs, rvs, k, lane, qp) : band_backward_pipe_step<4, true>(sb, sbn, gs, rvs, k, lane, qp);
+                } else
+                    x = bw == 3 ? band_backward_pipe_step<3, false>(sb, sbn, gs, rvs, k, lane, qp) : band_backward_pipe_step<4, false>(sb, sbn, gs, rvs, k, lane, qp);
+                have_qp = next;
+            } else
+#elif SDV_BAND_BACKWARD_V2
             if (nd == bw && (bw == 3 || bw == 4)) { // full step of the common band widths: specialised body
                 x = bw == 3 ? band_backward_full_step<3>(sb, gs, rvs, k, lane) : band_backward_full_step<4>(sb, gs, rvs, k, lane);
             } else
@@ -1249,6 +1377,7 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
             x = (x0 + x1) + (x2v + x3);
             x += __shfl_xor_sync(FULL, x, 16);
             }
+            BAND_TICKB(1);
             if (hh == 0) {
                 gs[k * BN + c] = x;
 #if SDV_BAND_BABE
@@ -1269,11 +1398,14 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
             }
 #endif
             __syncwarp();
+            BAND_TICKB(2);
             if (lane == 0 && it + NS < BAND_BNB) {
                 const int k2 = BAND_BNB - 1 - (it + NS);
                 mbar_expect_tx(&full[s], stage_bytes);
                 bulk_g2s(ring + s * stage_doubles, Lb + (size_t)k2 * stage_doubles, stage_bytes, &full[s]);
             }
+            __syncwarp();
+            BAND_TICKB(3);
             if (++s == NS) {
                 s = 0;
                 ph ^= 1;
@@ -1282,18 +1414,30 @@ __global__ void __launch_bounds__(BCT, 1) k_chol_band(const DevProblem *__restri
     }
     __syncthreads();
 #if SDV_BAND_BABE
+#ifdef SDV_BAND_PROF
+    if (rev && prof && threadIdx.x == 0) { // CTA 1's backward solve: slots 6, 7 of warps 6, 7, and its wait for the separator unknowns
+        for (int q = 0; q < 4; q++) prof[(6 + (q >> 1)) * 8 + 6 + (q & 1)] = (double)tbk[q];
+        prof[8 * 8 + 6] = (double)t_xsep;
+    }
+    const long long t_sync3 = rdclk();
+#endif
     if (babe) { // #3: both halves of x are in CTA 0's shared memory and in dxp
         __threadfence();
         cluster_sync_all();
         if (rev) return;
     }
+#ifdef SDV_BAND_PROF
+    if (prof && threadIdx.x == 0) prof[8 * 8 + 7] = (double)(rdclk() - t_sync3); // CTA 0 waiting for CTA 1 at the end
+#endif
 #endif
     BAND_TICK(5);
 #ifdef SDV_BAND_PROF
     if (prof && lane == 0)
         for (int q = 0; q < 6; q++) prof[warp * 8 + q] = (double)tp[q]; // warp 0: [setup, wait, chain, -, tail, backward]
-    if (prof && lane == 0 && warp == 0)
+    if (prof && lane == 0 && warp == 0) {
         for (int q = 0; q < 5; q++) prof[(q >> 1) * 8 + 6 + (q & 1)] = (double)tw[q]; // free slots 6, 7 of warps 0, 1, 2
+        for (int q = 0; q < 4; q++) prof[(4 + (q >> 1)) * 8 + 6 + (q & 1)] = (double)tbk[q]; // slots 6, 7 of warps 4, 5
+    }
 #endif
 
     // ---------------------------------------------------------------------- reduced-parameter update, model-decrease terms,

@@ -24,8 +24,22 @@
 
 namespace sdv {
 
-constexpr int FT = 160;         // threads per CTA = slots per tile (upper bound)
-constexpr int FT_LMK = 64;      // landmarks per tile (upper bound)
+// tile geometry (compile-time; -DSDV_FT / -DSDV_FT_LMK / -DSDV_FUSED_CPS for experiments: smaller tiles, more CTAs per SM)
+#ifndef SDV_FT
+#define SDV_FT 160
+#endif
+#ifndef SDV_FT_LMK
+#define SDV_FT_LMK 64
+#endif
+#ifndef SDV_FUSED_CPS
+#define SDV_FUSED_CPS 2
+#endif
+constexpr int FT = SDV_FT;          // threads per CTA = slots per tile (upper bound)
+constexpr int FT_LMK = SDV_FT_LMK;  // landmarks per tile (upper bound)
+constexpr int FUSED_CPS = SDV_FUSED_CPS;                      // resident CTAs per SM of k_lin_schur (shared memory: FT_SMEM_SCHUR each)
+constexpr int FUSED_CPS_BACK = FUSED_CPS > 3 ? FUSED_CPS : 3; // ... of k_backsub_cost
+constexpr int FTW = (FT + 31) / 32; // warps per CTA
+static_assert(FT > FT_LMK, "one thread per landmark plus one in the tile prologue");
 constexpr int FT_SD = 75;       // doubles per slot in shared memory: W 18 | Y 18 | D 39 (21 block, 6 rhs, 6 diag, 6 raw gradient)
 constexpr int FT_SMEM_SCHUR = (FT * FT_SD + 9 * FT + FT_LMK * 10) * (int)sizeof(double);
 constexpr int LMK_AUX = 12;     // V^-1 (6) | g_l (3) | D_l (3)
@@ -139,10 +153,22 @@ SDV_DEV void tri_ij(int k, int &i, int &j) { // k = i (i + 1) / 2 + j, j <= i < 
     j = k - i * (i + 1) / 2;
 }
 
+#ifdef SDV_SCHUR_PROF
+// developer trace (clock64 of thread 0 of CTA 0 and of the last CTA after every phase of their FIRST tile, globaltimer at entry / exit)
+__device__ double g_schur_prof[32];
+#define SCHUR_TICK(q) do { if (tid == 0 && tile == (int)blockIdx.x && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) g_schur_prof[(blockIdx.x ? 16 : 0) + (q)] = (double)(clock64() - t_entry); } while (0)
+#else
+#define SCHUR_TICK(q) do { } while (0)
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt, double *Sb,
+__global__ void __launch_bounds__(FT, FUSED_CPS) k_lin_schur(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, SolverOpts opt, double *Sb,
                                                      double *scale_l, double *lmk_aux) {
     const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
+#ifdef SDV_SCHUR_PROF
+    const long long t_entry = clock64();
+    unsigned long long gt0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
     if (st->status != 0) return;
     const LinBuf &B = st->cur ? B1 : B0;
     extern __shared__ double fsm[];
@@ -152,7 +178,7 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
     __shared__ int sp[FT_LMK + 1], scol[FT], sframe[FT], rbeg[FT_LMK + 1];
     __shared__ unsigned char rflag[FT_LMK];
     __shared__ int s_nruns;
-    __shared__ double gred[FT / 32];
+    __shared__ double gred[FTW];
     const int tid = threadIdx.x;
     const int ld = P.ld;
     double *g = Sb + (size_t)P.n_pad * ld, *cdiag = g + ld, *graw = cdiag + ld;
@@ -166,6 +192,7 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
         __syncthreads();
         const int ns = sp[nl];
         const bool active = tid < ns;
+        SCHUR_TICK(0);
         // ---------------------------------------------------------------- phase A: one thread per slot
         SlotAcc a;
         double hl[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
@@ -187,6 +214,7 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
             double p[3];
             landmark_position(P, B, l, p);
             const int qa = P.slot_obs_ptr[s], qb = P.slot_obs_ptr[s + 1];
+            SCHUR_TICK(1);
             for (int q = qa; q < qb; q++) {
                 double r[2], Jp[12], Jl[6];
                 obs_eval<KIND>(P, B, P.slot_obs[q], p, r, Jp, Jl);
@@ -213,7 +241,9 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
         for (int k = 0; k < 6; k++) part[k * FT + tid] = hl[k];
 #pragma unroll
         for (int k = 0; k < 3; k++) part[(6 + k) * FT + tid] = gl[k];
+        SCHUR_TICK(2);
         __syncthreads();
+        SCHUR_TICK(3);
         // ---------------------------------------------------------------- phase L: one thread per landmark
         if (tid < nl) {
             const int l = lA + tid, t0 = sp[tid], t1 = sp[tid + 1], m = t1 - t0;
@@ -288,7 +318,9 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
             for (int k = 0; k < 3; k++) lmd[tid * 10 + 6 + k] = g3[k];
             lmd[tid * 10 + 9] = elim ? 1.0 : 0.0;
         }
+        SCHUR_TICK(4);
         __syncthreads();
+        SCHUR_TICK(5);
         // ---------------------------------------------------------------- phase S: per slot, Schur products into shared memory
         if (active) {
             double *sd = slotd + tid * FT_SD;
@@ -346,7 +378,9 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
             rbeg[nr] = nl;
             s_nruns = nr;
         }
+        SCHUR_TICK(6);
         __syncthreads();
+        SCHUR_TICK(7);
         // ---------------------------------------------------------------- phase B: one thread per entry of a run's block
         const int nruns = s_nruns;
         for (int r = 0; r < nruns; r++) {
@@ -395,13 +429,24 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
                 atomicAdd(dst, s);
             }
         }
+        SCHUR_TICK(8);
         __syncthreads(); // the next tile reuses every shared array
+        SCHUR_TICK(9);
     }
+#ifdef SDV_SCHUR_PROF
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        g_schur_prof[(blockIdx.x ? 16 : 0) + 10] = (double)(clock64() - t_entry);
+        g_schur_prof[(blockIdx.x ? 16 : 0) + 11] = (double)gt0;
+        g_schur_prof[(blockIdx.x ? 16 : 0) + 12] = (double)gt1;
+    }
+#endif
     for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     if ((tid & 31) == 0) gred[tid >> 5] = gmax;
     __syncthreads();
     if (tid == 0) {
-        for (int q = 1; q < FT / 32; q++) gmax = fmax(gmax, gred[q]);
+        for (int q = 1; q < FTW; q++) gmax = fmax(gmax, gred[q]);
         if (gmax > 0.0) atomic_max_nonneg(reinterpret_cast<double *>(&acc->grad_max_bits), gmax);
     }
 }
@@ -409,14 +454,14 @@ __global__ void __launch_bounds__(FT, 2) k_lin_schur(const DevProblem *__restric
 // landmark back-substitution delta_l = -V^-1 (g_l + sum_f W_f^T delta_f) with W_f^T delta_f = sum_obs Jl^T (Jp delta_f) recomputed,
 // candidate landmark parameters, model-decrease / norm partial sums, and the cost of the visual factors at the candidate point
 template <int KIND>
-__global__ void __launch_bounds__(FT, 3) k_backsub_cost(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, const double *dxp,
+__global__ void __launch_bounds__(FT, FUSED_CPS_BACK) k_backsub_cost(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, const double *dxp,
                                                         const double *lmk_aux) {
     const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
     if (st->status != 0 || !st->step_valid) return;
     const int cand = 1 - st->cur;
     const LinBuf &Bx = st->cur ? B1 : B0;
     const LinBuf &Bc = st->cur ? B0 : B1;
-    __shared__ double part[3][FT], pc[FT_LMK][3], red[FT / 32][5];
+    __shared__ double part[3][FT], pc[FT_LMK][3], red[FTW][5];
     __shared__ int sp[FT_LMK + 1];
     const int tid = threadIdx.x;
     const int Oloc = P.o1 - P.o0;
@@ -529,7 +574,7 @@ __global__ void __launch_bounds__(FT, 3) k_backsub_cost(const DevProblem *__rest
     if (tid < 5) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < FT / 32; w++) v += red[w][tid];
+        for (int w = 0; w < FTW; w++) v += red[w][tid];
         if (tid == 4) v *= 0.5;
         double *dst = tid == 0 ? &acc->model_gd : (tid == 1 ? &acc->model_dd : (tid == 2 ? &acc->step_norm2 : (tid == 3 ? &acc->cand_norm2 : &acc->cost[cand])));
         if (v != 0.0) atomicAdd(dst, v);

@@ -1162,7 +1162,7 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         // tile capacity: the fused kernels run 2 CTAs per SM; when the whole rank fits in ONE wave of tiles of at most FT slots the
         // tiles are sized for exactly that (a second, nearly empty wave would double the kernel time: everything here is
         // latency-bound), otherwise full tiles
-        const int nsl_rank = gpu_struct ? nslots : slot_ptr[l1] - slot_ptr[l0], waves1 = h->num_sms * 2;
+        const int nsl_rank = gpu_struct ? nslots : slot_ptr[l1] - slot_ptr[l0], waves1 = h->num_sms * FUSED_CPS;
         int cap = FT;
         if (const char *e = getenv("SDV_FUSED_TILE_SLOTS")) cap = std::max(1, std::min(FT, atoi(e))); // tests: the result must not depend on the tiling
         else if (nsl_rank <= (long long)waves1 * (FT - max_slots)) cap = std::max(32, (nsl_rank + waves1 - 1) / waves1 + max_slots);
@@ -1688,8 +1688,8 @@ static int upload_impl(sdv_handle *h, const sdv_window *w, bool sync) {
         while (p2 < v) p2 <<= 1;
         return p2;
     };
-    h->fused_grid = std::max(1, std::min(pow2ceil(ntiles), h->num_sms * 2));
-    h->fused_grid_back = std::max(1, std::min(pow2ceil(ntiles), h->num_sms * 3));
+    h->fused_grid = std::max(1, std::min(pow2ceil(ntiles), h->num_sms * FUSED_CPS));
+    h->fused_grid_back = std::max(1, std::min(pow2ceil(ntiles), h->num_sms * FUSED_CPS_BACK));
     h->cost_grid = std::max(1, std::min(pow2ceil((Oloc + 255) / 256), h->num_sms * 4));
     h->p2l_grid = std::max(1, (np2l + 127) / 128);
     // dense Cholesky: one thread-block cluster when the reduced system is small enough, per-panel launches otherwise
@@ -2745,6 +2745,11 @@ int sdv_debug_read(sdv_handle *h, int32_t what, double *out, int64_t count) {
     case 3: src = h->d_scale_p; avail = h->P.n_pad; break;
     case 4: src = h->d_damp_p; avail = h->P.n_pad; break;
     case 5: src = h->d_prof; avail = 8 * CC_MAX; break;
+#ifdef SDV_SCHUR_PROF
+    case 6:
+        CK(cudaMemcpyFromSymbol(out, g_schur_prof, sizeof(double) * std::min<size_t>(32, (size_t)count)));
+        return SDV_OK;
+#endif
     default: return SDV_ERR_INVALID_ARGUMENT;
     }
     size_t nn = std::min<size_t>(avail, (size_t)count);

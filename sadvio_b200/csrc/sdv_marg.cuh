@@ -397,6 +397,208 @@ __global__ void __launch_bounds__(ET, 1) k_jacobi_pairs(double *G, double *V, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same Jacobi step with a THREAD-BLOCK CLUSTER per block pair (default; k_jacobi_pairs above remains the one-CTA fallback).
+// With ~20 pairs per step the one-CTA kernel keeps 20 of 148 SMs busy and walks all np rows twice per step (phase 1 and
+// phase 3: ~2/3 of its time).  Here CS CTAs share a pair: CTA r owns the rows [r rows_per_cta, (r + 1) rows_per_cta) of G and V,
+//   phase 1  forms its partial of the 32 x 32 block over its rows, the partials are summed through distributed shared memory
+//            IN RANK ORDER by every CTA, so all of them hold the bit-identical block and take identical decisions;
+//   phase 2  every CTA runs the same small Jacobi redundantly (nothing to exchange).  W <- J^T W J is ONE pass per step into a
+//            second buffer (every entry from its four sources), Q <- Q J in place: two CTA barriers per step instead of three;
+//   phase 3  panel <- panel Q on its own rows only, one thread per (matrix, half panel, row): 4 x 128 work items per pass.
+// No CTA touches another CTA's rows or another pair's columns: still one launch per step, no global synchronisation.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ET, 1) k_jacobi_pairs_cl(double *G, double *V, int np, int nb, int nbp, int step, unsigned long long *flags, int sweep, double tol,
+                                                           int inner_sweeps, const double *wmax, double floor_rel, int rows_per_cta) {
+    if (sweep > 0 && __longlong_as_double((long long)flags[sweep - 1]) <= tol) return; // converged in the previous sweep (uniform over the grid)
+    const int CS = (int)cluster_size(), rank = (int)cluster_rank();
+    int bi, bj;
+    round_robin(nbp, step, (int)blockIdx.x / CS, bi, bj);
+    if (bi >= nb || bj >= nb) return; // the bye of an odd block count (uniform over the cluster)
+    if (bi > bj) {
+        const int tmp = bi;
+        bi = bj;
+        bj = tmp;
+    }
+    __shared__ __align__(16) double W[EP][ELD], Q[EP][ELD], Tv[32][ELD], Tg[32][ELD];
+    __shared__ double ca[EP], cb[EP];
+    __shared__ int part[EP], pr[EB][2];
+    __shared__ double red[ET / 32];
+    const int t = threadIdx.x;
+    const int ci = EB * bi, cj = EB * bj;
+    const double tiny = floor_rel * sqrt(*wmax);
+    auto gcol = [&](int c) { return c < EB ? ci + c : cj + c - EB; };
+    const int r_lo = rank * rows_per_cta, r_hi = min(np, r_lo + rows_per_cta);
+    // ---- phase 1: partial block over this CTA's rows -> Tg
+    {
+        constexpr int RG = ET / 64;
+        const int rg = t % RG, blk = t / RG, hi = (blk >> 3) * 4, hj = (blk & 7) * 4;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+        for (int r0 = r_lo; r0 < r_hi; r0 += 32) {
+#pragma unroll
+            for (int q = 0; q < 1024 / ET; q++) {
+                const int e = t + ET * q, rr = e >> 5, cc = e & 31;
+                const bool in = r0 + rr < r_hi;
+                const size_t src = (size_t)(r0 + rr) * np + gcol(cc);
+                Tv[rr][cc] = in ? V[src] : 0.0;
+                Tg[rr][cc] = in ? G[src] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 32 / RG; k++) {
+                const int rr = RG * k + rg;
+                const double2 v01 = *reinterpret_cast<const double2 *>(&Tv[rr][hi]), v23 = *reinterpret_cast<const double2 *>(&Tv[rr][hi + 2]);
+                const double2 g01 = *reinterpret_cast<const double2 *>(&Tg[rr][hj]), g23 = *reinterpret_cast<const double2 *>(&Tg[rr][hj + 2]);
+                const double v4[4] = {v01.x, v01.y, v23.x, v23.y}, g4[4] = {g01.x, g01.y, g23.x, g23.y};
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][c] = fma(v4[a], g4[c], acc[a][c]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double v = acc[a][c];
+#pragma unroll
+                for (int o = 1; o < RG; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (rg == 0) Tg[hi + a][hj + c] = v;
+            }
+    }
+    cluster_sync_all(); // every partial is in its CTA's Tg (barrier.cluster: release / acquire, all threads of all CTAs)
+    for (int e = t; e < EP * EP; e += ET) {
+        const int i = e >> 5, j = e & 31;
+        double sum = 0.0;
+        for (int r = 0; r < CS; r++) sum += dsmem_load(&Tg[i][j], (unsigned)r); // rank order: the same sum in every CTA
+        W[i][j] = sum;
+    }
+    cluster_sync_all(); // nobody reads this CTA's Tg any more (it may exit or reuse it)
+    // H is symmetric up to rounding: symmetrise, Q = I, and measure how far from diagonal this block is
+    double off = 0.0;
+    for (int e = t; e < EP * EP; e += ET) {
+        const int i = e >> 5, j = e & 31;
+        Q[i][j] = i == j ? 1.0 : 0.0;
+        if (i < j) {
+            const double h = 0.5 * (W[i][j] + W[j][i]);
+            W[i][j] = h;
+            W[j][i] = h;
+            if (fabs(h) > tiny) {
+                const double d = fabs(W[i][i] * W[j][j]);
+                off = fmax(off, d > 0.0 ? fabs(h) * rsqrt(d) : 1.0);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) off = fmax(off, __shfl_xor_sync(0xffffffffu, off, o));
+    if ((t & 31) == 0) red[t >> 5] = off;
+    __syncthreads();
+    off = red[0];
+#pragma unroll
+    for (int q = 1; q < ET / 32; q++) off = fmax(off, red[q]);
+    if (t == 0 && rank == 0 && off > 0.0) atomicMax(&flags[sweep], (unsigned long long)__double_as_longlong(off));
+    if (off <= tol) return; // nothing to rotate (uniform over the cluster: identical W)
+    // ---- phase 2: W <- Q^T W Q, redundantly in every CTA of the cluster
+    double(*cur)[ELD] = W, (*nxt)[ELD] = Tv;
+    for (int isw = 0; isw < inner_sweeps; isw++) {
+        for (int st = 0; st < EP - 1; st++) {
+            if (t < EB) {
+                int p, q;
+                round_robin(EP, st, t, p, q);
+                if (p > q) {
+                    const int tmp = p;
+                    p = q;
+                    q = tmp;
+                }
+                const double app = cur[p][p], aqq = cur[q][q], apq = cur[p][q];
+                double c = 1.0, s = 0.0;
+                if (fabs(apq) > tiny && apq * apq > 1e-34 * fabs(app * aqq)) { // (angle from the approximate units, exact c for the t used: see k_jacobi_pairs)
+                    const double d = aqq - app, h2 = fma(d, d, 4.0 * apq * apq);
+                    double rs, ri;
+                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(h2));
+                    const double den = fabs(d) + h2 * rs;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ri) : "d"(den));
+                    const double tt = (d >= 0.0 ? 2.0 : -2.0) * apq * ri;
+                    if (isfinite(tt)) {
+                        c = band_rsqrt(fma(tt, tt, 1.0));
+                        s = tt * c;
+                    }
+                }
+                pr[t][0] = p;
+                pr[t][1] = q;
+                part[p] = q;
+                part[q] = p;
+                ca[p] = c;   // x_p' = c x_p - s x_q
+                cb[p] = -s;
+                ca[q] = c;   // x_q' = s x_p + c x_q
+                cb[q] = s;
+            }
+            __syncthreads();
+            for (int e = t; e < EP * EP; e += ET) { // (J^T W J)[i][j] from its four sources
+                const int i = e >> 5, j = e & 31, pi = part[i], pj = part[j];
+                const double aj = ca[j], bj2 = cb[j];
+                const double u = fma(aj, cur[i][j], bj2 * cur[i][pj]), v = fma(aj, cur[pi][j], bj2 * cur[pi][pj]);
+                nxt[i][j] = fma(ca[i], u, cb[i] * v);
+            }
+            for (int e = t; e < EB * EP; e += ET) { // columns p, q of Q, in place (one thread owns both entries of a row)
+                const int k = e >> 5, i = e & 31;
+                const int p = pr[k][0], q = pr[k][1];
+                const double c = ca[p], s = cb[q];
+                const double xp = Q[i][p], xq = Q[i][q];
+                Q[i][p] = c * xp - s * xq;
+                Q[i][q] = s * xp + c * xq;
+            }
+            __syncthreads();
+            double(*tmpb)[ELD] = cur;
+            cur = nxt;
+            nxt = tmpb;
+        }
+    }
+    // ---- phase 3: panel <- panel Q for G and V on this CTA's rows; thread = (matrix, half panel, row), 128 rows per pass
+    {
+        const int wh = t >> 7, which = wh >> 1, half = wh & 1;
+        double *X = which ? V : G;
+        for (int cbase = r_lo; cbase < r_hi; cbase += 128) {
+            const int r = cbase + (t & 127);
+            const bool valid = r < r_hi;
+            double a[EP];
+            double *rowi = X + (size_t)r * np + ci, *rowj = X + (size_t)r * np + cj;
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < EB; c += 2) {
+                    const double2 x = *reinterpret_cast<const double2 *>(rowi + c), y = *reinterpret_cast<const double2 *>(rowj + c);
+                    a[c] = x.x;
+                    a[c + 1] = x.y;
+                    a[EB + c] = y.x;
+                    a[EB + c + 1] = y.y;
+                }
+            }
+            __syncthreads(); // both halves of a row have been read before either is overwritten
+            if (valid) {
+                double *dst = half ? rowj : rowi;
+#pragma unroll 1
+                for (int j = 0; j < EB; j += 2) { // (rolled: see k_jacobi_pairs)
+                    double o0a = 0.0, o0b = 0.0, o1a = 0.0, o1b = 0.0;
+#pragma unroll
+                    for (int i = 0; i < EP; i += 2) {
+                        const double2 qa = *reinterpret_cast<const double2 *>(&Q[i][EB * half + j]); // same address in every lane of the warp: broadcast
+                        const double2 qb = *reinterpret_cast<const double2 *>(&Q[i + 1][EB * half + j]);
+                        o0a = fma(a[i], qa.x, o0a);
+                        o1a = fma(a[i], qa.y, o1a);
+                        o0b = fma(a[i + 1], qb.x, o0b);
+                        o1b = fma(a[i + 1], qb.y, o1b);
+                    }
+                    *reinterpret_cast<double2 *>(dst + j) = make_double2(o0a + o0b, o1a + o1b);
+                }
+            }
+        }
+    }
+}
+
 // largest squared column norm of the (symmetric) input matrix
 __global__ void k_max_colnorm2(const double *G, int np, double *out) {
     __shared__ double red[8];

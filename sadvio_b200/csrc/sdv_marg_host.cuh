@@ -42,8 +42,41 @@ int eig_sym(sdv_handle *h, double *G, double *V, int np, double *w, unsigned lon
     const double tol = 2.220446049250313e-16 * np; // |h_pq| / sqrt(h_pp h_qq): the rounding floor of an np-term dot product
     unsigned long long *hflags = reinterpret_cast<unsigned long long *>(h->h_rb); // (pinned, >= 256 bytes + LMState)
     int sweep = 0;
+    // cluster size of k_jacobi_pairs_cl: the largest one (<= 8) that keeps every block pair of a step resident at once; rows split in
+    // multiples of the 32-row tiles.  SDV_EIG_CLUSTER=1 (or a matrix of one or two tiles) selects the one-CTA kernel.
+    static const int cs_max = getenv("SDV_EIG_CLUSTER") ? std::max(1, std::min(8, atoi(getenv("SDV_EIG_CLUSTER")))) : 8;
+    int cs = 1, rows_per_cta = np;
+    cudaLaunchConfig_t lc = {};
+    cudaLaunchAttribute lat[1];
+    if (np > 64) {
+        for (int c = cs_max; c >= 2; c--) {
+            lc.gridDim = dim3(pairs * c);
+            lc.blockDim = dim3(ET);
+            lc.dynamicSmemBytes = 0;
+            lc.stream = s;
+            lat[0].id = cudaLaunchAttributeClusterDimension;
+            lat[0].val.clusterDim.x = c;
+            lat[0].val.clusterDim.y = 1;
+            lat[0].val.clusterDim.z = 1;
+            lc.attrs = lat;
+            lc.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k_jacobi_pairs_cl, &lc) == cudaSuccess && ncl >= pairs) {
+                cs = c;
+                break;
+            }
+            cudaGetLastError();
+        }
+        if (cs > 1) rows_per_cta = ((np + cs - 1) / cs + 31) / 32 * 32;
+    }
     for (; sweep < EIG_MAX_SWEEPS; sweep++) {
-        for (int st = 0; st < steps; st++) k_jacobi_pairs<<<pairs, ET, 0, s>>>(G, V, np, nb, nbp, st, flags, sweep, tol, inner, wmax, negl);
+        for (int st = 0; st < steps; st++) {
+            if (cs > 1) {
+                cudaError_t e = cudaLaunchKernelEx(&lc, k_jacobi_pairs_cl, G, V, np, nb, nbp, st, flags, sweep, tol, inner, (const double *)wmax, negl, rows_per_cta);
+                if (e != cudaSuccess) return fail(h, SDV_ERR_CUDA, std::string("k_jacobi_pairs_cl launch: ") + cudaGetErrorString(e));
+            } else
+                k_jacobi_pairs<<<pairs, ET, 0, s>>>(G, V, np, nb, nbp, st, flags, sweep, tol, inner, wmax, negl);
+        }
         h->launches += steps;
         if (sweep >= 3) { // look at the convergence flag (one small D2H per sweep from here on)
             CK(cudaMemcpyAsync(hflags, flags + sweep, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

@@ -24,6 +24,9 @@ for name in (sys.argv[1:] or ["tiny", "small", "C2", "C3"]):
     print("  warp 0 [setup wait chain bwd_wait tail backward] kcycles:", " ".join(f"{x/1e3:8.1f}" for x in prof[0:6]))
     print("  chain warp waits [step rhs copy (1,1) (2,1)] kcycles:", " ".join(f"{prof[(q >> 1) * 8 + 6 + (q & 1)]/1e3:7.1f}" for q in range(5)))
     print(f"  hand-over: CTA 0 waited {prof[23]/1e3:.1f} kcycles for CTA 1, separator transfer {prof[31]/1e3:.1f} kcycles")
+    print("  backward solve, warp 0 [stage wait, compute, publish, refill] kcycles:", " ".join(f"{prof[(4 + (q >> 1)) * 8 + 6 + (q & 1)]/1e3:7.1f}" for q in range(4)))
+    print("  backward solve, CTA 1 warp 0 [stage wait, compute, publish, refill] kcycles:", " ".join(f"{prof[(6 + (q >> 1)) * 8 + 6 + (q & 1)]/1e3:7.1f}" for q in range(4)),
+          f" waited {prof[70]/1e3:.1f} for the separator unknowns; CTA 0 waited {prof[71]/1e3:.1f} for CTA 1 at the end")
     pw = prof.reshape(16, 8)
     print("  per warp wait kcycles:", " ".join(f"{x/1e3:6.1f}" for x in pw[:, 1]))
     print("  per warp work kcycles:", " ".join(f"{x/1e3:6.1f}" for x in pw[:, 2]))

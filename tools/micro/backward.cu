@@ -100,14 +100,16 @@ template <int MODE, int BW> __global__ void __launch_bounds__(512, 1) k_backward
     const uint32_t stage_bytes = (uint32_t)stage_doubles * 8u;
     double *gs = sm, *rvs = gs + nb * BN, *ring = rvs + 32; // ring is 128-byte aligned: nb * 16 + 32 doubles
     for (int e = threadIdx.x; e < nb * BN; e += blockDim.x) gs[e] = y[e];
-    if (MODE == 2)
+    constexpr bool RES = MODE == 2 || MODE == 4 || MODE == 5; // factor resident in shared memory
+    constexpr bool PIPE = MODE == 3 || MODE == 4;             // the kernel's software-pipelined full steps (band_backward_pipe_step)
+    if (RES)
         for (int e = threadIdx.x; e < nb * stage_doubles; e += blockDim.x) ring[e] = Lb[e];
     if (threadIdx.x == 0)
         for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
     __syncthreads();
     if (warp != 0) return; // the other warps of the shipped kernel wait at a __syncthreads() during the backward solve
     const long long t0 = rdclk();
-    if (MODE != 2 && lane == 0)
+    if (!RES && lane == 0)
         for (int s = 0; s < NS && s < nb; s++) {
             const int k = nb - 1 - s;
             mbar_expect_tx(&full[s], stage_bytes);
@@ -116,23 +118,43 @@ template <int MODE, int BW> __global__ void __launch_bounds__(512, 1) k_backward
     const int c = lane & 15, hh = lane >> 4;
     int s = 0, ph = 0;
     long long t_first = 0;
+    bool have_qp = false;
+    double qp = 0.0;
     for (int it = 0; it < nb; it++) {
         const int k = nb - 1 - it;
         const int nd = BW < nb - 1 - k ? BW : nb - 1 - k;
-        const double *sb;
-        if (MODE == 2) sb = ring + (size_t)k * stage_doubles;
-        else {
+        const double *sb, *sbn = nullptr;
+        if (RES) {
+            sb = ring + (size_t)k * stage_doubles;
+            sbn = sb - stage_doubles;
+        } else {
             mbar_wait(&full[s], (unsigned)ph);
             sb = ring + s * stage_doubles;
         }
         if (it == 0) t_first = rdclk();
-        const double x = MODE == 0 ? step_generic(sb, gs, rvs, k, nd, BW, lane) : step_any<BW>(sb, gs, rvs, k, nd, lane, nd == BW);
+        double x;
+        if (MODE == 5) { // only what depends on x_(k+1): the floor of the dependence chain (result not checked)
+            double q0 = 0.0;
+            x = nd == BW ? band_backward_pipe_step<BW, false>(sb, sbn, gs, rvs, k, lane, q0) : step_generic(sb, gs, rvs, k, nd, BW, lane);
+        } else if (PIPE && nd == BW) {
+            const bool next = it + 1 < nb;
+            const int sn = s + 1 == NS ? 0 : s + 1;
+            if (!RES) sbn = ring + sn * stage_doubles;
+            if (!have_qp) qp = band_backward_partial<BW>(sb, gs, k, lane);
+            if (next) {
+                if (!RES) mbar_wait(&full[sn], (unsigned)(sn == 0 ? ph ^ 1 : ph));
+                x = band_backward_pipe_step<BW, true>(sb, sbn, gs, rvs, k, lane, qp);
+            } else
+                x = band_backward_pipe_step<BW, false>(sb, sbn, gs, rvs, k, lane, qp);
+            have_qp = next;
+        } else
+            x = MODE == 0 ? step_generic(sb, gs, rvs, k, nd, BW, lane) : step_any<BW>(sb, gs, rvs, k, nd, lane, nd == BW);
         if (hh == 0) {
             gs[k * BN + c] = x;
             xout[k * BN + c] = -x;
         }
         __syncwarp();
-        if (MODE != 2) {
+        if (!RES) {
             if (lane == 0 && it + NS < nb) {
                 const int k2 = nb - 1 - (it + NS);
                 mbar_expect_tx(&full[s], stage_bytes);
@@ -153,7 +175,7 @@ template <int MODE, int BW> __global__ void __launch_bounds__(512, 1) k_backward
 
 template <int MODE, int BW> static void run(const char *name, const double *dLb, const double *dy, double *dx, long long *dres, int nb, const std::vector<double> &xref) {
     const int stage_doubles = (BW + 2) * 256;
-    const size_t smem = (size_t)(nb * BN + 32 + (MODE == 2 ? nb : NS) * stage_doubles) * 8;
+    const size_t smem = (size_t)(nb * BN + 32 + ((MODE == 2 || MODE == 4 || MODE == 5) ? nb : NS) * stage_doubles) * 8;
     if (smem > 227 * 1024) {
         printf("%-44s skipped (needs %zu KB of shared memory)\n", name, smem / 1024);
         return;
@@ -225,10 +247,16 @@ int main(int argc, char **argv) {
         run<0, 3>("V0 shipped loop, TMA ring", dLb, dy, dx, dres, nb, xref);
         run<1, 3>("V1 full steps specialised (d = 1 last), TMA ring", dLb, dy, dx, dres, nb, xref);
         run<2, 3>("V2 specialised, factor resident in smem", dLb, dy, dx, dres, nb, xref);
+        run<3, 3>("V3 software-pipelined full steps, TMA ring", dLb, dy, dx, dres, nb, xref);
+        run<4, 3>("V4 software-pipelined, factor resident", dLb, dy, dx, dres, nb, xref);
+        run<5, 3>("V5 d = 1 block + inverse only, resident (floor)", dLb, dy, dx, dres, nb, xref);
     } else {
         run<0, 4>("V0 shipped loop, TMA ring", dLb, dy, dx, dres, nb, xref);
         run<1, 4>("V1 full steps specialised (d = 1 last), TMA ring", dLb, dy, dx, dres, nb, xref);
         run<2, 4>("V2 specialised, factor resident in smem", dLb, dy, dx, dres, nb, xref);
+        run<3, 4>("V3 software-pipelined full steps, TMA ring", dLb, dy, dx, dres, nb, xref);
+        run<4, 4>("V4 software-pipelined, factor resident", dLb, dy, dx, dres, nb, xref);
+        run<5, 4>("V5 d = 1 block + inverse only, resident (floor)", dLb, dy, dx, dres, nb, xref);
     }
     return 0;
 }
