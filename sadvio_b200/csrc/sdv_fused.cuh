@@ -454,10 +454,16 @@ __global__ void __launch_bounds__(FT, FUSED_CPS) k_lin_schur(const DevProblem *_
 // landmark back-substitution delta_l = -V^-1 (g_l + sum_f W_f^T delta_f) with W_f^T delta_f = sum_obs Jl^T (Jp delta_f) recomputed,
 // candidate landmark parameters, model-decrease / norm partial sums, and the cost of the visual factors at the candidate point
 template <int KIND>
+// Side job (Sz / nz): the reduced system S of this iteration has been consumed by the factorisation that ran before this kernel and
+// the next iteration accumulates into it from zero — the grid clears it here (a few 16-byte stores per thread) instead of a
+// memset node of its own at the head of every iteration.
 __global__ void __launch_bounds__(FT, FUSED_CPS_BACK) k_backsub_cost(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, const LMState *st, Accum *acc, const double *dxp,
-                                                        const double *lmk_aux) {
+                                                        const double *lmk_aux, double *Sz = nullptr, long long nz = 0) {
     const DevProblem &P = *Pg; // device-resident problem description: the launch parameters do not depend on the window (one CUDA graph serves them all)
-    if (st->status != 0 || !st->step_valid) return;
+    if (st->status != 0) return;
+    for (long long i = 2 * ((long long)blockIdx.x * FT + threadIdx.x); i < nz; i += 2 * (long long)gridDim.x * FT)
+        *reinterpret_cast<double2 *>(Sz + i) = make_double2(0.0, 0.0);
+    if (!st->step_valid) return;
     const int cand = 1 - st->cur;
     const LinBuf &Bx = st->cur ? B1 : B0;
     const LinBuf &Bc = st->cur ? B0 : B1;

@@ -1465,8 +1465,11 @@ SDV_DEV void ctrl_step(LMState *st, Accum *acc, const SolverOpts &opt, int max_i
 
 // start of a solve: x = 0 in both linearisation buffers, solver state and accumulators cleared (one launch instead of six
 // memset nodes whose sizes would tie the CUDA graph to the window)
-__global__ void k_reset(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc) {
+// (Sz / nz: the reduced-system buffer, zeroed here for the first iteration; k_backsub_cost zeroes it for the following ones)
+__global__ void k_reset(const DevProblem *__restrict__ Pg, LinBuf B0, LinBuf B1, LMState *st, Accum *acc, double *Sz = nullptr, long long nz = 0) {
     const DevProblem &P = *Pg;
+    for (long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i < nz; i += 2 * (long long)gridDim.x * blockDim.x)
+        *reinterpret_cast<double2 *>(Sz + i) = make_double2(0.0, 0.0);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (int i = tid; i < P.n_pad; i += nt) {
         B0.xp[i] = 0.0;

@@ -227,6 +227,17 @@ struct sdv_handle {
     int cap_O = 0, cap_L = 0, cap_P = 0, cap_nm = 0, cap_nfull = 0, cap_l2l = 0; // scratch-layout capacities (only grow)
     int cost_grid = 0, p2l_grid = 0;
     int64_t graph_launches_fixed = 0, graph_launches_iter = 0, graph_builds = 0;
+    // k LM iterations per trip of the WHILE node (a trip costs ~6 us on B200; every kernel returns at once after termination, so a
+    // trip that is cut short only launches a few empty kernels): k = the largest divisor <= 4 of the PREVIOUS solve's iteration count —
+    // consecutive windows of a running back end take the same number of iterations.  One instantiated graph per k in use is kept.
+    int graph_unroll = 1;
+    struct GraphSlot {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t gexec = nullptr;
+        unsigned long long cond = 0;
+        GraphSig sig;
+        int64_t l_fixed = 0, l_iter = 0;
+    } gcache[5];
     unsigned char *h_sol = nullptr;
     size_t sol_cap = 0;
     // comm
@@ -384,8 +395,7 @@ int sdv_destroy(sdv_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
-    if (h->gexec) cudaGraphExecDestroy(h->gexec);
-    if (h->graph) cudaGraphDestroy(h->graph);
+    destroy_graph(h);
     if (h->sgraph_exec) cudaGraphExecDestroy(h->sgraph_exec);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->side) cudaStreamDestroy(h->side);
@@ -1819,12 +1829,18 @@ void launch_schur(sdv_handle *h) { // fused visual linearisation + landmark Schu
     else k_lin_schur<1><<<h->fused_grid, FT, FT_SMEM_SCHUR, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc, h->opt, h->d_Sb, h->d_scale_l, h->d_lmk_aux);
     h->launches++;
 }
-void launch_backsub(sdv_handle *h) { // landmark back-substitution and the candidate cost of the visual factors in one kernel
+// the iteration's back-substitution kernel can also clear the reduced system for the next iteration (no memset node per iteration)
+// (EXPERIMENT, SDV_FOLD_S_CLEAR=1: measured SLOWER than the memset node — 0.514 against 0.499 ms per C3 solve, median of 200 —, off)
+bool backsub_clears_S(const sdv_handle *h) { return h->P.ntiles > 0 && getenv("SDV_FOLD_S_CLEAR"); }
+
+void launch_backsub(sdv_handle *h, bool clear_S = false) { // landmark back-substitution and the candidate cost of the visual factors in one kernel
     const DevProblem &P = h->P;
     if (P.ntiles <= 0) return;
     cudaStream_t s = h->stream;
-    if (P.kind == SDV_FACTOR_ANGULAR) k_backsub_cost<0><<<h->fused_grid_back, FT, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_dxp, h->d_lmk_aux);
-    else k_backsub_cost<1><<<h->fused_grid_back, FT, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_dxp, h->d_lmk_aux);
+    double *Sz = clear_S ? h->d_Sb : nullptr;
+    const long long nz = clear_S ? (long long)h->sb_elems : 0;
+    if (P.kind == SDV_FACTOR_ANGULAR) k_backsub_cost<0><<<h->fused_grid_back, FT, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_dxp, h->d_lmk_aux, Sz, nz);
+    else k_backsub_cost<1><<<h->fused_grid_back, FT, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc, h->d_dxp, h->d_lmk_aux, Sz, nz);
     h->launches++;
 }
 
@@ -2034,7 +2050,8 @@ int launch_factor_solve(sdv_handle *h) {
 int launch_iteration(sdv_handle *h) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
-    if (cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s) != cudaSuccess) return fail(h, SDV_ERR_CUDA, "memset S");
+    // S starts from zero: cleared by k_reset (first iteration) / by the previous iteration's k_backsub_cost, else by a memset node
+    if (!backsub_clears_S(h) && cudaMemsetAsync(h->d_Sb, 0, h->sb_elems * sizeof(double), s) != cudaSuccess) return fail(h, SDV_ERR_CUDA, "memset S");
     {
         // the non-visual factors accumulate into S with atomics as well: run them beside the landmark Schur kernel
         const bool fa = P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0);
@@ -2086,7 +2103,7 @@ int launch_iteration(sdv_handle *h) {
         // candidate linearisation: the factor kernel only needs the reduced parameters -> beside back-substitution + visual kernel
         const bool forked = has_factors(P) && fork_side(h, 1);
         launch_lin_factors(h, -2, forked ? h->side : s);
-        launch_backsub(h);
+        launch_backsub(h, backsub_clears_S(h));
         launch_lin_visual(h, -2, false); // only the PoseToLandmark pseudo-observations are linearised here (the visual cost comes out of k_backsub_cost)
         if (forked) join_side(h, 1);
     }
@@ -2104,7 +2121,8 @@ namespace {
 int enqueue_prologue(sdv_handle *h) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
-    k_reset<<<64, 256, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc); // x = 0, solver state and accumulators cleared
+    // x = 0, solver state and accumulators cleared (and the reduced system, when the iterations do not clear it with a memset node)
+    k_reset<<<64, 256, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, h->d_acc, backsub_clears_S(h) ? h->d_Sb : nullptr, backsub_clears_S(h) ? (long long)h->sb_elems : 0);
     k_prep_table<<<(P.F * P.C + 127) / 128, 128, 0, s>>>(h->d_P, h->B[0], h->B[1], h->d_st, 0);
     h->launches += 2;
     launch_linearize(h, 0, false);
@@ -2138,13 +2156,29 @@ int enqueue_readback(sdv_handle *h) {
     return SDV_OK;
 }
 
-void destroy_graph(sdv_handle *h) {
+void destroy_active_graph(sdv_handle *h) {
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->graph) cudaGraphDestroy(h->graph);
     h->gexec = nullptr;
     h->graph = nullptr;
     h->graph_ok = false;
     h->cond = 0;
+}
+void destroy_graph(sdv_handle *h) { // the active graph and every cached one
+    destroy_active_graph(h);
+    for (auto &c : h->gcache) {
+        if (c.gexec) cudaGraphExecDestroy(c.gexec);
+        if (c.graph) cudaGraphDestroy(c.graph);
+        c = sdv_handle::GraphSlot();
+    }
+}
+int desired_unroll(const sdv_handle *h) {
+    static const int forced = getenv("SDV_GRAPH_UNROLL") ? std::max(1, std::min(4, atoi(getenv("SDV_GRAPH_UNROLL")))) : 0;
+    if (forced) return forced;
+    const int it = std::max(1, h->last_iters);
+    for (int k = 4; k > 1; k--)
+        if (it % k == 0) return k;
+    return 1;
 }
 
 // prologue -> WHILE (status == 0) { one LM iteration } -> epilogue, as ONE graph launch per solve.
@@ -2169,8 +2203,26 @@ int build_solve_graph(sdv_handle *h) {
         sig.flags = (P.ntiles > 0 ? 1 : 0) | (P.o1 > P.o0 ? 2 : 0) | (has_factors(P) ? 4 : 0) | (P.sp_np2l > 0 ? 8 : 0) |
                     ((P.rank == 0 && (P.P > 0 || P.has_prior || P.mp_nfull > 0)) ? 16 : 0) | ((P.rank == 0 && (P.sp_has_imu || P.sp_has_lmk || P.sp_nl2l > 0)) ? 32 : 0);
     }
-    if (h->graph_ok && std::memcmp(&h->graph_sig, &sig, sizeof(sig)) == 0) return SDV_OK; // same launches, same arguments: replay
-    destroy_graph(h);
+    const int unroll = desired_unroll(h);
+    if (h->graph_ok && h->graph_unroll == unroll && std::memcmp(&h->graph_sig, &sig, sizeof(sig)) == 0) return SDV_OK; // same launches, same arguments: replay
+    if (h->graph_ok) { // park the active graph under its unroll factor ...
+        sdv_handle::GraphSlot &c = h->gcache[h->graph_unroll];
+        if (c.gexec) cudaGraphExecDestroy(c.gexec);
+        if (c.graph) cudaGraphDestroy(c.graph);
+        c.graph = h->graph; c.gexec = h->gexec; c.cond = h->cond; c.sig = h->graph_sig; c.l_fixed = h->graph_launches_fixed; c.l_iter = h->graph_launches_iter;
+        h->graph = nullptr; h->gexec = nullptr; h->graph_ok = false; h->cond = 0;
+    }
+    {   // ... and look for a parked one that fits
+        sdv_handle::GraphSlot &c = h->gcache[unroll];
+        if (c.gexec && std::memcmp(&c.sig, &sig, sizeof(sig)) == 0) {
+            h->graph = c.graph; h->gexec = c.gexec; h->cond = c.cond; h->graph_sig = c.sig; h->graph_launches_fixed = c.l_fixed; h->graph_launches_iter = c.l_iter;
+            h->graph_unroll = unroll;
+            h->graph_ok = true;
+            c = sdv_handle::GraphSlot();
+            return SDV_OK;
+        }
+    }
+    destroy_active_graph(h);
     if (!h->stream2 && cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) return SDV_OK;
     cudaStream_t s = h->stream;
     int64_t l0 = h->launches;
@@ -2208,10 +2260,11 @@ int build_solve_graph(sdv_handle *h) {
             h->stream = h->stream2;
             int64_t l1 = h->launches;
             if (cudaStreamBeginCaptureToGraph(h->stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) ok = false;
-            if (ok && launch_iteration(h) != SDV_OK) ok = false;
+            for (int u = 0; ok && u < unroll; u++) // `unroll` LM iterations per trip of the WHILE node (see sdv_handle::graph_unroll)
+                if (launch_iteration(h) != SDV_OK) ok = false;
             cudaGraph_t tmp = nullptr;
             if (cudaStreamEndCapture(h->stream2, &tmp) != cudaSuccess) ok = false;
-            l_iter = h->launches - l1;
+            l_iter = (h->launches - l1) / unroll;
             h->stream = keep;
         }
         if (ok && cudaStreamUpdateCaptureDependencies(s, &cnode, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) ok = false;
@@ -2234,6 +2287,7 @@ int build_solve_graph(sdv_handle *h) {
     }
     h->graph = g;
     h->graph_ok = true;
+    h->graph_unroll = unroll;
     h->graph_builds++;
     h->graph_sig = sig;
     h->graph_launches_fixed = l_fixed;
