@@ -367,8 +367,7 @@ def main():
             c5 = {"error": str(e)}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _teardown(solver, dist if world > 1 else None)
         return
 
     # ---------------- per-kernel timing (CUDA events on the library's stream) and roofline of the dominant kernel
@@ -504,8 +503,28 @@ def main():
         "solution": solution, "around_the_solve": extras,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _teardown(solver, dist if world > 1 else None)
+
+
+def _teardown(solver, dist):
+    """Release the library handle (its NCCL communicator and peer-memory mappings) BEFORE the process group and the interpreter go
+    away: a handle destroyed by the interpreter's shutdown, after torch has torn its own NCCL / CUDA state down, was seen to stall
+    a 2-rank run for minutes.  A watchdog ends a rank whose teardown still stalls — rank 0's JSON line is out by then."""
+    import threading
+
+    wd = threading.Timer(45.0, lambda: os._exit(0))
+    wd.daemon = True
+    wd.start()
+    try:
+        solver.close()
+    except Exception:  # noqa: BLE001
+        pass
+    if dist is not None:
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+    wd.cancel()
 
 
 if __name__ == "__main__":

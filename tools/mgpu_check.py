@@ -40,7 +40,14 @@ def main():
                   f"pose {rel(d.dpose, d0.dpose):.2e} v {rel(d.dv, d0.dv) if win.vio else 0:.2e} lmk {rel(d.dlmk, d0.dlmk):.2e} "
                   f"solve {dt*1e3:.3f} ms ({st['iterations']/dt:.0f} it/s) cuda graph builds {s.graph_builds()}", flush=True)
             assert st["iterations"] == st0["iterations"] and rel(d.dpose, d0.dpose) < 1e-6 and rel(d.dlmk, d0.dlmk) < 1e-5
+    import faulthandler
+    faulthandler.dump_traceback_later(20, exit=True)     # (a hang in the teardown shows where)
+    t0 = time.perf_counter()
+    s.close()
+    print(f"rank {rank}: solver closed after {time.perf_counter() - t0:.2f} s", flush=True)
     dist.destroy_process_group()
+    print(f"rank {rank}: process group destroyed after {time.perf_counter() - t0:.2f} s", flush=True)
+    faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":
