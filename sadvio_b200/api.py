@@ -14,8 +14,10 @@ the window state in place exactly as AOptimizer.cpp:122-146, :199-216, :262-296,
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -76,11 +78,27 @@ def default_config() -> abi.SdvConfig:
     return cfg
 
 
+_live_solvers: "weakref.WeakSet[Solver]" = weakref.WeakSet()
+
+
+def _close_all_solvers():
+    # at interpreter exit, BEFORE torch / NCCL tear their own state down (atexit runs last-registered first): a handle with a
+    # communicator that is destroyed later, from __del__ during shutdown, was seen to stall multi-rank runs for minutes
+    for s in list(_live_solvers):
+        try:
+            s.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class Solver:
     """Thin RAII wrapper around ``sdv_handle``."""
 
     def __init__(self, cfg: abi.SdvConfig | None = None, device: int = 0):
         L = lib()
+        if not _live_solvers:
+            atexit.unregister(_close_all_solvers)
+            atexit.register(_close_all_solvers)
         self.cfg = cfg or default_config()
         self.cfg.device = device
         self._h = C.c_void_p()
@@ -89,6 +107,7 @@ class Solver:
             self._h = None
             raise BackendUnavailable(f"sdv_create failed: {L.sdv_strerror(rc).decode()}")
         self._win = None
+        _live_solvers.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
