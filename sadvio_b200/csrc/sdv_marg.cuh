@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(ET, 1) k_jacobi_pairs(double *G, double *V, in
 // phase 3: ~2/3 of its time).  Here CS CTAs share a pair: CTA r owns the rows [r rows_per_cta, (r + 1) rows_per_cta) of G and V,
 //   phase 1  forms its partial of the 32 x 32 block over its rows, the partials are summed through distributed shared memory
 //            IN RANK ORDER by every CTA, so all of them hold the bit-identical block and take identical decisions;
-//   phase 2  every CTA runs the same small Jacobi redundantly (nothing to exchange).  W <- J^T W J is ONE pass per step into a
-//            second buffer (every entry from its four sources), Q <- Q J in place: two CTA barriers per step instead of three;
+//   phase 2  every CTA runs the same small Jacobi redundantly (nothing to exchange).  W <- J^T W J is ONE in-place pass per step (one
+//            thread per 2 x 2 group of a row pair and a column pair), Q <- Q J beside it: two CTA barriers per step instead of three;
 //   phase 3  panel <- panel Q on its own rows only, one thread per (matrix, half panel, row): 4 x 128 work items per pass.
 // No CTA touches another CTA's rows or another pair's columns: still one launch per step, no global synchronisation.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -421,8 +421,8 @@ __global__ void __launch_bounds__(ET, 1) k_jacobi_pairs_cl(double *G, double *V,
         bj = tmp;
     }
     __shared__ __align__(16) double W[EP][ELD], Q[EP][ELD], Tv[32][ELD], Tg[32][ELD];
-    __shared__ double ca[EP], cb[EP];
-    __shared__ int part[EP], pr[EB][2];
+    __shared__ double ca[EB], cb[EB]; // cos / sin of the 16 rotations of a step
+    __shared__ int pr[EB][2];
     __shared__ double red[ET / 32];
     const int t = threadIdx.x;
     const int ci = EB * bi, cj = EB * bj;
@@ -502,8 +502,9 @@ __global__ void __launch_bounds__(ET, 1) k_jacobi_pairs_cl(double *G, double *V,
     for (int q = 1; q < ET / 32; q++) off = fmax(off, red[q]);
     if (t == 0 && rank == 0 && off > 0.0) atomicMax(&flags[sweep], (unsigned long long)__double_as_longlong(off));
     if (off <= tol) return; // nothing to rotate (uniform over the cluster: identical W)
-    // ---- phase 2: W <- Q^T W Q, redundantly in every CTA of the cluster
-    double(*cur)[ELD] = W, (*nxt)[ELD] = Tv;
+    // ---- phase 2: W <- Q^T W Q, redundantly in every CTA of the cluster.  The phase is bound by shared-memory traffic, so a rotation
+    // step touches every entry once: thread (k, m) < 256 owns the 2 x 2 group {p_k, q_k} x {p_m, q_m} of W (both rotations applied to
+    // it in registers, in place: 4 loads + 4 stores for 4 entries), threads >= 256 rotate the columns of Q.
     for (int isw = 0; isw < inner_sweeps; isw++) {
         for (int st = 0; st < EP - 1; st++) {
             if (t < EB) {
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(ET, 1) k_jacobi_pairs_cl(double *G, double *V,
                     p = q;
                     q = tmp;
                 }
-                const double app = cur[p][p], aqq = cur[q][q], apq = cur[p][q];
+                const double app = W[p][p], aqq = W[q][q], apq = W[p][q];
                 double c = 1.0, s = 0.0;
                 if (fabs(apq) > tiny && apq * apq > 1e-34 * fabs(app * aqq)) { // (angle from the approximate units, exact c for the t used: see k_jacobi_pairs)
                     const double d = aqq - app, h2 = fma(d, d, 4.0 * apq * apq);
@@ -530,32 +531,31 @@ __global__ void __launch_bounds__(ET, 1) k_jacobi_pairs_cl(double *G, double *V,
                 }
                 pr[t][0] = p;
                 pr[t][1] = q;
-                part[p] = q;
-                part[q] = p;
-                ca[p] = c;   // x_p' = c x_p - s x_q
-                cb[p] = -s;
-                ca[q] = c;   // x_q' = s x_p + c x_q
-                cb[q] = s;
+                ca[t] = c; // x_p' = c x_p - s x_q,  x_q' = s x_p + c x_q
+                cb[t] = s;
             }
             __syncthreads();
-            for (int e = t; e < EP * EP; e += ET) { // (J^T W J)[i][j] from its four sources
-                const int i = e >> 5, j = e & 31, pi = part[i], pj = part[j];
-                const double aj = ca[j], bj2 = cb[j];
-                const double u = fma(aj, cur[i][j], bj2 * cur[i][pj]), v = fma(aj, cur[pi][j], bj2 * cur[pi][pj]);
-                nxt[i][j] = fma(ca[i], u, cb[i] * v);
-            }
-            for (int e = t; e < EB * EP; e += ET) { // columns p, q of Q, in place (one thread owns both entries of a row)
-                const int k = e >> 5, i = e & 31;
-                const int p = pr[k][0], q = pr[k][1];
-                const double c = ca[p], s = cb[q];
-                const double xp = Q[i][p], xq = Q[i][q];
-                Q[i][p] = c * xp - s * xq;
-                Q[i][q] = s * xp + c * xq;
+            if (t < EB * EB) {
+                const int kk = t >> 4, mm = t & 15;
+                const int p = pr[kk][0], q = pr[kk][1], r = pr[mm][0], u = pr[mm][1];
+                const double ck = ca[kk], sk = cb[kk], cm = ca[mm], sm = cb[mm];
+                const double w00 = W[p][r], w01 = W[p][u], w10 = W[q][r], w11 = W[q][u];
+                const double a1 = cm * w00 - sm * w01, b1 = sm * w00 + cm * w01, c1 = cm * w10 - sm * w11, d1 = sm * w10 + cm * w11; // columns r, u
+                W[p][r] = ck * a1 - sk * c1; // rows p, q
+                W[q][r] = sk * a1 + ck * c1;
+                W[p][u] = ck * b1 - sk * d1;
+                W[q][u] = sk * b1 + ck * d1;
+            } else {
+                for (int e = t - EB * EB; e < EB * EP; e += ET - EB * EB) { // columns p, q of Q (one thread owns both entries of a row)
+                    const int kk = e >> 5, i = e & 31;
+                    const int p = pr[kk][0], q = pr[kk][1];
+                    const double c = ca[kk], s = cb[kk];
+                    const double xp = Q[i][p], xq = Q[i][q];
+                    Q[i][p] = c * xp - s * xq;
+                    Q[i][q] = s * xp + c * xq;
+                }
             }
             __syncthreads();
-            double(*tmpb)[ELD] = cur;
-            cur = nxt;
-            nxt = tmpb;
         }
     }
     // ---- phase 3: panel <- panel Q for G and V on this CTA's rows; thread = (matrix, half panel, row), 128 rows per pass
