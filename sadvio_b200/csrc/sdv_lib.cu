@@ -251,7 +251,7 @@ struct sdv_handle {
     double *d_lmk_aux = nullptr; // [L][LMK_AUX]: V^-1, g_l, D_l of every eliminated landmark (k_lin_schur -> k_backsub_cost)
     int fused_grid = 0, fused_grid_back = 0;
     std::vector<uint32_t> tmp_tile_nz;
-    bool attrs_done = false;
+    bool attrs_done = false, viinit_attr_done = false;
     const void *lin_fn_cached = nullptr;
     int lin_smem_cached = -1, lin_per_sm = 1;
     int band_bw = -1, band_smem = 0; // 16-column block half-bandwidth of the reduced system (-1 = not computed), k_chol_band shared memory
@@ -2645,10 +2645,9 @@ int sdv_viinit(sdv_handle *h, const sdv_window *w, int32_t optim_scale, sdv_viin
     a.Jw = at<double>(d, s_Jw); a.rw = at<double>(d, s_rw); a.A = at<double>(d, s_A); a.vecs = at<double>(d, s_vec);
     a.out = at<double>(d, o_out); a.st = at<LMState>(d, o_st); a.acc = at<Accum>(d, o_acc);
     a.opt = h->opt;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->viinit_attr_done) { // (per handle: the attribute belongs to the device the handle is bound to)
         CK(cudaFuncSetAttribute(k_viinit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        h->viinit_attr_done = true;
     }
     k_viinit<<<1, VI_THREADS, a.a_in_smem ? a_bytes : 0, s>>>(a);
     h->launches++;

@@ -170,6 +170,17 @@ def test_viinit_fifty_keyframes_matches_oracle(solver):
 
 
 @pytest.mark.gpu
+def test_viinit_sixty_keyframes_normal_equations_in_global_memory(solver):
+    # n = 3 * 60 + 3 = 183 > 158: the normal equations no longer fit the 200 KB of shared memory, the kernel works in its global scratch
+    win = synth.make_window(synth.SynthConfig("vi60", 60, 600, span=4, seed=20260925 + 160))
+    w = rotated_scaled(win, np.array([0.05, -0.1, 0.0]), 0.9)
+    rc, res, st = solver.viinit(w, True)
+    rc0, res0, st0 = orc.viinit(w, True)
+    assert rc == rc0 == 0 and st["n_reduced"] == 183
+    _assert_same(res, st, res0, st0)
+
+
+@pytest.mark.gpu
 def test_viinit_through_the_optimizer_mirror(solver):
     win, gt = rf.euroc_viinit_window()
     opt = api.B200Optimizer.__new__(api.B200Optimizer)
