@@ -229,15 +229,21 @@ struct sdv_handle {
     int64_t graph_launches_fixed = 0, graph_launches_iter = 0, graph_builds = 0;
     // k LM iterations per trip of the WHILE node (a trip costs ~6 us on B200; every kernel returns at once after termination, so a
     // trip that is cut short only launches a few empty kernels): k = the largest divisor <= 4 of the PREVIOUS solve's iteration count —
-    // consecutive windows of a running back end take the same number of iterations.  One instantiated graph per k in use is kept.
+    // consecutive windows of a running back end take the same number of iterations.  Instantiated graphs that fall out of use are
+    // parked (keyed by signature + k, least recently used evicted): a handle that alternates between kinds of solves — the front-end
+    // optimizer instance runs landmarkOptimization and the single-frame solves in turn — or between iteration counts replays them.
     int graph_unroll = 1;
+    static constexpr int GRAPH_CACHE = 8;
     struct GraphSlot {
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t gexec = nullptr;
         unsigned long long cond = 0;
         GraphSig sig;
+        int unroll = 0;
         int64_t l_fixed = 0, l_iter = 0;
-    } gcache[5];
+        uint64_t last_use = 0;
+    } gcache[GRAPH_CACHE];
+    uint64_t graph_clock = 0;
     unsigned char *h_sol = nullptr;
     size_t sol_cap = 0;
     // comm
@@ -2205,23 +2211,29 @@ int build_solve_graph(sdv_handle *h) {
     }
     const int unroll = desired_unroll(h);
     if (h->graph_ok && h->graph_unroll == unroll && std::memcmp(&h->graph_sig, &sig, sizeof(sig)) == 0) return SDV_OK; // same launches, same arguments: replay
-    if (h->graph_ok) { // park the active graph under its unroll factor ...
-        sdv_handle::GraphSlot &c = h->gcache[h->graph_unroll];
-        if (c.gexec) cudaGraphExecDestroy(c.gexec);
-        if (c.graph) cudaGraphDestroy(c.graph);
-        c.graph = h->graph; c.gexec = h->gexec; c.cond = h->cond; c.sig = h->graph_sig; c.l_fixed = h->graph_launches_fixed; c.l_iter = h->graph_launches_iter;
+    if (h->graph_ok) { // park the active graph (least recently used slot) ...
+        sdv_handle::GraphSlot *c = &h->gcache[0];
+        for (auto &q : h->gcache) {
+            if (!q.gexec) {
+                c = &q;
+                break;
+            }
+            if (q.last_use < c->last_use) c = &q;
+        }
+        if (c->gexec) cudaGraphExecDestroy(c->gexec);
+        if (c->graph) cudaGraphDestroy(c->graph);
+        c->graph = h->graph; c->gexec = h->gexec; c->cond = h->cond; c->sig = h->graph_sig; c->unroll = h->graph_unroll;
+        c->l_fixed = h->graph_launches_fixed; c->l_iter = h->graph_launches_iter; c->last_use = ++h->graph_clock;
         h->graph = nullptr; h->gexec = nullptr; h->graph_ok = false; h->cond = 0;
     }
-    {   // ... and look for a parked one that fits
-        sdv_handle::GraphSlot &c = h->gcache[unroll];
-        if (c.gexec && std::memcmp(&c.sig, &sig, sizeof(sig)) == 0) {
+    for (auto &c : h->gcache) // ... and look for a parked one that fits
+        if (c.gexec && c.unroll == unroll && std::memcmp(&c.sig, &sig, sizeof(sig)) == 0) {
             h->graph = c.graph; h->gexec = c.gexec; h->cond = c.cond; h->graph_sig = c.sig; h->graph_launches_fixed = c.l_fixed; h->graph_launches_iter = c.l_iter;
             h->graph_unroll = unroll;
             h->graph_ok = true;
             c = sdv_handle::GraphSlot();
             return SDV_OK;
         }
-    }
     destroy_active_graph(h);
     if (!h->stream2 && cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) return SDV_OK;
     cudaStream_t s = h->stream;

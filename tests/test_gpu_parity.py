@@ -568,6 +568,29 @@ def test_one_cuda_graph_serves_consecutive_windows():
     s.close()
 
 
+def test_alternating_kinds_of_solves_replay_parked_graphs():
+    """The front-end optimizer instance runs landmarkOptimization and the single-frame solves in turn on ONE handle: every kind has
+    its own launch signature, and the graphs that fall out of use are parked instead of destroyed — after the first round no solve
+    captures or instantiates anything, and every solve still matches the oracle."""
+    s = api.Solver()
+    base = synth.make_window("small")
+    kinds = [lambda: api.landmark_window(synth.make_window("small"), 3)[0], lambda: api.single_frame_window(synth.make_window("small"), 0, False)[0],
+             lambda: api.single_frame_window(synth.make_window("small"), 0, True)[0], lambda: synth.make_window("small")]
+    builds = []
+    for rnd in range(3):
+        for mk in kinds:
+            win = mk()
+            g = s.solve_window(win)
+            o = orc.solve_window(win, mode=0, nthreads=4)
+            assert g[2]["iterations"] == o[2]["iterations"] and g[2]["termination"] == o[2]["termination"]
+            assert np.abs(g[1].dpose - o[1].dpose).max() <= 1e-6 * max(np.abs(o[1].dpose).max(), 1e-12)
+        builds.append(s.graph_builds())
+    assert builds[2] == builds[1], builds          # (round 1 may still add the graphs of the iteration counts it learned in round 0)
+    assert builds[1] <= 2 * len(kinds), builds
+    del base
+    s.close()
+
+
 def test_parallel_host_structure_pass_matches_the_serial_one():
     """Windows with >= 16384 observations build their slot lists on four host threads (observation list cut at landmark
     boundaries); SDV_NO_HOST_POOL=1 forces the serial pass.  Same LM trace and solution, also when a keyframe re-appears
