@@ -30,6 +30,17 @@ def main():
                             trace_cost=np.asarray(st["trace_cost"]), trace_accepted=np.asarray(st["trace_accepted"]),
                             obs_lmk=win.obs_lmk, obs_frame=win.obs_frame, obs_cam=win.obs_cam)
         print(name, "iterations", st["iterations"], "final cost", st["final_cost"])
+    # AOptimizer::VIInit on the reference's own initialisation fixture (imu_test.cpp:813-880, tests/ref_fixtures.py: 10 EuRoC keyframes
+    # shrunk by 0.5): the oracle's parameter blocks and LM trace
+    from tests import ref_fixtures as rf
+
+    win, _ = rf.euroc_viinit_window()
+    rc, res, st = oracle.viinit(win, True)
+    assert rc == 0
+    np.savez_compressed(os.path.join(here, "viinit_euroc.npz"), dv=res["dv"], r_wi=res["r_wi"], lam=res["lam"], scale=res["scale"],
+                        iterations=st["iterations"], termination=st["termination"], trace_cost=np.asarray(st["trace_cost"]),
+                        trace_accepted=np.asarray(st["trace_accepted"]))
+    print("viinit_euroc iterations", st["iterations"], "scale", res["scale"])
 
 
 if __name__ == "__main__":

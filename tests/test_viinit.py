@@ -88,6 +88,23 @@ def test_oracle_viinit_reference_euroc_run():
     rf.check_euroc_viinit(win, gt)
 
 
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "viinit_euroc.npz"))
+
+
+def test_oracle_viinit_matches_the_committed_golden():
+    """tests/golden/viinit_euroc.npz (tests/golden/make_golden.py) pins the oracle's VIInit against drift."""
+    g = _golden()
+    win, _ = rf.euroc_viinit_window()
+    rc, res, st = orc.viinit(win, True)
+    assert rc == 0 and st["iterations"] == int(g["iterations"]) and st["termination"] == str(g["termination"])
+    n = st["iterations"] + 1
+    assert np.allclose(st["trace_cost"][:n], g["trace_cost"][:n], rtol=1e-10) and np.array_equal(np.asarray(st["trace_accepted"][:n]), g["trace_accepted"][:n])
+    assert np.abs(res["dv"] - g["dv"]).max() <= 1e-9 * np.abs(g["dv"]).max() and abs(res["lam"] - float(g["lam"])) <= 1e-9
+    assert np.abs(res["r_wi"] - g["r_wi"]).max() <= 1e-9 * max(np.abs(g["r_wi"]).max(), 1e-6)
+
+
 def test_oracle_viinit_recovers_gravity_direction_with_fixed_scale():
     win, _ = rf.euroc_viinit_window(scale_factor=1.0)
     rot = np.array([0.12, -0.2, 0.0])
@@ -143,6 +160,21 @@ def test_viinit_reference_euroc_run_on_the_gpu(solver):
     assert st["kernel_launches"] == 2 and st["n_reduced"] == 3 * win.n_frames + 3
     api.viinit_write_back(win, res)
     rf.check_euroc_viinit(win, gt)                                # imu_test.cpp:873-878
+
+
+@pytest.mark.gpu
+def test_viinit_matches_the_committed_golden(solver):
+    """sdv_viinit against tests/golden/viinit_euroc.npz: same 47-step trace, parameter blocks within 1e-6 relative."""
+    g = _golden()
+    win, _ = rf.euroc_viinit_window()
+    rc, res, st = solver.viinit(win, True)
+    assert rc == 0 and st["iterations"] == int(g["iterations"]) and st["termination"] == str(g["termination"])
+    n = st["iterations"] + 1
+    assert np.array_equal(np.asarray(st["trace_accepted"][:n]), g["trace_accepted"][:n])
+    assert np.allclose(st["trace_cost"][:n], g["trace_cost"][:n], rtol=1e-7, atol=1e-12)
+    assert np.abs(res["dv"] - g["dv"]).max() <= 1e-6 * np.abs(g["dv"]).max()
+    assert abs(res["lam"] - float(g["lam"])) <= 1e-6 * abs(float(g["lam"])) and abs(res["scale"] - float(g["scale"])) <= 1e-6 * float(g["scale"])
+    assert np.abs(res["r_wi"] - g["r_wi"]).max() <= 1e-6 * max(np.abs(g["r_wi"]).max(), 1e-9) + 1e-12
 
 
 @pytest.mark.gpu
