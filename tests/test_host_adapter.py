@@ -626,3 +626,20 @@ def test_adapter_viinit_matches_python_binding(adapter_exe, optim_scale):
         f = F - 1 - k
         assert np.abs(row[:12] - ref.T_f_w[f]).max() < 1e-9 and np.abs(row[12:15] - ref.v[f]).max() < 1e-9
     assert np.abs(lm - ref.lmk_t).max() < 1e-9
+
+
+def test_viinit_needs_an_imu_on_every_frame_and_ignores_previous_keyframes_outside_the_map(adapter_exe):
+    """AOptimizer.cpp:487 dereferences getIMU() of every frame of the map (no solve without it: the adapter reports that instead of
+    crashing), and a frame whose getLastKF() is not in the map gets no IMUFactorInit (:489)."""
+    win = synth.make_window("small", vio=False)
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), False)
+    out = subprocess.run([adapter_exe, "dump_viinit", "1", "0"], input=txt, capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[:2] == ["dump_viinit", "ok 0"]
+    win = synth.make_window("small")
+    txt, _, _, _ = graph_text(win, np.random.default_rng(0), True)          # file frames 0, 1 are older frames that left the map
+    lines = txt.split("\n")
+    k = next(i for i, ln in enumerate(lines) if ln.endswith(" -1") and len(ln.split()) > 100)   # the oldest window frame's IMU line
+    lines[k] = lines[k][:-2] + "0"                                         # ... now names file frame 0 as its previous keyframe
+    got = parse_dump(subprocess.run([adapter_exe, "dump_viinit", "1", "0"], input="\n".join(lines), capture_output=True, text=True, check=True).stdout)
+    assert got.n_frames == win.n_frames and got.n_imu == win.n_imu and got.n_obs == 0
+    assert np.array_equal(got.imu_i, win.imu_i) and np.array_equal(got.imu_j, win.imu_j)
