@@ -44,6 +44,9 @@ def test_ctypes_mirror_matches_c_layout():
       printf("%zu %zu %zu\n", offsetof(sdv_stats, trace_accepted), offsetof(sdv_stats, kernel_launches),
              offsetof(sdv_sparse_prior, l2l_sqrt_inf));
       printf("%zu %zu %zu %zu\n", sizeof(sdv_imu_intervals), sizeof(sdv_preint), offsetof(sdv_imu_intervals, eta), offsetof(sdv_imu_intervals, rate_hz));
+      printf("%zu %zu %zu %zu %zu\n", sizeof(sdv_viinit_result), offsetof(sdv_viinit_result, r_wi), offsetof(sdv_viinit_result, lambda),
+             offsetof(sdv_viinit_result, R_w_i), offsetof(sdv_viinit_result, scale));
+      printf("%zu %zu %zu %zu\n", sizeof(sdv_marginal_sizes), sizeof(sdv_marginal), offsetof(sdv_marginal, lmk_sqrt_inf), offsetof(sdv_marginal, l2l_delta));
       return 0; }
     """
     with tempfile.TemporaryDirectory() as td:
@@ -57,7 +60,10 @@ def test_ctypes_mirror_matches_c_layout():
             C.sizeof(abi.SdvDelta), C.sizeof(abi.SdvStats),
             abi.SdvWindow.T_f_w.offset, abi.SdvWindow.obs_lmk.offset, abi.SdvWindow.imu_cov.offset, abi.SdvWindow.sparse_prior.offset,
             abi.SdvStats.trace_accepted.offset, abi.SdvStats.kernel_launches.offset, abi.SdvSparsePrior.l2l_sqrt_inf.offset,
-            C.sizeof(abi.SdvImuIntervals), C.sizeof(abi.SdvPreint), abi.SdvImuIntervals.eta.offset, abi.SdvImuIntervals.rate_hz.offset]
+            C.sizeof(abi.SdvImuIntervals), C.sizeof(abi.SdvPreint), abi.SdvImuIntervals.eta.offset, abi.SdvImuIntervals.rate_hz.offset,
+            C.sizeof(abi.SdvViinitResult), abi.SdvViinitResult.r_wi.offset, abi.SdvViinitResult.lambda_.offset, abi.SdvViinitResult.R_w_i.offset,
+            abi.SdvViinitResult.scale.offset,
+            C.sizeof(abi.SdvMarginalSizes), C.sizeof(abi.SdvMarginal), abi.SdvMarginal.lmk_sqrt_inf.offset, abi.SdvMarginal.l2l_delta.offset]
     assert got == want
 
 
