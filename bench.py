@@ -336,6 +336,9 @@ def main():
     e2e = {"value": e_its / e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e_steps), "d2h_bytes_per_step": int(d2h / e_steps),
            "ms_per_step": 1e3 * e_t / e_steps, "windows_cycled": [{"n_lmks": int(w.n_lmks), "n_obs": int(w.n_obs)} for w in wins],
            "cuda_graph_builds_in_arm": int(solver.graph_builds() - builds0)}
+    if world > 1:
+        e2e["note"] = ("N > 1: every rank validates and uploads the WHOLE window from its own host copy before its landmark shard is solved "
+                       "(max over ranks of the host-timed call): the call gets slower with N although the resident solve does not (DESIGN.md section 9.5)")
 
     # ---------------- BASELINE config 5 (200 KF x 100k landmarks x 800k obs): the window where sharding landmarks can pay
     c5 = None
