@@ -201,14 +201,15 @@ def imu_init_eval(T_i, T_j, v_i, v_j, dt, pre, params=None, jac=True):
     return r, J.reshape(9, 15)
 
 
-def viinit(win: abi.Window, optim_scale: bool = True, cfg: abi.SdvConfig | None = None):
+def viinit(win: abi.Window, optim_scale: bool = True, cfg: abi.SdvConfig | None = None, all_blocks_free: bool = False):
     """The solve of AOptimizer::VIInit (AOptimizer.cpp:448-529) over the frames / IMU pairs of `win`.
-    Returns rc, dict(dv[F][3], r_wi[2], lam, R_w_i, scale), stats."""
+    Returns rc, dict(dv[F][3], r_wi[2], lam, R_w_i, scale), stats.  all_blocks_free: the shared dba / dbg blocks are parameters too
+    (the reference's own test of the functor, imu_test.cpp:498-541; VIInit itself sets them constant)."""
     cfg = cfg or default_config()
     ws = win.as_struct()
     dv, extra = np.zeros((win.n_frames, 3)), np.zeros(3)
     st = abi.SdvStats()
-    rc = lib().orc_viinit(C.byref(ws), C.byref(cfg), int(bool(optim_scale)), _p(dv), _p(extra), C.byref(st))
+    rc = lib().orc_viinit(C.byref(ws), C.byref(cfg), 2 if all_blocks_free else int(bool(optim_scale)), _p(dv), _p(extra), C.byref(st))
     return rc, dict(dv=dv, r_wi=extra[:2].copy(), lam=float(extra[2]), R_w_i=exp_so3([extra[0], extra[1], 0.0]),
                     scale=float(np.exp(extra[2]))), abi.stats_to_dict(st)
 

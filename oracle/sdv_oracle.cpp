@@ -71,7 +71,8 @@ struct Problem {
     int ba_id(int f) const { return 2 * F + f; }
     int bg_id(int f) const { return 3 * F + f; }
     int lmk_id(int l) const { return 4 * F + l; }
-    // AOptimizer::VIInit (AOptimizer.cpp:448-581): 0 = a window solve, 1 = VIInit with the scale constant, 2 = scale free
+    // AOptimizer::VIInit (AOptimizer.cpp:448-581): 0 = a window solve, 1 = VIInit with the scale constant, 2 = scale free,
+    // 3 = every block of the functor free incl. the shared dba / dbg (the reference's own functor test, imu_test.cpp:498-541)
     int viinit = 0;
     int rwi_id() const { return 4 * F + L; }     // r_wi_par, size 2 (:467-468)
     int lam_id() const { return 4 * F + L + 1; } // lambda, size 1 (:480-483)
@@ -238,7 +239,7 @@ static bool build_problem_viinit(const sdv_window *w, Problem &P) {
         P.pbs[P.pose_id(f)].constant = true; // poses are not parameters of VIInit
         for (int k = 1; k <= 3; k++) {
             P.pbs[k * F + f].size = 3;
-            P.pbs[k * F + f].constant = k != 1;
+            P.pbs[k * F + f].constant = k != 1 && !(P.viinit == 3 && f == 0); // (mode 3: blocks ba_id(0) / bg_id(0) stand for the shared dba / dbg)
         }
     }
     for (int l = 0; l < L; l++) {
@@ -247,7 +248,7 @@ static bool build_problem_viinit(const sdv_window *w, Problem &P) {
     }
     P.pbs[P.rwi_id()].size = 2;
     P.pbs[P.lam_id()].size = 1;
-    P.pbs[P.lam_id()].constant = P.viinit != 2;
+    P.pbs[P.lam_id()].constant = P.viinit == 1;
     int off = 0;
     for (auto &p : P.pbs) {
         p.off = off;
@@ -260,8 +261,9 @@ static bool build_problem_viinit(const sdv_window *w, Problem &P) {
         r.kind = K_IMU_INIT;
         r.idx = p;
         r.nres = 9;
-        r.pb = {P.rwi_id(), P.vel_id(w->imu_i[p]), P.vel_id(w->imu_j[p]), P.lam_id()};
-        r.npb = 4;
+        if (P.viinit == 3) r.pb = {P.rwi_id(), P.vel_id(w->imu_i[p]), P.vel_id(w->imu_j[p]), P.ba_id(0), P.bg_id(0), P.lam_id()};
+        else r.pb = {P.rwi_id(), P.vel_id(w->imu_i[p]), P.vel_id(w->imu_j[p]), P.lam_id()};
+        r.npb = (int)r.pb.size();
         P.rbs.push_back(r);
         if (!ImuFactor::InfSqrt(Mat<9, 9>::From(w->imu_cov + 81 * p), P.imu_inf_sqrt[p])) return false;
     }
@@ -360,6 +362,7 @@ static bool eval_block(const Problem &P, const RBlock &rb, const double *x, doub
         e.J_dv_bg = M3::From(w->imu_J_dv_bg + 9 * p);
         e.J_dp_ba = M3::From(w->imu_J_dp_ba + 9 * p);
         e.J_dp_bg = M3::From(w->imu_J_dp_bg + 9 * p);
+        if (rb.npb == 6) return e.Evaluate(pp, res, J); // every block a parameter (imu_test.cpp:498-541)
         // the shared dba / dbg blocks are constant at zero: Ceres passes their values and a NULL Jacobian pointer
         static const double zero3[3] = {0, 0, 0};
         const double *p6[6] = {pp[0], pp[1], pp[2], zero3, zero3, pp[3]};
@@ -1183,7 +1186,7 @@ int orc_viinit(const sdv_window *w, const sdv_config *cfg, int optim_scale, doub
     d.dba = dba.data();
     d.dbg = dbg.data();
     d.dlmk = dl.data();
-    int rc = solve_lm(&ww, cfg, &d, st, 1, 1, nullptr, nullptr, optim_scale ? 2 : 1, extra);
+    int rc = solve_lm(&ww, cfg, &d, st, 1, 1, nullptr, nullptr, optim_scale == 2 ? 3 : (optim_scale ? 2 : 1), extra); // optim_scale = 2: every block free
     st->ms_total_host = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
 }

@@ -75,6 +75,24 @@ def test_imu_init_factor_scale_jacobian_omits_exp_lambda():
     assert np.abs(J[:, 14] - num).max() > 0.1 * np.abs(num).max()
 
 
+def test_reference_imu_factor_init_solve():
+    """imu_test.cpp:489-541: after the free-fall inertial optimisation both poses are shrunk by 0.5 and ONE IMUFactorInit with all six
+    parameter blocks free (gravity direction, both velocities, dba, dbg, log-scale) is solved with Ceres' defaults (50 iterations):
+    the recovered scale must undo the shrinking, |0.5 - 1 / exp(lambda)| < 1e-2."""
+    win = rf.free_fall_window()
+    rc, d, st = orc.solve_window(win)                            # :473-483 (checked by tests/test_oracle_solver.py)
+    assert rc == 0
+    api.write_back(win, d, True)
+    for f in range(2):                                           # :490-496
+        T = win.T_f_w[f].reshape(3, 4).copy()
+        T[:, 3] *= 0.5
+        win.T_f_w[f] = T.reshape(12)
+    win.max_num_iterations = 50                                  # ceres::Solver::Options default
+    rc, res, st = orc.viinit(win, True, all_blocks_free=True)
+    assert rc == 0 and st["final_cost"] < 1e-3 * st["initial_cost"]
+    assert abs(0.5 - 1.0 / np.exp(res["lam"])) < 1e-2            # :541
+
+
 def test_oracle_viinit_reference_euroc_run():
     """imu_test.cpp:813-880 through the oracle + the host write-back (AOptimizer.cpp:531-567)."""
     win, gt = rf.euroc_viinit_window()
