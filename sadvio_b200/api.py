@@ -484,7 +484,10 @@ class B200Optimizer:
     def VIInit(self, local_map: abi.Window, optim_scale: bool = False):  # noqa: N802
         """AOptimizer::VIInit(local_map, R_w_i, optim_scale) (AOptimizer.cpp:448-581): returns (exp(lambda), R_w_i) and updates
         the map in place.  `local_map.imu_*` must list every (getLastKF(), frame) pair — VIInit has no dt test (:485-502)."""
-        rc, res, st = self.solver.viinit(local_map, optim_scale)
+        try:
+            rc, res, st = self.solver.viinit(local_map, optim_scale)
+        except RuntimeError:
+            return float("nan"), None   # no solve ran (malformed input, CUDA error): state untouched, like the C++ adapter
         self.last_stats = st
         viinit_write_back(local_map, res)   # the reference ignores the summary here too
         return res["scale"], res["R_w_i"]
